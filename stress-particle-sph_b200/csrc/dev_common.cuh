@@ -1,0 +1,261 @@
+// Device-side common definitions for the Stress-Particle SPH step engine (sm_100a).
+//
+// Arithmetic contract: this translation unit is compiled with -fmad=false, so every a*b+c below is two
+// IEEE roundings exactly as written (the reference is built without FMA contraction);
+// fp64/fp32 division and sqrt are nvcc's IEEE-compliant defaults (-prec-div/-prec-sqrt true, -ftz false).
+// Explicit __fma_rn() calls are used only inside exactly-rounded division helpers.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace spsph {
+
+enum : int { SP_NODE = 0, SP_STRESS = 1, SP_DUMMY = 2 };
+
+// Scalars the kernels need; passed by value as a kernel parameter (one simulation == one copy).
+struct DevParams {
+  int nnode, nstress, ntotal, ntotal2, ndummy, npoints;
+  int skf, scale_k, cspm, update_x, xsph, ncrit, ntype_eco, ntype_solid;
+  int no_bcs, bc_nloop;  // bc_nloop: Normal_BCs loop bound (ntotal or nnode), mat:1683
+  int sp_sph, inside_approach, vel_vector, shift_update;
+  int adapt;  // ncrit == 12
+  double pi, D11, D12, D22, D33, D41, D42;
+  double alpha, beta, damping, dx, r_x, r_y, disp_tol, ae_thr;
+  double props[20];
+  double xmin_dom[2], xmax_dom[2];
+  // Drucker-Prager constants of adapt_stress2 (fp64, mat:2096-2100), computed once on the host with the
+  // same expressions (sqrt and division are correctly rounded on both sides)
+  double dp_alpha2, dp_kc;
+  // per step (host-computed: time curves, exp/sin of Normal_BCs and gravity factor involve libm)
+  int itimestep;
+  double time_sph, dt;
+  double grav[2];      // factg*ft_grav*cgrav(:), mat:2688-2711
+  double bcval[16];    // bc_value per BC id at t_actual, mat:1696-1722
+  int bcvar[16];       // bc_list(2, id)
+};
+
+// Cell grid of one step (grid_find_NEW Task 1, main:1245-1258); lives in device memory, written by
+// k_grid_params, read by every neighbour kernel.
+struct GridInfo {
+  double xmin[2], xmax[2], deltx[2];
+  int ndivx[2];
+  int ncell;
+  int overflow;  // 1 if ncell exceeds the allocated cell capacity
+  // raw reductions
+  double rxmin[2], rxmax[2], rhmax;
+  int nactive[3];  // in-domain particles per species
+};
+
+struct StepStatus {  // copied to pinned host memory after the count pass
+  long long n_pairs;
+  long long tot0, totC, totD;  // list storage needed (entries incl. slice padding)
+  int ncell, overflow, err;
+  int pad;
+};
+
+__device__ __forceinline__ double2 ld2(const double *p, int i) { return reinterpret_cast<const double2 *>(p)[i]; }
+__device__ __forceinline__ void st2(double *p, int i, double2 v) { reinterpret_cast<double2 *>(p)[i] = v; }
+
+struct Stress4 {
+  double s1, s2, s3, s4;
+};
+__device__ __forceinline__ Stress4 ld4(const double *p, int i) {
+  const double2 a = reinterpret_cast<const double2 *>(p)[2 * i];
+  const double2 b = reinterpret_cast<const double2 *>(p)[2 * i + 1];
+  return Stress4{a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ void st4(double *p, int i, const Stress4 &s) {
+  reinterpret_cast<double2 *>(p)[2 * i] = make_double2(s.s1, s.s2);
+  reinterpret_cast<double2 *>(p)[2 * i + 1] = make_double2(s.s3, s.s4);
+}
+
+// ---- smoothing kernel, main:1440-1538 (skf = 1, ndimn = 2); fp64 evaluation, caller rounds to fp32 ----
+// dx,dy = x(pair_i) - x(pair_j); r = sqrt(dx*dx + dy*dy) as computed by the neighbour search.
+__device__ __forceinline__ void sph_kernel(const DevParams &P, double r, double dx, double dy, double h, double &w,
+                                           double &gx, double &gy) {
+  const double q = r / h;
+  w = 0.;
+  gx = 0.;
+  gy = 0.;
+  const double factor = 15.e0 / (7.e0 * P.pi * h * h);
+  if (q >= 0 && q <= 1.e0) {
+    w = factor * ((double)(2.f / 3.f) - q * q + q * q * q / 2.);
+    const double t = factor * (-2. + 1.5 * q) / (h * h);
+    gx = t * dx;
+    gy = t * dy;
+  } else if (q > 1.e0 && q <= 2) {
+    const double t = 2. - q;
+    w = factor * 1.e0 / 6.e0 * (t * t * t);
+    const double u = -factor * 1.e0 / 6.e0 * 3. * (t * t) / h;
+    gx = u * (dx / r);
+    gy = u * (dy / r);
+  }
+}
+
+// ---- adapt_stress2 body for one particle, mat:2087-2161 (fp64) ----
+__device__ __forceinline__ void adapt_stress(const DevParams &P, Stress4 &s) {
+  const double alpha2 = P.dp_alpha2, kc = P.dp_kc;
+  double smean = (s.s1 + s.s2 + s.s4) / 3.0;
+  double d1 = s.s1 - smean, d2 = s.s2 - smean, d3 = s.s3, d4 = s.s4 - smean;
+  double varj2 = d3 * d3 + 0.5 * (d1 * d1 + d2 * d2 + d4 * d4);
+  double yield = -alpha2 * 3 * smean + kc;
+  if (yield < 0) {
+    const double sh = kc / (3 * alpha2);
+    s.s1 = s.s1 - smean + sh;
+    s.s2 = s.s2 - smean + sh;
+    s.s4 = s.s4 - smean + sh;
+    smean = (s.s1 + s.s2 + s.s4) / 3.0;
+    d1 = s.s1 - smean;
+    d2 = s.s2 - smean;
+    d3 = s.s3;
+    d4 = s.s4 - smean;
+    varj2 = d3 * d3 + 0.5 * (d1 * d1 + d2 * d2 + d4 * d4);
+    yield = -alpha2 * 3 * smean + kc;
+  }
+  const double sq = sqrt(varj2);
+  if (yield < sq) {
+    double rn = (-3 * alpha2 * smean + kc) / sq;
+    if (sq <= (double)10e-06f) rn = 0;
+    s.s1 = rn * d1 + smean;
+    s.s2 = rn * d2 + smean;
+    s.s4 = rn * d4 + smean;
+    s.s3 = rn * d3;
+  }
+}
+
+// ---- Normal_BCs for one particle, mat:1665-1770 ----
+__device__ __forceinline__ void apply_bcs(const DevParams &P, const int *__restrict__ bc_or_not,
+                                          const int *__restrict__ bc_info, int ip, double2 &v, Stress4 &s) {
+  if (P.no_bcs <= 0 || ip >= P.bc_nloop) return;
+  if (bc_or_not[ip] != 1) return;
+  const int *bi = bc_info + 8 * (size_t)ip;
+  if (bi[1] == 0) return;
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    const int t = bi[2 + i];
+    if (t == 0) continue;
+    const double val = P.bcval[t - 1];
+    const int var = P.bcvar[t - 1];
+    if (var == 5)
+      v.x = val;
+    else if (var == 6)
+      v.y = val;
+    else if (var == 1)
+      s.s1 = val;
+    else if (var == 3)
+      s.s3 = val;
+    else if (var == 2)
+      s.s2 = val;
+  }
+}
+
+// ---- drucker_prager, mat:1958-2083: fp32 locals; returns G (= -Gs) and vivel ----
+__device__ __forceinline__ void drucker_prager(const DevParams &P, const Stress4 &st, double g11, double g12, double g21,
+                                               double g22, double &f_drucker, double G[4], double vivel[4]) {
+  const double f0 = f_drucker;
+  const float tanfi = (float)P.props[12], coh = (float)P.props[13];
+  const float young = (float)P.props[2], poiss = (float)P.props[3];
+  const float smean = (float)((st.s1 + st.s2 + st.s4) / 3.0);
+  const float d1 = (float)(st.s1 - (double)smean);
+  const float d2 = (float)(st.s2 - (double)smean);
+  const float d3 = (float)st.s3;
+  const float d4 = (float)(st.s4 - (double)smean);
+  const float varj2 = d3 * d3 + 0.5f * (d1 * d1 + d2 * d2 + d4 * d4);
+  const float vari1 = 3 * smean;
+  const float eps11 = (float)g11;
+  const float eps12 = (float)(0.5 * (g12 + g21));
+  const float eps22 = (float)g22;
+  const float emean = eps11 + eps22;
+  const float alpha2 = tanfi / (sqrtf(9 + 12 * (tanfi * tanfi)));
+  const float kc = (3 * coh) / (sqrtf(9 + 12 * (tanfi * tanfi)));
+  const float yield = -alpha2 * vari1 + kc;
+  const float sq = sqrtf(varj2);
+  const float f1 = sq - yield;
+  f_drucker = (double)f1;
+  const double df = (double)f1 - f0;
+  const float G_mod = young / (2.f * (1.f + poiss));
+  const float K_mod = young / (3.f * (1.f - 2.f * poiss));
+  const float s_eps = d1 * eps11 + 2 * d3 * eps12 + d2 * eps22;
+  if (P.time_sph > 0 && f1 >= 0 && df >= 0 && sq >= 10e-06f) {
+    const float gq = G_mod / sq;
+    const float lambda_1 = 3 * alpha2 * K_mod * emean;
+    const float lambda_2 = gq * s_eps;
+    const float G2 = (lambda_1 + lambda_2) / G_mod;
+    G[0] = (double)((gq * d1) * G2);
+    G[1] = (double)((gq * d2) * G2);
+    G[2] = (double)((gq * d3) * G2);
+    G[3] = (double)((gq * d4) * G2);
+    const float is = 1.f / sq;
+    const float c6 = 1.f / 6.f;
+    vivel[0] = (double)((c6 * is) * (2 * d1 - d2 - d4)) * (double)G2;
+    vivel[1] = (double)((c6 * is) * (2 * d2 - d1 - d4)) * (double)G2;
+    vivel[2] = (double)(is * d3) * (double)G2;
+    vivel[3] = (double)((c6 * is) * (2 * d4 - d1 - d2)) * (double)G2;
+  } else {
+    G[0] = G[1] = G[2] = G[3] = 0.0;
+    vivel[0] = vivel[1] = vivel[2] = vivel[3] = 0.0;
+  }
+}
+
+// ---- Get_Vivel (von Mises branch, ncrit = 2) + Get_Dmatx: strain_localisation copy :2169-2576, fp64 ----
+// Returns Gs = -De * vivel and vivel. The trigonometric terms of invar09/yieldf09 only feed cons1..3 of
+// the other criteria and are not evaluated.
+__device__ __forceinline__ void von_mises_perzyna(const DevParams &P, const Stress4 &st, double evpstn, double Gs[4],
+                                                  double vivel[4]) {
+  const double root3 = (double)1.7320507764816284f;  // sqrt(3.00) in default REAL
+  const double smean = (st.s1 + st.s2 + st.s4) / 3.0;
+  double devia[4];
+  devia[0] = st.s1 - smean;
+  devia[1] = st.s2 - smean;
+  devia[2] = st.s3;
+  devia[3] = st.s4 - smean;
+  const double varj2 = devia[2] * devia[2] + 0.5 * (devia[0] * devia[0] + devia[1] * devia[1] + devia[3] * devia[3]);
+  const double steff = sqrt(varj2);
+  const double yield = root3 * steff;
+  const double fdatm0 = P.props[6], hards = P.props[7];
+  double fdatm = fdatm0 + hards * evpstn;
+  double fact = fabs(fdatm) / fabs(fdatm0);
+  if (fact < (double)0.1f) fact = (double)0.1f;
+  fdatm = fdatm0 * fact;
+  vivel[0] = vivel[1] = vivel[2] = vivel[3] = 0.0;
+  if (yield > fdatm) {
+    double veca2[4] = {0, 0, 0, 0}, veca3[4];
+    if (steff > 0) {
+      for (int s = 0; s < 4; ++s) veca2[s] = devia[s] / (2.0 * steff);
+      veca2[2] = devia[2] / steff;
+    }
+    veca3[0] = devia[1] * devia[3] + varj2 / 3.0;
+    veca3[1] = devia[0] * devia[3] + varj2 / 3.0;
+    veca3[2] = -2.0 * devia[2] * devia[3];
+    veca3[3] = devia[0] * devia[1] - devia[2] * devia[2] + varj2 / 3.0;
+    const double veca1[4] = {1.0, 1.0, 0.0, 1.0};
+    const double cons1 = 0.0, cons2 = root3, cons3 = 0.0;
+    double avect[4];
+    for (int s = 0; s < 4; ++s) avect[s] = cons1 * veca1[s] + cons2 * veca2[s] + cons3 * veca3[s];
+    const double allow = (double)0.01f;
+    const double gamma = P.props[9], delta = P.props[10], nflow = P.props[11];
+    const double fcurr = yield - fdatm;
+    const double fnorm = fcurr / fdatm;
+    if (fnorm >= allow) {
+      double cmult;
+      if (nflow != 1)
+        cmult = gamma * (exp(delta * fnorm) - 1.0);
+      else
+        cmult = gamma * ((delta == 1.0) ? fnorm : pow(fnorm, delta));
+      for (int s = 0; s < 4; ++s) vivel[s] = cmult * avect[s];
+    }
+  }
+  const double young = P.props[2], poiss = P.props[3];
+  const double cst = young * (1.0 - poiss) / ((1.0 + poiss) * (1.0 - 2.0 * poiss));
+  const double off = cst * poiss / (1.0 - poiss);
+  const double d33 = (1.0 - 2.0 * poiss) * cst / (2.0 * (1.0 - poiss));
+  // Gs(i) = Gs(i) - Dmatx(i,j)*vivel(j), j = 1..4 in order, zero entries included (mat:1933-1937)
+  const double D[4][4] = {{cst, off, 0.0, off}, {off, cst, 0.0, off}, {0.0, 0.0, d33, 0.0}, {off, off, 0.0, cst}};
+  for (int a = 0; a < 4; ++a) {
+    double g = 0.0;
+    for (int b = 0; b < 4; ++b) g = g - D[a][b] * vivel[b];
+    Gs[a] = g;
+  }
+}
+
+}  // namespace spsph

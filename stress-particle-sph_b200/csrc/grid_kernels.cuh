@@ -1,0 +1,683 @@
+// Neighbour search: cell grid, counting sort of velocity / stress / dummy particles, per-particle ordered
+// neighbour enumeration and the fp32 pair weights (reference: Check_Out_Domain main:1170-1194,
+// grid_find_NEW main:1199-1435, kernel main:1440-1538, Pint_Update mat:1574-1634).
+//
+// Design (not a port of the linked list): the reference's global pair list becomes, per particle, gather
+// lists stored as warp-sliced ELL (32 particles per slice, entry e of lane l at off + 32*e + l) so that one
+// thread per particle walks its own partners in the reference's traversal order with coalesced loads and no
+// atomics in any sum. Restricted to one particle, the reference's creation order is "partners sorted by
+// (cell id, particle index)" (SURVEY.md App. B), which is exactly the order a cell-sorted enumeration
+// produces; the list re-use rule (new list nodes prepended => visited first, reversed) is applied when the
+// entries are written.
+#pragma once
+#include "dev_common.cuh"
+
+namespace spsph {
+
+constexpr int SLICE = 32;
+
+struct SortArrays {  // per species s in {node, stress, dummy}; species-sorted index k
+  const int *start[3];      // [ncell+1] first sorted index of each cell
+  const int *order[3];      // [n_s] original 0-based particle id
+  const double2 *pos[3];    // [n_s] positions
+  const double *h[3];       // [n_s] smoothing lengths
+  const int *cell[3];       // [n_s] cell id (or -1 for out-of-domain particles parked at the end)
+};
+
+// thread-slot space: nodes [0,NNp), stress particles [NNp, NNp+NSp), dummies after; NNp, NSp multiples of 32
+struct SlotMap {
+  int nn, ns, nd;     // particle counts
+  int nnp, nsp, ndp;  // padded to multiples of SLICE
+  __host__ __device__ int total() const { return nnp + nsp + ndp; }
+};
+__device__ __forceinline__ bool slot_decode(const SlotMap &m, int t, int &sp, int &k) {
+  if (t < m.nnp) {
+    sp = SP_NODE;
+    k = t;
+    return k < m.nn;
+  }
+  t -= m.nnp;
+  if (t < m.nsp) {
+    sp = SP_STRESS;
+    k = t;
+    return k < m.ns;
+  }
+  t -= m.nsp;
+  sp = SP_DUMMY;
+  k = t;
+  return k < m.nd;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Check_Out_Domain + bounding box / max h of the in-domain particles (min/max are order-independent).
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_min(double v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmin(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ double warp_max(double v) {
+  for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__global__ void k_domain_bbox(DevParams P, const double *__restrict__ x, const double *__restrict__ hsml,
+                              int *__restrict__ if_out, double *__restrict__ partial /* [gridDim.x][5] */) {
+  double xmn = 1.e+10, ymn = 1.e+10, xmx = -1.e+10, ymx = -1.e+10, hmx = 0.0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.ntotal2; i += gridDim.x * blockDim.x) {
+    const double2 p = ld2(x, i);
+    int out = if_out[i];
+    const double dxx = (p.x - P.xmin_dom[0]) * (p.x - P.xmax_dom[0]);
+    const double dyy = (p.y - P.xmin_dom[1]) * (p.y - P.xmax_dom[1]);
+    if (dxx > 0.0 || dyy > 0.0) {
+      if (!out) if_out[i] = 1;
+      out = 1;
+    }
+    if (!out) {
+      xmn = fmin(xmn, p.x);
+      xmx = fmax(xmx, p.x);
+      ymn = fmin(ymn, p.y);
+      ymx = fmax(ymx, p.y);
+      hmx = fmax(hmx, hsml[i]);
+    }
+  }
+  __shared__ double sh[5][32];
+  xmn = warp_min(xmn);
+  ymn = warp_min(ymn);
+  xmx = warp_max(xmx);
+  ymx = warp_max(ymx);
+  hmx = warp_max(hmx);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  if (l == 0) {
+    sh[0][w] = xmn;
+    sh[1][w] = ymn;
+    sh[2][w] = xmx;
+    sh[3][w] = ymx;
+    sh[4][w] = hmx;
+  }
+  __syncthreads();
+  if (w == 0) {
+    const int nw = blockDim.x >> 5;
+    xmn = l < nw ? sh[0][l] : 1.e+10;
+    ymn = l < nw ? sh[1][l] : 1.e+10;
+    xmx = l < nw ? sh[2][l] : -1.e+10;
+    ymx = l < nw ? sh[3][l] : -1.e+10;
+    hmx = l < nw ? sh[4][l] : 0.0;
+    xmn = warp_min(xmn);
+    ymn = warp_min(ymn);
+    xmx = warp_max(xmx);
+    ymx = warp_max(ymx);
+    hmx = warp_max(hmx);
+    if (l == 0) {
+      double *o = partial + 5 * blockIdx.x;
+      o[0] = xmn;
+      o[1] = ymn;
+      o[2] = xmx;
+      o[3] = ymx;
+      o[4] = hmx;
+    }
+  }
+}
+
+// grid_find_NEW Task 1 (main:1245-1258) on one thread; also clears the per-step counters.
+__global__ void k_grid_params(int nblocks, const double *__restrict__ partial, GridInfo *__restrict__ G,
+                              int cell_capacity) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double mn[2] = {1.e+10, 1.e+10}, mx[2] = {-1.e+10, -1.e+10}, hmx = 0.0;
+  for (int b = 0; b < nblocks; ++b) {
+    const double *o = partial + 5 * b;
+    mn[0] = fmin(mn[0], o[0]);
+    mn[1] = fmin(mn[1], o[1]);
+    mx[0] = fmax(mx[0], o[2]);
+    mx[1] = fmax(mx[1], o[3]);
+    hmx = fmax(hmx, o[4]);
+  }
+  for (int d = 0; d < 2; ++d) {
+    double xmin = mn[d], xmax = mx[d];
+    double deltx = hmx * 2;
+    const double length = xmax - xmin;
+    const int ndiv = (int)((length / deltx) + 1);
+    const double length_new = ndiv * deltx;
+    xmin = xmin - (length_new - length) / 2 - (double)0.001f * length;
+    xmax = xmax + (length_new - length) / 2 + (double)0.001f * length;
+    G->xmin[d] = xmin;
+    G->xmax[d] = xmax;
+    G->deltx[d] = deltx;
+    G->ndivx[d] = ndiv;
+    G->rxmin[d] = mn[d];
+    G->rxmax[d] = mx[d];
+  }
+  G->rhmax = hmx;
+  const long long nc = (long long)G->ndivx[0] * (long long)G->ndivx[1];
+  G->overflow = (nc > (long long)cell_capacity || nc <= 0) ? 1 : 0;
+  G->ncell = G->overflow ? 1 : (int)nc;
+  if (G->overflow) {  // keep the remaining kernels in bounds; the host reports the error
+    G->ndivx[0] = 1;
+    G->ndivx[1] = 1;
+  }
+}
+
+// zero the per-cell counters (3 species x (ncell+1)) -- size known only on the device
+__global__ void k_zero_cells(const GridInfo *__restrict__ G, int *__restrict__ cnt, int cell_stride) {
+  const int n = G->ncell + 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    cnt[i] = 0;
+    cnt[cell_stride + i] = 0;
+    cnt[2 * cell_stride + i] = 0;
+  }
+}
+
+__device__ __forceinline__ int species_of(const DevParams &P, int i) {
+  return i < P.nnode ? SP_NODE : (i < P.ntotal ? SP_STRESS : SP_DUMMY);
+}
+
+// grid_find_NEW Task 2 (main:1277-1286): cell id of every in-domain particle + per-cell species counts
+__global__ void k_cell_id(DevParams P, const GridInfo *__restrict__ G, const double *__restrict__ x,
+                          const int *__restrict__ if_out, int *__restrict__ which_cell, int *__restrict__ cnt,
+                          int cell_stride, int *__restrict__ nout /* [3] */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.ntotal2) return;
+  const int sp = species_of(P, i);
+  if (if_out[i] || G->overflow) {  // on a cell-table overflow nothing is binned; the host reports the error
+    which_cell[i] = -1 - atomicAdd(&nout[sp], 1);  // parked after the sorted particles, order irrelevant
+    return;
+  }
+  const double2 p = ld2(x, i);
+  int ix = (int)((p.x - G->xmin[0]) / G->deltx[0] + 1);
+  int iy = (int)((p.y - G->xmin[1]) / G->deltx[1] + 1);
+  if (ix > G->ndivx[0]) ix = G->ndivx[0];
+  if (iy > G->ndivx[1]) iy = G->ndivx[1];
+  const int c = G->ndivx[0] * (iy - 1) + (ix - 1);  // 0-based cell id, same ordering as the reference's
+  which_cell[i] = c;
+  atomicAdd(&cnt[sp * cell_stride + c], 1);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Device-wide exclusive scan of int32 (three-kernel reduce / scan-of-sums / apply). `n` comes from device
+// memory (n_ptr) plus a constant, so no host round trip is needed. blockIdx.y selects one of several
+// independent rows (row stride in elements).
+// ------------------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_BLOCKS = 296;  // 2 per SM
+
+__device__ __forceinline__ int block_excl_scan(int v, int *total) {
+  __shared__ int wsum[SCAN_THREADS / 32];
+  const int l = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+  for (int o = 1; o < 32; o <<= 1) {
+    const int t = __shfl_up_sync(0xffffffffu, inc, o);
+    if (l >= o) inc += t;
+  }
+  if (l == 31) wsum[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    int s = l < SCAN_THREADS / 32 ? wsum[l] : 0;
+    for (int o = 1; o < 32; o <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, s, o);
+      if (l >= o) s += t;
+    }
+    if (l < SCAN_THREADS / 32) wsum[l] = s;
+  }
+  __syncthreads();
+  const int base = w > 0 ? wsum[w - 1] : 0;
+  if (total) *total = wsum[SCAN_THREADS / 32 - 1];
+  __syncthreads();
+  return base + inc - v;
+}
+
+__device__ __forceinline__ void scan_chunk(int n, int &b, int &e) {
+  const int per = (n + SCAN_BLOCKS - 1) / SCAN_BLOCKS;
+  const int chunk = ((per + SCAN_THREADS - 1) / SCAN_THREADS) * SCAN_THREADS;
+  const long long bb = (long long)blockIdx.x * chunk;
+  b = bb < n ? (int)bb : n;
+  e = (bb + chunk) < n ? (int)(bb + chunk) : n;
+}
+
+__global__ void k_scan_reduce(const int *__restrict__ in, int row_stride, const int *__restrict__ n_ptr, int n_add,
+                              int *__restrict__ bsum) {
+  const int n = (n_ptr ? *n_ptr : 0) + n_add;
+  const int *row = in + (size_t)blockIdx.y * row_stride;
+  int b, e;
+  scan_chunk(n, b, e);
+  int s = 0;
+  for (int i = b + threadIdx.x; i < e; i += SCAN_THREADS) s += row[i];
+  int tot;
+  block_excl_scan(s, &tot);
+  if (threadIdx.x == 0) bsum[blockIdx.y * SCAN_BLOCKS + blockIdx.x] = tot;
+}
+__global__ void k_scan_sums(int *__restrict__ bsum, long long *__restrict__ totals) {
+  // one block per row; SCAN_BLOCKS <= 2*SCAN_THREADS
+  int *row = bsum + blockIdx.x * SCAN_BLOCKS;
+  __shared__ int carry;
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  for (int base = 0; base < SCAN_BLOCKS; base += SCAN_THREADS) {
+    const int i = base + threadIdx.x;
+    const int v = i < SCAN_BLOCKS ? row[i] : 0;
+    int tot;
+    const int ex = block_excl_scan(v, &tot);
+    const int c = carry;
+    if (i < SCAN_BLOCKS) row[i] = c + ex;
+    __syncthreads();
+    if (threadIdx.x == 0) carry = c + tot;
+    __syncthreads();
+  }
+  if (threadIdx.x == 0 && totals) totals[blockIdx.x] = carry;
+}
+__global__ void k_scan_apply(const int *__restrict__ in, int *__restrict__ out, int row_stride,
+                             const int *__restrict__ n_ptr, int n_add, const int *__restrict__ bsum) {
+  const int n = (n_ptr ? *n_ptr : 0) + n_add;
+  const int *row = in + (size_t)blockIdx.y * row_stride;
+  int *orow = out + (size_t)blockIdx.y * row_stride;
+  int b, e;
+  scan_chunk(n, b, e);
+  int carry = bsum[blockIdx.y * SCAN_BLOCKS + blockIdx.x];
+  for (int base = b; base < e; base += SCAN_THREADS) {
+    const int i = base + threadIdx.x;
+    const int v = i < e ? row[i] : 0;
+    int tot;
+    const int ex = block_excl_scan(v, &tot);
+    if (i < e) orow[i] = carry + ex;
+    carry += tot;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Counting sort: scatter into cell segments (arbitrary order inside a cell), then rank inside the cell by
+// original index so that the final order is deterministic and equals the reference's list_picell order
+// (ascending particle index within a cell, main:1299-1305).
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_scatter(DevParams P, const int *__restrict__ which_cell, const int *__restrict__ start,
+                          int *__restrict__ fill, int cell_stride, int *__restrict__ tmp /* 3 rows, stride ntotal2 */) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.ntotal2) return;
+  const int c = which_cell[i];
+  if (c < 0) return;
+  const int sp = species_of(P, i);
+  const int slot = start[sp * cell_stride + c] + atomicAdd(&fill[sp * cell_stride + c], 1);
+  tmp[(size_t)sp * P.ntotal2 + slot] = i;
+}
+
+__global__ void k_rank(DevParams P, const GridInfo *__restrict__ G, const double *__restrict__ x,
+                       const double *__restrict__ hsml, const int *__restrict__ which_cell,
+                       const int *__restrict__ start, int cell_stride, const int *__restrict__ tmp,
+                       int *__restrict__ order, double2 *__restrict__ spos, double *__restrict__ sh,
+                       int *__restrict__ scell, int *__restrict__ pos_of /* [ntotal2] species-sorted index */) {
+  // one thread per particle in original order
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.ntotal2) return;
+  const int sp = species_of(P, i);
+  const int c = which_cell[i];
+  const size_t row = (size_t)sp * P.ntotal2;
+  int k;
+  if (c < 0) {
+    const int nact = start[sp * cell_stride + G->ncell];
+    k = nact + (-1 - c);
+  } else {
+    const int b = start[sp * cell_stride + c], e = start[sp * cell_stride + c + 1];
+    int r = 0;
+    for (int j = b; j < e; ++j) r += (tmp[row + j] < i) ? 1 : 0;
+    k = b + r;
+  }
+  order[row + k] = i;
+  spos[row + k] = ld2(x, i);
+  sh[row + k] = hsml[i];
+  scell[row + k] = c < 0 ? -1 : c;
+  pos_of[i] = k;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Neighbour enumeration.
+// ------------------------------------------------------------------------------------------------------
+struct Cand {  // one accepted partner
+  int q;       // species-sorted index
+  double dxq, dyq, r, mh;  // dx = x_p - x_q (p-perspective); caller flips for the reference orientation
+};
+
+// acceptance test of main:1345-1353 (symmetric in the two particles)
+__device__ __forceinline__ bool pair_accept(const DevParams &P, double2 pp, double hp, double2 pq, double hq, double &dx,
+                                            double &dy, double &r, double &mh) {
+  dx = pp.x - pq.x;
+  dy = pp.y - pq.y;
+  double driac = dx * dx;
+  driac = driac + dy * dy;
+  mh = (hp + hq) / 2.;
+  r = sqrt(driac);
+  return r < P.scale_k * mh;
+}
+
+// unified (cell, species, index) slot of the reference's creation order
+__device__ __forceinline__ int unified_slot(const SortArrays &S, int c, int sp, int k) {
+  const int sn = S.start[0][c], ss = S.start[1][c], sd = S.start[2][c];
+  int u = sn + ss + sd;
+  if (sp >= SP_STRESS) u += S.start[0][c + 1] - sn;
+  if (sp >= SP_DUMMY) u += S.start[1][c + 1] - ss;
+  return u + (k - S.start[sp][c]);
+}
+
+// Growth rule of the reference's list: pairs whose creation index exceeds the old list
+// capacity M are visited first and reversed. thr = (ua*, ub*): pair (ua<ub) is "old" iff (ua,ub) <=lex thr.
+struct GrowthRule {
+  int mode;  // 0: all old (forward), 1: all new (fully reversed: first step), 2: split at (ua, ub)
+  int ua, ub;
+};
+__device__ __forceinline__ bool pair_is_old(const GrowthRule &g, int u1, int u2) {
+  if (g.mode == 0) return true;
+  if (g.mode == 1) return false;
+  const int a = u1 < u2 ? u1 : u2, b = u1 < u2 ? u2 : u1;
+  return (a < g.ua) || (a == g.ua && b <= g.ub);
+}
+
+// Count pass: per thread slot the lengths of its gather lists, its forward pair count (creation index)
+// and its total interaction count (countiac, main:1355-1356).
+__global__ void __launch_bounds__(128)
+k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, int *__restrict__ n0, int *__restrict__ n1,
+        int *__restrict__ nfwd_u /* unified order */, int *__restrict__ nall, int *__restrict__ w0 /* slice widths */,
+        int *__restrict__ wC, int *__restrict__ wD) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int sp, k;
+  const bool live = (t < M.total()) && slot_decode(M, t, sp, k);
+  int c0 = 0, c1 = 0, cf = 0, ca = 0;
+  if (live) {
+    const int c = S.cell[sp][k];
+    if (c >= 0) {
+      const double2 pp = S.pos[sp][k];
+      const double hp = S.h[sp][k];
+      const int ndx = G->ndivx[0], ndy = G->ndivx[1];
+      const int cy = c / ndx, cx = c - cy * ndx;
+      for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy)
+        for (int jx = max(cx - 1, 0); jx <= min(cx + 1, ndx - 1); ++jx) {
+          const int cq = jy * ndx + jx;
+#pragma unroll
+          for (int sq = 0; sq < 3; ++sq) {
+            const int b = S.start[sq][cq], e = S.start[sq][cq + 1];
+            for (int q = b; q < e; ++q) {
+              if (sq == sp && q == k) continue;
+              double dx, dy, r, mh;
+              if (!pair_accept(P, pp, hp, S.pos[sq][q], S.h[sq][q], dx, dy, r, mh)) continue;
+              ++ca;
+              const bool fwd = (cq > c) || (cq == c && (sq > sp || (sq == sp && q > k)));
+              cf += fwd ? 1 : 0;
+              if (sp == SP_DUMMY) continue;
+              if (sq == sp)
+                ++c1;
+              else
+                ++c0;  // node<->stress (type 1) and node/stress<->dummy (types 6, 9)
+            }
+          }
+        }
+      nfwd_u[unified_slot(S, c, sp, k)] = cf;
+    }
+    nall[t] = ca;
+  }
+  if (t < M.nnp + M.nsp) {  // list-owning slots
+    if (live) {
+      n0[t] = c0;
+      n1[t] = c1;
+    } else {
+      n0[t] = 0;
+      n1[t] = 0;
+    }
+    int m0 = c0, m1 = c1;
+    for (int o = 16; o > 0; o >>= 1) {
+      m0 = max(m0, __shfl_xor_sync(0xffffffffu, m0, o));
+      m1 = max(m1, __shfl_xor_sync(0xffffffffu, m1, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+      const int sl = t / SLICE;
+      w0[sl] = m0 * SLICE;
+      const bool is_node = t < M.nnp;
+      wC[sl] = is_node ? m1 * SLICE : 0;
+      wD[sl] = is_node ? 0 : m1 * SLICE;
+    }
+  }
+}
+
+// after the scans: totals -> status block
+__global__ void k_status(const GridInfo *__restrict__ G, const long long *__restrict__ totals, StepStatus *st) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st->tot0 = totals[0];
+  st->totC = totals[1];
+  st->totD = totals[2];
+  st->n_pairs = totals[3];
+  st->ncell = G->ncell;
+  st->overflow = G->overflow;
+  st->err = 0;
+}
+
+// Finds the split point of the growth rule: the pair with creation index M (1-based) -> (ua*, ub*).
+__global__ void k_growth_threshold(DevParams P, SlotMap Mm, const GridInfo *__restrict__ G, SortArrays S,
+                                   const int *__restrict__ base_u /* exclusive scan of nfwd_u */, long long Mold,
+                                   GrowthRule *__restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int nact = S.start[0][G->ncell] + S.start[1][G->ncell] + S.start[2][G->ncell];
+  // largest unified slot ua with base_u[ua] < Mold  (creation indices of ua are base+1 .. base+nfwd)
+  int lo = 0, hi = nact - 1;
+  while (lo < hi) {
+    const int mid = (lo + hi + 1) >> 1;
+    if ((long long)base_u[mid] < Mold)
+      lo = mid;
+    else
+      hi = mid - 1;
+  }
+  const int ua = lo;
+  const int want = (int)(Mold - (long long)base_u[ua]);  // the want-th forward partner of ua is the last old pair
+  // locate ua's cell: largest c with U(c) <= ua
+  int cl = 0, ch = G->ncell - 1;
+  while (cl < ch) {
+    const int mid = (cl + ch + 1) >> 1;
+    const int U = S.start[0][mid] + S.start[1][mid] + S.start[2][mid];
+    if (U <= ua)
+      cl = mid;
+    else
+      ch = mid - 1;
+  }
+  const int c = cl;
+  int rem = ua - (S.start[0][c] + S.start[1][c] + S.start[2][c]);
+  int sp = 0;
+  for (; sp < 3; ++sp) {
+    const int n = S.start[sp][c + 1] - S.start[sp][c];
+    if (rem < n) break;
+    rem -= n;
+  }
+  const int k = S.start[sp][c] + rem;
+  const double2 pp = S.pos[sp][k];
+  const double hp = S.h[sp][k];
+  const int ndx = G->ndivx[0], ndy = G->ndivx[1];
+  const int cy = c / ndx, cx = c - cy * ndx;
+  int seen = 0, ub = ua;
+  for (int jy = cy; jy <= min(cy + 1, ndy - 1) && seen < want; ++jy)
+    for (int jx = max(cx - 1, 0); jx <= min(cx + 1, ndx - 1) && seen < want; ++jx) {
+      const int cq = jy * ndx + jx;
+      if (cq < c) continue;
+      for (int sq = 0; sq < 3 && seen < want; ++sq) {
+        const int b = S.start[sq][cq], e = S.start[sq][cq + 1];
+        for (int q = b; q < e && seen < want; ++q) {
+          const bool fwd = (cq > c) || (sq > sp || (sq == sp && q > k));
+          if (!fwd) continue;
+          double dx, dy, r, mh;
+          if (!pair_accept(P, pp, hp, S.pos[sq][q], S.h[sq][q], dx, dy, r, mh)) continue;
+          ++seen;
+          ub = unified_slot(S, cq, sq, q);
+        }
+      }
+    }
+  out->mode = 2;
+  out->ua = ua;
+  out->ub = ub;
+}
+
+struct ListPtrs {
+  // list 0: node <- stress/dummy partners and stress <- node/dummy partners (types 1, 6, 9), reference
+  //         orientation of the gradient (pair_i - pair_j after Pint_Update)
+  int *idx0;
+  float *w0, *gx0, *gy0;
+  // list C: node <- node (type 3), own-perspective gradient; list D: stress <- stress (type 2), weight only
+  int *idxC;
+  float *wC, *gxC, *gyC;
+  int *idxD;
+  float *wD;
+  const int *off0, *offC, *offD;  // per slice, exclusive scans of the slice widths
+};
+
+// Fill pass: writes every list entry at its traversal position.
+__global__ void __launch_bounds__(128)
+k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ n0,
+       const int *__restrict__ n1, const GrowthRule *__restrict__ growth, ListPtrs L, int *__restrict__ bc_int,
+       float *__restrict__ n_int) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M.nnp + M.nsp) return;
+  int sp, k;
+  if (!slot_decode(M, t, sp, k)) return;
+  const int id = S.order[sp][k];
+  const int c = S.cell[sp][k];
+  const int cnt0 = n0[t], cnt1 = n1[t];
+  if (sp == SP_NODE) n_int[id] = (float)cnt1;  // node-node interaction count (main:870-871 / 221-222)
+  if (c < 0) {
+    if (sp == SP_NODE) bc_int[id] = 0;
+    return;
+  }
+  const GrowthRule gr = *growth;
+  const int lane = t & 31, sl = t / SLICE;
+  const size_t o0 = (size_t)L.off0[sl] + lane;
+  const size_t o1 = (size_t)(sp == SP_NODE ? L.offC[sl] : L.offD[sl]) + lane;
+  const double2 pp = S.pos[sp][k];
+  const double hp = S.h[sp][k];
+  const int ndx = G->ndivx[0], ndy = G->ndivx[1];
+  const int cy = c / ndx, cx = c - cy * ndx;
+  const int up = unified_slot(S, c, sp, k);
+  // number of "old" entries per list (prefix of the ascending order); only the split mode needs a pre-count
+  int s0 = (gr.mode == 1) ? 0 : cnt0, s1 = (gr.mode == 1) ? 0 : cnt1;
+  if (gr.mode == 2 && up >= gr.ua) {
+    s0 = 0;
+    s1 = 0;
+    // partners at or before ua live in cells <= cell(ua); cheap conservative test on the first stencil cell
+    const int cfirst = max(cy - 1, 0) * ndx + max(cx - 1, 0);
+    if (unified_slot(S, cfirst, 0, S.start[0][cfirst]) <= gr.ua) {
+      for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy)
+        for (int jx = max(cx - 1, 0); jx <= min(cx + 1, ndx - 1); ++jx) {
+          const int cq = jy * ndx + jx;
+          for (int sq = 0; sq < 3; ++sq) {
+            const int b = S.start[sq][cq], e = S.start[sq][cq + 1];
+            for (int q = b; q < e; ++q) {
+              if (sq == sp && q == k) continue;
+              double dx, dy, r, mh;
+              if (!pair_accept(P, pp, hp, S.pos[sq][q], S.h[sq][q], dx, dy, r, mh)) continue;
+              if (!pair_is_old(gr, up, unified_slot(S, cq, sq, q))) continue;
+              if (sq == sp)
+                ++s1;
+              else
+                ++s0;
+            }
+          }
+        }
+    }
+  }
+  int e0 = 0, e1 = 0, has_dummy = 0;
+  for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy)
+    for (int jx = max(cx - 1, 0); jx <= min(cx + 1, ndx - 1); ++jx) {
+      const int cq = jy * ndx + jx;
+#pragma unroll
+      for (int sq = 0; sq < 3; ++sq) {
+        const int b = S.start[sq][cq], e = S.start[sq][cq + 1];
+        for (int q = b; q < e; ++q) {
+          if (sq == sp && q == k) continue;
+          double dx, dy, r, mh;
+          if (!pair_accept(P, pp, hp, S.pos[sq][q], S.h[sq][q], dx, dy, r, mh)) continue;
+          const int qid = S.order[sq][q];
+          double w, gx, gy;
+          if (sq == sp) {
+            sph_kernel(P, r, dx, dy, mh, w, gx, gy);  // own perspective: x_p - x_q
+            const int pos = (e1 < s1) ? (cnt1 - s1) + e1 : (cnt1 - 1 - e1);
+            const size_t a = o1 + (size_t)pos * SLICE;
+            if (sp == SP_NODE) {
+              L.idxC[a] = qid;
+              L.wC[a] = (float)w;
+              L.gxC[a] = (float)gx;
+              L.gyC[a] = (float)gy;
+            } else {
+              L.idxD[a] = qid;
+              L.wD[a] = (float)w;
+            }
+            ++e1;
+          } else {
+            // Pint_Update orientation: pair_i = stress particle (type 1) or dummy (types 6, 9)
+            const bool p_is_i = (sp == SP_STRESS && sq == SP_NODE);
+            if (p_is_i)
+              sph_kernel(P, r, dx, dy, mh, w, gx, gy);
+            else
+              sph_kernel(P, r, -dx, -dy, mh, w, gx, gy);
+            const int pos = (e0 < s0) ? (cnt0 - s0) + e0 : (cnt0 - 1 - e0);
+            const size_t a = o0 + (size_t)pos * SLICE;
+            L.idx0[a] = qid;
+            L.w0[a] = (float)w;
+            L.gx0[a] = (float)gx;
+            L.gy0[a] = (float)gy;
+            if (sq == SP_DUMMY) has_dummy = 1;
+            ++e0;
+          }
+        }
+      }
+    }
+  if (sp == SP_NODE) bc_int[id] = has_dummy;  // main:506,579
+}
+
+// Export of the reference's pair list (creation order + traversal position), for parity tests and tools.
+__global__ void k_export_pairs(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S,
+                               const int *__restrict__ base_u, long long n_pairs, long long Mold, int *__restrict__ pi,
+                               int *__restrict__ pj, int *__restrict__ ptype, float *__restrict__ pw,
+                               float *__restrict__ pgx, float *__restrict__ pgy) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int sp, k;
+  if (t >= M.total() || !slot_decode(M, t, sp, k)) return;
+  const int c = S.cell[sp][k];
+  if (c < 0) return;
+  const double2 pp = S.pos[sp][k];
+  const double hp = S.h[sp][k];
+  const int ndx = G->ndivx[0], ndy = G->ndivx[1];
+  const int cy = c / ndx, cx = c - cy * ndx;
+  long long ci = base_u[unified_slot(S, c, sp, k)];  // 0-based creation index of this particle's first pair
+  const int idp = S.order[sp][k];
+  const int itp[3] = {2, 1, 25};
+  for (int jy = cy; jy <= min(cy + 1, ndy - 1); ++jy)
+    for (int jx = max(cx - 1, 0); jx <= min(cx + 1, ndx - 1); ++jx) {
+      const int cq = jy * ndx + jx;
+      if (cq < c) continue;
+      for (int sq = 0; sq < 3; ++sq) {
+        const int b = S.start[sq][cq], e = S.start[sq][cq + 1];
+        for (int q = b; q < e; ++q) {
+          const bool fwd = (cq > c) || (sq > sp || (sq == sp && q > k));
+          if (!fwd) continue;
+          double dx, dy, r, mh, w, gx, gy;
+          if (!pair_accept(P, pp, hp, S.pos[sq][q], S.h[sq][q], dx, dy, r, mh)) continue;
+          sph_kernel(P, r, dx, dy, mh, w, gx, gy);
+          int i = idp + 1, j = S.order[sq][q] + 1;  // 1-based ids, creation orientation (itotal, jtotal)
+          float fgx = (float)gx, fgy = (float)gy;
+          const int ii = itp[sp], jj = itp[sq];
+          if ((ii == 2 && jj == 1) || (ii == 2 && jj == 25) || (ii == 1 && jj == 25)) {  // Pint_Update swap
+            const int tmp = i;
+            i = j;
+            j = tmp;
+            fgx = -fgx;
+            fgy = -fgy;
+          }
+          const int isumm = ii + jj;
+          const int ty = isumm == 3 ? 1 : isumm == 2 ? 2 : isumm == 4 ? 3 : isumm == 27 ? 6 : isumm == 26 ? 9 : 0;
+          // traversal position
+          long long pos = ci;
+          if (n_pairs > Mold) {
+            const long long over = n_pairs - Mold;
+            pos = (ci >= Mold) ? (n_pairs - 1 - ci) : (over + ci);
+          }
+          pi[pos] = i;
+          pj[pos] = j;
+          ptype[pos] = ty;
+          pw[pos] = (float)w;
+          pgx[pos] = fgx;
+          pgy[pos] = fgy;
+          ++ci;
+        }
+      }
+    }
+}
+
+}  // namespace spsph

@@ -1,0 +1,729 @@
+// libspsph_cuda.so -- C-ABI (include/spsph.h) of the B200-native Stress-Particle SPH time-step engine.
+//
+// Host orchestration of one time_integration (2_SPH_main_2018.f90:78-184) as a fixed sequence of kernel
+// launches on one stream; the only host round trip per step is the read-back of the pair / list totals
+// after the count pass (needed to size the neighbour lists and to apply the reference's list-growth rule).
+// There is no CPU fallback: every entry point fails if CUDA is unavailable.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "spsph.h"
+#include "step_kernels.cuh"
+
+using namespace spsph;
+
+#define CUDA_TRY(call)                                                                            \
+  do {                                                                                            \
+    cudaError_t e_ = (call);                                                                      \
+    if (e_ != cudaSuccess) {                                                                      \
+      h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                                \
+      return 1;                                                                                   \
+    }                                                                                             \
+  } while (0)
+
+struct spsph_handle {
+  spsph_params hp{};
+  DevParams P{};
+  SlotMap M{};
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::string err;
+  std::vector<void *> allocs;
+  bool uploaded = false;
+
+  // particle state (original order)
+  double *x = nullptr, *x00 = nullptr, *rho = nullptr, *mass = nullptr, *hsml = nullptr, *mor = nullptr;
+  double *V[2] = {nullptr, nullptr}, *S[2] = {nullptr, nullptr};
+  double *sor = nullptr, *epsp = nullptr, *fdp = nullptr, *norm = nullptr, *AE = nullptr;
+  double *vel0 = nullptr, *stress0 = nullptr, *vx0 = nullptr, *RKv = nullptr, *RKs = nullptr, *RKe = nullptr;
+  double *displ = nullptr, *x_10 = nullptr, *disp_10 = nullptr;
+  float *wallpos = nullptr, *horiz = nullptr, *n_int = nullptr;
+  int *bc_int = nullptr, *bc_or_not = nullptr, *bc_info = nullptr, *if_out = nullptr;
+  int cur = 0;
+  std::vector<double> h_internal_vars;  // rows 2..10 of Internal_Vars never change on the hot path
+  std::vector<int32_t> h_itype;
+
+  // grid / sort
+  GridInfo *G = nullptr;
+  double *bbox_partial = nullptr;
+  int bbox_blocks = 0;
+  int cell_capacity = 0, cell_stride = 0;
+  int *cell_cnt = nullptr, *cell_start = nullptr, *cell_fill = nullptr;
+  int *which_cell = nullptr, *tmp_ids = nullptr, *order = nullptr, *scell = nullptr, *pos_of = nullptr, *nout = nullptr;
+  double2 *spos = nullptr;
+  double *sh = nullptr;
+  int *scan_bsum = nullptr;
+  long long *scan_totals = nullptr;  // [0..2] list storage, [3] pairs, [4..6] cells
+  // lists
+  int *n0 = nullptr, *n1 = nullptr, *nall = nullptr, *nfwd_u = nullptr, *base_u = nullptr;
+  int *wslice = nullptr, *oslice = nullptr;  // 3 rows x nslices
+  int nslices = 0;
+  GrowthRule *growth = nullptr;
+  long long cap0 = 0, capC = 0, capD = 0;
+  ListPtrs L{};
+  StepStatus *status_d = nullptr, *status_h = nullptr;
+  int *stats_d = nullptr;
+
+  long long m_pairs = 0;       // max pair count of all previous steps (main:1210)
+  long long last_n_pairs = 0;  // of the last step
+  long long last_m_before = 0;
+  float last_ms = 0.f;
+  long long last_launches = 0, launches = 0;
+};
+
+namespace {
+
+template <class T>
+int dalloc(spsph_handle *h, T **p, size_t n) {
+  void *q = nullptr;
+  if (n == 0) n = 1;
+  CUDA_TRY(cudaMalloc(&q, n * sizeof(T)));
+  h->allocs.push_back(q);
+  *p = (T *)q;
+  return 0;
+}
+
+int round_up(int a, int b) { return ((a + b - 1) / b) * b; }
+
+SortArrays sort_arrays(spsph_handle *h) {
+  SortArrays S;
+  const size_t n2 = (size_t)h->P.ntotal2;
+  for (int s = 0; s < 3; ++s) {
+    S.start[s] = h->cell_start + (size_t)s * h->cell_stride;
+    S.order[s] = h->order + s * n2;
+    S.pos[s] = h->spos + s * n2;
+    S.h[s] = h->sh + s * n2;
+    S.cell[s] = h->scell + s * n2;
+  }
+  return S;
+}
+
+StatePtrs state_ptrs(spsph_handle *h) {
+  StatePtrs s;
+  s.x = h->x;
+  s.mass = h->mass;
+  s.rho = h->rho;
+  s.hsml = h->hsml;
+  s.mor = h->mor;
+  s.wallpos = h->wallpos;
+  s.horiz = h->horiz;
+  s.bc_or_not = h->bc_or_not;
+  s.bc_info = h->bc_info;
+  s.V[0] = h->V[0];
+  s.V[1] = h->V[1];
+  s.S[0] = h->S[0];
+  s.S[1] = h->S[1];
+  s.sor = h->sor;
+  s.epsp = h->epsp;
+  s.fdp = h->fdp;
+  s.norm = h->norm;
+  s.AE = h->AE;
+  s.vel0 = h->vel0;
+  s.stress0 = h->stress0;
+  s.vx0 = h->vx0;
+  s.RKv = h->RKv;
+  s.RKs = h->RKs;
+  s.RKe = h->RKe;
+  return s;
+}
+
+// piecewise-linear time curve, shared by Normal_BCs (mat:1707-1722) and gravity_force (mat:2688-2704)
+double tcurve(const spsph_params &p, int it_curves, double t) {
+  if (it_curves < 1 || it_curves > p.ntcurves) return 0.0;
+  double tt0 = 0, tt1 = 0;
+  int ipts = 1;
+  const int npts = p.nptstcurves[it_curves - 1];
+  for (ipts = 1; ipts <= npts - 1; ++ipts) {
+    tt0 = p.ttcurves[it_curves - 1][ipts - 1];
+    tt1 = p.ttcurves[it_curves - 1][ipts];
+    if (t >= tt0 && t <= tt1) break;
+    tt0 = -1000.;
+  }
+  if (tt0 >= 0.0) {
+    const double xi = (t - tt0) / (tt1 - tt0);
+    return (1. - xi) * (double)p.ftcurves[it_curves - 1][ipts - 1] + xi * (double)p.ftcurves[it_curves - 1][ipts];
+  }
+  return 0.0;
+}
+
+// per-step scalars: gravity factor and the value of every prescribed BC at t_actual
+void step_scalars(spsph_handle *h, int itimestep, double time_sph, double dt) {
+  const spsph_params &p = h->hp;
+  DevParams &P = h->P;
+  P.itimestep = itimestep;
+  P.time_sph = time_sph;
+  P.dt = dt;
+  P.grav[0] = P.grav[1] = 0.0;
+  if (p.ic_grav != 0) {
+    double factg = tcurve(p, p.tcurve_grav, time_sph);
+    factg = factg * p.ft_grav;
+    if (p.ic_grav == 1) {
+      P.grav[0] = factg * p.cgrav[0];
+      P.grav[1] = factg * p.cgrav[1];
+    }
+  }
+  const double ic_time = 0.0;  // uninitialised in the reference: zero reading
+  const double t_actual = time_sph + ic_time * dt;
+  for (int b = 0; b < p.no_bcs; ++b) {
+    const double *bl = p.bc_list[b];
+    const int it_curves = (int)bl[2];
+    double v = 0.0;
+    if (it_curves == 0) {
+      const double a0 = bl[4], a1 = bl[3], w = bl[5], phi = bl[6], tt = bl[7];
+      const double fact = 1.0 - std::exp(-t_actual / tt);
+      const double argum = w * t_actual - phi;
+      v = (a0 + a1 * std::sin(argum)) * fact;
+    } else if (it_curves > 0) {
+      v = tcurve(p, it_curves, t_actual);
+      v = v * bl[3];
+    }
+    P.bcval[b] = v;
+    P.bcvar[b] = (int)bl[1];
+  }
+}
+
+int ensure_lists(spsph_handle *h, long long t0, long long tC, long long tD) {
+  auto grow = [&](long long need, long long &cap) { return need > cap ? (cap = need + need / 8 + 1024, true) : false; };
+  if (grow(t0, h->cap0)) {
+    cudaFree(h->L.idx0);
+    cudaFree(h->L.w0);
+    cudaFree(h->L.gx0);
+    cudaFree(h->L.gy0);
+    CUDA_TRY(cudaMalloc((void **)&h->L.idx0, (size_t)h->cap0 * 4));
+    CUDA_TRY(cudaMalloc((void **)&h->L.w0, (size_t)h->cap0 * 4));
+    CUDA_TRY(cudaMalloc((void **)&h->L.gx0, (size_t)h->cap0 * 4));
+    CUDA_TRY(cudaMalloc((void **)&h->L.gy0, (size_t)h->cap0 * 4));
+  }
+  if (grow(tC, h->capC)) {
+    cudaFree(h->L.idxC);
+    cudaFree(h->L.wC);
+    cudaFree(h->L.gxC);
+    cudaFree(h->L.gyC);
+    CUDA_TRY(cudaMalloc((void **)&h->L.idxC, (size_t)h->capC * 4));
+    CUDA_TRY(cudaMalloc((void **)&h->L.wC, (size_t)h->capC * 4));
+    CUDA_TRY(cudaMalloc((void **)&h->L.gxC, (size_t)h->capC * 4));
+    CUDA_TRY(cudaMalloc((void **)&h->L.gyC, (size_t)h->capC * 4));
+  }
+  if (grow(tD, h->capD)) {
+    cudaFree(h->L.idxD);
+    cudaFree(h->L.wD);
+    CUDA_TRY(cudaMalloc((void **)&h->L.idxD, (size_t)h->capD * 4));
+    CUDA_TRY(cudaMalloc((void **)&h->L.wD, (size_t)h->capD * 4));
+  }
+  return 0;
+}
+
+// exclusive scan of `rows` rows of int32 (stride elements apart) over n = *n_ptr + n_add elements each
+void launch_scan(spsph_handle *h, const int *in, int *out, int rows, int stride, const int *n_ptr, int n_add,
+                 long long *totals) {
+  dim3 g(SCAN_BLOCKS, rows);
+  k_scan_reduce<<<g, SCAN_THREADS, 0, h->stream>>>(in, stride, n_ptr, n_add, h->scan_bsum);
+  k_scan_sums<<<rows, SCAN_THREADS, 0, h->stream>>>(h->scan_bsum, totals);
+  k_scan_apply<<<g, SCAN_THREADS, 0, h->stream>>>(in, out, stride, n_ptr, n_add, h->scan_bsum);
+  h->launches += 3;
+}
+
+// neighbour search up to and including the list fill; leaves the pair totals in h->status_h
+int build_neighbours(spsph_handle *h) {
+  const DevParams &P = h->P;
+  const int n2 = P.ntotal2;
+  const int TB = 256;
+  cudaStream_t s = h->stream;
+  k_domain_bbox<<<h->bbox_blocks, TB, 0, s>>>(P, h->x, h->hsml, h->if_out, h->bbox_partial);
+  k_grid_params<<<1, 32, 0, s>>>(h->bbox_blocks, h->bbox_partial, h->G, h->cell_capacity);
+  k_zero_cells<<<296, TB, 0, s>>>(h->G, h->cell_cnt, h->cell_stride);
+  k_zero_cells<<<296, TB, 0, s>>>(h->G, h->cell_fill, h->cell_stride);
+  CUDA_TRY(cudaMemsetAsync(h->nout, 0, 3 * sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(h->nfwd_u, 0, (size_t)n2 * sizeof(int), s));
+  k_cell_id<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->G, h->x, h->if_out, h->which_cell, h->cell_cnt, h->cell_stride,
+                                               h->nout);
+  h->launches += 5;
+  launch_scan(h, h->cell_cnt, h->cell_start, 3, h->cell_stride, &h->G->ncell, 1, h->scan_totals + 4);
+  k_scatter<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->which_cell, h->cell_start, h->cell_fill, h->cell_stride, h->tmp_ids);
+  k_rank<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->G, h->x, h->hsml, h->which_cell, h->cell_start, h->cell_stride,
+                                            h->tmp_ids, h->order, h->spos, h->sh, h->scell, h->pos_of);
+  const SortArrays S = sort_arrays(h);
+  const int T = h->M.total();
+  k_count<<<(T + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->nfwd_u, h->nall, h->wslice,
+                                           h->wslice + h->nslices, h->wslice + 2 * h->nslices);
+  h->launches += 3;
+  launch_scan(h, h->wslice, h->oslice, 3, h->nslices, nullptr, h->nslices, h->scan_totals);
+  launch_scan(h, h->nfwd_u, h->base_u, 1, n2, nullptr, n2, h->scan_totals + 3);
+  k_status<<<1, 32, 0, s>>>(h->G, h->scan_totals, h->status_d);
+  h->launches += 1;
+  CUDA_TRY(cudaMemcpyAsync(h->status_h, h->status_d, sizeof(StepStatus), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaStreamSynchronize(s));
+  const StepStatus st = *h->status_h;
+  if (st.overflow) {
+    h->err = "cell grid larger than the capacity derived from Xmin_Domain/Xmax_Domain";
+    return 1;
+  }
+  if (st.tot0 >= (1ll << 31) || st.totC >= (1ll << 31) || st.totD >= (1ll << 31)) {
+    h->err = "neighbour list exceeds 2^31 entries on one device";
+    return 1;
+  }
+  if (ensure_lists(h, st.tot0, st.totC, st.totD)) return 1;
+  h->L.off0 = h->oslice;
+  h->L.offC = h->oslice + h->nslices;
+  h->L.offD = h->oslice + 2 * h->nslices;
+  // list-growth rule
+  h->last_m_before = h->m_pairs;
+  h->last_n_pairs = st.n_pairs;
+  GrowthRule gr{0, 0, 0};
+  if (st.n_pairs > h->m_pairs) gr.mode = (h->m_pairs == 0) ? 1 : 2;
+  CUDA_TRY(cudaMemcpyAsync(h->growth, &gr, sizeof(gr), cudaMemcpyHostToDevice, s));
+  if (gr.mode == 2) {
+    k_growth_threshold<<<1, 32, 0, s>>>(P, h->M, h->G, S, h->base_u, h->m_pairs, h->growth);
+    h->launches += 1;
+  }
+  if (st.n_pairs > h->m_pairs) h->m_pairs = st.n_pairs;
+  const int TL = h->M.nnp + h->M.nsp;
+  k_fill<<<(TL + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int, h->n_int);
+  h->launches += 1;
+  return 0;
+}
+
+int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
+  if (!h->uploaded) {
+    h->err = "spsph_step called before spsph_upload";
+    return 1;
+  }
+  step_scalars(h, itimestep, time_sph, dt);
+  if (build_neighbours(h)) return 1;
+  const DevParams &P = h->P;
+  const spsph_params &p = h->hp;
+  cudaStream_t s = h->stream;
+  const SortArrays S = sort_arrays(h);
+  const StatePtrs st = state_ptrs(h);
+  const int TL = h->M.nnp + h->M.nsp;
+  const int GB = (TL + 127) / 128;
+  const int adapt = P.adapt, bc = p.no_bcs > 0 ? 1 : 0;
+  bool first_a = true;
+  int cur = h->cur;
+  // SPH_shift block, main:99-109
+  if (p.sph_shift && itimestep > 1 && ((itimestep - 1) % p.shift_update == 0)) {
+    k_sweep_a<true><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, st, cur, 1 - cur, adapt, 0, 1);
+    h->launches += 1;
+    cur = 1 - cur;
+    first_a = false;
+  }
+  // RK4, main:653-802
+  const int A = 1 - cur, B = cur;  // rk_begin: cur -> A ; sweep A: A -> B ; sweep B: B -> A
+  k_rk_begin<<<(P.ntotal + 255) / 256, 256, 0, s>>>(P, st, cur, A);
+  h->launches += 1;
+  const double f1rk[4] = {0., 0.5, 0.5, 1.0}, f2rk[4] = {1., 2., 2., 1.0};
+  for (int stg = 0; stg < 4; ++stg) {
+    if (first_a)
+      k_sweep_a<true><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, st, A, B, adapt, bc, 0);
+    else
+      k_sweep_a<false><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, st, A, B, adapt, bc, 0);
+    first_a = false;
+    const int last = (stg == 3);
+    const double f1n = last ? 0.0 : f1rk[stg + 1];
+    if (stg == 0)
+      k_sweep_b<true><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, h->n1, st, B, A, f1n, f2rk[stg], last);
+    else
+      k_sweep_b<false><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, h->n1, st, B, A, f1n, f2rk[stg], last);
+    h->launches += 2;
+  }
+  // final stress_point_update + adapt_stress2 + BCs, main:130-135
+  k_sweep_a<false><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, st, A, B, adapt, bc, 1);
+  cur = B;
+  h->cur = cur;
+  // positions, main:140-182
+  k_move<<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n1, st, cur, h->x, h->x00, h->displ);
+  h->launches += 2;
+  if (p.update_x && p.sp_sph && !p.inside_approach) {
+    k_shift<<<(P.nnode + 255) / 256, 256, 0, s>>>(P, h->V[cur], h->x, h->x_10, h->disp_10, h->bc_int, h->n_int);
+    h->launches += 1;
+  }
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char *spsph_version(void) { return "spsph-b200 0.1 (sm_100a)"; }
+
+const char *spsph_last_error(spsph_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
+  if (!out || !p) return 1;
+  *out = nullptr;
+  spsph_handle *h = new spsph_handle();
+  *out = h;  // returned even on failure so that spsph_last_error can be read; caller destroys it
+  if (p->struct_bytes != (int32_t)sizeof(spsph_params)) {
+    h->err = "spsph_params layout mismatch (struct_bytes)";
+    return 1;
+  }
+  h->hp = *p;
+  // ---- scope checks: everything the reference would run for these inputs must exist on the device ----
+  auto fail = [&](const char *m) {
+    h->err = m;
+    return 1;
+  };
+  if (p->ndimn != 2 || p->nstre != 4) return fail("only ndimn = 2, nstre = 4 (plane strain) is supported");
+  if (p->skf != 1) return fail("only the cubic spline kernel (skf = 1) is supported");
+  if (!p->sp_sph) return fail("standard SPH mode (SP_SPH = F) is not supported yet");
+  if (p->cont_density) return fail("cont_density = T is not supported");
+  if (p->art_stress) return fail("art_stress = T is not supported");
+  if (p->ifsigman != 0) return fail("ifsigman = 1 (apply_stress_free) is not supported");
+  if ((p->variant == SPSPH_VARIANT_BUI && p->inside_approach) || (p->inside_approach && p->dummy_nodes))
+    return fail("boundary_forces (inside approach with wall particles) is not supported yet");
+  if (p->ntype_eco > 1 && !(p->ncrit == 2 || p->ncrit == 12))
+    return fail("only ncrit = 2 (von Mises) and ncrit = 12 (Drucker-Prager) are supported");
+  if (p->ntype_eco > 1 && p->ncrit == 2 && !(p->props[6] > (double)0.001f))
+    return fail("initial yield surface size too small (the reference STOPs, mat:2322-2332)");
+  if (p->sph_shift && p->shift_update <= 0) return fail("shift_update must be positive");
+  if (p->no_bcs > 16) return fail("too many BCs");
+  if (p->nnode + p->nstress != p->ntotal || p->ntotal + p->ndummy != p->ntotal2) return fail("inconsistent counts");
+  if (!p->inside_approach && p->nstress != p->nnode * p->npoints) return fail("nstress != npoints*nnode");
+
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) return fail("no CUDA device available (this library has no CPU fallback)");
+  if (device < 0 || device >= ndev) return fail("bad CUDA device index");
+  h->device = device;
+  CUDA_TRY(cudaSetDevice(device));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreate(&h->ev0));
+  CUDA_TRY(cudaEventCreate(&h->ev1));
+
+  DevParams &P = h->P;
+  P.nnode = p->nnode;
+  P.nstress = p->nstress;
+  P.ntotal = p->ntotal;
+  P.ntotal2 = p->ntotal2;
+  P.ndummy = p->ndummy;
+  P.npoints = p->npoints;
+  P.skf = p->skf;
+  P.scale_k = (p->skf == 1) ? 2 : 3;
+  P.cspm = p->cspm;
+  P.update_x = p->update_x;
+  P.xsph = p->xsph;
+  P.ncrit = p->ncrit;
+  P.ntype_eco = p->ntype_eco;
+  P.ntype_solid = p->ntype_solid;
+  P.no_bcs = p->no_bcs;
+  P.bc_nloop = p->bc_loop_ntotal ? p->ntotal : p->nnode;
+  P.sp_sph = p->sp_sph;
+  P.inside_approach = p->inside_approach;
+  P.vel_vector = p->vel_vector;
+  P.shift_update = p->shift_update > 0 ? p->shift_update : 1;
+  P.adapt = (p->ncrit == 12) ? 1 : 0;
+  P.pi = p->pi;
+  P.D11 = p->D11;
+  P.D12 = p->D12;
+  P.D22 = p->D22;
+  P.D33 = p->D33;
+  P.D41 = p->D41;
+  P.D42 = p->D42;
+  P.alpha = p->alpha;
+  P.beta = p->beta;
+  P.damping = p->damping;
+  P.dx = p->dx;
+  P.r_x = p->r_x;
+  P.r_y = p->r_y;
+  P.disp_tol = p->disp_tol;
+  P.ae_thr = (double)p->ae_threshold;
+  for (int k = 0; k < 20; ++k) P.props[k] = p->props[k];
+  for (int d = 0; d < 2; ++d) {
+    P.xmin_dom[d] = p->xmin_domain[d];
+    P.xmax_dom[d] = p->xmax_domain[d];
+  }
+  {  // adapt_stress2 constants, mat:2096-2100 (fp64)
+    const double tanfi = p->props[12], coh = p->props[13];
+    P.dp_alpha2 = tanfi / (std::sqrt(9 + 12 * (tanfi * tanfi)));
+    P.dp_kc = (3 * coh) / (std::sqrt(9 + 12 * (tanfi * tanfi)));
+  }
+
+  SlotMap &M = h->M;
+  M.nn = p->nnode;
+  M.ns = p->nstress;
+  M.nd = p->ndummy;
+  M.nnp = round_up(M.nn, SLICE);
+  M.nsp = round_up(M.ns, SLICE);
+  M.ndp = round_up(M.nd, SLICE);
+  h->nslices = (M.nnp + M.nsp) / SLICE;
+
+  const size_t n2 = (size_t)p->ntotal2, nt = (size_t)p->ntotal, nn = (size_t)p->nnode, ns = (size_t)p->nstress;
+  int rc = 0;
+  rc |= dalloc(h, &h->x, 2 * n2) | dalloc(h, &h->x00, 2 * n2) | dalloc(h, &h->rho, n2) | dalloc(h, &h->mass, n2);
+  rc |= dalloc(h, &h->hsml, n2) | dalloc(h, &h->mor, n2);
+  for (int b = 0; b < 2; ++b) rc |= dalloc(h, &h->V[b], 2 * nt) | dalloc(h, &h->S[b], 4 * nt);
+  rc |= dalloc(h, &h->sor, 3 * nt) | dalloc(h, &h->epsp, nt) | dalloc(h, &h->fdp, nt) | dalloc(h, &h->norm, nt);
+  rc |= dalloc(h, &h->AE, 5 * nt) | dalloc(h, &h->vel0, 2 * nn) | dalloc(h, &h->stress0, 4 * ns);
+  rc |= dalloc(h, &h->vx0, 2 * nt) | dalloc(h, &h->RKv, 2 * nn) | dalloc(h, &h->RKs, 4 * ns) | dalloc(h, &h->RKe, ns);
+  rc |= dalloc(h, &h->displ, 2 * nn) | dalloc(h, &h->x_10, 2 * nn) | dalloc(h, &h->disp_10, nn);
+  rc |= dalloc(h, &h->wallpos, n2) | dalloc(h, &h->horiz, n2) | dalloc(h, &h->n_int, nn);
+  rc |= dalloc(h, &h->bc_int, nn) | dalloc(h, &h->bc_or_not, nt) | dalloc(h, &h->bc_info, 8 * nt);
+  rc |= dalloc(h, &h->if_out, n2);
+  rc |= dalloc(h, &h->G, 1);
+  h->bbox_blocks = 296;
+  rc |= dalloc(h, &h->bbox_partial, 5 * (size_t)h->bbox_blocks);
+  rc |= dalloc(h, &h->which_cell, n2) | dalloc(h, &h->tmp_ids, 3 * n2) | dalloc(h, &h->order, 3 * n2);
+  rc |= dalloc(h, &h->scell, 3 * n2) | dalloc(h, &h->pos_of, n2) | dalloc(h, &h->nout, 4);
+  rc |= dalloc(h, &h->spos, 3 * n2) | dalloc(h, &h->sh, 3 * n2);
+  rc |= dalloc(h, &h->scan_bsum, 4 * (size_t)SCAN_BLOCKS) | dalloc(h, &h->scan_totals, 8);
+  const size_t T = (size_t)M.total();
+  rc |= dalloc(h, &h->n0, T) | dalloc(h, &h->n1, T) | dalloc(h, &h->nall, T);
+  rc |= dalloc(h, &h->nfwd_u, n2) | dalloc(h, &h->base_u, n2);
+  rc |= dalloc(h, &h->wslice, 3 * (size_t)h->nslices) | dalloc(h, &h->oslice, 3 * (size_t)h->nslices);
+  rc |= dalloc(h, &h->growth, 1) | dalloc(h, &h->status_d, 1) | dalloc(h, &h->stats_d, 4);
+  if (rc) return 1;
+  CUDA_TRY(cudaMallocHost((void **)&h->status_h, sizeof(StepStatus)));
+  CUDA_TRY(cudaMemset(h->nall, 0, T * sizeof(int)));
+  CUDA_TRY(cudaMemset(h->AE, 0, 5 * nt * sizeof(double)));
+  CUDA_TRY(cudaMemset(h->norm, 0, nt * sizeof(double)));
+  return 0;
+}
+
+int spsph_upload(spsph_handle *h, const spsph_state *s) {
+  if (!h || !s) return 1;
+  const spsph_params &p = h->hp;
+  const size_t n2 = (size_t)p.ntotal2, nt = (size_t)p.ntotal, nn = (size_t)p.nnode;
+  if (!s->x || !s->vel || !s->stress || !s->rho || !s->mass || !s->hsml || !s->itype) {
+    h->err = "spsph_upload: x, vel, stress, rho, mass, hsml and itype are required";
+    return 1;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  // particle order contract: nodes, stress particles, dummies (mat:961-1026)
+  for (size_t i = 0; i < n2; ++i) {
+    const int want = i < nn ? 2 : (i < nt ? 1 : 25);
+    if (s->itype[i] != want) {
+      h->err = "spsph_upload: itype does not follow the order nodes(2), stress particles(1), dummies(25)";
+      return 1;
+    }
+  }
+  h->h_itype.assign(s->itype, s->itype + n2);
+  cudaStream_t st = h->stream;
+  auto up = [&](void *d, const void *src, size_t bytes) {
+    if (!src) return cudaMemsetAsync(d, 0, bytes, st);
+    return cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st);
+  };
+  CUDA_TRY(up(h->x, s->x, 2 * n2 * 8));
+  CUDA_TRY(up(h->x00, s->x00 ? s->x00 : s->x, 2 * n2 * 8));
+  CUDA_TRY(up(h->rho, s->rho, n2 * 8));
+  CUDA_TRY(up(h->mass, s->mass, n2 * 8));
+  CUDA_TRY(up(h->hsml, s->hsml, n2 * 8));
+  std::vector<double> mor(n2);
+  double hmax = 0.0;
+  for (size_t i = 0; i < n2; ++i) {
+    mor[i] = s->mass[i] / s->rho[i];
+    hmax = std::fmax(hmax, s->hsml[i]);
+  }
+  CUDA_TRY(up(h->mor, mor.data(), n2 * 8));
+  h->cur = 0;
+  CUDA_TRY(up(h->V[0], s->vel, 2 * nt * 8));
+  CUDA_TRY(up(h->S[0], s->stress, 4 * nt * 8));
+  std::vector<double> e1(nt, 0.0);
+  if (s->internal_vars) {
+    h->h_internal_vars.assign(s->internal_vars, s->internal_vars + (size_t)SPSPH_NINT_VARS * nt);
+    for (size_t i = 0; i < nt; ++i) e1[i] = s->internal_vars[(size_t)SPSPH_NINT_VARS * i];
+  } else {
+    h->h_internal_vars.assign((size_t)SPSPH_NINT_VARS * nt, 0.0);
+  }
+  CUDA_TRY(up(h->epsp, e1.data(), nt * 8));
+  CUDA_TRY(up(h->fdp, s->f_drucker, nt * 8));
+  CUDA_TRY(up(h->displ, s->displ, 2 * nn * 8));
+  CUDA_TRY(up(h->x_10, s->x_10 ? s->x_10 : s->x, 2 * nn * 8));
+  CUDA_TRY(up(h->disp_10, s->disp_10, nn * 8));
+  CUDA_TRY(up(h->wallpos, s->wall_position, n2 * 4));
+  CUDA_TRY(up(h->horiz, s->horizontal_or_not, n2 * 4));
+  CUDA_TRY(up(h->n_int, s->n_int, nn * 4));
+  CUDA_TRY(up(h->bc_int, s->bc_int, nn * 4));
+  CUDA_TRY(up(h->if_out, s->if_out_domain, n2 * 4));
+  CUDA_TRY(up(h->bc_or_not, s->bc_or_not, nt * 4));
+  CUDA_TRY(up(h->bc_info, s->bc_info, 8 * nt * 4));
+  CUDA_TRY(cudaStreamSynchronize(st));  // host staging vectors go out of scope
+  // cell-table capacity: the in-domain bounding box can never exceed the control domain (main:1187-1192)
+  if (!h->cell_cnt) {
+    if (!(hmax > 0.0)) {
+      h->err = "spsph_upload: hsml must be positive";
+      return 1;
+    }
+    double nc = 1.0;
+    for (int d = 0; d < 2; ++d) {
+      const double len = p.xmax_domain[d] - p.xmin_domain[d];
+      nc *= std::floor(len / (2 * hmax)) + 2.0;
+    }
+    const double cap_max = 400e6;
+    if (!(nc > 0) || nc > cap_max) nc = cap_max;
+    h->cell_capacity = (int)nc;
+    h->cell_stride = h->cell_capacity + 8;
+    if (dalloc(h, &h->cell_cnt, 3 * (size_t)h->cell_stride)) return 1;
+    if (dalloc(h, &h->cell_start, 3 * (size_t)h->cell_stride)) return 1;
+    if (dalloc(h, &h->cell_fill, 3 * (size_t)h->cell_stride)) return 1;
+  }
+  h->m_pairs = 0;
+  h->uploaded = true;
+  return 0;
+}
+
+int spsph_step(spsph_handle *h, int32_t itimestep_sph, double time_sph, double dt_sph) {
+  if (!h) return 1;
+  CUDA_TRY(cudaSetDevice(h->device));
+  return step_impl(h, itimestep_sph, time_sph, dt_sph);
+}
+
+int spsph_run(spsph_handle *h, int32_t first_itimestep, double time_sph, double dt_sph, int32_t nsteps,
+              double *time_sph_out) {
+  if (!h) return 1;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const long long l0 = h->launches;
+  CUDA_TRY(cudaEventRecord(h->ev0, h->stream));
+  for (int k = 0; k < nsteps; ++k) {
+    if (step_impl(h, first_itimestep + k, time_sph, dt_sph)) return 1;
+    time_sph = time_sph + dt_sph;  // 1_SPH_2018.f90:174
+  }
+  CUDA_TRY(cudaEventRecord(h->ev1, h->stream));
+  CUDA_TRY(cudaEventSynchronize(h->ev1));
+  CUDA_TRY(cudaEventElapsedTime(&h->last_ms, h->ev0, h->ev1));
+  h->last_launches = h->launches - l0;
+  if (time_sph_out) *time_sph_out = time_sph;
+  return 0;
+}
+
+int spsph_last_run_ms(spsph_handle *h, float *ms, int64_t *kernel_launches) {
+  if (!h) return 1;
+  if (ms) *ms = h->last_ms;
+  if (kernel_launches) *kernel_launches = h->last_launches;
+  return 0;
+}
+
+int spsph_sync(spsph_handle *h) {
+  if (!h) return 1;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int spsph_download(spsph_handle *h, const spsph_state *s) {
+  if (!h || !s) return 1;
+  const spsph_params &p = h->hp;
+  const size_t n2 = (size_t)p.ntotal2, nt = (size_t)p.ntotal, nn = (size_t)p.nnode;
+  CUDA_TRY(cudaSetDevice(h->device));
+  cudaStream_t st = h->stream;
+  auto down = [&](void *dst, const void *src, size_t bytes) {
+    if (!dst) return cudaSuccess;
+    return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
+  };
+  CUDA_TRY(down(s->x, h->x, 2 * n2 * 8));
+  if (s->vel) {  // dummy particles carry no velocity/stress on the device (zero, as after main:690)
+    std::memset(s->vel, 0, 2 * n2 * 8);
+    CUDA_TRY(down(s->vel, h->V[h->cur], 2 * nt * 8));
+  }
+  if (s->stress) {
+    std::memset(s->stress, 0, 4 * n2 * 8);
+    CUDA_TRY(down(s->stress, h->S[h->cur], 4 * nt * 8));
+  }
+  CUDA_TRY(down(s->rho, h->rho, n2 * 8));
+  CUDA_TRY(down(s->mass, h->mass, n2 * 8));
+  CUDA_TRY(down(s->hsml, h->hsml, n2 * 8));
+  std::vector<double> e1;
+  if (s->internal_vars) {
+    e1.resize(nt);
+    CUDA_TRY(cudaMemcpyAsync(e1.data(), h->epsp, nt * 8, cudaMemcpyDeviceToHost, st));
+  }
+  CUDA_TRY(down(s->f_drucker, h->fdp, nt * 8));
+  CUDA_TRY(down(s->x00, h->x00, 2 * n2 * 8));
+  CUDA_TRY(down(s->displ, h->displ, 2 * nn * 8));
+  CUDA_TRY(down(s->x_10, h->x_10, 2 * nn * 8));
+  CUDA_TRY(down(s->disp_10, h->disp_10, nn * 8));
+  CUDA_TRY(down(s->n_int, h->n_int, nn * 4));
+  CUDA_TRY(down(s->bc_int, h->bc_int, nn * 4));
+  CUDA_TRY(down(s->if_out_domain, h->if_out, n2 * 4));
+  CUDA_TRY(down(s->bc_or_not, h->bc_or_not, nt * 4));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (s->itype) std::memcpy(s->itype, h->h_itype.data(), n2 * sizeof(int32_t));
+  if (s->internal_vars) {
+    std::memcpy(s->internal_vars, h->h_internal_vars.data(), (size_t)SPSPH_NINT_VARS * nt * 8);
+    for (size_t i = 0; i < nt; ++i) s->internal_vars[(size_t)SPSPH_NINT_VARS * i] = e1[i];
+  }
+  return 0;
+}
+
+int spsph_pair_stats(spsph_handle *h, int64_t *npairs, int32_t *maxiac, int32_t *miniac, int32_t *noiac) {
+  if (!h) return 1;
+  CUDA_TRY(cudaSetDevice(h->device));
+  const int init[4] = {0, 1000, 0, 0};
+  CUDA_TRY(cudaMemcpyAsync(h->stats_d, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
+  k_pair_stats<<<148, 256, 0, h->stream>>>(h->M, h->nall, h->stats_d);
+  int out[4];
+  CUDA_TRY(cudaMemcpyAsync(out, h->stats_d, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (npairs) *npairs = h->last_n_pairs;
+  if (maxiac) *maxiac = out[0];
+  if (miniac) *miniac = out[1];
+  if (noiac) *noiac = out[2];
+  return 0;
+}
+
+int spsph_pairs(spsph_handle *h, int64_t *npairs, int32_t *pair_i, int32_t *pair_j, int32_t *pint_type, float *w,
+                float *dwdx, float *dwdy) {
+  if (!h) return 1;
+  const long long n = h->last_n_pairs;
+  if (npairs) *npairs = n;
+  if (!pair_i) return 0;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int *d_i = nullptr, *d_j = nullptr, *d_t = nullptr;
+  float *d_w = nullptr, *d_x = nullptr, *d_y = nullptr;
+  const size_t b = (size_t)(n > 0 ? n : 1) * 4;
+  CUDA_TRY(cudaMalloc((void **)&d_i, b));
+  CUDA_TRY(cudaMalloc((void **)&d_j, b));
+  CUDA_TRY(cudaMalloc((void **)&d_t, b));
+  CUDA_TRY(cudaMalloc((void **)&d_w, b));
+  CUDA_TRY(cudaMalloc((void **)&d_x, b));
+  CUDA_TRY(cudaMalloc((void **)&d_y, b));
+  const int T = h->M.total();
+  // NB: valid until the next spsph_step (positions in the sorted arrays are those of the last search)
+  k_export_pairs<<<(T + 127) / 128, 128, 0, h->stream>>>(h->P, h->M, h->G, sort_arrays(h), h->base_u, n,
+                                                         h->last_m_before, d_i, d_j, d_t, d_w, d_x, d_y);
+  CUDA_TRY(cudaMemcpyAsync(pair_i, d_i, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(pair_j, d_j, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(pint_type, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(w, d_w, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(dwdx, d_x, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaMemcpyAsync(dwdy, d_y, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  cudaFree(d_i);
+  cudaFree(d_j);
+  cudaFree(d_t);
+  cudaFree(d_w);
+  cudaFree(d_x);
+  cudaFree(d_y);
+  return 0;
+}
+
+int spsph_destroy(spsph_handle *h) {
+  if (!h) return 0;
+  if (h->stream) {
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+  }
+  for (void *q : h->allocs) cudaFree(q);
+  cudaFree(h->L.idx0);
+  cudaFree(h->L.w0);
+  cudaFree(h->L.gx0);
+  cudaFree(h->L.gy0);
+  cudaFree(h->L.idxC);
+  cudaFree(h->L.wC);
+  cudaFree(h->L.gxC);
+  cudaFree(h->L.gyC);
+  cudaFree(h->L.idxD);
+  cudaFree(h->L.wD);
+  if (h->status_h) cudaFreeHost(h->status_h);
+  if (h->ev0) cudaEventDestroy(h->ev0);
+  if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete h;
+  return 0;
+}
+
+}  // extern "C"

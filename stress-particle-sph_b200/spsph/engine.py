@@ -1,0 +1,120 @@
+"""Device engine: ctypes binding of the C-ABI in include/spsph.h (libspsph_cuda.so).
+
+Engine mirrors the reference driver's three call sites (1_SPH_2018.f90:132,173,156): upload after set-up,
+step == time_integration, download before the writers. No CPU fallback: without the CUDA library or a GPU
+the constructor raises.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import _abi
+
+_PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CUDA_SO = os.path.join(_PKG, "libspsph_cuda.so")
+_lib = None
+
+
+def cuda_lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(_CUDA_SO):
+            raise RuntimeError(f"{_CUDA_SO} is missing: the CUDA extension must be built (python __graft_entry__.py); "
+                               "there is no CPU fallback")
+        L = C.CDLL(_CUDA_SO)
+        H = C.c_void_p
+        L.spsph_create.argtypes = [C.POINTER(H), C.POINTER(_abi.Params), C.c_int]
+        L.spsph_upload.argtypes = [H, C.POINTER(_abi.State)]
+        L.spsph_step.argtypes = [H, C.c_int32, C.c_double, C.c_double]
+        L.spsph_run.argtypes = [H, C.c_int32, C.c_double, C.c_double, C.c_int32, C.POINTER(C.c_double)]
+        L.spsph_download.argtypes = [H, C.POINTER(_abi.State)]
+        L.spsph_pair_stats.argtypes = [H, C.POINTER(C.c_int64)] + [C.POINTER(C.c_int32)] * 3
+        L.spsph_pairs.argtypes = [H, C.POINTER(C.c_int64)] + [C.c_void_p] * 6
+        L.spsph_last_run_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
+        L.spsph_sync.argtypes = [H]
+        L.spsph_destroy.argtypes = [H]
+        L.spsph_last_error.restype = C.c_char_p
+        L.spsph_last_error.argtypes = [H]
+        L.spsph_version.restype = C.c_char_p
+        _lib = L
+    return _lib
+
+
+EXPORTS = ["spsph_create", "spsph_upload", "spsph_step", "spsph_run", "spsph_download", "spsph_pair_stats",
+           "spsph_pairs", "spsph_last_run_ms", "spsph_sync", "spsph_destroy", "spsph_last_error", "spsph_version"]
+
+
+class Engine:
+    def __init__(self, problem, device=0, upload=True):
+        self.L = cuda_lib()
+        self.p = _abi.copy_params(problem.params)
+        self.h = C.c_void_p()
+        rc = self.L.spsph_create(C.byref(self.h), C.byref(self.p), device)
+        if rc:
+            msg = self.L.spsph_last_error(self.h).decode() if self.h else "spsph_create failed"
+            if self.h:
+                self.L.spsph_destroy(self.h)
+                self.h = None
+            raise RuntimeError(msg)
+        if upload:
+            self.upload(problem.arrays)
+
+    def _chk(self, rc):
+        if rc:
+            raise RuntimeError(self.L.spsph_last_error(self.h).decode())
+
+    def upload(self, arrays):
+        st = _abi.state_from_arrays(arrays)
+        self._chk(self.L.spsph_upload(self.h, C.byref(st)))
+
+    def step(self, itimestep, time_sph, dt):
+        self._chk(self.L.spsph_step(self.h, itimestep, time_sph, dt))
+
+    def run(self, first_itimestep, time_sph, dt, nsteps):
+        t = C.c_double()
+        self._chk(self.L.spsph_run(self.h, first_itimestep, time_sph, dt, nsteps, C.byref(t)))
+        return t.value
+
+    def last_run(self):
+        ms, n = C.c_float(), C.c_int64()
+        self.L.spsph_last_run_ms(self.h, C.byref(ms), C.byref(n))
+        return ms.value, n.value
+
+    def sync(self):
+        self._chk(self.L.spsph_sync(self.h))
+
+    def download(self, arrays=None):
+        if arrays is None:
+            st, arrays = _abi.alloc_state(self.p)
+        else:
+            st = _abi.state_from_arrays(arrays)
+        self._chk(self.L.spsph_download(self.h, C.byref(st)))
+        return arrays
+
+    def pair_stats(self):
+        n = C.c_int64()
+        a, b, c = C.c_int32(), C.c_int32(), C.c_int32()
+        self._chk(self.L.spsph_pair_stats(self.h, n, a, b, c))
+        return dict(npairs=n.value, maxiac=a.value, miniac=b.value, noiac=c.value)
+
+    def pairs(self):
+        n = C.c_int64()
+        self._chk(self.L.spsph_pairs(self.h, C.byref(n), None, None, None, None, None, None))
+        k = n.value
+        out = dict(pair_i=np.zeros(k, np.int32), pair_j=np.zeros(k, np.int32), pint_type=np.zeros(k, np.int32),
+                   w=np.zeros(k, np.float32), dwdx=np.zeros(k, np.float32), dwdy=np.zeros(k, np.float32))
+        self._chk(self.L.spsph_pairs(self.h, C.byref(n), *[out[f].ctypes.data for f in
+                                                            ("pair_i", "pair_j", "pint_type", "w", "dwdx", "dwdy")]))
+        return out
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.L.spsph_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -1,0 +1,124 @@
+"""GPU parity tests: the CUDA path (through the C-ABI) against the CPU oracle on identical inputs.
+
+Bar (BASELINE.json north_star): neighbour pair sets bit-exact; x, vel, stress within 1e-9 relative L-inf
+after 100 steps. The engine is built to reproduce the oracle's arithmetic exactly (same operation order, no
+FMA contraction), so these tests assert *bitwise* equality of the fp64 state; REL_TOL documents the
+contractual tolerance and is what a failure is measured against in the message.
+"""
+import numpy as np
+import pytest
+
+REL_TOL = 1e-9  # north_star tolerance (relative L-inf after 100 steps)
+
+pytestmark = pytest.mark.gpu
+
+STATE_KEYS = ("x", "vel", "stress", "internal_vars", "f_drucker", "displ", "x_10", "disp_10", "n_int", "bc_int",
+              "if_out_domain")
+
+
+def _load(deck_dir, kind, **kw):
+    import spsph
+    variant = {"refined_bui_spec": "bui", "wide_slope_spec": "vs"}.get(kind, kind)
+    return spsph.load(deck_dir(kind, **kw), variant)
+
+
+def _compare(a, b, nt, label):
+    for k in STATE_KEYS:
+        x, y = a[k], b[k]
+        if k in ("x", "vel", "stress"):
+            x, y = x[:nt], y[:nt]  # dummy-particle scratch values are not part of the observable state
+        if not np.array_equal(x, y):
+            scale = max(np.abs(y).max(), 1e-300)
+            rel = np.abs(x.astype(np.float64) - y.astype(np.float64)).max() / scale
+            bad = int((x != y).sum())
+            raise AssertionError(f"{label}: {k} differs from the oracle in {bad} entries, rel L-inf = {rel:.3e} "
+                                 f"(tolerance {REL_TOL:g})")
+
+
+def _pairs_equal(pa, pb, label):
+    assert len(pa["pair_i"]) == len(pb["pair_i"]), f"{label}: pair count {len(pa['pair_i'])} vs {len(pb['pair_i'])}"
+    for f in ("pair_i", "pair_j", "pint_type"):
+        assert np.array_equal(pa[f], pb[f]), f"{label}: {f} differs"
+    for f in ("w", "dwdx", "dwdy"):  # fp32 weights must be bit-identical
+        assert np.array_equal(pa[f].view(np.uint32), pb[f].view(np.uint32)), f"{label}: {f} differs bitwise"
+
+
+@pytest.mark.parametrize("kind", ["bui", "vs", "sl"])
+def test_pairs_bit_exact_first_steps(deck_dir, kind):
+    """ordered pair list (traversal order, orientation, types, fp32 weights) for steps 1..3"""
+    import spsph
+    from oracle_binding import Oracle
+    prob = _load(deck_dir, kind)
+    dt = prob.blocks[0]["dt"]
+    eng, orc = spsph.Engine(prob), Oracle(prob)
+    t = 0.0
+    for it in (1, 2, 3):
+        eng.step(it, t, dt)
+        orc.step(it, t, dt)
+        _pairs_equal(eng.pairs(), orc.pairs(), f"{kind} step {it}")
+        assert eng.pair_stats() == orc.pair_stats()
+        t = t + dt
+    _compare(eng.download(), orc.download(), prob.params.ntotal, f"{kind} after 3 steps")
+
+
+@pytest.mark.parametrize("kind,nsteps", [("bui", 100), ("vs", 100), ("sl", 100)])
+def test_state_after_100_steps(deck_dir, kind, nsteps):
+    import spsph
+    from oracle_binding import Oracle
+    prob = _load(deck_dir, kind)
+    dt = prob.blocks[0]["dt"]
+    eng, orc = spsph.Engine(prob), Oracle(prob)
+    ta = eng.run(1, 0.0, dt, nsteps)
+    tb = orc.run(1, 0.0, dt, nsteps)
+    assert ta == tb
+    _compare(eng.download(), orc.download(), prob.params.ntotal, f"{kind} after {nsteps} steps")
+    _pairs_equal(eng.pairs(), orc.pairs(), f"{kind} step {nsteps}")
+
+
+def test_bui_long_run_with_list_growth(deck_dir):
+    """600 steps of the Bui column: the pair count passes its previous maximum many times, which exercises
+    the reference's list-growth traversal rule in the fp32 artificial-viscosity sums."""
+    import spsph
+    from oracle_binding import Oracle
+    prob = _load(deck_dir, "bui")
+    dt = prob.blocks[0]["dt"]
+    eng, orc = spsph.Engine(prob), Oracle(prob)
+    t = 0.0
+    grown = 0
+    last = 0
+    for chunk in range(6):
+        t1 = eng.run(1 + 100 * chunk, t, dt, 100)
+        t2 = orc.run(1 + 100 * chunk, t, dt, 100)
+        assert t1 == t2
+        t = t1
+        _compare(eng.download(), orc.download(), prob.params.ntotal, f"bui after {100 * (chunk + 1)} steps")
+        n = orc.pair_stats()["npairs"]
+        grown += n > last
+        last = max(last, n)
+    assert grown >= 2
+
+
+def test_restart_from_download(deck_dir):
+    """download -> upload into a fresh engine reproduces the uninterrupted run except for the list-capacity
+    history (m_pairs), so only a forward-order step is compared: VS has a constant pair count."""
+    import spsph
+    prob = _load(deck_dir, "vs")
+    dt = prob.blocks[0]["dt"]
+    e1 = spsph.Engine(prob)
+    t = e1.run(1, 0.0, dt, 20)
+    mid = e1.download()
+    t_end = e1.run(21, t, dt, 20)
+    ref = e1.download()
+    p2 = prob.copy()
+    for k in mid:
+        p2.arrays[k] = mid[k]
+    for k in ("rho", "mass", "hsml", "itype", "wall_position", "horizontal_or_not", "bc_info"):
+        p2.arrays[k] = prob.arrays[k]
+    e2 = spsph.Engine(p2)
+    assert e2.run(21, t, dt, 20) == t_end
+    got = e2.download()
+    nt = prob.params.ntotal
+    for k in ("vel", "stress", "displ"):
+        # step 21 of the restarted run walks its (new) list reversed; fp64 sums reorder -> tolerance, not bits
+        scale = np.abs(ref[k][:nt]).max()
+        assert np.abs(got[k][:nt] - ref[k][:nt]).max() <= 1e-9 * scale
