@@ -19,6 +19,7 @@ struct DevParams {
   int no_bcs, bc_nloop;  // bc_nloop: Normal_BCs loop bound (ntotal or nnode), mat:1683
   int sp_sph, inside_approach, vel_vector, shift_update;
   int adapt;  // ncrit == 12
+  int track_nint;  // n_int is only refreshed by artificial_viscosity / XSPH_update / isolated_nodes
   double pi, D11, D12, D22, D33, D41, D42;
   double alpha, beta, damping, dx, r_x, r_y, disp_tol, ae_thr;
   double props[20];

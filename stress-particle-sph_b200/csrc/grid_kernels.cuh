@@ -531,7 +531,7 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
   const int id = S.order[sp][k];
   const int c = S.cell[sp][k];
   const int cnt0 = n0[t], cnt1 = n1[t];
-  if (sp == SP_NODE) n_int[id] = (float)cnt1;  // node-node interaction count (main:870-871 / 221-222)
+  if (sp == SP_NODE && P.track_nint) n_int[id] = (float)cnt1;  // node-node interaction count (main:870-871 / 221-222)
   if (c < 0) {
     if (sp == SP_NODE) bc_int[id] = 0;
     return;

@@ -417,6 +417,8 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   P.vel_vector = p->vel_vector;
   P.shift_update = p->shift_update > 0 ? p->shift_update : 1;
   P.adapt = (p->ncrit == 12) ? 1 : 0;
+  // main:843 (artificial_viscosity), main:203 (XSPH_update), main:347/384 (isolated_nodes via shift_stress_points)
+  P.track_nint = ((p->alpha > 0 || p->beta > 0) || (p->update_x && (p->xsph || (p->sp_sph && !p->inside_approach)))) ? 1 : 0;
   P.pi = p->pi;
   P.D11 = p->D11;
   P.D12 = p->D12;
