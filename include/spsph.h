@@ -116,6 +116,10 @@ int spsph_pairs(spsph_handle *h, int64_t *npairs, int32_t *pair_i, int32_t *pair
 /* device timing helpers for the bench: elapsed GPU ms of the last spsph_run (CUDA events on
  * the engine's stream) and number of kernels launched by it. */
 int spsph_last_run_ms(spsph_handle *h, float *ms, int64_t *kernel_launches);
+/* optional per-kernel timing: enable, run some steps, then read (total_ms, launches) for kid = 0,1,... until
+ * the call returns non-zero. Times are CUDA-event intervals on the engine's stream. */
+int spsph_profile(spsph_handle *h, int enable);
+int spsph_profile_get(spsph_handle *h, int kid, const char **name, double *total_ms, int64_t *launches);
 int spsph_sync(spsph_handle *h);
 int spsph_destroy(spsph_handle *h);
 const char *spsph_last_error(spsph_handle *h);

@@ -73,7 +73,23 @@ struct spsph_handle {
   long long last_m_before = 0;
   float last_ms = 0.f;
   long long last_launches = 0, launches = 0;
+
+  // optional per-kernel timing (CUDA events on the engine stream between launches)
+  bool profiling = false;
+  std::vector<cudaEvent_t> ev_pool;
+  std::vector<int> ev_kid;
+  size_t ev_used = 0;
+  double prof_ms[32] = {0};
+  long long prof_n[32] = {0};
 };
+
+enum KernelId {
+  KID_BBOX = 0, KID_GRID, KID_ZERO, KID_CELLID, KID_SCAN, KID_SCATTER, KID_RANK, KID_COUNT, KID_STATUS, KID_THRESH,
+  KID_FILL, KID_RKBEGIN, KID_SWEEPA, KID_SWEEPB, KID_MOVE, KID_SHIFT, KID_N
+};
+static const char *kKernelNames[KID_N] = {"k_domain_bbox", "k_grid_params", "k_zero_cells", "k_cell_id", "k_scan_*",
+                                          "k_scatter", "k_rank", "k_count", "k_status", "k_growth_threshold", "k_fill",
+                                          "k_rk_begin", "k_sweep_a", "k_sweep_b", "k_move", "k_shift"};
 
 namespace {
 
@@ -88,6 +104,37 @@ int dalloc(spsph_handle *h, T **p, size_t n) {
 }
 
 int round_up(int a, int b) { return ((a + b - 1) / b) * b; }
+
+// bookkeeping after every kernel launch: launch counter (+ an event when profiling)
+void mark(spsph_handle *h, int kid, int n = 1) {
+  h->launches += n;
+  if (!h->profiling) return;
+  if (h->ev_used == h->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    h->ev_pool.push_back(e);
+    h->ev_kid.push_back(0);
+  }
+  h->ev_kid[h->ev_used] = kid;
+  cudaEventRecord(h->ev_pool[h->ev_used], h->stream);
+  ++h->ev_used;
+}
+// fold the recorded events into per-kernel totals (interval since the previous event on the stream)
+void prof_collect(spsph_handle *h) {
+  if (!h->profiling || h->ev_used < 2) {
+    h->ev_used = 0;
+    return;
+  }
+  cudaEventSynchronize(h->ev_pool[h->ev_used - 1]);
+  for (size_t i = 1; i < h->ev_used; ++i) {
+    if (h->ev_kid[i] < 0) continue;
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, h->ev_pool[i - 1], h->ev_pool[i]);
+    h->prof_ms[h->ev_kid[i]] += ms;
+    h->prof_n[h->ev_kid[i]] += 1;
+  }
+  h->ev_used = 0;
+}
 
 SortArrays sort_arrays(spsph_handle *h) {
   SortArrays S;
@@ -224,7 +271,7 @@ void launch_scan(spsph_handle *h, const int *in, int *out, int rows, int stride,
   k_scan_reduce<<<g, SCAN_THREADS, 0, h->stream>>>(in, stride, n_ptr, n_add, h->scan_bsum);
   k_scan_sums<<<rows, SCAN_THREADS, 0, h->stream>>>(h->scan_bsum, totals);
   k_scan_apply<<<g, SCAN_THREADS, 0, h->stream>>>(in, out, stride, n_ptr, n_add, h->scan_bsum);
-  h->launches += 3;
+  mark(h, KID_SCAN, 3);
 }
 
 // neighbour search up to and including the list fill; leaves the pair totals in h->status_h
@@ -233,28 +280,36 @@ int build_neighbours(spsph_handle *h) {
   const int n2 = P.ntotal2;
   const int TB = 256;
   cudaStream_t s = h->stream;
+  if (h->profiling) {  // anchor event so that the first kernel's interval is well defined
+    mark(h, -1, 0);
+  }
   k_domain_bbox<<<h->bbox_blocks, TB, 0, s>>>(P, h->x, h->hsml, h->if_out, h->bbox_partial);
+  mark(h, KID_BBOX);
   k_grid_params<<<1, 32, 0, s>>>(h->bbox_blocks, h->bbox_partial, h->G, h->cell_capacity);
+  mark(h, KID_GRID);
   k_zero_cells<<<296, TB, 0, s>>>(h->G, h->cell_cnt, h->cell_stride);
   k_zero_cells<<<296, TB, 0, s>>>(h->G, h->cell_fill, h->cell_stride);
   CUDA_TRY(cudaMemsetAsync(h->nout, 0, 3 * sizeof(int), s));
   CUDA_TRY(cudaMemsetAsync(h->nfwd_u, 0, (size_t)n2 * sizeof(int), s));
+  mark(h, KID_ZERO, 2);
   k_cell_id<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->G, h->x, h->if_out, h->which_cell, h->cell_cnt, h->cell_stride,
                                                h->nout);
-  h->launches += 5;
+  mark(h, KID_CELLID);
   launch_scan(h, h->cell_cnt, h->cell_start, 3, h->cell_stride, &h->G->ncell, 1, h->scan_totals + 4);
   k_scatter<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->which_cell, h->cell_start, h->cell_fill, h->cell_stride, h->tmp_ids);
+  mark(h, KID_SCATTER);
   k_rank<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->G, h->x, h->hsml, h->which_cell, h->cell_start, h->cell_stride,
                                             h->tmp_ids, h->order, h->spos, h->sh, h->scell, h->pos_of);
+  mark(h, KID_RANK);
   const SortArrays S = sort_arrays(h);
   const int T = h->M.total();
   k_count<<<(T + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->nfwd_u, h->nall, h->wslice,
                                            h->wslice + h->nslices, h->wslice + 2 * h->nslices);
-  h->launches += 3;
+  mark(h, KID_COUNT);
   launch_scan(h, h->wslice, h->oslice, 3, h->nslices, nullptr, h->nslices, h->scan_totals);
   launch_scan(h, h->nfwd_u, h->base_u, 1, n2, nullptr, n2, h->scan_totals + 3);
   k_status<<<1, 32, 0, s>>>(h->G, h->scan_totals, h->status_d);
-  h->launches += 1;
+  mark(h, KID_STATUS);
   CUDA_TRY(cudaMemcpyAsync(h->status_h, h->status_d, sizeof(StepStatus), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   const StepStatus st = *h->status_h;
@@ -276,14 +331,15 @@ int build_neighbours(spsph_handle *h) {
   GrowthRule gr{0, 0, 0};
   if (st.n_pairs > h->m_pairs) gr.mode = (h->m_pairs == 0) ? 1 : 2;
   CUDA_TRY(cudaMemcpyAsync(h->growth, &gr, sizeof(gr), cudaMemcpyHostToDevice, s));
+  if (h->profiling) mark(h, -1, 0);  // do not charge the host round trip to the next kernel
   if (gr.mode == 2) {
     k_growth_threshold<<<1, 32, 0, s>>>(P, h->M, h->G, S, h->base_u, h->m_pairs, h->growth);
-    h->launches += 1;
+    mark(h, KID_THRESH);
   }
   if (st.n_pairs > h->m_pairs) h->m_pairs = st.n_pairs;
   const int TL = h->M.nnp + h->M.nsp;
   k_fill<<<(TL + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int, h->n_int);
-  h->launches += 1;
+  mark(h, KID_FILL);
   return 0;
 }
 
@@ -307,20 +363,21 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   // SPH_shift block, main:99-109
   if (p.sph_shift && itimestep > 1 && ((itimestep - 1) % p.shift_update == 0)) {
     k_sweep_a<true><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, st, cur, 1 - cur, adapt, 0, 1);
-    h->launches += 1;
+    mark(h, KID_SWEEPA);
     cur = 1 - cur;
     first_a = false;
   }
   // RK4, main:653-802
   const int A = 1 - cur, B = cur;  // rk_begin: cur -> A ; sweep A: A -> B ; sweep B: B -> A
   k_rk_begin<<<(P.ntotal + 255) / 256, 256, 0, s>>>(P, st, cur, A);
-  h->launches += 1;
+  mark(h, KID_RKBEGIN);
   const double f1rk[4] = {0., 0.5, 0.5, 1.0}, f2rk[4] = {1., 2., 2., 1.0};
   for (int stg = 0; stg < 4; ++stg) {
     if (first_a)
       k_sweep_a<true><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, st, A, B, adapt, bc, 0);
     else
       k_sweep_a<false><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, st, A, B, adapt, bc, 0);
+    mark(h, KID_SWEEPA);
     first_a = false;
     const int last = (stg == 3);
     const double f1n = last ? 0.0 : f1rk[stg + 1];
@@ -328,20 +385,22 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
       k_sweep_b<true><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, h->n1, st, B, A, f1n, f2rk[stg], last);
     else
       k_sweep_b<false><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, h->n1, st, B, A, f1n, f2rk[stg], last);
-    h->launches += 2;
+    mark(h, KID_SWEEPB);
   }
   // final stress_point_update + adapt_stress2 + BCs, main:130-135
   k_sweep_a<false><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, st, A, B, adapt, bc, 1);
+  mark(h, KID_SWEEPA);
   cur = B;
   h->cur = cur;
   // positions, main:140-182
   k_move<<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n1, st, cur, h->x, h->x00, h->displ);
-  h->launches += 2;
+  mark(h, KID_MOVE);
   if (p.update_x && p.sp_sph && !p.inside_approach) {
     k_shift<<<(P.nnode + 255) / 256, 256, 0, s>>>(P, h->V[cur], h->x, h->x_10, h->disp_10, h->bc_int, h->n_int);
-    h->launches += 1;
+    mark(h, KID_SHIFT);
   }
   CUDA_TRY(cudaGetLastError());
+  if (h->profiling) prof_collect(h);
   return 0;
 }
 
@@ -599,6 +658,25 @@ int spsph_last_run_ms(spsph_handle *h, float *ms, int64_t *kernel_launches) {
   return 0;
 }
 
+int spsph_profile(spsph_handle *h, int enable) {
+  if (!h) return 1;
+  h->profiling = enable != 0;
+  h->ev_used = 0;
+  for (int k = 0; k < 32; ++k) {
+    h->prof_ms[k] = 0.0;
+    h->prof_n[k] = 0;
+  }
+  return 0;
+}
+
+int spsph_profile_get(spsph_handle *h, int kid, const char **name, double *total_ms, int64_t *launches) {
+  if (!h || kid < 0 || kid >= KID_N) return 1;
+  if (name) *name = kKernelNames[kid];
+  if (total_ms) *total_ms = h->prof_ms[kid];
+  if (launches) *launches = h->prof_n[kid];
+  return 0;
+}
+
 int spsph_sync(spsph_handle *h) {
   if (!h) return 1;
   CUDA_TRY(cudaSetDevice(h->device));
@@ -710,6 +788,7 @@ int spsph_destroy(spsph_handle *h) {
     cudaStreamSynchronize(h->stream);
   }
   for (void *q : h->allocs) cudaFree(q);
+  for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   cudaFree(h->L.idx0);
   cudaFree(h->L.w0);
   cudaFree(h->L.gx0);

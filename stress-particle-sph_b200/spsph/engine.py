@@ -33,6 +33,8 @@ def cuda_lib():
         L.spsph_pairs.argtypes = [H, C.POINTER(C.c_int64)] + [C.c_void_p] * 6
         L.spsph_last_run_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
         L.spsph_sync.argtypes = [H]
+        L.spsph_profile.argtypes = [H, C.c_int]
+        L.spsph_profile_get.argtypes = [H, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.spsph_destroy.argtypes = [H]
         L.spsph_last_error.restype = C.c_char_p
         L.spsph_last_error.argtypes = [H]
@@ -42,7 +44,7 @@ def cuda_lib():
 
 
 EXPORTS = ["spsph_create", "spsph_upload", "spsph_step", "spsph_run", "spsph_download", "spsph_pair_stats",
-           "spsph_pairs", "spsph_last_run_ms", "spsph_sync", "spsph_destroy", "spsph_last_error", "spsph_version"]
+           "spsph_pairs", "spsph_last_run_ms", "spsph_sync", "spsph_profile", "spsph_profile_get", "spsph_destroy", "spsph_last_error", "spsph_version"]
 
 
 class Engine:
@@ -80,6 +82,21 @@ class Engine:
         ms, n = C.c_float(), C.c_int64()
         self.L.spsph_last_run_ms(self.h, C.byref(ms), C.byref(n))
         return ms.value, n.value
+
+    def profile(self, enable=True):
+        self._chk(self.L.spsph_profile(self.h, 1 if enable else 0))
+
+    def profile_get(self):
+        """{kernel name: (total_ms, launches)} accumulated since profile(True)"""
+        out = {}
+        kid = 0
+        while True:
+            name, ms, n = C.c_char_p(), C.c_double(), C.c_int64()
+            if self.L.spsph_profile_get(self.h, kid, C.byref(name), C.byref(ms), C.byref(n)):
+                break
+            out[name.value.decode()] = (ms.value, n.value)
+            kid += 1
+        return out
 
     def sync(self):
         self._chk(self.L.spsph_sync(self.h))
