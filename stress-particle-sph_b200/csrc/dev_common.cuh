@@ -42,6 +42,7 @@ struct GridInfo {
   int ndivx[2];
   int ncell;
   int overflow;  // 1 if ncell exceeds the allocated cell capacity
+  int uniform_h;  // all in-domain particles share one smoothing length (enables hoisted kernel constants)
   // raw reductions
   double rxmin[2], rxmax[2], rhmax;
   int nactive[3];  // in-domain particles per species

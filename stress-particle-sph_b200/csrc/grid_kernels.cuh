@@ -20,6 +20,7 @@ struct SortArrays {  // per species s in {node, stress, dummy}; species-sorted i
   const int *start[3];      // [ncell+1] first sorted index of each cell
   const int *order[3];      // [n_s] original 0-based particle id
   const double2 *pos[3];    // [n_s] positions
+  const float2 *upos[3];    // [n_s] positions in cell units relative to the grid origin (fp32 prefilter only)
   const double *h[3];       // [n_s] smoothing lengths
   const int *cell[3];       // [n_s] cell id (or -1 for out-of-domain particles parked at the end)
 };
@@ -61,8 +62,8 @@ __device__ __forceinline__ double warp_max(double v) {
 }
 
 __global__ void k_domain_bbox(DevParams P, const double *__restrict__ x, const double *__restrict__ hsml,
-                              int *__restrict__ if_out, double *__restrict__ partial /* [gridDim.x][5] */) {
-  double xmn = 1.e+10, ymn = 1.e+10, xmx = -1.e+10, ymx = -1.e+10, hmx = 0.0;
+                              int *__restrict__ if_out, double *__restrict__ partial /* [gridDim.x][6] */) {
+  double xmn = 1.e+10, ymn = 1.e+10, xmx = -1.e+10, ymx = -1.e+10, hmx = 0.0, hmn = 1.e+300;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.ntotal2; i += gridDim.x * blockDim.x) {
     const double2 p = ld2(x, i);
     int out = if_out[i];
@@ -78,14 +79,16 @@ __global__ void k_domain_bbox(DevParams P, const double *__restrict__ x, const d
       ymn = fmin(ymn, p.y);
       ymx = fmax(ymx, p.y);
       hmx = fmax(hmx, hsml[i]);
+      hmn = fmin(hmn, hsml[i]);
     }
   }
-  __shared__ double sh[5][32];
+  __shared__ double sh[6][32];
   xmn = warp_min(xmn);
   ymn = warp_min(ymn);
   xmx = warp_max(xmx);
   ymx = warp_max(ymx);
   hmx = warp_max(hmx);
+  hmn = warp_min(hmn);
   const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
   if (l == 0) {
     sh[0][w] = xmn;
@@ -93,6 +96,7 @@ __global__ void k_domain_bbox(DevParams P, const double *__restrict__ x, const d
     sh[2][w] = xmx;
     sh[3][w] = ymx;
     sh[4][w] = hmx;
+    sh[5][w] = hmn;
   }
   __syncthreads();
   if (w == 0) {
@@ -102,18 +106,21 @@ __global__ void k_domain_bbox(DevParams P, const double *__restrict__ x, const d
     xmx = l < nw ? sh[2][l] : -1.e+10;
     ymx = l < nw ? sh[3][l] : -1.e+10;
     hmx = l < nw ? sh[4][l] : 0.0;
+    hmn = l < nw ? sh[5][l] : 1.e+300;
     xmn = warp_min(xmn);
     ymn = warp_min(ymn);
     xmx = warp_max(xmx);
     ymx = warp_max(ymx);
     hmx = warp_max(hmx);
+    hmn = warp_min(hmn);
     if (l == 0) {
-      double *o = partial + 5 * blockIdx.x;
+      double *o = partial + 6 * blockIdx.x;
       o[0] = xmn;
       o[1] = ymn;
       o[2] = xmx;
       o[3] = ymx;
       o[4] = hmx;
+      o[5] = hmn;
     }
   }
 }
@@ -122,14 +129,15 @@ __global__ void k_domain_bbox(DevParams P, const double *__restrict__ x, const d
 __global__ void k_grid_params(int nblocks, const double *__restrict__ partial, GridInfo *__restrict__ G,
                               int cell_capacity) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double mn[2] = {1.e+10, 1.e+10}, mx[2] = {-1.e+10, -1.e+10}, hmx = 0.0;
+  double mn[2] = {1.e+10, 1.e+10}, mx[2] = {-1.e+10, -1.e+10}, hmx = 0.0, hmn = 1.e+300;
   for (int b = 0; b < nblocks; ++b) {
-    const double *o = partial + 5 * b;
+    const double *o = partial + 6 * b;
     mn[0] = fmin(mn[0], o[0]);
     mn[1] = fmin(mn[1], o[1]);
     mx[0] = fmax(mx[0], o[2]);
     mx[1] = fmax(mx[1], o[3]);
     hmx = fmax(hmx, o[4]);
+    hmn = fmin(hmn, o[5]);
   }
   for (int d = 0; d < 2; ++d) {
     double xmin = mn[d], xmax = mx[d];
@@ -147,6 +155,7 @@ __global__ void k_grid_params(int nblocks, const double *__restrict__ partial, G
     G->rxmax[d] = mx[d];
   }
   G->rhmax = hmx;
+  G->uniform_h = (hmn == hmx) ? 1 : 0;
   const long long nc = (long long)G->ndivx[0] * (long long)G->ndivx[1];
   G->overflow = (nc > (long long)cell_capacity || nc <= 0) ? 1 : 0;
   G->ncell = G->overflow ? 1 : (int)nc;
@@ -301,7 +310,8 @@ __global__ void k_rank(DevParams P, const GridInfo *__restrict__ G, const double
                        const double *__restrict__ hsml, const int *__restrict__ which_cell,
                        const int *__restrict__ start, int cell_stride, const int *__restrict__ tmp,
                        int *__restrict__ order, double2 *__restrict__ spos, double *__restrict__ sh,
-                       int *__restrict__ scell, int *__restrict__ pos_of /* [ntotal2] species-sorted index */) {
+                       int *__restrict__ scell, int *__restrict__ pos_of /* [ntotal2] species-sorted index */,
+                       float2 *__restrict__ supos) {
   // one thread per particle in original order
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.ntotal2) return;
@@ -319,7 +329,9 @@ __global__ void k_rank(DevParams P, const GridInfo *__restrict__ G, const double
     k = b + r;
   }
   order[row + k] = i;
-  spos[row + k] = ld2(x, i);
+  const double2 xi = ld2(x, i);
+  supos[row + k] = make_float2((float)((xi.x - G->xmin[0]) / G->deltx[0]), (float)((xi.y - G->xmin[1]) / G->deltx[1]));
+  spos[row + k] = xi;
   sh[row + k] = hsml[i];
   scell[row + k] = c < 0 ? -1 : c;
   pos_of[i] = k;
@@ -367,56 +379,177 @@ __device__ __forceinline__ bool pair_is_old(const GrowthRule &g, int u1, int u2)
   return (a < g.ua) || (a == g.ua && b <= g.ub);
 }
 
+// ---- exactly rounded division by a value whose correctly rounded reciprocal is known (Markstein): the
+// result equals IEEE a/b bit for bit (checked exhaustively against the hardware divide in
+// tests/test_oracle_cpu.py::test_fast_division_identity); used to hoist the per-pair divisions by h and r.
+__device__ __forceinline__ double div_rn(double a, double b, double rb) {
+  double q = a * rb;
+  double r = __fma_rn(-b, q, a);
+  q = __fma_rn(r, rb, q);
+  r = __fma_rn(-b, q, a);
+  return __fma_rn(r, rb, q);
+}
+
+struct KernelConsts {  // per-thread constants of `kernel` (main:1468-1492) for a fixed smoothing length h
+  double h, rh, hh, rhh, factor, f6, m63;
+};
+__device__ __forceinline__ KernelConsts kernel_consts(const DevParams &P, double h) {
+  KernelConsts K;
+  K.h = h;
+  K.rh = 1.0 / h;
+  K.hh = h * h;
+  K.rhh = 1.0 / K.hh;
+  K.factor = 15.e0 / (7.e0 * P.pi * h * h);
+  K.f6 = K.factor * 1.e0 / 6.e0;
+  K.m63 = -K.f6 * 3.;
+  return K;
+}
+// same values as sph_kernel(), bit for bit, for mhsml == K.h; GRAD = false skips the gradient
+template <bool GRAD>
+__device__ __forceinline__ void sph_kernel_fast(const KernelConsts &K, double r, double dx, double dy, double &w,
+                                                double &gx, double &gy) {
+  const double q = div_rn(r, K.h, K.rh);
+  w = 0.;
+  gx = 0.;
+  gy = 0.;
+  if (q >= 0 && q <= 1.e0) {
+    w = K.factor * ((double)(2.f / 3.f) - q * q + q * q * q * 0.5);
+    if (GRAD) {
+      const double t = div_rn(K.factor * (-2. + 1.5 * q), K.hh, K.rhh);
+      gx = t * dx;
+      gy = t * dy;
+    }
+  } else if (q > 1.e0 && q <= 2) {
+    const double t = 2. - q;
+    w = K.f6 * (t * t * t);
+    if (GRAD) {
+      const double u = div_rn(K.m63 * (t * t), K.h, K.rh);
+      const double rr = __drcp_rn(r);
+      gx = u * div_rn(dx, r, rr);
+      gy = u * div_rn(dy, r, rr);
+    }
+  }
+}
+
+// Acceptance test with a squared-distance prefilter: sqrt() only for candidates within 2e-15 (relative) of
+// the cut-off, where the reference's `sqrt(driac) < scale_k*mhsml` decides. Returns the squared distance.
+__device__ __forceinline__ bool pair_accept_fast(double scale_k, double2 pp, double hp, double2 pq, double hq,
+                                                 double &dx, double &dy, double &driac, double &mh) {
+  dx = pp.x - pq.x;
+  dy = pp.y - pq.y;
+  driac = dx * dx;
+  driac = driac + dy * dy;
+  mh = (hp + hq) / 2.;
+  const double c = scale_k * mh;
+  const double c2 = c * c;
+  if (driac < c2 * 0.999999999999998) return true;
+  if (driac > c2 * 1.000000000000002) return false;
+  return sqrt(driac) < c;
+}
+
+// fp32 prefilter in cell units: classifies a candidate as sure-accept (1), sure-reject (0) or undecided (2).
+// Only valid when all particles share one h (cut-off == scale_k*h) and the grid is small enough for fp32;
+// `lo`/`hi` bracket the squared cut-off by the fp32 coordinate error (see prefilter_bounds()).
+struct Prefilter {
+  int on;
+  float lo, hi;
+};
+__device__ __forceinline__ Prefilter prefilter_bounds(const DevParams &P, const GridInfo *G, double hp) {
+  Prefilter f;
+  const int nmax = max(G->ndivx[0], G->ndivx[1]);
+  // coordinate error <= nmax * 2^-23 per component after the fp32 rounding and the subtraction
+  const double eps = 8.0 * (double)nmax * 1.1920929e-07;
+  const double c = (double)P.scale_k * hp / G->deltx[0];  // cut-off in cell units (== 1 for skf = 1)
+  f.on = (G->uniform_h != 0 && eps < 0.05 * c && G->deltx[0] == G->deltx[1]) ? 1 : 0;
+  const double a = (c - eps) > 0 ? (c - eps) : 0.0, b = c + eps;
+  f.lo = (float)(a * a * 0.999);
+  f.hi = (float)(b * b * 1.001);
+  return f;
+}
+__device__ __forceinline__ int prefilter_test(const Prefilter &f, float2 up, float2 uq) {
+  const float du = up.x - uq.x, dv = up.y - uq.y;
+  const float d2 = __fmaf_rn(du, du, dv * dv);
+  return d2 > f.hi ? 0 : (d2 < f.lo ? 1 : 2);
+}
+
+// One row of the 3x3 stencil: the cells (cx-1..cx+1, jy) are consecutive cell ids, so each species' particles
+// of the whole row form ONE contiguous range of the species-sorted arrays.
+struct RowRange {
+  int ca, cb;  // first and last cell id of the row segment
+};
+__device__ __forceinline__ RowRange row_range(int ndx, int cx, int jy) {
+  return RowRange{jy * ndx + max(cx - 1, 0), jy * ndx + min(cx + 1, ndx - 1)};
+}
+
 // Count pass: per thread slot the lengths of its gather lists, its forward pair count (creation index)
-// and its total interaction count (countiac, main:1355-1356).
+// and its total interaction count (countiac, main:1355-1356). Order-independent, so rows are scanned as
+// merged ranges.
 __global__ void __launch_bounds__(128)
 k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, int *__restrict__ n0, int *__restrict__ n1,
         int *__restrict__ nfwd_u /* unified order */, int *__restrict__ nall, int *__restrict__ w0 /* slice widths */,
         int *__restrict__ wC, int *__restrict__ wD) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  int sp, k;
+  int sp = 0, k = 0;
   const bool live = (t < M.total()) && slot_decode(M, t, sp, k);
   int c0 = 0, c1 = 0, cf = 0, ca = 0;
   if (live) {
-    const int c = S.cell[sp][k];
+    const int *__restrict__ cellp = sp == 0 ? S.cell[0] : (sp == 1 ? S.cell[1] : S.cell[2]);
+    const int c = cellp[k];
     if (c >= 0) {
-      const double2 pp = S.pos[sp][k];
-      const double hp = S.h[sp][k];
+      const double2 *__restrict__ posp = sp == 0 ? S.pos[0] : (sp == 1 ? S.pos[1] : S.pos[2]);
+      const double *__restrict__ hpp = sp == 0 ? S.h[0] : (sp == 1 ? S.h[1] : S.h[2]);
+      const double2 pp = posp[k];
+      const double hp = hpp[k];
+      const bool uni = G->uniform_h != 0;
+      const double sk = (double)P.scale_k;
+      const Prefilter pf = prefilter_bounds(P, G, hp);
+      const float2 *__restrict__ uposp = sp == 0 ? S.upos[0] : (sp == 1 ? S.upos[1] : S.upos[2]);
+      const float2 up = uposp[k];
       const int ndx = G->ndivx[0], ndy = G->ndivx[1];
       const int cy = c / ndx, cx = c - cy * ndx;
-      for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy)
-        for (int jx = max(cx - 1, 0); jx <= min(cx + 1, ndx - 1); ++jx) {
-          const int cq = jy * ndx + jx;
+      for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy) {
+        const RowRange rr = row_range(ndx, cx, jy);
 #pragma unroll
-          for (int sq = 0; sq < 3; ++sq) {
-            const int b = S.start[sq][cq], e = S.start[sq][cq + 1];
-            for (int q = b; q < e; ++q) {
-              if (sq == sp && q == k) continue;
-              double dx, dy, r, mh;
-              if (!pair_accept(P, pp, hp, S.pos[sq][q], S.h[sq][q], dx, dy, r, mh)) continue;
-              ++ca;
-              const bool fwd = (cq > c) || (cq == c && (sq > sp || (sq == sp && q > k)));
-              cf += fwd ? 1 : 0;
-              if (sp == SP_DUMMY) continue;
-              if (sq == sp)
-                ++c1;
-              else
-                ++c0;  // node<->stress (type 1) and node/stress<->dummy (types 6, 9)
+        for (int sq = 0; sq < 3; ++sq) {
+          const int b = S.start[sq][rr.ca], e = S.start[sq][rr.cb + 1];
+          // forward partners (creation order): later row, or same row from the threshold index on
+          int fthr;
+          if (jy > cy)
+            fthr = b;
+          else if (jy < cy)
+            fthr = e;
+          else
+            fthr = (sq == sp) ? k + 1 : (sq > sp ? S.start[sq][c] : S.start[sq][c + 1]);
+          int acc = 0, accf = 0;
+          for (int q = b; q < e; ++q) {
+            if (sq == sp && q == k) continue;
+            int cls = 2;
+            if (pf.on) cls = prefilter_test(pf, up, S.upos[sq][q]);
+            if (cls == 0) continue;
+            if (cls == 2) {
+              double dx, dy, d2, mh;
+              if (!pair_accept_fast(sk, pp, hp, S.pos[sq][q], uni ? hp : S.h[sq][q], dx, dy, d2, mh)) continue;
             }
+            ++acc;
+            accf += (q >= fthr) ? 1 : 0;
+          }
+          ca += acc;
+          cf += accf;
+          if (sp != SP_DUMMY) {
+            if (sq == sp)
+              c1 += acc;
+            else
+              c0 += acc;  // node<->stress (type 1) and node/stress<->dummy (types 6, 9)
           }
         }
+      }
       nfwd_u[unified_slot(S, c, sp, k)] = cf;
     }
     nall[t] = ca;
   }
   if (t < M.nnp + M.nsp) {  // list-owning slots
-    if (live) {
-      n0[t] = c0;
-      n1[t] = c1;
-    } else {
-      n0[t] = 0;
-      n1[t] = 0;
-    }
+    n0[t] = live ? c0 : 0;
+    n1[t] = live ? c1 : 0;
     int m0 = c0, m1 = c1;
     for (int o = 16; o > 0; o >>= 1) {
       m0 = max(m0, __shfl_xor_sync(0xffffffffu, m0, o));
@@ -520,16 +653,28 @@ struct ListPtrs {
 };
 
 // Fill pass: writes every list entry at its traversal position.
-__global__ void __launch_bounds__(128)
+// Accepted candidates are first compacted into per-thread shared-memory queues (cheap, divergent scan), then
+// the kernel evaluation + stores run as dense loops with (nearly) all lanes active and row-aligned stores.
+constexpr int QCAP = 40;
+constexpr int FILL_THREADS = 128;
+
+__global__ void __launch_bounds__(FILL_THREADS)
 k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ n0,
        const int *__restrict__ n1, const GrowthRule *__restrict__ growth, ListPtrs L, int *__restrict__ bc_int,
        float *__restrict__ n_int) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  __shared__ int q0buf[QCAP][FILL_THREADS];  // cross-species partners (species in the top 2 bits)
+  __shared__ int q1buf[QCAP][FILL_THREADS];  // same-species partners
+  const int tid = threadIdx.x;
+  const int t = blockIdx.x * blockDim.x + tid;
   if (t >= M.nnp + M.nsp) return;
   int sp, k;
   if (!slot_decode(M, t, sp, k)) return;
-  const int id = S.order[sp][k];
-  const int c = S.cell[sp][k];
+  const int *__restrict__ orderp = sp == 0 ? S.order[0] : S.order[1];
+  const int *__restrict__ cellp = sp == 0 ? S.cell[0] : S.cell[1];
+  const double2 *__restrict__ posp = sp == 0 ? S.pos[0] : S.pos[1];
+  const double *__restrict__ hpp = sp == 0 ? S.h[0] : S.h[1];
+  const int id = orderp[k];
+  const int c = cellp[k];
   const int cnt0 = n0[t], cnt1 = n1[t];
   if (sp == SP_NODE && P.track_nint) n_int[id] = (float)cnt1;  // node-node interaction count (main:870-871 / 221-222)
   if (c < 0) {
@@ -540,84 +685,149 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
   const int lane = t & 31, sl = t / SLICE;
   const size_t o0 = (size_t)L.off0[sl] + lane;
   const size_t o1 = (size_t)(sp == SP_NODE ? L.offC[sl] : L.offD[sl]) + lane;
-  const double2 pp = S.pos[sp][k];
-  const double hp = S.h[sp][k];
+  const double2 pp = posp[k];
+  const double hp = hpp[k];
+  const bool uni = G->uniform_h != 0;
+  const double sk = (double)P.scale_k;
+  const KernelConsts K = kernel_consts(P, hp);
+  const Prefilter pf = prefilter_bounds(P, G, hp);
+  const float2 up = (sp == 0 ? S.upos[0] : S.upos[1])[k];
   const int ndx = G->ndivx[0], ndy = G->ndivx[1];
   const int cy = c / ndx, cx = c - cy * ndx;
-  const int up = unified_slot(S, c, sp, k);
   // number of "old" entries per list (prefix of the ascending order); only the split mode needs a pre-count
   int s0 = (gr.mode == 1) ? 0 : cnt0, s1 = (gr.mode == 1) ? 0 : cnt1;
-  if (gr.mode == 2 && up >= gr.ua) {
-    s0 = 0;
-    s1 = 0;
-    // partners at or before ua live in cells <= cell(ua); cheap conservative test on the first stencil cell
-    const int cfirst = max(cy - 1, 0) * ndx + max(cx - 1, 0);
-    if (unified_slot(S, cfirst, 0, S.start[0][cfirst]) <= gr.ua) {
-      for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy)
-        for (int jx = max(cx - 1, 0); jx <= min(cx + 1, ndx - 1); ++jx) {
-          const int cq = jy * ndx + jx;
-          for (int sq = 0; sq < 3; ++sq) {
-            const int b = S.start[sq][cq], e = S.start[sq][cq + 1];
-            for (int q = b; q < e; ++q) {
-              if (sq == sp && q == k) continue;
-              double dx, dy, r, mh;
-              if (!pair_accept(P, pp, hp, S.pos[sq][q], S.h[sq][q], dx, dy, r, mh)) continue;
-              if (!pair_is_old(gr, up, unified_slot(S, cq, sq, q))) continue;
-              if (sq == sp)
-                ++s1;
-              else
-                ++s0;
+  if (gr.mode == 2) {
+    const int up = unified_slot(S, c, sp, k);
+    if (up >= gr.ua) {
+      s0 = 0;
+      s1 = 0;
+      // partners at or before ua live in cells <= cell(ua); cheap conservative test on the first stencil cell
+      const int cfirst = max(cy - 1, 0) * ndx + max(cx - 1, 0);
+      if (unified_slot(S, cfirst, 0, S.start[0][cfirst]) <= gr.ua) {
+        for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy)
+          for (int jx = max(cx - 1, 0); jx <= min(cx + 1, ndx - 1); ++jx) {
+            const int cq = jy * ndx + jx;
+            for (int sq = 0; sq < 3; ++sq) {
+              const int b = S.start[sq][cq], e = S.start[sq][cq + 1];
+              for (int q = b; q < e; ++q) {
+                if (sq == sp && q == k) continue;
+                double dx, dy, r, mh;
+                if (!pair_accept(P, pp, hp, S.pos[sq][q], S.h[sq][q], dx, dy, r, mh)) continue;
+                if (!pair_is_old(gr, up, unified_slot(S, cq, sq, q))) continue;
+                if (sq == sp)
+                  ++s1;
+                else
+                  ++s0;
+              }
             }
           }
-        }
-    }
-  }
-  int e0 = 0, e1 = 0, has_dummy = 0;
-  for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy)
-    for (int jx = max(cx - 1, 0); jx <= min(cx + 1, ndx - 1); ++jx) {
-      const int cq = jy * ndx + jx;
-#pragma unroll
-      for (int sq = 0; sq < 3; ++sq) {
-        const int b = S.start[sq][cq], e = S.start[sq][cq + 1];
-        for (int q = b; q < e; ++q) {
-          if (sq == sp && q == k) continue;
-          double dx, dy, r, mh;
-          if (!pair_accept(P, pp, hp, S.pos[sq][q], S.h[sq][q], dx, dy, r, mh)) continue;
-          const int qid = S.order[sq][q];
-          double w, gx, gy;
-          if (sq == sp) {
-            sph_kernel(P, r, dx, dy, mh, w, gx, gy);  // own perspective: x_p - x_q
-            const int pos = (e1 < s1) ? (cnt1 - s1) + e1 : (cnt1 - 1 - e1);
-            const size_t a = o1 + (size_t)pos * SLICE;
-            if (sp == SP_NODE) {
-              L.idxC[a] = qid;
-              L.wC[a] = (float)w;
-              L.gxC[a] = (float)gx;
-              L.gyC[a] = (float)gy;
-            } else {
-              L.idxD[a] = qid;
-              L.wD[a] = (float)w;
-            }
-            ++e1;
-          } else {
-            // Pint_Update orientation: pair_i = stress particle (type 1) or dummy (types 6, 9)
-            const bool p_is_i = (sp == SP_STRESS && sq == SP_NODE);
-            if (p_is_i)
-              sph_kernel(P, r, dx, dy, mh, w, gx, gy);
-            else
-              sph_kernel(P, r, -dx, -dy, mh, w, gx, gy);
-            const int pos = (e0 < s0) ? (cnt0 - s0) + e0 : (cnt0 - 1 - e0);
-            const size_t a = o0 + (size_t)pos * SLICE;
-            L.idx0[a] = qid;
-            L.w0[a] = (float)w;
-            L.gx0[a] = (float)gx;
-            L.gy0[a] = (float)gy;
-            if (sq == SP_DUMMY) has_dummy = 1;
-            ++e0;
-          }
-        }
       }
     }
+  }
+  int e0 = 0, e1 = 0, has_dummy = 0, nq0 = 0, nq1 = 0;
+
+  auto drain = [&]() {
+    // list 0: cross-species partners, reference orientation of the gradient (pair_i - pair_j)
+    for (int j = 0; j < nq0; ++j) {
+      const int pk = q0buf[j][tid];
+      const int sq = (int)((unsigned)pk >> 30), q = pk & 0x3fffffff;
+      const double2 pq = S.pos[sq][q];
+      const double hq = uni ? hp : S.h[sq][q];
+      double dx = pp.x - pq.x, dy = pp.y - pq.y;
+      double d2 = dx * dx;
+      d2 = d2 + dy * dy;
+      const double mh = (hp + hq) / 2.;
+      const double r = sqrt(d2);
+      // Pint_Update orientation: pair_i = stress particle (type 1) or dummy (types 6, 9)
+      const bool p_is_i = (sp == SP_STRESS && sq == SP_NODE);
+      if (!p_is_i) {
+        dx = -dx;
+        dy = -dy;
+      }
+      double w, gx, gy;
+      if (mh == K.h)
+        sph_kernel_fast<true>(K, r, dx, dy, w, gx, gy);
+      else
+        sph_kernel(P, r, dx, dy, mh, w, gx, gy);
+      const int pos = (e0 < s0) ? (cnt0 - s0) + e0 : (cnt0 - 1 - e0);
+      const size_t a = o0 + (size_t)pos * SLICE;
+      L.idx0[a] = S.order[sq][q];
+      L.w0[a] = (float)w;
+      L.gx0[a] = (float)gx;
+      L.gy0[a] = (float)gy;
+      if (sq == SP_DUMMY) has_dummy = 1;
+      ++e0;
+    }
+    // list C / D: same-species partners, own-perspective gradient (nodes) or weight only (stress particles)
+    for (int j = 0; j < nq1; ++j) {
+      const int q = q1buf[j][tid];
+      const double2 pq = posp[q];
+      const double hq = uni ? hp : hpp[q];
+      const double dx = pp.x - pq.x, dy = pp.y - pq.y;
+      double d2 = dx * dx;
+      d2 = d2 + dy * dy;
+      const double mh = (hp + hq) / 2.;
+      const double r = sqrt(d2);
+      const int pos = (e1 < s1) ? (cnt1 - s1) + e1 : (cnt1 - 1 - e1);
+      const size_t a = o1 + (size_t)pos * SLICE;
+      double w, gx, gy;
+      if (sp == SP_NODE) {
+        if (mh == K.h)
+          sph_kernel_fast<true>(K, r, dx, dy, w, gx, gy);
+        else
+          sph_kernel(P, r, dx, dy, mh, w, gx, gy);
+        L.idxC[a] = orderp[q];
+        L.wC[a] = (float)w;
+        L.gxC[a] = (float)gx;
+        L.gyC[a] = (float)gy;
+      } else {
+        if (mh == K.h)
+          sph_kernel_fast<false>(K, r, dx, dy, w, gx, gy);
+        else
+          sph_kernel(P, r, dx, dy, mh, w, gx, gy);
+        L.idxD[a] = orderp[q];
+        L.wD[a] = (float)w;
+      }
+      ++e1;
+    }
+    nq0 = 0;
+    nq1 = 0;
+  };
+
+  auto scan = [&](int sq, int b, int e) {
+    for (int q = b; q < e; ++q) {
+      if (sq == sp && q == k) continue;
+      int cls = 2;
+      if (pf.on) cls = prefilter_test(pf, up, S.upos[sq][q]);
+      if (cls == 0) continue;
+      if (cls == 2) {
+        double dx, dy, d2, mh;
+        if (!pair_accept_fast(sk, pp, hp, S.pos[sq][q], uni ? hp : S.h[sq][q], dx, dy, d2, mh)) continue;
+      }
+      if (sq == sp) {
+        q1buf[nq1++][tid] = q;
+      } else {
+        q0buf[nq0++][tid] = (sq << 30) | q;
+      }
+      if (nq0 == QCAP || nq1 == QCAP) drain();
+    }
+  };
+
+  for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy) {
+    const RowRange rr = row_range(ndx, cx, jy);
+    const int nd_row = S.start[2][rr.cb + 1] - S.start[2][rr.ca];
+    if (nd_row == 0) {
+      // no wall particles in this row: every list takes partners of a single species, whose order
+      // (cell id, particle index) is the order of the merged range
+      scan(0, S.start[0][rr.ca], S.start[0][rr.cb + 1]);
+      scan(1, S.start[1][rr.ca], S.start[1][rr.cb + 1]);
+    } else {
+      // wall particles interleave with the other species cell by cell: (cell id, species, index) order
+      for (int cq = rr.ca; cq <= rr.cb; ++cq)
+        for (int sq = 0; sq < 3; ++sq) scan(sq, S.start[sq][cq], S.start[sq][cq + 1]);
+    }
+  }
+  drain();
   if (sp == SP_NODE) bc_int[id] = has_dummy;  // main:506,579
 }
 

@@ -37,8 +37,12 @@ struct spsph_handle {
 
   // particle state (original order)
   double *x = nullptr, *x00 = nullptr, *rho = nullptr, *mass = nullptr, *hsml = nullptr, *mor = nullptr;
-  double *V[2] = {nullptr, nullptr}, *S[2] = {nullptr, nullptr};
-  double *sor = nullptr, *epsp = nullptr, *fdp = nullptr, *norm = nullptr, *AE = nullptr;
+  Rec4 *NA = nullptr, *NB[2] = {nullptr, nullptr}, *SB[2] = {nullptr, nullptr};
+  Rec8 *SA = nullptr;
+  double *NSa = nullptr, *SVa = nullptr;
+  double *NSb[2] = {nullptr, nullptr}, *SFb[2] = {nullptr, nullptr}, *SVb[2] = {nullptr, nullptr};
+  double *stage_vel = nullptr, *stage_stress = nullptr;  // reference-layout staging for upload / download
+  double *epsp = nullptr, *fdp = nullptr, *norm = nullptr, *AE = nullptr;
   double *vel0 = nullptr, *stress0 = nullptr, *vx0 = nullptr, *RKv = nullptr, *RKs = nullptr, *RKe = nullptr;
   double *displ = nullptr, *x_10 = nullptr, *disp_10 = nullptr;
   float *wallpos = nullptr, *horiz = nullptr, *n_int = nullptr;
@@ -55,6 +59,7 @@ struct spsph_handle {
   int *cell_cnt = nullptr, *cell_start = nullptr, *cell_fill = nullptr;
   int *which_cell = nullptr, *tmp_ids = nullptr, *order = nullptr, *scell = nullptr, *pos_of = nullptr, *nout = nullptr;
   double2 *spos = nullptr;
+  float2 *supos = nullptr;
   double *sh = nullptr;
   int *scan_bsum = nullptr;
   long long *scan_totals = nullptr;  // [0..2] list storage, [3] pairs, [4..6] cells
@@ -143,13 +148,15 @@ SortArrays sort_arrays(spsph_handle *h) {
     S.start[s] = h->cell_start + (size_t)s * h->cell_stride;
     S.order[s] = h->order + s * n2;
     S.pos[s] = h->spos + s * n2;
+    S.upos[s] = h->supos + s * n2;
     S.h[s] = h->sh + s * n2;
     S.cell[s] = h->scell + s * n2;
   }
   return S;
 }
 
-StatePtrs state_ptrs(spsph_handle *h) {
+// `wb`: format-B buffer set that is written / current; the other set is the read side of a B -> B sweep
+StatePtrs state_ptrs(spsph_handle *h, int wb) {
   StatePtrs s;
   s.x = h->x;
   s.mass = h->mass;
@@ -160,11 +167,19 @@ StatePtrs state_ptrs(spsph_handle *h) {
   s.horiz = h->horiz;
   s.bc_or_not = h->bc_or_not;
   s.bc_info = h->bc_info;
-  s.V[0] = h->V[0];
-  s.V[1] = h->V[1];
-  s.S[0] = h->S[0];
-  s.S[1] = h->S[1];
-  s.sor = h->sor;
+  s.NA = h->NA;
+  s.SA = h->SA;
+  s.NSa = h->NSa;
+  s.SVa = h->SVa;
+  s.NB = h->NB[wb];
+  s.SB = h->SB[wb];
+  s.NSb = h->NSb[wb];
+  s.SFb = h->SFb[wb];
+  s.SVb = h->SVb[wb];
+  s.NBr = h->NB[1 - wb];
+  s.NSbr = h->NSb[1 - wb];
+  s.SFbr = h->SFb[1 - wb];
+  s.SVbr = h->SVb[1 - wb];
   s.epsp = h->epsp;
   s.fdp = h->fdp;
   s.norm = h->norm;
@@ -299,7 +314,7 @@ int build_neighbours(spsph_handle *h) {
   k_scatter<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->which_cell, h->cell_start, h->cell_fill, h->cell_stride, h->tmp_ids);
   mark(h, KID_SCATTER);
   k_rank<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->G, h->x, h->hsml, h->which_cell, h->cell_start, h->cell_stride,
-                                            h->tmp_ids, h->order, h->spos, h->sh, h->scell, h->pos_of);
+                                            h->tmp_ids, h->order, h->spos, h->sh, h->scell, h->pos_of, h->supos);
   mark(h, KID_RANK);
   const SortArrays S = sort_arrays(h);
   const int T = h->M.total();
@@ -354,49 +369,55 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   const spsph_params &p = h->hp;
   cudaStream_t s = h->stream;
   const SortArrays S = sort_arrays(h);
-  const StatePtrs st = state_ptrs(h);
-  const int TL = h->M.nnp + h->M.nsp;
-  const int GB = (TL + 127) / 128;
+  const SlotMap &M = h->M;
+  const int GN = (M.nn + 127) / 128, GS = (M.ns + 127) / 128, GB = (M.nnp + M.nsp + 127) / 128;
   const int adapt = P.adapt, bc = p.no_bcs > 0 ? 1 : 0;
+  const int *ord_n = S.order[0], *ord_s = S.order[1];
   bool first_a = true;
-  int cur = h->cur;
-  // SPH_shift block, main:99-109
+  // SPH_shift block, main:99-109: format B -> the other format-B buffer set
   if (p.sph_shift && itimestep > 1 && ((itimestep - 1) % p.shift_update == 0)) {
-    k_sweep_a<true><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, st, cur, 1 - cur, adapt, 0, 1);
-    mark(h, KID_SWEEPA);
-    cur = 1 - cur;
+    const StatePtrs sw = state_ptrs(h, 1 - h->cur);
+    k_sweep_a_sp<true, true><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, sw, adapt, 0);
+    k_sweep_a_node<true, true, true><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, sw, adapt, 0);
+    mark(h, KID_SWEEPA, 2);
+    h->cur = 1 - h->cur;
     first_a = false;
   }
+  const StatePtrs st = state_ptrs(h, h->cur);
   // RK4, main:653-802
-  const int A = 1 - cur, B = cur;  // rk_begin: cur -> A ; sweep A: A -> B ; sweep B: B -> A
-  k_rk_begin<<<(P.ntotal + 255) / 256, 256, 0, s>>>(P, st, cur, A);
+  k_rk_begin<<<(P.ntotal + 255) / 256, 256, 0, s>>>(P, st);
   mark(h, KID_RKBEGIN);
   const double f1rk[4] = {0., 0.5, 0.5, 1.0}, f2rk[4] = {1., 2., 2., 1.0};
   for (int stg = 0; stg < 4; ++stg) {
-    if (first_a)
-      k_sweep_a<true><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, st, A, B, adapt, bc, 0);
-    else
-      k_sweep_a<false><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, st, A, B, adapt, bc, 0);
-    mark(h, KID_SWEEPA);
+    if (first_a) {
+      k_sweep_a_sp<true, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
+      k_sweep_a_node<true, false, false><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+    } else {
+      k_sweep_a_sp<false, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
+      k_sweep_a_node<false, false, false><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+    }
+    mark(h, KID_SWEEPA, 2);
     first_a = false;
     const int last = (stg == 3);
     const double f1n = last ? 0.0 : f1rk[stg + 1];
-    if (stg == 0)
-      k_sweep_b<true><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, h->n1, st, B, A, f1n, f2rk[stg], last);
-    else
-      k_sweep_b<false><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, h->n1, st, B, A, f1n, f2rk[stg], last);
-    mark(h, KID_SWEEPB);
+    if (stg == 0) {
+      k_sweep_b_sp<true><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last);
+      k_sweep_b_node<true><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, h->n1, st, f1n, f2rk[stg], last);
+    } else {
+      k_sweep_b_sp<false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last);
+      k_sweep_b_node<false><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, h->n1, st, f1n, f2rk[stg], last);
+    }
+    mark(h, KID_SWEEPB, 2);
   }
   // final stress_point_update + adapt_stress2 + BCs, main:130-135
-  k_sweep_a<false><<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n0, st, A, B, adapt, bc, 1);
-  mark(h, KID_SWEEPA);
-  cur = B;
-  h->cur = cur;
+  k_sweep_a_sp<false, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
+  k_sweep_a_node<false, false, true><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+  mark(h, KID_SWEEPA, 2);
   // positions, main:140-182
-  k_move<<<GB, 128, 0, s>>>(P, h->M, S, h->L, h->n1, st, cur, h->x, h->x00, h->displ);
+  k_move<<<GB, 128, 0, s>>>(P, M, S, h->L, h->n1, st, h->x, h->x00, h->displ);
   mark(h, KID_MOVE);
   if (p.update_x && p.sp_sph && !p.inside_approach) {
-    k_shift<<<(P.nnode + 255) / 256, 256, 0, s>>>(P, h->V[cur], h->x, h->x_10, h->disp_10, h->bc_int, h->n_int);
+    k_shift<<<(P.nnode + 255) / 256, 256, 0, s>>>(P, st.NB, h->x, h->x_10, h->disp_10, h->bc_int, h->n_int);
     mark(h, KID_SHIFT);
   }
   CUDA_TRY(cudaGetLastError());
@@ -517,8 +538,13 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   int rc = 0;
   rc |= dalloc(h, &h->x, 2 * n2) | dalloc(h, &h->x00, 2 * n2) | dalloc(h, &h->rho, n2) | dalloc(h, &h->mass, n2);
   rc |= dalloc(h, &h->hsml, n2) | dalloc(h, &h->mor, n2);
-  for (int b = 0; b < 2; ++b) rc |= dalloc(h, &h->V[b], 2 * nt) | dalloc(h, &h->S[b], 4 * nt);
-  rc |= dalloc(h, &h->sor, 3 * nt) | dalloc(h, &h->epsp, nt) | dalloc(h, &h->fdp, nt) | dalloc(h, &h->norm, nt);
+  rc |= dalloc(h, &h->NA, nn) | dalloc(h, &h->SA, ns) | dalloc(h, &h->NSa, 4 * nn) | dalloc(h, &h->SVa, 2 * ns);
+  for (int b = 0; b < 2; ++b) {
+    rc |= dalloc(h, &h->NB[b], nn) | dalloc(h, &h->SB[b], ns) | dalloc(h, &h->NSb[b], 4 * nn);
+    rc |= dalloc(h, &h->SFb[b], 4 * ns) | dalloc(h, &h->SVb[b], 2 * ns);
+  }
+  rc |= dalloc(h, &h->stage_vel, 2 * nt) | dalloc(h, &h->stage_stress, 4 * nt);
+  rc |= dalloc(h, &h->epsp, nt) | dalloc(h, &h->fdp, nt) | dalloc(h, &h->norm, nt);
   rc |= dalloc(h, &h->AE, 5 * nt) | dalloc(h, &h->vel0, 2 * nn) | dalloc(h, &h->stress0, 4 * ns);
   rc |= dalloc(h, &h->vx0, 2 * nt) | dalloc(h, &h->RKv, 2 * nn) | dalloc(h, &h->RKs, 4 * ns) | dalloc(h, &h->RKe, ns);
   rc |= dalloc(h, &h->displ, 2 * nn) | dalloc(h, &h->x_10, 2 * nn) | dalloc(h, &h->disp_10, nn);
@@ -527,10 +553,10 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   rc |= dalloc(h, &h->if_out, n2);
   rc |= dalloc(h, &h->G, 1);
   h->bbox_blocks = 296;
-  rc |= dalloc(h, &h->bbox_partial, 5 * (size_t)h->bbox_blocks);
+  rc |= dalloc(h, &h->bbox_partial, 6 * (size_t)h->bbox_blocks);
   rc |= dalloc(h, &h->which_cell, n2) | dalloc(h, &h->tmp_ids, 3 * n2) | dalloc(h, &h->order, 3 * n2);
   rc |= dalloc(h, &h->scell, 3 * n2) | dalloc(h, &h->pos_of, n2) | dalloc(h, &h->nout, 4);
-  rc |= dalloc(h, &h->spos, 3 * n2) | dalloc(h, &h->sh, 3 * n2);
+  rc |= dalloc(h, &h->spos, 3 * n2) | dalloc(h, &h->sh, 3 * n2) | dalloc(h, &h->supos, 3 * n2);
   rc |= dalloc(h, &h->scan_bsum, 4 * (size_t)SCAN_BLOCKS) | dalloc(h, &h->scan_totals, 8);
   const size_t T = (size_t)M.total();
   rc |= dalloc(h, &h->n0, T) | dalloc(h, &h->n1, T) | dalloc(h, &h->nall, T);
@@ -581,8 +607,9 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   }
   CUDA_TRY(up(h->mor, mor.data(), n2 * 8));
   h->cur = 0;
-  CUDA_TRY(up(h->V[0], s->vel, 2 * nt * 8));
-  CUDA_TRY(up(h->S[0], s->stress, 4 * nt * 8));
+  CUDA_TRY(up(h->stage_vel, s->vel, 2 * nt * 8));
+  CUDA_TRY(up(h->stage_stress, s->stress, 4 * nt * 8));
+  k_pack_state<<<((int)nt + 255) / 256, 256, 0, st>>>(h->P, h->stage_vel, h->stage_stress, state_ptrs(h, 0));
   std::vector<double> e1(nt, 0.0);
   if (s->internal_vars) {
     h->h_internal_vars.assign(s->internal_vars, s->internal_vars + (size_t)SPSPH_NINT_VARS * nt);
@@ -695,13 +722,15 @@ int spsph_download(spsph_handle *h, const spsph_state *s) {
     return cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDeviceToHost, st);
   };
   CUDA_TRY(down(s->x, h->x, 2 * n2 * 8));
+  if (s->vel || s->stress)
+    k_unpack_state<<<((int)nt + 255) / 256, 256, 0, st>>>(h->P, state_ptrs(h, h->cur), h->stage_vel, h->stage_stress);
   if (s->vel) {  // dummy particles carry no velocity/stress on the device (zero, as after main:690)
-    std::memset(s->vel, 0, 2 * n2 * 8);
-    CUDA_TRY(down(s->vel, h->V[h->cur], 2 * nt * 8));
+    std::memset(s->vel + 2 * nt, 0, 2 * (n2 - nt) * 8);
+    CUDA_TRY(down(s->vel, h->stage_vel, 2 * nt * 8));
   }
   if (s->stress) {
-    std::memset(s->stress, 0, 4 * n2 * 8);
-    CUDA_TRY(down(s->stress, h->S[h->cur], 4 * nt * 8));
+    std::memset(s->stress + 4 * nt, 0, 4 * (n2 - nt) * 8);
+    CUDA_TRY(down(s->stress, h->stage_stress, 4 * nt * 8));
   }
   CUDA_TRY(down(s->rho, h->rho, n2 * 8));
   CUDA_TRY(down(s->mass, h->mass, n2 * 8));

@@ -6,58 +6,138 @@
 // One thread per velocity / stress particle, walking its gather list front to back: every per-particle sum
 // is accumulated in the reference's traversal order (fp32 sums bit-exact, fp64 sums too), no atomics.
 //
-// Buffering: a sweep A (interpolation) maps state buffer `src` to `dst` completely, the following sweep B
-// (gradients + constitutive update + RK stage epilogue + next-stage predictor) maps `dst` back to `src`.
-// Each kernel only reads neighbour values from the buffer it does not write, so there are no races.
+// Data layout. The state lives in two buffer sets with *different record formats*, each written by the
+// kernel that precedes its reader so that a neighbour gather is one aligned 32-byte sector:
+//   format A (input of sweep A = stress_point_update):
+//       NA[node] = {vx, vy, m/rho, -}            SA[sp] = {s1, s2, s3, s4, m/rho, eps_p, -, -}
+//       NSa[node] = own stress (carried)         SVa[sp] = own velocity (carried)
+//   format B (input of sweep B = get_derivatives; also the state between time steps):
+//       NB[node] = {vx, vy, m, rho}              SB[sp] = {s1/rho^2, s2/rho^2, s3/rho^2, m}
+//       NSb[node] = own stress                   SFb[sp] = own stress, SVb[sp] = own velocity
+// Sweep A maps A -> B, sweep B (with the fused RK4 stage epilogue and next-stage predictor) maps B -> A; a
+// kernel only gathers from the format it does not write, so there are no read/write races.
+// List entries are streamed with ld.global.cs (read once per sweep), four entries in flight per thread.
 #pragma once
 #include "grid_kernels.cuh"
 
 namespace spsph {
 
+struct __align__(32) Rec4 {
+  double a, b, c, d;
+};
+struct __align__(32) Rec8 {
+  double s1, s2, s3, s4, mor, epsp, p0, p1;
+};
+
 struct StatePtrs {
   // constant per step / persistent (original particle order)
-  const double *x;         // (2, ntotal2)
-  const double *mass, *rho, *hsml, *mor;  // mor = mass/rho
+  const double *x;  // (2, ntotal2)
+  const double *mass, *rho, *hsml, *mor;
   const float *wallpos, *horiz;
   const int *bc_or_not, *bc_info;
-  // ping-pong buffers
-  double *V[2];    // (2, ntotal)
-  double *S[2];    // (4, ntotal)
-  double *sor;     // (3, ntotal) stress(1:3)/rho**2 of the buffer written by the last sweep A
-  double *epsp;    // (ntotal) Internal_Vars(1,:)
-  double *fdp;     // (ntotal) f_drucker
-  double *norm;    // (ntotal) cspm_norm of stress_point_update (frozen within a step)
-  double *AE;      // (5, ntotal) inverted CSPM matrix of get_derivatives (frozen within a step)
-  double *vel0;    // (2, nnode)
-  double *stress0; // (4, nstress)
-  double *vx0;     // (2, ntotal)
-  double *RKv;     // (2, nnode)
-  double *RKs;     // (4, nstress)
-  double *RKe;     // (nstress)
+  // format A
+  Rec4 *NA;     // [nnode]
+  Rec8 *SA;     // [nstress]
+  double *NSa;  // (4, nnode)
+  double *SVa;  // (2, nstress)
+  // format B (== state between steps)
+  Rec4 *NB;     // [nnode]
+  Rec4 *SB;     // [nstress]
+  double *NSb;  // (4, nnode)
+  double *SFb;  // (4, nstress)
+  double *SVb;  // (2, nstress)
+  // read side of a format-B -> format-B sweep (the SPH_shift interpolation): the other B buffer set
+  const Rec4 *NBr;
+  const double *NSbr, *SFbr, *SVbr;
+  double *epsp;     // (ntotal) Internal_Vars(1,:)
+  double *fdp;      // (ntotal) f_drucker
+  double *norm;     // (ntotal) cspm_norm of stress_point_update (frozen within a step)
+  double *AE;       // (5, ntotal) inverted CSPM matrix of get_derivatives (frozen within a step)
+  double *vel0;     // (2, nnode)
+  double *stress0;  // (4, nstress)
+  double *vx0;      // (2, ntotal)
+  double *RKv;      // (2, nnode)
+  double *RKs;      // (4, nstress)
+  double *RKe;      // (nstress)
 };
+
+__device__ __forceinline__ Rec4 ldrec(const Rec4 *p, int i) {
+  const double2 a = reinterpret_cast<const double2 *>(p)[2 * (size_t)i];
+  const double2 b = reinterpret_cast<const double2 *>(p)[2 * (size_t)i + 1];
+  return Rec4{a.x, a.y, b.x, b.y};
+}
+__device__ __forceinline__ void strec(Rec4 *p, int i, double a, double b, double c, double d) {
+  reinterpret_cast<double2 *>(p)[2 * (size_t)i] = make_double2(a, b);
+  reinterpret_cast<double2 *>(p)[2 * (size_t)i + 1] = make_double2(c, d);
+}
+__device__ __forceinline__ int ldcs_i(const int *p) { return __ldcs(p); }
+__device__ __forceinline__ float ldcs_f(const float *p) { return __ldcs(p); }
+
+constexpr int UNR = 4;  // list entries in flight per thread
+
+// state format conversions at the boundary of the time loop ---------------------------------------------
+// pack: reference-layout vel/stress (upload) -> format B
+__global__ void k_pack_state(DevParams P, const double *__restrict__ vel, const double *__restrict__ stress,
+                             StatePtrs st) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= P.ntotal) return;
+  const double2 v = ld2(vel, id);
+  const Stress4 s = ld4(stress, id);
+  if (id < P.nnode) {
+    strec(st.NB, id, v.x, v.y, st.mass[id], st.rho[id]);
+    st4(st.NSb, id, s);
+  } else {
+    const int ks = id - P.nnode;
+    const double r = st.rho[id];
+    const double r2 = r * r;
+    strec(st.SB, ks, s.s1 / r2, s.s2 / r2, s.s3 / r2, st.mass[id]);
+    st4(st.SFb, ks, s);
+    st2(st.SVb, ks, v);
+  }
+}
+// unpack: format B -> reference-layout vel (2,ntotal) and stress (4,ntotal) for download
+__global__ void k_unpack_state(DevParams P, StatePtrs st, double *__restrict__ vel, double *__restrict__ stress) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= P.ntotal) return;
+  if (id < P.nnode) {
+    const Rec4 r = ldrec(st.NB, id);
+    st2(vel, id, make_double2(r.a, r.b));
+    st4(stress, id, ld4(st.NSb, id));
+  } else {
+    const int ks = id - P.nnode;
+    st2(vel, id, ld2(st.SVb, ks));
+    st4(stress, id, ld4(st.SFb, ks));
+  }
+}
 
 // ------------------------------------------------------------------------------------------------------
 // RK4 prologue (main:681-690 + first predictor main:700-701 with f1rk = 0 + adapt_stress2/BCs main:715-716):
-// saves vel0/stress0/vx0, zeroes the accumulators, and builds the stage-1 input buffer where stress-particle
-// velocities, node stresses (and all dummy values) start from zero (main:690).
+// format B (state) -> format A (stage-1 input); saves vel0/stress0/vx0 and zeroes the RK accumulators.
+// Stress-particle velocities and node stresses start from zero (main:690).
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_rk_begin(DevParams P, StatePtrs st, int cur, int dst) {
+__global__ void k_rk_begin(DevParams P, StatePtrs st) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= P.ntotal) return;
-  const double2 v = ld2(st.V[cur], id);
-  const Stress4 s = ld4(st.S[cur], id);
-  st2(st.vx0, id, v);
   double2 vn;
   Stress4 sn;
   if (id < P.nnode) {
+    const Rec4 r = ldrec(st.NB, id);
+    const double2 v = make_double2(r.a, r.b);
+    st2(st.vx0, id, v);
     st2(st.vel0, id, v);
     st2(st.RKv, id, make_double2(0.0, 0.0));
-    // RHS_2 = 0: vel0 + f1rk(1)*dt*RHS_2
-    vn.x = v.x + 0. * (P.dt) * 0.0;
+    vn.x = v.x + 0. * (P.dt) * 0.0;  // vel0 + f1rk(1)*dt*RHS_2 with RHS_2 = 0
     vn.y = v.y + 0. * (P.dt) * 0.0;
     sn = Stress4{0.0, 0.0, 0.0, 0.0};
+    if (P.adapt) adapt_stress(P, sn);
+    apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
+    strec(st.NA, id, vn.x, vn.y, st.mor[id], 0.0);
+    st4(st.NSa, id, sn);
   } else {
     const int ks = id - P.nnode;
+    const double2 v = ld2(st.SVb, ks);
+    const Stress4 s = ld4(st.SFb, ks);
+    st2(st.vx0, id, v);
     st4(st.stress0, ks, s);
     st4(st.RKs, ks, Stress4{0.0, 0.0, 0.0, 0.0});
     st.RKe[ks] = 0.0;
@@ -66,148 +146,237 @@ __global__ void k_rk_begin(DevParams P, StatePtrs st, int cur, int dst) {
     sn.s2 = s.s2 + 0. * (P.dt) * 0.0;
     sn.s3 = s.s3 + 0. * (P.dt) * 0.0;
     sn.s4 = s.s4 + 0. * (P.dt) * 0.0;
+    if (P.adapt) adapt_stress(P, sn);
+    apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
+    Rec8 *o = st.SA + ks;
+    reinterpret_cast<double2 *>(o)[0] = make_double2(sn.s1, sn.s2);
+    reinterpret_cast<double2 *>(o)[1] = make_double2(sn.s3, sn.s4);
+    reinterpret_cast<double2 *>(o)[2] = make_double2(st.mor[id], st.epsp[id]);
+    st2(st.SVa, ks, vn);
   }
-  if (P.adapt) adapt_stress(P, sn);
-  apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
-  st2(st.V[dst], id, vn);
-  st4(st.S[dst], id, sn);
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Sweep A: stress_point_update (+ the adapt_stress2 / BCs that follow it).
+// Sweep A (stress_point_update + the adapt_stress2 / BCs that follow it).
+//   FROMB = false: input in format A (inside RK4 and the final interpolation of the step)
+//   FROMB = true : input in format B (the SPH_shift interpolation at the start of a step, main:99-109)
+//   FIRST: first sweep A of the step -> computes and stores cspm_norm
 // ------------------------------------------------------------------------------------------------------
-template <bool FIRST>
+template <bool FIRST, bool FROMB>
 __global__ void __launch_bounds__(128)
-k_sweep_a(DevParams P, SlotMap M, SortArrays So, ListPtrs L, const int *__restrict__ n0, StatePtrs st, int src, int dst,
-          int do_adapt, int do_bc, int want_epsp) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= M.nnp + M.nsp) return;
-  int sp, k;
-  if (!slot_decode(M, t, sp, k)) return;
-  const int id = So.order[sp][k];
+k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L, const int *__restrict__ n0,
+             StatePtrs st, int do_adapt, int do_bc) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;  // species-sorted index of the stress particle
+  if (k >= M.ns) return;
+  const int t = M.nnp + k;
+  const int id = order_s[k];
+  const int ks = id - P.nnode;
   const int cnt = n0[t];
   const size_t o0 = (size_t)L.off0[t / SLICE] + (t & 31);
-  const double *__restrict__ Vs = st.V[src];
-  const double *__restrict__ Ss = st.S[src];
-  double2 v = ld2(Vs, id);
-  Stress4 s = ld4(Ss, id);
-  double nrm = 0.0;
-  if (sp == SP_STRESS) {
-    double vtx = 0.0, vty = 0.0;
-    for (int e = 0; e < cnt; ++e) {
-      const size_t a = o0 + (size_t)e * SLICE;
-      const int q = L.idx0[a];
-      if (q >= P.ntotal) continue;  // dummy partner (type 9): no part in the interpolation
-      const double w = (double)L.w0[a];
-      const double h2 = st.mor[q] * w;
-      const double2 vq = ld2(Vs, q);
-      vtx = vtx + vq.x * h2;
-      vty = vty + vq.y * h2;
-      if (FIRST) nrm = nrm + (w * st.mass[q]) / st.rho[q];
-    }
-    if (FIRST)
-      st.norm[id] = nrm;
-    else
-      nrm = st.norm[id];
-    if (nrm != 0) {
-      v.x = vtx / nrm;
-      v.y = vty / nrm;
-    }
+  double2 v;
+  Stress4 s;
+  if (FROMB) {
+    v = ld2(st.SVbr, ks);
+    s = ld4(st.SFbr, ks);
   } else {
-    double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, te = 0.0;
-    for (int e = 0; e < cnt; ++e) {
-      const size_t a = o0 + (size_t)e * SLICE;
-      const int q = L.idx0[a];
-      if (q >= P.ntotal) continue;  // dummy partner (type 6)
-      const double w = (double)L.w0[a];
-      const double h1 = st.mor[q] * w;
-      const Stress4 sq = ld4(Ss, q);
-      t1 = t1 + sq.s1 * h1;
-      t2 = t2 + sq.s2 * h1;
-      t3 = t3 + sq.s3 * h1;
-      t4 = t4 + sq.s4 * h1;
-      if (want_epsp) te = te + st.epsp[q] * h1;
-      if (FIRST) nrm = nrm + (w * st.mass[q]) / st.rho[q];
+    v = ld2(st.SVa, ks);
+    const Rec8 *o = st.SA + ks;
+    const double2 a = reinterpret_cast<const double2 *>(o)[0], b = reinterpret_cast<const double2 *>(o)[1];
+    s = Stress4{a.x, a.y, b.x, b.y};
+  }
+  double vtx = 0.0, vty = 0.0, nrm = 0.0;
+  for (int e0 = 0; e0 < cnt; e0 += UNR) {
+    int q[UNR];
+    float w[UNR];
+    Rec4 r[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const size_t a = o0 + (size_t)(e0 + u) * SLICE;
+      q[u] = ldcs_i(L.idx0 + a);
+      w[u] = ldcs_f(L.w0 + a);
     }
-    if (FIRST)
-      st.norm[id] = nrm;
-    else
-      nrm = st.norm[id];
-    if (nrm != 0) {
-      s.s1 = t1 / nrm;
-      s.s2 = t2 / nrm;
-      s.s3 = t3 / nrm;
-      s.s4 = t4 / nrm;
-      if (want_epsp) st.epsp[id] = te / nrm;
-    } else {
-      v.x = 0;
-      v.y = 0;
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (e0 + u >= cnt || q[u] >= P.nnode) q[u] = -1;  // past the end, or dummy partner (type 9)
+      r[u] = ldrec(FROMB ? st.NBr : (const Rec4 *)st.NA, q[u] < 0 ? 0 : q[u]);
     }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (q[u] < 0) continue;
+      const double wd = (double)w[u];
+      const double mor = FROMB ? (r[u].c / r[u].d) : r[u].c;  // mass/rho
+      const double h2 = mor * wd;
+      vtx = vtx + r[u].a * h2;
+      vty = vty + r[u].b * h2;
+      if (FIRST) {
+        const double mq = FROMB ? r[u].c : st.mass[q[u]];
+        const double rq = FROMB ? r[u].d : st.rho[q[u]];
+        nrm = nrm + (wd * mq) / rq;
+      }
+    }
+  }
+  if (FIRST)
+    st.norm[id] = nrm;
+  else
+    nrm = st.norm[id];
+  if (nrm != 0) {
+    v.x = vtx / nrm;
+    v.y = vty / nrm;
   }
   if (do_adapt) adapt_stress(P, s);
   if (do_bc) apply_bcs(P, st.bc_or_not, st.bc_info, id, v, s);
-  st2(st.V[dst], id, v);
-  st4(st.S[dst], id, s);
-  const double r = st.rho[id];
-  const double r2 = r * r;
-  st.sor[3 * (size_t)id] = s.s1 / r2;
-  st.sor[3 * (size_t)id + 1] = s.s2 / r2;
-  st.sor[3 * (size_t)id + 2] = s.s3 / r2;
+  st2(st.SVb, ks, v);
+  st4(st.SFb, ks, s);
+  const double rr = st.rho[id];
+  const double r2 = rr * rr;
+  strec(st.SB, ks, s.s1 / r2, s.s2 / r2, s.s3 / r2, st.mass[id]);
+}
+
+template <bool FIRST, bool FROMB, bool EPSP>
+__global__ void __launch_bounds__(128)
+k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n0,
+               StatePtrs st, int do_adapt, int do_bc) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= M.nn) return;
+  const int t = k;
+  const int id = order_n[k];
+  const int cnt = n0[t];
+  const size_t o0 = (size_t)L.off0[t / SLICE] + (t & 31);
+  double2 v;
+  Stress4 s;
+  if (FROMB) {
+    const Rec4 r = ldrec(st.NBr, id);
+    v = make_double2(r.a, r.b);
+    s = ld4(st.NSbr, id);
+  } else {
+    const Rec4 r = ldrec(st.NA, id);
+    v = make_double2(r.a, r.b);
+    s = ld4(st.NSa, id);
+  }
+  double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, te = 0.0, nrm = 0.0;
+  for (int e0 = 0; e0 < cnt; e0 += UNR) {
+    int q[UNR];
+    float w[UNR];
+    Stress4 sq[UNR];
+    double mor[UNR], ep[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const size_t a = o0 + (size_t)(e0 + u) * SLICE;
+      q[u] = ldcs_i(L.idx0 + a);
+      w[u] = ldcs_f(L.w0 + a);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (e0 + u >= cnt || q[u] >= P.ntotal) q[u] = -1;  // past the end, or dummy partner (type 6)
+      const int qs = q[u] < 0 ? 0 : q[u] - P.nnode;
+      if (FROMB) {
+        sq[u] = ld4(st.SFbr, qs);
+        mor[u] = st.mor[qs + P.nnode];
+        ep[u] = EPSP ? st.epsp[qs + P.nnode] : 0.0;
+      } else {
+        const Rec8 *o = st.SA + qs;
+        const double2 a = reinterpret_cast<const double2 *>(o)[0], b = reinterpret_cast<const double2 *>(o)[1];
+        const double2 c = reinterpret_cast<const double2 *>(o)[2];
+        sq[u] = Stress4{a.x, a.y, b.x, b.y};
+        mor[u] = c.x;
+        ep[u] = c.y;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (q[u] < 0) continue;
+      const double wd = (double)w[u];
+      const double h1 = mor[u] * wd;
+      t1 = t1 + sq[u].s1 * h1;
+      t2 = t2 + sq[u].s2 * h1;
+      t3 = t3 + sq[u].s3 * h1;
+      t4 = t4 + sq[u].s4 * h1;
+      if (EPSP) te = te + ep[u] * h1;
+      if (FIRST) nrm = nrm + (wd * st.mass[q[u]]) / st.rho[q[u]];
+    }
+  }
+  if (FIRST)
+    st.norm[id] = nrm;
+  else
+    nrm = st.norm[id];
+  if (nrm != 0) {
+    s.s1 = t1 / nrm;
+    s.s2 = t2 / nrm;
+    s.s3 = t3 / nrm;
+    s.s4 = t4 / nrm;
+    if (EPSP) st.epsp[id] = te / nrm;
+  } else {
+    v.x = 0;
+    v.y = 0;
+  }
+  if (do_adapt) adapt_stress(P, s);
+  if (do_bc) apply_bcs(P, st.bc_or_not, st.bc_info, id, v, s);
+  strec(st.NB, id, v.x, v.y, st.mass[id], st.rho[id]);
+  st4(st.NSb, id, s);
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Sweep B: get_derivatives + plastic_terms + gravity/damping + artificial viscosity + Jaumann terms +
-// RK4 stage accumulation + next-stage predictor (or the final RK4 update when `last`).
-//   reads buffer b (written by sweep A), writes buffer a.
+// Sweep B (get_derivatives + plastic_terms + gravity/damping + artificial viscosity + Jaumann terms + RK4
+// stage accumulation + next-stage predictor, or the final RK4 update when `last`): format B -> format A.
 // ------------------------------------------------------------------------------------------------------
 template <bool FIRST>
 __global__ void __launch_bounds__(128)
-k_sweep_b(DevParams P, SlotMap M, SortArrays So, ListPtrs L, const int *__restrict__ n0, const int *__restrict__ n1,
-          StatePtrs st, int b, int a_, double f1next, double f2, int last) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= M.nnp + M.nsp) return;
-  int sp, k;
-  if (!slot_decode(M, t, sp, k)) return;
-  const int id = So.order[sp][k];
+k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L, const int *__restrict__ n0,
+             StatePtrs st, double f1next, double f2, int last) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= M.ns) return;
+  const int t = M.nnp + k;
+  const int id = order_s[k];
+  const int ks = id - P.nnode;
   const int cnt = n0[t];
-  const int lane = t & 31, sl = t / SLICE;
-  const size_t o0 = (size_t)L.off0[sl] + lane;
-  const double *__restrict__ Vb = st.V[b];
-  const double *__restrict__ Sb = st.S[b];
-  const double2 vp = ld2(Vb, id);
-  const Stress4 sp_ = ld4(Sb, id);
-  const double2 xp = ld2(st.x, id);
+  const size_t o0 = (size_t)L.off0[t / SLICE] + (t & 31);
+  const double2 vp = ld2(st.SVb, ks);
+  const Stress4 sp_ = ld4(st.SFb, ks);
+  double2 xp = make_double2(0.0, 0.0);
+  if ((FIRST && P.cspm) || P.ndummy > 0) xp = ld2(st.x, id);
   double ae1 = 0.0, ae2 = 0.0, ae3 = 0.0, ae4 = 0.0, ae5 = 1.0;
-
-  if (sp == SP_STRESS) {
-    const int ks = id - P.nnode;
-    double g11 = 0.0, g12 = 0.0, g21 = 0.0, g22 = 0.0;  // grad1_tmp(d,k): d velocity component, k direction
-    for (int e = 0; e < cnt; ++e) {
-      const size_t a = o0 + (size_t)e * SLICE;
-      const int q = L.idx0[a];
-      const double gx = (double)L.gx0[a], gy = (double)L.gy0[a];
-      if (q < P.ntotal) {  // type 1: q is the node
-        const double mq = st.mass[q], rq = st.rho[q];
-        const double h1 = gx * mq / rq;
-        const double h2 = gy * mq / rq;
-        const double2 vq = ld2(Vb, q);
-        g11 = g11 + (vq.x - vp.x) * h1;
-        g12 = g12 + (vq.x - vp.x) * h2;
-        g21 = g21 + (vq.y - vp.y) * h1;
-        g22 = g22 + (vq.y - vp.y) * h2;
+  double g11 = 0.0, g12 = 0.0, g21 = 0.0, g22 = 0.0;  // grad1_tmp(d,k): d velocity component, k direction
+  for (int e0 = 0; e0 < cnt; e0 += UNR) {
+    int q[UNR];
+    float gxf[UNR], gyf[UNR];
+    Rec4 r[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const size_t a = o0 + (size_t)(e0 + u) * SLICE;
+      q[u] = ldcs_i(L.idx0 + a);
+      gxf[u] = ldcs_f(L.gx0 + a);
+      gyf[u] = ldcs_f(L.gy0 + a);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (e0 + u >= cnt) q[u] = -1;
+      r[u] = ldrec(st.NB, (q[u] < 0 || q[u] >= P.nnode) ? 0 : q[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (q[u] < 0) continue;
+      const double gx = (double)gxf[u], gy = (double)gyf[u];
+      if (q[u] < P.nnode) {  // type 1: q is the node; r = {vx, vy, m, rho}
+        const double h1 = gx * r[u].c / r[u].d;
+        const double h2 = gy * r[u].c / r[u].d;
+        g11 = g11 + (r[u].a - vp.x) * h1;
+        g12 = g12 + (r[u].a - vp.x) * h2;
+        g21 = g21 + (r[u].b - vp.y) * h1;
+        g22 = g22 + (r[u].b - vp.y) * h2;
         if (FIRST && P.cspm) {
-          const double2 xq = ld2(st.x, q);
+          const double2 xq = ld2(st.x, q[u]);
           ae1 = ae1 + (xq.x - xp.x) * h1;
           ae2 = ae2 + (xq.y - xp.y) * h1;
           ae3 = ae3 + (xq.x - xp.x) * h2;
           ae4 = ae4 + (xq.y - xp.y) * h2;
         }
       } else {  // type 9: q is a dummy wall particle (no-slip mirror velocity), main:552-575
+        const int qd = q[u];
         const double beta_max = 1.5, vel_wall = 0.0;
-        const double wall = (double)st.wallpos[q];
-        const double2 xq = ld2(st.x, q);
+        const double wall = (double)st.wallpos[qd];
+        const double2 xq = ld2(st.x, qd);
         double da, db;
-        if (st.horiz[q] == 1.f) {
+        if (st.horiz[qd] == 1.f) {
           da = fabs(xp.y - wall);
           db = fabs(xq.y - wall);
         } else {
@@ -218,7 +387,7 @@ k_sweep_b(DevParams P, SlotMap M, SortArrays So, ListPtrs L, const int *__restri
         const double beta = (bq < beta_max) ? bq : beta_max;
         const double dvx = vp.x * (1 - beta) + beta * vel_wall;
         const double dvy = vp.y * (1 - beta) + beta * vel_wall;
-        const double mq = st.mass[q], rq = st.rho[q];
+        const double mq = st.mass[qd], rq = st.rho[qd];
         const double h1 = gx * mq / rq;
         const double h2 = gy * mq / rq;
         g11 = g11 + (vp.x - dvx) * h1;
@@ -227,134 +396,172 @@ k_sweep_b(DevParams P, SlotMap M, SortArrays So, ListPtrs L, const int *__restri
         g22 = g22 + (vp.y - dvy) * h2;
       }
     }
-    if (P.cspm) {
-      double *AEp = st.AE + 5 * (size_t)id;
-      if (FIRST) {
-        ae5 = ae1 * ae4 - ae2 * ae3;
-        if (fabs(ae5) < P.ae_thr) {
-          ae5 = 1;
-          ae1 = 1;
-          ae2 = 0;
-          ae3 = 0;
-          ae4 = 1;
-        } else {
-          ae5 = 1 / ae5;
-        }
-        AEp[0] = ae1;
-        AEp[1] = ae2;
-        AEp[2] = ae3;
-        AEp[3] = ae4;
-        AEp[4] = ae5;
+  }
+  if (P.cspm) {
+    double *AEp = st.AE + 5 * (size_t)id;
+    if (FIRST) {
+      ae5 = ae1 * ae4 - ae2 * ae3;
+      if (fabs(ae5) < P.ae_thr) {
+        ae5 = 1;
+        ae1 = 1;
+        ae2 = 0;
+        ae3 = 0;
+        ae4 = 1;
       } else {
-        ae1 = AEp[0];
-        ae2 = AEp[1];
-        ae3 = AEp[2];
-        ae4 = AEp[3];
-        ae5 = AEp[4];
+        ae5 = 1 / ae5;
       }
-      // main:619-622: the second statement sees the already-corrected first column
-      g11 = ae5 * (ae1 * g11 + ae2 * g12);
-      g12 = ae5 * (ae3 * g11 + ae4 * g12);
-      g21 = ae5 * (ae1 * g21 + ae2 * g22);
-      g22 = ae5 * (ae3 * g21 + ae4 * g22);
-    }
-    // div1, main:633-636
-    const double d1 = -(P.D11 * g11 + P.D12 * g22);
-    const double d2 = -(P.D12 * g11 + P.D22 * g22);
-    const double d3 = -(P.D33 * g21 + P.D33 * g12);
-    const double d4 = -(P.D41 * g11 + P.D42 * g22);
-    // plastic_terms, mat:1884-1954
-    double Gs[4] = {0.0, 0.0, 0.0, 0.0}, der1 = 0.0;
-    if (P.ntype_eco > 1) {
-      Stress4 s2 = sp_;
-      if (P.ntype_solid == 1) s2.s4 = P.props[3] * (s2.s1 + s2.s2);
-      double vivel[4] = {0.0, 0.0, 0.0, 0.0};
-      if (P.ncrit <= 5) {
-        von_mises_perzyna(P, s2, st.epsp[id], Gs, vivel);
-      } else if (P.ncrit == 12) {
-        double G2[4];
-        double fd = st.fdp[id];
-        drucker_prager(P, s2, g11, g12, g21, g22, fd, G2, vivel);
-        st.fdp[id] = fd;
-        Gs[0] = -G2[0];
-        Gs[1] = -G2[1];
-        Gs[2] = -G2[2];
-        Gs[3] = -G2[3];
-      }
-      if (P.ntype_solid == 0)
-        der1 = vivel[0];
-      else
-        der1 = sqrt((2.0 * (vivel[0] * vivel[0] + vivel[1] * vivel[1] + vivel[3] * vivel[3]) + vivel[2] * vivel[2]) / 3.0);
-    }
-    double rke = st.RKe[ks] + der1 * f2;
-    // Jaumann terms, main:751-757
-    double sp1 = 0.0, sp2 = 0.0, sp3 = 0.0, sp4 = 0.0;
-    if (P.update_x) {
-      const double o1 = 0.5 * (g12 - g21), o2 = -0.5 * (g12 - g21);
-      sp1 = 2 * o1 * sp_.s3;
-      sp2 = 2 * o2 * sp_.s3;
-      sp3 = o2 * sp_.s1 + o1 * sp_.s2;
-    }
-    const double r1 = -d1 + sp1 + Gs[0];
-    const double r2 = -d2 + sp2 + Gs[1];
-    const double r3 = -d3 + sp3 + Gs[2];
-    const double r4 = -d4 + sp4 + Gs[3];
-    Stress4 rk = ld4(st.RKs, ks);
-    rk.s1 = rk.s1 + f2 * r1;
-    rk.s2 = rk.s2 + f2 * r2;
-    rk.s3 = rk.s3 + f2 * r3;
-    rk.s4 = rk.s4 + f2 * r4;
-    const Stress4 s0 = ld4(st.stress0, ks);
-    Stress4 sn;
-    if (!last) {
-      st4(st.RKs, ks, rk);
-      st.RKe[ks] = rke;
-      sn.s1 = s0.s1 + f1next * (P.dt) * r1;
-      sn.s2 = s0.s2 + f1next * (P.dt) * r2;
-      sn.s3 = s0.s3 + f1next * (P.dt) * r3;
-      sn.s4 = s0.s4 + f1next * (P.dt) * r4;
+      AEp[0] = ae1;
+      AEp[1] = ae2;
+      AEp[2] = ae3;
+      AEp[3] = ae4;
+      AEp[4] = ae5;
     } else {
-      sn.s1 = s0.s1 + (P.dt / 6) * rk.s1;
-      sn.s2 = s0.s2 + (P.dt / 6) * rk.s2;
-      sn.s3 = s0.s3 + (P.dt / 6) * rk.s3;
-      sn.s4 = s0.s4 + (P.dt / 6) * rk.s4;
-      // update_strain, mat:1864-1880 with Ddev_strn = RK_dev_strain/6 (main:799)
-      st.epsp[id] = st.epsp[id] + P.dt * (rke / 6);
+      ae1 = AEp[0];
+      ae2 = AEp[1];
+      ae3 = AEp[2];
+      ae4 = AEp[3];
+      ae5 = AEp[4];
     }
-    if (P.adapt) adapt_stress(P, sn);
-    double2 vn = vp;
-    apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
-    st2(st.V[a_], id, vn);
-    st4(st.S[a_], id, sn);
+    // main:619-622: the second statement sees the already-corrected first column
+    g11 = ae5 * (ae1 * g11 + ae2 * g12);
+    g12 = ae5 * (ae3 * g11 + ae4 * g12);
+    g21 = ae5 * (ae1 * g21 + ae2 * g22);
+    g22 = ae5 * (ae3 * g21 + ae4 * g22);
+  }
+  // div1, main:633-636
+  const double d1 = -(P.D11 * g11 + P.D12 * g22);
+  const double d2 = -(P.D12 * g11 + P.D22 * g22);
+  const double d3 = -(P.D33 * g21 + P.D33 * g12);
+  const double d4 = -(P.D41 * g11 + P.D42 * g22);
+  // plastic_terms, mat:1884-1954
+  double Gs[4] = {0.0, 0.0, 0.0, 0.0}, der1 = 0.0;
+  if (P.ntype_eco > 1) {
+    Stress4 s2 = sp_;
+    if (P.ntype_solid == 1) s2.s4 = P.props[3] * (s2.s1 + s2.s2);
+    double vivel[4] = {0.0, 0.0, 0.0, 0.0};
+    if (P.ncrit <= 5) {
+      von_mises_perzyna(P, s2, st.epsp[id], Gs, vivel);
+    } else if (P.ncrit == 12) {
+      double G2[4];
+      double fd = st.fdp[id];
+      drucker_prager(P, s2, g11, g12, g21, g22, fd, G2, vivel);
+      st.fdp[id] = fd;
+      Gs[0] = -G2[0];
+      Gs[1] = -G2[1];
+      Gs[2] = -G2[2];
+      Gs[3] = -G2[3];
+    }
+    if (P.ntype_solid == 0)
+      der1 = vivel[0];
+    else
+      der1 = sqrt((2.0 * (vivel[0] * vivel[0] + vivel[1] * vivel[1] + vivel[3] * vivel[3]) + vivel[2] * vivel[2]) / 3.0);
+  }
+  const double rke = st.RKe[ks] + der1 * f2;
+  // Jaumann terms, main:751-757
+  double sp1 = 0.0, sp2 = 0.0, sp3 = 0.0, sp4 = 0.0;
+  if (P.update_x) {
+    const double o1 = 0.5 * (g12 - g21), o2 = -0.5 * (g12 - g21);
+    sp1 = 2 * o1 * sp_.s3;
+    sp2 = 2 * o2 * sp_.s3;
+    sp3 = o2 * sp_.s1 + o1 * sp_.s2;
+  }
+  const double r1 = -d1 + sp1 + Gs[0];
+  const double r2 = -d2 + sp2 + Gs[1];
+  const double r3 = -d3 + sp3 + Gs[2];
+  const double r4 = -d4 + sp4 + Gs[3];
+  Stress4 rk = ld4(st.RKs, ks);
+  rk.s1 = rk.s1 + f2 * r1;
+  rk.s2 = rk.s2 + f2 * r2;
+  rk.s3 = rk.s3 + f2 * r3;
+  rk.s4 = rk.s4 + f2 * r4;
+  const Stress4 s0 = ld4(st.stress0, ks);
+  Stress4 sn;
+  double ep = st.epsp[id];
+  if (!last) {
+    st4(st.RKs, ks, rk);
+    st.RKe[ks] = rke;
+    sn.s1 = s0.s1 + f1next * (P.dt) * r1;
+    sn.s2 = s0.s2 + f1next * (P.dt) * r2;
+    sn.s3 = s0.s3 + f1next * (P.dt) * r3;
+    sn.s4 = s0.s4 + f1next * (P.dt) * r4;
   } else {
-    // ---------------- node ----------------
-    const double *sorp = st.sor + 3 * (size_t)id;
-    const double so1 = sorp[0], so2 = sorp[1], so3 = sorp[2];
-    const double rp = st.rho[id];
-    double a11 = 0.0, a12 = 0.0, a21 = 0.0, a22 = 0.0, a31 = 0.0, a32 = 0.0;  // grad2_tmp(s,k)
-    for (int e = 0; e < cnt; ++e) {
-      const size_t a = o0 + (size_t)e * SLICE;
-      const int q = L.idx0[a];
-      const double gx = (double)L.gx0[a], gy = (double)L.gy0[a];
-      const double mq = st.mass[q];
-      double q1, q2, q3;
-      if (q < P.ntotal) {  // type 1: q is the stress particle
-        const double *sorq = st.sor + 3 * (size_t)q;
-        q1 = sorq[0];
-        q2 = sorq[1];
-        q3 = sorq[2];
+    sn.s1 = s0.s1 + (P.dt / 6) * rk.s1;
+    sn.s2 = s0.s2 + (P.dt / 6) * rk.s2;
+    sn.s3 = s0.s3 + (P.dt / 6) * rk.s3;
+    sn.s4 = s0.s4 + (P.dt / 6) * rk.s4;
+    // update_strain, mat:1864-1880 with Ddev_strn = RK_dev_strain/6 (main:799)
+    ep = ep + P.dt * (rke / 6);
+    st.epsp[id] = ep;
+  }
+  if (P.adapt) adapt_stress(P, sn);
+  double2 vn = vp;
+  apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
+  Rec8 *o = st.SA + ks;
+  reinterpret_cast<double2 *>(o)[0] = make_double2(sn.s1, sn.s2);
+  reinterpret_cast<double2 *>(o)[1] = make_double2(sn.s3, sn.s4);
+  reinterpret_cast<double2 *>(o)[2] = make_double2(st.mor[id], ep);
+  st2(st.SVa, ks, vn);
+}
+
+template <bool FIRST>
+__global__ void __launch_bounds__(128)
+k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n0,
+               const int *__restrict__ n1, StatePtrs st, double f1next, double f2, int last) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= M.nn) return;
+  const int t = k;
+  const int id = order_n[k];
+  const int cnt = n0[t];
+  const int lane = t & 31, sl = t / SLICE;
+  const size_t o0 = (size_t)L.off0[sl] + lane;
+  const Rec4 self = ldrec(st.NB, id);  // {vx, vy, m, rho}
+  const double2 vp = make_double2(self.a, self.b);
+  const double rp = self.d;
+  const Stress4 sp_ = ld4(st.NSb, id);
+  const double r2p = rp * rp;
+  const double so1 = sp_.s1 / r2p, so2 = sp_.s2 / r2p, so3 = sp_.s3 / r2p;  // stress(1:3,i)/rho(i)**2
+  const double2 xp = ld2(st.x, id);
+  double ae1 = 0.0, ae2 = 0.0, ae3 = 0.0, ae4 = 0.0, ae5 = 1.0;
+  double a11 = 0.0, a12 = 0.0, a21 = 0.0, a22 = 0.0, a31 = 0.0, a32 = 0.0;  // grad2_tmp(s,k)
+  for (int e0 = 0; e0 < cnt; e0 += UNR) {
+    int q[UNR];
+    float gxf[UNR], gyf[UNR];
+    Rec4 r[UNR];
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      const size_t a = o0 + (size_t)(e0 + u) * SLICE;
+      q[u] = ldcs_i(L.idx0 + a);
+      gxf[u] = ldcs_f(L.gx0 + a);
+      gyf[u] = ldcs_f(L.gy0 + a);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (e0 + u >= cnt) q[u] = -1;
+      r[u] = ldrec(st.SB, (q[u] < 0 || q[u] >= P.ntotal) ? 0 : q[u] - P.nnode);
+    }
+#pragma unroll
+    for (int u = 0; u < UNR; ++u) {
+      if (q[u] < 0) continue;
+      const double gx = (double)gxf[u], gy = (double)gyf[u];
+      double q1, q2, q3, mq;
+      if (q[u] < P.ntotal) {  // type 1: q is the stress particle; r = {s1/rho^2, s2/rho^2, s3/rho^2, m}
+        q1 = r[u].a;
+        q2 = r[u].b;
+        q3 = r[u].c;
+        mq = r[u].d;
         if (FIRST && P.cspm) {
-          const double rq = st.rho[q];
+          const double rq = st.rho[q[u]];
           const double h1b = -gx * mq / rq;
           const double h2b = -gy * mq / rq;
-          const double2 xq = ld2(st.x, q);
+          const double2 xq = ld2(st.x, q[u]);
           ae1 = ae1 + (xq.x - xp.x) * h1b;
           ae2 = ae2 + (xq.y - xp.y) * h1b;
           ae3 = ae3 + (xq.x - xp.x) * h2b;
           ae4 = ae4 + (xq.y - xp.y) * h2b;
         }
       } else {  // type 6: dummy takes the node's stress (main:580)
-        const double rq = st.rho[q];
+        const double rq = st.rho[q[u]];
+        mq = st.mass[q[u]];
         q1 = sp_.s1 / (rq * rq);
         q2 = sp_.s2 / (rq * rq);
         q3 = sp_.s3 / (rq * rq);
@@ -367,110 +574,135 @@ k_sweep_b(DevParams P, SlotMap M, SortArrays So, ListPtrs L, const int *__restri
       a31 = a31 - mq * (gx * c3);
       a32 = a32 - mq * (gy * c3);
     }
-    if (P.cspm) {
-      double *AEp = st.AE + 5 * (size_t)id;
-      if (FIRST) {
-        ae5 = ae1 * ae4 - ae2 * ae3;
-        if (fabs(ae5) < P.ae_thr) {
-          ae5 = 1;
-          ae1 = 1;
-          ae2 = 0;
-          ae3 = 0;
-          ae4 = 1;
-        } else {
-          ae5 = 1 / ae5;
-        }
-        AEp[0] = ae1;
-        AEp[1] = ae2;
-        AEp[2] = ae3;
-        AEp[3] = ae4;
-        AEp[4] = ae5;
+  }
+  if (P.cspm) {
+    double *AEp = st.AE + 5 * (size_t)id;
+    if (FIRST) {
+      ae5 = ae1 * ae4 - ae2 * ae3;
+      if (fabs(ae5) < P.ae_thr) {
+        ae5 = 1;
+        ae1 = 1;
+        ae2 = 0;
+        ae3 = 0;
+        ae4 = 1;
       } else {
-        ae1 = AEp[0];
-        ae2 = AEp[1];
-        ae3 = AEp[2];
-        ae4 = AEp[3];
-        ae5 = AEp[4];
+        ae5 = 1 / ae5;
       }
-      // main:623-626: only stress components 1..ndimn are corrected
-      a11 = ae5 * (ae1 * a11 + ae2 * a12);
-      a12 = ae5 * (ae3 * a11 + ae4 * a12);
-      a21 = ae5 * (ae1 * a21 + ae2 * a22);
-      a22 = ae5 * (ae3 * a21 + ae4 * a22);
+      AEp[0] = ae1;
+      AEp[1] = ae2;
+      AEp[2] = ae3;
+      AEp[3] = ae4;
+      AEp[4] = ae5;
+    } else {
+      ae1 = AEp[0];
+      ae2 = AEp[1];
+      ae3 = AEp[2];
+      ae4 = AEp[3];
+      ae5 = AEp[4];
     }
-    const double dv1 = -(a11 + a32);  // div2, main:641-642
-    const double dv2 = -(a31 + a22);
-    // gravity_force, mat:2809-2871
-    const double sg1 = P.grav[0] - P.damping * vp.x;
-    const double sg2 = P.grav[1] - P.damping * vp.y;
-    // artificial_viscosity, main:826-904 (fp32 locals and accumulators, list order)
-    double av1 = 0.0, av2 = 0.0;
-    if (P.alpha > 0 || P.beta > 0) {
-      const int cntc = n1[t];
-      const size_t oc = (size_t)L.offC[sl] + lane;
-      const double hp = st.hsml[id];
-      float acc1 = 0.f, acc2 = 0.f;
-      for (int e = 0; e < cntc; ++e) {
-        const size_t a = oc + (size_t)e * SLICE;
-        const int q = L.idxC[a];
-        const float gxf = L.gxC[a], gyf = L.gyC[a];
-        const double2 xq = ld2(st.x, q);
-        const double2 vq = ld2(Vb, q);
-        const float xij = (float)(xp.x - xq.x);
-        const float yij = (float)(xp.y - xq.y);
-        const float h = (float)(0.5 * (hp + st.hsml[q]));
-        const float rho2 = (float)(0.5 * (rp + st.rho[q]));
+    // main:623-626: only stress components 1..ndimn are corrected
+    a11 = ae5 * (ae1 * a11 + ae2 * a12);
+    a12 = ae5 * (ae3 * a11 + ae4 * a12);
+    a21 = ae5 * (ae1 * a21 + ae2 * a22);
+    a22 = ae5 * (ae3 * a21 + ae4 * a22);
+  }
+  const double dv1 = -(a11 + a32);  // div2, main:641-642
+  const double dv2 = -(a31 + a22);
+  // gravity_force, mat:2809-2871
+  const double sg1 = P.grav[0] - P.damping * vp.x;
+  const double sg2 = P.grav[1] - P.damping * vp.y;
+  // artificial_viscosity, main:826-904 (fp32 locals and accumulators, list order)
+  double av1 = 0.0, av2 = 0.0;
+  if (P.alpha > 0 || P.beta > 0) {
+    const int cntc = n1[t];
+    const size_t oc = (size_t)L.offC[sl] + lane;
+    const double hp = st.hsml[id];
+    float acc1 = 0.f, acc2 = 0.f;
+    for (int e0 = 0; e0 < cntc; e0 += UNR) {
+      int q[UNR];
+      float gxf[UNR], gyf[UNR];
+      Rec4 r[UNR];
+      double2 xq[UNR];
+      double hq[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        const size_t a = oc + (size_t)(e0 + u) * SLICE;
+        q[u] = ldcs_i(L.idxC + a);
+        gxf[u] = ldcs_f(L.gxC + a);
+        gyf[u] = ldcs_f(L.gyC + a);
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (e0 + u >= cntc) q[u] = -1;
+        const int qq = q[u] < 0 ? 0 : q[u];
+        r[u] = ldrec(st.NB, qq);
+        xq[u] = ld2(st.x, qq);
+        hq[u] = st.hsml[qq];
+      }
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (q[u] < 0) continue;
+        const float xij = (float)(xp.x - xq[u].x);
+        const float yij = (float)(xp.y - xq[u].y);
+        const float h = (float)(0.5 * (hp + hq[u]));
+        const float rho2 = (float)(0.5 * (rp + r[u].d));
         const float cs = 600.f;
-        float div_u = (float)((double)xij * (vp.x - vq.x));
-        div_u = (float)((double)div_u + (double)yij * (vp.y - vq.y));
+        float div_u = (float)((double)xij * (vp.x - r[u].a));
+        div_u = (float)((double)div_u + (double)yij * (vp.y - r[u].b));
         const float sq = sqrtf(xij * xij + yij * yij);
         const float theta = (h * div_u) / (sq * sq + 0.01f * (h * h));
         float visc = 0.f;
         if (div_u < 0)
           visc = (float)((-P.alpha * (double)cs * (double)theta + P.beta * (double)(theta * theta)) / (double)rho2);
-        const double mq = st.mass[q];
-        acc1 = (float)((double)acc1 + (double)(visc * gxf) * mq);
-        acc2 = (float)((double)acc2 + (double)(visc * gyf) * mq);
+        acc1 = (float)((double)acc1 + (double)(visc * gxf[u]) * r[u].c);
+        acc2 = (float)((double)acc2 + (double)(visc * gyf[u]) * r[u].c);
       }
-      av1 = (double)(-acc1);
-      av2 = (double)(-acc2);
     }
-    const double r1 = -dv1 + sg1 + av1 + 0.0 + 0.0;  // + f_bound + art_force (both zero here, main:763-764)
-    const double r2 = -dv2 + sg2 + av2 + 0.0 + 0.0;
-    double2 rk = ld2(st.RKv, id);
-    rk.x = rk.x + f2 * r1;
-    rk.y = rk.y + f2 * r2;
-    const double2 v0 = ld2(st.vel0, id);
-    double2 vn;
-    if (!last) {
-      st2(st.RKv, id, rk);
-      vn.x = v0.x + f1next * (P.dt) * r1;
-      vn.y = v0.y + f1next * (P.dt) * r2;
-    } else {
-      vn.x = v0.x + (P.dt / 6) * rk.x;
-      vn.y = v0.y + (P.dt / 6) * rk.y;
-    }
-    Stress4 sn = sp_;
-    if (P.adapt) adapt_stress(P, sn);
-    apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
-    st2(st.V[a_], id, vn);
-    st4(st.S[a_], id, sn);
+    av1 = (double)(-acc1);
+    av2 = (double)(-acc2);
   }
+  const double r1 = -dv1 + sg1 + av1 + 0.0 + 0.0;  // + f_bound + art_force (both zero here, main:763-764)
+  const double r2 = -dv2 + sg2 + av2 + 0.0 + 0.0;
+  double2 rk = ld2(st.RKv, id);
+  rk.x = rk.x + f2 * r1;
+  rk.y = rk.y + f2 * r2;
+  const double2 v0 = ld2(st.vel0, id);
+  double2 vn;
+  if (!last) {
+    st2(st.RKv, id, rk);
+    vn.x = v0.x + f1next * (P.dt) * r1;
+    vn.y = v0.y + f1next * (P.dt) * r2;
+  } else {
+    vn.x = v0.x + (P.dt / 6) * rk.x;
+    vn.y = v0.y + (P.dt / 6) * rk.y;
+  }
+  Stress4 sn = sp_;
+  if (P.adapt) adapt_stress(P, sn);
+  apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
+  strec(st.NA, id, vn.x, vn.y, st.mor[id], 0.0);
+  st4(st.NSa, id, sn);
 }
 
 // ------------------------------------------------------------------------------------------------------
 // Position update, main:140-182: XSPH_update (main:189-239) or the fp32 mid-velocity rule; displ.
+// Velocities come from format B (the state at the end of the step).
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
-k_move(DevParams P, SlotMap M, SortArrays So, ListPtrs L, const int *__restrict__ n1, StatePtrs st, int cur,
+k_move(DevParams P, SlotMap M, SortArrays So, ListPtrs L, const int *__restrict__ n1, StatePtrs st,
        double *__restrict__ x, const double *__restrict__ x00, double *__restrict__ displ) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= M.nnp + M.nsp) return;
-  int sp, k;
-  if (!slot_decode(M, t, sp, k)) return;
-  const int id = So.order[sp][k];
-  const double *__restrict__ Vc = st.V[cur];
-  const double2 vp = ld2(Vc, id);
+  const bool is_node = t < M.nnp;
+  const int k = is_node ? t : t - M.nnp;
+  if (k >= (is_node ? M.nn : M.ns)) return;
+  const int id = is_node ? So.order[0][k] : So.order[1][k];
+  double2 vp;
+  if (is_node) {
+    const Rec4 r = ldrec(st.NB, id);
+    vp = make_double2(r.a, r.b);
+  } else {
+    vp = ld2(st.SVb, id - P.nnode);
+  }
   const double2 xp = ld2(x, id);
   if (P.update_x) {
     double2 xn;
@@ -478,27 +710,60 @@ k_move(DevParams P, SlotMap M, SortArrays So, ListPtrs L, const int *__restrict_
       const int cnt = n1[t];
       const int lane = t & 31, sl = t / SLICE;
       double sx = 0.0, sy = 0.0;
-      if (sp == SP_NODE) {
+      if (is_node) {
         const size_t oc = (size_t)L.offC[sl] + lane;
-        for (int e = 0; e < cnt; ++e) {
-          const size_t a = oc + (size_t)e * SLICE;
-          const int q = L.idxC[a];
-          const double w = (double)L.wC[a];
-          const double2 vq = ld2(Vc, q);
-          const double mr = st.mor[q];
-          sx = sx + mr * (vq.x - vp.x) * w;
-          sy = sy + mr * (vq.y - vp.y) * w;
+        for (int e0 = 0; e0 < cnt; e0 += UNR) {
+          int q[UNR];
+          float w[UNR];
+          Rec4 r[UNR];
+          double mr[UNR];
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const size_t a = oc + (size_t)(e0 + u) * SLICE;
+            q[u] = ldcs_i(L.idxC + a);
+            w[u] = ldcs_f(L.wC + a);
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            if (e0 + u >= cnt) q[u] = -1;
+            r[u] = ldrec(st.NB, q[u] < 0 ? 0 : q[u]);
+            mr[u] = st.mor[q[u] < 0 ? 0 : q[u]];
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            if (q[u] < 0) continue;
+            const double wd = (double)w[u];
+            sx = sx + mr[u] * (r[u].a - vp.x) * wd;
+            sy = sy + mr[u] * (r[u].b - vp.y) * wd;
+          }
         }
       } else {
         const size_t od = (size_t)L.offD[sl] + lane;
-        for (int e = 0; e < cnt; ++e) {
-          const size_t a = od + (size_t)e * SLICE;
-          const int q = L.idxD[a];
-          const double w = (double)L.wD[a];
-          const double2 vq = ld2(Vc, q);
-          const double mr = st.mor[q];
-          sx = sx + mr * (vq.x - vp.x) * w;
-          sy = sy + mr * (vq.y - vp.y) * w;
+        for (int e0 = 0; e0 < cnt; e0 += UNR) {
+          int q[UNR];
+          float w[UNR];
+          double2 vq[UNR];
+          double mr[UNR];
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            const size_t a = od + (size_t)(e0 + u) * SLICE;
+            q[u] = ldcs_i(L.idxD + a);
+            w[u] = ldcs_f(L.wD + a);
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            if (e0 + u >= cnt) q[u] = -1;
+            const int qq = q[u] < 0 ? P.nnode : q[u];
+            vq[u] = ld2(st.SVb, qq - P.nnode);
+            mr[u] = st.mor[qq];
+          }
+#pragma unroll
+          for (int u = 0; u < UNR; ++u) {
+            if (q[u] < 0) continue;
+            const double wd = (double)w[u];
+            sx = sx + mr[u] * (vq[u].x - vp.x) * wd;
+            sy = sy + mr[u] * (vq[u].y - vp.y) * wd;
+          }
         }
       }
       const double eps = 0.5;
@@ -512,11 +777,11 @@ k_move(DevParams P, SlotMap M, SortArrays So, ListPtrs L, const int *__restrict_
       xn.y = xp.y + (double)hy * P.dt;
     }
     st2(x, id, xn);
-    if (sp == SP_NODE) {
+    if (is_node) {
       const double2 x0 = ld2(x00, id);
       st2(displ, id, make_double2(xn.x - x0.x, xn.y - x0.y));  // main:171
     }
-  } else if (sp == SP_NODE) {
+  } else if (is_node) {
     const double2 v0 = ld2(st.vx0, id);
     double2 d = ld2(displ, id);
     d.x = d.x + 0.5 * (v0.x + vp.x) * P.dt;  // main:180
@@ -526,12 +791,13 @@ k_move(DevParams P, SlotMap M, SortArrays So, ListPtrs L, const int *__restrict_
 }
 
 // shift_stress_points, main:244-368 (outside approach): one thread per node re-seats its stress particles.
-__global__ void k_shift(DevParams P, const double *__restrict__ Vc, double *__restrict__ x, double *__restrict__ x_10,
+__global__ void k_shift(DevParams P, const Rec4 *__restrict__ NB, double *__restrict__ x, double *__restrict__ x_10,
                         double *__restrict__ disp_10, const int *__restrict__ bc_int, const float *__restrict__ n_int) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.nnode) return;
   const double2 xi = ld2(x, i);
-  const double2 v = ld2(Vc, i);
+  const Rec4 rr = ldrec(NB, i);
+  const double2 v = make_double2(rr.a, rr.b);
   const int k = P.nnode + i * P.npoints;  // 0-based id of this node's first stress particle
   const double dx = P.dx;
   if (P.itimestep % P.shift_update == 0) {

@@ -186,3 +186,15 @@ def test_product_never_touches_oracle():
             if f.endswith((".py", ".cpp", ".hpp", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "oracle_binding" not in txt and "liboracle" not in txt and "sph_oracle" not in txt, f
+
+
+def test_fast_division_identity(tmp_path):
+    """div_rn() (grid_kernels.cuh) must equal the IEEE quotient bit for bit: 2e7 random + adversarial cases on the
+    host FPU (600 M were run once); the GPU pair-weight parity tests cover the device side."""
+    import subprocess
+    exe = str(tmp_path / "div_identity")
+    src = os.path.join(ROOT, "tests", "native", "div_identity.cpp")
+    subprocess.run(["g++", "-O2", "-mfma", "-ffp-contract=off", "-o", exe, src], check=True)
+    r = subprocess.run([exe, "20000000"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stdout
+    assert "two-step=0" in r.stdout
