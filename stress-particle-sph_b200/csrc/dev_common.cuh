@@ -61,14 +61,18 @@ __device__ __forceinline__ void st2(double *p, int i, double2 v) { reinterpret_c
 struct Stress4 {
   double s1, s2, s3, s4;
 };
+// (4, n) arrays are 32-byte aligned per particle: one 256-bit access each (LDG/STG.E.ENL2.256 on sm_100a)
 __device__ __forceinline__ Stress4 ld4(const double *p, int i) {
-  const double2 a = reinterpret_cast<const double2 *>(p)[2 * i];
-  const double2 b = reinterpret_cast<const double2 *>(p)[2 * i + 1];
-  return Stress4{a.x, a.y, b.x, b.y};
+  Stress4 s;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
+               : "=d"(s.s1), "=d"(s.s2), "=d"(s.s3), "=d"(s.s4)
+               : "l"(p + 4 * (size_t)i));
+  return s;
 }
 __device__ __forceinline__ void st4(double *p, int i, const Stress4 &s) {
-  reinterpret_cast<double2 *>(p)[2 * i] = make_double2(s.s1, s.s2);
-  reinterpret_cast<double2 *>(p)[2 * i + 1] = make_double2(s.s3, s.s4);
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p + 4 * (size_t)i), "d"(s.s1), "d"(s.s2), "d"(s.s3),
+               "d"(s.s4)
+               : "memory");
 }
 
 // ---- smoothing kernel, main:1440-1538 (skf = 1, ndimn = 2); fp64 evaluation, caller rounds to fp32 ----

@@ -61,19 +61,131 @@ struct StatePtrs {
   double *RKe;      // (nstress)
 };
 
-__device__ __forceinline__ Rec4 ldrec(const Rec4 *p, int i) {
-  const double2 a = reinterpret_cast<const double2 *>(p)[2 * (size_t)i];
-  const double2 b = reinterpret_cast<const double2 *>(p)[2 * (size_t)i + 1];
-  return Rec4{a.x, a.y, b.x, b.y};
+// 32-byte records move with one 256-bit access (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a): a gathered record
+// costs one L1 sector access instead of two 128-bit ones -- the L1 sector rate bounds the pair-sum kernels.
+__device__ __forceinline__ Rec4 ld256(const void *p) {
+  Rec4 r;
+  asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
+  return r;
 }
+__device__ __forceinline__ void st256(void *p, double a, double b, double c, double d) {
+  asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
+}
+__device__ __forceinline__ Rec4 ldrec(const Rec4 *p, int i) { return ld256(p + i); }
 __device__ __forceinline__ void strec(Rec4 *p, int i, double a, double b, double c, double d) {
-  reinterpret_cast<double2 *>(p)[2 * (size_t)i] = make_double2(a, b);
-  reinterpret_cast<double2 *>(p)[2 * (size_t)i + 1] = make_double2(c, d);
+  st256(p + i, a, b, c, d);
 }
 __device__ __forceinline__ int ldcs_i(const int *p) { return __ldcs(p); }
 __device__ __forceinline__ float ldcs_f(const float *p) { return __ldcs(p); }
 
 constexpr int UNR = 4;  // list entries in flight per thread
+
+// ------------------------------------------------------------------------------------------------------
+// Streaming of a warp's ELL slice through shared memory.
+// The slice of one warp is contiguous in every list array (row e = 32 consecutive 4-byte entries, rows back
+// to back), so a group of 4 rows of one array is 512 contiguous bytes = one 16-byte cp.async per lane. Each
+// warp owns a private ring of ELL_NG groups per array; HBM latency is hidden by the ring depth, independent
+// of register count, and the neighbour gathers for group g+1 are issued before group g is consumed.
+// ------------------------------------------------------------------------------------------------------
+#ifndef SPSPH_PREFETCH
+#define SPSPH_PREFETCH 0  // 1: gathers of group g+1 are issued before group g is consumed (register double buffer)
+#endif
+#ifndef SPSPH_MINB
+#define SPSPH_MINB 4      // min resident blocks per SM requested from ptxas for the sweep kernels
+#endif
+constexpr int ELL_GROUP = 4;  // rows per cp.async group
+constexpr int ELL_NG = 4;     // groups in the ring (16 rows = 2 KB per array per warp in flight)
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() {
+  asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
+}
+
+// NARR arrays are streamed (array 0 holds the partner ids). `rows` is the slice width (warp-uniform), `cnt` the
+// calling lane's own list length. gather(q) -> R fetches the partner record (q < 0: past the end);
+// compute(q[4], a1[4], a2[4], rec[4], nvalid) consumes one group of entries in list order (a1/a2: raw 32-bit
+// payloads of arrays 1 and 2; entries u >= nvalid are past the end of this lane's list and must be ignored).
+template <int NARR, class R, class GatherF, class ComputeF>
+__device__ __forceinline__ void ell_stream(const int *const *arr, size_t slice_off, int rows, int cnt, int *smw,
+                                           GatherF gather, ComputeF compute) {
+  const int lane = threadIdx.x & 31;
+  const int ng = (rows + ELL_GROUP - 1) / ELL_GROUP;
+  if (ng == 0) return;
+  auto issue = [&](int g) {
+    if (g < ng) {
+#pragma unroll
+      for (int a = 0; a < NARR; ++a)
+        cp_async16(smw + ((g % ELL_NG) * NARR + a) * (ELL_GROUP * 32) + lane * 4,
+                   arr[a] + slice_off + (size_t)g * (ELL_GROUP * 32) + lane * 4);
+    }
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int g = 0; g < ELL_NG; ++g) issue(g);
+  cp_async_wait<ELL_NG - 1>();
+  __syncwarp();
+  R cur[ELL_GROUP];
+#if SPSPH_PREFETCH
+#pragma unroll
+  for (int u = 0; u < ELL_GROUP; ++u) {
+    const int q = smw[u * 32 + lane];
+    cur[u] = gather(u < cnt ? q : -1);
+  }
+#endif
+  for (int g = 0; g < ng; ++g) {
+#if SPSPH_PREFETCH
+    R nxt[ELL_GROUP];
+    if (g + 1 < ng) {
+      cp_async_wait<ELL_NG - 2>();
+      __syncwarp();
+      const int *sn = smw + (((g + 1) % ELL_NG) * NARR) * (ELL_GROUP * 32);
+#pragma unroll
+      for (int u = 0; u < ELL_GROUP; ++u) {
+        const int q = sn[u * 32 + lane];
+        nxt[u] = gather(((g + 1) * ELL_GROUP + u) < cnt ? q : -1);
+      }
+    }
+    const int *sl = smw + ((g % ELL_NG) * NARR) * (ELL_GROUP * 32);
+#else
+    if (g > 0) {
+      cp_async_wait<ELL_NG - 1>();
+      __syncwarp();
+    }
+    const int *sl = smw + ((g % ELL_NG) * NARR) * (ELL_GROUP * 32);
+#pragma unroll
+    for (int u = 0; u < ELL_GROUP; ++u) {
+      const int qq = sl[u * 32 + lane];
+      cur[u] = gather((g * ELL_GROUP + u) < cnt ? qq : -1);
+    }
+#endif
+    int q[ELL_GROUP], a1[ELL_GROUP], a2[ELL_GROUP];
+#pragma unroll
+    for (int u = 0; u < ELL_GROUP; ++u) {
+      q[u] = sl[u * 32 + lane];
+      a1[u] = NARR > 1 ? sl[(ELL_GROUP * 32) + u * 32 + lane] : 0;
+      a2[u] = NARR > 2 ? sl[2 * (ELL_GROUP * 32) + u * 32 + lane] : 0;
+    }
+    const int nvalid = cnt - g * ELL_GROUP;  // may be <= 0 or > ELL_GROUP
+    compute(q, a1, a2, cur, nvalid);
+    __syncwarp();
+    issue(g + ELL_NG);
+#if SPSPH_PREFETCH
+#pragma unroll
+    for (int u = 0; u < ELL_GROUP; ++u) cur[u] = nxt[u];
+#endif
+  }
+  cp_async_wait<0>();
+}
+__device__ __forceinline__ int warp_max_i(int v) {
+  for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+#define ELL_SMEM(NARR) (ELL_NG * (NARR) * ELL_GROUP * 32)  // ints per warp
 
 // state format conversions at the boundary of the time loop ---------------------------------------------
 // pack: reference-layout vel/stress (upload) -> format B
@@ -163,16 +275,18 @@ __global__ void k_rk_begin(DevParams P, StatePtrs st) {
 //   FIRST: first sweep A of the step -> computes and stores cspm_norm
 // ------------------------------------------------------------------------------------------------------
 template <bool FIRST, bool FROMB>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, SPSPH_MINB)
 k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L, const int *__restrict__ n0,
              StatePtrs st, int do_adapt, int do_bc) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;  // species-sorted index of the stress particle
-  if (k >= M.ns) return;
-  const int t = M.nnp + k;
+  const int k0 = blockIdx.x * blockDim.x + threadIdx.x;  // species-sorted index of the stress particle
+  if ((k0 & ~31) >= M.ns) return;                         // whole warp past the end
+  const bool live = k0 < M.ns;
+  const int k = live ? k0 : 0;
+  const int t = M.nnp + k0;
   const int id = order_s[k];
   const int ks = id - P.nnode;
-  const int cnt = n0[t];
-  const size_t o0 = (size_t)L.off0[t / SLICE] + (t & 31);
+  const int cnt = live ? n0[t] : 0;
+  const int wrows = warp_max_i(cnt);
   double2 v;
   Stress4 s;
   if (FROMB) {
@@ -185,36 +299,35 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
     s = Stress4{a.x, a.y, b.x, b.y};
   }
   double vtx = 0.0, vty = 0.0, nrm = 0.0;
-  for (int e0 = 0; e0 < cnt; e0 += UNR) {
-    int q[UNR];
-    float w[UNR];
-    Rec4 r[UNR];
+  {
+    __shared__ __align__(16) int smem[4 * ELL_SMEM(2)];
+    const int *arrs[2] = {L.idx0, reinterpret_cast<const int *>(L.w0)};
+    const Rec4 *__restrict__ NR = FROMB ? st.NBr : (const Rec4 *)st.NA;
+    ell_stream<2, Rec4>(
+        arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(2),
+        [&](int q) { return ldrec(NR, (q < 0 || q >= P.nnode) ? 0 : q); },
+        [&](const int(&q)[ELL_GROUP], const int(&a1)[ELL_GROUP], const int(&)[ELL_GROUP], const Rec4(&r)[ELL_GROUP],
+            int nvalid) {
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const size_t a = o0 + (size_t)(e0 + u) * SLICE;
-      q[u] = ldcs_i(L.idx0 + a);
-      w[u] = ldcs_f(L.w0 + a);
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if (e0 + u >= cnt || q[u] >= P.nnode) q[u] = -1;  // past the end, or dummy partner (type 9)
-      r[u] = ldrec(FROMB ? st.NBr : (const Rec4 *)st.NA, q[u] < 0 ? 0 : q[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if (q[u] < 0) continue;
-      const double wd = (double)w[u];
-      const double mor = FROMB ? (r[u].c / r[u].d) : r[u].c;  // mass/rho
-      const double h2 = mor * wd;
-      vtx = vtx + r[u].a * h2;
-      vty = vty + r[u].b * h2;
-      if (FIRST) {
-        const double mq = FROMB ? r[u].c : st.mass[q[u]];
-        const double rq = FROMB ? r[u].d : st.rho[q[u]];
-        nrm = nrm + (wd * mq) / rq;
-      }
-    }
+          for (int u = 0; u < ELL_GROUP; ++u) {
+            const bool ok = (u < nvalid) && (q[u] < P.nnode);  // dummy partners (type 9) take no part
+            const double wd = (double)__int_as_float(a1[u]);
+            const double mor = FROMB ? (r[u].c / r[u].d) : r[u].c;  // mass/rho
+            const double h2 = mor * wd;
+            const double tx = vtx + r[u].a * h2, ty = vty + r[u].b * h2;
+            vtx = ok ? tx : vtx;
+            vty = ok ? ty : vty;
+            if (FIRST) {
+              if (ok) {
+                const double mq = FROMB ? r[u].c : st.mass[q[u]];
+                const double rq = FROMB ? r[u].d : st.rho[q[u]];
+                nrm = nrm + (wd * mq) / rq;
+              }
+            }
+          }
+        });
   }
+  if (!live) return;
   if (FIRST)
     st.norm[id] = nrm;
   else
@@ -233,15 +346,17 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
 }
 
 template <bool FIRST, bool FROMB, bool EPSP>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, SPSPH_MINB)
 k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n0,
                StatePtrs st, int do_adapt, int do_bc) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= M.nn) return;
-  const int t = k;
+  const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((k0 & ~31) >= M.nn) return;  // whole warp past the end
+  const bool live = k0 < M.nn;
+  const int k = live ? k0 : 0;
+  const int t = k0;
   const int id = order_n[k];
-  const int cnt = n0[t];
-  const size_t o0 = (size_t)L.off0[t / SLICE] + (t & 31);
+  const int cnt = live ? n0[t] : 0;
+  const int wrows = warp_max_i(cnt);
   double2 v;
   Stress4 s;
   if (FROMB) {
@@ -254,47 +369,56 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
     s = ld4(st.NSa, id);
   }
   double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, te = 0.0, nrm = 0.0;
-  for (int e0 = 0; e0 < cnt; e0 += UNR) {
-    int q[UNR];
-    float w[UNR];
-    Stress4 sq[UNR];
-    double mor[UNR], ep[UNR];
+  {
+    struct RecS {
+      Stress4 s;
+      double mor, ep;
+    };
+    __shared__ __align__(16) int smem[4 * ELL_SMEM(2)];
+    const int *arrs[2] = {L.idx0, reinterpret_cast<const int *>(L.w0)};
+    ell_stream<2, RecS>(
+        arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(2),
+        [&](int q) {
+          const int qs = (q < 0 || q >= P.ntotal) ? 0 : q - P.nnode;
+          RecS r;
+          if (FROMB) {
+            r.s = ld4(st.SFbr, qs);
+            r.mor = st.mor[qs + P.nnode];
+            r.ep = EPSP ? st.epsp[qs + P.nnode] : 0.0;
+          } else {
+            const Rec8 *o = st.SA + qs;
+            const Rec4 a = ld256(o);
+            const double2 c = reinterpret_cast<const double2 *>(o)[2];
+            r.s = Stress4{a.a, a.b, a.c, a.d};
+            r.mor = c.x;
+            r.ep = c.y;
+          }
+          return r;
+        },
+        [&](const int(&q)[ELL_GROUP], const int(&a1)[ELL_GROUP], const int(&)[ELL_GROUP], const RecS(&r)[ELL_GROUP],
+            int nvalid) {
 #pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const size_t a = o0 + (size_t)(e0 + u) * SLICE;
-      q[u] = ldcs_i(L.idx0 + a);
-      w[u] = ldcs_f(L.w0 + a);
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if (e0 + u >= cnt || q[u] >= P.ntotal) q[u] = -1;  // past the end, or dummy partner (type 6)
-      const int qs = q[u] < 0 ? 0 : q[u] - P.nnode;
-      if (FROMB) {
-        sq[u] = ld4(st.SFbr, qs);
-        mor[u] = st.mor[qs + P.nnode];
-        ep[u] = EPSP ? st.epsp[qs + P.nnode] : 0.0;
-      } else {
-        const Rec8 *o = st.SA + qs;
-        const double2 a = reinterpret_cast<const double2 *>(o)[0], b = reinterpret_cast<const double2 *>(o)[1];
-        const double2 c = reinterpret_cast<const double2 *>(o)[2];
-        sq[u] = Stress4{a.x, a.y, b.x, b.y};
-        mor[u] = c.x;
-        ep[u] = c.y;
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if (q[u] < 0) continue;
-      const double wd = (double)w[u];
-      const double h1 = mor[u] * wd;
-      t1 = t1 + sq[u].s1 * h1;
-      t2 = t2 + sq[u].s2 * h1;
-      t3 = t3 + sq[u].s3 * h1;
-      t4 = t4 + sq[u].s4 * h1;
-      if (EPSP) te = te + ep[u] * h1;
-      if (FIRST) nrm = nrm + (wd * st.mass[q[u]]) / st.rho[q[u]];
-    }
+          for (int u = 0; u < ELL_GROUP; ++u) {
+            const bool ok = (u < nvalid) && (q[u] < P.ntotal);  // dummy partners (type 6) take no part
+            const double wd = (double)__int_as_float(a1[u]);
+            const double h1 = r[u].mor * wd;
+            const double n1 = t1 + r[u].s.s1 * h1, n2 = t2 + r[u].s.s2 * h1, n3 = t3 + r[u].s.s3 * h1,
+                         n4 = t4 + r[u].s.s4 * h1;
+            t1 = ok ? n1 : t1;
+            t2 = ok ? n2 : t2;
+            t3 = ok ? n3 : t3;
+            t4 = ok ? n4 : t4;
+            if (EPSP) {
+              const double ne = te + r[u].ep * h1;
+              te = ok ? ne : te;
+            }
+            if (FIRST) {
+              if (ok) nrm = nrm + (wd * st.mass[q[u]]) / st.rho[q[u]];
+            }
+          }
+        });
   }
+  if (!live) return;
   if (FIRST)
     st.norm[id] = nrm;
   else
@@ -320,63 +444,46 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
 // stage accumulation + next-stage predictor, or the final RK4 update when `last`): format B -> format A.
 // ------------------------------------------------------------------------------------------------------
 template <bool FIRST>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, SPSPH_MINB)
 k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L, const int *__restrict__ n0,
              StatePtrs st, double f1next, double f2, int last) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= M.ns) return;
-  const int t = M.nnp + k;
+  const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((k0 & ~31) >= M.ns) return;  // whole warp past the end
+  const bool live = k0 < M.ns;
+  const int k = live ? k0 : 0;
+  const int t = M.nnp + k0;
   const int id = order_s[k];
   const int ks = id - P.nnode;
-  const int cnt = n0[t];
-  const size_t o0 = (size_t)L.off0[t / SLICE] + (t & 31);
+  const int cnt = live ? n0[t] : 0;
+  const int wrows = warp_max_i(cnt);
   const double2 vp = ld2(st.SVb, ks);
   const Stress4 sp_ = ld4(st.SFb, ks);
   double2 xp = make_double2(0.0, 0.0);
   if ((FIRST && P.cspm) || P.ndummy > 0) xp = ld2(st.x, id);
   double ae1 = 0.0, ae2 = 0.0, ae3 = 0.0, ae4 = 0.0, ae5 = 1.0;
   double g11 = 0.0, g12 = 0.0, g21 = 0.0, g22 = 0.0;  // grad1_tmp(d,k): d velocity component, k direction
-  for (int e0 = 0; e0 < cnt; e0 += UNR) {
-    int q[UNR];
-    float gxf[UNR], gyf[UNR];
-    Rec4 r[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const size_t a = o0 + (size_t)(e0 + u) * SLICE;
-      q[u] = ldcs_i(L.idx0 + a);
-      gxf[u] = ldcs_f(L.gx0 + a);
-      gyf[u] = ldcs_f(L.gy0 + a);
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if (e0 + u >= cnt) q[u] = -1;
-      r[u] = ldrec(st.NB, (q[u] < 0 || q[u] >= P.nnode) ? 0 : q[u]);
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if (q[u] < 0) continue;
-      const double gx = (double)gxf[u], gy = (double)gyf[u];
-      if (q[u] < P.nnode) {  // type 1: q is the node; r = {vx, vy, m, rho}
-        const double h1 = gx * r[u].c / r[u].d;
-        const double h2 = gy * r[u].c / r[u].d;
-        g11 = g11 + (r[u].a - vp.x) * h1;
-        g12 = g12 + (r[u].a - vp.x) * h2;
-        g21 = g21 + (r[u].b - vp.y) * h1;
-        g22 = g22 + (r[u].b - vp.y) * h2;
+    auto entry_slow = [&](int q, int a1, int a2, const Rec4 &r) {
+      const double gx = (double)__int_as_float(a1), gy = (double)__int_as_float(a2);
+      if (q < P.nnode) {  // type 1: q is the node; r = {vx, vy, m, rho}
+        const double h1 = gx * r.c / r.d;
+        const double h2 = gy * r.c / r.d;
+        g11 = g11 + (r.a - vp.x) * h1;
+        g12 = g12 + (r.a - vp.x) * h2;
+        g21 = g21 + (r.b - vp.y) * h1;
+        g22 = g22 + (r.b - vp.y) * h2;
         if (FIRST && P.cspm) {
-          const double2 xq = ld2(st.x, q[u]);
+          const double2 xq = ld2(st.x, q);
           ae1 = ae1 + (xq.x - xp.x) * h1;
           ae2 = ae2 + (xq.y - xp.y) * h1;
           ae3 = ae3 + (xq.x - xp.x) * h2;
           ae4 = ae4 + (xq.y - xp.y) * h2;
         }
       } else {  // type 9: q is a dummy wall particle (no-slip mirror velocity), main:552-575
-        const int qd = q[u];
         const double beta_max = 1.5, vel_wall = 0.0;
-        const double wall = (double)st.wallpos[qd];
-        const double2 xq = ld2(st.x, qd);
+        const double wall = (double)st.wallpos[q];
+        const double2 xq = ld2(st.x, q);
         double da, db;
-        if (st.horiz[qd] == 1.f) {
+        if (st.horiz[q] == 1.f) {
           da = fabs(xp.y - wall);
           db = fabs(xq.y - wall);
         } else {
@@ -387,7 +494,7 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
         const double beta = (bq < beta_max) ? bq : beta_max;
         const double dvx = vp.x * (1 - beta) + beta * vel_wall;
         const double dvy = vp.y * (1 - beta) + beta * vel_wall;
-        const double mq = st.mass[qd], rq = st.rho[qd];
+        const double mq = st.mass[q], rq = st.rho[q];
         const double h1 = gx * mq / rq;
         const double h2 = gy * mq / rq;
         g11 = g11 + (vp.x - dvx) * h1;
@@ -395,8 +502,47 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
         g21 = g21 + (vp.y - dvy) * h1;
         g22 = g22 + (vp.y - dvy) * h2;
       }
-    }
+    };
+  {
+    __shared__ __align__(16) int smem[4 * ELL_SMEM(3)];
+    const int *arrs[3] = {L.idx0, reinterpret_cast<const int *>(L.gx0), reinterpret_cast<const int *>(L.gy0)};
+    ell_stream<3, Rec4>(
+        arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(3),
+        [&](int q) { return ldrec(st.NB, (q < 0 || q >= P.nnode) ? 0 : q); },
+        [&](const int(&q)[ELL_GROUP], const int(&a1)[ELL_GROUP], const int(&a2)[ELL_GROUP], const Rec4(&r)[ELL_GROUP],
+            int nvalid) {
+          bool special = false;  // wall partner in this group (type 9), or the once-per-step CSPM matrix pass
+#pragma unroll
+          for (int u = 0; u < ELL_GROUP; ++u) special |= (u < nvalid) && (q[u] >= P.nnode);
+          if ((FIRST && P.cspm) || __any_sync(0xffffffffu, special)) {
+#pragma unroll
+            for (int u = 0; u < ELL_GROUP; ++u)
+              if (u < nvalid) entry_slow(q[u], a1[u], a2[u], r[u]);
+            return;
+          }
+          // branch-free path: the four entries' division chains are independent and interleave
+          double h1[ELL_GROUP], h2[ELL_GROUP];
+#pragma unroll
+          for (int u = 0; u < ELL_GROUP; ++u) {
+            const double gx = (double)__int_as_float(a1[u]), gy = (double)__int_as_float(a2[u]);
+            const double rr = __drcp_rn(r[u].d);
+            h1[u] = div_rn(gx * r[u].c, r[u].d, rr);  // dwdx*mass(i)/rho(i), main:514
+            h2[u] = div_rn(gy * r[u].c, r[u].d, rr);
+          }
+#pragma unroll
+          for (int u = 0; u < ELL_GROUP; ++u) {
+            const bool ok = u < nvalid;
+            const double dvx = r[u].a - vp.x, dvy = r[u].b - vp.y;
+            const double n11 = g11 + dvx * h1[u], n12 = g12 + dvx * h2[u], n21 = g21 + dvy * h1[u],
+                         n22 = g22 + dvy * h2[u];
+            g11 = ok ? n11 : g11;
+            g12 = ok ? n12 : g12;
+            g21 = ok ? n21 : g21;
+            g22 = ok ? n22 : g22;
+          }
+        });
   }
+  if (!live) return;
   if (P.cspm) {
     double *AEp = st.AE + 5 * (size_t)id;
     if (FIRST) {
@@ -504,16 +650,18 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
 }
 
 template <bool FIRST>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, SPSPH_MINB)
 k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n0,
                const int *__restrict__ n1, StatePtrs st, double f1next, double f2, int last) {
-  const int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k >= M.nn) return;
-  const int t = k;
+  const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((k0 & ~31) >= M.nn) return;  // whole warp past the end
+  const bool live = k0 < M.nn;
+  const int k = live ? k0 : 0;
+  const int t = k0;
   const int id = order_n[k];
-  const int cnt = n0[t];
-  const int lane = t & 31, sl = t / SLICE;
-  const size_t o0 = (size_t)L.off0[sl] + lane;
+  const int cnt = live ? n0[t] : 0;
+  const int wrows = warp_max_i(cnt);
+  const int sl = t / SLICE;
   const Rec4 self = ldrec(st.NB, id);  // {vx, vy, m, rho}
   const double2 vp = make_double2(self.a, self.b);
   const double rp = self.d;
@@ -523,45 +671,29 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
   const double2 xp = ld2(st.x, id);
   double ae1 = 0.0, ae2 = 0.0, ae3 = 0.0, ae4 = 0.0, ae5 = 1.0;
   double a11 = 0.0, a12 = 0.0, a21 = 0.0, a22 = 0.0, a31 = 0.0, a32 = 0.0;  // grad2_tmp(s,k)
-  for (int e0 = 0; e0 < cnt; e0 += UNR) {
-    int q[UNR];
-    float gxf[UNR], gyf[UNR];
-    Rec4 r[UNR];
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      const size_t a = o0 + (size_t)(e0 + u) * SLICE;
-      q[u] = ldcs_i(L.idx0 + a);
-      gxf[u] = ldcs_f(L.gx0 + a);
-      gyf[u] = ldcs_f(L.gy0 + a);
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if (e0 + u >= cnt) q[u] = -1;
-      r[u] = ldrec(st.SB, (q[u] < 0 || q[u] >= P.ntotal) ? 0 : q[u] - P.nnode);
-    }
-#pragma unroll
-    for (int u = 0; u < UNR; ++u) {
-      if (q[u] < 0) continue;
-      const double gx = (double)gxf[u], gy = (double)gyf[u];
+  __shared__ __align__(16) int smem[4 * ELL_SMEM(3)];
+  int *smw = smem + (threadIdx.x >> 5) * ELL_SMEM(3);
+    auto entry_slow = [&](int q, int a1, int a2, const Rec4 &r) {
+      const double gx = (double)__int_as_float(a1), gy = (double)__int_as_float(a2);
       double q1, q2, q3, mq;
-      if (q[u] < P.ntotal) {  // type 1: q is the stress particle; r = {s1/rho^2, s2/rho^2, s3/rho^2, m}
-        q1 = r[u].a;
-        q2 = r[u].b;
-        q3 = r[u].c;
-        mq = r[u].d;
+      if (q < P.ntotal) {  // type 1: q is the stress particle; r = {s1/rho^2, s2/rho^2, s3/rho^2, m}
+        q1 = r.a;
+        q2 = r.b;
+        q3 = r.c;
+        mq = r.d;
         if (FIRST && P.cspm) {
-          const double rq = st.rho[q[u]];
+          const double rq = st.rho[q];
           const double h1b = -gx * mq / rq;
           const double h2b = -gy * mq / rq;
-          const double2 xq = ld2(st.x, q[u]);
+          const double2 xq = ld2(st.x, q);
           ae1 = ae1 + (xq.x - xp.x) * h1b;
           ae2 = ae2 + (xq.y - xp.y) * h1b;
           ae3 = ae3 + (xq.x - xp.x) * h2b;
           ae4 = ae4 + (xq.y - xp.y) * h2b;
         }
       } else {  // type 6: dummy takes the node's stress (main:580)
-        const double rq = st.rho[q[u]];
-        mq = st.mass[q[u]];
+        const double rq = st.rho[q];
+        mq = st.mass[q];
         q1 = sp_.s1 / (rq * rq);
         q2 = sp_.s2 / (rq * rq);
         q3 = sp_.s3 / (rq * rq);
@@ -573,7 +705,39 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
       a22 = a22 - mq * (gy * c2);
       a31 = a31 - mq * (gx * c3);
       a32 = a32 - mq * (gy * c3);
-    }
+    };
+  {
+    const int *arrs[3] = {L.idx0, reinterpret_cast<const int *>(L.gx0), reinterpret_cast<const int *>(L.gy0)};
+    ell_stream<3, Rec4>(
+        arrs, (size_t)L.off0[sl], wrows, cnt, smw,
+        [&](int q) { return ldrec(st.SB, (q < 0 || q >= P.ntotal) ? 0 : q - P.nnode); },
+        [&](const int(&q)[ELL_GROUP], const int(&a1)[ELL_GROUP], const int(&a2)[ELL_GROUP], const Rec4(&r)[ELL_GROUP],
+            int nvalid) {
+          bool special = false;  // wall partner in this group (type 6), or the once-per-step CSPM matrix pass
+#pragma unroll
+          for (int u = 0; u < ELL_GROUP; ++u) special |= (u < nvalid) && (q[u] >= P.ntotal);
+          if ((FIRST && P.cspm) || __any_sync(0xffffffffu, special)) {
+#pragma unroll
+            for (int u = 0; u < ELL_GROUP; ++u)
+              if (u < nvalid) entry_slow(q[u], a1[u], a2[u], r[u]);
+            return;
+          }
+#pragma unroll
+          for (int u = 0; u < ELL_GROUP; ++u) {
+            const bool ok = u < nvalid;
+            const double gx = (double)__int_as_float(a1[u]), gy = (double)__int_as_float(a2[u]);
+            const double c1 = so1 + r[u].a, c2 = so2 + r[u].b, c3 = so3 + r[u].c, mq = r[u].d;
+            const double n11 = a11 - mq * (gx * c1), n12 = a12 - mq * (gy * c1);
+            const double n21 = a21 - mq * (gx * c2), n22 = a22 - mq * (gy * c2);
+            const double n31 = a31 - mq * (gx * c3), n32 = a32 - mq * (gy * c3);
+            a11 = ok ? n11 : a11;
+            a12 = ok ? n12 : a12;
+            a21 = ok ? n21 : a21;
+            a22 = ok ? n22 : a22;
+            a31 = ok ? n31 : a31;
+            a32 = ok ? n32 : a32;
+          }
+        });
   }
   if (P.cspm) {
     double *AEp = st.AE + 5 * (size_t)id;
@@ -614,53 +778,55 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
   // artificial_viscosity, main:826-904 (fp32 locals and accumulators, list order)
   double av1 = 0.0, av2 = 0.0;
   if (P.alpha > 0 || P.beta > 0) {
-    const int cntc = n1[t];
-    const size_t oc = (size_t)L.offC[sl] + lane;
+    const int cntc = live ? n1[t] : 0;
+    const int wrowsC = warp_max_i(cntc);
     const double hp = st.hsml[id];
     float acc1 = 0.f, acc2 = 0.f;
-    for (int e0 = 0; e0 < cntc; e0 += UNR) {
-      int q[UNR];
-      float gxf[UNR], gyf[UNR];
-      Rec4 r[UNR];
-      double2 xq[UNR];
-      double hq[UNR];
+    struct RecV {
+      Rec4 n;
+      double2 x;
+      double h;
+    };
+    const int *arrs[3] = {L.idxC, reinterpret_cast<const int *>(L.gxC), reinterpret_cast<const int *>(L.gyC)};
+    __syncwarp();
+    ell_stream<3, RecV>(
+        arrs, (size_t)L.offC[sl], wrowsC, cntc, smw,
+        [&](int q) {
+          const int qq = q < 0 ? 0 : q;
+          RecV r;
+          r.n = ldrec(st.NB, qq);
+          r.x = ld2(st.x, qq);
+          r.h = st.hsml[qq];
+          return r;
+        },
+        [&](const int(&)[ELL_GROUP], const int(&a1v)[ELL_GROUP], const int(&a2v)[ELL_GROUP], const RecV(&rv)[ELL_GROUP],
+            int nvalid) {
 #pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        const size_t a = oc + (size_t)(e0 + u) * SLICE;
-        q[u] = ldcs_i(L.idxC + a);
-        gxf[u] = ldcs_f(L.gxC + a);
-        gyf[u] = ldcs_f(L.gyC + a);
-      }
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        if (e0 + u >= cntc) q[u] = -1;
-        const int qq = q[u] < 0 ? 0 : q[u];
-        r[u] = ldrec(st.NB, qq);
-        xq[u] = ld2(st.x, qq);
-        hq[u] = st.hsml[qq];
-      }
-#pragma unroll
-      for (int u = 0; u < UNR; ++u) {
-        if (q[u] < 0) continue;
-        const float xij = (float)(xp.x - xq[u].x);
-        const float yij = (float)(xp.y - xq[u].y);
-        const float h = (float)(0.5 * (hp + hq[u]));
-        const float rho2 = (float)(0.5 * (rp + r[u].d));
-        const float cs = 600.f;
-        float div_u = (float)((double)xij * (vp.x - r[u].a));
-        div_u = (float)((double)div_u + (double)yij * (vp.y - r[u].b));
-        const float sq = sqrtf(xij * xij + yij * yij);
-        const float theta = (h * div_u) / (sq * sq + 0.01f * (h * h));
-        float visc = 0.f;
-        if (div_u < 0)
-          visc = (float)((-P.alpha * (double)cs * (double)theta + P.beta * (double)(theta * theta)) / (double)rho2);
-        acc1 = (float)((double)acc1 + (double)(visc * gxf[u]) * r[u].c);
-        acc2 = (float)((double)acc2 + (double)(visc * gyf[u]) * r[u].c);
-      }
-    }
+          for (int u = 0; u < ELL_GROUP; ++u) {
+            if (u >= nvalid) continue;
+            const int a1 = a1v[u], a2 = a2v[u];
+            const RecV &r = rv[u];
+            const float gxf = __int_as_float(a1), gyf = __int_as_float(a2);
+            const float xij = (float)(xp.x - r.x.x);
+            const float yij = (float)(xp.y - r.x.y);
+            const float h = (float)(0.5 * (hp + r.h));
+            const float rho2 = (float)(0.5 * (rp + r.n.d));
+            const float cs = 600.f;
+            float div_u = (float)((double)xij * (vp.x - r.n.a));
+            div_u = (float)((double)div_u + (double)yij * (vp.y - r.n.b));
+            const float sq = sqrtf(xij * xij + yij * yij);
+            const float theta = (h * div_u) / (sq * sq + 0.01f * (h * h));
+            float visc = 0.f;
+            if (div_u < 0)
+              visc = (float)((-P.alpha * (double)cs * (double)theta + P.beta * (double)(theta * theta)) / (double)rho2);
+            acc1 = (float)((double)acc1 + (double)(visc * gxf) * r.n.c);
+            acc2 = (float)((double)acc2 + (double)(visc * gyf) * r.n.c);
+          }
+        });
     av1 = (double)(-acc1);
     av2 = (double)(-acc2);
   }
+  if (!live) return;
   const double r1 = -dv1 + sg1 + av1 + 0.0 + 0.0;  // + f_bound + art_force (both zero here, main:763-764)
   const double r2 = -dv2 + sg2 + av2 + 0.0 + 0.0;
   double2 rk = ld2(st.RKv, id);

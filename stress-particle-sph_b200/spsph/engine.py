@@ -12,7 +12,7 @@ import numpy as np
 from . import _abi
 
 _PKG = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-_CUDA_SO = os.path.join(_PKG, "libspsph_cuda.so")
+_CUDA_SO = os.environ.get("SPSPH_CUDA_SO") or os.path.join(_PKG, "libspsph_cuda.so")  # override: kernel tuning experiments
 _lib = None
 
 
