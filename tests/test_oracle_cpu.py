@@ -198,3 +198,39 @@ def test_fast_division_identity(tmp_path):
     r = subprocess.run([exe, "20000000"], capture_output=True, text=True)
     assert r.returncode == 0, r.stdout
     assert "two-step=0" in r.stdout
+
+
+def test_fortran_shim_matches_header():
+    """fortran/spsph_shim.f90 cannot be compiled here (no Fortran compiler); check statically that it declares
+    every spsph_params / spsph_state member of include/spsph.h in the same order and binds every entry point."""
+    hdr = open(os.path.join(ROOT, "include", "spsph.h")).read()
+    f90 = open(os.path.join(ROOT, "stress-particle-sph_b200", "fortran", "spsph_shim.f90")).read().lower()
+
+    def c_members(struct):
+        body = re.search(r"typedef struct %s \{(.*?)\} %s;" % (struct, struct), hdr, re.S).group(1)
+        body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+        names = []
+        for decl in body.split(";"):
+            decl = decl.strip()
+            if not decl:
+                continue
+            decl = re.sub(r"^(const\s+)?(int32_t|float|double)\s*", "", decl)
+            for part in decl.split(","):
+                names.append(re.sub(r"\[.*?\]|[\*\s]", "", part))
+        return [n.lower() for n in names if n]
+
+    def f_members(typename):
+        body = re.search(r"type, bind\(c\) :: %s(.*?)end type" % typename, f90, re.S).group(1)
+        names = []
+        for line in body.splitlines():
+            line = line.split("!")[0]
+            if "::" not in line:
+                continue
+            for part in re.split(r",(?![^()]*\))", line.split("::")[1]):
+                names.append(re.sub(r"\(.*\)", "", part).strip())
+        return [n for n in names if n]
+
+    assert c_members("spsph_params") == f_members("spsph_params")
+    assert c_members("spsph_state") == f_members("spsph_state")
+    for name in set(re.findall(r"\b(spsph_[a-z_]+)\s*\(", hdr)):
+        assert 'name="%s"' % name in f90, name
