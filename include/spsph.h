@@ -120,6 +120,16 @@ int spsph_last_run_ms(spsph_handle *h, float *ms, int64_t *kernel_launches);
  * the call returns non-zero. Times are CUDA-event intervals on the engine's stream. */
 int spsph_profile(spsph_handle *h, int enable);
 int spsph_profile_get(spsph_handle *h, int kid, const char **name, double *total_ms, int64_t *launches);
+/* ---- multi-GPU x-slab decomposition: one process per GPU, every rank creates a handle on its own device and
+ * uploads the COMPLETE problem, then calls spsph_dist_init with the same slab planes. planes[r] <= x < planes[r+1]
+ * is rank r's slab (planes[0] = -inf, planes[nranks] = +inf). After that spsph_step exchanges ghost particles
+ * and migrants with the neighbouring slabs over NCCL once per step; spsph_download returns this rank's local
+ * view and spsph_dist_flags tells which entries are authoritative (1 owned, 2 ghost, 0 remote/stale).
+ * id128: NCCL unique id from spsph_dist_unique_id on rank 0, distributed by the launcher (file, MPI, torch). */
+int spsph_dist_unique_id(char *id128);
+int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *id128, const double *planes,
+                    int32_t halo_cells, int32_t halo_capacity);
+int spsph_dist_flags(spsph_handle *h, int32_t *flags);
 int spsph_sync(spsph_handle *h);
 int spsph_destroy(spsph_handle *h);
 const char *spsph_last_error(spsph_handle *h);

@@ -52,7 +52,8 @@ struct StepStatus {  // copied to pinned host memory after the count pass
   long long n_pairs;
   long long tot0, totC, totD;  // list storage needed (entries incl. slice padding)
   int ncell, overflow, err;
-  int pad;
+  int nloc[3];  // particles per species that need processing: in the grid + out-of-domain (remote ones excluded)
+  int pad[2];
 };
 
 __device__ __forceinline__ double2 ld2(const double *p, int i) { return reinterpret_cast<const double2 *>(p)[i]; }

@@ -1,0 +1,210 @@
+// Multi-GPU x-slab decomposition: ownership, halo selection, pack / unpack of the per-step exchange.
+//
+// Design (re-thought for NVLink): every rank holds full-size particle arrays indexed by the
+// reference's global particle number but only its slab (owned particles) plus a WIDE halo of ghost particles is
+// "local"; everything else is flagged remote and never enters the cell grid. Once per step, before the
+// neighbour search, each rank sends the full state of its owned particles lying within the halo distance of a
+// neighbouring slab (one fixed-capacity NCCL send/recv pair per side, no count round trip); after that the
+// whole time step -- neighbour search, 4 RK stages, position update -- runs with NO further communication
+// except one 6-double all-reduce for the global grid bounds and one 8-byte all-reduce of the pair count.
+// Every sweep reads partners at most one cell (2h) away, so the ghost region computed redundantly degrades by
+// one cell per dependent sweep; with a halo of (number of dependent sweeps + 2) cells the owned particles'
+// results are bit-identical to the single-GPU run. Particles migrate between slabs as part of the same
+// exchange (the receiver re-derives ownership from the position it receives).
+#pragma once
+#include "step_kernels.cuh"
+
+namespace spsph {
+
+enum : int { LF_REMOTE = 0, LF_OWNED = 1, LF_GHOST = 2 };
+// doubles per exchanged particle: id, x(2), vel(2), stress(4), eps_p, f_drucker, x_10(2), disp_10, displ(2), out flag, spare
+constexpr int HALO_REC = 18;
+
+struct DistGeom {
+  int rank, nranks;
+  double lo, hi;  // this rank's slab is lo <= x_key < hi (lo = -inf on rank 0, hi = +inf on the last rank)
+  double H;       // halo distance
+  int sp_follows_node;  // outside approach: a stress particle is owned by the rank that owns its node
+  int cap;        // record capacity of one halo message
+};
+
+// position that decides ownership: a stress particle of the outside approach follows its velocity particle,
+// because shift_stress_points (main:244-368) re-seats it from that particle's thread
+__device__ __forceinline__ double key_x(const DevParams &P, const DistGeom &D, const double *__restrict__ x, int i) {
+  if (D.sp_follows_node && i >= P.nnode && i < P.ntotal) return x[2 * (size_t)((i - P.nnode) / P.npoints)];
+  return x[2 * (size_t)i];
+}
+
+// initial flags after upload (all ranks hold identical, complete data)
+__global__ void k_dist_init_flags(DevParams P, DistGeom D, const double *__restrict__ x, int *__restrict__ lflag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.ntotal2) return;
+  const double xk = key_x(P, D, x, i), xi = x[2 * (size_t)i];
+  int f = LF_REMOTE;
+  if (xk >= D.lo && xk < D.hi)
+    f = LF_OWNED;
+  else if (xi >= D.lo - D.H && xi < D.hi + D.H)
+    f = LF_GHOST;
+  lflag[i] = f;
+}
+
+// halo selection + migration (see file header). cnt[0]/cnt[1]: number of records for the left/right neighbour.
+__global__ void k_halo_select(DevParams P, DistGeom D, const double *__restrict__ x, int *__restrict__ lflag,
+                              int *__restrict__ cnt, int *__restrict__ idsL, int *__restrict__ idsR,
+                              int *__restrict__ err) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.ntotal2) return;
+  const int f = lflag[i];
+  if (f == LF_GHOST) {
+    lflag[i] = LF_REMOTE;  // refreshed by its owner below if it is still inside our halo
+    return;
+  }
+  if (f != LF_OWNED) return;
+  const double xk = key_x(P, D, x, i), xi = x[2 * (size_t)i];
+  bool toL = false, toR = false;
+  if (xk < D.lo) {  // migrates to the left neighbour; we keep it as a ghost (its state is current)
+    toL = true;
+    lflag[i] = LF_GHOST;
+  } else if (xk >= D.hi) {
+    toR = true;
+    lflag[i] = LF_GHOST;
+  } else {
+    if (D.rank > 0 && xi < D.lo + D.H) toL = true;
+    if (D.rank < D.nranks - 1 && xi >= D.hi - D.H) toR = true;
+  }
+  if (toL) {
+    const int k = atomicAdd(&cnt[0], 1);
+    if (k < D.cap)
+      idsL[k] = i;
+    else
+      *err = 1;
+  }
+  if (toR) {
+    const int k = atomicAdd(&cnt[1], 1);
+    if (k < D.cap)
+      idsR[k] = i;
+    else
+      *err = 1;
+  }
+}
+
+struct HaloArrays {
+  double *x, *epsp, *fdp, *x_10, *disp_10, *displ;
+  int *if_out;
+};
+
+// message layout: record 0 = header {count}, records 1..count = particles
+__global__ void k_halo_pack(DevParams P, StatePtrs st, HaloArrays A, const int *__restrict__ cnt_ptr, int cap,
+                            const int *__restrict__ ids, double *__restrict__ msg) {
+  const int n = min(*cnt_ptr, cap);
+  if (blockIdx.x == 0 && threadIdx.x == 0) msg[0] = (double)n;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int i = ids[k];
+    double *o = msg + (size_t)HALO_REC * (k + 1);
+    o[0] = (double)i;
+    o[1] = A.x[2 * (size_t)i];
+    o[2] = A.x[2 * (size_t)i + 1];
+    o[16] = (double)A.if_out[i];
+    o[17] = 0.0;
+    if (i < P.nnode) {
+      const Rec4 r = ldrec(st.NB, i);
+      const Stress4 s = ld4(st.NSb, i);
+      o[3] = r.a;
+      o[4] = r.b;
+      o[5] = s.s1;
+      o[6] = s.s2;
+      o[7] = s.s3;
+      o[8] = s.s4;
+      o[9] = st.epsp[i];
+      o[10] = st.fdp[i];
+      o[11] = A.x_10[2 * (size_t)i];
+      o[12] = A.x_10[2 * (size_t)i + 1];
+      o[13] = A.disp_10[i];
+      o[14] = A.displ[2 * (size_t)i];
+      o[15] = A.displ[2 * (size_t)i + 1];
+    } else if (i < P.ntotal) {
+      const int ks = i - P.nnode;
+      const double2 v = ld2(st.SVb, ks);
+      const Stress4 s = ld4(st.SFb, ks);
+      o[3] = v.x;
+      o[4] = v.y;
+      o[5] = s.s1;
+      o[6] = s.s2;
+      o[7] = s.s3;
+      o[8] = s.s4;
+      o[9] = st.epsp[i];
+      o[10] = st.fdp[i];
+      o[11] = o[12] = o[13] = o[14] = o[15] = 0.0;
+    } else {
+      for (int q = 3; q < 16; ++q) o[q] = 0.0;
+    }
+  }
+}
+
+__global__ void k_halo_unpack(DevParams P, DistGeom D, StatePtrs st, HaloArrays A, const double *__restrict__ msg,
+                              int *__restrict__ lflag) {
+  const int n = (int)msg[0];
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const double *o = msg + (size_t)HALO_REC * (k + 1);
+    const int i = (int)o[0];
+    A.x[2 * (size_t)i] = o[1];
+    A.x[2 * (size_t)i + 1] = o[2];
+    A.if_out[i] = (int)o[16];
+    if (i < P.nnode) {
+      strec(st.NB, i, o[3], o[4], st.mass[i], st.rho[i]);
+      st4(st.NSb, i, Stress4{o[5], o[6], o[7], o[8]});
+      st.epsp[i] = o[9];
+      st.fdp[i] = o[10];
+      A.x_10[2 * (size_t)i] = o[11];
+      A.x_10[2 * (size_t)i + 1] = o[12];
+      A.disp_10[i] = o[13];
+      A.displ[2 * (size_t)i] = o[14];
+      A.displ[2 * (size_t)i + 1] = o[15];
+    } else if (i < P.ntotal) {
+      const int ks = i - P.nnode;
+      st2(st.SVb, ks, make_double2(o[3], o[4]));
+      const Stress4 s{o[5], o[6], o[7], o[8]};
+      st4(st.SFb, ks, s);
+      const double r = st.rho[i];
+      const double r2 = r * r;
+      strec(st.SB, ks, s.s1 / r2, s.s2 / r2, s.s3 / r2, st.mass[i]);
+      st.epsp[i] = o[9];
+      st.fdp[i] = o[10];
+    }
+    lflag[i] = LF_GHOST;  // ownership is settled by k_halo_own once every position has arrived
+  }
+}
+
+// receiver side of migration: a received particle whose key position lies in our slab becomes owned
+__global__ void k_halo_own(DevParams P, DistGeom D, const double *__restrict__ x, const double *__restrict__ msg,
+                           int *__restrict__ lflag) {
+  const int n = (int)msg[0];
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int i = (int)msg[(size_t)HALO_REC * (k + 1)];
+    const double xk = key_x(P, D, x, i);
+    if (xk >= D.lo && xk < D.hi) lflag[i] = LF_OWNED;
+  }
+}
+
+// local bounding box -> 6 values encoded for a single MAX all-reduce: {-xmin, -ymin, xmax, ymax, hmax, -hmin}
+__global__ void k_bbox_final(int nblocks, const double *__restrict__ partial, double *__restrict__ bb6) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double mn[2] = {1.e+10, 1.e+10}, mx[2] = {-1.e+10, -1.e+10}, hmx = 0.0, hmn = 1.e+300;
+  for (int b = 0; b < nblocks; ++b) {
+    const double *o = partial + 6 * b;
+    mn[0] = fmin(mn[0], o[0]);
+    mn[1] = fmin(mn[1], o[1]);
+    mx[0] = fmax(mx[0], o[2]);
+    mx[1] = fmax(mx[1], o[3]);
+    hmx = fmax(hmx, o[4]);
+    hmn = fmin(hmn, o[5]);
+  }
+  bb6[0] = -mn[0];
+  bb6[1] = -mn[1];
+  bb6[2] = mx[0];
+  bb6[3] = mx[1];
+  bb6[4] = hmx;
+  bb6[5] = -hmn;
+}
+
+}  // namespace spsph

@@ -15,6 +15,7 @@
 namespace spsph {
 
 constexpr int SLICE = 32;
+constexpr int PARK_REMOTE = -(1 << 30);  // which_cell <= PARK_REMOTE: remote particle (multi-GPU)
 
 struct SortArrays {  // per species s in {node, stress, dummy}; species-sorted index k
   const int *start[3];      // [ncell+1] first sorted index of each cell
@@ -61,10 +62,15 @@ __device__ __forceinline__ double warp_max(double v) {
   return v;
 }
 
+// lflag (multi-GPU only, else nullptr): 0 remote, 1 owned, 2 ghost; only owned particles enter the local
+// bounds (the global bounds are the all-reduce of the local ones), remote particles are skipped entirely.
 __global__ void k_domain_bbox(DevParams P, const double *__restrict__ x, const double *__restrict__ hsml,
-                              int *__restrict__ if_out, double *__restrict__ partial /* [gridDim.x][6] */) {
+                              int *__restrict__ if_out, const int *__restrict__ lflag,
+                              double *__restrict__ partial /* [gridDim.x][6] */) {
   double xmn = 1.e+10, ymn = 1.e+10, xmx = -1.e+10, ymx = -1.e+10, hmx = 0.0, hmn = 1.e+300;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.ntotal2; i += gridDim.x * blockDim.x) {
+    const int lf = lflag ? lflag[i] : 1;
+    if (lf == 0) continue;
     const double2 p = ld2(x, i);
     int out = if_out[i];
     const double dxx = (p.x - P.xmin_dom[0]) * (p.x - P.xmax_dom[0]);
@@ -73,7 +79,7 @@ __global__ void k_domain_bbox(DevParams P, const double *__restrict__ x, const d
       if (!out) if_out[i] = 1;
       out = 1;
     }
-    if (!out) {
+    if (!out && lf == 1) {
       xmn = fmin(xmn, p.x);
       xmx = fmax(xmx, p.x);
       ymn = fmin(ymn, p.y);
@@ -125,20 +131,12 @@ __global__ void k_domain_bbox(DevParams P, const double *__restrict__ x, const d
   }
 }
 
-// grid_find_NEW Task 1 (main:1245-1258) on one thread; also clears the per-step counters.
-__global__ void k_grid_params(int nblocks, const double *__restrict__ partial, GridInfo *__restrict__ G,
-                              int cell_capacity) {
+// grid_find_NEW Task 1 (main:1245-1258) on one thread. bb6 = {-xmin, -ymin, xmax, ymax, hmax, -hmin} of the
+// in-domain particles (already all-reduced over the ranks in a multi-GPU run).
+__global__ void k_grid_params(const double *__restrict__ bb6, GridInfo *__restrict__ G, int cell_capacity) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double mn[2] = {1.e+10, 1.e+10}, mx[2] = {-1.e+10, -1.e+10}, hmx = 0.0, hmn = 1.e+300;
-  for (int b = 0; b < nblocks; ++b) {
-    const double *o = partial + 6 * b;
-    mn[0] = fmin(mn[0], o[0]);
-    mn[1] = fmin(mn[1], o[1]);
-    mx[0] = fmax(mx[0], o[2]);
-    mx[1] = fmax(mx[1], o[3]);
-    hmx = fmax(hmx, o[4]);
-    hmn = fmin(hmn, o[5]);
-  }
+  const double mn[2] = {-bb6[0], -bb6[1]}, mx[2] = {bb6[2], bb6[3]};
+  const double hmx = bb6[4], hmn = -bb6[5];
   for (int d = 0; d < 2; ++d) {
     double xmin = mn[d], xmax = mx[d];
     double deltx = hmx * 2;
@@ -181,11 +179,15 @@ __device__ __forceinline__ int species_of(const DevParams &P, int i) {
 
 // grid_find_NEW Task 2 (main:1277-1286): cell id of every in-domain particle + per-cell species counts
 __global__ void k_cell_id(DevParams P, const GridInfo *__restrict__ G, const double *__restrict__ x,
-                          const int *__restrict__ if_out, int *__restrict__ which_cell, int *__restrict__ cnt,
-                          int cell_stride, int *__restrict__ nout /* [3] */) {
+                          const int *__restrict__ if_out, const int *__restrict__ lflag, int *__restrict__ which_cell,
+                          int *__restrict__ cnt, int cell_stride, int *__restrict__ nout /* [6] */) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.ntotal2) return;
   const int sp = species_of(P, i);
+  if (lflag && lflag[i] == 0) {  // remote (other rank's) particle: parked last, never processed
+    which_cell[i] = PARK_REMOTE - atomicAdd(&nout[3 + sp], 1);
+    return;
+  }
   if (if_out[i] || G->overflow) {  // on a cell-table overflow nothing is binned; the host reports the error
     which_cell[i] = -1 - atomicAdd(&nout[sp], 1);  // parked after the sorted particles, order irrelevant
     return;
@@ -311,7 +313,7 @@ __global__ void k_rank(DevParams P, const GridInfo *__restrict__ G, const double
                        const int *__restrict__ start, int cell_stride, const int *__restrict__ tmp,
                        int *__restrict__ order, double2 *__restrict__ spos, double *__restrict__ sh,
                        int *__restrict__ scell, int *__restrict__ pos_of /* [ntotal2] species-sorted index */,
-                       float2 *__restrict__ supos) {
+                       float2 *__restrict__ supos, const int *__restrict__ nout) {
   // one thread per particle in original order
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.ntotal2) return;
@@ -319,7 +321,10 @@ __global__ void k_rank(DevParams P, const GridInfo *__restrict__ G, const double
   const int c = which_cell[i];
   const size_t row = (size_t)sp * P.ntotal2;
   int k;
-  if (c < 0) {
+  if (c <= PARK_REMOTE) {
+    const int nact = start[sp * cell_stride + G->ncell];
+    k = nact + nout[sp] + (PARK_REMOTE - c);
+  } else if (c < 0) {
     const int nact = start[sp * cell_stride + G->ncell];
     k = nact + (-1 - c);
   } else {
@@ -487,7 +492,7 @@ __device__ __forceinline__ RowRange row_range(int ndx, int cx, int jy) {
 __global__ void __launch_bounds__(128)
 k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, int *__restrict__ n0, int *__restrict__ n1,
         int *__restrict__ nfwd_u /* unified order */, int *__restrict__ nall, int *__restrict__ w0 /* slice widths */,
-        int *__restrict__ wC, int *__restrict__ wD) {
+        int *__restrict__ wC, int *__restrict__ wD, const int *__restrict__ lflag) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   int sp = 0, k = 0;
   const bool live = (t < M.total()) && slot_decode(M, t, sp, k);
@@ -543,7 +548,12 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
           }
         }
       }
-      nfwd_u[unified_slot(S, c, sp, k)] = cf;
+      // creation index / statistics count every pair once: at the owner of its earlier member
+      const bool owned = !lflag || lflag[(sp == 0 ? S.order[0] : (sp == 1 ? S.order[1] : S.order[2]))[k]] == 1;
+      nfwd_u[unified_slot(S, c, sp, k)] = owned ? cf : 0;
+      if (!owned) ca = -1;
+    } else if (lflag && lflag[(sp == 0 ? S.order[0] : (sp == 1 ? S.order[1] : S.order[2]))[k]] != 1) {
+      ca = -1;
     }
     nall[t] = ca;
   }
@@ -566,7 +576,8 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
 }
 
 // after the scans: totals -> status block
-__global__ void k_status(const GridInfo *__restrict__ G, const long long *__restrict__ totals, StepStatus *st) {
+__global__ void k_status(const GridInfo *__restrict__ G, const long long *__restrict__ totals,
+                         const int *__restrict__ start, int cell_stride, const int *__restrict__ nout, StepStatus *st) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   st->tot0 = totals[0];
   st->totC = totals[1];
@@ -575,6 +586,7 @@ __global__ void k_status(const GridInfo *__restrict__ G, const long long *__rest
   st->ncell = G->ncell;
   st->overflow = G->overflow;
   st->err = 0;
+  for (int sp = 0; sp < 3; ++sp) st->nloc[sp] = start[sp * cell_stride + G->ncell] + nout[sp];
 }
 
 // Finds the split point of the growth rule: the pair with creation index M (1-based) -> (ua*, ub*).

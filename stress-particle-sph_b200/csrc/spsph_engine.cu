@@ -10,10 +10,22 @@
 #include <string>
 #include <vector>
 
+#include <dlfcn.h>
+#include <nccl.h>
+
 #include "spsph.h"
-#include "step_kernels.cuh"
+#include "dist_kernels.cuh"
 
 using namespace spsph;
+
+#define NCCL_TRY(call)                                                                            \
+  do {                                                                                            \
+    ncclResult_t r_ = (call);                                                                     \
+    if (r_ != ncclSuccess) {                                                                      \
+      h->err = std::string(#call) + ": " + (h->p_ncclGetErrorString ? h->p_ncclGetErrorString(r_) : "nccl error"); \
+      return 1;                                                                                   \
+    }                                                                                             \
+  } while (0)
 
 #define CUDA_TRY(call)                                                                            \
   do {                                                                                            \
@@ -79,6 +91,28 @@ struct spsph_handle {
   float last_ms = 0.f;
   long long last_launches = 0, launches = 0;
 
+  // multi-GPU x-slab decomposition (dist_kernels.cuh); NCCL is resolved with dlopen so that a single-GPU user
+  // needs no NCCL and a torch process re-uses the libnccl it has already loaded
+  bool dist = false;
+  DistGeom D{};
+  int *lflag = nullptr;       // [ntotal2] 0 remote, 1 owned, 2 ghost (nullptr-equivalent when !dist)
+  int *halo_cnt = nullptr;    // [2] + err flag [1]
+  int *halo_ids[2] = {nullptr, nullptr};
+  double *halo_send[2] = {nullptr, nullptr}, *halo_recv[2] = {nullptr, nullptr};
+  double *bb6 = nullptr;
+  void *nccl_lib = nullptr;
+  ncclComm_t comm = nullptr;
+  ncclResult_t (*p_ncclCommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*p_ncclCommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*p_ncclSend)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*p_ncclRecv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*p_ncclAllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
+                                  cudaStream_t) = nullptr;
+  ncclResult_t (*p_ncclGroupStart)() = nullptr;
+  ncclResult_t (*p_ncclGroupEnd)() = nullptr;
+  const char *(*p_ncclGetErrorString)(ncclResult_t) = nullptr;
+  int nloc[3] = {0, 0, 0};  // particles per species to process in the current step
+
   // optional per-kernel timing (CUDA events on the engine stream between launches)
   bool profiling = false;
   std::vector<cudaEvent_t> ev_pool;
@@ -90,11 +124,12 @@ struct spsph_handle {
 
 enum KernelId {
   KID_BBOX = 0, KID_GRID, KID_ZERO, KID_CELLID, KID_SCAN, KID_SCATTER, KID_RANK, KID_COUNT, KID_STATUS, KID_THRESH,
-  KID_FILL, KID_RKBEGIN, KID_SWEEPA, KID_SWEEPB, KID_MOVE, KID_SHIFT, KID_N
+  KID_FILL, KID_RKBEGIN, KID_SWEEPA, KID_SWEEPB, KID_MOVE, KID_SHIFT, KID_HALO, KID_N
 };
 static const char *kKernelNames[KID_N] = {"k_domain_bbox", "k_grid_params", "k_zero_cells", "k_cell_id", "k_scan_*",
                                           "k_scatter", "k_rank", "k_count", "k_status", "k_growth_threshold", "k_fill",
-                                          "k_rk_begin", "k_sweep_a", "k_sweep_b", "k_move", "k_shift"};
+                                          "k_rk_begin", "k_sweep_a", "k_sweep_b", "k_move", "k_shift",
+                                          "halo_exchange"};
 
 namespace {
 
@@ -289,6 +324,46 @@ void launch_scan(spsph_handle *h, const int *in, int *out, int rows, int stride,
   mark(h, KID_SCAN, 3);
 }
 
+// per-step halo exchange + migration (dist_kernels.cuh); everything is enqueued on the engine stream
+int halo_exchange(spsph_handle *h) {
+  const DevParams &P = h->P;
+  const DistGeom &D = h->D;
+  cudaStream_t s = h->stream;
+  const int n2 = P.ntotal2;
+  const StatePtrs st = state_ptrs(h, h->cur);
+  const HaloArrays A{h->x, h->epsp, h->fdp, h->x_10, h->disp_10, h->displ, h->if_out};
+  if (h->profiling) mark(h, -1, 0);
+  CUDA_TRY(cudaMemsetAsync(h->halo_cnt, 0, 2 * sizeof(int), s));
+  k_halo_select<<<(n2 + 255) / 256, 256, 0, s>>>(P, D, h->x, h->lflag, h->halo_cnt, h->halo_ids[0], h->halo_ids[1],
+                                                 h->halo_cnt + 2);
+  const size_t msg = (size_t)HALO_REC * (D.cap + 1);
+  for (int side = 0; side < 2; ++side)
+    k_halo_pack<<<148, 256, 0, s>>>(P, st, A, h->halo_cnt + side, D.cap, h->halo_ids[side], h->halo_send[side]);
+  const int left = D.rank - 1, right = D.rank + 1;
+  NCCL_TRY(h->p_ncclGroupStart());
+  if (left >= 0) {
+    NCCL_TRY(h->p_ncclSend(h->halo_send[0], msg, ncclDouble, left, h->comm, s));
+    NCCL_TRY(h->p_ncclRecv(h->halo_recv[0], msg, ncclDouble, left, h->comm, s));
+  }
+  if (right < D.nranks) {
+    NCCL_TRY(h->p_ncclSend(h->halo_send[1], msg, ncclDouble, right, h->comm, s));
+    NCCL_TRY(h->p_ncclRecv(h->halo_recv[1], msg, ncclDouble, right, h->comm, s));
+  }
+  NCCL_TRY(h->p_ncclGroupEnd());
+  for (int side = 0; side < 2; ++side) {
+    const int peer = side == 0 ? left : right;
+    if (peer < 0 || peer >= D.nranks) continue;
+    k_halo_unpack<<<148, 256, 0, s>>>(P, D, st, A, h->halo_recv[side], h->lflag);
+  }
+  for (int side = 0; side < 2; ++side) {
+    const int peer = side == 0 ? left : right;
+    if (peer < 0 || peer >= D.nranks) continue;
+    k_halo_own<<<148, 256, 0, s>>>(P, D, h->x, h->halo_recv[side], h->lflag);
+  }
+  mark(h, KID_HALO, 7);
+  return 0;
+}
+
 // neighbour search up to and including the list fill; leaves the pair totals in h->status_h
 int build_neighbours(spsph_handle *h) {
   const DevParams &P = h->P;
@@ -298,36 +373,51 @@ int build_neighbours(spsph_handle *h) {
   if (h->profiling) {  // anchor event so that the first kernel's interval is well defined
     mark(h, -1, 0);
   }
-  k_domain_bbox<<<h->bbox_blocks, TB, 0, s>>>(P, h->x, h->hsml, h->if_out, h->bbox_partial);
+  const int *lflag = h->dist ? h->lflag : nullptr;
+  k_domain_bbox<<<h->bbox_blocks, TB, 0, s>>>(P, h->x, h->hsml, h->if_out, lflag, h->bbox_partial);
   mark(h, KID_BBOX);
-  k_grid_params<<<1, 32, 0, s>>>(h->bbox_blocks, h->bbox_partial, h->G, h->cell_capacity);
-  mark(h, KID_GRID);
+  k_bbox_final<<<1, 32, 0, s>>>(h->bbox_blocks, h->bbox_partial, h->bb6);
+  if (h->dist)  // global grid bounds: the reference's cell grid (hence its pair order) is a global property
+    NCCL_TRY(h->p_ncclAllReduce(h->bb6, h->bb6, 6, ncclDouble, ncclMax, h->comm, s));
+  k_grid_params<<<1, 32, 0, s>>>(h->bb6, h->G, h->cell_capacity);
+  mark(h, KID_GRID, 2);
   k_zero_cells<<<296, TB, 0, s>>>(h->G, h->cell_cnt, h->cell_stride);
   k_zero_cells<<<296, TB, 0, s>>>(h->G, h->cell_fill, h->cell_stride);
-  CUDA_TRY(cudaMemsetAsync(h->nout, 0, 3 * sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(h->nout, 0, 6 * sizeof(int), s));
   CUDA_TRY(cudaMemsetAsync(h->nfwd_u, 0, (size_t)n2 * sizeof(int), s));
   mark(h, KID_ZERO, 2);
-  k_cell_id<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->G, h->x, h->if_out, h->which_cell, h->cell_cnt, h->cell_stride,
-                                               h->nout);
+  k_cell_id<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->G, h->x, h->if_out, lflag, h->which_cell, h->cell_cnt,
+                                               h->cell_stride, h->nout);
   mark(h, KID_CELLID);
   launch_scan(h, h->cell_cnt, h->cell_start, 3, h->cell_stride, &h->G->ncell, 1, h->scan_totals + 4);
   k_scatter<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->which_cell, h->cell_start, h->cell_fill, h->cell_stride, h->tmp_ids);
   mark(h, KID_SCATTER);
   k_rank<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->G, h->x, h->hsml, h->which_cell, h->cell_start, h->cell_stride,
-                                            h->tmp_ids, h->order, h->spos, h->sh, h->scell, h->pos_of, h->supos);
+                                            h->tmp_ids, h->order, h->spos, h->sh, h->scell, h->pos_of, h->supos, h->nout);
   mark(h, KID_RANK);
   const SortArrays S = sort_arrays(h);
   const int T = h->M.total();
   k_count<<<(T + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->nfwd_u, h->nall, h->wslice,
-                                           h->wslice + h->nslices, h->wslice + 2 * h->nslices);
+                                           h->wslice + h->nslices, h->wslice + 2 * h->nslices, lflag);
   mark(h, KID_COUNT);
   launch_scan(h, h->wslice, h->oslice, 3, h->nslices, nullptr, h->nslices, h->scan_totals);
   launch_scan(h, h->nfwd_u, h->base_u, 1, n2, nullptr, n2, h->scan_totals + 3);
-  k_status<<<1, 32, 0, s>>>(h->G, h->scan_totals, h->status_d);
+  if (h->dist)  // every pair is counted once, at the owner of its earlier member
+    NCCL_TRY(h->p_ncclAllReduce(h->scan_totals + 3, h->scan_totals + 3, 1, ncclInt64, ncclSum, h->comm, s));
+  k_status<<<1, 32, 0, s>>>(h->G, h->scan_totals, h->cell_start, h->cell_stride, h->nout, h->status_d);
   mark(h, KID_STATUS);
   CUDA_TRY(cudaMemcpyAsync(h->status_h, h->status_d, sizeof(StepStatus), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
   const StepStatus st = *h->status_h;
+  if (h->dist) {
+    int herr = 0;
+    CUDA_TRY(cudaMemcpyAsync(&herr, h->halo_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (herr) {
+      h->err = "multi-GPU: halo message capacity exceeded (too many particles near a slab boundary)";
+      return 1;
+    }
+  }
   if (st.overflow) {
     h->err = "cell grid larger than the capacity derived from Xmin_Domain/Xmax_Domain";
     return 1;
@@ -336,6 +426,7 @@ int build_neighbours(spsph_handle *h) {
     h->err = "neighbour list exceeds 2^31 entries on one device";
     return 1;
   }
+  for (int k = 0; k < 3; ++k) h->nloc[k] = st.nloc[k];
   if (ensure_lists(h, st.tot0, st.totC, st.totD)) return 1;
   h->L.off0 = h->oslice;
   h->L.offC = h->oslice + h->nslices;
@@ -347,12 +438,17 @@ int build_neighbours(spsph_handle *h) {
   if (st.n_pairs > h->m_pairs) gr.mode = (h->m_pairs == 0) ? 1 : 2;
   CUDA_TRY(cudaMemcpyAsync(h->growth, &gr, sizeof(gr), cudaMemcpyHostToDevice, s));
   if (h->profiling) mark(h, -1, 0);  // do not charge the host round trip to the next kernel
+  if (gr.mode == 2 && h->dist) {
+    h->err = "multi-GPU: the pair count grew past its previous maximum (reference list-growth rule, SURVEY App. B); "
+             "the split traversal order is not implemented for the slab decomposition yet";
+    return 1;
+  }
   if (gr.mode == 2) {
     k_growth_threshold<<<1, 32, 0, s>>>(P, h->M, h->G, S, h->base_u, h->m_pairs, h->growth);
     mark(h, KID_THRESH);
   }
   if (st.n_pairs > h->m_pairs) h->m_pairs = st.n_pairs;
-  const int TL = h->M.nnp + h->M.nsp;
+  const int TL = h->M.nnp + h->M.nsp;  // (parked slots return at once)
   k_fill<<<(TL + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int, h->n_int);
   mark(h, KID_FILL);
   return 0;
@@ -364,12 +460,16 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     return 1;
   }
   step_scalars(h, itimestep, time_sph, dt);
+  if (h->dist && halo_exchange(h)) return 1;
   if (build_neighbours(h)) return 1;
   const DevParams &P = h->P;
   const spsph_params &p = h->hp;
   cudaStream_t s = h->stream;
   const SortArrays S = sort_arrays(h);
-  const SlotMap &M = h->M;
+  SlotMap M = h->M;  // launch extents: only the particles this rank has to process (same slot layout)
+  M.nn = h->nloc[0];
+  M.ns = h->nloc[1];
+  const int *lflag = h->dist ? h->lflag : nullptr;
   const int GN = (M.nn + 127) / 128, GS = (M.ns + 127) / 128, GB = (M.nnp + M.nsp + 127) / 128;
   const int adapt = P.adapt, bc = p.no_bcs > 0 ? 1 : 0;
   const int *ord_n = S.order[0], *ord_s = S.order[1];
@@ -385,7 +485,7 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   }
   const StatePtrs st = state_ptrs(h, h->cur);
   // RK4, main:653-802
-  k_rk_begin<<<(P.ntotal + 255) / 256, 256, 0, s>>>(P, st);
+  k_rk_begin<<<(P.ntotal + 255) / 256, 256, 0, s>>>(P, st, lflag);
   mark(h, KID_RKBEGIN);
   const double f1rk[4] = {0., 0.5, 0.5, 1.0}, f2rk[4] = {1., 2., 2., 1.0};
   for (int stg = 0; stg < 4; ++stg) {
@@ -417,7 +517,7 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   k_move<<<GB, 128, 0, s>>>(P, M, S, h->L, h->n1, st, h->x, h->x00, h->displ);
   mark(h, KID_MOVE);
   if (p.update_x && p.sp_sph && !p.inside_approach) {
-    k_shift<<<(P.nnode + 255) / 256, 256, 0, s>>>(P, st.NB, h->x, h->x_10, h->disp_10, h->bc_int, h->n_int);
+    k_shift<<<(P.nnode + 255) / 256, 256, 0, s>>>(P, st.NB, h->x, h->x_10, h->disp_10, h->bc_int, h->n_int, lflag);
     mark(h, KID_SHIFT);
   }
   CUDA_TRY(cudaGetLastError());
@@ -555,7 +655,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   h->bbox_blocks = 296;
   rc |= dalloc(h, &h->bbox_partial, 6 * (size_t)h->bbox_blocks);
   rc |= dalloc(h, &h->which_cell, n2) | dalloc(h, &h->tmp_ids, 3 * n2) | dalloc(h, &h->order, 3 * n2);
-  rc |= dalloc(h, &h->scell, 3 * n2) | dalloc(h, &h->pos_of, n2) | dalloc(h, &h->nout, 4);
+  rc |= dalloc(h, &h->scell, 3 * n2) | dalloc(h, &h->pos_of, n2) | dalloc(h, &h->nout, 8) | dalloc(h, &h->bb6, 8);
   rc |= dalloc(h, &h->spos, 3 * n2) | dalloc(h, &h->sh, 3 * n2) | dalloc(h, &h->supos, 3 * n2);
   rc |= dalloc(h, &h->scan_bsum, 4 * (size_t)SCAN_BLOCKS) | dalloc(h, &h->scan_totals, 8);
   const size_t T = (size_t)M.total();
@@ -651,6 +751,10 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   }
   h->m_pairs = 0;
   h->uploaded = true;
+  if (h->dist) {  // a fresh upload holds complete data on every rank: re-derive owned / ghost / remote
+    k_dist_init_flags<<<((int)n2 + 255) / 256, 256, 0, st>>>(h->P, h->D, h->x, h->lflag);
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
   return 0;
 }
 
@@ -810,12 +914,101 @@ int spsph_pairs(spsph_handle *h, int64_t *npairs, int32_t *pair_i, int32_t *pair
   return 0;
 }
 
+int spsph_dist_unique_id(char *id128) {
+  void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!lib) return 1;
+  auto f = (ncclResult_t(*)(ncclUniqueId *))dlsym(lib, "ncclGetUniqueId");
+  if (!f) return 1;
+  ncclUniqueId u;
+  if (f(&u) != ncclSuccess) return 1;
+  std::memcpy(id128, u.internal, 128);
+  return 0;
+}
+
+int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *id128, const double *planes,
+                    int32_t halo_cells, int32_t halo_capacity) {
+  if (!h || !planes || nranks < 1 || rank < 0 || rank >= nranks) return 1;
+  if (!h->uploaded) {
+    h->err = "spsph_dist_init must follow spsph_upload (every rank uploads the complete problem)";
+    return 1;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  const spsph_params &p = h->hp;
+  h->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  if (!h->nccl_lib) {
+    h->err = std::string("cannot load libnccl.so.2: ") + dlerror();
+    return 1;
+  }
+#define NCCL_SYM(name)                                                            \
+  h->p_##name = (decltype(h->p_##name))dlsym(h->nccl_lib, #name);                \
+  if (!h->p_##name) {                                                             \
+    h->err = "libnccl.so.2 lacks " #name;                                         \
+    return 1;                                                                     \
+  }
+  NCCL_SYM(ncclCommInitRank)
+  NCCL_SYM(ncclCommDestroy)
+  NCCL_SYM(ncclSend)
+  NCCL_SYM(ncclRecv)
+  NCCL_SYM(ncclAllReduce)
+  NCCL_SYM(ncclGroupStart)
+  NCCL_SYM(ncclGroupEnd)
+  NCCL_SYM(ncclGetErrorString)
+#undef NCCL_SYM
+  ncclUniqueId u;
+  std::memcpy(u.internal, id128, 128);
+  NCCL_TRY(h->p_ncclCommInitRank(&h->comm, nranks, u, rank));
+  // halo distance: every dependent sweep of a step reads partners at most one cell (2*max h) away
+  double hmax = 0.0;
+  {
+    std::vector<double> hs((size_t)p.ntotal2);
+    CUDA_TRY(cudaMemcpy(hs.data(), h->hsml, hs.size() * 8, cudaMemcpyDeviceToHost));
+    for (double v : hs) hmax = std::fmax(hmax, v);
+  }
+  DistGeom &D = h->D;
+  D.rank = rank;
+  D.nranks = nranks;
+  D.lo = planes[rank];
+  D.hi = planes[rank + 1];
+  D.H = (double)halo_cells * 2.0 * hmax;
+  D.sp_follows_node = (p.sp_sph && !p.inside_approach) ? 1 : 0;
+  D.cap = halo_capacity;
+  if (nranks > 1 && (D.hi - D.lo) < D.H && rank > 0 && rank < nranks - 1) {
+    h->err = "multi-GPU: slab thinner than the halo distance";
+    return 1;
+  }
+  const size_t n2 = (size_t)p.ntotal2;
+  const size_t msg = (size_t)HALO_REC * ((size_t)D.cap + 1);
+  if (dalloc(h, &h->lflag, n2) || dalloc(h, &h->halo_cnt, 4)) return 1;
+  for (int side = 0; side < 2; ++side)
+    if (dalloc(h, &h->halo_ids[side], (size_t)D.cap) || dalloc(h, &h->halo_send[side], msg) ||
+        dalloc(h, &h->halo_recv[side], msg))
+      return 1;
+  CUDA_TRY(cudaMemset(h->halo_cnt, 0, 4 * sizeof(int)));
+  h->dist = true;
+  k_dist_init_flags<<<((int)n2 + 255) / 256, 256, 0, h->stream>>>(h->P, h->D, h->x, h->lflag);
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  return 0;
+}
+
+int spsph_dist_flags(spsph_handle *h, int32_t *flags) {
+  if (!h || !flags) return 1;
+  CUDA_TRY(cudaSetDevice(h->device));
+  CUDA_TRY(cudaStreamSynchronize(h->stream));
+  if (!h->dist) {
+    for (int i = 0; i < h->hp.ntotal2; ++i) flags[i] = 1;
+    return 0;
+  }
+  CUDA_TRY(cudaMemcpy(flags, h->lflag, (size_t)h->hp.ntotal2 * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int spsph_destroy(spsph_handle *h) {
   if (!h) return 0;
   if (h->stream) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
   }
+  if (h->comm && h->p_ncclCommDestroy) h->p_ncclCommDestroy(h->comm);
   for (void *q : h->allocs) cudaFree(q);
   for (cudaEvent_t e : h->ev_pool) cudaEventDestroy(e);
   cudaFree(h->L.idx0);

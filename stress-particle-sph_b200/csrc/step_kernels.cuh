@@ -227,9 +227,10 @@ __global__ void k_unpack_state(DevParams P, StatePtrs st, double *__restrict__ v
 // format B (state) -> format A (stage-1 input); saves vel0/stress0/vx0 and zeroes the RK accumulators.
 // Stress-particle velocities and node stresses start from zero (main:690).
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_rk_begin(DevParams P, StatePtrs st) {
+__global__ void k_rk_begin(DevParams P, StatePtrs st, const int *__restrict__ lflag) {
   const int id = blockIdx.x * blockDim.x + threadIdx.x;
   if (id >= P.ntotal) return;
+  if (lflag && lflag[id] == 0) return;  // remote particle (multi-GPU)
   double2 vn;
   Stress4 sn;
   if (id < P.nnode) {
@@ -958,9 +959,11 @@ k_move(DevParams P, SlotMap M, SortArrays So, ListPtrs L, const int *__restrict_
 
 // shift_stress_points, main:244-368 (outside approach): one thread per node re-seats its stress particles.
 __global__ void k_shift(DevParams P, const Rec4 *__restrict__ NB, double *__restrict__ x, double *__restrict__ x_10,
-                        double *__restrict__ disp_10, const int *__restrict__ bc_int, const float *__restrict__ n_int) {
+                        double *__restrict__ disp_10, const int *__restrict__ bc_int, const float *__restrict__ n_int,
+                        const int *__restrict__ lflag) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P.nnode) return;
+  if (lflag && lflag[i] == 0) return;  // remote particle (multi-GPU)
   const double2 xi = ld2(x, i);
   const Rec4 rr = ldrec(NB, i);
   const double2 v = make_double2(rr.a, rr.b);
@@ -1015,6 +1018,7 @@ __global__ void k_pair_stats(SlotMap M, const int *__restrict__ nall, int *__res
     int sp, k;
     if (!slot_decode(M, i, sp, k)) continue;  // padding slot
     const int c = nall[i];
+    if (c < 0) continue;  // not owned by this rank (multi-GPU)
     mx = max(mx, c);
     mn = min(mn, c);
     nz += (c == 0);

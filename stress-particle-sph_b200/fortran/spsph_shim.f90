@@ -112,6 +112,23 @@ module spsph_c_api
        real(c_double), intent(out) :: total_ms
        integer(c_int64_t), intent(out) :: launches
      end function
+     integer(c_int) function spsph_dist_unique_id(id128) bind(C, name="spsph_dist_unique_id")
+       import :: c_int, c_char
+       character(kind=c_char), intent(out) :: id128(128)
+     end function
+     integer(c_int) function spsph_dist_init(h, rank, nranks, id128, planes, halo_cells, halo_capacity) &
+          bind(C, name="spsph_dist_init")
+       import :: c_ptr, c_int, c_int32_t, c_char, c_double
+       type(c_ptr), value :: h
+       integer(c_int32_t), value :: rank, nranks, halo_cells, halo_capacity
+       character(kind=c_char), intent(in) :: id128(128)
+       real(c_double), intent(in) :: planes(*)
+     end function
+     integer(c_int) function spsph_dist_flags(h, flags) bind(C, name="spsph_dist_flags")
+       import :: c_ptr, c_int, c_int32_t
+       type(c_ptr), value :: h
+       integer(c_int32_t), intent(out) :: flags(*)
+     end function
      integer(c_int) function spsph_sync(h) bind(C, name="spsph_sync")
        import :: c_ptr, c_int
        type(c_ptr), value :: h

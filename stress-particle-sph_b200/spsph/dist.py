@@ -1,0 +1,87 @@
+"""Host-side planning of the multi-GPU x-slab decomposition (device side in
+csrc/dist_kernels.cuh). Pure numpy so that the partition logic is testable without a GPU.
+
+One process per GPU. Every rank loads the complete problem, creates its Engine, uploads everything and calls
+Engine.dist_init(plan): from then on each rank advances its slab plus a wide halo and exchanges ghost
+particles / migrants with its two neighbours over NCCL once per time step.
+"""
+import numpy as np
+
+REMOTE, OWNED, GHOST = 0, 1, 2
+
+
+def dependent_sweeps(params):
+    """number of kernels per time step that read partner values produced earlier in the same step; the
+    redundantly computed ghost region loses one cell of validity per such kernel"""
+    n = 8 + 1                      # 4 x (stress_point_update, get_derivatives) + the final stress_point_update
+    if params.sph_shift:
+        n += 1                     # interpolation at the start of the step (main:99-109)
+    if params.update_x and params.xsph:
+        n += 1                     # XSPH_update reads partner velocities (main:189-239)
+    return n
+
+
+def plan_slabs(problem, nranks, safety=2.0):
+    """-> dict(planes, halo_cells, halo_capacity, H). Slabs hold equal numbers of velocity particles; a plane is
+    placed midway between two distinct particle columns so that no particle sits on it initially."""
+    p = problem.params
+    x = problem.arrays["x"][:, 0]
+    xn = np.sort(x[:p.nnode])
+    planes = [-np.inf]
+    ux = np.unique(xn)
+    for r in range(1, nranks):
+        target = xn[(r * p.nnode) // nranks]
+        k = int(np.searchsorted(ux, target))
+        k = min(max(k, 1), len(ux) - 1)
+        planes.append(0.5 * (ux[k - 1] + ux[k]))
+    planes.append(np.inf)
+    planes = np.array(planes, dtype=np.float64)
+    halo_cells = dependent_sweeps(p) + 2
+    hmax = float(problem.arrays["hsml"].max())
+    H = halo_cells * 2.0 * hmax
+    cap = 1024
+    for r in range(1, nranks):
+        near = int(((x >= planes[r] - H) & (x < planes[r] + H)).sum())
+        cap = max(cap, int(safety * near) + 1024)
+    widths = np.diff(planes[1:-1]) if nranks > 2 else np.array([np.inf])
+    if nranks > 2 and widths.min() < H:
+        raise ValueError(f"slab width {widths.min():.4g} is below the halo distance {H:.4g}: use fewer ranks")
+    return dict(planes=planes, halo_cells=halo_cells, halo_capacity=cap, H=H)
+
+
+def key_x(problem):
+    """position that decides ownership (k_dist_init_flags / key_x in dist_kernels.cuh)"""
+    p = problem.params
+    x = problem.arrays["x"][:, 0].copy()
+    if p.sp_sph and not p.inside_approach:
+        node_of = (np.arange(p.nstress) // p.npoints)
+        x[p.nnode:p.ntotal] = problem.arrays["x"][node_of, 0]
+    return x
+
+
+def initial_flags(problem, plan, rank):
+    """numpy restatement of k_dist_init_flags: 0 remote, 1 owned, 2 ghost"""
+    lo, hi, H = plan["planes"][rank], plan["planes"][rank + 1], plan["H"]
+    xk, xi = key_x(problem), problem.arrays["x"][:, 0]
+    f = np.zeros(len(xi), np.int32)
+    f[(xi >= lo - H) & (xi < hi + H)] = GHOST
+    f[(xk >= lo) & (xk < hi)] = OWNED
+    return f
+
+
+def merge_owned(per_rank_arrays, per_rank_flags, params):
+    """assemble the global state from every rank's download: entry i comes from the rank that owns particle i"""
+    out = {k: v.copy() for k, v in per_rank_arrays[0].items()}
+    seen = np.zeros(params.ntotal2, bool)
+    for arrs, fl in zip(per_rank_arrays, per_rank_flags):
+        own = fl == OWNED
+        if (seen & own).any():
+            raise AssertionError("a particle is owned by two ranks")
+        seen |= own
+        for k, v in arrs.items():
+            n = v.shape[0]
+            m = own[:n]
+            out[k][m] = v[m]
+    if not seen.all():
+        raise AssertionError(f"{int((~seen).sum())} particles are owned by no rank")
+    return out

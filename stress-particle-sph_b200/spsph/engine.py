@@ -33,6 +33,9 @@ def cuda_lib():
         L.spsph_pairs.argtypes = [H, C.POINTER(C.c_int64)] + [C.c_void_p] * 6
         L.spsph_last_run_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
         L.spsph_sync.argtypes = [H]
+        L.spsph_dist_unique_id.argtypes = [C.c_char_p]
+        L.spsph_dist_init.argtypes = [H, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_double), C.c_int32, C.c_int32]
+        L.spsph_dist_flags.argtypes = [H, C.c_void_p]
         L.spsph_profile.argtypes = [H, C.c_int]
         L.spsph_profile_get.argtypes = [H, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.spsph_destroy.argtypes = [H]
@@ -44,7 +47,15 @@ def cuda_lib():
 
 
 EXPORTS = ["spsph_create", "spsph_upload", "spsph_step", "spsph_run", "spsph_download", "spsph_pair_stats",
-           "spsph_pairs", "spsph_last_run_ms", "spsph_sync", "spsph_profile", "spsph_profile_get", "spsph_destroy", "spsph_last_error", "spsph_version"]
+           "spsph_pairs", "spsph_last_run_ms", "spsph_sync", "spsph_profile", "spsph_profile_get",
+           "spsph_dist_unique_id", "spsph_dist_init", "spsph_dist_flags", "spsph_destroy", "spsph_last_error", "spsph_version"]
+
+
+def dist_unique_id():
+    buf = C.create_string_buffer(128)
+    if cuda_lib().spsph_dist_unique_id(buf):
+        raise RuntimeError("ncclGetUniqueId failed (libnccl.so.2 not loadable?)")
+    return buf.raw
 
 
 class Engine:
@@ -97,6 +108,19 @@ class Engine:
             out[name.value.decode()] = (ms.value, n.value)
             kid += 1
         return out
+
+    def dist_init(self, rank, nranks, unique_id, plan):
+        """join the x-slab decomposition (spsph.dist.plan_slabs); unique_id: 128 bytes from dist_unique_id()"""
+        planes = np.ascontiguousarray(plan["planes"], dtype=np.float64)
+        assert len(planes) == nranks + 1 and len(unique_id) == 128
+        self._chk(self.L.spsph_dist_init(self.h, rank, nranks, bytes(unique_id),
+                                         planes.ctypes.data_as(C.POINTER(C.c_double)), int(plan["halo_cells"]),
+                                         int(plan["halo_capacity"])))
+
+    def dist_flags(self):
+        f = np.zeros(self.p.ntotal2, np.int32)
+        self._chk(self.L.spsph_dist_flags(self.h, f.ctypes.data))
+        return f
 
     def sync(self):
         self._chk(self.L.spsph_sync(self.h))

@@ -1,0 +1,59 @@
+#!/usr/bin/env python
+"""One rank of a multi-GPU run (launched by torchrun or by tests/test_multi_gpu.py with RANK/WORLD_SIZE set).
+Runs `--steps` steps of a generated deck on the x-slab decomposition and writes this rank's download + ownership
+flags to `--out`/rank<r>.npz for the parity check against the oracle."""
+import argparse
+import os
+import sys
+import tempfile
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "stress-particle-sph_b200"))
+import spsph  # noqa: E402
+from spsph import decks, dist  # noqa: E402
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--kind", default="vs")
+    ap.add_argument("--ncol", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--out", required=True)
+    a = ap.parse_args()
+    import torch
+    import torch.distributed as td
+    rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+    local = int(os.environ.get("LOCAL_RANK", rank))
+    torch.cuda.set_device(local)
+    td.init_process_group("gloo")
+    d = tempfile.mkdtemp()
+    if a.kind == "refined_bui":
+        spec, var = decks.refined_bui_spec(ncol=a.ncol), "bui"
+    elif a.kind == "wide_slope":
+        spec, var = decks.wide_slope_spec(ncol=a.ncol, nslab=world), "vs"
+    else:
+        spec, var = decks.SHIPPED[a.kind](), a.kind
+    decks.write_deck(d, spec)
+    prob = spsph.load(d, var)
+    plan = dist.plan_slabs(prob, world)
+    uid = [spsph.dist_unique_id() if rank == 0 else None]
+    td.broadcast_object_list(uid, src=0)
+    eng = spsph.Engine(prob, device=local)
+    eng.dist_init(rank, world, uid[0], plan)
+    dt = prob.blocks[0]["dt"]
+    eng.run(1, 0.0, dt, a.steps)
+    ms, launches = eng.last_run()
+    arrs = eng.download()
+    flags = eng.dist_flags()
+    os.makedirs(a.out, exist_ok=True)
+    np.savez(os.path.join(a.out, f"rank{rank}.npz"), flags=flags, ms=ms, npairs=eng.pair_stats()["npairs"],
+             **{k: arrs[k] for k in ("x", "vel", "stress", "internal_vars", "f_drucker", "displ")})
+    td.barrier()
+    eng.close()
+    td.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
