@@ -130,6 +130,8 @@ int spsph_dist_unique_id(char *id128);
 int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *id128, const double *planes,
                     int32_t halo_cells, int32_t halo_capacity);
 int spsph_dist_flags(spsph_handle *h, int32_t *flags);
+/* particles per species (velocity, stress, wall) this rank processed in the last step: its slab + halo */
+int spsph_local_counts(spsph_handle *h, int32_t *nloc3);
 int spsph_sync(spsph_handle *h);
 int spsph_destroy(spsph_handle *h);
 const char *spsph_last_error(spsph_handle *h);

@@ -990,6 +990,12 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
   return 0;
 }
 
+int spsph_local_counts(spsph_handle *h, int32_t *nloc3) {
+  if (!h || !nloc3) return 1;
+  for (int k = 0; k < 3; ++k) nloc3[k] = h->nloc[k];
+  return 0;
+}
+
 int spsph_dist_flags(spsph_handle *h, int32_t *flags) {
   if (!h || !flags) return 1;
   CUDA_TRY(cudaSetDevice(h->device));

@@ -129,6 +129,11 @@ module spsph_c_api
        type(c_ptr), value :: h
        integer(c_int32_t), intent(out) :: flags(*)
      end function
+     integer(c_int) function spsph_local_counts(h, nloc3) bind(C, name="spsph_local_counts")
+       import :: c_ptr, c_int, c_int32_t
+       type(c_ptr), value :: h
+       integer(c_int32_t), intent(out) :: nloc3(3)
+     end function
      integer(c_int) function spsph_sync(h) bind(C, name="spsph_sync")
        import :: c_ptr, c_int
        type(c_ptr), value :: h

@@ -36,6 +36,7 @@ def cuda_lib():
         L.spsph_dist_unique_id.argtypes = [C.c_char_p]
         L.spsph_dist_init.argtypes = [H, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_double), C.c_int32, C.c_int32]
         L.spsph_dist_flags.argtypes = [H, C.c_void_p]
+        L.spsph_local_counts.argtypes = [H, C.c_void_p]
         L.spsph_profile.argtypes = [H, C.c_int]
         L.spsph_profile_get.argtypes = [H, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
         L.spsph_destroy.argtypes = [H]
@@ -48,7 +49,7 @@ def cuda_lib():
 
 EXPORTS = ["spsph_create", "spsph_upload", "spsph_step", "spsph_run", "spsph_download", "spsph_pair_stats",
            "spsph_pairs", "spsph_last_run_ms", "spsph_sync", "spsph_profile", "spsph_profile_get",
-           "spsph_dist_unique_id", "spsph_dist_init", "spsph_dist_flags", "spsph_destroy", "spsph_last_error", "spsph_version"]
+           "spsph_dist_unique_id", "spsph_dist_init", "spsph_dist_flags", "spsph_local_counts", "spsph_destroy", "spsph_last_error", "spsph_version"]
 
 
 def dist_unique_id():
@@ -116,6 +117,11 @@ class Engine:
         self._chk(self.L.spsph_dist_init(self.h, rank, nranks, bytes(unique_id),
                                          planes.ctypes.data_as(C.POINTER(C.c_double)), int(plan["halo_cells"]),
                                          int(plan["halo_capacity"])))
+
+    def local_counts(self):
+        n = np.zeros(3, np.int32)
+        self._chk(self.L.spsph_local_counts(self.h, n.ctypes.data))
+        return [int(v) for v in n]
 
     def dist_flags(self):
         f = np.zeros(self.p.ntotal2, np.int32)
