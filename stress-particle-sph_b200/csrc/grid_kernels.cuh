@@ -185,7 +185,13 @@ __global__ void k_cell_id(DevParams P, const GridInfo *__restrict__ G, const dou
   if (i >= P.ntotal2) return;
   const int sp = species_of(P, i);
   if (lflag && lflag[i] == 0) {  // remote (other rank's) particle: parked last, never processed
-    which_cell[i] = PARK_REMOTE - atomicAdd(&nout[3 + sp], 1);
+    // warp-aggregated counter (millions of remote particles would otherwise serialise on one address)
+    const unsigned grp = __match_any_sync(__activemask(), sp);
+    const int lane = threadIdx.x & 31, leader = __ffs(grp) - 1;
+    int base = 0;
+    if (lane == leader) base = atomicAdd(&nout[3 + sp], __popc(grp));
+    base = __shfl_sync(grp, base, leader);
+    which_cell[i] = PARK_REMOTE - (base + __popc(grp & ((1u << lane) - 1)));
     return;
   }
   if (if_out[i] || G->overflow) {  // on a cell-table overflow nothing is binned; the host reports the error
