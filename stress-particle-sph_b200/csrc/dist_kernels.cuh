@@ -124,10 +124,10 @@ __global__ void k_halo_pack(DevParams P, StatePtrs st, HaloArrays A, const int *
       o[15] = A.displ[2 * (size_t)i + 1];
     } else if (i < P.ntotal) {
       const int ks = i - P.nnode;
-      const double2 v = ld2(st.SVb, ks);
+      const Rec4 v = ldrec(st.SVb, ks);
       const Stress4 s = ld4(st.SFb, ks);
-      o[3] = v.x;
-      o[4] = v.y;
+      o[3] = v.a;
+      o[4] = v.b;
       o[5] = s.s1;
       o[6] = s.s2;
       o[7] = s.s3;
@@ -162,7 +162,7 @@ __global__ void k_halo_unpack(DevParams P, DistGeom D, StatePtrs st, HaloArrays 
       A.displ[2 * (size_t)i + 1] = o[15];
     } else if (i < P.ntotal) {
       const int ks = i - P.nnode;
-      st2(st.SVb, ks, make_double2(o[3], o[4]));
+      strec(st.SVb, ks, o[3], o[4], st.mor[i], 0.0);
       const Stress4 s{o[5], o[6], o[7], o[8]};
       st4(st.SFb, ks, s);
       const double r = st.rho[i];

@@ -662,9 +662,15 @@ struct ListPtrs {
   //         orientation of the gradient (pair_i - pair_j after Pint_Update)
   int *idx0;
   float *w0, *gx0, *gy0;
+  // (mass/rho)_partner * w as fp64 (low / high words), the factor h1/h2 of stress_point_update (main:430-431):
+  // streaming it removes the per-entry gather of the partner's mass/rho (the pair-sum kernels are bound by the
+  // L1 rate of gathered sectors, not by the streamed bytes)
+  int *h0lo, *h0hi;
   // list C: node <- node (type 3), own-perspective gradient; list D: stress <- stress (type 2), weight only
   int *idxC;
   float *wC, *gxC, *gyC;
+  // fp32 geometry of artificial_viscosity (main:856-864), frozen during a step: xij, yij, h = 0.5*(h_i+h_j)
+  float *xC, *yC, *hC;
   int *idxD;
   float *wD;
   const int *off0, *offC, *offD;  // per slice, exclusive scans of the slice widths
@@ -679,7 +685,7 @@ constexpr int FILL_THREADS = 128;
 __global__ void __launch_bounds__(FILL_THREADS)
 k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ n0,
        const int *__restrict__ n1, const GrowthRule *__restrict__ growth, ListPtrs L, int *__restrict__ bc_int,
-       float *__restrict__ n_int) {
+       float *__restrict__ n_int, const double *__restrict__ mor) {
   __shared__ int q0buf[QCAP][FILL_THREADS];  // cross-species partners (species in the top 2 bits)
   __shared__ int q1buf[QCAP][FILL_THREADS];  // same-species partners
   const int tid = threadIdx.x;
@@ -769,8 +775,13 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
         sph_kernel(P, r, dx, dy, mh, w, gx, gy);
       const int pos = (e0 < s0) ? (cnt0 - s0) + e0 : (cnt0 - 1 - e0);
       const size_t a = o0 + (size_t)pos * SLICE;
-      L.idx0[a] = S.order[sq][q];
-      L.w0[a] = (float)w;
+      const int qid = S.order[sq][q];
+      const float wf = (float)w;
+      const double h0 = (sq == SP_DUMMY) ? 0.0 : mor[qid] * (double)wf;
+      L.idx0[a] = qid;
+      L.h0lo[a] = __double2loint(h0);
+      L.h0hi[a] = __double2hiint(h0);
+      L.w0[a] = wf;
       L.gx0[a] = (float)gx;
       L.gy0[a] = (float)gy;
       if (sq == SP_DUMMY) has_dummy = 1;
@@ -798,6 +809,9 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
         L.wC[a] = (float)w;
         L.gxC[a] = (float)gx;
         L.gyC[a] = (float)gy;
+        L.xC[a] = (float)dx;                 // xij = real(x(1,i) - x(1,j)), main:856
+        L.yC[a] = (float)dy;
+        L.hC[a] = (float)(0.5 * (hp + hq));  // main:863
       } else {
         if (mh == K.h)
           sph_kernel_fast<false>(K, r, dx, dy, w, gx, gy);

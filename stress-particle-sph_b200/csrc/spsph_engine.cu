@@ -49,10 +49,9 @@ struct spsph_handle {
 
   // particle state (original order)
   double *x = nullptr, *x00 = nullptr, *rho = nullptr, *mass = nullptr, *hsml = nullptr, *mor = nullptr;
-  Rec4 *NA = nullptr, *NB[2] = {nullptr, nullptr}, *SB[2] = {nullptr, nullptr};
-  Rec8 *SA = nullptr;
-  double *NSa = nullptr, *SVa = nullptr;
-  double *NSb[2] = {nullptr, nullptr}, *SFb[2] = {nullptr, nullptr}, *SVb[2] = {nullptr, nullptr};
+  Rec4 *NB[2] = {nullptr, nullptr}, *SB[2] = {nullptr, nullptr}, *SVb[2] = {nullptr, nullptr}, *SA = nullptr;
+  double *NA = nullptr, *NSa = nullptr, *SVa = nullptr, *av = nullptr;
+  double *NSb[2] = {nullptr, nullptr}, *SFb[2] = {nullptr, nullptr};
   double *stage_vel = nullptr, *stage_stress = nullptr;  // reference-layout staging for upload / download
   double *epsp = nullptr, *fdp = nullptr, *norm = nullptr, *AE = nullptr;
   double *vel0 = nullptr, *stress0 = nullptr, *vx0 = nullptr, *RKv = nullptr, *RKs = nullptr, *RKe = nullptr;
@@ -215,6 +214,7 @@ StatePtrs state_ptrs(spsph_handle *h, int wb) {
   s.NSbr = h->NSb[1 - wb];
   s.SFbr = h->SFb[1 - wb];
   s.SVbr = h->SVb[1 - wb];
+  s.av = h->av;
   s.epsp = h->epsp;
   s.fdp = h->fdp;
   s.norm = h->norm;
@@ -290,6 +290,10 @@ int ensure_lists(spsph_handle *h, long long t0, long long tC, long long tD) {
     cudaFree(h->L.w0);
     cudaFree(h->L.gx0);
     cudaFree(h->L.gy0);
+    cudaFree(h->L.h0lo);
+    cudaFree(h->L.h0hi);
+    CUDA_TRY(cudaMalloc((void **)&h->L.h0lo, (size_t)h->cap0 * 4));
+    CUDA_TRY(cudaMalloc((void **)&h->L.h0hi, (size_t)h->cap0 * 4));
     CUDA_TRY(cudaMalloc((void **)&h->L.idx0, (size_t)h->cap0 * 4));
     CUDA_TRY(cudaMalloc((void **)&h->L.w0, (size_t)h->cap0 * 4));
     CUDA_TRY(cudaMalloc((void **)&h->L.gx0, (size_t)h->cap0 * 4));
@@ -300,6 +304,12 @@ int ensure_lists(spsph_handle *h, long long t0, long long tC, long long tD) {
     cudaFree(h->L.wC);
     cudaFree(h->L.gxC);
     cudaFree(h->L.gyC);
+    cudaFree(h->L.xC);
+    cudaFree(h->L.yC);
+    cudaFree(h->L.hC);
+    CUDA_TRY(cudaMalloc((void **)&h->L.xC, (size_t)h->capC * 4));
+    CUDA_TRY(cudaMalloc((void **)&h->L.yC, (size_t)h->capC * 4));
+    CUDA_TRY(cudaMalloc((void **)&h->L.hC, (size_t)h->capC * 4));
     CUDA_TRY(cudaMalloc((void **)&h->L.idxC, (size_t)h->capC * 4));
     CUDA_TRY(cudaMalloc((void **)&h->L.wC, (size_t)h->capC * 4));
     CUDA_TRY(cudaMalloc((void **)&h->L.gxC, (size_t)h->capC * 4));
@@ -449,7 +459,7 @@ int build_neighbours(spsph_handle *h) {
   }
   if (st.n_pairs > h->m_pairs) h->m_pairs = st.n_pairs;
   const int TL = h->M.nnp + h->M.nsp;  // (parked slots return at once)
-  k_fill<<<(TL + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int, h->n_int);
+  k_fill<<<(TL + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int, h->n_int, h->mor);
   mark(h, KID_FILL);
   return 0;
 }
@@ -500,14 +510,16 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     first_a = false;
     const int last = (stg == 3);
     const double f1n = last ? 0.0 : f1rk[stg + 1];
+    const bool artv = (P.alpha > 0 || P.beta > 0);
+    if (artv) k_artvisc<<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n1, st);
     if (stg == 0) {
       k_sweep_b_sp<true><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last);
-      k_sweep_b_node<true><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, h->n1, st, f1n, f2rk[stg], last);
+      k_sweep_b_node<true><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
     } else {
       k_sweep_b_sp<false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last);
-      k_sweep_b_node<false><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, h->n1, st, f1n, f2rk[stg], last);
+      k_sweep_b_node<false><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
     }
-    mark(h, KID_SWEEPB, 2);
+    mark(h, KID_SWEEPB, artv ? 3 : 2);
   }
   // final stress_point_update + adapt_stress2 + BCs, main:130-135
   k_sweep_a_sp<false, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
@@ -638,10 +650,11 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   int rc = 0;
   rc |= dalloc(h, &h->x, 2 * n2) | dalloc(h, &h->x00, 2 * n2) | dalloc(h, &h->rho, n2) | dalloc(h, &h->mass, n2);
   rc |= dalloc(h, &h->hsml, n2) | dalloc(h, &h->mor, n2);
-  rc |= dalloc(h, &h->NA, nn) | dalloc(h, &h->SA, ns) | dalloc(h, &h->NSa, 4 * nn) | dalloc(h, &h->SVa, 2 * ns);
+  rc |= dalloc(h, &h->NA, 2 * nn) | dalloc(h, &h->SA, ns) | dalloc(h, &h->NSa, 4 * nn) | dalloc(h, &h->SVa, 2 * ns);
+  rc |= dalloc(h, &h->av, 2 * nn);
   for (int b = 0; b < 2; ++b) {
     rc |= dalloc(h, &h->NB[b], nn) | dalloc(h, &h->SB[b], ns) | dalloc(h, &h->NSb[b], 4 * nn);
-    rc |= dalloc(h, &h->SFb[b], 4 * ns) | dalloc(h, &h->SVb[b], 2 * ns);
+    rc |= dalloc(h, &h->SFb[b], 4 * ns) | dalloc(h, &h->SVb[b], ns);
   }
   rc |= dalloc(h, &h->stage_vel, 2 * nt) | dalloc(h, &h->stage_stress, 4 * nt);
   rc |= dalloc(h, &h->epsp, nt) | dalloc(h, &h->fdp, nt) | dalloc(h, &h->norm, nt);
@@ -1021,6 +1034,11 @@ int spsph_destroy(spsph_handle *h) {
   cudaFree(h->L.w0);
   cudaFree(h->L.gx0);
   cudaFree(h->L.gy0);
+  cudaFree(h->L.h0lo);
+  cudaFree(h->L.h0hi);
+  cudaFree(h->L.xC);
+  cudaFree(h->L.yC);
+  cudaFree(h->L.hC);
   cudaFree(h->L.idxC);
   cudaFree(h->L.wC);
   cudaFree(h->L.gxC);

@@ -6,17 +6,20 @@
 // One thread per velocity / stress particle, walking its gather list front to back: every per-particle sum
 // is accumulated in the reference's traversal order (fp32 sums bit-exact, fp64 sums too), no atomics.
 //
-// Data layout. The state lives in two buffer sets with *different record formats*, each written by the
-// kernel that precedes its reader so that a neighbour gather is one aligned 32-byte sector:
+// Data layout. The pair-sum kernels are bound by the L1 rate of *gathered sectors* (about one 32-byte sector
+// per clock per SM for scattered lanes; ncu: l1tex__data_pipe_lsu_wavefronts at 86 % in round-1 profiles), not by
+// HBM. The state therefore lives in two buffer sets with *different record formats*, each written by the kernel
+// that precedes its reader, such that every neighbour gather is ONE aligned sector (or half of one):
 //   format A (input of sweep A = stress_point_update):
-//       NA[node] = {vx, vy, m/rho, -}            SA[sp] = {s1, s2, s3, s4, m/rho, eps_p, -, -}
+//       NA[node] = {vx, vy} (16 B)               SA[sp] = {s1, s2, s3, s4} (32 B)
 //       NSa[node] = own stress (carried)         SVa[sp] = own velocity (carried)
+//       the factor (m/rho)_partner * w of main:430-431 is streamed with the list (ListPtrs::h0lo/h0hi)
 //   format B (input of sweep B = get_derivatives; also the state between time steps):
 //       NB[node] = {vx, vy, m, rho}              SB[sp] = {s1/rho^2, s2/rho^2, s3/rho^2, m}
-//       NSb[node] = own stress                   SFb[sp] = own stress, SVb[sp] = own velocity
+//       NSb[node] = own stress                   SFb[sp] = own stress, SVb[sp] = {vx, vy, m/rho, -}
 // Sweep A maps A -> B, sweep B (with the fused RK4 stage epilogue and next-stage predictor) maps B -> A; a
 // kernel only gathers from the format it does not write, so there are no read/write races.
-// List entries are streamed with ld.global.cs (read once per sweep), four entries in flight per thread.
+// List rows are streamed through shared memory with cp.async (ell_stream), four entries in flight per thread.
 #pragma once
 #include "grid_kernels.cuh"
 
@@ -24,9 +27,6 @@ namespace spsph {
 
 struct __align__(32) Rec4 {
   double a, b, c, d;
-};
-struct __align__(32) Rec8 {
-  double s1, s2, s3, s4, mor, epsp, p0, p1;
 };
 
 struct StatePtrs {
@@ -36,19 +36,20 @@ struct StatePtrs {
   const float *wallpos, *horiz;
   const int *bc_or_not, *bc_info;
   // format A
-  Rec4 *NA;     // [nnode]
-  Rec8 *SA;     // [nstress]
+  double *NA;   // (2, nnode) velocity
+  Rec4 *SA;     // [nstress] stress
   double *NSa;  // (4, nnode)
   double *SVa;  // (2, nstress)
   // format B (== state between steps)
-  Rec4 *NB;     // [nnode]
-  Rec4 *SB;     // [nstress]
+  Rec4 *NB;     // [nnode] {vx, vy, m, rho}
+  Rec4 *SB;     // [nstress] {s1/rho^2, s2/rho^2, s3/rho^2, m}
   double *NSb;  // (4, nnode)
   double *SFb;  // (4, nstress)
-  double *SVb;  // (2, nstress)
+  Rec4 *SVb;    // [nstress] {vx, vy, m/rho, -}
+  double *av;   // (2, nnode) artificial viscosity acceleration of the current stage (k_artvisc -> k_sweep_b_node)
   // read side of a format-B -> format-B sweep (the SPH_shift interpolation): the other B buffer set
-  const Rec4 *NBr;
-  const double *NSbr, *SFbr, *SVbr;
+  const Rec4 *NBr, *SVbr;
+  const double *NSbr, *SFbr;
   double *epsp;     // (ntotal) Internal_Vars(1,:)
   double *fdp;      // (ntotal) f_drucker
   double *norm;     // (ntotal) cspm_norm of stress_point_update (frozen within a step)
@@ -87,18 +88,28 @@ constexpr int UNR = 4;  // list entries in flight per thread
 // warp owns a private ring of ELL_NG groups per array; HBM latency is hidden by the ring depth, independent
 // of register count, and the neighbour gathers for group g+1 are issued before group g is consumed.
 // ------------------------------------------------------------------------------------------------------
-#ifndef SPSPH_PREFETCH
-#define SPSPH_PREFETCH 0  // 1: gathers of group g+1 are issued before group g is consumed (register double buffer)
-#endif
 #ifndef SPSPH_MINB
 #define SPSPH_MINB 4      // min resident blocks per SM requested from ptxas for the sweep kernels
 #endif
 constexpr int ELL_GROUP = 4;  // rows per cp.async group
 constexpr int ELL_NG = 4;     // groups in the ring (16 rows = 2 KB per array per warp in flight)
 
-__device__ __forceinline__ void cp_async16(void *smem, const void *gmem) {
+// The list rows are read exactly once per sweep: L2 evict-first, so that the 0.7-1.3 GB streamed per sweep do
+// not push the gathered particle records (43-171 MB, re-read ~20-40 times each) out of the 126 MB L2.
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+  unsigned long long p;
+  asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(p));
+  return p;
+}
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem, unsigned long long pol) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
-  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+  asm volatile("cp.async.cg.shared.global.L2::cache_hint [%0], [%1], 16, %2;\n" ::"r"(sa), "l"(gmem), "l"(pol)
+               : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N>
@@ -106,78 +117,46 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
-// NARR arrays are streamed (array 0 holds the partner ids). `rows` is the slice width (warp-uniform), `cnt` the
-// calling lane's own list length. gather(q) -> R fetches the partner record (q < 0: past the end);
-// compute(q[4], a1[4], a2[4], rec[4], nvalid) consumes one group of entries in list order (a1/a2: raw 32-bit
-// payloads of arrays 1 and 2; entries u >= nvalid are past the end of this lane's list and must be ignored).
-template <int NARR, class R, class GatherF, class ComputeF>
+// NARR arrays of 4-byte entries are streamed (array 0 holds the partner ids). `rows` is the slice width
+// (warp-uniform), `cnt` the calling lane's own list length. gather(q) -> R fetches the partner record (q < 0:
+// past the end); compute(q[4], pay[NARR-1][4], rec[4], nvalid) consumes one group of entries in list order
+// (pay: raw 32-bit payloads of arrays 1..NARR-1; entries u >= nvalid are past the end of this lane's list).
+template <int NARR, int NG, class R, class GatherF, class ComputeF>
 __device__ __forceinline__ void ell_stream(const int *const *arr, size_t slice_off, int rows, int cnt, int *smw,
                                            GatherF gather, ComputeF compute) {
   const int lane = threadIdx.x & 31;
   const int ng = (rows + ELL_GROUP - 1) / ELL_GROUP;
   if (ng == 0) return;
+  const unsigned long long pol = l2_policy_evict_first();
   auto issue = [&](int g) {
     if (g < ng) {
 #pragma unroll
       for (int a = 0; a < NARR; ++a)
-        cp_async16(smw + ((g % ELL_NG) * NARR + a) * (ELL_GROUP * 32) + lane * 4,
-                   arr[a] + slice_off + (size_t)g * (ELL_GROUP * 32) + lane * 4);
+        cp_async16(smw + ((g % NG) * NARR + a) * (ELL_GROUP * 32) + lane * 4,
+                   arr[a] + slice_off + (size_t)g * (ELL_GROUP * 32) + lane * 4, pol);
     }
     cp_async_commit();
   };
 #pragma unroll
-  for (int g = 0; g < ELL_NG; ++g) issue(g);
-  cp_async_wait<ELL_NG - 1>();
-  __syncwarp();
-  R cur[ELL_GROUP];
-#if SPSPH_PREFETCH
-#pragma unroll
-  for (int u = 0; u < ELL_GROUP; ++u) {
-    const int q = smw[u * 32 + lane];
-    cur[u] = gather(u < cnt ? q : -1);
-  }
-#endif
+  for (int g = 0; g < NG; ++g) issue(g);
   for (int g = 0; g < ng; ++g) {
-#if SPSPH_PREFETCH
-    R nxt[ELL_GROUP];
-    if (g + 1 < ng) {
-      cp_async_wait<ELL_NG - 2>();
-      __syncwarp();
-      const int *sn = smw + (((g + 1) % ELL_NG) * NARR) * (ELL_GROUP * 32);
-#pragma unroll
-      for (int u = 0; u < ELL_GROUP; ++u) {
-        const int q = sn[u * 32 + lane];
-        nxt[u] = gather(((g + 1) * ELL_GROUP + u) < cnt ? q : -1);
-      }
-    }
-    const int *sl = smw + ((g % ELL_NG) * NARR) * (ELL_GROUP * 32);
-#else
-    if (g > 0) {
-      cp_async_wait<ELL_NG - 1>();
-      __syncwarp();
-    }
-    const int *sl = smw + ((g % ELL_NG) * NARR) * (ELL_GROUP * 32);
-#pragma unroll
-    for (int u = 0; u < ELL_GROUP; ++u) {
-      const int qq = sl[u * 32 + lane];
-      cur[u] = gather((g * ELL_GROUP + u) < cnt ? qq : -1);
-    }
-#endif
-    int q[ELL_GROUP], a1[ELL_GROUP], a2[ELL_GROUP];
+    cp_async_wait<NG - 1>();
+    __syncwarp();
+    const int *sl = smw + ((g % NG) * NARR) * (ELL_GROUP * 32);
+    int q[ELL_GROUP], pay[NARR > 1 ? NARR - 1 : 1][ELL_GROUP];
+    R cur[ELL_GROUP];
 #pragma unroll
     for (int u = 0; u < ELL_GROUP; ++u) {
       q[u] = sl[u * 32 + lane];
-      a1[u] = NARR > 1 ? sl[(ELL_GROUP * 32) + u * 32 + lane] : 0;
-      a2[u] = NARR > 2 ? sl[2 * (ELL_GROUP * 32) + u * 32 + lane] : 0;
+      cur[u] = gather((g * ELL_GROUP + u) < cnt ? q[u] : -1);
     }
-    const int nvalid = cnt - g * ELL_GROUP;  // may be <= 0 or > ELL_GROUP
-    compute(q, a1, a2, cur, nvalid);
-    __syncwarp();
-    issue(g + ELL_NG);
-#if SPSPH_PREFETCH
 #pragma unroll
-    for (int u = 0; u < ELL_GROUP; ++u) cur[u] = nxt[u];
-#endif
+    for (int a = 1; a < NARR; ++a)
+#pragma unroll
+      for (int u = 0; u < ELL_GROUP; ++u) pay[a - 1][u] = sl[a * (ELL_GROUP * 32) + u * 32 + lane];
+    compute(q, pay, cur, cnt - g * ELL_GROUP);
+    __syncwarp();
+    issue(g + NG);
   }
   cp_async_wait<0>();
 }
@@ -185,7 +164,7 @@ __device__ __forceinline__ int warp_max_i(int v) {
   for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
 }
-#define ELL_SMEM(NARR) (ELL_NG * (NARR) * ELL_GROUP * 32)  // ints per warp
+#define ELL_SMEM(NARR, NG) ((NG) * (NARR) * ELL_GROUP * 32)  // ints per warp
 
 // state format conversions at the boundary of the time loop ---------------------------------------------
 // pack: reference-layout vel/stress (upload) -> format B
@@ -204,7 +183,7 @@ __global__ void k_pack_state(DevParams P, const double *__restrict__ vel, const 
     const double r2 = r * r;
     strec(st.SB, ks, s.s1 / r2, s.s2 / r2, s.s3 / r2, st.mass[id]);
     st4(st.SFb, ks, s);
-    st2(st.SVb, ks, v);
+    strec(st.SVb, ks, v.x, v.y, st.mor[id], 0.0);
   }
 }
 // unpack: format B -> reference-layout vel (2,ntotal) and stress (4,ntotal) for download
@@ -217,7 +196,8 @@ __global__ void k_unpack_state(DevParams P, StatePtrs st, double *__restrict__ v
     st4(stress, id, ld4(st.NSb, id));
   } else {
     const int ks = id - P.nnode;
-    st2(vel, id, ld2(st.SVb, ks));
+    const Rec4 r = ldrec(st.SVb, ks);
+    st2(vel, id, make_double2(r.a, r.b));
     st4(stress, id, ld4(st.SFb, ks));
   }
 }
@@ -244,11 +224,12 @@ __global__ void k_rk_begin(DevParams P, StatePtrs st, const int *__restrict__ lf
     sn = Stress4{0.0, 0.0, 0.0, 0.0};
     if (P.adapt) adapt_stress(P, sn);
     apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
-    strec(st.NA, id, vn.x, vn.y, st.mor[id], 0.0);
+    st2(st.NA, id, vn);
     st4(st.NSa, id, sn);
   } else {
     const int ks = id - P.nnode;
-    const double2 v = ld2(st.SVb, ks);
+    const Rec4 r = ldrec(st.SVb, ks);
+    const double2 v = make_double2(r.a, r.b);
     const Stress4 s = ld4(st.SFb, ks);
     st2(st.vx0, id, v);
     st4(st.stress0, ks, s);
@@ -261,19 +242,19 @@ __global__ void k_rk_begin(DevParams P, StatePtrs st, const int *__restrict__ lf
     sn.s4 = s.s4 + 0. * (P.dt) * 0.0;
     if (P.adapt) adapt_stress(P, sn);
     apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
-    Rec8 *o = st.SA + ks;
-    reinterpret_cast<double2 *>(o)[0] = make_double2(sn.s1, sn.s2);
-    reinterpret_cast<double2 *>(o)[1] = make_double2(sn.s3, sn.s4);
-    reinterpret_cast<double2 *>(o)[2] = make_double2(st.mor[id], st.epsp[id]);
+    strec(st.SA, ks, sn.s1, sn.s2, sn.s3, sn.s4);
     st2(st.SVa, ks, vn);
   }
 }
+
+__device__ __forceinline__ double h0_of(int lo, int hi) { return __hiloint2double(hi, lo); }
 
 // ------------------------------------------------------------------------------------------------------
 // Sweep A (stress_point_update + the adapt_stress2 / BCs that follow it).
 //   FROMB = false: input in format A (inside RK4 and the final interpolation of the step)
 //   FROMB = true : input in format B (the SPH_shift interpolation at the start of a step, main:99-109)
-//   FIRST: first sweep A of the step -> computes and stores cspm_norm
+//   FIRST: first sweep A of the step -> computes and stores cspm_norm (needs w and the partner's m, rho)
+// Streams {partner id, (m/rho)_partner*w [, w]} and gathers ONE 16-byte (node velocity) or 32-byte (stress) record.
 // ------------------------------------------------------------------------------------------------------
 template <bool FIRST, bool FROMB>
 __global__ void __launch_bounds__(128, SPSPH_MINB)
@@ -291,38 +272,43 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   double2 v;
   Stress4 s;
   if (FROMB) {
-    v = ld2(st.SVbr, ks);
+    const Rec4 r = ldrec(st.SVbr, ks);
+    v = make_double2(r.a, r.b);
     s = ld4(st.SFbr, ks);
   } else {
     v = ld2(st.SVa, ks);
-    const Rec8 *o = st.SA + ks;
-    const double2 a = reinterpret_cast<const double2 *>(o)[0], b = reinterpret_cast<const double2 *>(o)[1];
-    s = Stress4{a.x, a.y, b.x, b.y};
+    const Rec4 r = ldrec(st.SA, ks);
+    s = Stress4{r.a, r.b, r.c, r.d};
   }
   double vtx = 0.0, vty = 0.0, nrm = 0.0;
   {
-    __shared__ __align__(16) int smem[4 * ELL_SMEM(2)];
-    const int *arrs[2] = {L.idx0, reinterpret_cast<const int *>(L.w0)};
-    const Rec4 *__restrict__ NR = FROMB ? st.NBr : (const Rec4 *)st.NA;
-    ell_stream<2, Rec4>(
-        arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(2),
-        [&](int q) { return ldrec(NR, (q < 0 || q >= P.nnode) ? 0 : q); },
-        [&](const int(&q)[ELL_GROUP], const int(&a1)[ELL_GROUP], const int(&)[ELL_GROUP], const Rec4(&r)[ELL_GROUP],
-            int nvalid) {
+    constexpr int NARR = FIRST ? 4 : 3;
+    __shared__ __align__(16) int smem[4 * ELL_SMEM(NARR, ELL_NG)];
+    const int *arrs[4] = {L.idx0, L.h0lo, L.h0hi, reinterpret_cast<const int *>(L.w0)};
+    const double *__restrict__ NAv = st.NA;
+    const Rec4 *__restrict__ NBv = st.NBr;
+    ell_stream<NARR, ELL_NG, double2>(
+        arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(NARR, ELL_NG),
+        [&](int q) {
+          const int qq = (q < 0 || q >= P.nnode) ? 0 : q;
+          if (FROMB) {
+            const Rec4 r = ldrec(NBv, qq);
+            return make_double2(r.a, r.b);
+          }
+          return ld2(NAv, qq);
+        },
+        [&](const int(&q)[ELL_GROUP], const int(&pay)[NARR - 1][ELL_GROUP], const double2(&r)[ELL_GROUP], int nvalid) {
 #pragma unroll
           for (int u = 0; u < ELL_GROUP; ++u) {
             const bool ok = (u < nvalid) && (q[u] < P.nnode);  // dummy partners (type 9) take no part
-            const double wd = (double)__int_as_float(a1[u]);
-            const double mor = FROMB ? (r[u].c / r[u].d) : r[u].c;  // mass/rho
-            const double h2 = mor * wd;
-            const double tx = vtx + r[u].a * h2, ty = vty + r[u].b * h2;
+            const double h2 = h0_of(pay[0][u], pay[1][u]);     // (mass(i)/rho(i))*w, main:431
+            const double tx = vtx + r[u].x * h2, ty = vty + r[u].y * h2;
             vtx = ok ? tx : vtx;
             vty = ok ? ty : vty;
             if (FIRST) {
               if (ok) {
-                const double mq = FROMB ? r[u].c : st.mass[q[u]];
-                const double rq = FROMB ? r[u].d : st.rho[q[u]];
-                nrm = nrm + (wd * mq) / rq;
+                const double wd = (double)__int_as_float(pay[NARR - 2][u]);
+                nrm = nrm + (wd * st.mass[q[u]]) / st.rho[q[u]];
               }
             }
           }
@@ -339,7 +325,7 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   }
   if (do_adapt) adapt_stress(P, s);
   if (do_bc) apply_bcs(P, st.bc_or_not, st.bc_info, id, v, s);
-  st2(st.SVb, ks, v);
+  strec(st.SVb, ks, v.x, v.y, st.mor[id], 0.0);
   st4(st.SFb, ks, s);
   const double rr = st.rho[id];
   const double r2 = rr * rr;
@@ -365,46 +351,34 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
     v = make_double2(r.a, r.b);
     s = ld4(st.NSbr, id);
   } else {
-    const Rec4 r = ldrec(st.NA, id);
-    v = make_double2(r.a, r.b);
+    v = ld2(st.NA, id);
     s = ld4(st.NSa, id);
   }
   double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, te = 0.0, nrm = 0.0;
   {
     struct RecS {
-      Stress4 s;
-      double mor, ep;
+      Rec4 s;
+      double ep;
     };
-    __shared__ __align__(16) int smem[4 * ELL_SMEM(2)];
-    const int *arrs[2] = {L.idx0, reinterpret_cast<const int *>(L.w0)};
-    ell_stream<2, RecS>(
-        arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(2),
+    constexpr int NARR = FIRST ? 4 : 3;
+    __shared__ __align__(16) int smem[4 * ELL_SMEM(NARR, ELL_NG)];
+    const int *arrs[4] = {L.idx0, L.h0lo, L.h0hi, reinterpret_cast<const int *>(L.w0)};
+    ell_stream<NARR, ELL_NG, RecS>(
+        arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(NARR, ELL_NG),
         [&](int q) {
           const int qs = (q < 0 || q >= P.ntotal) ? 0 : q - P.nnode;
           RecS r;
-          if (FROMB) {
-            r.s = ld4(st.SFbr, qs);
-            r.mor = st.mor[qs + P.nnode];
-            r.ep = EPSP ? st.epsp[qs + P.nnode] : 0.0;
-          } else {
-            const Rec8 *o = st.SA + qs;
-            const Rec4 a = ld256(o);
-            const double2 c = reinterpret_cast<const double2 *>(o)[2];
-            r.s = Stress4{a.a, a.b, a.c, a.d};
-            r.mor = c.x;
-            r.ep = c.y;
-          }
+          r.s = FROMB ? ld256(st.SFbr + 4 * (size_t)qs) : ldrec(st.SA, qs);
+          r.ep = EPSP ? st.epsp[qs + P.nnode] : 0.0;
           return r;
         },
-        [&](const int(&q)[ELL_GROUP], const int(&a1)[ELL_GROUP], const int(&)[ELL_GROUP], const RecS(&r)[ELL_GROUP],
-            int nvalid) {
+        [&](const int(&q)[ELL_GROUP], const int(&pay)[NARR - 1][ELL_GROUP], const RecS(&r)[ELL_GROUP], int nvalid) {
 #pragma unroll
           for (int u = 0; u < ELL_GROUP; ++u) {
             const bool ok = (u < nvalid) && (q[u] < P.ntotal);  // dummy partners (type 6) take no part
-            const double wd = (double)__int_as_float(a1[u]);
-            const double h1 = r[u].mor * wd;
-            const double n1 = t1 + r[u].s.s1 * h1, n2 = t2 + r[u].s.s2 * h1, n3 = t3 + r[u].s.s3 * h1,
-                         n4 = t4 + r[u].s.s4 * h1;
+            const double h1 = h0_of(pay[0][u], pay[1][u]);      // (mass(j)/rho(j))*w, main:430
+            const double n1 = t1 + r[u].s.a * h1, n2 = t2 + r[u].s.b * h1, n3 = t3 + r[u].s.c * h1,
+                         n4 = t4 + r[u].s.d * h1;
             t1 = ok ? n1 : t1;
             t2 = ok ? n2 : t2;
             t3 = ok ? n3 : t3;
@@ -414,7 +388,10 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
               te = ok ? ne : te;
             }
             if (FIRST) {
-              if (ok) nrm = nrm + (wd * st.mass[q[u]]) / st.rho[q[u]];
+              if (ok) {
+                const double wd = (double)__int_as_float(pay[NARR - 2][u]);
+                nrm = nrm + (wd * st.mass[q[u]]) / st.rho[q[u]];
+              }
             }
           }
         });
@@ -441,8 +418,8 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
 }
 
 // ------------------------------------------------------------------------------------------------------
-// Sweep B (get_derivatives + plastic_terms + gravity/damping + artificial viscosity + Jaumann terms + RK4
-// stage accumulation + next-stage predictor, or the final RK4 update when `last`): format B -> format A.
+// Sweep B (get_derivatives + plastic_terms + gravity/damping + Jaumann terms + RK4 stage accumulation +
+// next-stage predictor, or the final RK4 update when `last`): format B -> format A.
 // ------------------------------------------------------------------------------------------------------
 template <bool FIRST>
 __global__ void __launch_bounds__(128, SPSPH_MINB)
@@ -457,7 +434,8 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   const int ks = id - P.nnode;
   const int cnt = live ? n0[t] : 0;
   const int wrows = warp_max_i(cnt);
-  const double2 vp = ld2(st.SVb, ks);
+  const Rec4 selfv = ldrec(st.SVb, ks);
+  const double2 vp = make_double2(selfv.a, selfv.b);
   const Stress4 sp_ = ld4(st.SFb, ks);
   double2 xp = make_double2(0.0, 0.0);
   if ((FIRST && P.cspm) || P.ndummy > 0) xp = ld2(st.x, id);
@@ -505,27 +483,26 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
       }
     };
   {
-    __shared__ __align__(16) int smem[4 * ELL_SMEM(3)];
+    __shared__ __align__(16) int smem[4 * ELL_SMEM(3, ELL_NG)];
     const int *arrs[3] = {L.idx0, reinterpret_cast<const int *>(L.gx0), reinterpret_cast<const int *>(L.gy0)};
-    ell_stream<3, Rec4>(
-        arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(3),
+    ell_stream<3, ELL_NG, Rec4>(
+        arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(3, ELL_NG),
         [&](int q) { return ldrec(st.NB, (q < 0 || q >= P.nnode) ? 0 : q); },
-        [&](const int(&q)[ELL_GROUP], const int(&a1)[ELL_GROUP], const int(&a2)[ELL_GROUP], const Rec4(&r)[ELL_GROUP],
-            int nvalid) {
+        [&](const int(&q)[ELL_GROUP], const int(&pay)[2][ELL_GROUP], const Rec4(&r)[ELL_GROUP], int nvalid) {
           bool special = false;  // wall partner in this group (type 9), or the once-per-step CSPM matrix pass
 #pragma unroll
           for (int u = 0; u < ELL_GROUP; ++u) special |= (u < nvalid) && (q[u] >= P.nnode);
           if ((FIRST && P.cspm) || __any_sync(0xffffffffu, special)) {
 #pragma unroll
             for (int u = 0; u < ELL_GROUP; ++u)
-              if (u < nvalid) entry_slow(q[u], a1[u], a2[u], r[u]);
+              if (u < nvalid) entry_slow(q[u], pay[0][u], pay[1][u], r[u]);
             return;
           }
           // branch-free path: the four entries' division chains are independent and interleave
           double h1[ELL_GROUP], h2[ELL_GROUP];
 #pragma unroll
           for (int u = 0; u < ELL_GROUP; ++u) {
-            const double gx = (double)__int_as_float(a1[u]), gy = (double)__int_as_float(a2[u]);
+            const double gx = (double)__int_as_float(pay[0][u]), gy = (double)__int_as_float(pay[1][u]);
             const double rr = __drcp_rn(r[u].d);
             h1[u] = div_rn(gx * r[u].c, r[u].d, rr);  // dwdx*mass(i)/rho(i), main:514
             h2[u] = div_rn(gy * r[u].c, r[u].d, rr);
@@ -623,7 +600,6 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   rk.s4 = rk.s4 + f2 * r4;
   const Stress4 s0 = ld4(st.stress0, ks);
   Stress4 sn;
-  double ep = st.epsp[id];
   if (!last) {
     st4(st.RKs, ks, rk);
     st.RKe[ks] = rke;
@@ -637,23 +613,72 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
     sn.s3 = s0.s3 + (P.dt / 6) * rk.s3;
     sn.s4 = s0.s4 + (P.dt / 6) * rk.s4;
     // update_strain, mat:1864-1880 with Ddev_strn = RK_dev_strain/6 (main:799)
-    ep = ep + P.dt * (rke / 6);
-    st.epsp[id] = ep;
+    st.epsp[id] = st.epsp[id] + P.dt * (rke / 6);
   }
   if (P.adapt) adapt_stress(P, sn);
   double2 vn = vp;
   apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
-  Rec8 *o = st.SA + ks;
-  reinterpret_cast<double2 *>(o)[0] = make_double2(sn.s1, sn.s2);
-  reinterpret_cast<double2 *>(o)[1] = make_double2(sn.s3, sn.s4);
-  reinterpret_cast<double2 *>(o)[2] = make_double2(st.mor[id], ep);
+  strec(st.SA, ks, sn.s1, sn.s2, sn.s3, sn.s4);
   st2(st.SVa, ks, vn);
+}
+
+
+// artificial_viscosity, main:826-904 (fp32 locals and accumulators, list order): one thread per node over its
+// node-node list; xij, yij, h were rounded to fp32 when the list was built, so ONE 32-byte gather per entry.
+__global__ void __launch_bounds__(128, SPSPH_MINB)
+k_artvisc(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n1, StatePtrs st) {
+  const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((k0 & ~31) >= M.nn) return;  // whole warp past the end
+  const bool live = k0 < M.nn;
+  const int k = live ? k0 : 0;
+  const int t = k0;
+  const int id = order_n[k];
+  const int cntc = live ? n1[t] : 0;
+  const int wrowsC = warp_max_i(cntc);
+  const Rec4 self = ldrec(st.NB, id);  // {vx, vy, m, rho}
+  const double2 vp = make_double2(self.a, self.b);
+  const double rp = self.d;
+  float acc1 = 0.f, acc2 = 0.f;
+  constexpr int NG = 3;
+  __shared__ __align__(16) int smem[4 * ELL_SMEM(6, NG)];
+  const int *arrs[6] = {L.idxC, reinterpret_cast<const int *>(L.gxC), reinterpret_cast<const int *>(L.gyC),
+                        reinterpret_cast<const int *>(L.xC), reinterpret_cast<const int *>(L.yC),
+                        reinterpret_cast<const int *>(L.hC)};
+  ell_stream<6, NG, Rec4>(
+      arrs, (size_t)L.offC[t / SLICE], wrowsC, cntc, smem + (threadIdx.x >> 5) * ELL_SMEM(6, NG),
+      [&](int q) { return ldrec(st.NB, q < 0 ? 0 : q); },
+      [&](const int(&)[ELL_GROUP], const int(&pay)[5][ELL_GROUP], const Rec4(&r)[ELL_GROUP], int nvalid) {
+        float visc[ELL_GROUP];
+#pragma unroll
+        for (int u = 0; u < ELL_GROUP; ++u) {  // independent per entry: interleaves
+          const float xij = __int_as_float(pay[2][u]), yij = __int_as_float(pay[3][u]), h = __int_as_float(pay[4][u]);
+          const float rho2 = (float)(0.5 * (rp + r[u].d));
+          const float cs = 600.f;
+          float div_u = (float)((double)xij * (vp.x - r[u].a));
+          div_u = (float)((double)div_u + (double)yij * (vp.y - r[u].b));
+          const float sq = sqrtf(xij * xij + yij * yij);
+          const float theta = (h * div_u) / (sq * sq + 0.01f * (h * h));
+          visc[u] = 0.f;
+          if (div_u < 0)
+            visc[u] = (float)((-P.alpha * (double)cs * (double)theta + P.beta * (double)(theta * theta)) / (double)rho2);
+        }
+#pragma unroll
+        for (int u = 0; u < ELL_GROUP; ++u) {  // ordered fp32 accumulation
+          const float gxf = __int_as_float(pay[0][u]), gyf = __int_as_float(pay[1][u]);
+          const float a1 = (float)((double)acc1 + (double)(visc[u] * gxf) * r[u].c);
+          const float a2 = (float)((double)acc2 + (double)(visc[u] * gyf) * r[u].c);
+          acc1 = (u < nvalid) ? a1 : acc1;
+          acc2 = (u < nvalid) ? a2 : acc2;
+        }
+      });
+  if (!live) return;
+  st2(st.av, id, make_double2((double)(-acc1), (double)(-acc2)));  // art_visc = -art_visc_temp, main:901
 }
 
 template <bool FIRST>
 __global__ void __launch_bounds__(128, SPSPH_MINB)
 k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n0,
-               const int *__restrict__ n1, StatePtrs st, double f1next, double f2, int last) {
+               StatePtrs st, double f1next, double f2, int last) {
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
   if ((k0 & ~31) >= M.nn) return;  // whole warp past the end
   const bool live = k0 < M.nn;
@@ -669,11 +694,10 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
   const Stress4 sp_ = ld4(st.NSb, id);
   const double r2p = rp * rp;
   const double so1 = sp_.s1 / r2p, so2 = sp_.s2 / r2p, so3 = sp_.s3 / r2p;  // stress(1:3,i)/rho(i)**2
-  const double2 xp = ld2(st.x, id);
+  double2 xp = make_double2(0.0, 0.0);
+  if (FIRST && P.cspm) xp = ld2(st.x, id);
   double ae1 = 0.0, ae2 = 0.0, ae3 = 0.0, ae4 = 0.0, ae5 = 1.0;
   double a11 = 0.0, a12 = 0.0, a21 = 0.0, a22 = 0.0, a31 = 0.0, a32 = 0.0;  // grad2_tmp(s,k)
-  __shared__ __align__(16) int smem[4 * ELL_SMEM(3)];
-  int *smw = smem + (threadIdx.x >> 5) * ELL_SMEM(3);
     auto entry_slow = [&](int q, int a1, int a2, const Rec4 &r) {
       const double gx = (double)__int_as_float(a1), gy = (double)__int_as_float(a2);
       double q1, q2, q3, mq;
@@ -708,25 +732,25 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
       a32 = a32 - mq * (gy * c3);
     };
   {
+    __shared__ __align__(16) int smem[4 * ELL_SMEM(3, ELL_NG)];
     const int *arrs[3] = {L.idx0, reinterpret_cast<const int *>(L.gx0), reinterpret_cast<const int *>(L.gy0)};
-    ell_stream<3, Rec4>(
-        arrs, (size_t)L.off0[sl], wrows, cnt, smw,
+    ell_stream<3, ELL_NG, Rec4>(
+        arrs, (size_t)L.off0[sl], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(3, ELL_NG),
         [&](int q) { return ldrec(st.SB, (q < 0 || q >= P.ntotal) ? 0 : q - P.nnode); },
-        [&](const int(&q)[ELL_GROUP], const int(&a1)[ELL_GROUP], const int(&a2)[ELL_GROUP], const Rec4(&r)[ELL_GROUP],
-            int nvalid) {
+        [&](const int(&q)[ELL_GROUP], const int(&pay)[2][ELL_GROUP], const Rec4(&r)[ELL_GROUP], int nvalid) {
           bool special = false;  // wall partner in this group (type 6), or the once-per-step CSPM matrix pass
 #pragma unroll
           for (int u = 0; u < ELL_GROUP; ++u) special |= (u < nvalid) && (q[u] >= P.ntotal);
           if ((FIRST && P.cspm) || __any_sync(0xffffffffu, special)) {
 #pragma unroll
             for (int u = 0; u < ELL_GROUP; ++u)
-              if (u < nvalid) entry_slow(q[u], a1[u], a2[u], r[u]);
+              if (u < nvalid) entry_slow(q[u], pay[0][u], pay[1][u], r[u]);
             return;
           }
 #pragma unroll
           for (int u = 0; u < ELL_GROUP; ++u) {
             const bool ok = u < nvalid;
-            const double gx = (double)__int_as_float(a1[u]), gy = (double)__int_as_float(a2[u]);
+            const double gx = (double)__int_as_float(pay[0][u]), gy = (double)__int_as_float(pay[1][u]);
             const double c1 = so1 + r[u].a, c2 = so2 + r[u].b, c3 = so3 + r[u].c, mq = r[u].d;
             const double n11 = a11 - mq * (gx * c1), n12 = a12 - mq * (gy * c1);
             const double n21 = a21 - mq * (gx * c2), n22 = a22 - mq * (gy * c2);
@@ -740,6 +764,7 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
           }
         });
   }
+  if (!live) return;
   if (P.cspm) {
     double *AEp = st.AE + 5 * (size_t)id;
     if (FIRST) {
@@ -776,58 +801,13 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
   // gravity_force, mat:2809-2871
   const double sg1 = P.grav[0] - P.damping * vp.x;
   const double sg2 = P.grav[1] - P.damping * vp.y;
-  // artificial_viscosity, main:826-904 (fp32 locals and accumulators, list order)
+  // artificial viscosity of this stage (k_artvisc), zero when alpha = beta = 0 (art_visc stays 0, main:688)
   double av1 = 0.0, av2 = 0.0;
   if (P.alpha > 0 || P.beta > 0) {
-    const int cntc = live ? n1[t] : 0;
-    const int wrowsC = warp_max_i(cntc);
-    const double hp = st.hsml[id];
-    float acc1 = 0.f, acc2 = 0.f;
-    struct RecV {
-      Rec4 n;
-      double2 x;
-      double h;
-    };
-    const int *arrs[3] = {L.idxC, reinterpret_cast<const int *>(L.gxC), reinterpret_cast<const int *>(L.gyC)};
-    __syncwarp();
-    ell_stream<3, RecV>(
-        arrs, (size_t)L.offC[sl], wrowsC, cntc, smw,
-        [&](int q) {
-          const int qq = q < 0 ? 0 : q;
-          RecV r;
-          r.n = ldrec(st.NB, qq);
-          r.x = ld2(st.x, qq);
-          r.h = st.hsml[qq];
-          return r;
-        },
-        [&](const int(&)[ELL_GROUP], const int(&a1v)[ELL_GROUP], const int(&a2v)[ELL_GROUP], const RecV(&rv)[ELL_GROUP],
-            int nvalid) {
-#pragma unroll
-          for (int u = 0; u < ELL_GROUP; ++u) {
-            if (u >= nvalid) continue;
-            const int a1 = a1v[u], a2 = a2v[u];
-            const RecV &r = rv[u];
-            const float gxf = __int_as_float(a1), gyf = __int_as_float(a2);
-            const float xij = (float)(xp.x - r.x.x);
-            const float yij = (float)(xp.y - r.x.y);
-            const float h = (float)(0.5 * (hp + r.h));
-            const float rho2 = (float)(0.5 * (rp + r.n.d));
-            const float cs = 600.f;
-            float div_u = (float)((double)xij * (vp.x - r.n.a));
-            div_u = (float)((double)div_u + (double)yij * (vp.y - r.n.b));
-            const float sq = sqrtf(xij * xij + yij * yij);
-            const float theta = (h * div_u) / (sq * sq + 0.01f * (h * h));
-            float visc = 0.f;
-            if (div_u < 0)
-              visc = (float)((-P.alpha * (double)cs * (double)theta + P.beta * (double)(theta * theta)) / (double)rho2);
-            acc1 = (float)((double)acc1 + (double)(visc * gxf) * r.n.c);
-            acc2 = (float)((double)acc2 + (double)(visc * gyf) * r.n.c);
-          }
-        });
-    av1 = (double)(-acc1);
-    av2 = (double)(-acc2);
+    const double2 a = ld2(st.av, id);
+    av1 = a.x;
+    av2 = a.y;
   }
-  if (!live) return;
   const double r1 = -dv1 + sg1 + av1 + 0.0 + 0.0;  // + f_bound + art_force (both zero here, main:763-764)
   const double r2 = -dv2 + sg2 + av2 + 0.0 + 0.0;
   double2 rk = ld2(st.RKv, id);
@@ -846,93 +826,71 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
   Stress4 sn = sp_;
   if (P.adapt) adapt_stress(P, sn);
   apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
-  strec(st.NA, id, vn.x, vn.y, st.mor[id], 0.0);
+  st2(st.NA, id, vn);
   st4(st.NSa, id, sn);
 }
 
+
 // ------------------------------------------------------------------------------------------------------
 // Position update, main:140-182: XSPH_update (main:189-239) or the fp32 mid-velocity rule; displ.
-// Velocities come from format B (the state at the end of the step).
+// Velocities come from format B (the state at the end of the step); one 32-byte gather per list entry.
 // ------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(128)
 k_move(DevParams P, SlotMap M, SortArrays So, ListPtrs L, const int *__restrict__ n1, StatePtrs st,
        double *__restrict__ x, const double *__restrict__ x00, double *__restrict__ displ) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= M.nnp + M.nsp) return;
-  const bool is_node = t < M.nnp;
-  const int k = is_node ? t : t - M.nnp;
-  if (k >= (is_node ? M.nn : M.ns)) return;
+  const int t0 = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t0 >= M.nnp + M.nsp) return;
+  const bool is_node = t0 < M.nnp;  // warp-uniform (nnp is a multiple of 32)
+  const int k0 = is_node ? t0 : t0 - M.nnp;
+  const int nlive = is_node ? M.nn : M.ns;
+  if ((k0 & ~31) >= nlive) return;  // whole warp past the end
+  const bool live = k0 < nlive;
+  const int k = live ? k0 : 0;
   const int id = is_node ? So.order[0][k] : So.order[1][k];
   double2 vp;
-  if (is_node) {
-    const Rec4 r = ldrec(st.NB, id);
+  {
+    const Rec4 r = is_node ? ldrec(st.NB, id) : ldrec(st.SVb, id - P.nnode);
     vp = make_double2(r.a, r.b);
-  } else {
-    vp = ld2(st.SVb, id - P.nnode);
   }
+  double sx = 0.0, sy = 0.0;
+  if (P.update_x && P.xsph) {
+    const int cnt = live ? n1[t0] : 0;
+    const int wrows = warp_max_i(cnt);
+    const int sl = t0 / SLICE;
+    __shared__ __align__(16) int smem[4 * ELL_SMEM(2, ELL_NG)];
+    int *smw = smem + (threadIdx.x >> 5) * ELL_SMEM(2, ELL_NG);
+    auto body = [&](const int(&)[ELL_GROUP], const int(&pay)[1][ELL_GROUP], const Rec4(&r)[ELL_GROUP], int nvalid,
+                    bool node) {
+#pragma unroll
+      for (int u = 0; u < ELL_GROUP; ++u) {
+        const double wd = (double)__int_as_float(pay[0][u]);
+        const double mr = node ? (r[u].c / r[u].d) : r[u].c;  // mass(j)/rho(j)
+        const double nx = sx + mr * (r[u].a - vp.x) * wd, ny = sy + mr * (r[u].b - vp.y) * wd;
+        sx = (u < nvalid) ? nx : sx;
+        sy = (u < nvalid) ? ny : sy;
+      }
+    };
+    if (is_node) {
+      const int *arrs[2] = {L.idxC, reinterpret_cast<const int *>(L.wC)};
+      ell_stream<2, ELL_NG, Rec4>(
+          arrs, (size_t)L.offC[sl], wrows, cnt, smw, [&](int q) { return ldrec(st.NB, q < 0 ? 0 : q); },
+          [&](const int(&q)[ELL_GROUP], const int(&pay)[1][ELL_GROUP], const Rec4(&r)[ELL_GROUP], int nvalid) {
+            body(q, pay, r, nvalid, true);
+          });
+    } else {
+      const int *arrs[2] = {L.idxD, reinterpret_cast<const int *>(L.wD)};
+      ell_stream<2, ELL_NG, Rec4>(
+          arrs, (size_t)L.offD[sl], wrows, cnt, smw, [&](int q) { return ldrec(st.SVb, q < 0 ? 0 : q - P.nnode); },
+          [&](const int(&q)[ELL_GROUP], const int(&pay)[1][ELL_GROUP], const Rec4(&r)[ELL_GROUP], int nvalid) {
+            body(q, pay, r, nvalid, false);
+          });
+    }
+  }
+  if (!live) return;
   const double2 xp = ld2(x, id);
   if (P.update_x) {
     double2 xn;
     if (P.xsph) {
-      const int cnt = n1[t];
-      const int lane = t & 31, sl = t / SLICE;
-      double sx = 0.0, sy = 0.0;
-      if (is_node) {
-        const size_t oc = (size_t)L.offC[sl] + lane;
-        for (int e0 = 0; e0 < cnt; e0 += UNR) {
-          int q[UNR];
-          float w[UNR];
-          Rec4 r[UNR];
-          double mr[UNR];
-#pragma unroll
-          for (int u = 0; u < UNR; ++u) {
-            const size_t a = oc + (size_t)(e0 + u) * SLICE;
-            q[u] = ldcs_i(L.idxC + a);
-            w[u] = ldcs_f(L.wC + a);
-          }
-#pragma unroll
-          for (int u = 0; u < UNR; ++u) {
-            if (e0 + u >= cnt) q[u] = -1;
-            r[u] = ldrec(st.NB, q[u] < 0 ? 0 : q[u]);
-            mr[u] = st.mor[q[u] < 0 ? 0 : q[u]];
-          }
-#pragma unroll
-          for (int u = 0; u < UNR; ++u) {
-            if (q[u] < 0) continue;
-            const double wd = (double)w[u];
-            sx = sx + mr[u] * (r[u].a - vp.x) * wd;
-            sy = sy + mr[u] * (r[u].b - vp.y) * wd;
-          }
-        }
-      } else {
-        const size_t od = (size_t)L.offD[sl] + lane;
-        for (int e0 = 0; e0 < cnt; e0 += UNR) {
-          int q[UNR];
-          float w[UNR];
-          double2 vq[UNR];
-          double mr[UNR];
-#pragma unroll
-          for (int u = 0; u < UNR; ++u) {
-            const size_t a = od + (size_t)(e0 + u) * SLICE;
-            q[u] = ldcs_i(L.idxD + a);
-            w[u] = ldcs_f(L.wD + a);
-          }
-#pragma unroll
-          for (int u = 0; u < UNR; ++u) {
-            if (e0 + u >= cnt) q[u] = -1;
-            const int qq = q[u] < 0 ? P.nnode : q[u];
-            vq[u] = ld2(st.SVb, qq - P.nnode);
-            mr[u] = st.mor[qq];
-          }
-#pragma unroll
-          for (int u = 0; u < UNR; ++u) {
-            if (q[u] < 0) continue;
-            const double wd = (double)w[u];
-            sx = sx + mr[u] * (vq[u].x - vp.x) * wd;
-            sy = sy + mr[u] * (vq[u].y - vp.y) * wd;
-          }
-        }
-      }
       const double eps = 0.5;
       xn.x = xp.x + P.dt * (vp.x + eps * sx);
       xn.y = xp.y + P.dt * (vp.y + eps * sy);
