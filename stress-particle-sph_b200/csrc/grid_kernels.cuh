@@ -492,13 +492,17 @@ __device__ __forceinline__ RowRange row_range(int ndx, int cx, int jy) {
   return RowRange{jy * ndx + max(cx - 1, 0), jy * ndx + min(cx + 1, ndx - 1)};
 }
 
-// Count pass: per thread slot the lengths of its gather lists, its forward pair count (creation index)
-// and its total interaction count (countiac, main:1355-1356). Order-independent, so rows are scanned as
-// merged ranges.
+// Count pass: per thread slot the lengths of its gather lists, its forward pair count (creation index) and its
+// total interaction count (countiac, main:1355-1356). The accepted partners are also recorded, in list order, in
+// a fixed-capacity scratch (CAND_CAP rows per 32-particle slice) so that the fill pass does not have to search
+// again; a particle with more partners than that raises `overflow` and the step falls back to k_fill_scan.
+constexpr int CAND_CAP = 64;
+
 __global__ void __launch_bounds__(128)
 k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, int *__restrict__ n0, int *__restrict__ n1,
         int *__restrict__ nfwd_u /* unified order */, int *__restrict__ nall, int *__restrict__ w0 /* slice widths */,
-        int *__restrict__ wC, int *__restrict__ wD, const int *__restrict__ lflag) {
+        int *__restrict__ wC, int *__restrict__ wD, const int *__restrict__ lflag, int *__restrict__ cand0,
+        int *__restrict__ cand1, int *__restrict__ overflow) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   int sp = 0, k = 0;
   const bool live = (t < M.total()) && slot_decode(M, t, sp, k);
@@ -518,42 +522,63 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
       const float2 up = uposp[k];
       const int ndx = G->ndivx[0], ndy = G->ndivx[1];
       const int cy = c / ndx, cx = c - cy * ndx;
+      const size_t cb = (size_t)(t / SLICE) * CAND_CAP * SLICE + (t & 31);
+      const bool owner_of_lists = sp != SP_DUMMY;
+      auto scan = [&](int sq, int b, int e, int fthr) {
+        const float2 *__restrict__ uq = sq == 0 ? S.upos[0] : (sq == 1 ? S.upos[1] : S.upos[2]);
+        const double2 *__restrict__ pq = sq == 0 ? S.pos[0] : (sq == 1 ? S.pos[1] : S.pos[2]);
+        const double *__restrict__ hq = sq == 0 ? S.h[0] : (sq == 1 ? S.h[1] : S.h[2]);
+        for (int q = b; q < e; ++q) {
+          if (sq == sp && q == k) continue;
+          int cls = 2;
+          if (pf.on) cls = prefilter_test(pf, up, uq[q]);
+          if (cls == 0) continue;
+          if (cls == 2) {
+            double dx, dy, d2, mh;
+            if (!pair_accept_fast(sk, pp, hp, pq[q], uni ? hp : hq[q], dx, dy, d2, mh)) continue;
+          }
+          ++ca;
+          cf += (q >= fthr) ? 1 : 0;
+          if (owner_of_lists) {
+            if (sq == sp) {
+              if (c1 < CAND_CAP) cand1[cb + (size_t)c1 * SLICE] = q;
+              ++c1;
+            } else {  // node<->stress (type 1) and node/stress<->dummy (types 6, 9)
+              if (c0 < CAND_CAP) cand0[cb + (size_t)c0 * SLICE] = (sq << 30) | q;
+              ++c0;
+            }
+          }
+        }
+      };
       for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy) {
         const RowRange rr = row_range(ndx, cx, jy);
+        // forward partners (creation order): later row, or same row from a threshold index on (per species)
+        int fthr[3];
 #pragma unroll
         for (int sq = 0; sq < 3; ++sq) {
-          const int b = S.start[sq][rr.ca], e = S.start[sq][rr.cb + 1];
-          // forward partners (creation order): later row, or same row from the threshold index on
-          int fthr;
           if (jy > cy)
-            fthr = b;
+            fthr[sq] = S.start[sq][rr.ca];
           else if (jy < cy)
-            fthr = e;
+            fthr[sq] = S.start[sq][rr.cb + 1];
           else
-            fthr = (sq == sp) ? k + 1 : (sq > sp ? S.start[sq][c] : S.start[sq][c + 1]);
-          int acc = 0, accf = 0;
-          for (int q = b; q < e; ++q) {
-            if (sq == sp && q == k) continue;
-            int cls = 2;
-            if (pf.on) cls = prefilter_test(pf, up, S.upos[sq][q]);
-            if (cls == 0) continue;
-            if (cls == 2) {
-              double dx, dy, d2, mh;
-              if (!pair_accept_fast(sk, pp, hp, S.pos[sq][q], uni ? hp : S.h[sq][q], dx, dy, d2, mh)) continue;
-            }
-            ++acc;
-            accf += (q >= fthr) ? 1 : 0;
-          }
-          ca += acc;
-          cf += accf;
-          if (sp != SP_DUMMY) {
-            if (sq == sp)
-              c1 += acc;
-            else
-              c0 += acc;  // node<->stress (type 1) and node/stress<->dummy (types 6, 9)
+            fthr[sq] = (sq == sp) ? k + 1 : (sq > sp ? S.start[sq][c] : S.start[sq][c + 1]);
+        }
+        const int nd_row = S.start[2][rr.cb + 1] - S.start[2][rr.ca];
+        if (nd_row == 0) {
+          // no wall particles in this row: every list takes partners of a single species, whose order
+          // (cell id, particle index) is the order of the merged range
+          scan(0, S.start[0][rr.ca], S.start[0][rr.cb + 1], fthr[0]);
+          scan(1, S.start[1][rr.ca], S.start[1][rr.cb + 1], fthr[1]);
+        } else {
+          // wall particles interleave with the other species cell by cell: (cell id, species, index) order
+          for (int cq = rr.ca; cq <= rr.cb; ++cq) {
+            scan(0, S.start[0][cq], S.start[0][cq + 1], fthr[0]);
+            scan(1, S.start[1][cq], S.start[1][cq + 1], fthr[1]);
+            scan(2, S.start[2][cq], S.start[2][cq + 1], fthr[2]);
           }
         }
       }
+      if (c0 > CAND_CAP || c1 > CAND_CAP) *overflow = 1;
       // creation index / statistics count every pair once: at the owner of its earlier member
       const bool owned = !lflag || lflag[(sp == 0 ? S.order[0] : (sp == 1 ? S.order[1] : S.order[2]))[k]] == 1;
       nfwd_u[unified_slot(S, c, sp, k)] = owned ? cf : 0;
@@ -583,7 +608,8 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
 
 // after the scans: totals -> status block
 __global__ void k_status(const GridInfo *__restrict__ G, const long long *__restrict__ totals,
-                         const int *__restrict__ start, int cell_stride, const int *__restrict__ nout, StepStatus *st) {
+                         const int *__restrict__ start, int cell_stride, const int *__restrict__ nout,
+                         const int *__restrict__ cand_overflow, StepStatus *st) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   st->tot0 = totals[0];
   st->totC = totals[1];
@@ -592,6 +618,7 @@ __global__ void k_status(const GridInfo *__restrict__ G, const long long *__rest
   st->ncell = G->ncell;
   st->overflow = G->overflow;
   st->err = 0;
+  st->pad[0] = *cand_overflow;
   for (int sp = 0; sp < 3; ++sp) st->nloc[sp] = start[sp * cell_stride + G->ncell] + nout[sp];
 }
 
@@ -683,7 +710,7 @@ constexpr int QCAP = 40;
 constexpr int FILL_THREADS = 128;
 
 __global__ void __launch_bounds__(FILL_THREADS)
-k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ n0,
+k_fill_scan(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ n0,
        const int *__restrict__ n1, const GrowthRule *__restrict__ growth, ListPtrs L, int *__restrict__ bc_int,
        float *__restrict__ n_int, const double *__restrict__ mor) {
   __shared__ int q0buf[QCAP][FILL_THREADS];  // cross-species partners (species in the top 2 bits)
@@ -860,6 +887,172 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
     }
   }
   drain();
+  if (sp == SP_NODE) bc_int[id] = has_dummy;  // main:506,579
+}
+
+// Fill pass, fast path: the accepted partners were recorded by k_count (cand0 / cand1, list order), so every
+// thread evaluates the kernel for its entries in a dense loop, four entries in flight.
+__global__ void __launch_bounds__(128)
+k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ n0,
+       const int *__restrict__ n1, const GrowthRule *__restrict__ growth, ListPtrs L, int *__restrict__ bc_int,
+       float *__restrict__ n_int, const double *__restrict__ mor, const int *__restrict__ cand0,
+       const int *__restrict__ cand1) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M.nnp + M.nsp) return;
+  int sp, k;
+  if (!slot_decode(M, t, sp, k)) return;
+  const int *__restrict__ orderp = sp == 0 ? S.order[0] : S.order[1];
+  const int *__restrict__ cellp = sp == 0 ? S.cell[0] : S.cell[1];
+  const double2 *__restrict__ posp = sp == 0 ? S.pos[0] : S.pos[1];
+  const double *__restrict__ hpp = sp == 0 ? S.h[0] : S.h[1];
+  const int id = orderp[k];
+  const int c = cellp[k];
+  const int cnt0 = n0[t], cnt1 = n1[t];
+  if (sp == SP_NODE && P.track_nint) n_int[id] = (float)cnt1;  // node-node interaction count (main:870-871 / 221-222)
+  if (c < 0) {
+    if (sp == SP_NODE) bc_int[id] = 0;
+    return;
+  }
+  const GrowthRule gr = *growth;
+  const int lane = t & 31, sl = t / SLICE;
+  const size_t o0 = (size_t)L.off0[sl] + lane;
+  const size_t o1 = (size_t)(sp == SP_NODE ? L.offC[sl] : L.offD[sl]) + lane;
+  const size_t cb = (size_t)sl * CAND_CAP * SLICE + lane;
+  const double2 pp = posp[k];
+  const double hp = hpp[k];
+  const bool uni = G->uniform_h != 0;
+  const KernelConsts K = kernel_consts(P, hp);
+  // number of "old" entries per list (prefix of the ascending order); only the split mode needs a pre-count
+  int s0 = (gr.mode == 1) ? 0 : cnt0, s1 = (gr.mode == 1) ? 0 : cnt1;
+  if (gr.mode == 2) {
+    const int up = unified_slot(S, c, sp, k);
+    if (up >= gr.ua) {
+      s0 = 0;
+      s1 = 0;
+      for (int e = 0; e < cnt0; ++e) {
+        const int pk = cand0[cb + (size_t)e * SLICE];
+        const int sq = (int)((unsigned)pk >> 30), q = pk & 0x3fffffff;
+        const int cq = (sq == 0 ? S.cell[0] : (sq == 1 ? S.cell[1] : S.cell[2]))[q];
+        s0 += pair_is_old(gr, up, unified_slot(S, cq, sq, q)) ? 1 : 0;
+      }
+      for (int e = 0; e < cnt1; ++e) {
+        const int q = cand1[cb + (size_t)e * SLICE];
+        s1 += pair_is_old(gr, up, unified_slot(S, cellp[q], sp, q)) ? 1 : 0;
+      }
+    }
+  }
+  constexpr int U = 4;
+  int has_dummy = 0;
+  // list 0: cross-species partners, reference orientation of the gradient (pair_i - pair_j after Pint_Update)
+  for (int e0 = 0; e0 < cnt0; e0 += U) {
+    int sq[U], q[U], qid[U];
+    double2 pq[U];
+    double hq[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = min(e0 + u, cnt0 - 1);
+      const int pk = cand0[cb + (size_t)e * SLICE];
+      sq[u] = (int)((unsigned)pk >> 30);
+      q[u] = pk & 0x3fffffff;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double2 *__restrict__ pqa = sq[u] == 0 ? S.pos[0] : (sq[u] == 1 ? S.pos[1] : S.pos[2]);
+      const int *__restrict__ oqa = sq[u] == 0 ? S.order[0] : (sq[u] == 1 ? S.order[1] : S.order[2]);
+      pq[u] = pqa[q[u]];
+      qid[u] = oqa[q[u]];
+      hq[u] = uni ? hp : (sq[u] == 0 ? S.h[0] : (sq[u] == 1 ? S.h[1] : S.h[2]))[q[u]];
+    }
+    double w[U], gx[U], gy[U], h0[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      double dx = pp.x - pq[u].x, dy = pp.y - pq[u].y;
+      double d2 = dx * dx;
+      d2 = d2 + dy * dy;
+      const double mh = (hp + hq[u]) / 2.;
+      const double r = sqrt(d2);
+      // Pint_Update orientation: pair_i = stress particle (type 1) or dummy (types 6, 9)
+      const bool p_is_i = (sp == SP_STRESS && sq[u] == SP_NODE);
+      if (!p_is_i) {
+        dx = -dx;
+        dy = -dy;
+      }
+      if (mh == K.h)
+        sph_kernel_fast<true>(K, r, dx, dy, w[u], gx[u], gy[u]);
+      else
+        sph_kernel(P, r, dx, dy, mh, w[u], gx[u], gy[u]);
+      h0[u] = (sq[u] == SP_DUMMY) ? 0.0 : mor[qid[u]] * (double)(float)w[u];
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u;
+      if (e >= cnt0) break;
+      const int pos = (e < s0) ? (cnt0 - s0) + e : (cnt0 - 1 - e);
+      const size_t a = o0 + (size_t)pos * SLICE;
+      L.idx0[a] = qid[u];
+      L.h0lo[a] = __double2loint(h0[u]);
+      L.h0hi[a] = __double2hiint(h0[u]);
+      L.w0[a] = (float)w[u];
+      L.gx0[a] = (float)gx[u];
+      L.gy0[a] = (float)gy[u];
+      if (sq[u] == SP_DUMMY) has_dummy = 1;
+    }
+  }
+  // list C / D: same-species partners, own-perspective gradient (nodes) or weight only (stress particles)
+  for (int e0 = 0; e0 < cnt1; e0 += U) {
+    int q[U], qid[U];
+    double2 pq[U];
+    double hq[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) q[u] = cand1[cb + (size_t)min(e0 + u, cnt1 - 1) * SLICE];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      pq[u] = posp[q[u]];
+      qid[u] = orderp[q[u]];
+      hq[u] = uni ? hp : hpp[q[u]];
+    }
+    double w[U], gx[U], gy[U], dxs[U], dys[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const double dx = pp.x - pq[u].x, dy = pp.y - pq[u].y;
+      double d2 = dx * dx;
+      d2 = d2 + dy * dy;
+      const double mh = (hp + hq[u]) / 2.;
+      const double r = sqrt(d2);
+      dxs[u] = dx;
+      dys[u] = dy;
+      if (sp == SP_NODE) {
+        if (mh == K.h)
+          sph_kernel_fast<true>(K, r, dx, dy, w[u], gx[u], gy[u]);
+        else
+          sph_kernel(P, r, dx, dy, mh, w[u], gx[u], gy[u]);
+      } else {
+        if (mh == K.h)
+          sph_kernel_fast<false>(K, r, dx, dy, w[u], gx[u], gy[u]);
+        else
+          sph_kernel(P, r, dx, dy, mh, w[u], gx[u], gy[u]);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u;
+      if (e >= cnt1) break;
+      const int pos = (e < s1) ? (cnt1 - s1) + e : (cnt1 - 1 - e);
+      const size_t a = o1 + (size_t)pos * SLICE;
+      if (sp == SP_NODE) {
+        L.idxC[a] = qid[u];
+        L.wC[a] = (float)w[u];
+        L.gxC[a] = (float)gx[u];
+        L.gyC[a] = (float)gy[u];
+        L.xC[a] = (float)dxs[u];                 // xij = real(x(1,i) - x(1,j)), main:856
+        L.yC[a] = (float)dys[u];
+        L.hC[a] = (float)(0.5 * (hp + hq[u]));   // main:863
+      } else {
+        L.idxD[a] = qid[u];
+        L.wD[a] = (float)w[u];
+      }
+    }
+  }
   if (sp == SP_NODE) bc_int[id] = has_dummy;  // main:506,579
 }
 

@@ -6,6 +6,7 @@
 // There is no CPU fallback: every entry point fails if CUDA is unavailable.
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -76,6 +77,8 @@ struct spsph_handle {
   long long *scan_totals = nullptr;  // [0..2] list storage, [3] pairs, [4..6] cells
   // lists
   int *n0 = nullptr, *n1 = nullptr, *nall = nullptr, *nfwd_u = nullptr, *base_u = nullptr;
+  int *cand0 = nullptr, *cand1 = nullptr, *cand_overflow = nullptr;  // accepted partners recorded by k_count
+  bool force_fill_scan = false;  // SPSPH_FORCE_FILL_SCAN=1: always take the overflow path (tests)
   int *wslice = nullptr, *oslice = nullptr;  // 3 rows x nslices
   int nslices = 0;
   GrowthRule *growth = nullptr;
@@ -395,6 +398,7 @@ int build_neighbours(spsph_handle *h) {
   k_zero_cells<<<296, TB, 0, s>>>(h->G, h->cell_fill, h->cell_stride);
   CUDA_TRY(cudaMemsetAsync(h->nout, 0, 6 * sizeof(int), s));
   CUDA_TRY(cudaMemsetAsync(h->nfwd_u, 0, (size_t)n2 * sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(h->cand_overflow, 0, sizeof(int), s));
   mark(h, KID_ZERO, 2);
   k_cell_id<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->G, h->x, h->if_out, lflag, h->which_cell, h->cell_cnt,
                                                h->cell_stride, h->nout);
@@ -408,13 +412,15 @@ int build_neighbours(spsph_handle *h) {
   const SortArrays S = sort_arrays(h);
   const int T = h->M.total();
   k_count<<<(T + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->nfwd_u, h->nall, h->wslice,
-                                           h->wslice + h->nslices, h->wslice + 2 * h->nslices, lflag);
+                                           h->wslice + h->nslices, h->wslice + 2 * h->nslices, lflag, h->cand0,
+                                           h->cand1, h->cand_overflow);
   mark(h, KID_COUNT);
   launch_scan(h, h->wslice, h->oslice, 3, h->nslices, nullptr, h->nslices, h->scan_totals);
   launch_scan(h, h->nfwd_u, h->base_u, 1, n2, nullptr, n2, h->scan_totals + 3);
   if (h->dist)  // every pair is counted once, at the owner of its earlier member
     NCCL_TRY(h->p_ncclAllReduce(h->scan_totals + 3, h->scan_totals + 3, 1, ncclInt64, ncclSum, h->comm, s));
-  k_status<<<1, 32, 0, s>>>(h->G, h->scan_totals, h->cell_start, h->cell_stride, h->nout, h->status_d);
+  k_status<<<1, 32, 0, s>>>(h->G, h->scan_totals, h->cell_start, h->cell_stride, h->nout, h->cand_overflow,
+                            h->status_d);
   mark(h, KID_STATUS);
   CUDA_TRY(cudaMemcpyAsync(h->status_h, h->status_d, sizeof(StepStatus), cudaMemcpyDeviceToHost, s));
   CUDA_TRY(cudaStreamSynchronize(s));
@@ -459,7 +465,12 @@ int build_neighbours(spsph_handle *h) {
   }
   if (st.n_pairs > h->m_pairs) h->m_pairs = st.n_pairs;
   const int TL = h->M.nnp + h->M.nsp;  // (parked slots return at once)
-  k_fill<<<(TL + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int, h->n_int, h->mor);
+  if (st.pad[0] || h->force_fill_scan)  // a particle has more partners than the candidate scratch holds: search again while filling
+    k_fill_scan<<<(TL + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int, h->n_int,
+                                                  h->mor);
+  else
+    k_fill<<<(TL + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int, h->n_int,
+                                             h->mor, h->cand0, h->cand1);
   mark(h, KID_FILL);
   return 0;
 }
@@ -555,6 +566,10 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
     return 1;
   }
   h->hp = *p;
+  {
+    const char *e = std::getenv("SPSPH_FORCE_FILL_SCAN");
+    h->force_fill_scan = e && e[0] == '1';
+  }
   // ---- scope checks: everything the reference would run for these inputs must exist on the device ----
   auto fail = [&](const char *m) {
     h->err = m;
@@ -673,7 +688,8 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   rc |= dalloc(h, &h->scan_bsum, 4 * (size_t)SCAN_BLOCKS) | dalloc(h, &h->scan_totals, 8);
   const size_t T = (size_t)M.total();
   rc |= dalloc(h, &h->n0, T) | dalloc(h, &h->n1, T) | dalloc(h, &h->nall, T);
-  rc |= dalloc(h, &h->nfwd_u, n2) | dalloc(h, &h->base_u, n2);
+  rc |= dalloc(h, &h->nfwd_u, n2) | dalloc(h, &h->base_u, n2) | dalloc(h, &h->cand_overflow, 4);
+  rc |= dalloc(h, &h->cand0, (size_t)h->nslices * CAND_CAP * SLICE) | dalloc(h, &h->cand1, (size_t)h->nslices * CAND_CAP * SLICE);
   rc |= dalloc(h, &h->wslice, 3 * (size_t)h->nslices) | dalloc(h, &h->oslice, 3 * (size_t)h->nslices);
   rc |= dalloc(h, &h->growth, 1) | dalloc(h, &h->status_d, 1) | dalloc(h, &h->stats_d, 4);
   if (rc) return 1;

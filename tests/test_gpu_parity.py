@@ -122,3 +122,17 @@ def test_restart_from_download(deck_dir):
         # step 21 of the restarted run walks its (new) list reversed; fp64 sums reorder -> tolerance, not bits
         scale = np.abs(ref[k][:nt]).max()
         assert np.abs(got[k][:nt] - ref[k][:nt]).max() <= 1e-9 * scale
+
+
+def test_fill_overflow_path(deck_dir, monkeypatch):
+    """k_fill_scan (taken when a particle has more partners than the candidate scratch holds) must give the
+    same lists as the fast path: forced here through SPSPH_FORCE_FILL_SCAN."""
+    import spsph
+    from oracle_binding import Oracle
+    monkeypatch.setenv("SPSPH_FORCE_FILL_SCAN", "1")
+    prob = _load(deck_dir, "bui")
+    dt = prob.blocks[0]["dt"]
+    eng, orc = spsph.Engine(prob), Oracle(prob)
+    eng.run(1, 0.0, dt, 40)
+    orc.run(1, 0.0, dt, 40)
+    _compare(eng.download(), orc.download(), prob.params.ntotal, "bui, fill overflow path, 40 steps")
