@@ -207,4 +207,153 @@ __global__ void k_bbox_final(int nblocks, const double *__restrict__ partial, do
   bb6[5] = -hmn;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// List-growth rule across slabs: find the pair whose GLOBAL creation index equals the old list
+// capacity M. Creation order = earlier member ascending by (cell id, species, particle number); every rank
+// knows, for its owned particles, the number of pairs they open (nfwd_u, local exclusive scan base_u). The
+// search narrows row -> cell -> particle with one small collective per level; everything stays on the stream.
+// ------------------------------------------------------------------------------------------------------
+constexpr int GT_CAP = 1 << 16;  // rows / cells per row the search can handle
+constexpr int GT_PCAP = 256;     // pair-opening particles of one cell listed per rank
+
+struct GtSel {
+  long long rem;  // remaining 1-based index inside the selected row / cell / particle
+  int row, cell, err, pad;
+};
+
+__device__ __forceinline__ int unified_of_cell(const SortArrays &S, int c) {
+  return S.start[0][c] + S.start[1][c] + S.start[2][c];
+}
+__device__ __forceinline__ long long gt_base(const SortArrays &S, const GridInfo *G, const int *base_u,
+                                             long long local_total, int c) {  // pairs opened in cells < c
+  const int U = unified_of_cell(S, c);
+  const int nact = unified_of_cell(S, G->ncell);
+  return U < nact ? (long long)base_u[U] : local_total;
+}
+
+__global__ void k_gt_rows(const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ base_u,
+                          const long long *__restrict__ local_total, long long *__restrict__ rows) {
+  const int y = blockIdx.x * blockDim.x + threadIdx.x;
+  if (y >= GT_CAP) return;
+  const int ndx = G->ndivx[0], ndy = G->ndivx[1];
+  long long v = 0;
+  if (y < ndy) v = gt_base(S, G, base_u, *local_total, (y + 1) * ndx) - gt_base(S, G, base_u, *local_total, y * ndx);
+  rows[y] = v;
+}
+__global__ void k_gt_pick_row(const GridInfo *__restrict__ G, const long long *__restrict__ rows, long long M,
+                              GtSel *__restrict__ sel) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  long long acc = 0;
+  sel->err = (G->ndivx[0] > GT_CAP || G->ndivx[1] > GT_CAP) ? 1 : 0;
+  sel->row = 0;
+  sel->rem = 0;
+  for (int y = 0; y < min(G->ndivx[1], GT_CAP); ++y) {
+    if (acc + rows[y] >= M) {
+      sel->row = y;
+      sel->rem = M - acc;
+      return;
+    }
+    acc += rows[y];
+  }
+  sel->err = 1;
+}
+__global__ void k_gt_cells(const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ base_u,
+                           const long long *__restrict__ local_total, const GtSel *__restrict__ sel,
+                           long long *__restrict__ cells) {
+  const int xx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (xx >= GT_CAP) return;
+  const int ndx = G->ndivx[0];
+  long long v = 0;
+  if (xx < ndx) {
+    const int c = sel->row * ndx + xx;
+    v = gt_base(S, G, base_u, *local_total, c + 1) - gt_base(S, G, base_u, *local_total, c);
+  }
+  cells[xx] = v;
+}
+// picks the cell, then lists this rank's pair-opening particles of that cell as (key, count)
+__global__ void k_gt_pick_cell(const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ nfwd_u,
+                               const long long *__restrict__ cells, GtSel *__restrict__ sel,
+                               long long *__restrict__ mine /* [GT_PCAP][2] */) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const int ndx = G->ndivx[0];
+  long long acc = 0;
+  int found = -1;
+  for (int xx = 0; xx < min(ndx, GT_CAP); ++xx) {
+    if (acc + cells[xx] >= sel->rem) {
+      found = xx;
+      break;
+    }
+    acc += cells[xx];
+  }
+  for (int i = 0; i < 2 * GT_PCAP; ++i) mine[i] = -1;
+  if (found < 0) {
+    sel->err = 1;
+    return;
+  }
+  const int c = sel->row * ndx + found;
+  sel->cell = c;
+  sel->rem = sel->rem - acc;
+  int n = 0;
+  for (int sp = 0; sp < 3; ++sp)
+    for (int k = S.start[sp][c]; k < S.start[sp][c + 1]; ++k) {
+      const int nf = nfwd_u[unified_slot(S, c, sp, k)];
+      if (nf <= 0) continue;  // ghosts and particles that open no pair
+      if (n >= GT_PCAP) {
+        sel->err = 1;
+        return;
+      }
+      mine[2 * n] = (long long)make_key(c, sp, S.order[sp][k]);
+      mine[2 * n + 1] = nf;
+      ++n;
+    }
+}
+// all = gathered lists of every rank; picks the particle and, on the rank that owns it, its rem-th forward partner
+__global__ void k_gt_pick_particle(DevParams P, const GridInfo *__restrict__ G, SortArrays S,
+                                   const int *__restrict__ pos_of, const long long *__restrict__ all, int nranks,
+                                   int myrank, GtSel *__restrict__ sel, long long *__restrict__ out2) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  out2[0] = 0;
+  out2[1] = 0;
+  out2[2] = 0;
+  const int n = nranks * GT_PCAP;
+  long long acc = 0, last = -1;
+  for (;;) {  // walk the entries in ascending key order (selection without sorting; n is small)
+    long long best = -1;
+    int bi = -1;
+    for (int i = 0; i < n; ++i) {
+      const long long kk = all[2 * i];
+      if (kk < 0 || kk <= last) continue;
+      if (bi < 0 || kk < best) {
+        best = kk;
+        bi = i;
+      }
+    }
+    if (bi < 0) {
+      sel->err = 1;
+      return;
+    }
+    const long long nf = all[2 * bi + 1];
+    if (acc + nf >= sel->rem) {
+      if (bi / GT_PCAP == myrank) {
+        const okey_t ka = (okey_t)best;
+        const int c = key_cell(ka), sp = (int)((ka >> 32) & 3), id = (int)(ka & 0xffffffffu);
+        out2[0] = best;
+        out2[2] = 1;  // found flag (a key may legitimately be 0)
+        out2[1] = (long long)mth_forward_partner(P, G, S, c, sp, pos_of[id], (int)(sel->rem - acc));
+      }
+      return;
+    }
+    acc += nf;
+    last = best;
+  }
+}
+__global__ void k_gt_finish(const long long *__restrict__ out2, const GtSel *__restrict__ sel, GrowthRule *__restrict__ g,
+                            int *__restrict__ err) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  g->mode = 2;
+  g->ka = (okey_t)out2[0];
+  g->kb = (okey_t)out2[1];
+  if (sel->err || out2[2] != 1) *err = 1;
+}
+
 }  // namespace spsph

@@ -378,16 +378,29 @@ __device__ __forceinline__ int unified_slot(const SortArrays &S, int c, int sp, 
 }
 
 // Growth rule of the reference's list: pairs whose creation index exceeds the old list
-// capacity M are visited first and reversed. thr = (ua*, ub*): pair (ua<ub) is "old" iff (ua,ub) <=lex thr.
+// capacity M are visited first and reversed. Particles are compared by the creation-order key
+// (cell id, species, particle number) -- globally meaningful, so the same rule serves the multi-GPU slabs:
+// pair (ka < kb) is "old" iff (ka, kb) <=lex (g.ka, g.kb), the keys of the pair with creation index M.
+typedef unsigned long long okey_t;
+__device__ __forceinline__ okey_t make_key(int cell, int sp, int id) {
+  return ((okey_t)(unsigned)cell << 34) | ((okey_t)(unsigned)sp << 32) | (okey_t)(unsigned)id;
+}
+__device__ __forceinline__ int key_cell(okey_t k) { return (int)(k >> 34); }
 struct GrowthRule {
-  int mode;  // 0: all old (forward), 1: all new (fully reversed: first step), 2: split at (ua, ub)
-  int ua, ub;
+  int mode;  // 0: all old (forward), 1: all new (fully reversed: first step), 2: split at (ka, kb)
+  int pad;
+  okey_t ka, kb;
 };
-__device__ __forceinline__ bool pair_is_old(const GrowthRule &g, int u1, int u2) {
+__device__ __forceinline__ bool pair_is_old(const GrowthRule &g, okey_t k1, okey_t k2) {
   if (g.mode == 0) return true;
   if (g.mode == 1) return false;
-  const int a = u1 < u2 ? u1 : u2, b = u1 < u2 ? u2 : u1;
-  return (a < g.ua) || (a == g.ua && b <= g.ub);
+  const okey_t a = k1 < k2 ? k1 : k2, b = k1 < k2 ? k2 : k1;
+  return (a < g.ka) || (a == g.ka && b <= g.kb);
+}
+__device__ __forceinline__ okey_t sorted_key(const SortArrays &S, int sq, int q) {
+  const int *cp = sq == 0 ? S.cell[0] : (sq == 1 ? S.cell[1] : S.cell[2]);
+  const int *op = sq == 0 ? S.order[0] : (sq == 1 ? S.order[1] : S.order[2]);
+  return make_key(cp[q], sq, op[q]);
 }
 
 // ---- exactly rounded division by a value whose correctly rounded reciprocal is known (Markstein): the
@@ -622,7 +635,36 @@ __global__ void k_status(const GridInfo *__restrict__ G, const long long *__rest
   for (int sp = 0; sp < 3; ++sp) st->nloc[sp] = start[sp * cell_stride + G->ncell] + nout[sp];
 }
 
-// Finds the split point of the growth rule: the pair with creation index M (1-based) -> (ua*, ub*).
+// key of the want-th (1-based) forward partner, in creation order, of the particle at (cell c, species sp,
+// species-sorted index k)
+__device__ okey_t mth_forward_partner(const DevParams &P, const GridInfo *G, const SortArrays &S, int c, int sp, int k,
+                                      int want) {
+  const double2 pp = S.pos[sp][k];
+  const double hp = S.h[sp][k];
+  const int ndx = G->ndivx[0], ndy = G->ndivx[1];
+  const int cy = c / ndx, cx = c - cy * ndx;
+  int seen = 0;
+  okey_t kb = 0;
+  for (int jy = cy; jy <= min(cy + 1, ndy - 1) && seen < want; ++jy)
+    for (int jx = max(cx - 1, 0); jx <= min(cx + 1, ndx - 1) && seen < want; ++jx) {
+      const int cq = jy * ndx + jx;
+      if (cq < c) continue;
+      for (int sq = 0; sq < 3 && seen < want; ++sq) {
+        const int b = S.start[sq][cq], e = S.start[sq][cq + 1];
+        for (int q = b; q < e && seen < want; ++q) {
+          const bool fwd = (cq > c) || (sq > sp || (sq == sp && q > k));
+          if (!fwd) continue;
+          double dx, dy, r, mh;
+          if (!pair_accept(P, pp, hp, S.pos[sq][q], S.h[sq][q], dx, dy, r, mh)) continue;
+          ++seen;
+          kb = make_key(cq, sq, S.order[sq][q]);
+        }
+      }
+    }
+  return kb;
+}
+
+// Finds the split point of the growth rule: the pair with creation index M (1-based) -> (ka*, kb*).
 __global__ void k_growth_threshold(DevParams P, SlotMap Mm, const GridInfo *__restrict__ G, SortArrays S,
                                    const int *__restrict__ base_u /* exclusive scan of nfwd_u */, long long Mold,
                                    GrowthRule *__restrict__ out) {
@@ -658,30 +700,9 @@ __global__ void k_growth_threshold(DevParams P, SlotMap Mm, const GridInfo *__re
     rem -= n;
   }
   const int k = S.start[sp][c] + rem;
-  const double2 pp = S.pos[sp][k];
-  const double hp = S.h[sp][k];
-  const int ndx = G->ndivx[0], ndy = G->ndivx[1];
-  const int cy = c / ndx, cx = c - cy * ndx;
-  int seen = 0, ub = ua;
-  for (int jy = cy; jy <= min(cy + 1, ndy - 1) && seen < want; ++jy)
-    for (int jx = max(cx - 1, 0); jx <= min(cx + 1, ndx - 1) && seen < want; ++jx) {
-      const int cq = jy * ndx + jx;
-      if (cq < c) continue;
-      for (int sq = 0; sq < 3 && seen < want; ++sq) {
-        const int b = S.start[sq][cq], e = S.start[sq][cq + 1];
-        for (int q = b; q < e && seen < want; ++q) {
-          const bool fwd = (cq > c) || (sq > sp || (sq == sp && q > k));
-          if (!fwd) continue;
-          double dx, dy, r, mh;
-          if (!pair_accept(P, pp, hp, S.pos[sq][q], S.h[sq][q], dx, dy, r, mh)) continue;
-          ++seen;
-          ub = unified_slot(S, cq, sq, q);
-        }
-      }
-    }
   out->mode = 2;
-  out->ua = ua;
-  out->ub = ub;
+  out->ka = make_key(c, sp, S.order[sp][k]);
+  out->kb = mth_forward_partner(P, G, S, c, sp, k, want);
 }
 
 struct ListPtrs {
@@ -748,13 +769,13 @@ k_fill_scan(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
   // number of "old" entries per list (prefix of the ascending order); only the split mode needs a pre-count
   int s0 = (gr.mode == 1) ? 0 : cnt0, s1 = (gr.mode == 1) ? 0 : cnt1;
   if (gr.mode == 2) {
-    const int up = unified_slot(S, c, sp, k);
-    if (up >= gr.ua) {
+    const okey_t up = make_key(c, sp, id);
+    if (up >= gr.ka) {
       s0 = 0;
       s1 = 0;
-      // partners at or before ua live in cells <= cell(ua); cheap conservative test on the first stencil cell
+      // partners at or before ka live in cells <= cell(ka); cheap conservative test on the first stencil cell
       const int cfirst = max(cy - 1, 0) * ndx + max(cx - 1, 0);
-      if (unified_slot(S, cfirst, 0, S.start[0][cfirst]) <= gr.ua) {
+      if (cfirst <= key_cell(gr.ka)) {
         for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy)
           for (int jx = max(cx - 1, 0); jx <= min(cx + 1, ndx - 1); ++jx) {
             const int cq = jy * ndx + jx;
@@ -764,7 +785,7 @@ k_fill_scan(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
                 if (sq == sp && q == k) continue;
                 double dx, dy, r, mh;
                 if (!pair_accept(P, pp, hp, S.pos[sq][q], S.h[sq][q], dx, dy, r, mh)) continue;
-                if (!pair_is_old(gr, up, unified_slot(S, cq, sq, q))) continue;
+                if (!pair_is_old(gr, up, make_key(cq, sq, S.order[sq][q]))) continue;
                 if (sq == sp)
                   ++s1;
                 else
@@ -925,20 +946,15 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
   // number of "old" entries per list (prefix of the ascending order); only the split mode needs a pre-count
   int s0 = (gr.mode == 1) ? 0 : cnt0, s1 = (gr.mode == 1) ? 0 : cnt1;
   if (gr.mode == 2) {
-    const int up = unified_slot(S, c, sp, k);
-    if (up >= gr.ua) {
+    const okey_t up = make_key(c, sp, id);
+    if (up >= gr.ka) {
       s0 = 0;
       s1 = 0;
       for (int e = 0; e < cnt0; ++e) {
         const int pk = cand0[cb + (size_t)e * SLICE];
-        const int sq = (int)((unsigned)pk >> 30), q = pk & 0x3fffffff;
-        const int cq = (sq == 0 ? S.cell[0] : (sq == 1 ? S.cell[1] : S.cell[2]))[q];
-        s0 += pair_is_old(gr, up, unified_slot(S, cq, sq, q)) ? 1 : 0;
+        s0 += pair_is_old(gr, up, sorted_key(S, (int)((unsigned)pk >> 30), pk & 0x3fffffff)) ? 1 : 0;
       }
-      for (int e = 0; e < cnt1; ++e) {
-        const int q = cand1[cb + (size_t)e * SLICE];
-        s1 += pair_is_old(gr, up, unified_slot(S, cellp[q], sp, q)) ? 1 : 0;
-      }
+      for (int e = 0; e < cnt1; ++e) s1 += pair_is_old(gr, up, sorted_key(S, sp, cand1[cb + (size_t)e * SLICE])) ? 1 : 0;
     }
   }
   constexpr int U = 4;

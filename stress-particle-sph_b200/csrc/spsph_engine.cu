@@ -102,6 +102,8 @@ struct spsph_handle {
   int *halo_ids[2] = {nullptr, nullptr};
   double *halo_send[2] = {nullptr, nullptr}, *halo_recv[2] = {nullptr, nullptr};
   double *bb6 = nullptr;
+  long long *gt_buf = nullptr, *gt_mine = nullptr, *gt_all = nullptr, *gt_out2 = nullptr;  // growth-rule search
+  GtSel *gt_sel = nullptr;
   void *nccl_lib = nullptr;
   ncclComm_t comm = nullptr;
   ncclResult_t (*p_ncclCommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
@@ -110,6 +112,7 @@ struct spsph_handle {
   ncclResult_t (*p_ncclRecv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*p_ncclAllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t,
                                   cudaStream_t) = nullptr;
+  ncclResult_t (*p_ncclAllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*p_ncclGroupStart)() = nullptr;
   ncclResult_t (*p_ncclGroupEnd)() = nullptr;
   const char *(*p_ncclGetErrorString)(ncclResult_t) = nullptr;
@@ -417,8 +420,10 @@ int build_neighbours(spsph_handle *h) {
   mark(h, KID_COUNT);
   launch_scan(h, h->wslice, h->oslice, 3, h->nslices, nullptr, h->nslices, h->scan_totals);
   launch_scan(h, h->nfwd_u, h->base_u, 1, n2, nullptr, n2, h->scan_totals + 3);
-  if (h->dist)  // every pair is counted once, at the owner of its earlier member
+  if (h->dist) {  // every pair is counted once, at the owner of its earlier member
+    CUDA_TRY(cudaMemcpyAsync(h->scan_totals + 6, h->scan_totals + 3, sizeof(long long), cudaMemcpyDeviceToDevice, s));
     NCCL_TRY(h->p_ncclAllReduce(h->scan_totals + 3, h->scan_totals + 3, 1, ncclInt64, ncclSum, h->comm, s));
+  }
   k_status<<<1, 32, 0, s>>>(h->G, h->scan_totals, h->cell_start, h->cell_stride, h->nout, h->cand_overflow,
                             h->status_d);
   mark(h, KID_STATUS);
@@ -426,11 +431,15 @@ int build_neighbours(spsph_handle *h) {
   CUDA_TRY(cudaStreamSynchronize(s));
   const StepStatus st = *h->status_h;
   if (h->dist) {
-    int herr = 0;
-    CUDA_TRY(cudaMemcpyAsync(&herr, h->halo_cnt + 2, sizeof(int), cudaMemcpyDeviceToHost, s));
+    int herr[2] = {0, 0};
+    CUDA_TRY(cudaMemcpyAsync(herr, h->halo_cnt + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
     CUDA_TRY(cudaStreamSynchronize(s));
-    if (herr) {
+    if (herr[0]) {
       h->err = "multi-GPU: halo message capacity exceeded (too many particles near a slab boundary)";
+      return 1;
+    }
+    if (herr[1]) {
+      h->err = "multi-GPU: the distributed list-growth search failed in the previous step (grid too large?)";
       return 1;
     }
   }
@@ -455,11 +464,21 @@ int build_neighbours(spsph_handle *h) {
   CUDA_TRY(cudaMemcpyAsync(h->growth, &gr, sizeof(gr), cudaMemcpyHostToDevice, s));
   if (h->profiling) mark(h, -1, 0);  // do not charge the host round trip to the next kernel
   if (gr.mode == 2 && h->dist) {
-    h->err = "multi-GPU: the pair count grew past its previous maximum (reference list-growth rule, SURVEY App. B); "
-             "the split traversal order is not implemented for the slab decomposition yet";
-    return 1;
-  }
-  if (gr.mode == 2) {
+    // distributed search for the pair with global creation index m_pairs (dist_kernels.cuh); no host sync
+    const long long *ltot = h->scan_totals + 6;  // local pair total saved before the all-reduce
+    k_gt_rows<<<GT_CAP / 256, 256, 0, s>>>(h->G, S, h->base_u, ltot, h->gt_buf);
+    NCCL_TRY(h->p_ncclAllReduce(h->gt_buf, h->gt_buf, GT_CAP, ncclInt64, ncclSum, h->comm, s));
+    k_gt_pick_row<<<1, 32, 0, s>>>(h->G, h->gt_buf, h->m_pairs, h->gt_sel);
+    k_gt_cells<<<GT_CAP / 256, 256, 0, s>>>(h->G, S, h->base_u, ltot, h->gt_sel, h->gt_buf);
+    NCCL_TRY(h->p_ncclAllReduce(h->gt_buf, h->gt_buf, GT_CAP, ncclInt64, ncclSum, h->comm, s));
+    k_gt_pick_cell<<<1, 32, 0, s>>>(h->G, S, h->nfwd_u, h->gt_buf, h->gt_sel, h->gt_mine);
+    NCCL_TRY(h->p_ncclAllGather(h->gt_mine, h->gt_all, 2 * GT_PCAP, ncclInt64, h->comm, s));
+    k_gt_pick_particle<<<1, 32, 0, s>>>(P, h->G, S, h->pos_of, h->gt_all, h->D.nranks, h->D.rank, h->gt_sel,
+                                        h->gt_out2);
+    NCCL_TRY(h->p_ncclAllReduce(h->gt_out2, h->gt_out2, 3, ncclInt64, ncclSum, h->comm, s));
+    k_gt_finish<<<1, 32, 0, s>>>(h->gt_out2, h->gt_sel, h->growth, h->halo_cnt + 3);
+    mark(h, KID_THRESH, 6);
+  } else if (gr.mode == 2) {
     k_growth_threshold<<<1, 32, 0, s>>>(P, h->M, h->G, S, h->base_u, h->m_pairs, h->growth);
     mark(h, KID_THRESH);
   }
@@ -979,6 +998,7 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
   NCCL_SYM(ncclSend)
   NCCL_SYM(ncclRecv)
   NCCL_SYM(ncclAllReduce)
+  NCCL_SYM(ncclAllGather)
   NCCL_SYM(ncclGroupStart)
   NCCL_SYM(ncclGroupEnd)
   NCCL_SYM(ncclGetErrorString)
@@ -1008,6 +1028,9 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
   const size_t n2 = (size_t)p.ntotal2;
   const size_t msg = (size_t)HALO_REC * ((size_t)D.cap + 1);
   if (dalloc(h, &h->lflag, n2) || dalloc(h, &h->halo_cnt, 4)) return 1;
+  if (dalloc(h, &h->gt_buf, (size_t)GT_CAP) || dalloc(h, &h->gt_mine, 2 * (size_t)GT_PCAP) ||
+      dalloc(h, &h->gt_all, 2 * (size_t)GT_PCAP * nranks) || dalloc(h, &h->gt_out2, 4) || dalloc(h, &h->gt_sel, 1))
+    return 1;
   for (int side = 0; side < 2; ++side)
     if (dalloc(h, &h->halo_ids[side], (size_t)D.cap) || dalloc(h, &h->halo_send[side], msg) ||
         dalloc(h, &h->halo_recv[side], msg))
