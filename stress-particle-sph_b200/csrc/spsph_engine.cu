@@ -60,7 +60,7 @@ struct spsph_handle {
   float *wallpos = nullptr, *horiz = nullptr, *n_int = nullptr;
   int *bc_int = nullptr, *bc_or_not = nullptr, *bc_info = nullptr, *if_out = nullptr;
   int cur = 0;
-  std::vector<double> h_internal_vars;  // rows 2..10 of Internal_Vars never change on the hot path
+  double *ivars = nullptr;  // device mirror of Internal_Vars(10, ntotal): rows 2..10 never change on the hot path
   std::vector<int32_t> h_itype;
 
   // grid / sort
@@ -137,6 +137,17 @@ static const char *kKernelNames[KID_N] = {"k_domain_bbox", "k_grid_params", "k_z
                                           "halo_exchange"};
 
 namespace {
+
+__global__ void k_upload_derive(int n2, int nt, const double *__restrict__ mass, const double *__restrict__ rho,
+                                double *__restrict__ mor, const double *__restrict__ ivars, double *__restrict__ epsp) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n2) mor[i] = mass[i] / rho[i];  // same IEEE division as the reference's mass(j)/rho(j)
+  if (i < nt) epsp[i] = ivars[(size_t)SPSPH_NINT_VARS * i];
+}
+__global__ void k_download_ivars(int nt, const double *__restrict__ epsp, double *__restrict__ ivars) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < nt) ivars[(size_t)SPSPH_NINT_VARS * i] = epsp[i];
+}
 
 template <class T>
 int dalloc(spsph_handle *h, T **p, size_t n) {
@@ -692,6 +703,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   }
   rc |= dalloc(h, &h->stage_vel, 2 * nt) | dalloc(h, &h->stage_stress, 4 * nt);
   rc |= dalloc(h, &h->epsp, nt) | dalloc(h, &h->fdp, nt) | dalloc(h, &h->norm, nt);
+  rc |= dalloc(h, &h->ivars, (size_t)SPSPH_NINT_VARS * nt);
   rc |= dalloc(h, &h->AE, 5 * nt) | dalloc(h, &h->vel0, 2 * nn) | dalloc(h, &h->stress0, 4 * ns);
   rc |= dalloc(h, &h->vx0, 2 * nt) | dalloc(h, &h->RKv, 2 * nn) | dalloc(h, &h->RKs, 4 * ns) | dalloc(h, &h->RKe, ns);
   rc |= dalloc(h, &h->displ, 2 * nn) | dalloc(h, &h->x_10, 2 * nn) | dalloc(h, &h->disp_10, nn);
@@ -747,25 +759,14 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   CUDA_TRY(up(h->rho, s->rho, n2 * 8));
   CUDA_TRY(up(h->mass, s->mass, n2 * 8));
   CUDA_TRY(up(h->hsml, s->hsml, n2 * 8));
-  std::vector<double> mor(n2);
   double hmax = 0.0;
-  for (size_t i = 0; i < n2; ++i) {
-    mor[i] = s->mass[i] / s->rho[i];
-    hmax = std::fmax(hmax, s->hsml[i]);
-  }
-  CUDA_TRY(up(h->mor, mor.data(), n2 * 8));
+  for (size_t i = 0; i < n2; ++i) hmax = std::fmax(hmax, s->hsml[i]);
   h->cur = 0;
   CUDA_TRY(up(h->stage_vel, s->vel, 2 * nt * 8));
   CUDA_TRY(up(h->stage_stress, s->stress, 4 * nt * 8));
+  CUDA_TRY(up(h->ivars, s->internal_vars, (size_t)SPSPH_NINT_VARS * nt * 8));
+  k_upload_derive<<<((int)n2 + 255) / 256, 256, 0, st>>>((int)n2, (int)nt, h->mass, h->rho, h->mor, h->ivars, h->epsp);
   k_pack_state<<<((int)nt + 255) / 256, 256, 0, st>>>(h->P, h->stage_vel, h->stage_stress, state_ptrs(h, 0));
-  std::vector<double> e1(nt, 0.0);
-  if (s->internal_vars) {
-    h->h_internal_vars.assign(s->internal_vars, s->internal_vars + (size_t)SPSPH_NINT_VARS * nt);
-    for (size_t i = 0; i < nt; ++i) e1[i] = s->internal_vars[(size_t)SPSPH_NINT_VARS * i];
-  } else {
-    h->h_internal_vars.assign((size_t)SPSPH_NINT_VARS * nt, 0.0);
-  }
-  CUDA_TRY(up(h->epsp, e1.data(), nt * 8));
   CUDA_TRY(up(h->fdp, s->f_drucker, nt * 8));
   CUDA_TRY(up(h->displ, s->displ, 2 * nn * 8));
   CUDA_TRY(up(h->x_10, s->x_10 ? s->x_10 : s->x, 2 * nn * 8));
@@ -777,7 +778,7 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   CUDA_TRY(up(h->if_out, s->if_out_domain, n2 * 4));
   CUDA_TRY(up(h->bc_or_not, s->bc_or_not, nt * 4));
   CUDA_TRY(up(h->bc_info, s->bc_info, 8 * nt * 4));
-  CUDA_TRY(cudaStreamSynchronize(st));  // host staging vectors go out of scope
+  CUDA_TRY(cudaStreamSynchronize(st));  // the caller may reuse its arrays as soon as upload returns
   // cell-table capacity: the in-domain bounding box can never exceed the control domain (main:1187-1192)
   if (!h->cell_cnt) {
     if (!(hmax > 0.0)) {
@@ -887,10 +888,9 @@ int spsph_download(spsph_handle *h, const spsph_state *s) {
   CUDA_TRY(down(s->rho, h->rho, n2 * 8));
   CUDA_TRY(down(s->mass, h->mass, n2 * 8));
   CUDA_TRY(down(s->hsml, h->hsml, n2 * 8));
-  std::vector<double> e1;
   if (s->internal_vars) {
-    e1.resize(nt);
-    CUDA_TRY(cudaMemcpyAsync(e1.data(), h->epsp, nt * 8, cudaMemcpyDeviceToHost, st));
+    k_download_ivars<<<((int)nt + 255) / 256, 256, 0, st>>>((int)nt, h->epsp, h->ivars);
+    CUDA_TRY(down(s->internal_vars, h->ivars, (size_t)SPSPH_NINT_VARS * nt * 8));
   }
   CUDA_TRY(down(s->f_drucker, h->fdp, nt * 8));
   CUDA_TRY(down(s->x00, h->x00, 2 * n2 * 8));
@@ -903,10 +903,6 @@ int spsph_download(spsph_handle *h, const spsph_state *s) {
   CUDA_TRY(down(s->bc_or_not, h->bc_or_not, nt * 4));
   CUDA_TRY(cudaStreamSynchronize(st));
   if (s->itype) std::memcpy(s->itype, h->h_itype.data(), n2 * sizeof(int32_t));
-  if (s->internal_vars) {
-    std::memcpy(s->internal_vars, h->h_internal_vars.data(), (size_t)SPSPH_NINT_VARS * nt * 8);
-    for (size_t i = 0; i < nt; ++i) s->internal_vars[(size_t)SPSPH_NINT_VARS * i] = e1[i];
-  }
   return 0;
 }
 
