@@ -537,30 +537,53 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
       const int cy = c / ndx, cx = c - cy * ndx;
       const size_t cb = (size_t)(t / SLICE) * CAND_CAP * SLICE + (t & 31);
       const bool owner_of_lists = sp != SP_DUMMY;
+      auto take = [&](int sq, int q, int fthr) {  // accepted partner, in list order
+        ++ca;
+        cf += (q >= fthr) ? 1 : 0;
+        if (owner_of_lists) {
+          if (sq == sp) {
+            if (c1 < CAND_CAP) cand1[cb + (size_t)c1 * SLICE] = q;
+            ++c1;
+          } else {  // node<->stress (type 1) and node/stress<->dummy (types 6, 9)
+            if (c0 < CAND_CAP) cand0[cb + (size_t)c0 * SLICE] = (sq << 30) | q;
+            ++c0;
+          }
+        }
+      };
       auto scan = [&](int sq, int b, int e, int fthr) {
         const float2 *__restrict__ uq = sq == 0 ? S.upos[0] : (sq == 1 ? S.upos[1] : S.upos[2]);
         const double2 *__restrict__ pq = sq == 0 ? S.pos[0] : (sq == 1 ? S.pos[1] : S.pos[2]);
         const double *__restrict__ hq = sq == 0 ? S.h[0] : (sq == 1 ? S.h[1] : S.h[2]);
-        for (int q = b; q < e; ++q) {
+        auto exact = [&](int q) {
+          double dx, dy, d2, mh;
+          return pair_accept_fast(sk, pp, hp, pq[q], uni ? hp : hq[q], dx, dy, d2, mh);
+        };
+        int q = b;
+        if (pf.on) {
+          // four candidates per iteration: independent loads, one combined "anything to do" test
+          for (; q + 4 <= e; q += 4) {
+            float2 u4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) u4[u] = uq[q + u];
+            int cls[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cls[u] = prefilter_test(pf, up, u4[u]);
+            if ((cls[0] | cls[1] | cls[2] | cls[3]) == 0) continue;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (cls[u] == 0 || (sq == sp && q + u == k)) continue;
+              if (cls[u] == 2 && !exact(q + u)) continue;
+              take(sq, q + u, fthr);
+            }
+          }
+        }
+        for (; q < e; ++q) {
           if (sq == sp && q == k) continue;
           int cls = 2;
           if (pf.on) cls = prefilter_test(pf, up, uq[q]);
           if (cls == 0) continue;
-          if (cls == 2) {
-            double dx, dy, d2, mh;
-            if (!pair_accept_fast(sk, pp, hp, pq[q], uni ? hp : hq[q], dx, dy, d2, mh)) continue;
-          }
-          ++ca;
-          cf += (q >= fthr) ? 1 : 0;
-          if (owner_of_lists) {
-            if (sq == sp) {
-              if (c1 < CAND_CAP) cand1[cb + (size_t)c1 * SLICE] = q;
-              ++c1;
-            } else {  // node<->stress (type 1) and node/stress<->dummy (types 6, 9)
-              if (c0 < CAND_CAP) cand0[cb + (size_t)c0 * SLICE] = (sq << 30) | q;
-              ++c0;
-            }
-          }
+          if (cls == 2 && !exact(q)) continue;
+          take(sq, q, fthr);
         }
       };
       for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy) {
