@@ -21,24 +21,59 @@ def dependent_sweeps(params):
     return n
 
 
-def plan_slabs(problem, nranks, safety=2.0):
-    """-> dict(planes, halo_cells, halo_capacity, H). Slabs hold equal numbers of velocity particles; a plane is
-    placed midway between two distinct particle columns so that no particle sits on it initially."""
+def plan_slabs(problem, nranks, safety=2.0, balance="processed"):
+    """-> dict(planes, halo_cells, halo_capacity, H). A plane is placed midway between two distinct particle
+    columns so that no particle sits on it initially. balance = "processed": slabs are sized so that every rank
+    PROCESSES the same number of velocity particles (owned + both halos; interior slabs come out narrower than
+    the two end slabs); balance = "owned": equal numbers of owned particles."""
     p = problem.params
     x = problem.arrays["x"][:, 0]
     xn = np.sort(x[:p.nnode])
-    planes = [-np.inf]
     ux = np.unique(xn)
-    for r in range(1, nranks):
-        target = xn[(r * p.nnode) // nranks]
-        k = int(np.searchsorted(ux, target))
-        k = min(max(k, 1), len(ux) - 1)
-        planes.append(0.5 * (ux[k - 1] + ux[k]))
-    planes.append(np.inf)
-    planes = np.array(planes, dtype=np.float64)
     halo_cells = dependent_sweeps(p) + 2
     hmax = float(problem.arrays["hsml"].max())
     H = halo_cells * 2.0 * hmax
+
+    def snap(v):  # midpoint between the two distinct columns around v
+        k = int(np.searchsorted(ux, v))
+        k = min(max(k, 1), len(ux) - 1)
+        return 0.5 * (ux[k - 1] + ux[k])
+
+    def count(lo, hi):
+        return int(np.searchsorted(xn, hi) - np.searchsorted(xn, lo))
+
+    def place(target):  # greedy left-to-right placement for a per-rank processed count `target`
+        pl = [-np.inf]
+        for r in range(nranks - 1):
+            lo = pl[-1] - H if r > 0 else -np.inf
+            base = int(np.searchsorted(xn, lo)) if r > 0 else 0
+            k = min(base + target, len(xn) - 1)
+            pl.append(snap(xn[k] - H))   # processed range of rank r ends at plane + H
+            if pl[-1] <= pl[-2] + (0 if r == 0 else H):
+                pl[-1] = snap((pl[-2] if r > 0 else xn[0]) + 1.0001 * H)
+        pl.append(np.inf)
+        return pl
+
+    if nranks > 1 and H > 0.25 * (xn[-1] - xn[0]) / nranks:
+        balance = "owned"  # halo comparable to the slab width (tiny problems): equalising the processed count is moot
+    if nranks == 1:
+        planes = [-np.inf, np.inf]
+    elif balance == "owned":
+        planes = [-np.inf] + [snap(xn[(r * p.nnode) // nranks]) for r in range(1, nranks)] + [np.inf]
+    else:
+        lo_t, hi_t = p.nnode // nranks, p.nnode
+        for _ in range(40):  # bisection on the common processed count: the last rank takes what is left
+            mid = (lo_t + hi_t) // 2
+            pl = place(mid)
+            last = count(pl[-2] - H, np.inf)
+            if last > mid:
+                lo_t = mid + 1
+            else:
+                hi_t = mid
+        planes = place(hi_t)
+    planes = np.array(planes, dtype=np.float64)
+    if nranks > 1 and not np.all(np.diff(planes[1:-1]) > 0) and nranks > 2:
+        raise ValueError("slab planning failed: planes are not increasing")
     cap = 1024
     for r in range(1, nranks):
         near = int(((x >= planes[r] - H) & (x < planes[r] + H)).sum())
