@@ -43,6 +43,7 @@ typedef struct spsph_params {
 
   int32_t ndimn, nstre;                                   /* mat:88,99 (always 2, 4) */
   int32_t nnode, nstress, ntotal, ntotal2, ndummy;        /* mat:440-461,733,804 */
+  int32_t ndummy2;                                        /* wall particles of the innermost layer, mat:794-802 */
   int32_t npoints;                                        /* mat:389,396 */
   int32_t sp_sph, inside_approach, sph_shift, vel_vector; /* mat:384-392 (logicals as 0/1) */
   int32_t shift_update, dummy_nodes;                      /* mat:392,423 */

@@ -46,7 +46,7 @@ struct Oracle {
   int nnode, ntotal, ntotal2;
   // state (1-based Fortran arrays stored 0-based, column-major)
   std::vector<double> x, vel, stress, rho, mass, hsml, internal_vars, f_drucker, x0, x00, vx0, displ, x_10, disp_10;
-  std::vector<double> grad_u, art_visc, Ddev_strn;
+  std::vector<double> grad_u, art_visc, Ddev_strn, f_bound;
   std::vector<int32_t> itype, if_out, bc_or_not, bc_info, bc_int, countiac;
   std::vector<float> wall_position, horizontal_or_not, n_int;
   // pair list: `created` in creation order; traversal order through order_of()
@@ -747,6 +747,42 @@ struct Oracle {
     for (size_t k = 0; k < av.size(); ++k) art_visc[k] = (double)(-av[k]);
   }
 
+  // ---- boundary_forces, main:1039-1165 (branch test == 2; default REAL locals) ---------------------
+  // Repulsion of the velocity particles by the innermost layer of wall particles, brute force over
+  // (wall particle j outer, node i inner); every local is fp32, f_bound accumulates in fp64.
+  void boundary_forces() {
+    std::fill(f_bound.begin(), f_bound.end(), 0.0);
+    const float c = 20;
+    const int start = ntotal + 1, finish = ntotal + p.ndummy2;
+    for (int j = start; j <= finish; ++j)
+      for (int i = 1; i <= nnode; ++i) {
+        float r[2];
+        r[0] = (float)(X(1, i) - X(1, j));
+        r[1] = (float)(X(2, i) - X(2, j));
+        const float r2 = std::sqrt(r[0] * r[0] + r[1] * r[1]);
+        const float d0 = (float)(p.dx / 2.);
+        float f2;
+        const float h = (float)(0.5 * (hsml[i - 1] + hsml[j - 1]));
+        const float r_bound = r2 / (0.75f * h);
+        if (r2 > 0 && r2 < 1.5f * d0)
+          f2 = 1 - (r2 / (1.5f * d0));
+        else
+          f2 = 0.0f;
+        float f;
+        if (0 < r_bound && r_bound <= 2.f / 3.f)
+          f = 2.f / 3.f;
+        else if (2.f / 3.f < r_bound && r_bound <= 1)
+          f = 2 * r_bound - 1.5f * (r_bound * r_bound);
+        else if (1 < r_bound && r_bound < 2)
+          f = 0.5f * ((2 - r_bound) * (2 - r_bound));
+        else
+          f = 0.f;
+        const float pre = (0.01f * (c * c)) * f2 * f;
+        for (int d = 0; d < 2; ++d)
+          f_bound[2 * (size_t)(i - 1) + d] = f_bound[2 * (size_t)(i - 1) + d] + (double)(pre * (r[d] / (r2 * r2)));
+      }
+  }
+
   // ---- RK4, main:653-802 -----------------------------------------------------------------------
   bool rk4() {
     const double f1rk[4] = {0., 0.5, 0.5, 1.0}, f2rk[4] = {1., 2., 2., 1.0};
@@ -800,6 +836,7 @@ struct Oracle {
         for (int i = 1; i <= nnode; ++i)
           for (int d = 1; d <= 2; ++d) source_grav[2 * (size_t)(i - 1) + d - 1] = g[d - 1] - p.damping * V(d, i);
       }
+      if (p.inside_approach) boundary_forces();  // Bui copy main:742; elsewhere .and. dummy_nodes (ndummy2 = 0 then)
       if (p.alpha > 0 || p.beta > 0) artificial_viscosity();
       if (p.art_stress) {
         err = "art_stress = T is not supported (not exercised by any shipped input)";
@@ -825,8 +862,8 @@ struct Oracle {
       for (int i = 1; i <= nnode; ++i)
         for (int d = 0; d < 2; ++d) {
           const size_t k = 2 * (size_t)(i - 1) + d;
-          // f_bound (never written unless boundary_forces runs, App. C-2) and art_force are zero
-          RHS_2[k] = -divf2[k] + source_grav[k] + art_visc[k] + 0.0 + 0.0;
+          // f_bound is zero unless boundary_forces runs (App. C-2); art_force is zero (art_stress = F)
+          RHS_2[k] = -divf2[k] + source_grav[k] + art_visc[k] + f_bound[k] + 0.0;
         }
       for (int i = 1; i <= nnode; ++i)
         for (int d = 0; d < 2; ++d) {
@@ -1056,6 +1093,7 @@ void *oracle_create(const spsph_params *p, const spsph_state *s) {
   copy_in(o->bc_info, s->bc_info, 8 * nt);
   o->grad_u.assign(4 * nt, 0.0);
   o->art_visc.assign(2 * nn, 0.0);
+  o->f_bound.assign(2 * nn, 0.0);
   o->Ddev_strn.assign(nt, 0.0);
   o->countiac.assign(n2, 0);
   return o;

@@ -51,7 +51,7 @@ struct spsph_handle {
   // particle state (original order)
   double *x = nullptr, *x00 = nullptr, *rho = nullptr, *mass = nullptr, *hsml = nullptr, *mor = nullptr;
   Rec4 *NB[2] = {nullptr, nullptr}, *SB[2] = {nullptr, nullptr}, *SVb[2] = {nullptr, nullptr}, *SA = nullptr;
-  double *NA = nullptr, *NSa = nullptr, *SVa = nullptr, *av = nullptr;
+  double *NA = nullptr, *NSa = nullptr, *SVa = nullptr, *av = nullptr, *fbound = nullptr;
   double *NSb[2] = {nullptr, nullptr}, *SFb[2] = {nullptr, nullptr};
   double *stage_vel = nullptr, *stage_stress = nullptr;  // reference-layout staging for upload / download
   double *epsp = nullptr, *fdp = nullptr, *norm = nullptr, *AE = nullptr;
@@ -232,6 +232,7 @@ StatePtrs state_ptrs(spsph_handle *h, int wb) {
   s.SFbr = h->SFb[1 - wb];
   s.SVbr = h->SVb[1 - wb];
   s.av = h->av;
+  s.fbound = h->fbound;
   s.epsp = h->epsp;
   s.fdp = h->fdp;
   s.norm = h->norm;
@@ -535,12 +536,19 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     first_a = false;
   }
   const StatePtrs st = state_ptrs(h, h->cur);
+  const bool std_sph = !p.sp_sph;
+  if (p.inside_approach && p.ndummy2 > 0) {  // boundary_forces (main:742): x is frozen during the 4 stages
+    k_bound_force<<<GN, 128, 0, s>>>(P, M, h->G, S, p.ndummy2, h->fbound);
+    mark(h, KID_MOVE);
+  }
   // RK4, main:653-802
   k_rk_begin<<<(P.ntotal + 255) / 256, 256, 0, s>>>(P, st, lflag);
   mark(h, KID_RKBEGIN);
   const double f1rk[4] = {0., 0.5, 0.5, 1.0}, f2rk[4] = {1., 2., 2., 1.0};
   for (int stg = 0; stg < 4; ++stg) {
-    if (first_a) {
+    if (std_sph) {
+      k_sweep_a_std<<<(P.ntotal + 255) / 256, 256, 0, s>>>(P, st, lflag);
+    } else if (first_a) {
       k_sweep_a_sp<true, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
       k_sweep_a_node<true, false, false><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
     } else {
@@ -563,12 +571,20 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     mark(h, KID_SWEEPB, artv ? 3 : 2);
   }
   // final stress_point_update + adapt_stress2 + BCs, main:130-135
-  k_sweep_a_sp<false, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
-  k_sweep_a_node<false, false, true><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+  if (std_sph) {
+    k_sweep_a_std<<<(P.ntotal + 255) / 256, 256, 0, s>>>(P, st, lflag);
+  } else {
+    k_sweep_a_sp<false, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
+    k_sweep_a_node<false, false, true><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+  }
   mark(h, KID_SWEEPA, 2);
   // positions, main:140-182
   k_move<<<GB, 128, 0, s>>>(P, M, S, h->L, h->n1, st, h->x, h->x00, h->displ);
   mark(h, KID_MOVE);
+  if (p.update_x && std_sph) {  // main:166
+    k_sp_follow<<<(P.nnode + 255) / 256, 256, 0, s>>>(P, h->x, lflag);
+    mark(h, KID_SHIFT);
+  }
   if (p.update_x && p.sp_sph && !p.inside_approach) {
     k_shift<<<(P.nnode + 255) / 256, 256, 0, s>>>(P, st.NB, h->x, h->x_10, h->disp_10, h->bc_int, h->n_int, lflag);
     mark(h, KID_SHIFT);
@@ -607,12 +623,9 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   };
   if (p->ndimn != 2 || p->nstre != 4) return fail("only ndimn = 2, nstre = 4 (plane strain) is supported");
   if (p->skf != 1) return fail("only the cubic spline kernel (skf = 1) is supported");
-  if (!p->sp_sph) return fail("standard SPH mode (SP_SPH = F) is not supported yet");
   if (p->cont_density) return fail("cont_density = T is not supported");
   if (p->art_stress) return fail("art_stress = T is not supported");
   if (p->ifsigman != 0) return fail("ifsigman = 1 (apply_stress_free) is not supported");
-  if ((p->variant == SPSPH_VARIANT_BUI && p->inside_approach) || (p->inside_approach && p->dummy_nodes))
-    return fail("boundary_forces (inside approach with wall particles) is not supported yet");
   if (p->ntype_eco > 1 && !(p->ncrit == 2 || p->ncrit == 12))
     return fail("only ncrit = 2 (von Mises) and ncrit = 12 (Drucker-Prager) are supported");
   if (p->ntype_eco > 1 && p->ncrit == 2 && !(p->props[6] > (double)0.001f))
@@ -621,6 +634,8 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   if (p->no_bcs > 16) return fail("too many BCs");
   if (p->nnode + p->nstress != p->ntotal || p->ntotal + p->ndummy != p->ntotal2) return fail("inconsistent counts");
   if (!p->inside_approach && p->nstress != p->nnode * p->npoints) return fail("nstress != npoints*nnode");
+  if (!p->sp_sph && (p->nstress != p->nnode || p->sph_shift)) return fail("standard SPH needs nstress == nnode");
+  if (p->ndummy2 < 0 || p->ndummy2 > p->ndummy) return fail("ndummy2 out of range");
 
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -696,7 +711,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   rc |= dalloc(h, &h->x, 2 * n2) | dalloc(h, &h->x00, 2 * n2) | dalloc(h, &h->rho, n2) | dalloc(h, &h->mass, n2);
   rc |= dalloc(h, &h->hsml, n2) | dalloc(h, &h->mor, n2);
   rc |= dalloc(h, &h->NA, 2 * nn) | dalloc(h, &h->SA, ns) | dalloc(h, &h->NSa, 4 * nn) | dalloc(h, &h->SVa, 2 * ns);
-  rc |= dalloc(h, &h->av, 2 * nn);
+  rc |= dalloc(h, &h->av, 2 * nn) | dalloc(h, &h->fbound, 2 * nn);
   for (int b = 0; b < 2; ++b) {
     rc |= dalloc(h, &h->NB[b], nn) | dalloc(h, &h->SB[b], ns) | dalloc(h, &h->NSb[b], 4 * nn);
     rc |= dalloc(h, &h->SFb[b], 4 * ns) | dalloc(h, &h->SVb[b], ns);
@@ -728,6 +743,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   CUDA_TRY(cudaMemset(h->nall, 0, T * sizeof(int)));
   CUDA_TRY(cudaMemset(h->AE, 0, 5 * nt * sizeof(double)));
   CUDA_TRY(cudaMemset(h->norm, 0, nt * sizeof(double)));
+  CUDA_TRY(cudaMemset(h->fbound, 0, 2 * nn * sizeof(double)));
   return 0;
 }
 
@@ -1015,7 +1031,7 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
   D.lo = planes[rank];
   D.hi = planes[rank + 1];
   D.H = (double)halo_cells * 2.0 * hmax;
-  D.sp_follows_node = (p.sp_sph && !p.inside_approach) ? 1 : 0;
+  D.sp_follows_node = (!p.inside_approach) ? 1 : 0;  // outside approach and standard SPH
   D.cap = halo_capacity;
   if (nranks > 1 && (D.hi - D.lo) < D.H && rank > 0 && rank < nranks - 1) {
     h->err = "multi-GPU: slab thinner than the halo distance";

@@ -47,6 +47,7 @@ struct StatePtrs {
   double *SFb;  // (4, nstress)
   Rec4 *SVb;    // [nstress] {vx, vy, m/rho, -}
   double *av;   // (2, nnode) artificial viscosity acceleration of the current stage (k_artvisc -> k_sweep_b_node)
+  double *fbound;  // (2, nnode) boundary_forces of the current step (zero unless the inside approach has walls)
   // read side of a format-B -> format-B sweep (the SPH_shift interpolation): the other B buffer set
   const Rec4 *NBr, *SVbr;
   const double *NSbr, *SFbr;
@@ -808,8 +809,9 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
     av1 = a.x;
     av2 = a.y;
   }
-  const double r1 = -dv1 + sg1 + av1 + 0.0 + 0.0;  // + f_bound + art_force (both zero here, main:763-764)
-  const double r2 = -dv2 + sg2 + av2 + 0.0 + 0.0;
+  const double2 fb = ld2(st.fbound, id);           // f_bound (main:764): zero unless boundary_forces ran
+  const double r1 = -dv1 + sg1 + av1 + fb.x + 0.0;  // ... + art_force (zero: art_stress = F)
+  const double r2 = -dv2 + sg2 + av2 + fb.y + 0.0;
   double2 rk = ld2(st.RKv, id);
   rk.x = rk.x + f2 * r1;
   rk.y = rk.y + f2 * r2;
@@ -830,6 +832,116 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
   st4(st.NSa, id, sn);
 }
 
+
+// ------------------------------------------------------------------------------------------------------
+// Standard SPH mode (SP_SPH = F): stress_point_update degenerates to copies between a velocity particle and the
+// stress particle that shadows it (main:472-480); no adapt_stress2 / BCs follow it (main:720-723,132-135).
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_sweep_a_std(DevParams P, StatePtrs st, const int *__restrict__ lflag) {
+  const int id = blockIdx.x * blockDim.x + threadIdx.x;
+  if (id >= P.ntotal) return;
+  if (lflag && lflag[id] == 0) return;
+  if (id < P.nnode) {  // stress(:,i) = stress(:,nnode+i); Internal_Vars(1,i) = Internal_Vars(1,nnode+i)
+    const double2 v = ld2(st.NA, id);
+    const Rec4 s = ldrec(st.SA, id);
+    strec(st.NB, id, v.x, v.y, st.mass[id], st.rho[id]);
+    st4(st.NSb, id, Stress4{s.a, s.b, s.c, s.d});
+    st.epsp[id] = st.epsp[P.nnode + id];
+  } else {             // vel(:,nnode+i) = vel(:,i)
+    const int ks = id - P.nnode;
+    const double2 v = ld2(st.NA, ks);
+    const Rec4 s = ldrec(st.SA, ks);
+    strec(st.SVb, ks, v.x, v.y, st.mor[id], 0.0);
+    st4(st.SFb, ks, Stress4{s.a, s.b, s.c, s.d});
+    const double rr = st.rho[id];
+    const double r2 = rr * rr;
+    strec(st.SB, ks, s.a / r2, s.b / r2, s.c / r2, st.mass[id]);
+  }
+}
+// x(:,nnode+1:ntotal) = x(:,1:nnode), main:166
+__global__ void k_sp_follow(DevParams P, double *__restrict__ x, const int *__restrict__ lflag) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P.nnode) return;
+  if (lflag && lflag[i] == 0) return;
+  st2(x, P.nnode + i, ld2(x, i));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// boundary_forces, main:1039-1165 (branch test == 2): repulsion of a velocity particle by the innermost layer of
+// wall particles; fp32 locals, fp64 accumulation in ascending wall-particle number. Only wall particles closer
+// than 0.75*dx contribute a non-zero term, so the brute-force double loop becomes a 3x3-cell query.
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_bound_force(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, int ndummy2,
+                              double *__restrict__ fbound) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= M.nn) return;
+  const int id = S.order[0][k];
+  const int c = S.cell[0][k];
+  double f1 = 0.0, f2acc = 0.0;
+  if (c >= 0) {
+    const double2 pp = S.pos[0][k];
+    const double hp = S.h[0][k];
+    const int ndx = G->ndivx[0], ndy = G->ndivx[1];
+    const int cy = c / ndx, cx = c - cy * ndx;
+    constexpr int MAXC = 16;
+    int cid[MAXC];
+    double tx[MAXC], ty[MAXC];
+    int n = 0;
+    const float d0 = (float)(P.dx / 2.);
+    const float cs = 20.f;
+    for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy)
+      for (int jx = max(cx - 1, 0); jx <= min(cx + 1, ndx - 1); ++jx) {
+        const int cq = jy * ndx + jx;
+        for (int q = S.start[2][cq]; q < S.start[2][cq + 1]; ++q) {
+          const int j = S.order[2][q];
+          if (j >= P.ntotal + ndummy2) continue;  // only the innermost wall layer (main:1119-1121)
+          const double2 pq = S.pos[2][q];
+          const float r0 = (float)(pp.x - pq.x), r1 = (float)(pp.y - pq.y);
+          const float r2 = sqrtf(r0 * r0 + r1 * r1);
+          if (!(r2 > 0 && r2 < 1.5f * d0)) continue;  // f2 = 0: the term is (+-)0 and leaves the sum unchanged
+          const float f2 = 1 - (r2 / (1.5f * d0));
+          const float h = (float)(0.5 * (hp + S.h[2][q]));
+          const float rb = r2 / (0.75f * h);
+          float f;
+          if (0 < rb && rb <= 2.f / 3.f)
+            f = 2.f / 3.f;
+          else if (2.f / 3.f < rb && rb <= 1)
+            f = 2 * rb - 1.5f * (rb * rb);
+          else if (1 < rb && rb < 2)
+            f = 0.5f * ((2 - rb) * (2 - rb));
+          else
+            f = 0.f;
+          const float pre = (0.01f * (cs * cs)) * f2 * f;
+          if (n < MAXC) {
+            cid[n] = j;
+            tx[n] = (double)(pre * (r0 / (r2 * r2)));
+            ty[n] = (double)(pre * (r1 / (r2 * r2)));
+            ++n;
+          }
+        }
+      }
+    // ascending wall-particle number = the reference's loop order (j outer)
+    for (int a = 1; a < n; ++a) {
+      const int ci = cid[a];
+      const double ax = tx[a], ay = ty[a];
+      int b = a - 1;
+      while (b >= 0 && cid[b] > ci) {
+        cid[b + 1] = cid[b];
+        tx[b + 1] = tx[b];
+        ty[b + 1] = ty[b];
+        --b;
+      }
+      cid[b + 1] = ci;
+      tx[b + 1] = ax;
+      ty[b + 1] = ay;
+    }
+    for (int a = 0; a < n; ++a) {
+      f1 = f1 + tx[a];
+      f2acc = f2acc + ty[a];
+    }
+  }
+  st2(fbound, id, make_double2(f1, f2acc));
+}
 
 // ------------------------------------------------------------------------------------------------------
 // Position update, main:140-182: XSPH_update (main:189-239) or the fp32 mid-velocity rule; displ.

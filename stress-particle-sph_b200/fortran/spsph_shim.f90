@@ -22,6 +22,7 @@ module spsph_c_api
      integer(c_int32_t) :: struct_bytes, variant
      integer(c_int32_t) :: ndimn, nstre
      integer(c_int32_t) :: nnode, nstress, ntotal, ntotal2, ndummy
+     integer(c_int32_t) :: ndummy2
      integer(c_int32_t) :: npoints
      integer(c_int32_t) :: sp_sph, inside_approach, sph_shift, vel_vector
      integer(c_int32_t) :: shift_update, dummy_nodes
@@ -191,7 +192,7 @@ contains
     prm%variant = variant
     prm%ndimn = ndimn; prm%nstre = nstre
     prm%nnode = nnode; prm%nstress = nstress; prm%ntotal = ntotal; prm%ntotal2 = ntotal2
-    prm%ndummy = ntotal2 - ntotal; prm%npoints = npoints
+    prm%ndummy = ntotal2 - ntotal; prm%ndummy2 = ndummy2; prm%npoints = npoints
     prm%sp_sph = merge(1, 0, SP_SPH); prm%inside_approach = merge(1, 0, inside_approach)
     prm%sph_shift = merge(1, 0, SPH_shift); prm%vel_vector = merge(1, 0, vel_vector)
     prm%shift_update = shift_update; prm%dummy_nodes = merge(1, 0, dummy_nodes)

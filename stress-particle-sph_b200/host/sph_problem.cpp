@@ -276,6 +276,7 @@ Problem load_problem(const std::string &dir, int variant) {
       ndummy2 += ndiv_wall[i];
     }
     ndummy = nrow * ndummy2;
+    p.ndummy2 = ndummy2;
     x_dummy.assign(2 * (size_t)ndummy, 0.0);
     hor_dummy.assign(ndummy, 0.f);
     wallpos_dummy.assign(ndummy, 0.f);

@@ -17,7 +17,7 @@ class Params(C.Structure):
     _fields_ = (
         [("struct_bytes", C.c_int32), ("variant", C.c_int32)]
         + [(n, C.c_int32) for n in (
-            "ndimn", "nstre", "nnode", "nstress", "ntotal", "ntotal2", "ndummy", "npoints",
+            "ndimn", "nstre", "nnode", "nstress", "ntotal", "ntotal2", "ndummy", "ndummy2", "npoints",
             "sp_sph", "inside_approach", "sph_shift", "vel_vector", "shift_update", "dummy_nodes",
             "skf", "sle", "cspm", "update_x", "xsph", "cont_density", "art_stress",
             "ntype_eco", "ncrit", "ntype_solid", "no_bcs", "ifsigman", "ic_grav", "tcurve_grav",

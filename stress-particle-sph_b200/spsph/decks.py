@@ -97,13 +97,15 @@ def write_deck(directory, spec):
 
 # ---- the three shipped example problems (values from example_problems/*/{input.txt,*.dat,*.pts}) ----------
 
-def bui_spec(dx=0.1, dt=1.5e-4, maxtimestep=10, walls=None):
-    """soil_failure_bui_et_al_2008/outside_approach/velocity_vector_update (== the top-level input.txt)."""
+def bui_spec(dx=0.1, dt=1.5e-4, maxtimestep=10, walls=None, mode="vel_vector", npoints=2):
+    """soil_failure_bui_et_al_2008. mode: "vel_vector" = outside_approach/velocity_vector_update (== the top-level
+    input.txt), "outside" = outside_approach/, "inside" = inside_approach/SP<npoints>, "standard" = standard_sph/."""
     if walls is None:
         walls = [(1, -0.1, -0.1, 2.1), (2, -0.1, -0.3, 9)]
     return dict(
         name="co_soil", variant="bui", title="cohesive_soil_failure_Bui_2008", ntype_solid=2,
-        inside_approach=False, npoints=2, sph_shift=True, vel_vector=True, shift_update=1,
+        sp_sph=(mode != "standard"), inside_approach=(mode == "inside"), npoints=npoints, sph_shift=True,
+        vel_vector=(mode == "vel_vector"), shift_update=1,
         rx_factor=0.3333333333333, ry_factor=0.3333333333333, disp_tol=0.125, sml=1.2,
         blocks=[dict(dt=dt, time_end=2.5, maxtimestep=maxtimestep, print_step=1, save_step=1, plot_step=1)],
         props=[2, 12, 1.8e06, 0.3, 1., 1850, 2000., 0, 0., 5., 1., 1],
@@ -117,36 +119,41 @@ _VS_BCS = [(1, 5, 1, 0, 0, 0, 0, 0), (2, 6, 1, 0, 0, 0, 0, 0), (3, 1, 1, 0, 0, 0
            (5, 2, 1, 0, 0, 0, 0, 0)]
 
 
-def vertical_slope_spec(dx=0.5, dt=0.001, width=10., maxtimestep=10000000):
-    """vertical_slope (elastic_cut): elastic block, CSPM, damping, segment BCs; `width` stretches it in x."""
+def vertical_slope_spec(dx=0.5, dt=0.001, width=10., maxtimestep=10000000, npoints=1, standard=False):
+    """vertical_slope (elastic_cut): elastic block, CSPM, damping, segment BCs; `width` stretches it in x.
+    npoints = 1,2,3 -> SP1/SP2/SP3 (the top-level deck is SP1); standard -> standard/ (SP_SPH = F)."""
     w = width
     segs = [(0., 0., w, 0., 1), (0., 0., w, 0., 2), (0, 0.5, 0., 10., 1), (0, 0.5, 0., 10., 4),
             (0., 10., w, 10., 5), (0., 10., w, 10., 4), (w, 0.5, w, 10., 3), (w, 0.5, w, 10., 4)]
     return dict(
         name="elastic_cut", variant="vs", title="square_elastic_vertical_cut",
-        inside_approach=True, npoints=1, sml=0.8,
+        sp_sph=not standard, inside_approach=True, npoints=npoints, sml=0.8,
         blocks=[dict(dt=dt, time_end=2, maxtimestep=maxtimestep)],
         props=[1, 2, 8.e07, 0.3, 1., 2.e3, 200000., 0, 0., 2, 1., 1],
         bcs=_VS_BCS, segments=segs, curves=[([0, 1, 100], [0, 1, 1])], domain=[-1, -1, max(41, w + 31), 41],
         cspm=True, update_x=False, xsph=False, sle=2, damping=50, alpha=0, beta=0,
-        gravity=(0., -9.81, 1, 1.), geom=dict(x1=0, x4=w, y1=0, y4=10, dx=dx, dy=dx))
+        gravity=(0., -9.81, 1, 1.), geom=dict(x1=0, x4=w, y1=0, y4=10, dx=dx, dy=dx),
+        out=[1] * 7 + [0, 0, 0])
 
 
-def strain_localisation_spec(dx=0.0125, dt=0.00001, maxtimestep=10000000):
-    """strain_localisation_in_soil_sample (localisation): von-Mises Perzyna with softening, CSPM, BC curves."""
+def strain_localisation_spec(dx=0.0125, dt=0.00001, maxtimestep=10000000, npoints=1, standard=False):
+    """strain_localisation_in_soil_sample (localisation): von-Mises Perzyna with softening, CSPM, BC curves.
+    npoints = 1,2,3 -> SP1/SP2/SP3; standard -> standard/ (SP_SPH = F, alpha = beta = 0.5)."""
     bcs = [(1, 5, 1, 0, 0, 0, 0, 0), (2, 6, 1, 0, 0, 0, 0, 0), (3, 1, 2, 0, 0, 0, 0, 0), (4, 3, 1, 0, 0, 0, 0, 0),
            (5, 6, 1, 1, 0, 0, 0, 0)]
     segs = [(0., 0., 0., 1., 1), (0., 0., 0., 1., 4), (0., 1., 0.5, 1., 1), (0., 1., 0.5, 1., 5),
             (0.5, 0., 0.5, 1., 3), (0.5, 0., 0.5, 1., 4), (0., 0., 0.5, 0., 1), (0., 0., 0.5, 0., 2)]
     return dict(
         name="localisation", variant="sl", title="strain_localisation_test",
-        inside_approach=True, npoints=1, sml=1.2,
+        sp_sph=not standard, inside_approach=True, npoints=npoints, sml=1.2,
         blocks=[dict(dt=dt, time_end=0.021, maxtimestep=maxtimestep)],
         props=[2, 2, 8.e07, 0.25, 1., 2.e3, 5.e5, -8.e06, 0., 50., 1., 1],
         bcs=bcs, segments=segs,
         curves=[([0., 0.0005, 0.0005, 0.2, 1], [0, 1, 1, 1, 1]), ([0., 0.005, 0.0051, 1], [1.0, 1.0, 1.0, 1.0])],
-        domain=[-1, -1, 41, 41], cspm=True, update_x=True, xsph=False, sle=2, damping=0, alpha=0.0, beta=0.0,
-        gravity=None, out=[0, 0, 1, 0, 1, 1, 1, 0, 0, 0], geom=dict(x1=0, x4=0.5, y1=0, y4=1, dx=dx, dy=dx))
+        domain=[-1, -1, 41, 41], cspm=True, update_x=True, xsph=False, sle=2, damping=0,
+        alpha=0.5 if standard else 0.0, beta=0.5 if standard else 0.0,
+        gravity=None, out=[0, 0, 1, 0, 0, 0, 1, 0, 0, 0] if standard else [0, 0, 1, 0, 1, 1, 1, 0, 0, 0],
+        geom=dict(x1=0, x4=0.5, y1=0, y4=1, dx=dx, dy=dx))
 
 
 # ---- synthetic refined problems (BASELINE.json configs 4 and 5; SURVEY.md section 8d) ---------------------

@@ -136,3 +136,45 @@ def test_fill_overflow_path(deck_dir, monkeypatch):
     eng.run(1, 0.0, dt, 40)
     orc.run(1, 0.0, dt, 40)
     _compare(eng.download(), orc.download(), prob.params.ntotal, "bui, fill overflow path, 40 steps")
+
+
+# every other input set the reference ships (16 runnable input sets), regenerated by the deck
+# writer: outside approach with fixed re-seating, standard SPH (SP_SPH = F), inside approach with 1/2/3 stress
+# particles per cell (with boundary_forces against the walls in the Bui problem)
+VARIANTS = [("bui", dict(mode="outside")), ("bui", dict(mode="standard")), ("bui", dict(mode="inside", npoints=1)),
+            ("bui", dict(mode="inside", npoints=2)), ("bui", dict(mode="inside", npoints=3)),
+            ("vs", dict(npoints=2)), ("vs", dict(npoints=3)), ("vs", dict(standard=True)),
+            ("sl", dict(npoints=2)), ("sl", dict(npoints=3)), ("sl", dict(standard=True))]
+
+
+@pytest.mark.parametrize("kind,kw", VARIANTS, ids=[f"{k}-{'-'.join(f'{a}{b}' for a, b in v.items())}" for k, v in VARIANTS])
+def test_shipped_variants_60_steps(deck_dir, kind, kw):
+    import spsph
+    from oracle_binding import Oracle
+    prob = spsph.load(deck_dir(kind, **kw), kind)
+    dt = prob.blocks[0]["dt"]
+    eng, orc = spsph.Engine(prob), Oracle(prob)
+    eng.run(1, 0.0, dt, 60)
+    orc.run(1, 0.0, dt, 60)
+    assert eng.pair_stats() == orc.pair_stats()
+    _compare(eng.download(), orc.download(), prob.params.ntotal, f"{kind} {kw} after 60 steps")
+    _pairs_equal(eng.pairs(), orc.pairs(), f"{kind} {kw} step 60")
+
+
+def test_boundary_forces_active(deck_dir):
+    """inside approach against walls, long enough (1500 steps) for bottom particles to come within 0.75*dx of
+    the innermost wall layer, where boundary_forces (main:1039-1165) is non-zero"""
+    import spsph
+    from oracle_binding import Oracle
+    prob = spsph.load(deck_dir("bui", mode="inside", npoints=1), "bui")
+    p = prob.params
+    dt = prob.blocks[0]["dt"]
+    eng, orc = spsph.Engine(prob), Oracle(prob)
+    eng.run(1, 0.0, dt, 1500)
+    orc.run(1, 0.0, dt, 1500)
+    a, b = eng.download(), orc.download()
+    _compare(a, b, p.ntotal, "bui inside SP1 after 1500 steps")
+    from scipy.spatial import cKDTree
+    walls = b["x"][p.ntotal:p.ntotal + p.ndummy2]
+    d, _ = cKDTree(walls).query(b["x"][:p.nnode])
+    assert (d < 0.75 * p.dx).any(), "no velocity particle came close enough to a wall to feel boundary_forces"

@@ -25,6 +25,48 @@ def test_regenerated_decks_equal_shipped_inputs(deck_dir, kind):
         assert np.array_equal(a.arrays[k], b.arrays[k]), k
 
 
+VARIANT_DIRS = [
+    ("bui", "soil_failure_bui_et_al_2008", dict()),
+    ("bui", "soil_failure_bui_et_al_2008/outside_approach", dict(mode="outside")),
+    ("bui", "soil_failure_bui_et_al_2008/standard_sph", dict(mode="standard")),
+    ("bui", "soil_failure_bui_et_al_2008/inside_approach/SP1", dict(mode="inside", npoints=1)),
+    ("bui", "soil_failure_bui_et_al_2008/inside_approach/SP2", dict(mode="inside", npoints=2)),
+    ("bui", "soil_failure_bui_et_al_2008/inside_approach/SP3", dict(mode="inside", npoints=3)),
+    ("vs", "vertical_slope/SP1", dict()), ("vs", "vertical_slope/SP2", dict(npoints=2)),
+    ("vs", "vertical_slope/SP3", dict(npoints=3)), ("vs", "vertical_slope/standard", dict(standard=True)),
+    ("sl", "strain_localisation_in_soil_sample/SP1", dict()),
+    ("sl", "strain_localisation_in_soil_sample/SP2", dict(npoints=2)),
+    ("sl", "strain_localisation_in_soil_sample/SP3", dict(npoints=3)),
+    ("sl", "strain_localisation_in_soil_sample/standard", dict(standard=True)),
+]
+
+
+@pytest.mark.parametrize("kind,path,kw", VARIANT_DIRS, ids=[p for _, p, _ in VARIANT_DIRS])
+@pytest.mark.skipif(not os.path.isdir(REF), reason="reference checkout not present")
+def test_all_shipped_input_sets_regenerate(deck_dir, kind, path, kw):
+    """all 16 input sets of the reference: the deck writer reproduces particles, parameters and time blocks"""
+    import spsph
+    d = os.path.join(REF, path)
+    if not os.path.exists(os.path.join(d, "input.txt")):
+        pytest.skip("no input.txt")
+    src = d
+    name = {"bui": "co_soil", "vs": "elastic_cut", "sl": "localisation"}[kind]
+    if not os.path.exists(os.path.join(d, name + ".dat")):  # top-level Bui input.txt uses the velocity-vector deck
+        import shutil
+        import tempfile
+        src = tempfile.mkdtemp()
+        shutil.copy(os.path.join(d, "input.txt"), src)
+        base = os.path.join(REF, REF_DIRS[kind])
+        for ext in (".dat", ".pts"):
+            shutil.copy(os.path.join(base, name + ext), src)
+    a = spsph.load(src, kind)
+    b = spsph.load(deck_dir(kind, **kw), kind)
+    assert bytes(a.params) == bytes(b.params)
+    assert [(x["dt"], x["time_end"]) for x in a.blocks] == [(x["dt"], x["time_end"]) for x in b.blocks]
+    for k in a.arrays:
+        assert np.array_equal(a.arrays[k], b.arrays[k]), k
+
+
 def test_particle_counts_match_survey(deck_dir):
     """counts derived independently from the input files."""
     import spsph
