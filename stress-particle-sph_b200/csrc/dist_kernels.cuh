@@ -188,23 +188,31 @@ __global__ void k_halo_own(DevParams P, DistGeom D, const double *__restrict__ x
 
 // local bounding box -> 6 values encoded for a single MAX all-reduce: {-xmin, -ymin, xmax, ymax, hmax, -hmin}
 __global__ void k_bbox_final(int nblocks, const double *__restrict__ partial, double *__restrict__ bb6) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double mn[2] = {1.e+10, 1.e+10}, mx[2] = {-1.e+10, -1.e+10}, hmx = 0.0, hmn = 1.e+300;
-  for (int b = 0; b < nblocks; ++b) {
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;  // one warp; min / max are order-independent
+  double mn0 = 1.e+10, mn1 = 1.e+10, mx0 = -1.e+10, mx1 = -1.e+10, hmx = 0.0, hmn = 1.e+300;
+  for (int b = threadIdx.x; b < nblocks; b += 32) {
     const double *o = partial + 6 * b;
-    mn[0] = fmin(mn[0], o[0]);
-    mn[1] = fmin(mn[1], o[1]);
-    mx[0] = fmax(mx[0], o[2]);
-    mx[1] = fmax(mx[1], o[3]);
+    mn0 = fmin(mn0, o[0]);
+    mn1 = fmin(mn1, o[1]);
+    mx0 = fmax(mx0, o[2]);
+    mx1 = fmax(mx1, o[3]);
     hmx = fmax(hmx, o[4]);
     hmn = fmin(hmn, o[5]);
   }
-  bb6[0] = -mn[0];
-  bb6[1] = -mn[1];
-  bb6[2] = mx[0];
-  bb6[3] = mx[1];
-  bb6[4] = hmx;
-  bb6[5] = -hmn;
+  mn0 = warp_min(mn0);
+  mn1 = warp_min(mn1);
+  mx0 = warp_max(mx0);
+  mx1 = warp_max(mx1);
+  hmx = warp_max(hmx);
+  hmn = warp_min(hmn);
+  if (threadIdx.x == 0) {
+    bb6[0] = -mn0;
+    bb6[1] = -mn1;
+    bb6[2] = mx0;
+    bb6[3] = mx1;
+    bb6[4] = hmx;
+    bb6[5] = -hmn;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------

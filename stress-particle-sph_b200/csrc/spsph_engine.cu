@@ -302,7 +302,10 @@ void step_scalars(spsph_handle *h, int itimestep, double time_sph, double dt) {
 }
 
 int ensure_lists(spsph_handle *h, long long t0, long long tC, long long tD) {
-  auto grow = [&](long long need, long long &cap) { return need > cap ? (cap = need + need / 8 + 1024, true) : false; };
+  // 1024 entries of slack: the sweeps stream whole groups of rows and may read (never use) up to 7 rows past a slice
+  auto grow = [&](long long need, long long &cap) {
+    return need + 1024 > cap ? (cap = need + need / 8 + 2048, true) : false;
+  };
   if (grow(t0, h->cap0)) {
     cudaFree(h->L.idx0);
     cudaFree(h->L.w0);
@@ -726,7 +729,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   rc |= dalloc(h, &h->bc_int, nn) | dalloc(h, &h->bc_or_not, nt) | dalloc(h, &h->bc_info, 8 * nt);
   rc |= dalloc(h, &h->if_out, n2);
   rc |= dalloc(h, &h->G, 1);
-  h->bbox_blocks = 296;
+  h->bbox_blocks = 148 * 8;
   rc |= dalloc(h, &h->bbox_partial, 6 * (size_t)h->bbox_blocks);
   rc |= dalloc(h, &h->which_cell, n2) | dalloc(h, &h->tmp_ids, 3 * n2) | dalloc(h, &h->order, 3 * n2);
   rc |= dalloc(h, &h->scell, 3 * n2) | dalloc(h, &h->pos_of, n2) | dalloc(h, &h->nout, 8) | dalloc(h, &h->bb6, 8);

@@ -93,6 +93,10 @@ constexpr int UNR = 4;  // list entries in flight per thread
 #define SPSPH_MINB 4      // min resident blocks per SM requested from ptxas for the sweep kernels
 #endif
 constexpr int ELL_GROUP = 4;  // rows per cp.async group
+#ifndef SPSPH_ELL_SUB
+#define SPSPH_ELL_SUB 4
+#endif
+constexpr int ELL_SUB = SPSPH_ELL_SUB;  // entries gathered + consumed together (in flight per thread)
 constexpr int ELL_NG = 4;     // groups in the ring (16 rows = 2 KB per array per warp in flight)
 
 // The list rows are read exactly once per sweep: L2 evict-first, so that the 0.7-1.3 GB streamed per sweep do
@@ -122,19 +126,22 @@ __device__ __forceinline__ void cp_async_wait() {
 // (warp-uniform), `cnt` the calling lane's own list length. gather(q) -> R fetches the partner record (q < 0:
 // past the end); compute(q[4], pay[NARR-1][4], rec[4], nvalid) consumes one group of entries in list order
 // (pay: raw 32-bit payloads of arrays 1..NARR-1; entries u >= nvalid are past the end of this lane's list).
-template <int NARR, int NG, class R, class GatherF, class ComputeF>
+template <int NARR, int NG, class R, int GR = ELL_GROUP, int SUB = ELL_SUB, class GatherF, class ComputeF>
 __device__ __forceinline__ void ell_stream(const int *const *arr, size_t slice_off, int rows, int cnt, int *smw,
                                            GatherF gather, ComputeF compute) {
+  static_assert(GR % 4 == 0 && GR % SUB == 0, "group = whole 16-byte cp.async rows, consumed in SUB-entry parts");
   const int lane = threadIdx.x & 31;
-  const int ng = (rows + ELL_GROUP - 1) / ELL_GROUP;
+  const int ng = (rows + GR - 1) / GR;
   if (ng == 0) return;
   const unsigned long long pol = l2_policy_evict_first();
   auto issue = [&](int g) {
     if (g < ng) {
 #pragma unroll
       for (int a = 0; a < NARR; ++a)
-        cp_async16(smw + ((g % NG) * NARR + a) * (ELL_GROUP * 32) + lane * 4,
-                   arr[a] + slice_off + (size_t)g * (ELL_GROUP * 32) + lane * 4, pol);
+#pragma unroll
+        for (int c = 0; c < GR / 4; ++c)
+          cp_async16(smw + ((g % NG) * NARR + a) * (GR * 32) + c * 128 + lane * 4,
+                     arr[a] + slice_off + (size_t)g * (GR * 32) + c * 128 + lane * 4, pol);
     }
     cp_async_commit();
   };
@@ -143,19 +150,22 @@ __device__ __forceinline__ void ell_stream(const int *const *arr, size_t slice_o
   for (int g = 0; g < ng; ++g) {
     cp_async_wait<NG - 1>();
     __syncwarp();
-    const int *sl = smw + ((g % NG) * NARR) * (ELL_GROUP * 32);
-    int q[ELL_GROUP], pay[NARR > 1 ? NARR - 1 : 1][ELL_GROUP];
-    R cur[ELL_GROUP];
+    const int *sl = smw + ((g % NG) * NARR) * (GR * 32);
 #pragma unroll
-    for (int u = 0; u < ELL_GROUP; ++u) {
-      q[u] = sl[u * 32 + lane];
-      cur[u] = gather((g * ELL_GROUP + u) < cnt ? q[u] : -1);
+    for (int hh = 0; hh < GR / SUB; ++hh) {
+      int q[SUB], pay[NARR > 1 ? NARR - 1 : 1][SUB];
+      R cur[SUB];
+#pragma unroll
+      for (int u = 0; u < SUB; ++u) {
+        q[u] = sl[(hh * SUB + u) * 32 + lane];
+        cur[u] = gather((g * GR + hh * SUB + u) < cnt ? q[u] : -1);
+      }
+#pragma unroll
+      for (int a = 1; a < NARR; ++a)
+#pragma unroll
+        for (int u = 0; u < SUB; ++u) pay[a - 1][u] = sl[a * (GR * 32) + (hh * SUB + u) * 32 + lane];
+      compute(q, pay, cur, cnt - g * GR - hh * SUB);
     }
-#pragma unroll
-    for (int a = 1; a < NARR; ++a)
-#pragma unroll
-      for (int u = 0; u < ELL_GROUP; ++u) pay[a - 1][u] = sl[a * (ELL_GROUP * 32) + u * 32 + lane];
-    compute(q, pay, cur, cnt - g * ELL_GROUP);
     __syncwarp();
     issue(g + NG);
   }
@@ -166,6 +176,14 @@ __device__ __forceinline__ int warp_max_i(int v) {
   return v;
 }
 #define ELL_SMEM(NARR, NG) ((NG) * (NARR) * ELL_GROUP * 32)  // ints per warp
+#define ELL_SMEM_G(NARR, NG, GR) ((NG) * (NARR) * (GR) * 32)
+#ifndef SPSPH_A_GR
+#define SPSPH_A_GR 4
+#endif
+#ifndef SPSPH_A_NG
+#define SPSPH_A_NG 4
+#endif
+constexpr int A_GR = SPSPH_A_GR, A_NG = SPSPH_A_NG;  // sweep A: rows per group (all in flight per thread), ring depth
 
 // state format conversions at the boundary of the time loop ---------------------------------------------
 // pack: reference-layout vel/stress (upload) -> format B
@@ -284,12 +302,12 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   double vtx = 0.0, vty = 0.0, nrm = 0.0;
   {
     constexpr int NARR = FIRST ? 4 : 3;
-    __shared__ __align__(16) int smem[4 * ELL_SMEM(NARR, ELL_NG)];
+    __shared__ __align__(16) int smem[4 * ELL_SMEM_G(NARR, A_NG, A_GR)];
     const int *arrs[4] = {L.idx0, L.h0lo, L.h0hi, reinterpret_cast<const int *>(L.w0)};
     const double *__restrict__ NAv = st.NA;
     const Rec4 *__restrict__ NBv = st.NBr;
-    ell_stream<NARR, ELL_NG, double2>(
-        arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(NARR, ELL_NG),
+    ell_stream<NARR, A_NG, double2, A_GR, A_GR>(
+        arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM_G(NARR, A_NG, A_GR),
         [&](int q) {
           const int qq = (q < 0 || q >= P.nnode) ? 0 : q;
           if (FROMB) {
@@ -298,9 +316,9 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
           }
           return ld2(NAv, qq);
         },
-        [&](const int(&q)[ELL_GROUP], const int(&pay)[NARR - 1][ELL_GROUP], const double2(&r)[ELL_GROUP], int nvalid) {
+        [&](const int(&q)[A_GR], const int(&pay)[NARR - 1][A_GR], const double2(&r)[A_GR], int nvalid) {
 #pragma unroll
-          for (int u = 0; u < ELL_GROUP; ++u) {
+          for (int u = 0; u < A_GR; ++u) {
             const bool ok = (u < nvalid) && (q[u] < P.nnode);  // dummy partners (type 9) take no part
             const double h2 = h0_of(pay[0][u], pay[1][u]);     // (mass(i)/rho(i))*w, main:431
             const double tx = vtx + r[u].x * h2, ty = vty + r[u].y * h2;
@@ -362,10 +380,10 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
       double ep;
     };
     constexpr int NARR = FIRST ? 4 : 3;
-    __shared__ __align__(16) int smem[4 * ELL_SMEM(NARR, ELL_NG)];
+    __shared__ __align__(16) int smem[4 * ELL_SMEM_G(NARR, A_NG, A_GR)];
     const int *arrs[4] = {L.idx0, L.h0lo, L.h0hi, reinterpret_cast<const int *>(L.w0)};
-    ell_stream<NARR, ELL_NG, RecS>(
-        arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(NARR, ELL_NG),
+    ell_stream<NARR, A_NG, RecS, A_GR, A_GR>(
+        arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM_G(NARR, A_NG, A_GR),
         [&](int q) {
           const int qs = (q < 0 || q >= P.ntotal) ? 0 : q - P.nnode;
           RecS r;
@@ -373,9 +391,9 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
           r.ep = EPSP ? st.epsp[qs + P.nnode] : 0.0;
           return r;
         },
-        [&](const int(&q)[ELL_GROUP], const int(&pay)[NARR - 1][ELL_GROUP], const RecS(&r)[ELL_GROUP], int nvalid) {
+        [&](const int(&q)[A_GR], const int(&pay)[NARR - 1][A_GR], const RecS(&r)[A_GR], int nvalid) {
 #pragma unroll
-          for (int u = 0; u < ELL_GROUP; ++u) {
+          for (int u = 0; u < A_GR; ++u) {
             const bool ok = (u < nvalid) && (q[u] < P.ntotal);  // dummy partners (type 6) take no part
             const double h1 = h0_of(pay[0][u], pay[1][u]);      // (mass(j)/rho(j))*w, main:430
             const double n1 = t1 + r[u].s.a * h1, n2 = t2 + r[u].s.b * h1, n3 = t3 + r[u].s.c * h1,
@@ -489,27 +507,27 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
     ell_stream<3, ELL_NG, Rec4>(
         arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(3, ELL_NG),
         [&](int q) { return ldrec(st.NB, (q < 0 || q >= P.nnode) ? 0 : q); },
-        [&](const int(&q)[ELL_GROUP], const int(&pay)[2][ELL_GROUP], const Rec4(&r)[ELL_GROUP], int nvalid) {
+        [&](const int(&q)[ELL_SUB], const int(&pay)[2][ELL_SUB], const Rec4(&r)[ELL_SUB], int nvalid) {
           bool special = false;  // wall partner in this group (type 9), or the once-per-step CSPM matrix pass
 #pragma unroll
-          for (int u = 0; u < ELL_GROUP; ++u) special |= (u < nvalid) && (q[u] >= P.nnode);
+          for (int u = 0; u < ELL_SUB; ++u) special |= (u < nvalid) && (q[u] >= P.nnode);
           if ((FIRST && P.cspm) || __any_sync(0xffffffffu, special)) {
 #pragma unroll
-            for (int u = 0; u < ELL_GROUP; ++u)
+            for (int u = 0; u < ELL_SUB; ++u)
               if (u < nvalid) entry_slow(q[u], pay[0][u], pay[1][u], r[u]);
             return;
           }
           // branch-free path: the four entries' division chains are independent and interleave
-          double h1[ELL_GROUP], h2[ELL_GROUP];
+          double h1[ELL_SUB], h2[ELL_SUB];
 #pragma unroll
-          for (int u = 0; u < ELL_GROUP; ++u) {
+          for (int u = 0; u < ELL_SUB; ++u) {
             const double gx = (double)__int_as_float(pay[0][u]), gy = (double)__int_as_float(pay[1][u]);
             const double rr = __drcp_rn(r[u].d);
             h1[u] = div_rn(gx * r[u].c, r[u].d, rr);  // dwdx*mass(i)/rho(i), main:514
             h2[u] = div_rn(gy * r[u].c, r[u].d, rr);
           }
 #pragma unroll
-          for (int u = 0; u < ELL_GROUP; ++u) {
+          for (int u = 0; u < ELL_SUB; ++u) {
             const bool ok = u < nvalid;
             const double dvx = r[u].a - vp.x, dvy = r[u].b - vp.y;
             const double n11 = g11 + dvx * h1[u], n12 = g12 + dvx * h2[u], n21 = g21 + dvy * h1[u],
@@ -648,10 +666,10 @@ k_artvisc(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, c
   ell_stream<6, NG, Rec4>(
       arrs, (size_t)L.offC[t / SLICE], wrowsC, cntc, smem + (threadIdx.x >> 5) * ELL_SMEM(6, NG),
       [&](int q) { return ldrec(st.NB, q < 0 ? 0 : q); },
-      [&](const int(&)[ELL_GROUP], const int(&pay)[5][ELL_GROUP], const Rec4(&r)[ELL_GROUP], int nvalid) {
-        float visc[ELL_GROUP];
+      [&](const int(&)[ELL_SUB], const int(&pay)[5][ELL_SUB], const Rec4(&r)[ELL_SUB], int nvalid) {
+        float visc[ELL_SUB];
 #pragma unroll
-        for (int u = 0; u < ELL_GROUP; ++u) {  // independent per entry: interleaves
+        for (int u = 0; u < ELL_SUB; ++u) {  // independent per entry: interleaves
           const float xij = __int_as_float(pay[2][u]), yij = __int_as_float(pay[3][u]), h = __int_as_float(pay[4][u]);
           const float rho2 = (float)(0.5 * (rp + r[u].d));
           const float cs = 600.f;
@@ -664,7 +682,7 @@ k_artvisc(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, c
             visc[u] = (float)((-P.alpha * (double)cs * (double)theta + P.beta * (double)(theta * theta)) / (double)rho2);
         }
 #pragma unroll
-        for (int u = 0; u < ELL_GROUP; ++u) {  // ordered fp32 accumulation
+        for (int u = 0; u < ELL_SUB; ++u) {  // ordered fp32 accumulation
           const float gxf = __int_as_float(pay[0][u]), gyf = __int_as_float(pay[1][u]);
           const float a1 = (float)((double)acc1 + (double)(visc[u] * gxf) * r[u].c);
           const float a2 = (float)((double)acc2 + (double)(visc[u] * gyf) * r[u].c);
@@ -738,18 +756,18 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
     ell_stream<3, ELL_NG, Rec4>(
         arrs, (size_t)L.off0[sl], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(3, ELL_NG),
         [&](int q) { return ldrec(st.SB, (q < 0 || q >= P.ntotal) ? 0 : q - P.nnode); },
-        [&](const int(&q)[ELL_GROUP], const int(&pay)[2][ELL_GROUP], const Rec4(&r)[ELL_GROUP], int nvalid) {
+        [&](const int(&q)[ELL_SUB], const int(&pay)[2][ELL_SUB], const Rec4(&r)[ELL_SUB], int nvalid) {
           bool special = false;  // wall partner in this group (type 6), or the once-per-step CSPM matrix pass
 #pragma unroll
-          for (int u = 0; u < ELL_GROUP; ++u) special |= (u < nvalid) && (q[u] >= P.ntotal);
+          for (int u = 0; u < ELL_SUB; ++u) special |= (u < nvalid) && (q[u] >= P.ntotal);
           if ((FIRST && P.cspm) || __any_sync(0xffffffffu, special)) {
 #pragma unroll
-            for (int u = 0; u < ELL_GROUP; ++u)
+            for (int u = 0; u < ELL_SUB; ++u)
               if (u < nvalid) entry_slow(q[u], pay[0][u], pay[1][u], r[u]);
             return;
           }
 #pragma unroll
-          for (int u = 0; u < ELL_GROUP; ++u) {
+          for (int u = 0; u < ELL_SUB; ++u) {
             const bool ok = u < nvalid;
             const double gx = (double)__int_as_float(pay[0][u]), gy = (double)__int_as_float(pay[1][u]);
             const double c1 = so1 + r[u].a, c2 = so2 + r[u].b, c3 = so3 + r[u].c, mq = r[u].d;
@@ -971,10 +989,10 @@ k_move(DevParams P, SlotMap M, SortArrays So, ListPtrs L, const int *__restrict_
     const int sl = t0 / SLICE;
     __shared__ __align__(16) int smem[4 * ELL_SMEM(2, ELL_NG)];
     int *smw = smem + (threadIdx.x >> 5) * ELL_SMEM(2, ELL_NG);
-    auto body = [&](const int(&)[ELL_GROUP], const int(&pay)[1][ELL_GROUP], const Rec4(&r)[ELL_GROUP], int nvalid,
+    auto body = [&](const int(&)[ELL_SUB], const int(&pay)[1][ELL_SUB], const Rec4(&r)[ELL_SUB], int nvalid,
                     bool node) {
 #pragma unroll
-      for (int u = 0; u < ELL_GROUP; ++u) {
+      for (int u = 0; u < ELL_SUB; ++u) {
         const double wd = (double)__int_as_float(pay[0][u]);
         const double mr = node ? (r[u].c / r[u].d) : r[u].c;  // mass(j)/rho(j)
         const double nx = sx + mr * (r[u].a - vp.x) * wd, ny = sy + mr * (r[u].b - vp.y) * wd;
@@ -986,14 +1004,14 @@ k_move(DevParams P, SlotMap M, SortArrays So, ListPtrs L, const int *__restrict_
       const int *arrs[2] = {L.idxC, reinterpret_cast<const int *>(L.wC)};
       ell_stream<2, ELL_NG, Rec4>(
           arrs, (size_t)L.offC[sl], wrows, cnt, smw, [&](int q) { return ldrec(st.NB, q < 0 ? 0 : q); },
-          [&](const int(&q)[ELL_GROUP], const int(&pay)[1][ELL_GROUP], const Rec4(&r)[ELL_GROUP], int nvalid) {
+          [&](const int(&q)[ELL_SUB], const int(&pay)[1][ELL_SUB], const Rec4(&r)[ELL_SUB], int nvalid) {
             body(q, pay, r, nvalid, true);
           });
     } else {
       const int *arrs[2] = {L.idxD, reinterpret_cast<const int *>(L.wD)};
       ell_stream<2, ELL_NG, Rec4>(
           arrs, (size_t)L.offD[sl], wrows, cnt, smw, [&](int q) { return ldrec(st.SVb, q < 0 ? 0 : q - P.nnode); },
-          [&](const int(&q)[ELL_GROUP], const int(&pay)[1][ELL_GROUP], const Rec4(&r)[ELL_GROUP], int nvalid) {
+          [&](const int(&q)[ELL_SUB], const int(&pay)[1][ELL_SUB], const Rec4(&r)[ELL_SUB], int nvalid) {
             body(q, pay, r, nvalid, false);
           });
     }
