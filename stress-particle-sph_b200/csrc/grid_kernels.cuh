@@ -511,7 +511,10 @@ __device__ __forceinline__ RowRange row_range(int ndx, int cx, int jy) {
 // again; a particle with more partners than that raises `overflow` and the step falls back to k_fill_scan.
 constexpr int CAND_CAP = 64;
 
-__global__ void __launch_bounds__(128)
+#ifndef SPSPH_COUNT_MINB
+#define SPSPH_COUNT_MINB 8
+#endif
+__global__ void __launch_bounds__(128, SPSPH_COUNT_MINB)
 k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, int *__restrict__ n0, int *__restrict__ n1,
         int *__restrict__ nfwd_u /* unified order */, int *__restrict__ nall, int *__restrict__ w0 /* slice widths */,
         int *__restrict__ wC, int *__restrict__ wD, const int *__restrict__ lflag, int *__restrict__ cand0,
@@ -935,8 +938,14 @@ k_fill_scan(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
 }
 
 // Fill pass, fast path: the accepted partners were recorded by k_count (cand0 / cand1, list order), so every
-// thread evaluates the kernel for its entries in a dense loop, four entries in flight.
-__global__ void __launch_bounds__(128)
+// thread evaluates the kernel for its entries in a dense loop, two entries in flight at 8 blocks per SM (measured best).
+#ifndef SPSPH_FILL_MINB
+#define SPSPH_FILL_MINB 8
+#endif
+#ifndef SPSPH_FILL_U
+#define SPSPH_FILL_U 2
+#endif
+__global__ void __launch_bounds__(128, SPSPH_FILL_MINB)
 k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ n0,
        const int *__restrict__ n1, const GrowthRule *__restrict__ growth, ListPtrs L, int *__restrict__ bc_int,
        float *__restrict__ n_int, const double *__restrict__ mor, const int *__restrict__ cand0,
@@ -980,7 +989,7 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
       for (int e = 0; e < cnt1; ++e) s1 += pair_is_old(gr, up, sorted_key(S, sp, cand1[cb + (size_t)e * SLICE])) ? 1 : 0;
     }
   }
-  constexpr int U = 4;
+  constexpr int U = SPSPH_FILL_U;
   int has_dummy = 0;
   // list 0: cross-species partners, reference orientation of the gradient (pair_i - pair_j after Pint_Update)
   for (int e0 = 0; e0 < cnt0; e0 += U) {

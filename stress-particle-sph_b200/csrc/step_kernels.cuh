@@ -677,9 +677,11 @@ k_artvisc(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, c
           div_u = (float)((double)div_u + (double)yij * (vp.y - r[u].b));
           const float sq = sqrtf(xij * xij + yij * yij);
           const float theta = (h * div_u) / (sq * sq + 0.01f * (h * h));
-          visc[u] = 0.f;
-          if (div_u < 0)
-            visc[u] = (float)((-P.alpha * (double)cs * (double)theta + P.beta * (double)(theta * theta)) / (double)rho2);
+          // evaluated for every entry (no divergent branch; the four division chains interleave), kept if approaching
+          const double rho2d = (double)rho2;
+          const double num = -P.alpha * (double)cs * (double)theta + P.beta * (double)(theta * theta);
+          const float vv = (float)div_rn(num, rho2d, __drcp_rn(rho2d));
+          visc[u] = (div_u < 0) ? vv : 0.f;
         }
 #pragma unroll
         for (int u = 0; u < ELL_SUB; ++u) {  // ordered fp32 accumulation
