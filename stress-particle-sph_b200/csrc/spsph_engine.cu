@@ -43,6 +43,9 @@ struct spsph_handle {
   SlotMap M{};
   int device = 0;
   cudaStream_t stream = nullptr;
+  cudaStream_t stream2 = nullptr;  // node-side sweeps run beside the stress-particle-side ones (independent data)
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool dual = true;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::string err;
   std::vector<void *> allocs;
@@ -548,37 +551,60 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   k_rk_begin<<<(P.ntotal + 255) / 256, 256, 0, s>>>(P, st, lflag);
   mark(h, KID_RKBEGIN);
   const double f1rk[4] = {0., 0.5, 0.5, 1.0}, f2rk[4] = {1., 2., 2., 1.0};
+  // The node-side and the stress-particle-side kernel of a sweep touch disjoint outputs and only read the
+  // other side's previous-format records, so they run side by side on two streams (s2 forks from / joins s).
+  cudaStream_t s2 = h->dual ? h->stream2 : s;
+  auto fork = [&]() {
+    if (s2 != s) {
+      cudaEventRecord(h->ev_fork, s);
+      cudaStreamWaitEvent(s2, h->ev_fork, 0);
+    }
+  };
+  auto join = [&]() {
+    if (s2 != s) {
+      cudaEventRecord(h->ev_join, s2);
+      cudaStreamWaitEvent(s, h->ev_join, 0);
+    }
+  };
   for (int stg = 0; stg < 4; ++stg) {
     if (std_sph) {
       k_sweep_a_std<<<(P.ntotal + 255) / 256, 256, 0, s>>>(P, st, lflag);
-    } else if (first_a) {
-      k_sweep_a_sp<true, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
-      k_sweep_a_node<true, false, false><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
     } else {
-      k_sweep_a_sp<false, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
-      k_sweep_a_node<false, false, false><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+      fork();
+      if (first_a) {
+        k_sweep_a_sp<true, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
+        k_sweep_a_node<true, false, false><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+      } else {
+        k_sweep_a_sp<false, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
+        k_sweep_a_node<false, false, false><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+      }
+      join();
     }
     mark(h, KID_SWEEPA, 2);
     first_a = false;
     const int last = (stg == 3);
     const double f1n = last ? 0.0 : f1rk[stg + 1];
     const bool artv = (P.alpha > 0 || P.beta > 0);
-    if (artv) k_artvisc<<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n1, st);
+    fork();
+    if (artv) k_artvisc<<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n1, st);
     if (stg == 0) {
       k_sweep_b_sp<true><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last);
-      k_sweep_b_node<true><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
+      k_sweep_b_node<true><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
     } else {
       k_sweep_b_sp<false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last);
-      k_sweep_b_node<false><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
+      k_sweep_b_node<false><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
     }
+    join();
     mark(h, KID_SWEEPB, artv ? 3 : 2);
   }
   // final stress_point_update + adapt_stress2 + BCs, main:130-135
   if (std_sph) {
     k_sweep_a_std<<<(P.ntotal + 255) / 256, 256, 0, s>>>(P, st, lflag);
   } else {
+    fork();
     k_sweep_a_sp<false, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
-    k_sweep_a_node<false, false, true><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+    k_sweep_a_node<false, false, true><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+    join();
   }
   mark(h, KID_SWEEPA, 2);
   // positions, main:140-182
@@ -647,6 +673,10 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   h->device = device;
   CUDA_TRY(cudaSetDevice(device));
   CUDA_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&h->stream2, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
+  if (const char *e = getenv("SPSPH_DUAL_STREAM")) h->dual = atoi(e) != 0;
   CUDA_TRY(cudaEventCreate(&h->ev0));
   CUDA_TRY(cudaEventCreate(&h->ev1));
 
@@ -1102,6 +1132,9 @@ int spsph_destroy(spsph_handle *h) {
   if (h->status_h) cudaFreeHost(h->status_h);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->stream2) cudaStreamDestroy(h->stream2);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return 0;

@@ -16,6 +16,7 @@ ap.add_argument("--kind", default="refined_bui")
 ap.add_argument("--ncol", type=int, default=1632)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--profile", action="store_true")
+ap.add_argument("--warmup", type=int, default=0)
 a = ap.parse_args()
 d = tempfile.mkdtemp()
 if a.kind == "refined_bui":
@@ -28,9 +29,10 @@ decks.write_deck(d, spec)
 prob = spsph.load(d, var)
 eng = spsph.Engine(prob)
 dt = prob.blocks[0]["dt"]
+t0 = eng.run(1, 0.0, dt, a.warmup) if a.warmup else 0.0
 if a.profile:
     eng.profile(True)
-eng.run(1, 0.0, dt, a.steps)
+eng.run(1 + a.warmup, t0, dt, a.steps)
 ms, n = eng.last_run()
 print(f"{a.kind} ncol={a.ncol}: {prob.params.ntotal} particles, {a.steps} steps, {ms / a.steps:.3f} ms/step, "
       f"{n} launches, {eng.pair_stats()}")
