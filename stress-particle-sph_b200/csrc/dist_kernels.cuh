@@ -16,7 +16,9 @@
 
 namespace spsph {
 
-enum : int { LF_REMOTE = 0, LF_OWNED = 1, LF_GHOST = 2 };
+// LF_STALE: a ghost of the previous step waiting to be refreshed by its owner (only between k_halo_select and
+// k_list_compact; it is still on the local list, so k_halo_unpack must not append it again)
+enum : int { LF_REMOTE = 0, LF_OWNED = 1, LF_GHOST = 2, LF_STALE = 3 };
 // doubles per exchanged particle: id, x(2), vel(2), stress(4), eps_p, f_drucker, x_10(2), disp_10, displ(2), out flag, spare
 constexpr int HALO_REC = 18;
 
@@ -48,43 +50,80 @@ __global__ void k_dist_init_flags(DevParams P, DistGeom D, const double *__restr
   lflag[i] = f;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// The local list: particle numbers with lflag != LF_REMOTE, in no particular order (every consumer is
+// order-independent: min/max, per-cell counts, the deterministic in-cell ranking of k_rank). Built once from the
+// flags, then maintained per step by k_halo_select (marks stale ghosts) -> k_halo_unpack (appends newcomers) ->
+// k_list_compact (drops ghosts that were not refreshed), so no per-step pass scales with the global count.
+// ------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void list_append_warp(bool keep, int i, int *__restrict__ ids, int *__restrict__ n) {
+  const unsigned act = __activemask();
+  const unsigned m = __ballot_sync(act, keep);
+  if (!m) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(n, __popc(m));
+  base = __shfl_sync(act, base, leader);
+  if (keep) ids[base + __popc(m & ((1u << lane) - 1))] = i;
+}
+__global__ void k_list_build(int n2, const int *__restrict__ lflag, int *__restrict__ ids, int *__restrict__ n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  list_append_warp(i < n2 && lflag[i] != LF_REMOTE, i, ids, n);
+}
+__global__ void k_list_compact(const int *__restrict__ ids_in, const int *__restrict__ n_in, int *__restrict__ lflag,
+                               int *__restrict__ ids_out, int *__restrict__ n_out) {
+  const int n = *n_in;
+  const int nround = (n + 31) & ~31;  // whole warps enter list_append_warp
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nround; k += gridDim.x * blockDim.x) {
+    int i = -1;
+    bool keep = false;
+    if (k < n) {
+      i = ids_in[k];
+      const int f = lflag[i];
+      keep = (f != LF_STALE);
+      if (!keep) lflag[i] = LF_REMOTE;
+    }
+    list_append_warp(keep, i, ids_out, n_out);
+  }
+}
+
 // halo selection + migration (see file header). cnt[0]/cnt[1]: number of records for the left/right neighbour.
 __global__ void k_halo_select(DevParams P, DistGeom D, const double *__restrict__ x, int *__restrict__ lflag,
-                              int *__restrict__ cnt, int *__restrict__ idsL, int *__restrict__ idsR,
+                              LocalList LL, int *__restrict__ cnt, int *__restrict__ idsL, int *__restrict__ idsR,
                               int *__restrict__ err) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.ntotal2) return;
-  const int f = lflag[i];
-  if (f == LF_GHOST) {
-    lflag[i] = LF_REMOTE;  // refreshed by its owner below if it is still inside our halo
-    return;
-  }
-  if (f != LF_OWNED) return;
-  const double xk = key_x(P, D, x, i), xi = x[2 * (size_t)i];
-  bool toL = false, toR = false;
-  if (xk < D.lo) {  // migrates to the left neighbour; we keep it as a ghost (its state is current)
-    toL = true;
-    lflag[i] = LF_GHOST;
-  } else if (xk >= D.hi) {
-    toR = true;
-    lflag[i] = LF_GHOST;
-  } else {
-    if (D.rank > 0 && xi < D.lo + D.H) toL = true;
-    if (D.rank < D.nranks - 1 && xi >= D.hi - D.H) toR = true;
-  }
-  if (toL) {
-    const int k = atomicAdd(&cnt[0], 1);
-    if (k < D.cap)
-      idsL[k] = i;
-    else
-      *err = 1;
-  }
-  if (toR) {
-    const int k = atomicAdd(&cnt[1], 1);
-    if (k < D.cap)
-      idsR[k] = i;
-    else
-      *err = 1;
+  SPSPH_FOR_LOCAL(LL, kk, i) {
+    const int f = lflag[i];
+    if (f == LF_GHOST) {
+      lflag[i] = LF_STALE;  // refreshed by its owner below if it is still inside our halo
+      continue;
+    }
+    if (f != LF_OWNED) continue;
+    const double xk = key_x(P, D, x, i), xi = x[2 * (size_t)i];
+    bool toL = false, toR = false;
+    if (xk < D.lo) {  // migrates to the left neighbour; we keep it as a ghost (its state is current)
+      toL = true;
+      lflag[i] = LF_GHOST;
+    } else if (xk >= D.hi) {
+      toR = true;
+      lflag[i] = LF_GHOST;
+    } else {
+      if (D.rank > 0 && xi < D.lo + D.H) toL = true;
+      if (D.rank < D.nranks - 1 && xi >= D.hi - D.H) toR = true;
+    }
+    if (toL) {
+      const int k = atomicAdd(&cnt[0], 1);
+      if (k < D.cap)
+        idsL[k] = i;
+      else
+        *err = 1;
+    }
+    if (toR) {
+      const int k = atomicAdd(&cnt[1], 1);
+      if (k < D.cap)
+        idsR[k] = i;
+      else
+        *err = 1;
+    }
   }
 }
 
@@ -142,7 +181,7 @@ __global__ void k_halo_pack(DevParams P, StatePtrs st, HaloArrays A, const int *
 }
 
 __global__ void k_halo_unpack(DevParams P, DistGeom D, StatePtrs st, HaloArrays A, const double *__restrict__ msg,
-                              int *__restrict__ lflag) {
+                              int *__restrict__ lflag, int *__restrict__ list_ids, int *__restrict__ list_n) {
   const int n = (int)msg[0];
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const double *o = msg + (size_t)HALO_REC * (k + 1);
@@ -171,6 +210,7 @@ __global__ void k_halo_unpack(DevParams P, DistGeom D, StatePtrs st, HaloArrays 
       st.epsp[i] = o[9];
       st.fdp[i] = o[10];
     }
+    if (lflag[i] == LF_REMOTE) list_ids[atomicAdd(list_n, 1)] = i;  // newcomer: joins the local list
     lflag[i] = LF_GHOST;  // ownership is settled by k_halo_own once every position has arrived
   }
 }

@@ -15,7 +15,6 @@
 namespace spsph {
 
 constexpr int SLICE = 32;
-constexpr int PARK_REMOTE = -(1 << 30);  // which_cell <= PARK_REMOTE: remote particle (multi-GPU)
 
 struct SortArrays {  // per species s in {node, stress, dummy}; species-sorted index k
   const int *start[3];      // [ncell+1] first sorted index of each cell
@@ -50,6 +49,38 @@ __device__ __forceinline__ bool slot_decode(const SlotMap &m, int t, int &sp, in
   return k < m.nd;
 }
 
+// Segmented block -> slot mapping: blocks [0, seg_n) walk node slots, the next seg_s stress-particle slots, the
+// rest wall-particle slots. On a slab only the leading slots of a species hold local particles, so the grids of the
+// slot-indexed kernels are sized by the local counts (or a bound on them) instead of the global ones.
+// Returns -1 for a thread past the end of its species' slot range (whole warps: the ranges are multiples of 32).
+__device__ __forceinline__ int seg_slot(const SlotMap &M, int seg_n, int seg_s) {
+  const int b = blockIdx.x;
+  if (b < seg_n) {
+    const int u = b * blockDim.x + threadIdx.x;
+    return u < M.nnp ? u : -1;
+  }
+  if (b < seg_n + seg_s) {
+    const int u = (b - seg_n) * blockDim.x + threadIdx.x;
+    return u < M.nsp ? M.nnp + u : -1;
+  }
+  const int u = (b - seg_n - seg_s) * blockDim.x + threadIdx.x;
+  return u < M.ndp ? M.nnp + M.nsp + u : -1;
+}
+
+// Particles a kernel has to visit. Single GPU: all of them (ids == nullptr, identity). Multi-GPU: the compact
+// list of this rank's local (owned + ghost) particle numbers kept by dist_kernels.cuh, so that no per-step pass
+// is proportional to the global particle count.
+struct LocalList {
+  const int *ids;  // nullptr: identity
+  const int *n;    // device count (ids != nullptr)
+  int nfull;
+};
+__device__ __forceinline__ int ll_count(const LocalList &l) { return l.ids ? *l.n : l.nfull; }
+__device__ __forceinline__ int ll_id(const LocalList &l, int k) { return l.ids ? l.ids[k] : k; }
+#define SPSPH_FOR_LOCAL(LL, K, I)                                                                       \
+  for (int K = blockIdx.x * blockDim.x + threadIdx.x, n_ll_ = ll_count(LL), I = 0;                      \
+       K < n_ll_ && ((I = ll_id(LL, K)), true); K += gridDim.x * blockDim.x)
+
 // ------------------------------------------------------------------------------------------------------
 // Check_Out_Domain + bounding box / max h of the in-domain particles (min/max are order-independent).
 // ------------------------------------------------------------------------------------------------------
@@ -65,10 +96,10 @@ __device__ __forceinline__ double warp_max(double v) {
 // lflag (multi-GPU only, else nullptr): 0 remote, 1 owned, 2 ghost; only owned particles enter the local
 // bounds (the global bounds are the all-reduce of the local ones), remote particles are skipped entirely.
 __global__ void k_domain_bbox(DevParams P, const double *__restrict__ x, const double *__restrict__ hsml,
-                              int *__restrict__ if_out, const int *__restrict__ lflag,
+                              int *__restrict__ if_out, const int *__restrict__ lflag, LocalList LL,
                               double *__restrict__ partial /* [gridDim.x][6] */) {
   double xmn = 1.e+10, ymn = 1.e+10, xmx = -1.e+10, ymx = -1.e+10, hmx = 0.0, hmn = 1.e+300;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < P.ntotal2; i += gridDim.x * blockDim.x) {
+  SPSPH_FOR_LOCAL(LL, kk, i) {
     const int lf = lflag ? lflag[i] : 1;
     if (lf == 0) continue;
     const double2 p = ld2(x, i);
@@ -179,33 +210,23 @@ __device__ __forceinline__ int species_of(const DevParams &P, int i) {
 
 // grid_find_NEW Task 2 (main:1277-1286): cell id of every in-domain particle + per-cell species counts
 __global__ void k_cell_id(DevParams P, const GridInfo *__restrict__ G, const double *__restrict__ x,
-                          const int *__restrict__ if_out, const int *__restrict__ lflag, int *__restrict__ which_cell,
+                          const int *__restrict__ if_out, LocalList LL, int *__restrict__ which_cell,
                           int *__restrict__ cnt, int cell_stride, int *__restrict__ nout /* [6] */) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.ntotal2) return;
-  const int sp = species_of(P, i);
-  if (lflag && lflag[i] == 0) {  // remote (other rank's) particle: parked last, never processed
-    // warp-aggregated counter (millions of remote particles would otherwise serialise on one address)
-    const unsigned grp = __match_any_sync(__activemask(), sp);
-    const int lane = threadIdx.x & 31, leader = __ffs(grp) - 1;
-    int base = 0;
-    if (lane == leader) base = atomicAdd(&nout[3 + sp], __popc(grp));
-    base = __shfl_sync(grp, base, leader);
-    which_cell[i] = PARK_REMOTE - (base + __popc(grp & ((1u << lane) - 1)));
-    return;
+  SPSPH_FOR_LOCAL(LL, kk, i) {
+    const int sp = species_of(P, i);
+    if (if_out[i] || G->overflow) {  // on a cell-table overflow nothing is binned; the host reports the error
+      which_cell[i] = -1 - atomicAdd(&nout[sp], 1);  // parked after the sorted particles, order irrelevant
+      continue;
+    }
+    const double2 p = ld2(x, i);
+    int ix = (int)((p.x - G->xmin[0]) / G->deltx[0] + 1);
+    int iy = (int)((p.y - G->xmin[1]) / G->deltx[1] + 1);
+    if (ix > G->ndivx[0]) ix = G->ndivx[0];
+    if (iy > G->ndivx[1]) iy = G->ndivx[1];
+    const int c = G->ndivx[0] * (iy - 1) + (ix - 1);  // 0-based cell id, same ordering as the reference's
+    which_cell[i] = c;
+    atomicAdd(&cnt[sp * cell_stride + c], 1);
   }
-  if (if_out[i] || G->overflow) {  // on a cell-table overflow nothing is binned; the host reports the error
-    which_cell[i] = -1 - atomicAdd(&nout[sp], 1);  // parked after the sorted particles, order irrelevant
-    return;
-  }
-  const double2 p = ld2(x, i);
-  int ix = (int)((p.x - G->xmin[0]) / G->deltx[0] + 1);
-  int iy = (int)((p.y - G->xmin[1]) / G->deltx[1] + 1);
-  if (ix > G->ndivx[0]) ix = G->ndivx[0];
-  if (iy > G->ndivx[1]) iy = G->ndivx[1];
-  const int c = G->ndivx[0] * (iy - 1) + (ix - 1);  // 0-based cell id, same ordering as the reference's
-  which_cell[i] = c;
-  atomicAdd(&cnt[sp * cell_stride + c], 1);
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -303,49 +324,47 @@ __global__ void k_scan_apply(const int *__restrict__ in, int *__restrict__ out, 
 // original index so that the final order is deterministic and equals the reference's list_picell order
 // (ascending particle index within a cell, main:1299-1305).
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_scatter(DevParams P, const int *__restrict__ which_cell, const int *__restrict__ start,
+__global__ void k_scatter(DevParams P, LocalList LL, const int *__restrict__ which_cell, const int *__restrict__ start,
                           int *__restrict__ fill, int cell_stride, int *__restrict__ tmp /* 3 rows, stride ntotal2 */) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.ntotal2) return;
-  const int c = which_cell[i];
-  if (c < 0) return;
-  const int sp = species_of(P, i);
-  const int slot = start[sp * cell_stride + c] + atomicAdd(&fill[sp * cell_stride + c], 1);
-  tmp[(size_t)sp * P.ntotal2 + slot] = i;
+  SPSPH_FOR_LOCAL(LL, kk, i) {
+    const int c = which_cell[i];
+    if (c < 0) continue;
+    const int sp = species_of(P, i);
+    const int slot = start[sp * cell_stride + c] + atomicAdd(&fill[sp * cell_stride + c], 1);
+    tmp[(size_t)sp * P.ntotal2 + slot] = i;
+  }
 }
 
-__global__ void k_rank(DevParams P, const GridInfo *__restrict__ G, const double *__restrict__ x,
+__global__ void k_rank(DevParams P, LocalList LL, const GridInfo *__restrict__ G, const double *__restrict__ x,
                        const double *__restrict__ hsml, const int *__restrict__ which_cell,
                        const int *__restrict__ start, int cell_stride, const int *__restrict__ tmp,
                        int *__restrict__ order, double2 *__restrict__ spos, double *__restrict__ sh,
                        int *__restrict__ scell, int *__restrict__ pos_of /* [ntotal2] species-sorted index */,
                        float2 *__restrict__ supos, const int *__restrict__ nout) {
-  // one thread per particle in original order
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.ntotal2) return;
-  const int sp = species_of(P, i);
-  const int c = which_cell[i];
-  const size_t row = (size_t)sp * P.ntotal2;
-  int k;
-  if (c <= PARK_REMOTE) {
-    const int nact = start[sp * cell_stride + G->ncell];
-    k = nact + nout[sp] + (PARK_REMOTE - c);
-  } else if (c < 0) {
-    const int nact = start[sp * cell_stride + G->ncell];
-    k = nact + (-1 - c);
-  } else {
-    const int b = start[sp * cell_stride + c], e = start[sp * cell_stride + c + 1];
-    int r = 0;
-    for (int j = b; j < e; ++j) r += (tmp[row + j] < i) ? 1 : 0;
-    k = b + r;
+  // one thread per (local) particle
+  SPSPH_FOR_LOCAL(LL, kk, i) {
+    const int sp = species_of(P, i);
+    const int c = which_cell[i];
+    const size_t row = (size_t)sp * P.ntotal2;
+    int k;
+    if (c < 0) {
+      const int nact = start[sp * cell_stride + G->ncell];
+      k = nact + (-1 - c);
+    } else {
+      const int b = start[sp * cell_stride + c], e = start[sp * cell_stride + c + 1];
+      int r = 0;
+      for (int j = b; j < e; ++j) r += (tmp[row + j] < i) ? 1 : 0;
+      k = b + r;
+    }
+    order[row + k] = i;
+    const double2 xi = ld2(x, i);
+    supos[row + k] =
+        make_float2((float)((xi.x - G->xmin[0]) / G->deltx[0]), (float)((xi.y - G->xmin[1]) / G->deltx[1]));
+    spos[row + k] = xi;
+    sh[row + k] = hsml[i];
+    scell[row + k] = c < 0 ? -1 : c;
+    pos_of[i] = k;
   }
-  order[row + k] = i;
-  const double2 xi = ld2(x, i);
-  supos[row + k] = make_float2((float)((xi.x - G->xmin[0]) / G->deltx[0]), (float)((xi.y - G->xmin[1]) / G->deltx[1]));
-  spos[row + k] = xi;
-  sh[row + k] = hsml[i];
-  scell[row + k] = c < 0 ? -1 : c;
-  pos_of[i] = k;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -518,10 +537,14 @@ __global__ void __launch_bounds__(128, SPSPH_COUNT_MINB)
 k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, int *__restrict__ n0, int *__restrict__ n1,
         int *__restrict__ nfwd_u /* unified order */, int *__restrict__ nall, int *__restrict__ w0 /* slice widths */,
         int *__restrict__ wC, int *__restrict__ wD, const int *__restrict__ lflag, int *__restrict__ cand0,
-        int *__restrict__ cand1, int *__restrict__ overflow) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+        int *__restrict__ cand1, int *__restrict__ overflow, const int *__restrict__ nout, int seg_n, int seg_s) {
+  // grid sized by a bound on the local slots (slices that are not visited keep the zero width of the host memset)
+  const int t = seg_slot(M, seg_n, seg_s);
+  if (t < 0) return;
   int sp = 0, k = 0;
-  const bool live = (t < M.total()) && slot_decode(M, t, sp, k);
+  bool live = (t < M.total()) && slot_decode(M, t, sp, k);
+  // only the leading slots of a species are occupied this step (in-grid particles, then out-of-domain ones)
+  if (live) live = k < (sp == 0 ? S.start[0] : (sp == 1 ? S.start[1] : S.start[2]))[G->ncell] + nout[sp];
   int c0 = 0, c1 = 0, cf = 0, ca = 0;
   if (live) {
     const int *__restrict__ cellp = sp == 0 ? S.cell[0] : (sp == 1 ? S.cell[1] : S.cell[2]);
@@ -759,12 +782,12 @@ constexpr int FILL_THREADS = 128;
 __global__ void __launch_bounds__(FILL_THREADS)
 k_fill_scan(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ n0,
        const int *__restrict__ n1, const GrowthRule *__restrict__ growth, ListPtrs L, int *__restrict__ bc_int,
-       float *__restrict__ n_int, const double *__restrict__ mor) {
+       float *__restrict__ n_int, const double *__restrict__ mor, int seg_n, int seg_s) {
   __shared__ int q0buf[QCAP][FILL_THREADS];  // cross-species partners (species in the top 2 bits)
   __shared__ int q1buf[QCAP][FILL_THREADS];  // same-species partners
   const int tid = threadIdx.x;
-  const int t = blockIdx.x * blockDim.x + tid;
-  if (t >= M.nnp + M.nsp) return;
+  const int t = seg_slot(M, seg_n, seg_s);
+  if (t < 0 || t >= M.nnp + M.nsp) return;
   int sp, k;
   if (!slot_decode(M, t, sp, k)) return;
   const int *__restrict__ orderp = sp == 0 ? S.order[0] : S.order[1];
@@ -949,9 +972,9 @@ __global__ void __launch_bounds__(128, SPSPH_FILL_MINB)
 k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ n0,
        const int *__restrict__ n1, const GrowthRule *__restrict__ growth, ListPtrs L, int *__restrict__ bc_int,
        float *__restrict__ n_int, const double *__restrict__ mor, const int *__restrict__ cand0,
-       const int *__restrict__ cand1) {
-  const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= M.nnp + M.nsp) return;
+       const int *__restrict__ cand1, int seg_n, int seg_s) {
+  const int t = seg_slot(M, seg_n, seg_s);
+  if (t < 0 || t >= M.nnp + M.nsp) return;
   int sp, k;
   if (!slot_decode(M, t, sp, k)) return;
   const int *__restrict__ orderp = sp == 0 ? S.order[0] : S.order[1];

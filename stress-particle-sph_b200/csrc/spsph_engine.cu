@@ -102,6 +102,10 @@ struct spsph_handle {
   DistGeom D{};
   int *lflag = nullptr;       // [ntotal2] 0 remote, 1 owned, 2 ghost (nullptr-equivalent when !dist)
   int *halo_cnt = nullptr;    // [2] + err flag [1]
+  int *list_ids[2] = {nullptr, nullptr};  // local list (double-buffered for the per-step compaction)
+  int *list_n = nullptr;                  // [2] device counts
+  int list_cur = 0;
+  bool nloc_valid = false;                // nloc[] holds the previous step's counts (bounds the k_count grid)
   int *halo_ids[2] = {nullptr, nullptr};
   double *halo_send[2] = {nullptr, nullptr}, *halo_recv[2] = {nullptr, nullptr};
   double *bb6 = nullptr;
@@ -358,6 +362,21 @@ void launch_scan(spsph_handle *h, const int *in, int *out, int rows, int stride,
   mark(h, KID_SCAN, 3);
 }
 
+// particles a per-particle kernel visits, and the grid for it
+static LocalList local_list(const spsph_handle *h, int nfull) {
+  if (!h->dist) return LocalList{nullptr, nullptr, nfull};
+  return LocalList{h->list_ids[h->list_cur], h->list_n + h->list_cur, nfull};
+}
+static int list_grid(const spsph_handle *h, int nfull, int tb) { return h->dist ? 148 * 8 : (nfull + tb - 1) / tb; }
+static int rebuild_local_list(spsph_handle *h, cudaStream_t s) {
+  const int n2 = h->P.ntotal2;
+  h->list_cur = 0;
+  h->nloc_valid = false;
+  CUDA_TRY(cudaMemsetAsync(h->list_n, 0, 2 * sizeof(int), s));
+  k_list_build<<<(n2 + 255) / 256, 256, 0, s>>>(n2, h->lflag, h->list_ids[0], h->list_n);
+  return 0;
+}
+
 // per-step halo exchange + migration (dist_kernels.cuh); everything is enqueued on the engine stream
 int halo_exchange(spsph_handle *h) {
   const DevParams &P = h->P;
@@ -368,8 +387,9 @@ int halo_exchange(spsph_handle *h) {
   const HaloArrays A{h->x, h->epsp, h->fdp, h->x_10, h->disp_10, h->displ, h->if_out};
   if (h->profiling) mark(h, -1, 0);
   CUDA_TRY(cudaMemsetAsync(h->halo_cnt, 0, 2 * sizeof(int), s));
-  k_halo_select<<<(n2 + 255) / 256, 256, 0, s>>>(P, D, h->x, h->lflag, h->halo_cnt, h->halo_ids[0], h->halo_ids[1],
-                                                 h->halo_cnt + 2);
+  const LocalList LL = local_list(h, n2);
+  k_halo_select<<<list_grid(h, n2, 256), 256, 0, s>>>(P, D, h->x, h->lflag, LL, h->halo_cnt, h->halo_ids[0],
+                                                       h->halo_ids[1], h->halo_cnt + 2);
   const size_t msg = (size_t)HALO_REC * (D.cap + 1);
   for (int side = 0; side < 2; ++side)
     k_halo_pack<<<148, 256, 0, s>>>(P, st, A, h->halo_cnt + side, D.cap, h->halo_ids[side], h->halo_send[side]);
@@ -387,14 +407,20 @@ int halo_exchange(spsph_handle *h) {
   for (int side = 0; side < 2; ++side) {
     const int peer = side == 0 ? left : right;
     if (peer < 0 || peer >= D.nranks) continue;
-    k_halo_unpack<<<148, 256, 0, s>>>(P, D, st, A, h->halo_recv[side], h->lflag);
+    k_halo_unpack<<<148, 256, 0, s>>>(P, D, st, A, h->halo_recv[side], h->lflag, h->list_ids[h->list_cur],
+                                      h->list_n + h->list_cur);
   }
   for (int side = 0; side < 2; ++side) {
     const int peer = side == 0 ? left : right;
     if (peer < 0 || peer >= D.nranks) continue;
     k_halo_own<<<148, 256, 0, s>>>(P, D, h->x, h->halo_recv[side], h->lflag);
   }
-  mark(h, KID_HALO, 7);
+  // drop the ghosts nobody refreshed (they left our halo) from the local list
+  CUDA_TRY(cudaMemsetAsync(h->list_n + (1 - h->list_cur), 0, sizeof(int), s));
+  k_list_compact<<<148 * 4, 256, 0, s>>>(h->list_ids[h->list_cur], h->list_n + h->list_cur, h->lflag,
+                                         h->list_ids[1 - h->list_cur], h->list_n + (1 - h->list_cur));
+  h->list_cur = 1 - h->list_cur;
+  mark(h, KID_HALO, 8);
   return 0;
 }
 
@@ -408,7 +434,9 @@ int build_neighbours(spsph_handle *h) {
     mark(h, -1, 0);
   }
   const int *lflag = h->dist ? h->lflag : nullptr;
-  k_domain_bbox<<<h->bbox_blocks, TB, 0, s>>>(P, h->x, h->hsml, h->if_out, lflag, h->bbox_partial);
+  const LocalList LL = local_list(h, n2);
+  const int GL = list_grid(h, n2, TB);
+  k_domain_bbox<<<h->bbox_blocks, TB, 0, s>>>(P, h->x, h->hsml, h->if_out, lflag, LL, h->bbox_partial);
   mark(h, KID_BBOX);
   k_bbox_final<<<1, 32, 0, s>>>(h->bbox_blocks, h->bbox_partial, h->bb6);
   if (h->dist)  // global grid bounds: the reference's cell grid (hence its pair order) is a global property
@@ -419,25 +447,36 @@ int build_neighbours(spsph_handle *h) {
   k_zero_cells<<<296, TB, 0, s>>>(h->G, h->cell_fill, h->cell_stride);
   CUDA_TRY(cudaMemsetAsync(h->nout, 0, 6 * sizeof(int), s));
   CUDA_TRY(cudaMemsetAsync(h->nfwd_u, 0, (size_t)n2 * sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(h->wslice, 0, 3 * (size_t)h->nslices * sizeof(int), s));
   CUDA_TRY(cudaMemsetAsync(h->cand_overflow, 0, sizeof(int), s));
   mark(h, KID_ZERO, 2);
-  k_cell_id<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->G, h->x, h->if_out, lflag, h->which_cell, h->cell_cnt,
-                                               h->cell_stride, h->nout);
+  k_cell_id<<<GL, TB, 0, s>>>(P, h->G, h->x, h->if_out, LL, h->which_cell, h->cell_cnt, h->cell_stride, h->nout);
   mark(h, KID_CELLID);
   launch_scan(h, h->cell_cnt, h->cell_start, 3, h->cell_stride, &h->G->ncell, 1, h->scan_totals + 4);
-  k_scatter<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->which_cell, h->cell_start, h->cell_fill, h->cell_stride, h->tmp_ids);
+  k_scatter<<<GL, TB, 0, s>>>(P, LL, h->which_cell, h->cell_start, h->cell_fill, h->cell_stride, h->tmp_ids);
   mark(h, KID_SCATTER);
-  k_rank<<<(n2 + TB - 1) / TB, TB, 0, s>>>(P, h->G, h->x, h->hsml, h->which_cell, h->cell_start, h->cell_stride,
-                                            h->tmp_ids, h->order, h->spos, h->sh, h->scell, h->pos_of, h->supos, h->nout);
+  k_rank<<<GL, TB, 0, s>>>(P, LL, h->G, h->x, h->hsml, h->which_cell, h->cell_start, h->cell_stride, h->tmp_ids,
+                           h->order, h->spos, h->sh, h->scell, h->pos_of, h->supos, h->nout);
   mark(h, KID_RANK);
   const SortArrays S = sort_arrays(h);
-  const int T = h->M.total();
-  k_count<<<(T + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->nfwd_u, h->nall, h->wslice,
-                                           h->wslice + h->nslices, h->wslice + 2 * h->nslices, lflag, h->cand0,
-                                           h->cand1, h->cand_overflow);
+  // slots that can hold local particles: all of them, or (slab) last step's local count plus what two halo
+  // messages can add
+  int bound[3] = {h->M.nnp, h->M.nsp, h->M.ndp};
+  if (h->dist && h->nloc_valid)
+    for (int k = 0; k < 3; ++k) {
+      const long long b = (long long)h->nloc[k] + 2ll * h->D.cap + 32;
+      if (b < bound[k]) bound[k] = (int)b;
+    }
+  const int seg_n = (bound[0] + 127) / 128, seg_s = (bound[1] + 127) / 128, seg_d = (bound[2] + 127) / 128;
+  k_count<<<seg_n + seg_s + seg_d, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->nfwd_u, h->nall, h->wslice,
+                                                 h->wslice + h->nslices, h->wslice + 2 * h->nslices, lflag,
+                                                 h->cand0, h->cand1, h->cand_overflow, h->nout, seg_n, seg_s);
   mark(h, KID_COUNT);
   launch_scan(h, h->wslice, h->oslice, 3, h->nslices, nullptr, h->nslices, h->scan_totals);
-  launch_scan(h, h->nfwd_u, h->base_u, 1, n2, nullptr, n2, h->scan_totals + 3);
+  if (h->dist)  // unified slots of local particles are the leading ones: scan only those
+    launch_scan(h, h->nfwd_u, h->base_u, 1, n2, h->list_n + h->list_cur, 0, h->scan_totals + 3);
+  else
+    launch_scan(h, h->nfwd_u, h->base_u, 1, n2, nullptr, n2, h->scan_totals + 3);
   if (h->dist) {  // every pair is counted once, at the owner of its earlier member
     CUDA_TRY(cudaMemcpyAsync(h->scan_totals + 6, h->scan_totals + 3, sizeof(long long), cudaMemcpyDeviceToDevice, s));
     NCCL_TRY(h->p_ncclAllReduce(h->scan_totals + 3, h->scan_totals + 3, 1, ncclInt64, ncclSum, h->comm, s));
@@ -470,6 +509,7 @@ int build_neighbours(spsph_handle *h) {
     return 1;
   }
   for (int k = 0; k < 3; ++k) h->nloc[k] = st.nloc[k];
+  h->nloc_valid = true;
   if (ensure_lists(h, st.tot0, st.totC, st.totD)) return 1;
   h->L.off0 = h->oslice;
   h->L.offC = h->oslice + h->nslices;
@@ -501,13 +541,17 @@ int build_neighbours(spsph_handle *h) {
     mark(h, KID_THRESH);
   }
   if (st.n_pairs > h->m_pairs) h->m_pairs = st.n_pairs;
-  const int TL = h->M.nnp + h->M.nsp;  // (parked slots return at once)
+  SlotMap ML = h->M;  // only the slots of this rank's local particles hold data
+  ML.nn = h->nloc[0];
+  ML.ns = h->nloc[1];
+  ML.nd = h->nloc[2];
+  const int fseg_n = (ML.nn + 127) / 128, fseg_s = (ML.ns + 127) / 128;
   if (st.pad[0] || h->force_fill_scan)  // a particle has more partners than the candidate scratch holds: search again while filling
-    k_fill_scan<<<(TL + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int, h->n_int,
-                                                  h->mor);
-  else
-    k_fill<<<(TL + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int, h->n_int,
-                                             h->mor, h->cand0, h->cand1);
+    k_fill_scan<<<fseg_n + fseg_s, 128, 0, s>>>(P, ML, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int, h->n_int,
+                                                h->mor, fseg_n, fseg_s);
+  else if (fseg_n + fseg_s > 0)
+    k_fill<<<fseg_n + fseg_s, 128, 0, s>>>(P, ML, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int, h->n_int, h->mor,
+                                           h->cand0, h->cand1, fseg_n, fseg_s);
   mark(h, KID_FILL);
   return 0;
 }
@@ -548,7 +592,7 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     mark(h, KID_MOVE);
   }
   // RK4, main:653-802
-  k_rk_begin<<<(P.ntotal + 255) / 256, 256, 0, s>>>(P, st, lflag);
+  k_rk_begin<<<list_grid(h, P.ntotal, 256), 256, 0, s>>>(P, st, local_list(h, P.ntotal));
   mark(h, KID_RKBEGIN);
   const double f1rk[4] = {0., 0.5, 0.5, 1.0}, f2rk[4] = {1., 2., 2., 1.0};
   // The node-side and the stress-particle-side kernel of a sweep touch disjoint outputs and only read the
@@ -568,7 +612,7 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   };
   for (int stg = 0; stg < 4; ++stg) {
     if (std_sph) {
-      k_sweep_a_std<<<(P.ntotal + 255) / 256, 256, 0, s>>>(P, st, lflag);
+      k_sweep_a_std<<<list_grid(h, P.ntotal, 256), 256, 0, s>>>(P, st, local_list(h, P.ntotal));
     } else {
       fork();
       if (first_a) {
@@ -599,7 +643,7 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   }
   // final stress_point_update + adapt_stress2 + BCs, main:130-135
   if (std_sph) {
-    k_sweep_a_std<<<(P.ntotal + 255) / 256, 256, 0, s>>>(P, st, lflag);
+    k_sweep_a_std<<<list_grid(h, P.ntotal, 256), 256, 0, s>>>(P, st, local_list(h, P.ntotal));
   } else {
     fork();
     k_sweep_a_sp<false, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
@@ -611,11 +655,12 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   k_move<<<GB, 128, 0, s>>>(P, M, S, h->L, h->n1, st, h->x, h->x00, h->displ);
   mark(h, KID_MOVE);
   if (p.update_x && std_sph) {  // main:166
-    k_sp_follow<<<(P.nnode + 255) / 256, 256, 0, s>>>(P, h->x, lflag);
+    k_sp_follow<<<list_grid(h, P.nnode, 256), 256, 0, s>>>(P, h->x, local_list(h, P.nnode));
     mark(h, KID_SHIFT);
   }
   if (p.update_x && p.sp_sph && !p.inside_approach) {
-    k_shift<<<(P.nnode + 255) / 256, 256, 0, s>>>(P, st.NB, h->x, h->x_10, h->disp_10, h->bc_int, h->n_int, lflag);
+    k_shift<<<list_grid(h, P.nnode, 256), 256, 0, s>>>(P, st.NB, h->x, h->x_10, h->disp_10, h->bc_int, h->n_int,
+                                                       local_list(h, P.nnode));
     mark(h, KID_SHIFT);
   }
   CUDA_TRY(cudaGetLastError());
@@ -851,6 +896,7 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   h->uploaded = true;
   if (h->dist) {  // a fresh upload holds complete data on every rank: re-derive owned / ghost / remote
     k_dist_init_flags<<<((int)n2 + 255) / 256, 256, 0, st>>>(h->P, h->D, h->x, h->lflag);
+    if (rebuild_local_list(h, st)) return 1;
     CUDA_TRY(cudaStreamSynchronize(st));
   }
   return 0;
@@ -960,7 +1006,11 @@ int spsph_pair_stats(spsph_handle *h, int64_t *npairs, int32_t *maxiac, int32_t 
   CUDA_TRY(cudaSetDevice(h->device));
   const int init[4] = {0, 1000, 0, 0};
   CUDA_TRY(cudaMemcpyAsync(h->stats_d, init, sizeof(init), cudaMemcpyHostToDevice, h->stream));
-  k_pair_stats<<<148, 256, 0, h->stream>>>(h->M, h->nall, h->stats_d);
+  SlotMap M = h->M;  // only the slots of this rank's local particles were written by the last k_count
+  M.nn = h->nloc[0];
+  M.ns = h->nloc[1];
+  M.nd = h->nloc[2];
+  k_pair_stats<<<148, 256, 0, h->stream>>>(M, h->nall, h->stats_d);
   int out[4];
   CUDA_TRY(cudaMemcpyAsync(out, h->stats_d, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -988,8 +1038,12 @@ int spsph_pairs(spsph_handle *h, int64_t *npairs, int32_t *pair_i, int32_t *pair
   CUDA_TRY(cudaMalloc((void **)&d_x, b));
   CUDA_TRY(cudaMalloc((void **)&d_y, b));
   const int T = h->M.total();
+  SlotMap ML = h->M;  // only the slots of this rank's local particles hold data
+  ML.nn = h->nloc[0];
+  ML.ns = h->nloc[1];
+  ML.nd = h->nloc[2];
   // NB: valid until the next spsph_step (positions in the sorted arrays are those of the last search)
-  k_export_pairs<<<(T + 127) / 128, 128, 0, h->stream>>>(h->P, h->M, h->G, sort_arrays(h), h->base_u, n,
+  k_export_pairs<<<(T + 127) / 128, 128, 0, h->stream>>>(h->P, ML, h->G, sort_arrays(h), h->base_u, n,
                                                          h->last_m_before, d_i, d_j, d_t, d_w, d_x, d_y);
   CUDA_TRY(cudaMemcpyAsync(pair_i, d_i, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaMemcpyAsync(pair_j, d_j, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
@@ -1073,6 +1127,7 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
   const size_t n2 = (size_t)p.ntotal2;
   const size_t msg = (size_t)HALO_REC * ((size_t)D.cap + 1);
   if (dalloc(h, &h->lflag, n2) || dalloc(h, &h->halo_cnt, 4)) return 1;
+  if (dalloc(h, &h->list_ids[0], n2) || dalloc(h, &h->list_ids[1], n2) || dalloc(h, &h->list_n, 2)) return 1;
   if (dalloc(h, &h->gt_buf, (size_t)GT_CAP) || dalloc(h, &h->gt_mine, 2 * (size_t)GT_PCAP) ||
       dalloc(h, &h->gt_all, 2 * (size_t)GT_PCAP * nranks) || dalloc(h, &h->gt_out2, 4) || dalloc(h, &h->gt_sel, 1))
     return 1;
@@ -1083,6 +1138,7 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
   CUDA_TRY(cudaMemset(h->halo_cnt, 0, 4 * sizeof(int)));
   h->dist = true;
   k_dist_init_flags<<<((int)n2 + 255) / 256, 256, 0, h->stream>>>(h->P, h->D, h->x, h->lflag);
+  if (rebuild_local_list(h, h->stream)) return 1;
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;
 }

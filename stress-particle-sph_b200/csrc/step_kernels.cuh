@@ -226,10 +226,9 @@ __global__ void k_unpack_state(DevParams P, StatePtrs st, double *__restrict__ v
 // format B (state) -> format A (stage-1 input); saves vel0/stress0/vx0 and zeroes the RK accumulators.
 // Stress-particle velocities and node stresses start from zero (main:690).
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_rk_begin(DevParams P, StatePtrs st, const int *__restrict__ lflag) {
-  const int id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= P.ntotal) return;
-  if (lflag && lflag[id] == 0) return;  // remote particle (multi-GPU)
+__global__ void k_rk_begin(DevParams P, StatePtrs st, LocalList LL) {
+  SPSPH_FOR_LOCAL(LL, kk, id) {
+  if (id >= P.ntotal) continue;  // wall particle
   double2 vn;
   Stress4 sn;
   if (id < P.nnode) {
@@ -263,6 +262,7 @@ __global__ void k_rk_begin(DevParams P, StatePtrs st, const int *__restrict__ lf
     apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
     strec(st.SA, ks, sn.s1, sn.s2, sn.s3, sn.s4);
     st2(st.SVa, ks, vn);
+  }
   }
 }
 
@@ -857,10 +857,9 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
 // Standard SPH mode (SP_SPH = F): stress_point_update degenerates to copies between a velocity particle and the
 // stress particle that shadows it (main:472-480); no adapt_stress2 / BCs follow it (main:720-723,132-135).
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_sweep_a_std(DevParams P, StatePtrs st, const int *__restrict__ lflag) {
-  const int id = blockIdx.x * blockDim.x + threadIdx.x;
-  if (id >= P.ntotal) return;
-  if (lflag && lflag[id] == 0) return;
+__global__ void k_sweep_a_std(DevParams P, StatePtrs st, LocalList LL) {
+  SPSPH_FOR_LOCAL(LL, kk, id) {
+  if (id >= P.ntotal) continue;
   if (id < P.nnode) {  // stress(:,i) = stress(:,nnode+i); Internal_Vars(1,i) = Internal_Vars(1,nnode+i)
     const double2 v = ld2(st.NA, id);
     const Rec4 s = ldrec(st.SA, id);
@@ -877,13 +876,13 @@ __global__ void k_sweep_a_std(DevParams P, StatePtrs st, const int *__restrict__
     const double r2 = rr * rr;
     strec(st.SB, ks, s.a / r2, s.b / r2, s.c / r2, st.mass[id]);
   }
+  }
 }
 // x(:,nnode+1:ntotal) = x(:,1:nnode), main:166
-__global__ void k_sp_follow(DevParams P, double *__restrict__ x, const int *__restrict__ lflag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.nnode) return;
-  if (lflag && lflag[i] == 0) return;
-  st2(x, P.nnode + i, ld2(x, i));
+__global__ void k_sp_follow(DevParams P, double *__restrict__ x, LocalList LL) {
+  SPSPH_FOR_LOCAL(LL, kk, i) {
+    if (i < P.nnode) st2(x, P.nnode + i, ld2(x, i));
+  }
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -1050,10 +1049,9 @@ k_move(DevParams P, SlotMap M, SortArrays So, ListPtrs L, const int *__restrict_
 // shift_stress_points, main:244-368 (outside approach): one thread per node re-seats its stress particles.
 __global__ void k_shift(DevParams P, const Rec4 *__restrict__ NB, double *__restrict__ x, double *__restrict__ x_10,
                         double *__restrict__ disp_10, const int *__restrict__ bc_int, const float *__restrict__ n_int,
-                        const int *__restrict__ lflag) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= P.nnode) return;
-  if (lflag && lflag[i] == 0) return;  // remote particle (multi-GPU)
+                        LocalList LL) {
+  SPSPH_FOR_LOCAL(LL, kk, i) {
+  if (i >= P.nnode) continue;
   const double2 xi = ld2(x, i);
   const Rec4 rr = ldrec(NB, i);
   const double2 v = make_double2(rr.a, rr.b);
@@ -1098,9 +1096,9 @@ __global__ void k_shift(DevParams P, const Rec4 *__restrict__ NB, double *__rest
   if (n_int[i] < 2) collapse = true;
   if (collapse)
     for (int q = 0; q < P.npoints && q < 3; ++q) st2(x, k + q, xi);
+  }
 }
 
-// pair statistics of grid_find_NEW, main:1405-1422
 __global__ void k_pair_stats(SlotMap M, const int *__restrict__ nall, int *__restrict__ out /* max,min,zero */) {
   int mx = 0, mn = 1000, nz = 0;
   const int n = M.total();
