@@ -27,7 +27,8 @@ struct DistGeom {
   double lo, hi;  // this rank's slab is lo <= x_key < hi (lo = -inf on rank 0, hi = +inf on the last rank)
   double H;       // halo distance
   int sp_follows_node;  // outside approach: a stress particle is owned by the rank that owns its node
-  int cap;        // record capacity of one halo message
+  int cap;        // record capacity of one halo message buffer
+  int lim[2];     // records this step's message to the left / right neighbour may hold (<= cap)
 };
 
 // position that decides ownership: a stress particle of the outside approach follows its velocity particle,
@@ -56,35 +57,29 @@ __global__ void k_dist_init_flags(DevParams P, DistGeom D, const double *__restr
 // flags, then maintained per step by k_halo_select (marks stale ghosts) -> k_halo_unpack (appends newcomers) ->
 // k_list_compact (drops ghosts that were not refreshed), so no per-step pass scales with the global count.
 // ------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void list_append_warp(bool keep, int i, int *__restrict__ ids, int *__restrict__ n) {
-  const unsigned act = __activemask();
-  const unsigned m = __ballot_sync(act, keep);
-  if (!m) return;
-  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
-  int base = 0;
-  if (lane == leader) base = atomicAdd(n, __popc(m));
-  base = __shfl_sync(act, base, leader);
-  if (keep) ids[base + __popc(m & ((1u << lane) - 1))] = i;
-}
-__global__ void k_list_build(int n2, const int *__restrict__ lflag, int *__restrict__ ids, int *__restrict__ n) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  list_append_warp(i < n2 && lflag[i] != LF_REMOTE, i, ids, n);
-}
-__global__ void k_list_compact(const int *__restrict__ ids_in, const int *__restrict__ n_in, int *__restrict__ lflag,
-                               int *__restrict__ ids_out, int *__restrict__ n_out) {
-  const int n = *n_in;
-  const int nround = (n + 31) & ~31;  // whole warps enter list_append_warp
-  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < nround; k += gridDim.x * blockDim.x) {
-    int i = -1;
-    bool keep = false;
-    if (k < n) {
-      i = ids_in[k];
-      const int f = lflag[i];
-      keep = (f != LF_STALE);
-      if (!keep) lflag[i] = LF_REMOTE;
-    }
-    list_append_warp(keep, i, ids_out, n_out);
+// Order-preserving compaction (keep flags -> exclusive scan -> scatter): the list starts in ascending particle
+// number and stays nearly so (newcomers are appended), which keeps the per-particle passes streaming.
+// ids_in == nullptr: identity (initial build from the flags of all particles).
+__global__ void k_list_flags(const int *__restrict__ ids_in, const int *__restrict__ n_in, int nfull,
+                             int *__restrict__ lflag, int *__restrict__ keep) {
+  const int n = ids_in ? *n_in : nfull;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    const int i = ids_in ? ids_in[k] : k;
+    const int f = lflag[i];
+    const bool kp = (f == LF_OWNED || f == LF_GHOST);
+    if (f == LF_STALE) lflag[i] = LF_REMOTE;  // a ghost nobody refreshed: it left our halo
+    keep[k] = kp ? 1 : 0;
   }
+}
+__global__ void k_list_scatter(const int *__restrict__ ids_in, const int *__restrict__ n_in, int nfull,
+                               const int *__restrict__ keep, const int *__restrict__ pos, int *__restrict__ ids_out,
+                               int *__restrict__ n_out) {
+  const int n = ids_in ? *n_in : nfull;
+  for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+    if (keep[k]) ids_out[pos[k]] = ids_in ? ids_in[k] : k;
+    if (k == n - 1) *n_out = pos[k] + keep[k];
+  }
+  if (n == 0 && blockIdx.x == 0 && threadIdx.x == 0) *n_out = 0;
 }
 
 // halo selection + migration (see file header). cnt[0]/cnt[1]: number of records for the left/right neighbour.
@@ -112,14 +107,14 @@ __global__ void k_halo_select(DevParams P, DistGeom D, const double *__restrict_
     }
     if (toL) {
       const int k = atomicAdd(&cnt[0], 1);
-      if (k < D.cap)
+      if (k < D.lim[0])
         idsL[k] = i;
       else
         *err = 1;
     }
     if (toR) {
       const int k = atomicAdd(&cnt[1], 1);
-      if (k < D.cap)
+      if (k < D.lim[1])
         idsR[k] = i;
       else
         *err = 1;

@@ -104,8 +104,14 @@ struct spsph_handle {
   int *halo_cnt = nullptr;    // [2] + err flag [1]
   int *list_ids[2] = {nullptr, nullptr};  // local list (double-buffered for the per-step compaction)
   int *list_n = nullptr;                  // [2] device counts
+  int *list_keep = nullptr, *list_pos = nullptr;  // [ntotal2] scratch of the order-preserving compaction
   int list_cur = 0;
   bool nloc_valid = false;                // nloc[] holds the previous step's counts (bounds the k_count grid)
+  // record counts of the previous step's halo messages (sent / received, left / right): they size this step's
+  // NCCL transfers; both ends of a link derive the same size from the same number (the message header)
+  int halo_prev_send[2] = {0, 0}, halo_prev_recv[2] = {0, 0};
+  bool halo_prev_valid = false;
+  double *dist_h = nullptr;               // pinned: [0..1] received header counts, [2..3] halo_cnt + error flags (as int)
   int *halo_ids[2] = {nullptr, nullptr};
   double *halo_send[2] = {nullptr, nullptr}, *halo_recv[2] = {nullptr, nullptr};
   double *bb6 = nullptr;
@@ -354,12 +360,12 @@ int ensure_lists(spsph_handle *h, long long t0, long long tC, long long tD) {
 
 // exclusive scan of `rows` rows of int32 (stride elements apart) over n = *n_ptr + n_add elements each
 void launch_scan(spsph_handle *h, const int *in, int *out, int rows, int stride, const int *n_ptr, int n_add,
-                 long long *totals) {
+                 long long *totals, int kid) {
   dim3 g(SCAN_BLOCKS, rows);
   k_scan_reduce<<<g, SCAN_THREADS, 0, h->stream>>>(in, stride, n_ptr, n_add, h->scan_bsum);
   k_scan_sums<<<rows, SCAN_THREADS, 0, h->stream>>>(h->scan_bsum, totals);
   k_scan_apply<<<g, SCAN_THREADS, 0, h->stream>>>(in, out, stride, n_ptr, n_add, h->scan_bsum);
-  mark(h, KID_SCAN, 3);
+  mark(h, kid, 3);
 }
 
 // particles a per-particle kernel visits, and the grid for it
@@ -368,18 +374,39 @@ static LocalList local_list(const spsph_handle *h, int nfull) {
   return LocalList{h->list_ids[h->list_cur], h->list_n + h->list_cur, nfull};
 }
 static int list_grid(const spsph_handle *h, int nfull, int tb) { return h->dist ? 148 * 8 : (nfull + tb - 1) / tb; }
-static int rebuild_local_list(spsph_handle *h, cudaStream_t s) {
+void launch_scan(spsph_handle *h, const int *in, int *out, int rows, int stride, const int *n_ptr, int n_add,
+                 long long *totals, int kid);
+// order-preserving compaction of the local list (ids_in == nullptr: build from the flags of all particles)
+static int compact_local_list(spsph_handle *h, const int *ids_in, const int *n_in, int *ids_out, int *n_out) {
   const int n2 = h->P.ntotal2;
+  cudaStream_t s = h->stream;
+  const int g = ids_in ? 148 * 8 : (n2 + 255) / 256;
+  k_list_flags<<<g, 256, 0, s>>>(ids_in, n_in, n2, h->lflag, h->list_keep);
+  launch_scan(h, h->list_keep, h->list_pos, 1, n2, ids_in ? n_in : nullptr, ids_in ? 0 : n2, h->scan_totals + 7,
+              KID_HALO);
+  k_list_scatter<<<g, 256, 0, s>>>(ids_in, n_in, n2, h->list_keep, h->list_pos, ids_out, n_out);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+static int rebuild_local_list(spsph_handle *h) {
   h->list_cur = 0;
   h->nloc_valid = false;
-  CUDA_TRY(cudaMemsetAsync(h->list_n, 0, 2 * sizeof(int), s));
-  k_list_build<<<(n2 + 255) / 256, 256, 0, s>>>(n2, h->lflag, h->list_ids[0], h->list_n);
-  return 0;
+  h->halo_prev_valid = false;
+  return compact_local_list(h, nullptr, nullptr, h->list_ids[0], h->list_n);
 }
 
 // per-step halo exchange + migration (dist_kernels.cuh); everything is enqueued on the engine stream
+// Size of a halo message: the full buffer until the previous step's record count is known, then that count plus
+// 12.5 % + 4096 records (counts drift by a few particles per step; an overflow raises the error flag).
+static int halo_limit(const spsph_handle *h, int prev_count) {
+  if (!h->halo_prev_valid) return h->D.cap;
+  const long long l = (long long)prev_count + prev_count / 8 + 4096;
+  return l < h->D.cap ? (int)l : h->D.cap;
+}
 int halo_exchange(spsph_handle *h) {
   const DevParams &P = h->P;
+  h->D.lim[0] = halo_limit(h, h->halo_prev_send[0]);
+  h->D.lim[1] = halo_limit(h, h->halo_prev_send[1]);
   const DistGeom &D = h->D;
   cudaStream_t s = h->stream;
   const int n2 = P.ntotal2;
@@ -390,18 +417,20 @@ int halo_exchange(spsph_handle *h) {
   const LocalList LL = local_list(h, n2);
   k_halo_select<<<list_grid(h, n2, 256), 256, 0, s>>>(P, D, h->x, h->lflag, LL, h->halo_cnt, h->halo_ids[0],
                                                        h->halo_ids[1], h->halo_cnt + 2);
-  const size_t msg = (size_t)HALO_REC * (D.cap + 1);
   for (int side = 0; side < 2; ++side)
-    k_halo_pack<<<148, 256, 0, s>>>(P, st, A, h->halo_cnt + side, D.cap, h->halo_ids[side], h->halo_send[side]);
+    k_halo_pack<<<148, 256, 0, s>>>(P, st, A, h->halo_cnt + side, D.lim[side], h->halo_ids[side], h->halo_send[side]);
   const int left = D.rank - 1, right = D.rank + 1;
+  const size_t msg_s[2] = {(size_t)HALO_REC * (D.lim[0] + 1), (size_t)HALO_REC * (D.lim[1] + 1)};
+  const size_t msg_r[2] = {(size_t)HALO_REC * (halo_limit(h, h->halo_prev_recv[0]) + 1),
+                           (size_t)HALO_REC * (halo_limit(h, h->halo_prev_recv[1]) + 1)};
   NCCL_TRY(h->p_ncclGroupStart());
   if (left >= 0) {
-    NCCL_TRY(h->p_ncclSend(h->halo_send[0], msg, ncclDouble, left, h->comm, s));
-    NCCL_TRY(h->p_ncclRecv(h->halo_recv[0], msg, ncclDouble, left, h->comm, s));
+    NCCL_TRY(h->p_ncclSend(h->halo_send[0], msg_s[0], ncclDouble, left, h->comm, s));
+    NCCL_TRY(h->p_ncclRecv(h->halo_recv[0], msg_r[0], ncclDouble, left, h->comm, s));
   }
   if (right < D.nranks) {
-    NCCL_TRY(h->p_ncclSend(h->halo_send[1], msg, ncclDouble, right, h->comm, s));
-    NCCL_TRY(h->p_ncclRecv(h->halo_recv[1], msg, ncclDouble, right, h->comm, s));
+    NCCL_TRY(h->p_ncclSend(h->halo_send[1], msg_s[1], ncclDouble, right, h->comm, s));
+    NCCL_TRY(h->p_ncclRecv(h->halo_recv[1], msg_r[1], ncclDouble, right, h->comm, s));
   }
   NCCL_TRY(h->p_ncclGroupEnd());
   for (int side = 0; side < 2; ++side) {
@@ -416,11 +445,11 @@ int halo_exchange(spsph_handle *h) {
     k_halo_own<<<148, 256, 0, s>>>(P, D, h->x, h->halo_recv[side], h->lflag);
   }
   // drop the ghosts nobody refreshed (they left our halo) from the local list
-  CUDA_TRY(cudaMemsetAsync(h->list_n + (1 - h->list_cur), 0, sizeof(int), s));
-  k_list_compact<<<148 * 4, 256, 0, s>>>(h->list_ids[h->list_cur], h->list_n + h->list_cur, h->lflag,
-                                         h->list_ids[1 - h->list_cur], h->list_n + (1 - h->list_cur));
+  if (compact_local_list(h, h->list_ids[h->list_cur], h->list_n + h->list_cur, h->list_ids[1 - h->list_cur],
+                         h->list_n + (1 - h->list_cur)))
+    return 1;
   h->list_cur = 1 - h->list_cur;
-  mark(h, KID_HALO, 8);
+  mark(h, KID_HALO, 9);
   return 0;
 }
 
@@ -452,7 +481,7 @@ int build_neighbours(spsph_handle *h) {
   mark(h, KID_ZERO, 2);
   k_cell_id<<<GL, TB, 0, s>>>(P, h->G, h->x, h->if_out, LL, h->which_cell, h->cell_cnt, h->cell_stride, h->nout);
   mark(h, KID_CELLID);
-  launch_scan(h, h->cell_cnt, h->cell_start, 3, h->cell_stride, &h->G->ncell, 1, h->scan_totals + 4);
+  launch_scan(h, h->cell_cnt, h->cell_start, 3, h->cell_stride, &h->G->ncell, 1, h->scan_totals + 4, KID_SCAN);
   k_scatter<<<GL, TB, 0, s>>>(P, LL, h->which_cell, h->cell_start, h->cell_fill, h->cell_stride, h->tmp_ids);
   mark(h, KID_SCATTER);
   k_rank<<<GL, TB, 0, s>>>(P, LL, h->G, h->x, h->hsml, h->which_cell, h->cell_start, h->cell_stride, h->tmp_ids,
@@ -464,7 +493,8 @@ int build_neighbours(spsph_handle *h) {
   int bound[3] = {h->M.nnp, h->M.nsp, h->M.ndp};
   if (h->dist && h->nloc_valid)
     for (int k = 0; k < 3; ++k) {
-      const long long b = (long long)h->nloc[k] + 2ll * h->D.cap + 32;
+      const long long b = (long long)h->nloc[k] + halo_limit(h, h->halo_prev_recv[0]) +
+                          halo_limit(h, h->halo_prev_recv[1]) + 32;
       if (b < bound[k]) bound[k] = (int)b;
     }
   const int seg_n = (bound[0] + 127) / 128, seg_s = (bound[1] + 127) / 128, seg_d = (bound[2] + 127) / 128;
@@ -472,11 +502,11 @@ int build_neighbours(spsph_handle *h) {
                                                  h->wslice + h->nslices, h->wslice + 2 * h->nslices, lflag,
                                                  h->cand0, h->cand1, h->cand_overflow, h->nout, seg_n, seg_s);
   mark(h, KID_COUNT);
-  launch_scan(h, h->wslice, h->oslice, 3, h->nslices, nullptr, h->nslices, h->scan_totals);
+  launch_scan(h, h->wslice, h->oslice, 3, h->nslices, nullptr, h->nslices, h->scan_totals, KID_SCAN);
   if (h->dist)  // unified slots of local particles are the leading ones: scan only those
-    launch_scan(h, h->nfwd_u, h->base_u, 1, n2, h->list_n + h->list_cur, 0, h->scan_totals + 3);
+    launch_scan(h, h->nfwd_u, h->base_u, 1, n2, h->list_n + h->list_cur, 0, h->scan_totals + 3, KID_SCAN);
   else
-    launch_scan(h, h->nfwd_u, h->base_u, 1, n2, nullptr, n2, h->scan_totals + 3);
+    launch_scan(h, h->nfwd_u, h->base_u, 1, n2, nullptr, n2, h->scan_totals + 3, KID_SCAN);
   if (h->dist) {  // every pair is counted once, at the owner of its earlier member
     CUDA_TRY(cudaMemcpyAsync(h->scan_totals + 6, h->scan_totals + 3, sizeof(long long), cudaMemcpyDeviceToDevice, s));
     NCCL_TRY(h->p_ncclAllReduce(h->scan_totals + 3, h->scan_totals + 3, 1, ncclInt64, ncclSum, h->comm, s));
@@ -485,20 +515,30 @@ int build_neighbours(spsph_handle *h) {
                             h->status_d);
   mark(h, KID_STATUS);
   CUDA_TRY(cudaMemcpyAsync(h->status_h, h->status_d, sizeof(StepStatus), cudaMemcpyDeviceToHost, s));
+  if (h->dist) {  // the same round trip brings back the halo counts (they size the next step's messages)
+    h->dist_h[0] = h->dist_h[1] = 0.0;
+    if (h->D.rank > 0) CUDA_TRY(cudaMemcpyAsync(h->dist_h, h->halo_recv[0], sizeof(double), cudaMemcpyDeviceToHost, s));
+    if (h->D.rank < h->D.nranks - 1)
+      CUDA_TRY(cudaMemcpyAsync(h->dist_h + 1, h->halo_recv[1], sizeof(double), cudaMemcpyDeviceToHost, s));
+    CUDA_TRY(cudaMemcpyAsync(h->dist_h + 2, h->halo_cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  }
   CUDA_TRY(cudaStreamSynchronize(s));
   const StepStatus st = *h->status_h;
   if (h->dist) {
-    int herr[2] = {0, 0};
-    CUDA_TRY(cudaMemcpyAsync(herr, h->halo_cnt + 2, 2 * sizeof(int), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaStreamSynchronize(s));
-    if (herr[0]) {
+    const int *hc = reinterpret_cast<const int *>(h->dist_h + 2);  // halo_cnt[0..1], error flags [2..3]
+    if (hc[2]) {
       h->err = "multi-GPU: halo message capacity exceeded (too many particles near a slab boundary)";
       return 1;
     }
-    if (herr[1]) {
+    if (hc[3]) {
       h->err = "multi-GPU: the distributed list-growth search failed in the previous step (grid too large?)";
       return 1;
     }
+    for (int side = 0; side < 2; ++side) {
+      h->halo_prev_send[side] = hc[side];
+      h->halo_prev_recv[side] = (int)h->dist_h[side];
+    }
+    h->halo_prev_valid = true;
   }
   if (st.overflow) {
     h->err = "cell grid larger than the capacity derived from Xmin_Domain/Xmax_Domain";
@@ -818,6 +858,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   rc |= dalloc(h, &h->growth, 1) | dalloc(h, &h->status_d, 1) | dalloc(h, &h->stats_d, 4);
   if (rc) return 1;
   CUDA_TRY(cudaMallocHost((void **)&h->status_h, sizeof(StepStatus)));
+  CUDA_TRY(cudaMallocHost((void **)&h->dist_h, 4 * sizeof(double)));
   CUDA_TRY(cudaMemset(h->nall, 0, T * sizeof(int)));
   CUDA_TRY(cudaMemset(h->AE, 0, 5 * nt * sizeof(double)));
   CUDA_TRY(cudaMemset(h->norm, 0, nt * sizeof(double)));
@@ -896,7 +937,7 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   h->uploaded = true;
   if (h->dist) {  // a fresh upload holds complete data on every rank: re-derive owned / ghost / remote
     k_dist_init_flags<<<((int)n2 + 255) / 256, 256, 0, st>>>(h->P, h->D, h->x, h->lflag);
-    if (rebuild_local_list(h, st)) return 1;
+    if (rebuild_local_list(h)) return 1;
     CUDA_TRY(cudaStreamSynchronize(st));
   }
   return 0;
@@ -1127,7 +1168,9 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
   const size_t n2 = (size_t)p.ntotal2;
   const size_t msg = (size_t)HALO_REC * ((size_t)D.cap + 1);
   if (dalloc(h, &h->lflag, n2) || dalloc(h, &h->halo_cnt, 4)) return 1;
-  if (dalloc(h, &h->list_ids[0], n2) || dalloc(h, &h->list_ids[1], n2) || dalloc(h, &h->list_n, 2)) return 1;
+  if (dalloc(h, &h->list_ids[0], n2) || dalloc(h, &h->list_ids[1], n2) || dalloc(h, &h->list_n, 2) ||
+      dalloc(h, &h->list_keep, n2) || dalloc(h, &h->list_pos, n2))
+    return 1;
   if (dalloc(h, &h->gt_buf, (size_t)GT_CAP) || dalloc(h, &h->gt_mine, 2 * (size_t)GT_PCAP) ||
       dalloc(h, &h->gt_all, 2 * (size_t)GT_PCAP * nranks) || dalloc(h, &h->gt_out2, 4) || dalloc(h, &h->gt_sel, 1))
     return 1;
@@ -1138,7 +1181,7 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
   CUDA_TRY(cudaMemset(h->halo_cnt, 0, 4 * sizeof(int)));
   h->dist = true;
   k_dist_init_flags<<<((int)n2 + 255) / 256, 256, 0, h->stream>>>(h->P, h->D, h->x, h->lflag);
-  if (rebuild_local_list(h, h->stream)) return 1;
+  if (rebuild_local_list(h)) return 1;
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;
 }
@@ -1186,6 +1229,7 @@ int spsph_destroy(spsph_handle *h) {
   cudaFree(h->L.idxD);
   cudaFree(h->L.wD);
   if (h->status_h) cudaFreeHost(h->status_h);
+  if (h->dist_h) cudaFreeHost(h->dist_h);
   if (h->ev0) cudaEventDestroy(h->ev0);
   if (h->ev1) cudaEventDestroy(h->ev1);
   if (h->ev_fork) cudaEventDestroy(h->ev_fork);
