@@ -53,6 +53,7 @@ struct spsph_handle {
 
   // particle state (original order)
   double *x = nullptr, *x00 = nullptr, *rho = nullptr, *mass = nullptr, *hsml = nullptr, *mor = nullptr;
+  double2 *mrho = nullptr;  // {mass, rho} per particle
   Rec4 *NB[2] = {nullptr, nullptr}, *SB[2] = {nullptr, nullptr}, *SVb[2] = {nullptr, nullptr}, *SA = nullptr;
   double *NA = nullptr, *NSa = nullptr, *SVa = nullptr, *av = nullptr, *fbound = nullptr;
   double *NSb[2] = {nullptr, nullptr}, *SFb[2] = {nullptr, nullptr};
@@ -152,9 +153,13 @@ static const char *kKernelNames[KID_N] = {"k_domain_bbox", "k_grid_params", "k_z
 namespace {
 
 __global__ void k_upload_derive(int n2, int nt, const double *__restrict__ mass, const double *__restrict__ rho,
-                                double *__restrict__ mor, const double *__restrict__ ivars, double *__restrict__ epsp) {
+                                double *__restrict__ mor, double2 *__restrict__ mrho, const double *__restrict__ ivars,
+                                double *__restrict__ epsp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n2) mor[i] = mass[i] / rho[i];  // same IEEE division as the reference's mass(j)/rho(j)
+  if (i < n2) {
+    mor[i] = mass[i] / rho[i];  // same IEEE division as the reference's mass(j)/rho(j)
+    mrho[i] = make_double2(mass[i], rho[i]);  // one 16-byte gather where a sweep needs both
+  }
   if (i < nt) epsp[i] = ivars[(size_t)SPSPH_NINT_VARS * i];
 }
 __global__ void k_download_ivars(int nt, const double *__restrict__ epsp, double *__restrict__ ivars) {
@@ -227,6 +232,7 @@ StatePtrs state_ptrs(spsph_handle *h, int wb) {
   s.rho = h->rho;
   s.hsml = h->hsml;
   s.mor = h->mor;
+  s.mrho = h->mrho;
   s.wallpos = h->wallpos;
   s.horiz = h->horiz;
   s.bc_or_not = h->bc_or_not;
@@ -827,7 +833,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   const size_t n2 = (size_t)p->ntotal2, nt = (size_t)p->ntotal, nn = (size_t)p->nnode, ns = (size_t)p->nstress;
   int rc = 0;
   rc |= dalloc(h, &h->x, 2 * n2) | dalloc(h, &h->x00, 2 * n2) | dalloc(h, &h->rho, n2) | dalloc(h, &h->mass, n2);
-  rc |= dalloc(h, &h->hsml, n2) | dalloc(h, &h->mor, n2);
+  rc |= dalloc(h, &h->hsml, n2) | dalloc(h, &h->mor, n2) | dalloc(h, &h->mrho, n2);
   rc |= dalloc(h, &h->NA, 2 * nn) | dalloc(h, &h->SA, ns) | dalloc(h, &h->NSa, 4 * nn) | dalloc(h, &h->SVa, 2 * ns);
   rc |= dalloc(h, &h->av, 2 * nn) | dalloc(h, &h->fbound, 2 * nn);
   for (int b = 0; b < 2; ++b) {
@@ -900,7 +906,8 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   CUDA_TRY(up(h->stage_vel, s->vel, 2 * nt * 8));
   CUDA_TRY(up(h->stage_stress, s->stress, 4 * nt * 8));
   CUDA_TRY(up(h->ivars, s->internal_vars, (size_t)SPSPH_NINT_VARS * nt * 8));
-  k_upload_derive<<<((int)n2 + 255) / 256, 256, 0, st>>>((int)n2, (int)nt, h->mass, h->rho, h->mor, h->ivars, h->epsp);
+  k_upload_derive<<<((int)n2 + 255) / 256, 256, 0, st>>>((int)n2, (int)nt, h->mass, h->rho, h->mor, h->mrho, h->ivars,
+                                                          h->epsp);
   k_pack_state<<<((int)nt + 255) / 256, 256, 0, st>>>(h->P, h->stage_vel, h->stage_stress, state_ptrs(h, 0));
   CUDA_TRY(up(h->fdp, s->f_drucker, nt * 8));
   CUDA_TRY(up(h->displ, s->displ, 2 * nn * 8));

@@ -33,6 +33,7 @@ struct StatePtrs {
   // constant per step / persistent (original particle order)
   const double *x;  // (2, ntotal2)
   const double *mass, *rho, *hsml, *mor;
+  const double2 *mrho;  // {mass, rho}: one gather where a sweep needs both (the cspm_norm pass)
   const float *wallpos, *horiz;
   const int *bc_or_not, *bc_info;
   // format A
@@ -306,29 +307,39 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
     const int *arrs[4] = {L.idx0, L.h0lo, L.h0hi, reinterpret_cast<const int *>(L.w0)};
     const double *__restrict__ NAv = st.NA;
     const Rec4 *__restrict__ NBv = st.NBr;
-    ell_stream<NARR, A_NG, double2, A_GR, A_GR>(
+    // FIRST also needs the partner's mass and density (cspm_norm, main:433): they ride in the same 32-byte record
+    // (format B) or come with one extra 16-byte gather (format A)
+    struct RecN {
+      double2 v, mr;
+    };
+    ell_stream<NARR, A_NG, RecN, A_GR, A_GR>(
         arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM_G(NARR, A_NG, A_GR),
         [&](int q) {
           const int qq = (q < 0 || q >= P.nnode) ? 0 : q;
+          RecN o;
           if (FROMB) {
             const Rec4 r = ldrec(NBv, qq);
-            return make_double2(r.a, r.b);
+            o.v = make_double2(r.a, r.b);
+            o.mr = make_double2(r.c, r.d);
+          } else {
+            o.v = ld2(NAv, qq);
+            o.mr = FIRST ? st.mrho[qq] : make_double2(0.0, 0.0);
           }
-          return ld2(NAv, qq);
+          return o;
         },
-        [&](const int(&q)[A_GR], const int(&pay)[NARR - 1][A_GR], const double2(&r)[A_GR], int nvalid) {
+        [&](const int(&q)[A_GR], const int(&pay)[NARR - 1][A_GR], const RecN(&r)[A_GR], int nvalid) {
 #pragma unroll
           for (int u = 0; u < A_GR; ++u) {
             const bool ok = (u < nvalid) && (q[u] < P.nnode);  // dummy partners (type 9) take no part
             const double h2 = h0_of(pay[0][u], pay[1][u]);     // (mass(i)/rho(i))*w, main:431
-            const double tx = vtx + r[u].x * h2, ty = vty + r[u].y * h2;
+            const double tx = vtx + r[u].v.x * h2, ty = vty + r[u].v.y * h2;
             vtx = ok ? tx : vtx;
             vty = ok ? ty : vty;
             if (FIRST) {
-              if (ok) {
-                const double wd = (double)__int_as_float(pay[NARR - 2][u]);
-                nrm = nrm + (wd * st.mass[q[u]]) / st.rho[q[u]];
-              }
+              const double wd = (double)__int_as_float(pay[NARR - 2][u]);
+              const double rq = ok ? r[u].mr.y : 1.0;
+              const double nn = nrm + div_rn(wd * r[u].mr.x, rq, __drcp_rn(rq));
+              nrm = ok ? nn : nrm;
             }
           }
         });
@@ -378,6 +389,7 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
     struct RecS {
       Rec4 s;
       double ep;
+      double2 mr;
     };
     constexpr int NARR = FIRST ? 4 : 3;
     __shared__ __align__(16) int smem[4 * ELL_SMEM_G(NARR, A_NG, A_GR)];
@@ -389,6 +401,7 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
           RecS r;
           r.s = FROMB ? ld256(st.SFbr + 4 * (size_t)qs) : ldrec(st.SA, qs);
           r.ep = EPSP ? st.epsp[qs + P.nnode] : 0.0;
+          r.mr = FIRST ? st.mrho[qs + P.nnode] : make_double2(0.0, 0.0);
           return r;
         },
         [&](const int(&q)[A_GR], const int(&pay)[NARR - 1][A_GR], const RecS(&r)[A_GR], int nvalid) {
@@ -407,10 +420,10 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
               te = ok ? ne : te;
             }
             if (FIRST) {
-              if (ok) {
-                const double wd = (double)__int_as_float(pay[NARR - 2][u]);
-                nrm = nrm + (wd * st.mass[q[u]]) / st.rho[q[u]];
-              }
+              const double wd = (double)__int_as_float(pay[NARR - 2][u]);
+              const double rq = ok ? r[u].mr.y : 1.0;
+              const double nn = nrm + div_rn(wd * r[u].mr.x, rq, __drcp_rn(rq));
+              nrm = ok ? nn : nrm;
             }
           }
         });
