@@ -1,0 +1,47 @@
+"""TEST INFRASTRUCTURE. The runs of the reference's own executables that pin the oracle: shared by
+oracle/make_reference_goldens.py (which produces tests/golden/ref_<case>.npz) and the tests that read them."""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "stress-particle-sph_b200"))
+from spsph import decks  # noqa: E402
+
+# case -> (binary, deck spec, steps to run, steps whose frames are kept | plot cadence).
+# A tuple of steps: the binary plots every step (plot_step = 1: its fp32 output clock then fires exactly once per
+# step, 1_SPH_2018.f90:86-89) and the listed frames are kept. That only works for short runs: the reference opens
+# its frame files on unit numbers nnode + step etc. (mat:2937-2939), which collide with its own input unit 997 at
+# step 136 of the Bui problem. Long runs therefore plot every `cadence` steps and keep whatever frames appear
+# (the output clock is fp32, so a frame can land one step late).
+CASES = {
+    # the three top-level example inputs (BASELINE configs 0-2), 100 steps as north_star asks
+    "bui": ("bui", lambda n: decks.bui_spec(maxtimestep=n), 100, (1, 50, 100)),
+    "vs": ("vs", lambda n: decks.vertical_slope_spec(maxtimestep=n), 100, (1, 50, 100)),
+    "sl": ("sl", lambda n: decks.strain_localisation_spec(maxtimestep=n), 100, (100,)),
+    # a long Bui run: the pair list grows and the split traversal order of SURVEY App. B is exercised
+    "bui_long": ("bui", lambda n: decks.bui_spec(maxtimestep=n), 610, 300),
+    # the other input sets the reference ships
+    "bui_outside": ("bui", lambda n: decks.bui_spec(maxtimestep=n, mode="outside"), 60, (60,)),
+    "bui_inside_sp1": ("bui", lambda n: decks.bui_spec(maxtimestep=n, mode="inside", npoints=1), 60, (60,)),
+    "bui_inside_sp2": ("bui", lambda n: decks.bui_spec(maxtimestep=n, mode="inside", npoints=2), 60, (60,)),
+    "bui_inside_sp3": ("bui", lambda n: decks.bui_spec(maxtimestep=n, mode="inside", npoints=3), 60, (60,)),
+    "bui_standard": ("bui", lambda n: decks.bui_spec(maxtimestep=n, mode="standard"), 60, (60,)),
+    "vs_sp2": ("vs", lambda n: decks.vertical_slope_spec(maxtimestep=n, npoints=2), 60, (60,)),
+    "vs_sp3": ("vs", lambda n: decks.vertical_slope_spec(maxtimestep=n, npoints=3), 60, (60,)),
+    "vs_standard": ("vs", lambda n: decks.vertical_slope_spec(maxtimestep=n, standard=True), 60, (60,)),
+    "sl_sp2": ("sl", lambda n: decks.strain_localisation_spec(maxtimestep=n, npoints=2), 40, (40,)),
+    "sl_sp3": ("sl", lambda n: decks.strain_localisation_spec(maxtimestep=n, npoints=3), 40, (40,)),
+    "sl_standard": ("sl", lambda n: decks.strain_localisation_spec(maxtimestep=n, standard=True), 40, (40,)),
+    # the inside approach pressed against its walls long enough for boundary_forces to act
+    "bui_inside_sp1_long": ("bui", lambda n: decks.bui_spec(maxtimestep=n, mode="inside", npoints=1), 1510, 1500),
+}
+
+
+def golden_path(case):
+    return os.path.join(ROOT, "tests", "golden", f"ref_{case}.npz")
+
+
+def spec_of(case):
+    """deck specification of a case, with the step count the golden run used"""
+    which, spec_fn, nsteps, _ = CASES[case]
+    return which, spec_fn(nsteps)

@@ -2,12 +2,17 @@
 // may include, link or call this file.  Only tests/, __graft_entry__.smoke() and bench.py's
 // cpu_baseline / --impl reference legs use it, and only as the checker / CPU baseline.
 //
-// PARITY UNPINNED: the reference ships no golden vectors, tests or expected outputs, and it cannot be
-// built or run here (no Fortran compiler in this image; the shipped ELF binaries need libgfortran.so.3).
-// This file is a serial C++ restatement of the reference's time step that follows the Fortran statement
+// PARITY PINNED against the reference itself. The reference ships no golden vectors or tests and cannot be
+// COMPILED here (no Fortran compiler in this image), but its repository ships the authors' own executables
+// (example_problems/*/sph, gfortran 4.8.5 -O3, built from the sources beside them) that only lack
+// libgfortran.so.3. oracle/gfortran_shim.c supplies that run-time library, oracle/make_reference_goldens.py runs
+// the unmodified binaries on every input set the reference ships (100 steps of the three problems, 60 / 40 steps
+// of the 11 variants, 602 steps through list growth, 1501 steps into the wall forces) and stores what they print,
+// all digits, in tests/golden/ref_*.npz. This file reproduces all of it BIT FOR BIT -- positions, velocities,
+// stresses, plastic strain of every velocity and stress particle (tests/test_reference_pinned_cpu.py).
+// It is a serial C++ restatement of the reference's time step that follows the Fortran statement
 // by statement -- same loop order, same expression order, same fp32/fp64 mix, same
 // pair creation and traversal order (App. B), zero-initialised reading of the undefined values (App. C).
-// tools/make_reference_goldens.sh documents how to pin it with a real gfortran build elsewhere.
 //
 // Reference files followed ("main:" = code/2_SPH_main_2018.f90, identical in all copies except two
 // lines; "mat:" = example_problems/soil_failure_bui_et_al_2008/3_SPH_material_2018.f90 unless a copy is
