@@ -39,6 +39,7 @@ BIN = {"bui": os.path.join(EX, "soil_failure_bui_et_al_2008", "sph"),
 SHIM_DIR = os.path.join(ROOT, "oracle", "_ref")
 LOADER = "/lib64/ld-linux-x86-64.so.2"
 
+import reference_runner  # noqa: E402
 from ref_cases import CASES  # noqa: E402
 
 
@@ -78,8 +79,7 @@ def run_case(name):
     os.makedirs(run)
     decks.write_deck(run, spec)
     t0 = time.time()
-    with open(os.path.join(run, "stdout.txt"), "w") as so, open(os.path.join(run, "stderr.txt"), "w") as se:
-        rc = subprocess.run([LOADER, "--library-path", SHIM_DIR, BIN[which]], cwd=run, stdout=so, stderr=se).returncode
+    rc, _ = reference_runner.run(run, which)
     if rc != 0:
         raise RuntimeError(f"{name}: the reference binary exited with {rc}: " + open(os.path.join(run, "stderr.txt")).read()[-400:])
     out = {"variant": which, "nsteps": nsteps}
