@@ -164,10 +164,11 @@ def test_oracle_vertical_slope_static_limit(deck_dir):
 
 def test_golden_fixtures_match_oracle(deck_dir):
     """tests/golden/*.npz were produced by tests/golden/make_golden.py from this oracle; they pin the oracle
-    (and through it the CUDA path) against accidental change. They are NOT reference outputs."""
+    (and through it the CUDA path) against accidental change. They are NOT reference outputs -- those are
+    tests/golden/ref_*.npz, checked by tests/test_reference_pinned_cpu.py."""
     import spsph
     from oracle_binding import Oracle
-    files = sorted(f for f in os.listdir(GOLD) if f.endswith(".npz")) if os.path.isdir(GOLD) else []
+    files = sorted(f for f in os.listdir(GOLD) if f.endswith("steps.npz")) if os.path.isdir(GOLD) else []
     assert files, "golden fixtures missing"
     for f in files:
         g = np.load(os.path.join(GOLD, f))
