@@ -52,6 +52,7 @@ struct Oracle {
   // state (1-based Fortran arrays stored 0-based, column-major)
   std::vector<double> x, vel, stress, rho, mass, hsml, internal_vars, f_drucker, x0, x00, vx0, displ, x_10, disp_10;
   std::vector<double> grad_u, art_visc, Ddev_strn, f_bound;
+  std::vector<double> subset, normal;  // get_nodes_on_free_surface (module arrays, DP): subset(ntotal), normal(2,ntotal)
   std::vector<int32_t> itype, if_out, bc_or_not, bc_info, bc_int, countiac;
   std::vector<float> wall_position, horizontal_or_not, n_int;
   // pair list: `created` in creation order; traversal order through order_of()
@@ -892,6 +893,140 @@ struct Oracle {
     return true;
   }
 
+  // ---- get_nodes_on_free_surface, mat:1116-1411 (every local is default REAL = fp32; subset, normal, x, mass,
+  // rho, hsml are DP). Uses this step's pair list with the already updated positions (App. C-7). Rewrites
+  // bc_or_not: 1 stays, free-surface particles become 2, all others 0.
+  void get_nodes_on_free_surface() {
+    const size_t nt = (size_t)ntotal;
+    std::vector<float> A(4 * nt, 0.f), ff(2 * nt, 0.f), tt(2 * nt, 0.f), tau(2 * nt, 0.f), f_int(nt, 0.f),
+        grad_f(2 * nt, 0.f), neighbour(nt, 0.f);
+    subset.assign(nt, 0.0);
+    normal.assign(2 * nt, 0.0);
+    const int64_t n = (int64_t)created.size();
+    auto add = [](float acc, double term) { return (float)((double)acc + term); };  // real = real + dp
+    // Step 1: renormalisation matrix and sum of the kernel gradients (pair types 1, 2, 3)
+    for (int64_t t = 0; t < n; ++t) {
+      const Pair &c = created[creation_index(t)];
+      if (c.pint_type < 1 || c.pint_type > 3) continue;
+      const int i = c.pair_i, j = c.pair_j;
+      const size_t a = (size_t)(i - 1), b = (size_t)(j - 1);
+      const float hf1i = (float)(mass[b] * (double)c.dwdx / rho[b]);
+      const float hf1j = (float)(-mass[a] * (double)c.dwdx / rho[a]);
+      A[4 * a + 0] = add(A[4 * a + 0], (X(1, j) - X(1, i)) * (double)hf1i);
+      A[4 * b + 0] = add(A[4 * b + 0], (X(1, i) - X(1, j)) * (double)hf1j);
+      ff[2 * a + 0] = ff[2 * a + 0] + hf1i;
+      ff[2 * b + 0] = ff[2 * b + 0] + hf1j;
+      const float hf2i = (float)(mass[b] * (double)c.dwdy / rho[b]);
+      const float hf2j = (float)(-mass[a] * (double)c.dwdy / rho[a]);
+      A[4 * a + 1] = add(A[4 * a + 1], (X(2, j) - X(2, i)) * (double)hf1i);
+      A[4 * a + 2] = add(A[4 * a + 2], (X(1, j) - X(1, i)) * (double)hf2i);
+      A[4 * a + 3] = add(A[4 * a + 3], (X(2, j) - X(2, i)) * (double)hf2i);
+      A[4 * b + 1] = add(A[4 * b + 1], (X(2, i) - X(2, j)) * (double)hf1j);
+      A[4 * b + 2] = add(A[4 * b + 2], (X(1, i) - X(1, j)) * (double)hf2j);
+      A[4 * b + 3] = add(A[4 * b + 3], (X(2, i) - X(2, j)) * (double)hf2j);
+      ff[2 * a + 1] = ff[2 * a + 1] + hf2i;
+      ff[2 * b + 1] = ff[2 * b + 1] + hf2j;
+    }
+    // Step 2: first approximation of the normal; Step 3a: scan point and tangent
+    for (int i = 1; i <= ntotal; ++i) {
+      const size_t a = (size_t)(i - 1);
+      for (int k = 0; k < 4; ++k)
+        if (std::fabs(A[4 * a + k]) <= 1.e-8f) A[4 * a + k] = 0.f;
+      const float v1 = -(A[4 * a + 0] * ff[2 * a] + A[4 * a + 1] * ff[2 * a + 1]);
+      const float v2 = -(A[4 * a + 2] * ff[2 * a] + A[4 * a + 3] * ff[2 * a + 1]);
+      const float v3 = powf(v1 * v1 + v2 * v2, 0.5f);
+      normal[2 * a] = (double)(v1 / v3);
+      normal[2 * a + 1] = (double)(v2 / v3);
+    }
+    for (int i = 1; i <= ntotal; ++i) {
+      const size_t a = (size_t)(i - 1);
+      tt[2 * a] = (float)(X(1, i) + hsml[a] * normal[2 * a]);
+      tt[2 * a + 1] = (float)(X(2, i) + hsml[a] * normal[2 * a + 1]);
+      tau[2 * a] = (float)(-normal[2 * a + 1]);
+      tau[2 * a + 1] = (float)(normal[2 * a]);
+    }
+    // Step 3b: is there a particle inside the scan region? `me` looks at `other`
+    const float sqrt2 = 1.41421354f;  // 2**0.5 folded by the compiler to the fp32 constant
+    auto scan = [&](int me, int other) {
+      const size_t a = (size_t)(me - 1);
+      if (subset[a] != 0) return;
+      const double dx = X(1, other) - X(1, me), dy = X(2, other) - X(2, me);
+      const float dist = (float)std::pow(dx * dx + dy * dy, (double)0.5f);
+      const float xt1 = (float)(X(1, other) - (double)tt[2 * a]);
+      const float xt2 = (float)(X(2, other) - (double)tt[2 * a + 1]);
+      const float xt_norm = powf(xt1 * xt1 + xt2 * xt2, 0.5f);
+      const float prod_scal = (float)(std::fabs(normal[2 * a] * (double)xt1 + normal[2 * a + 1] * (double)xt2) +
+                                      (double)std::fabs(tau[2 * a] * xt1 + tau[2 * a + 1] * xt2));
+      const float limit = (float)((double)sqrt2 * hsml[a]);
+      if (dist >= limit && (double)xt_norm < hsml[a]) {
+        subset[a] = 2;
+        f_int[a] = -1;
+      } else if (dist < limit && (double)prod_scal < hsml[a]) {
+        subset[a] = 2;
+        f_int[a] = -1;
+      }
+    };
+    for (int64_t t = 0; t < n; ++t) {
+      const Pair &c = created[creation_index(t)];
+      if (c.pint_type == 2 || c.pint_type == 3) {
+        scan(c.pair_i, c.pair_j);
+        scan(c.pair_j, c.pair_i);
+      }
+      if (c.pint_type == 6 || c.pint_type == 9) scan(c.pair_j, c.pair_i);  // pair_i is the wall particle
+    }
+    for (size_t a = 0; a < nt; ++a)
+      if (subset[a] == 0) subset[a] = 1;
+    for (size_t a = 0; a < nt; ++a)
+      if (bc_or_not[a] != 1) bc_or_not[a] = 0;
+    for (size_t a = 0; a < nt; ++a) {
+      if (subset[a] == 2 && bc_or_not[a] != 1)
+        bc_or_not[a] = 0;
+      else if (subset[a] == 1 && bc_or_not[a] != 1)
+        bc_or_not[a] = 2;
+      else if (subset[a] == 1 && bc_or_not[a] == 1)
+        subset[a] = 2;
+    }
+    // Step 4: better normal from the neighbouring surface particles, oriented by the gradient of f_int
+    std::fill(normal.begin(), normal.end(), 0.0);
+    for (int64_t t = 0; t < n; ++t) {
+      const Pair &c = created[creation_index(t)];
+      if (c.pint_type < 1 || c.pint_type > 3) continue;
+      const int i = c.pair_i, j = c.pair_j;
+      const size_t a = (size_t)(i - 1), b = (size_t)(j - 1);
+      if (subset[a] == 1 && subset[b] == 1) {
+        const float x1 = (float)X(1, i), y1 = (float)X(2, i), x2 = (float)X(1, j), y2 = (float)X(2, j);
+        const float x_vect = x2 - x1, y_vect = y2 - y1;
+        normal[2 * a] = normal[2 * a] - (double)y_vect;
+        normal[2 * a + 1] = normal[2 * a + 1] + (double)x_vect;
+        normal[2 * b] = normal[2 * b] - (double)y_vect;
+        normal[2 * b + 1] = normal[2 * b + 1] + (double)x_vect;
+        neighbour[a] = neighbour[a] + 1;
+        neighbour[b] = neighbour[b] + 1;
+      }
+      const float hf1i = (float)(mass[b] * (double)c.dwdx / rho[b]);
+      const float hf1j = (float)(-mass[a] * (double)c.dwdx / rho[a]);
+      const float hf2i = (float)(mass[b] * (double)c.dwdy / rho[b]);
+      const float hf2j = (float)(-mass[a] * (double)c.dwdy / rho[a]);
+      grad_f[2 * a] = grad_f[2 * a] + (f_int[b] - f_int[a]) * hf1i;
+      grad_f[2 * b] = grad_f[2 * b] + (f_int[a] - f_int[b]) * hf1j;
+      grad_f[2 * a + 1] = grad_f[2 * a + 1] + (f_int[b] - f_int[a]) * hf2i;
+      grad_f[2 * b + 1] = grad_f[2 * b + 1] + (f_int[a] - f_int[b]) * hf2j;
+    }
+    for (size_t a = 0; a < nt; ++a) {
+      if (subset[a] != 1) continue;
+      normal[2 * a] = normal[2 * a] / (double)neighbour[a];
+      normal[2 * a + 1] = normal[2 * a + 1] / (double)neighbour[a];
+      const float norm_vect = (float)std::pow(normal[2 * a] * normal[2 * a] + normal[2 * a + 1] * normal[2 * a + 1], (double)0.5f);
+      normal[2 * a] = normal[2 * a] / (double)norm_vect;
+      normal[2 * a + 1] = normal[2 * a + 1] / (double)norm_vect;
+      const float p_scal = (float)((double)grad_f[2 * a] * normal[2 * a] + (double)grad_f[2 * a + 1] * normal[2 * a + 1]);
+      if (p_scal < 0) {
+        normal[2 * a] = -normal[2 * a];
+        normal[2 * a + 1] = -normal[2 * a + 1];
+      }
+    }
+  }
+
   // ---- XSPH_update, main:189-239 ---------------------------------------------------------------
   void xsph_update() {
     std::vector<double> vel_sum(2 * (size_t)ntotal, 0.0);
@@ -914,8 +1049,10 @@ struct Oracle {
         }
         n_int[i - 1] = n_int[i - 1] + 1;
         n_int[j - 1] = n_int[j - 1] + 1;
-        // the transient bc_or_not = 3 marks (main:224-230) are wiped by get_nodes_on_free_surface before
-        // anything reads them (App. C-7); not restated.
+        // main:224-230: neighbours of a free-surface node are marked 3 until get_nodes_on_free_surface rewrites
+        // bc_or_not at the end of this step (a marked particle with bc_or_not == 1 thereby loses its BCs)
+        if (bc_or_not[i - 1] == 2 && bc_or_not[j - 1] != 2) bc_or_not[j - 1] = 3;
+        if (bc_or_not[j - 1] == 2 && bc_or_not[i - 1] != 2) bc_or_not[i - 1] = 3;
       }
     }
     for (int i = 1; i <= ntotal; ++i)
@@ -1038,8 +1175,7 @@ struct Oracle {
           x[k] = x0[k] + (double)vel_half * dt_sph;
         }
       }
-      // get_nodes_on_free_surface (mat:1135-1430): only feeds surface_points.csv when ifsigman = 0; see
-      // SURVEY App. C-7. Not part of the state; restated separately when the "next" row is built.
+      get_nodes_on_free_surface();  // main:152-154 (ndimn == 2 always here)
       if (p.sp_sph && !p.inside_approach) shift_stress_points();
       if (!p.sp_sph)
         for (int i = 1; i <= nnode; ++i) {

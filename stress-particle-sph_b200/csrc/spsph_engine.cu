@@ -50,6 +50,7 @@ struct spsph_handle {
   std::string err;
   std::vector<void *> allocs;
   bool uploaded = false;
+  bool have_lists = false;  // the pair lists of a completed step are on the device (free-surface detection)
 
   // particle state (original order)
   double *x = nullptr, *x00 = nullptr, *rho = nullptr, *mass = nullptr, *hsml = nullptr, *mor = nullptr;
@@ -710,6 +711,7 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     mark(h, KID_SHIFT);
   }
   CUDA_TRY(cudaGetLastError());
+  h->have_lists = true;
   if (h->profiling) prof_collect(h);
   return 0;
 }
@@ -746,6 +748,9 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   if (p->cont_density) return fail("cont_density = T is not supported");
   if (p->art_stress) return fail("art_stress = T is not supported");
   if (p->ifsigman != 0) return fail("ifsigman = 1 (apply_stress_free) is not supported");
+  if (p->xsph && p->update_x && p->no_bcs > 0)
+    return fail("XSPH together with boundary conditions is not supported (XSPH_update strips the BC flag of particles "
+                "next to a free-surface node, main:224-230)");
   if (p->ntype_eco > 1 && !(p->ncrit == 2 || p->ncrit == 12))
     return fail("only ncrit = 2 (von Mises) and ncrit = 12 (Drucker-Prager) are supported");
   if (p->ntype_eco > 1 && p->ncrit == 2 && !(p->props[6] > (double)0.001f))
@@ -941,6 +946,7 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
     if (dalloc(h, &h->cell_fill, 3 * (size_t)h->cell_stride)) return 1;
   }
   h->m_pairs = 0;
+  h->have_lists = false;
   h->uploaded = true;
   if (h->dist) {  // a fresh upload holds complete data on every rank: re-derive owned / ghost / remote
     k_dist_init_flags<<<((int)n2 + 255) / 256, 256, 0, st>>>(h->P, h->D, h->x, h->lflag);
@@ -1034,6 +1040,17 @@ int spsph_download(spsph_handle *h, const spsph_state *s) {
   if (s->internal_vars) {
     k_download_ivars<<<((int)nt + 255) / 256, 256, 0, st>>>((int)nt, h->epsp, h->ivars);
     CUDA_TRY(down(s->internal_vars, h->ivars, (size_t)SPSPH_NINT_VARS * nt * 8));
+  }
+  if (s->bc_or_not && p.update_x && h->have_lists) {
+    // get_nodes_on_free_surface (main:152-154 runs it at the end of every step; only bc_or_not leaves it)
+    SlotMap ML = h->M;
+    ML.nn = h->nloc[0];
+    ML.ns = h->nloc[1];
+    ML.nd = h->nloc[2];
+    const int T = ML.nnp + ML.nsp;
+    k_free_surface<<<(T + 127) / 128, 128, 0, st>>>(h->P, ML, sort_arrays(h), h->pos_of, h->L, h->n0, h->n1, h->growth,
+                                                    h->x, h->mass, h->rho, h->hsml, h->bc_or_not);
+    CUDA_TRY(cudaGetLastError());
   }
   CUDA_TRY(down(s->f_drucker, h->fdp, nt * 8));
   CUDA_TRY(down(s->x00, h->x00, 2 * n2 * 8));

@@ -1112,6 +1112,158 @@ __global__ void k_shift(DevParams P, const Rec4 *__restrict__ NB, double *__rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------------
+// get_nodes_on_free_surface, mat:1116-1411, steps 1-3 and the bc_or_not rewrite (mat:1333-1349): which particles
+// lie on the free surface. Runs on demand (spsph_download) with the pair lists of the last step and the positions
+// after it, exactly what the reference holds when it writes surface_points.csv. One thread per particle.
+//   Step 1 sums fp32 accumulators over pair types 1, 2, 3 in the reference's traversal order; the two gather
+//   lists of a particle (cross-species / same-species) are each in that order and are merged on the fly by the
+//   creation-order keys (new pairs first and descending, then old pairs ascending: SURVEY App. B).
+//   Step 3 is an OR over pairs, so its order is irrelevant.
+// Stress-stress entries carry no stored gradient; it is re-evaluated from the positions the list was built with
+// (S.pos), the same arithmetic as k_fill. Step 4 (the refined normal) only feeds apply_stress_free (ifsigman = 1,
+// not supported) and is not evaluated.
+// Deviation: the reference's `x**0.5` calls libm powf/pow, which are not correctly rounded (powf differs from sqrtf
+// in 6e-4 of all arguments, by one ulp); the device uses the correctly rounded square root. A classification can
+// differ only when a comparison of step 3 is decided by that last bit.
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_free_surface(DevParams P, SlotMap M, SortArrays S, const int *__restrict__ pos_of, ListPtrs L,
+                               const int *__restrict__ n0, const int *__restrict__ n1,
+                               const GrowthRule *__restrict__ growth, const double *__restrict__ x,
+                               const double *__restrict__ mass, const double *__restrict__ rho,
+                               const double *__restrict__ hsml, int *__restrict__ bc_or_not) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M.nnp + M.nsp) return;
+  int sp, k;
+  if (!slot_decode(M, t, sp, k)) return;
+  const int id = S.order[sp][k];
+  const int c = S.cell[sp][k];
+  const int cnt0 = c < 0 ? 0 : n0[t], cnt1 = c < 0 ? 0 : n1[t];
+  const int lane = t & 31, sl = t / SLICE;
+  const size_t o0 = (size_t)L.off0[sl] + lane;
+  const size_t o1 = (size_t)(sp == SP_NODE ? L.offC[sl] : L.offD[sl]) + lane;
+  const GrowthRule gr = *growth;
+  const okey_t kp = make_key(c < 0 ? 0 : c, sp, id);
+  const double2 xp = ld2(x, id);
+  const double hp = hsml[id];
+  const double2 pp_old = S.pos[sp][k];
+  const KernelConsts K = kernel_consts(P, S.h[sp][k]);
+  auto species = [&](int q) { return q < P.nnode ? SP_NODE : (q < P.ntotal ? SP_STRESS : SP_DUMMY); };
+  auto key_of = [&](int q) {
+    const int sq = species(q);
+    return make_key(S.cell[sq][pos_of[q]], sq, q);
+  };
+  // traversal precedence of an entry: new pairs first (descending key), then old pairs (ascending key)
+  auto before = [&](okey_t ka, okey_t kb) {
+    const bool oa = pair_is_old(gr, kp, ka), ob = pair_is_old(gr, kp, kb);
+    if (oa != ob) return !oa;
+    return oa ? ka < kb : ka > kb;
+  };
+  float A1 = 0.f, A2 = 0.f, A3 = 0.f, A4 = 0.f, f1 = 0.f, f2 = 0.f;
+  auto step1 = [&](int q, float gx, float gy) {  // gx, gy: gradient from this particle's perspective
+    const double mq = mass[q], rq = rho[q];
+    const float h1 = (float)(mq * (double)gx / rq), h2 = (float)(mq * (double)gy / rq);
+    const double2 xq = ld2(x, q);
+    A1 = (float)((double)A1 + (xq.x - xp.x) * (double)h1);
+    f1 = f1 + h1;
+    A2 = (float)((double)A2 + (xq.y - xp.y) * (double)h1);
+    A3 = (float)((double)A3 + (xq.x - xp.x) * (double)h2);
+    A4 = (float)((double)A4 + (xq.y - xp.y) * (double)h2);
+    f2 = f2 + h2;
+  };
+  auto entry1 = [&](int e, int &q, float &gx, float &gy) {  // same-species entry e
+    const size_t a = o1 + (size_t)e * SLICE;
+    if (sp == SP_NODE) {
+      q = L.idxC[a];
+      gx = L.gxC[a];
+      gy = L.gyC[a];
+    } else {
+      q = L.idxD[a];
+      const double2 pq = S.pos[SP_STRESS][pos_of[q]];
+      const double hq = S.h[SP_STRESS][pos_of[q]];
+      const double dx = pp_old.x - pq.x, dy = pp_old.y - pq.y;
+      double d2 = dx * dx;
+      d2 = d2 + dy * dy;
+      const double mh = (K.h + hq) / 2.;
+      const double r = sqrt(d2);
+      double w, gxd = 0.0, gyd = 0.0;
+      if (mh == K.h)
+        sph_kernel_fast<true>(K, r, dx, dy, w, gxd, gyd);
+      else
+        sph_kernel(P, r, dx, dy, mh, w, gxd, gyd);
+      gx = (float)gxd;
+      gy = (float)gyd;
+    }
+  };
+  // Step 1: merged traversal of the type-1 entries of list 0 and all entries of list C / D
+  {
+    int e0 = 0, e1 = 0;
+    auto skip_walls = [&]() {
+      while (e0 < cnt0 && L.idx0[o0 + (size_t)e0 * SLICE] >= P.ntotal) ++e0;
+    };
+    skip_walls();
+    while (e0 < cnt0 || e1 < cnt1) {
+      bool take0;
+      if (e0 >= cnt0)
+        take0 = false;
+      else if (e1 >= cnt1)
+        take0 = true;
+      else {
+        const int q0 = L.idx0[o0 + (size_t)e0 * SLICE];
+        const int q1 = sp == SP_NODE ? L.idxC[o1 + (size_t)e1 * SLICE] : L.idxD[o1 + (size_t)e1 * SLICE];
+        take0 = before(key_of(q0), key_of(q1));
+      }
+      if (take0) {
+        const size_t a = o0 + (size_t)e0 * SLICE;
+        const float gx = L.gx0[a], gy = L.gy0[a];  // reference orientation: pair_i = stress particle
+        if (sp == SP_STRESS)
+          step1(L.idx0[a], gx, gy);
+        else
+          step1(L.idx0[a], -gx, -gy);
+        ++e0;
+        skip_walls();
+      } else {
+        int q;
+        float gx, gy;
+        entry1(e1, q, gx, gy);
+        step1(q, gx, gy);
+        ++e1;
+      }
+    }
+  }
+  // Step 2: first approximation of the normal, scan point and tangent
+  if (fabsf(A1) <= 1.e-8f) A1 = 0.f;
+  if (fabsf(A2) <= 1.e-8f) A2 = 0.f;
+  if (fabsf(A3) <= 1.e-8f) A3 = 0.f;
+  if (fabsf(A4) <= 1.e-8f) A4 = 0.f;
+  const float v1 = -(A1 * f1 + A2 * f2), v2 = -(A3 * f1 + A4 * f2);
+  const float v3 = __fsqrt_rn(v1 * v1 + v2 * v2);
+  const double nx = (double)(v1 / v3), ny = (double)(v2 / v3);
+  const float tt1 = (float)(xp.x + hp * nx), tt2 = (float)(xp.y + hp * ny);
+  const float tau1 = (float)(-ny), tau2 = (float)nx;
+  const float limit = (float)((double)1.41421354f * hp);
+  // Step 3: is any same-species or wall partner inside the scan region?
+  bool covered = false;
+  auto scan = [&](int q) {
+    const double2 xq = ld2(x, q);
+    const double dx = xq.x - xp.x, dy = xq.y - xp.y;
+    const float dist = (float)sqrt(dx * dx + dy * dy);
+    const float xt1 = (float)(xq.x - (double)tt1), xt2 = (float)(xq.y - (double)tt2);
+    const float xt_norm = __fsqrt_rn(xt1 * xt1 + xt2 * xt2);
+    const float prod_scal = (float)(fabs(nx * (double)xt1 + ny * (double)xt2) + (double)fabsf(tau1 * xt1 + tau2 * xt2));
+    if (dist >= limit && (double)xt_norm < hp)
+      covered = true;
+    else if (dist < limit && (double)prod_scal < hp)
+      covered = true;
+  };
+  for (int e = 0; e < cnt1 && !covered; ++e) scan(sp == SP_NODE ? L.idxC[o1 + (size_t)e * SLICE] : L.idxD[o1 + (size_t)e * SLICE]);
+  for (int e = 0; e < cnt0 && !covered; ++e) {
+    const int q = L.idx0[o0 + (size_t)e * SLICE];
+    if (q >= P.ntotal) scan(q);
+  }
+  if (bc_or_not[id] != 1) bc_or_not[id] = covered ? 0 : 2;
+}
+
 __global__ void k_pair_stats(SlotMap M, const int *__restrict__ nall, int *__restrict__ out /* max,min,zero */) {
   int mx = 0, mn = 1000, nz = 0;
   const int n = M.total();

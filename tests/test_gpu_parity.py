@@ -13,7 +13,7 @@ REL_TOL = 1e-9  # north_star tolerance (relative L-inf after 100 steps)
 pytestmark = pytest.mark.gpu
 
 STATE_KEYS = ("x", "vel", "stress", "internal_vars", "f_drucker", "displ", "x_10", "disp_10", "n_int", "bc_int",
-              "if_out_domain")
+              "if_out_domain", "bc_or_not")  # bc_or_not: get_nodes_on_free_surface marks (2 = on the free surface)
 
 
 def _load(deck_dir, kind, **kw):

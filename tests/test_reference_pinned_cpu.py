@@ -31,6 +31,12 @@ def compare_with_golden(case, g, step, arrays, p, label):
                     f"{label} differs from the reference binary: case {case}, step {step}, "
                     f"{'velocity' if tag == 'n' else 'stress'} particles, field {key}: rel Linf "
                     f"{d.max() / max(np.abs(ref).max(), 1e-300):.3e} (worst particle {k}: ref {ref[k]}, got {mine[k]})")
+    # surface_points.csv: positions of the velocity particles that get_nodes_on_free_surface marked (bc_or_not = 2)
+    surf = arrays["x"][:nn][arrays["bc_or_not"][:nn] == 2]
+    ref = g[f"surf{step}"]
+    assert surf.shape == ref.shape and np.array_equal(surf, ref), (
+        f"{label}: free-surface nodes differ from the reference binary's surface_points.csv: case {case}, step {step}, "
+        f"{len(surf)} vs {len(ref)} nodes")
 
 
 @pytest.mark.parametrize("case", list(CASES))
