@@ -32,6 +32,14 @@ CASES = {
     "sl_sp2": ("sl", lambda n: decks.strain_localisation_spec(maxtimestep=n, npoints=2), 40, (40,)),
     "sl_sp3": ("sl", lambda n: decks.strain_localisation_spec(maxtimestep=n, npoints=3), 40, (40,)),
     "sl_standard": ("sl", lambda n: decks.strain_localisation_spec(maxtimestep=n, standard=True), 40, (40,)),
+    # the synthetic refinements bench.py runs (BASELINE configs 3 and 4) at a size the reference can do
+    "bui_refined": ("bui", lambda n: decks.refined_bui_spec(ncol=68, maxtimestep=n), 30, (30,)),
+    "vs_wide": ("vs", lambda n: decks.wide_slope_spec(ncol=60, nslab=2, maxtimestep=n), 30, (30,)),
+    # smoothing kernels other than the cubic spline (main:1494-1536)
+    "bui_gauss": ("bui", lambda n: dict(decks.bui_spec(maxtimestep=n), skf=2), 30, (30,)),
+    "bui_quintic": ("bui", lambda n: dict(decks.bui_spec(maxtimestep=n), skf=3), 30, (30,)),
+    "vs_gauss": ("vs", lambda n: dict(decks.vertical_slope_spec(maxtimestep=n), skf=2), 30, (30,)),
+    "sl_quintic": ("sl", lambda n: dict(decks.strain_localisation_spec(maxtimestep=n), skf=3), 20, (20,)),
     # the inside approach pressed against its walls long enough for boundary_forces to act
     "bui_inside_sp1_long": ("bui", lambda n: decks.bui_spec(maxtimestep=n, mode="inside", npoints=1), 1510, 1500),
 }

@@ -104,8 +104,9 @@ struct Oracle {
       }
     } else if (p.skf == 3) {  // quintic, main:1506-1535
       const double factor = 7.e0 / (478.e0 * pi * h * h);
-      auto p5 = [](double a) { return a * a * a * a * a; };
-      auto p4 = [](double a) { return a * a * a * a; };
+      // gfortran calls libgcc's __powidf2 for x**5 / x**4: square-and-multiply, x**5 = x*((x*x)*(x*x))
+      auto p5 = [](double a) { const double a2 = a * a; return a * (a2 * a2); };
+      auto p4 = [](double a) { const double a2 = a * a; return a2 * a2; };
       if (q >= 0 && q <= 1) {
         w = factor * (p5(3 - q) - 6 * p5(2 - q) + 15 * p5(1 - q));
         for (int d = 0; d < 2; ++d) dwdx[d] = factor * ((-120 + 120 * q - 50 * (q * q)) / (h * h) * dx2[d]);

@@ -76,26 +76,64 @@ __device__ __forceinline__ void st4(double *p, int i, const Stress4 &s) {
                : "memory");
 }
 
-// ---- smoothing kernel, main:1440-1538 (skf = 1, ndimn = 2); fp64 evaluation, caller rounds to fp32 ----
-// dx,dy = x(pair_i) - x(pair_j); r = sqrt(dx*dx + dy*dy) as computed by the neighbour search.
+// ---- smoothing kernel, main:1440-1538 (ndimn = 2): cubic spline (skf = 1), Gauss (2), quintic (3); fp64
+// evaluation, caller rounds to fp32. dx,dy = x(pair_i) - x(pair_j); r = sqrt(dx*dx + dy*dy) as computed by the
+// neighbour search. Integer powers follow libgcc's __powidf2, which is what gfortran calls for `**5` / `**4`:
+// x**5 = x * ((x*x)*(x*x)), x**4 = (x*x)*(x*x). The Gauss kernel's exp() is CUDA's (<= 1 ulp) where the reference
+// calls glibc's: the fp32-rounded weights can differ in the last bit with probability ~1e-9 per pair.
+__device__ __forceinline__ double powi5(double a) {
+  const double a2 = a * a;
+  return a * (a2 * a2);
+}
+__device__ __forceinline__ double powi4(double a) {
+  const double a2 = a * a;
+  return a2 * a2;
+}
 __device__ __forceinline__ void sph_kernel(const DevParams &P, double r, double dx, double dy, double h, double &w,
                                            double &gx, double &gy) {
   const double q = r / h;
   w = 0.;
   gx = 0.;
   gy = 0.;
-  const double factor = 15.e0 / (7.e0 * P.pi * h * h);
-  if (q >= 0 && q <= 1.e0) {
-    w = factor * ((double)(2.f / 3.f) - q * q + q * q * q / 2.);
-    const double t = factor * (-2. + 1.5 * q) / (h * h);
-    gx = t * dx;
-    gy = t * dy;
-  } else if (q > 1.e0 && q <= 2) {
-    const double t = 2. - q;
-    w = factor * 1.e0 / 6.e0 * (t * t * t);
-    const double u = -factor * 1.e0 / 6.e0 * 3. * (t * t) / h;
-    gx = u * (dx / r);
-    gy = u * (dy / r);
+  if (P.skf == 1) {
+    const double factor = 15.e0 / (7.e0 * P.pi * h * h);
+    if (q >= 0 && q <= 1.e0) {
+      w = factor * ((double)(2.f / 3.f) - q * q + q * q * q / 2.);
+      const double t = factor * (-2. + 1.5 * q) / (h * h);
+      gx = t * dx;
+      gy = t * dy;
+    } else if (q > 1.e0 && q <= 2) {
+      const double t = 2. - q;
+      w = factor * 1.e0 / 6.e0 * (t * t * t);
+      const double u = -factor * 1.e0 / 6.e0 * 3. * (t * t) / h;
+      gx = u * (dx / r);
+      gy = u * (dy / r);
+    }
+  } else if (P.skf == 2) {  // main:1494-1504
+    const double factor = 1.e0 / ((h * h) * P.pi);
+    if (q >= 0 && q <= 3) {
+      w = factor * exp(-q * q);
+      gx = w * (-2. * dx / h / h);
+      gy = w * (-2. * dy / h / h);
+    }
+  } else if (P.skf == 3) {  // main:1506-1535
+    const double factor = 7.e0 / (478.e0 * P.pi * h * h);
+    if (q >= 0 && q <= 1) {
+      w = factor * (powi5(3 - q) - 6 * powi5(2 - q) + 15 * powi5(1 - q));
+      const double t = (-120 + 120 * q - 50 * (q * q)) / (h * h);
+      gx = factor * (t * dx);
+      gy = factor * (t * dy);
+    } else if (q > 1 && q <= 2) {
+      w = factor * (powi5(3 - q) - 6 * powi5(2 - q));
+      const double u = factor * (-5 * powi4(3 - q) + 30 * powi4(2 - q)) / h;
+      gx = u * (dx / r);
+      gy = u * (dy / r);
+    } else if (q > 2 && q <= 3) {
+      w = factor * powi5(3 - q);
+      const double u = factor * (-5 * powi4(3 - q)) / h;
+      gx = u * (dx / r);
+      gy = u * (dy / r);
+    }
   }
 }
 

@@ -866,7 +866,7 @@ k_fill_scan(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
         dy = -dy;
       }
       double w, gx, gy;
-      if (mh == K.h)
+      if (P.skf == 1 && mh == K.h)
         sph_kernel_fast<true>(K, r, dx, dy, w, gx, gy);
       else
         sph_kernel(P, r, dx, dy, mh, w, gx, gy);
@@ -898,7 +898,7 @@ k_fill_scan(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
       const size_t a = o1 + (size_t)pos * SLICE;
       double w, gx, gy;
       if (sp == SP_NODE) {
-        if (mh == K.h)
+        if (P.skf == 1 && mh == K.h)
           sph_kernel_fast<true>(K, r, dx, dy, w, gx, gy);
         else
           sph_kernel(P, r, dx, dy, mh, w, gx, gy);
@@ -910,7 +910,7 @@ k_fill_scan(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
         L.yC[a] = (float)dy;
         L.hC[a] = (float)(0.5 * (hp + hq));  // main:863
       } else {
-        if (mh == K.h)
+        if (P.skf == 1 && mh == K.h)
           sph_kernel_fast<false>(K, r, dx, dy, w, gx, gy);
         else
           sph_kernel(P, r, dx, dy, mh, w, gx, gy);
@@ -1048,7 +1048,7 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
         dx = -dx;
         dy = -dy;
       }
-      if (mh == K.h)
+      if (P.skf == 1 && mh == K.h)
         sph_kernel_fast<true>(K, r, dx, dy, w[u], gx[u], gy[u]);
       else
         sph_kernel(P, r, dx, dy, mh, w[u], gx[u], gy[u]);
@@ -1093,12 +1093,12 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
       dxs[u] = dx;
       dys[u] = dy;
       if (sp == SP_NODE) {
-        if (mh == K.h)
+        if (P.skf == 1 && mh == K.h)
           sph_kernel_fast<true>(K, r, dx, dy, w[u], gx[u], gy[u]);
         else
           sph_kernel(P, r, dx, dy, mh, w[u], gx[u], gy[u]);
       } else {
-        if (mh == K.h)
+        if (P.skf == 1 && mh == K.h)
           sph_kernel_fast<false>(K, r, dx, dy, w[u], gx[u], gy[u]);
         else
           sph_kernel(P, r, dx, dy, mh, w[u], gx[u], gy[u]);

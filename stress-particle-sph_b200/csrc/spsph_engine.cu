@@ -744,7 +744,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
     return 1;
   };
   if (p->ndimn != 2 || p->nstre != 4) return fail("only ndimn = 2, nstre = 4 (plane strain) is supported");
-  if (p->skf != 1) return fail("only the cubic spline kernel (skf = 1) is supported");
+  if (p->skf < 1 || p->skf > 3) return fail("skf must be 1 (cubic spline), 2 (Gauss) or 3 (quintic)");
   if (p->cont_density) return fail("cont_density = T is not supported");
   if (p->art_stress) return fail("art_stress = T is not supported");
   if (p->ifsigman != 0) return fail("ifsigman = 1 (apply_stress_free) is not supported");

@@ -1187,7 +1187,7 @@ __global__ void k_free_surface(DevParams P, SlotMap M, SortArrays S, const int *
       const double mh = (K.h + hq) / 2.;
       const double r = sqrt(d2);
       double w, gxd = 0.0, gyd = 0.0;
-      if (mh == K.h)
+      if (P.skf == 1 && mh == K.h)
         sph_kernel_fast<true>(K, r, dx, dy, w, gxd, gyd);
       else
         sph_kernel(P, r, dx, dy, mh, w, gxd, gyd);
