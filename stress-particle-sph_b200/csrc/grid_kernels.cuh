@@ -49,24 +49,6 @@ __device__ __forceinline__ bool slot_decode(const SlotMap &m, int t, int &sp, in
   return k < m.nd;
 }
 
-// Segmented block -> slot mapping: blocks [0, seg_n) walk node slots, the next seg_s stress-particle slots, the
-// rest wall-particle slots. On a slab only the leading slots of a species hold local particles, so the grids of the
-// slot-indexed kernels are sized by the local counts (or a bound on them) instead of the global ones.
-// Returns -1 for a thread past the end of its species' slot range (whole warps: the ranges are multiples of 32).
-__device__ __forceinline__ int seg_slot(const SlotMap &M, int seg_n, int seg_s) {
-  const int b = blockIdx.x;
-  if (b < seg_n) {
-    const int u = b * blockDim.x + threadIdx.x;
-    return u < M.nnp ? u : -1;
-  }
-  if (b < seg_n + seg_s) {
-    const int u = (b - seg_n) * blockDim.x + threadIdx.x;
-    return u < M.nsp ? M.nnp + u : -1;
-  }
-  const int u = (b - seg_n - seg_s) * blockDim.x + threadIdx.x;
-  return u < M.ndp ? M.nnp + M.nsp + u : -1;
-}
-
 // Particles a kernel has to visit. Single GPU: all of them (ids == nullptr, identity). Multi-GPU: the compact
 // list of this rank's local (owned + ghost) particle numbers kept by dist_kernels.cuh, so that no per-step pass
 // is proportional to the global particle count.
@@ -537,14 +519,16 @@ __global__ void __launch_bounds__(128, SPSPH_COUNT_MINB)
 k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, int *__restrict__ n0, int *__restrict__ n1,
         int *__restrict__ nfwd_u /* unified order */, int *__restrict__ nall, int *__restrict__ w0 /* slice widths */,
         int *__restrict__ wC, int *__restrict__ wD, const int *__restrict__ lflag, int *__restrict__ cand0,
-        int *__restrict__ cand1, int *__restrict__ overflow, const int *__restrict__ nout, int seg_n, int seg_s) {
-  // grid sized by a bound on the local slots (slices that are not visited keep the zero width of the host memset)
-  const int t = seg_slot(M, seg_n, seg_s);
-  if (t < 0) return;
+        int *__restrict__ cand1, int *__restrict__ overflow, const int *__restrict__ nout, int t0, int tn) {
+  // slots [t0, t0 + tn): all of them on a single GPU; on a slab one launch per species over the leading slots that
+  // can hold local particles (slices that are not visited keep the zero width of the host memset)
+  const int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= t0 + tn) return;
   int sp = 0, k = 0;
   bool live = (t < M.total()) && slot_decode(M, t, sp, k);
   // only the leading slots of a species are occupied this step (in-grid particles, then out-of-domain ones)
-  if (live) live = k < (sp == 0 ? S.start[0] : (sp == 1 ? S.start[1] : S.start[2]))[G->ncell] + nout[sp];
+  // (single GPU: every particle is sorted, nothing to check)
+  if (live && lflag) live = k < (sp == 0 ? S.start[0] : (sp == 1 ? S.start[1] : S.start[2]))[G->ncell] + nout[sp];
   int c0 = 0, c1 = 0, cf = 0, ca = 0;
   if (live) {
     const int *__restrict__ cellp = sp == 0 ? S.cell[0] : (sp == 1 ? S.cell[1] : S.cell[2]);
@@ -782,12 +766,12 @@ constexpr int FILL_THREADS = 128;
 __global__ void __launch_bounds__(FILL_THREADS)
 k_fill_scan(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ n0,
        const int *__restrict__ n1, const GrowthRule *__restrict__ growth, ListPtrs L, int *__restrict__ bc_int,
-       float *__restrict__ n_int, const double *__restrict__ mor, int seg_n, int seg_s) {
+       float *__restrict__ n_int, const double *__restrict__ mor, int t0, int tn) {
   __shared__ int q0buf[QCAP][FILL_THREADS];  // cross-species partners (species in the top 2 bits)
   __shared__ int q1buf[QCAP][FILL_THREADS];  // same-species partners
   const int tid = threadIdx.x;
-  const int t = seg_slot(M, seg_n, seg_s);
-  if (t < 0 || t >= M.nnp + M.nsp) return;
+  const int t = t0 + blockIdx.x * blockDim.x + tid;
+  if (t >= t0 + tn) return;
   int sp, k;
   if (!slot_decode(M, t, sp, k)) return;
   const int *__restrict__ orderp = sp == 0 ? S.order[0] : S.order[1];
@@ -968,13 +952,16 @@ k_fill_scan(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
 #ifndef SPSPH_FILL_U
 #define SPSPH_FILL_U 2
 #endif
+// UNIFORM: cubic spline and one smoothing length for all particles (known to the host after upload): only the
+// hoisted-constant kernel evaluation is compiled in, which keeps the general kernels' registers out of the hot path
+template <bool UNIFORM>
 __global__ void __launch_bounds__(128, SPSPH_FILL_MINB)
 k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ n0,
        const int *__restrict__ n1, const GrowthRule *__restrict__ growth, ListPtrs L, int *__restrict__ bc_int,
        float *__restrict__ n_int, const double *__restrict__ mor, const int *__restrict__ cand0,
-       const int *__restrict__ cand1, int seg_n, int seg_s) {
-  const int t = seg_slot(M, seg_n, seg_s);
-  if (t < 0 || t >= M.nnp + M.nsp) return;
+       const int *__restrict__ cand1, int t0, int tn) {
+  const int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= t0 + tn) return;
   int sp, k;
   if (!slot_decode(M, t, sp, k)) return;
   const int *__restrict__ orderp = sp == 0 ? S.order[0] : S.order[1];
@@ -996,7 +983,7 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
   const size_t cb = (size_t)sl * CAND_CAP * SLICE + lane;
   const double2 pp = posp[k];
   const double hp = hpp[k];
-  const bool uni = G->uniform_h != 0;
+  const bool uni = UNIFORM || G->uniform_h != 0;
   const KernelConsts K = kernel_consts(P, hp);
   // number of "old" entries per list (prefix of the ascending order); only the split mode needs a pre-count
   int s0 = (gr.mode == 1) ? 0 : cnt0, s1 = (gr.mode == 1) ? 0 : cnt1;
@@ -1048,7 +1035,7 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
         dx = -dx;
         dy = -dy;
       }
-      if (P.skf == 1 && mh == K.h)
+      if (UNIFORM || (P.skf == 1 && mh == K.h))
         sph_kernel_fast<true>(K, r, dx, dy, w[u], gx[u], gy[u]);
       else
         sph_kernel(P, r, dx, dy, mh, w[u], gx[u], gy[u]);
@@ -1093,12 +1080,12 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
       dxs[u] = dx;
       dys[u] = dy;
       if (sp == SP_NODE) {
-        if (P.skf == 1 && mh == K.h)
+        if (UNIFORM || (P.skf == 1 && mh == K.h))
           sph_kernel_fast<true>(K, r, dx, dy, w[u], gx[u], gy[u]);
         else
           sph_kernel(P, r, dx, dy, mh, w[u], gx[u], gy[u]);
       } else {
-        if (P.skf == 1 && mh == K.h)
+        if (UNIFORM || (P.skf == 1 && mh == K.h))
           sph_kernel_fast<false>(K, r, dx, dy, w[u], gx[u], gy[u]);
         else
           sph_kernel(P, r, dx, dy, mh, w[u], gx[u], gy[u]);

@@ -50,6 +50,7 @@ struct spsph_handle {
   std::string err;
   std::vector<void *> allocs;
   bool uploaded = false;
+  bool uniform_cubic = false;  // skf = 1 and one smoothing length for every particle (set at upload)
   bool have_lists = false;  // the pair lists of a completed step are on the device (free-surface detection)
 
   // particle state (original order)
@@ -504,11 +505,22 @@ int build_neighbours(spsph_handle *h) {
                           halo_limit(h, h->halo_prev_recv[1]) + 32;
       if (b < bound[k]) bound[k] = (int)b;
     }
-  const int seg_n = (bound[0] + 127) / 128, seg_s = (bound[1] + 127) / 128, seg_d = (bound[2] + 127) / 128;
-  k_count<<<seg_n + seg_s + seg_d, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->nfwd_u, h->nall, h->wslice,
+  if (!h->dist) {  // single GPU: every slot is live, one launch over all of them
+    const int tn = h->M.total();
+    k_count<<<(tn + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->nfwd_u, h->nall, h->wslice,
+                                             h->wslice + h->nslices, h->wslice + 2 * h->nslices, lflag, h->cand0,
+                                             h->cand1, h->cand_overflow, h->nout, 0, tn);
+  } else {  // slab: one launch per species over the leading slots that can hold local particles
+    const int t0s[3] = {0, h->M.nnp, h->M.nnp + h->M.nsp};
+    for (int k = 0; k < 3; ++k) {
+      const int tn = (bound[k] + 31) & ~31;
+      if (tn > 0)
+        k_count<<<(tn + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->nfwd_u, h->nall, h->wslice,
                                                  h->wslice + h->nslices, h->wslice + 2 * h->nslices, lflag,
-                                                 h->cand0, h->cand1, h->cand_overflow, h->nout, seg_n, seg_s);
-  mark(h, KID_COUNT);
+                                                 h->cand0, h->cand1, h->cand_overflow, h->nout, t0s[k], tn);
+    }
+  }
+  mark(h, KID_COUNT, h->dist ? 3 : 1);
   launch_scan(h, h->wslice, h->oslice, 3, h->nslices, nullptr, h->nslices, h->scan_totals, KID_SCAN);
   if (h->dist)  // unified slots of local particles are the leading ones: scan only those
     launch_scan(h, h->nfwd_u, h->base_u, 1, n2, h->list_n + h->list_cur, 0, h->scan_totals + 3, KID_SCAN);
@@ -592,14 +604,22 @@ int build_neighbours(spsph_handle *h) {
   ML.nn = h->nloc[0];
   ML.ns = h->nloc[1];
   ML.nd = h->nloc[2];
-  const int fseg_n = (ML.nn + 127) / 128, fseg_s = (ML.ns + 127) / 128;
-  if (st.pad[0] || h->force_fill_scan)  // a particle has more partners than the candidate scratch holds: search again while filling
-    k_fill_scan<<<fseg_n + fseg_s, 128, 0, s>>>(P, ML, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int, h->n_int,
-                                                h->mor, fseg_n, fseg_s);
-  else if (fseg_n + fseg_s > 0)
-    k_fill<<<fseg_n + fseg_s, 128, 0, s>>>(P, ML, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int, h->n_int, h->mor,
-                                           h->cand0, h->cand1, fseg_n, fseg_s);
-  mark(h, KID_FILL);
+  // single GPU: one launch over all list-owning slots; slab: one launch per species over its local slots
+  const int nfl = h->dist ? 2 : 1;
+  const int ft0[2] = {0, ML.nnp}, ftn[2] = {h->dist ? ((ML.nn + 31) & ~31) : ML.nnp + ML.nsp, (ML.ns + 31) & ~31};
+  for (int k = 0; k < nfl; ++k) {
+    if (ftn[k] == 0) continue;
+    if (st.pad[0] || h->force_fill_scan)  // a particle has more partners than the candidate scratch holds: search again while filling
+      k_fill_scan<<<(ftn[k] + 127) / 128, 128, 0, s>>>(P, ML, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int,
+                                                       h->n_int, h->mor, ft0[k], ftn[k]);
+    else if (h->uniform_cubic)
+      k_fill<true><<<(ftn[k] + 127) / 128, 128, 0, s>>>(P, ML, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int,
+                                                        h->n_int, h->mor, h->cand0, h->cand1, ft0[k], ftn[k]);
+    else
+      k_fill<false><<<(ftn[k] + 127) / 128, 128, 0, s>>>(P, ML, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int,
+                                                         h->n_int, h->mor, h->cand0, h->cand1, ft0[k], ftn[k]);
+  }
+  mark(h, KID_FILL, h->dist ? 2 : 1);
   return 0;
 }
 
@@ -905,8 +925,12 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   CUDA_TRY(up(h->rho, s->rho, n2 * 8));
   CUDA_TRY(up(h->mass, s->mass, n2 * 8));
   CUDA_TRY(up(h->hsml, s->hsml, n2 * 8));
-  double hmax = 0.0;
-  for (size_t i = 0; i < n2; ++i) hmax = std::fmax(hmax, s->hsml[i]);
+  double hmax = 0.0, hmin = 1.e300;
+  for (size_t i = 0; i < n2; ++i) {
+    hmax = std::fmax(hmax, s->hsml[i]);
+    hmin = std::fmin(hmin, s->hsml[i]);
+  }
+  h->uniform_cubic = (h->hp.skf == 1 && hmin == hmax);  // hsml never changes on the device (cont_density unsupported)
   h->cur = 0;
   CUDA_TRY(up(h->stage_vel, s->vel, 2 * nt * 8));
   CUDA_TRY(up(h->stage_stress, s->stress, 4 * nt * 8));
