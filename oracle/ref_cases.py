@@ -40,6 +40,13 @@ CASES = {
     "bui_quintic": ("bui", lambda n: dict(decks.bui_spec(maxtimestep=n), skf=3), 30, (30,)),
     "vs_gauss": ("vs", lambda n: dict(decks.vertical_slope_spec(maxtimestep=n), skf=2), 30, (30,)),
     "sl_quintic": ("sl", lambda n: dict(decks.strain_localisation_spec(maxtimestep=n), skf=3), 20, (20,)),
+    # options no shipped input switches on: artificial stress (main:908-1016), continuity density with and without
+    # the smoothing-length update (main:706-713, 772-797, 807-821)
+    "bui_art_stress": ("bui", lambda n: dict(decks.bui_spec(maxtimestep=n), art_stress=True), 40, (40,)),
+    "sl_art_stress": ("sl", lambda n: dict(decks.strain_localisation_spec(maxtimestep=n), art_stress=True), 30, (30,)),
+    "bui_cont_density": ("bui", lambda n: dict(decks.bui_spec(maxtimestep=n), cont_density=True), 40, (40,)),
+    "vs_cont_density_sle2": ("vs", lambda n: dict(decks.vertical_slope_spec(maxtimestep=n), cont_density=True), 40, (40,)),
+    "sl_cont_density_sle2": ("sl", lambda n: dict(decks.strain_localisation_spec(maxtimestep=n), cont_density=True), 30, (30,)),
     # the inside approach pressed against its walls long enough for boundary_forces to act
     "bui_inside_sp1_long": ("bui", lambda n: decks.bui_spec(maxtimestep=n, mode="inside", npoints=1), 1510, 1500),
 }
@@ -53,3 +60,7 @@ def spec_of(case):
     """deck specification of a case, with the step count the golden run used"""
     which, spec_fn, nsteps, _ = CASES[case]
     return which, spec_fn(nsteps)
+
+
+# cases whose options the CUDA engine does not implement yet: spsph_create must refuse them (DESIGN.md section 7)
+DEVICE_UNSUPPORTED = {"bui_art_stress", "sl_art_stress", "bui_cont_density", "vs_cont_density_sle2", "sl_cont_density_sle2"}

@@ -798,7 +798,11 @@ struct Oracle {
     std::vector<double> RK_stress(4 * nt, 0.0), RK_vel(2 * nt, 0.0), RK_dev_strain(nt, 0.0);
     std::vector<double> RHS_1(4 * nt, 0.0), RHS_2(2 * nt, 0.0), source_stress(4 * nt, 0.0), spin(4 * nt, 0.0),
         omega(2 * nt, 0.0);
-    std::vector<double> source_grav(2 * (size_t)nnode, 0.0);
+    std::vector<double> source_grav(2 * (size_t)nnode, 0.0), art_force(2 * (size_t)nnode, 0.0);
+    // continuity density (main:686-689): rho0, hsml0 of the stress particles; RK_rho, RK_hsml, RHS_rho, RHS_hsml(ntotal)
+    const size_t ns = nt - (size_t)nnode;
+    std::vector<double> rho0(rho.begin() + nnode, rho.begin() + ntotal), hsml0(hsml.begin() + nnode, hsml.begin() + ntotal);
+    std::vector<double> RK_rho(nt, 0.0), RK_hsml(nt, 0.0), RHS_rho(nt, 0.0), RHS_hsml(nt, 0.0);
     std::fill(art_visc.begin(), art_visc.end(), 0.0);
     std::fill(vel.begin(), vel.end(), 0.0);        // main:690: all entries incl. dummies
     std::fill(stress.begin(), stress.end(), 0.0);  //
@@ -811,9 +815,16 @@ struct Oracle {
       for (int i = nnode + 1; i <= ntotal; ++i)
         for (int s = 1; s <= 4; ++s)
           S(s, i) = stress0[4 * (size_t)(i - 1) + s - 1] + f1rk[st] * (dt)*RHS_1[4 * (size_t)(i - 1) + s - 1];
-      if (p.cont_density) {
-        err = "cont_density = T is not supported (not exercised by any shipped input)";
-        return false;
+      if (p.cont_density) {  // main:706-713; density_update main:807-821 reads the grad_u of the PREVIOUS sweep
+        for (size_t k = 0; k < ns; ++k) {
+          const int i = nnode + 1 + (int)k;
+          RHS_rho[i - 1] = -rho[i - 1] * (GU(1, 1, i) + GU(2, 2, i));
+        }
+        for (size_t k = 0; k < ns; ++k) rho[nnode + k] = rho0[k] + f1rk[st] * (dt)*RHS_rho[nnode + k];
+        if (p.sle == 2) {
+          for (size_t k = 0; k < ns; ++k) RHS_hsml[nnode + k] = -(hsml0[k] / (rho[nnode + k] * 2)) * RHS_rho[nnode + k];
+          for (size_t k = 0; k < ns; ++k) hsml[nnode + k] = hsml0[k] + f1rk[st] * (dt)*RHS_hsml[nnode + k];
+        }
       }
       if (ncrit == 12) adapt_stress2();
       if (p.no_bcs > 0) bcs();
@@ -845,10 +856,7 @@ struct Oracle {
       }
       if (p.inside_approach) boundary_forces();  // Bui copy main:742; elsewhere .and. dummy_nodes (ndummy2 = 0 then)
       if (p.alpha > 0 || p.beta > 0) artificial_viscosity();
-      if (p.art_stress) {
-        err = "art_stress = T is not supported (not exercised by any shipped input)";
-        return false;
-      }
+      if (p.art_stress) artificial_force(art_force);  // main:746
       if (p.update_x) {  // main:751-757, get_spin_rate_tensor main:1021-1034
         for (int i = 1; i <= ntotal; ++i) {
           omega[2 * (size_t)(i - 1)] = 0.5 * (GU(1, 2, i) - GU(2, 1, i));
@@ -869,8 +877,8 @@ struct Oracle {
       for (int i = 1; i <= nnode; ++i)
         for (int d = 0; d < 2; ++d) {
           const size_t k = 2 * (size_t)(i - 1) + d;
-          // f_bound is zero unless boundary_forces runs (App. C-2); art_force is zero (art_stress = F)
-          RHS_2[k] = -divf2[k] + source_grav[k] + art_visc[k] + f_bound[k] + 0.0;
+          // f_bound is zero unless boundary_forces runs (App. C-2); art_force is zero unless art_stress = T
+          RHS_2[k] = -divf2[k] + source_grav[k] + art_visc[k] + f_bound[k] + art_force[k];
         }
       for (int i = 1; i <= nnode; ++i)
         for (int d = 0; d < 2; ++d) {
@@ -882,6 +890,11 @@ struct Oracle {
           const size_t k = 4 * (size_t)(i - 1) + s;
           RK_stress[k] = RK_stress[k] + f2rk[st] * RHS_1[k];
         }
+      if (p.cont_density) {  // main:772-777
+        for (size_t k = 0; k < nt; ++k) RK_rho[k] = RK_rho[k] + f2rk[st] * RHS_rho[k];
+        if (p.sle == 2)
+          for (size_t k = 0; k < nt; ++k) RK_hsml[k] = RK_hsml[k] + f2rk[st] * RHS_hsml[k];
+      }
     }
     for (int i = 1; i <= nnode; ++i)
       for (int d = 1; d <= 2; ++d) V(d, i) = vel0[2 * (size_t)(i - 1) + d - 1] + (dt / 6) * RK_vel[2 * (size_t)(i - 1) + d - 1];
@@ -890,8 +903,63 @@ struct Oracle {
         S(s, i) = stress0[4 * (size_t)(i - 1) + s - 1] + (dt / 6) * RK_stress[4 * (size_t)(i - 1) + s - 1];
     if (ncrit == 12) adapt_stress2();
     if (p.no_bcs > 0) bcs();
+    if (p.cont_density) {  // main:792-797
+      for (size_t k = 0; k < ns; ++k) rho[nnode + k] = rho0[k] + (dt / 6.) * RK_rho[nnode + k];
+      if (p.sle == 2)
+        for (size_t k = 0; k < ns; ++k) hsml[nnode + k] = hsml0[k] + (dt / 6.) * RK_hsml[nnode + k];
+    }
     for (size_t i = 0; i < nt; ++i) Ddev_strn[i] = RK_dev_strain[i] / 6;
     return true;
+  }
+
+  // ---- artificial_force, main:908-1016 (Monaghan 2000 artificial stress on node-node pairs; all DP) ----------
+  void artificial_force(std::vector<double> &art_force) {
+    const size_t nn = (size_t)nnode;
+    std::vector<double> sigma2(2 * nn, 0.0), R2(2 * nn, 0.0), R(3 * nn, 0.0), tmp(6 * nn, 0.0);  // tmp(istre,d,i)
+    const double eps = (double)0.1f, nexp = (double)2.55f;  // default-real literals assigned to DP variables
+    double w2 = 0.0, gradw2[2] = {0.0, 0.0};
+    const double hsml0 = (double)1.2f * p.dx;
+    const double dx2[2] = {p.dx, p.dy};
+    kernel(p.dx, dx2, hsml0, w2, gradw2);
+    const int64_t n = (int64_t)created.size();
+    for (int64_t t = 0; t < n; ++t) {
+      const Pair &c = created[creation_index(t)];
+      if (c.pint_type != 3) continue;
+      const int i = c.pair_i, j = c.pair_j;
+      const size_t a = (size_t)(i - 1), b = (size_t)(j - 1);
+      const double s12i = S(1, i) - S(2, i), s12j = S(1, j) - S(2, j);
+      const double theta = (s12i >= (double)1e-08f) ? 0.5 * std::atan(2 * S(3, i) / s12i) : 0.0;
+      const double theta2 = (s12j >= (double)1e-08f) ? 0.5 * std::atan(2 * S(3, j) / s12j) : 0.0;
+      const double ci = std::cos(theta), si = std::sin(theta), cj = std::cos(theta2), sj = std::sin(theta2);
+      sigma2[2 * a] = (ci * ci) * S(1, i) + 2 * ci * si * S(3, i) + (si * si) * S(2, i);
+      sigma2[2 * b] = (cj * cj) * S(1, j) + 2 * cj * sj * S(3, j) + (sj * sj) * S(2, j);
+      sigma2[2 * a + 1] = (si * si) * S(1, i) - 2 * ci * si * S(3, i) + (ci * ci) * S(2, i);
+      sigma2[2 * b + 1] = (sj * sj) * S(1, j) - 2 * cj * sj * S(3, j) + (cj * cj) * S(2, j);
+      const double f = ((double)c.w) / w2;
+      for (int k = 0; k < 2; ++k) {
+        R2[2 * a + k] = sigma2[2 * a + k] > 0 ? -eps * (sigma2[2 * a + k] / (rho[a] * rho[a])) : 0.0;
+        R2[2 * b + k] = sigma2[2 * b + k] > 0 ? -eps * (sigma2[2 * b + k] / (rho[b] * rho[b])) : 0.0;
+      }
+      R[3 * a] = R2[2 * a] * (ci * ci) + R2[2 * a + 1] * (si * si);
+      R[3 * a + 1] = R2[2 * a] * ((ci * ci) + (si * si));
+      R[3 * a + 2] = (R2[2 * a] - R2[2 * a + 1]) * (ci * si);
+      R[3 * b] = R2[2 * b] * (cj * cj) + R2[2 * b + 1] * (sj * sj);
+      R[3 * b + 1] = R2[2 * b] * ((cj * cj) + (sj * sj));
+      R[3 * b + 2] = (R2[2 * b] - R2[2 * b + 1]) * (cj * sj);
+      const double fn = std::pow(f, nexp);
+      for (int is = 0; is < 3; ++is) {
+        const double h1 = (double)c.dwdx * fn * (R[3 * a + is] + R[3 * b + is]);
+        tmp[6 * a + is] = tmp[6 * a + is] + mass[b] * h1;
+        tmp[6 * b + is] = tmp[6 * b + is] - mass[a] * h1;
+        const double h2 = (double)c.dwdy * fn * (R[3 * a + is] + R[3 * b + is]);
+        tmp[6 * a + 3 + is] = tmp[6 * a + 3 + is] + mass[b] * h2;
+        tmp[6 * b + 3 + is] = tmp[6 * b + 3 + is] - mass[a] * h2;
+      }
+    }
+    for (size_t a = 0; a < nn; ++a) {
+      art_force[2 * a] = tmp[6 * a + 0] + tmp[6 * a + 3 + 2];      // (1,1) + (3,2)
+      art_force[2 * a + 1] = tmp[6 * a + 2] + tmp[6 * a + 3 + 1];  // (3,1) + (2,2)
+    }
   }
 
   // ---- get_nodes_on_free_surface, mat:1116-1411 (every local is default REAL = fp32; subset, normal, x, mass,

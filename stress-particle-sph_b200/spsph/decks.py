@@ -70,7 +70,7 @@ def write_deck(directory, spec):
         dat += [f"ICtype_{lab}", "0"]
     dat += ["pa_sph nnps sle skf cspm update_x XSPH",
             _row(2, 2, spec.get("sle", 1), spec.get("skf", 1), spec["cspm"], spec["update_x"], spec["xsph"]),
-            "summ_dens cont_dens", _row(False, False), "damping", _row(spec["damping"]),
+            "summ_dens cont_dens", _row(False, spec.get("cont_density", False)), "damping", _row(spec["damping"]),
             "alpha beta", _row(spec["alpha"], spec["beta"])]
     if spec.get("gravity") is not None:
         gx, gy, curve, fac = spec["gravity"]
