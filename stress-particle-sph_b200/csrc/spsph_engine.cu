@@ -57,7 +57,9 @@ struct spsph_handle {
   double *x = nullptr, *x00 = nullptr, *rho = nullptr, *mass = nullptr, *hsml = nullptr, *mor = nullptr;
   double2 *mrho = nullptr;  // {mass, rho} per particle
   Rec4 *NB[2] = {nullptr, nullptr}, *SB[2] = {nullptr, nullptr}, *SVb[2] = {nullptr, nullptr}, *SA = nullptr;
-  double *NA = nullptr, *NSa = nullptr, *SVa = nullptr, *av = nullptr, *fbound = nullptr;
+  double *NA = nullptr, *NSa = nullptr, *SVa = nullptr, *av = nullptr, *fbound = nullptr, *aforce = nullptr;
+  Rec4 *RN = nullptr;
+  double art_w2 = 0.0;  // kernel(dx, (dx, dy), 1.2 dx): the reference spacing weight of artificial_force (main:926)
   double *NSb[2] = {nullptr, nullptr}, *SFb[2] = {nullptr, nullptr};
   double *stage_vel = nullptr, *stage_stress = nullptr;  // reference-layout staging for upload / download
   double *epsp = nullptr, *fdp = nullptr, *norm = nullptr, *AE = nullptr;
@@ -254,6 +256,8 @@ StatePtrs state_ptrs(spsph_handle *h, int wb) {
   s.SVbr = h->SVb[1 - wb];
   s.av = h->av;
   s.fbound = h->fbound;
+  s.aforce = h->aforce;
+  s.RN = h->RN;
   s.epsp = h->epsp;
   s.fdp = h->fdp;
   s.norm = h->norm;
@@ -698,6 +702,10 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     const bool artv = (P.alpha > 0 || P.beta > 0);
     fork();
     if (artv) k_artvisc<<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n1, st);
+    if (p.art_stress) {  // main:746
+      k_art_force_prep<<<GN, 128, 0, s2>>>(P, M, ord_n, st);
+      k_art_force<<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n1, st, h->art_w2);
+    }
     if (stg == 0) {
       k_sweep_b_sp<true><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last);
       k_sweep_b_node<true><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
@@ -744,6 +752,26 @@ const char *spsph_version(void) { return "spsph-b200 0.1 (sm_100a)"; }
 
 const char *spsph_last_error(spsph_handle *h) { return h ? h->err.c_str() : "null handle"; }
 
+// w of kernel(r, ., h) on the host (main:1468-1536), for the constant w2 = W(dx, 1.2 dx) of artificial_force (main:921-926)
+static double host_kernel_w(int skf, double pi, double r, double h) {
+  const double q = r / h;
+  auto p5 = [](double a) { const double a2 = a * a; return a * (a2 * a2); };
+  if (skf == 1) {
+    const double factor = 15.e0 / (7.e0 * pi * h * h);
+    if (q >= 0 && q <= 1.e0) return factor * ((double)(2.f / 3.f) - q * q + q * q * q / 2.);
+    if (q > 1.e0 && q <= 2) return factor * 1.e0 / 6.e0 * ((2. - q) * (2. - q) * (2. - q));
+  } else if (skf == 2) {
+    const double factor = 1.e0 / (std::pow(h, 2) * std::pow(pi, 2 / 2.));
+    if (q >= 0 && q <= 3) return factor * std::exp(-q * q);
+  } else if (skf == 3) {
+    const double factor = 7.e0 / (478.e0 * pi * h * h);
+    if (q >= 0 && q <= 1) return factor * (p5(3 - q) - 6 * p5(2 - q) + 15 * p5(1 - q));
+    if (q > 1 && q <= 2) return factor * (p5(3 - q) - 6 * p5(2 - q));
+    if (q > 2 && q <= 3) return factor * p5(3 - q);
+  }
+  return 0.0;
+}
+
 int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   if (!out || !p) return 1;
   *out = nullptr;
@@ -766,7 +794,6 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   if (p->ndimn != 2 || p->nstre != 4) return fail("only ndimn = 2, nstre = 4 (plane strain) is supported");
   if (p->skf < 1 || p->skf > 3) return fail("skf must be 1 (cubic spline), 2 (Gauss) or 3 (quintic)");
   if (p->cont_density) return fail("cont_density = T is not supported");
-  if (p->art_stress) return fail("art_stress = T is not supported");
   if (p->ifsigman != 0) return fail("ifsigman = 1 (apply_stress_free) is not supported");
   if (p->xsph && p->update_x && p->no_bcs > 0)
     return fail("XSPH together with boundary conditions is not supported (XSPH_update strips the BC flag of particles "
@@ -831,6 +858,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   P.beta = p->beta;
   P.damping = p->damping;
   P.dx = p->dx;
+  h->art_w2 = host_kernel_w(p->skf, p->pi, p->dx, (double)1.2f * p->dx);
   P.r_x = p->r_x;
   P.r_y = p->r_y;
   P.disp_tol = p->disp_tol;
@@ -860,7 +888,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   rc |= dalloc(h, &h->x, 2 * n2) | dalloc(h, &h->x00, 2 * n2) | dalloc(h, &h->rho, n2) | dalloc(h, &h->mass, n2);
   rc |= dalloc(h, &h->hsml, n2) | dalloc(h, &h->mor, n2) | dalloc(h, &h->mrho, n2);
   rc |= dalloc(h, &h->NA, 2 * nn) | dalloc(h, &h->SA, ns) | dalloc(h, &h->NSa, 4 * nn) | dalloc(h, &h->SVa, 2 * ns);
-  rc |= dalloc(h, &h->av, 2 * nn) | dalloc(h, &h->fbound, 2 * nn);
+  rc |= dalloc(h, &h->av, 2 * nn) | dalloc(h, &h->fbound, 2 * nn) | dalloc(h, &h->aforce, 2 * nn) | dalloc(h, &h->RN, nn);
   for (int b = 0; b < 2; ++b) {
     rc |= dalloc(h, &h->NB[b], nn) | dalloc(h, &h->SB[b], ns) | dalloc(h, &h->NSb[b], 4 * nn);
     rc |= dalloc(h, &h->SFb[b], 4 * ns) | dalloc(h, &h->SVb[b], ns);
@@ -894,6 +922,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   CUDA_TRY(cudaMemset(h->AE, 0, 5 * nt * sizeof(double)));
   CUDA_TRY(cudaMemset(h->norm, 0, nt * sizeof(double)));
   CUDA_TRY(cudaMemset(h->fbound, 0, 2 * nn * sizeof(double)));
+  CUDA_TRY(cudaMemset(h->aforce, 0, 2 * nn * sizeof(double)));
   return 0;
 }
 

@@ -49,6 +49,8 @@ struct StatePtrs {
   Rec4 *SVb;    // [nstress] {vx, vy, m/rho, -}
   double *av;   // (2, nnode) artificial viscosity acceleration of the current stage (k_artvisc -> k_sweep_b_node)
   double *fbound;  // (2, nnode) boundary_forces of the current step (zero unless the inside approach has walls)
+  double *aforce;  // (2, nnode) artificial_force of the current stage (zero unless art_stress = T)
+  Rec4 *RN;        // [nnode] artificial-stress terms R(1:3) of a node (k_art_force_prep -> k_art_force)
   // read side of a format-B -> format-B sweep (the SPH_shift interpolation): the other B buffer set
   const Rec4 *NBr, *SVbr;
   const double *NSbr, *SFbr;
@@ -842,9 +844,10 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
     av1 = a.x;
     av2 = a.y;
   }
-  const double2 fb = ld2(st.fbound, id);           // f_bound (main:764): zero unless boundary_forces ran
-  const double r1 = -dv1 + sg1 + av1 + fb.x + 0.0;  // ... + art_force (zero: art_stress = F)
-  const double r2 = -dv2 + sg2 + av2 + fb.y + 0.0;
+  const double2 fb = ld2(st.fbound, id);  // f_bound (main:764): zero unless boundary_forces ran
+  const double2 af = ld2(st.aforce, id);  // art_force: zero unless art_stress = T
+  const double r1 = -dv1 + sg1 + av1 + fb.x + af.x;
+  const double r2 = -dv2 + sg2 + av2 + fb.y + af.y;
   double2 rk = ld2(st.RKv, id);
   rk.x = rk.x + f2 * r1;
   rk.y = rk.y + f2 * r2;
@@ -1110,6 +1113,58 @@ __global__ void k_shift(DevParams P, const Rec4 *__restrict__ NB, double *__rest
   if (collapse)
     for (int q = 0; q < P.npoints && q < 3; ++q) st2(x, k + q, xi);
   }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// artificial_force, main:908-1016 (art_stress = T; Monaghan's artificial stress on node-node pairs, all fp64).
+// The principal-axis terms R(1:3) of a node depend on that node alone, so they are evaluated once per node and
+// stage (k_art_force_prep) and gathered per pair (k_art_force, ordered sums over the node-node list).
+// atan / sin / cos / pow are CUDA's where the reference calls glibc's: results agree to ~1e-15 relative per term,
+// not bit for bit (tests: 1e-9 relative after 40 steps against the reference executable).
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_art_force_prep(DevParams P, SlotMap M, const int *__restrict__ order_n, StatePtrs st) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= M.nn) return;
+  const int id = order_n[k];
+  const Stress4 s = ld4(st.NSb, id);
+  const double rp = st.rho[id];
+  const double eps = (double)0.1f;
+  const double s12 = s.s1 - s.s2;
+  const double theta = (s12 >= (double)1e-08f) ? 0.5 * atan(2 * s.s3 / s12) : 0.0;
+  const double c = cos(theta), sn = sin(theta);
+  const double sg1 = (c * c) * s.s1 + 2 * c * sn * s.s3 + (sn * sn) * s.s2;
+  const double sg2 = (sn * sn) * s.s1 - 2 * c * sn * s.s3 + (c * c) * s.s2;
+  const double R21 = sg1 > 0 ? -eps * (sg1 / (rp * rp)) : 0.0;
+  const double R22 = sg2 > 0 ? -eps * (sg2 / (rp * rp)) : 0.0;
+  strec(st.RN, id, R21 * (c * c) + R22 * (sn * sn), R21 * ((c * c) + (sn * sn)), (R21 - R22) * (c * sn), 0.0);
+}
+__global__ void __launch_bounds__(128)
+k_art_force(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n1,
+            StatePtrs st, double w2) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M.nn) return;
+  const int id = order_n[t];
+  const int cnt = n1[t];
+  const size_t o1 = (size_t)L.offC[t / SLICE] + (t & 31);
+  const Rec4 Rp = ldrec(st.RN, id);
+  const double nexp = (double)2.55f;
+  double t11 = 0.0, t21 = 0.0, t31 = 0.0, t12 = 0.0, t22 = 0.0, t32 = 0.0;  // art_force_temp(istre, d)
+  for (int e = 0; e < cnt; ++e) {
+    const size_t a = o1 + (size_t)e * SLICE;
+    const int q = L.idxC[a];
+    const Rec4 Rq = ldrec(st.RN, q);
+    const double mq = st.mass[q];
+    const double fn = pow((double)L.wC[a] / w2, nexp);
+    const double gx = (double)L.gxC[a], gy = (double)L.gyC[a];  // this node's perspective: +dwdx as pair_i, -dwdx as pair_j
+    const double s1 = Rp.a + Rq.a, s2 = Rp.b + Rq.b, s3 = Rp.c + Rq.c;
+    t11 = t11 + mq * (gx * fn * s1);
+    t21 = t21 + mq * (gx * fn * s2);
+    t31 = t31 + mq * (gx * fn * s3);
+    t12 = t12 + mq * (gy * fn * s1);
+    t22 = t22 + mq * (gy * fn * s2);
+    t32 = t32 + mq * (gy * fn * s3);
+  }
+  st2(st.aforce, id, make_double2(t11 + t32, t31 + t22));
 }
 
 // ------------------------------------------------------------------------------------------------------

@@ -10,7 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
 sys.path.insert(0, os.path.dirname(os.path.abspath(__file__)))
-from ref_cases import CASES, DEVICE_UNSUPPORTED, golden_path, spec_of  # noqa: E402
+from ref_cases import CASES, DEVICE_TOLERANCE, DEVICE_UNSUPPORTED, golden_path, spec_of  # noqa: E402
 from test_reference_pinned_cpu import compare_with_golden  # noqa: E402
 
 pytestmark = pytest.mark.gpu
@@ -34,5 +34,5 @@ def test_engine_reproduces_reference_binary(case, tmp_path):
     for step in (int(s) for s in g["steps"]):
         t = eng.run(1 + done, t, dt, step - done)
         done = step
-        compare_with_golden(case, g, step, eng.download(), prob.params, "CUDA engine")
+        compare_with_golden(case, g, step, eng.download(), prob.params, "CUDA engine", DEVICE_TOLERANCE.get(case, 0.0))
     eng.close()

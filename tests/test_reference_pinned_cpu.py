@@ -17,13 +17,16 @@ from ref_cases import CASES, golden_path, spec_of  # noqa: E402
 FIELDS = (("x", "x", None), ("vel", "vel", None), ("stress", "stress", None), ("strain", "internal_vars", 0))
 
 
-def compare_with_golden(case, g, step, arrays, p, label):
-    """arrays: a download (oracle or engine) after `step` steps; asserts equality with the reference frame"""
+def compare_with_golden(case, g, step, arrays, p, label, rel_tol=0.0):
+    """arrays: a download (oracle or engine) after `step` steps; asserts equality with the reference frame
+    (rel_tol > 0: relative L-inf per field instead, for paths that call a different libm)"""
     nn = p.nnode
     for tag, sl in (("n", slice(0, nn)), ("s", slice(nn, p.ntotal))):
         for key, mine_key, col in FIELDS:
             ref = g[f"{tag}{step}_{key}"]
             mine = arrays[mine_key][sl] if col is None else arrays[mine_key][sl, col]
+            if rel_tol > 0 and np.abs(ref - mine).max() <= rel_tol * max(np.abs(ref).max(), 1e-300):
+                continue
             if not np.array_equal(ref, mine):
                 d = np.abs(ref - mine)
                 k = int(np.argmax(d.reshape(len(ref), -1).max(axis=1)))
