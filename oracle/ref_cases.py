@@ -63,7 +63,7 @@ def spec_of(case):
 
 
 # cases whose options the CUDA engine does not implement yet: spsph_create must refuse them
-DEVICE_UNSUPPORTED = {"bui_cont_density", "vs_cont_density_sle2", "sl_cont_density_sle2"}
+DEVICE_UNSUPPORTED = set()
 # cases where the engine evaluates libm functions (atan, sin, cos, pow) with CUDA's implementations instead of
 # glibc's: agreement to the north star's 1e-9 relative L-inf instead of bit for bit
 DEVICE_TOLERANCE = {"bui_art_stress": 1e-9, "sl_art_stress": 1e-9}

@@ -16,6 +16,7 @@ enum : int { SP_NODE = 0, SP_STRESS = 1, SP_DUMMY = 2 };
 struct DevParams {
   int nnode, nstress, ntotal, ntotal2, ndummy, npoints;
   int skf, scale_k, cspm, update_x, xsph, ncrit, ntype_eco, ntype_solid;
+  int cont_density, sle;  // continuity density on the stress particles (main:706-713); sle = 2: smoothing length follows
   int no_bcs, bc_nloop;  // bc_nloop: Normal_BCs loop bound (ntotal or nnode), mat:1683
   int sp_sph, inside_approach, vel_vector, shift_update;
   int adapt;  // ncrit == 12

@@ -59,6 +59,7 @@ struct spsph_handle {
   Rec4 *NB[2] = {nullptr, nullptr}, *SB[2] = {nullptr, nullptr}, *SVb[2] = {nullptr, nullptr}, *SA = nullptr;
   double *NA = nullptr, *NSa = nullptr, *SVa = nullptr, *av = nullptr, *fbound = nullptr, *aforce = nullptr;
   Rec4 *RN = nullptr;
+  double *rho_new = nullptr, *rho0 = nullptr, *hsml0 = nullptr, *RKrho = nullptr, *RKh = nullptr, *divu = nullptr;  // cont_density
   double art_w2 = 0.0;  // kernel(dx, (dx, dy), 1.2 dx): the reference spacing weight of artificial_force (main:926)
   double *NSb[2] = {nullptr, nullptr}, *SFb[2] = {nullptr, nullptr};
   double *stage_vel = nullptr, *stage_stress = nullptr;  // reference-layout staging for upload / download
@@ -258,6 +259,16 @@ StatePtrs state_ptrs(spsph_handle *h, int wb) {
   s.fbound = h->fbound;
   s.aforce = h->aforce;
   s.RN = h->RN;
+  s.rho_w = h->rho;
+  s.hsml_w = h->hsml;
+  s.mor_w = h->mor;
+  s.mrho_w = h->mrho;
+  s.rho_new = h->rho_new;
+  s.rho0 = h->rho0;
+  s.hsml0 = h->hsml0;
+  s.RKrho = h->RKrho;
+  s.RKh = h->RKh;
+  s.divu = h->divu;
   s.epsp = h->epsp;
   s.fdp = h->fdp;
   s.norm = h->norm;
@@ -652,6 +663,7 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     const StatePtrs sw = state_ptrs(h, 1 - h->cur);
     k_sweep_a_sp<true, true><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, sw, adapt, 0);
     k_sweep_a_node<true, true, true><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, sw, adapt, 0);
+    if (p.cont_density) k_commit_node_rho<<<GN, 128, 0, s>>>(P, M, ord_n, sw);
     mark(h, KID_SWEEPA, 2);
     h->cur = 1 - h->cur;
     first_a = false;
@@ -668,7 +680,11 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   const double f1rk[4] = {0., 0.5, 0.5, 1.0}, f2rk[4] = {1., 2., 2., 1.0};
   // The node-side and the stress-particle-side kernel of a sweep touch disjoint outputs and only read the
   // other side's previous-format records, so they run side by side on two streams (s2 forks from / joins s).
-  cudaStream_t s2 = h->dual ? h->stream2 : s;
+  // Continuity density (cont_density = T): the densities move inside the step, so every sweep A recomputes
+  // cspm_norm and the (m/rho) w factors (FIRST variants), every sweep B the CSPM matrix, and the kernels run in the
+  // reference's read-before-write order on one stream.
+  const bool cd = p.cont_density != 0;
+  cudaStream_t s2 = (h->dual && !cd) ? h->stream2 : s;
   auto fork = [&]() {
     if (s2 != s) {
       cudaEventRecord(h->ev_fork, s);
@@ -686,9 +702,10 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
       k_sweep_a_std<<<list_grid(h, P.ntotal, 256), 256, 0, s>>>(P, st, local_list(h, P.ntotal));
     } else {
       fork();
-      if (first_a) {
+      if (first_a || cd) {
         k_sweep_a_sp<true, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
         k_sweep_a_node<true, false, false><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+        if (cd) k_commit_node_rho<<<GN, 128, 0, s>>>(P, M, ord_n, st);
       } else {
         k_sweep_a_sp<false, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
         k_sweep_a_node<false, false, false><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
@@ -706,11 +723,15 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
       k_art_force_prep<<<GN, 128, 0, s2>>>(P, M, ord_n, st);
       k_art_force<<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n1, st, h->art_w2);
     }
-    if (stg == 0) {
-      k_sweep_b_sp<true><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last);
+    const double f2n = last ? 0.0 : f2rk[stg + 1];
+    if (cd) {  // the node side reads the stress particles' density before their side integrates it
+      k_sweep_b_node<true><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
+      k_sweep_b_sp<true><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last, f2n);
+    } else if (stg == 0) {
+      k_sweep_b_sp<true><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last, f2n);
       k_sweep_b_node<true><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
     } else {
-      k_sweep_b_sp<false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last);
+      k_sweep_b_sp<false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last, f2n);
       k_sweep_b_node<false><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
     }
     join();
@@ -721,8 +742,14 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     k_sweep_a_std<<<list_grid(h, P.ntotal, 256), 256, 0, s>>>(P, st, local_list(h, P.ntotal));
   } else {
     fork();
-    k_sweep_a_sp<false, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
-    k_sweep_a_node<false, false, true><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+    if (cd) {
+      k_sweep_a_sp<true, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
+      k_sweep_a_node<true, false, true><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+      k_commit_node_rho<<<GN, 128, 0, s>>>(P, M, ord_n, st);
+    } else {
+      k_sweep_a_sp<false, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
+      k_sweep_a_node<false, false, true><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+    }
     join();
   }
   mark(h, KID_SWEEPA, 2);
@@ -793,7 +820,6 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   };
   if (p->ndimn != 2 || p->nstre != 4) return fail("only ndimn = 2, nstre = 4 (plane strain) is supported");
   if (p->skf < 1 || p->skf > 3) return fail("skf must be 1 (cubic spline), 2 (Gauss) or 3 (quintic)");
-  if (p->cont_density) return fail("cont_density = T is not supported");
   if (p->ifsigman != 0) return fail("ifsigman = 1 (apply_stress_free) is not supported");
   if (p->xsph && p->update_x && p->no_bcs > 0)
     return fail("XSPH together with boundary conditions is not supported (XSPH_update strips the BC flag of particles "
@@ -831,6 +857,8 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   P.ndummy = p->ndummy;
   P.npoints = p->npoints;
   P.skf = p->skf;
+  P.cont_density = p->cont_density ? 1 : 0;
+  P.sle = p->sle;
   P.scale_k = (p->skf == 1) ? 2 : 3;
   P.cspm = p->cspm;
   P.update_x = p->update_x;
@@ -889,6 +917,9 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   rc |= dalloc(h, &h->hsml, n2) | dalloc(h, &h->mor, n2) | dalloc(h, &h->mrho, n2);
   rc |= dalloc(h, &h->NA, 2 * nn) | dalloc(h, &h->SA, ns) | dalloc(h, &h->NSa, 4 * nn) | dalloc(h, &h->SVa, 2 * ns);
   rc |= dalloc(h, &h->av, 2 * nn) | dalloc(h, &h->fbound, 2 * nn) | dalloc(h, &h->aforce, 2 * nn) | dalloc(h, &h->RN, nn);
+  if (p->cont_density)
+    rc |= dalloc(h, &h->rho_new, nn) | dalloc(h, &h->rho0, nt - nn) | dalloc(h, &h->hsml0, nt - nn) |
+          dalloc(h, &h->RKrho, nt - nn) | dalloc(h, &h->RKh, nt - nn) | dalloc(h, &h->divu, nt - nn);
   for (int b = 0; b < 2; ++b) {
     rc |= dalloc(h, &h->NB[b], nn) | dalloc(h, &h->SB[b], ns) | dalloc(h, &h->NSb[b], 4 * nn);
     rc |= dalloc(h, &h->SFb[b], 4 * ns) | dalloc(h, &h->SVb[b], ns);
@@ -959,7 +990,9 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
     hmax = std::fmax(hmax, s->hsml[i]);
     hmin = std::fmin(hmin, s->hsml[i]);
   }
-  h->uniform_cubic = (h->hp.skf == 1 && hmin == hmax);  // hsml never changes on the device (cont_density unsupported)
+  // hsml only changes on the device with cont_density and sle = 2 (main:709-712)
+  h->uniform_cubic = (h->hp.skf == 1 && hmin == hmax && !(h->hp.cont_density && h->hp.sle == 2));
+  if (h->hp.cont_density) CUDA_TRY(cudaMemsetAsync(h->divu, 0, (nt - nn) * sizeof(double), st));  // grad_u = 0, mat:930
   h->cur = 0;
   CUDA_TRY(up(h->stage_vel, s->vel, 2 * nt * 8));
   CUDA_TRY(up(h->stage_stress, s->stress, 4 * nt * 8));
@@ -1195,6 +1228,10 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
   if (!h || !planes || nranks < 1 || rank < 0 || rank >= nranks) return 1;
   if (!h->uploaded) {
     h->err = "spsph_dist_init must follow spsph_upload (every rank uploads the complete problem)";
+    return 1;
+  }
+  if (h->hp.cont_density) {
+    h->err = "multi-GPU: cont_density = T is not supported (the halo records carry no density / smoothing length)";
     return 1;
   }
   CUDA_TRY(cudaSetDevice(h->device));

@@ -51,6 +51,13 @@ struct StatePtrs {
   double *fbound;  // (2, nnode) boundary_forces of the current step (zero unless the inside approach has walls)
   double *aforce;  // (2, nnode) artificial_force of the current stage (zero unless art_stress = T)
   Rec4 *RN;        // [nnode] artificial-stress terms R(1:3) of a node (k_art_force_prep -> k_art_force)
+  // continuity density (cont_density = T): the density of the stress particles is integrated by RK4, that of the
+  // velocity particles interpolated by every stress_point_update; with sle = 2 the smoothing length follows
+  double *rho_w, *hsml_w, *mor_w;  // writable views of rho, hsml, mor
+  double2 *mrho_w;                 // writable view of mrho
+  double *rho_new;                 // (nnode) interpolated density of a sweep A, committed by k_commit_node_rho
+  double *rho0, *hsml0, *RKrho, *RKh;  // (nstress) RK4 work arrays, main:686-689
+  double *divu;                    // (nstress) grad_u(1,1) + grad_u(2,2) of the last get_derivatives (persists across steps)
   // read side of a format-B -> format-B sweep (the SPH_shift interpolation): the other B buffer set
   const Rec4 *NBr, *SVbr;
   const double *NSbr, *SFbr;
@@ -265,6 +272,22 @@ __global__ void k_rk_begin(DevParams P, StatePtrs st, LocalList LL) {
     apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
     strec(st.SA, ks, sn.s1, sn.s2, sn.s3, sn.s4);
     st2(st.SVa, ks, vn);
+    if (P.cont_density) {  // main:686-689 and the stage-1 block main:706-713 (f1rk = 0, f2rk = 1)
+      const double r0 = st.rho[id], h0 = st.hsml[id], m = st.mass[id];
+      st.rho0[ks] = r0;
+      st.hsml0[ks] = h0;
+      const double rhs = -r0 * st.divu[ks];  // density_update with the grad_u of the previous step's last sweep
+      const double rn = r0 + 0. * (P.dt) * rhs;
+      st.rho_w[id] = rn;
+      st.mrho_w[id] = make_double2(m, rn);
+      st.mor_w[id] = m / rn;
+      st.RKrho[ks] = 0.0 + 1. * rhs;
+      if (P.sle == 2) {
+        const double rh = -(h0 / (rn * 2)) * rhs;
+        st.hsml_w[id] = h0 + 0. * (P.dt) * rh;
+        st.RKh[ks] = 0.0 + 1. * rh;
+      }
+    }
   }
   }
 }
@@ -333,7 +356,11 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
 #pragma unroll
           for (int u = 0; u < A_GR; ++u) {
             const bool ok = (u < nvalid) && (q[u] < P.nnode);  // dummy partners (type 9) take no part
-            const double h2 = h0_of(pay[0][u], pay[1][u]);     // (mass(i)/rho(i))*w, main:431
+            double h2 = h0_of(pay[0][u], pay[1][u]);           // (mass(i)/rho(i))*w, main:431
+            if (FIRST && P.cont_density) {  // the density moves: the streamed product of the fill pass is stale
+              const double rq = ok ? r[u].mr.y : 1.0;
+              h2 = div_rn(r[u].mr.x, rq, __drcp_rn(rq)) * (double)__int_as_float(pay[NARR - 2][u]);
+            }
             const double tx = vtx + r[u].v.x * h2, ty = vty + r[u].v.y * h2;
             vtx = ok ? tx : vtx;
             vty = ok ? ty : vty;
@@ -386,7 +413,7 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
     v = ld2(st.NA, id);
     s = ld4(st.NSa, id);
   }
-  double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, te = 0.0, nrm = 0.0;
+  double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, te = 0.0, nrm = 0.0, trho = 0.0;
   {
     struct RecS {
       Rec4 s;
@@ -410,7 +437,13 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
 #pragma unroll
           for (int u = 0; u < A_GR; ++u) {
             const bool ok = (u < nvalid) && (q[u] < P.ntotal);  // dummy partners (type 6) take no part
-            const double h1 = h0_of(pay[0][u], pay[1][u]);      // (mass(j)/rho(j))*w, main:430
+            double h1 = h0_of(pay[0][u], pay[1][u]);            // (mass(j)/rho(j))*w, main:430
+            if (FIRST && P.cont_density) {  // the density moves: recompute the factor, and interpolate rho (main:437)
+              const double rq = ok ? r[u].mr.y : 1.0;
+              h1 = div_rn(r[u].mr.x, rq, __drcp_rn(rq)) * (double)__int_as_float(pay[NARR - 2][u]);
+              const double nr = trho + r[u].mr.y * h1;
+              trho = ok ? nr : trho;
+            }
             const double n1 = t1 + r[u].s.a * h1, n2 = t2 + r[u].s.b * h1, n3 = t3 + r[u].s.c * h1,
                          n4 = t4 + r[u].s.d * h1;
             t1 = ok ? n1 : t1;
@@ -447,8 +480,24 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
   }
   if (do_adapt) adapt_stress(P, s);
   if (do_bc) apply_bcs(P, st.bc_or_not, st.bc_info, id, v, s);
-  strec(st.NB, id, v.x, v.y, st.mass[id], st.rho[id]);
+  double rnode = st.rho[id];
+  if (FIRST && P.cont_density) {  // rho(1:nnode) = rho_temp/cspm_norm, main:464-465 (unconditional)
+    rnode = trho / nrm;
+    st.rho_new[id] = rnode;  // committed after the sweep: the stress-particle side still reads the old value
+  }
+  strec(st.NB, id, v.x, v.y, st.mass[id], rnode);
   st4(st.NSb, id, s);
+}
+
+// cont_density: the interpolated density of the velocity particles becomes current once both sides of sweep A are done
+__global__ void k_commit_node_rho(DevParams P, SlotMap M, const int *__restrict__ order_n, StatePtrs st) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= M.nn) return;
+  const int id = order_n[k];
+  const double r = st.rho_new[id], m = st.mass[id];
+  st.rho_w[id] = r;
+  st.mrho_w[id] = make_double2(m, r);
+  st.mor_w[id] = m / r;
 }
 
 // ------------------------------------------------------------------------------------------------------
@@ -458,7 +507,7 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
 template <bool FIRST>
 __global__ void __launch_bounds__(128, SPSPH_MINB)
 k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L, const int *__restrict__ n0,
-             StatePtrs st, double f1next, double f2, int last) {
+             StatePtrs st, double f1next, double f2, int last, double f2next) {
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
   if ((k0 & ~31) >= M.ns) return;  // whole warp past the end
   const bool live = k0 < M.ns;
@@ -654,6 +703,31 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
   strec(st.SA, ks, sn.s1, sn.s2, sn.s3, sn.s4);
   st2(st.SVa, ks, vn);
+  if (P.cont_density) {
+    // the next stage's density block (main:706-713: density_update reads the grad_u just computed) or the final
+    // update (main:792-797); RK_rho takes the next stage's RHS at once, it does not change during that stage
+    const double div = g11 + g22;
+    st.divu[ks] = div;
+    const double m = st.mass[id];
+    double rn;
+    if (!last) {
+      const double rhs = -st.rho[id] * div;
+      rn = st.rho0[ks] + f1next * (P.dt) * rhs;
+      st.RKrho[ks] = st.RKrho[ks] + f2next * rhs;
+      if (P.sle == 2) {
+        const double h0 = st.hsml0[ks];
+        const double rh = -(h0 / (rn * 2)) * rhs;
+        st.hsml_w[id] = h0 + f1next * (P.dt) * rh;
+        st.RKh[ks] = st.RKh[ks] + f2next * rh;
+      }
+    } else {
+      rn = st.rho0[ks] + (P.dt / 6.) * st.RKrho[ks];
+      if (P.sle == 2) st.hsml_w[id] = st.hsml0[ks] + (P.dt / 6.) * st.RKh[ks];
+    }
+    st.rho_w[id] = rn;
+    st.mrho_w[id] = make_double2(m, rn);
+    st.mor_w[id] = m / rn;
+  }
 }
 
 
@@ -879,7 +953,14 @@ __global__ void k_sweep_a_std(DevParams P, StatePtrs st, LocalList LL) {
   if (id < P.nnode) {  // stress(:,i) = stress(:,nnode+i); Internal_Vars(1,i) = Internal_Vars(1,nnode+i)
     const double2 v = ld2(st.NA, id);
     const Rec4 s = ldrec(st.SA, id);
-    strec(st.NB, id, v.x, v.y, st.mass[id], st.rho[id]);
+    double rn = st.rho[id];
+    if (P.cont_density) {  // rho(1:nnode) = rho(nnode+1:ntotal), main:478
+      rn = st.rho[P.nnode + id];
+      st.rho_w[id] = rn;
+      st.mrho_w[id] = make_double2(st.mass[id], rn);
+      st.mor_w[id] = st.mass[id] / rn;
+    }
+    strec(st.NB, id, v.x, v.y, st.mass[id], rn);
     st4(st.NSb, id, Stress4{s.a, s.b, s.c, s.d});
     st.epsp[id] = st.epsp[P.nnode + id];
   } else {             // vel(:,nnode+i) = vel(:,i)
