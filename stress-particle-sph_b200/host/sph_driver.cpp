@@ -57,6 +57,13 @@ static void output_res(const spsph::Problem &P, int itimestep_sph, const std::st
   if (!f) return;
   for (int i = p.nnode; i < p.ntotal; ++i) row(f, i, false);
   std::fclose(f);
+  // nodes on the free surface (get_nodes_on_free_surface marks them bc_or_not = 2), mat:3061-3078
+  f = std::fopen((out + "/surface_points.csv." + tag).c_str(), "w");
+  if (!f) return;
+  std::fprintf(f, " x-coord,y-coord,\n");
+  for (int i = 0; i < p.nnode; ++i)
+    if (P.bc_or_not[i] == 2) std::fprintf(f, " %.17g , %.17g\n", P.x[2 * (size_t)i], P.x[2 * (size_t)i + 1]);
+  std::fclose(f);
 }
 
 int main(int argc, char **argv) {
@@ -112,7 +119,8 @@ int main(int argc, char **argv) {
       time_sph = time_sph + dt;
       time = time + dt;
       ++total;
-      const bool stop = (time > b.time_end) || (max_steps >= 0 && total >= max_steps);
+      if (time > b.time_end) break;  // 1_SPH_2018.f90:82: leaves the block before any output
+      const bool stop = (max_steps >= 0 && total >= max_steps);  // --max-steps (not in the reference) ends with a frame
       if (t_plot_reset >= time_plot || stop) {
         if (spsph_download(h, &st)) return die("spsph_download");
         output_res(P, itimestep_sph, out);

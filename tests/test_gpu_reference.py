@@ -36,3 +36,30 @@ def test_engine_reproduces_reference_binary(case, tmp_path):
         done = step
         compare_with_golden(case, g, step, eng.download(), prob.params, "CUDA engine", DEVICE_TOLERANCE.get(case, 0.0))
     eng.close()
+
+
+def test_driver_frames_match_reference_cadence(tmp_path):
+    """host/sph_driver.cpp (the PROGRAM SPH_2018 stand-in) plots at the steps the reference executable plots (its
+    output clock is an fp32 accumulation: frames land at steps 301 and 602 for plot_step = 300) and lists the same
+    free-surface nodes in surface_points.csv"""
+    import subprocess
+    from spsph import decks
+    g = np.load(golden_path("bui_long"))
+    variant, spec = spec_of("bui_long")
+    for blk in spec["blocks"]:
+        blk["plot_step"] = 300
+        blk["print_step"] = blk["save_step"] = 10 ** 6
+    deck = tmp_path / "deck"
+    deck.mkdir()
+    decks.write_deck(str(deck), spec)
+    drv = os.path.join(ROOT, "stress-particle-sph_b200", "sph_driver")
+    subprocess.check_call([drv, str(deck), variant], stdout=subprocess.DEVNULL)
+    frames = sorted(int(f.split(".")[-1]) for f in os.listdir(deck) if f.startswith("nodes.csv."))
+    assert frames == [0] + [int(s) for s in g["steps"]], frames
+    for step in (int(s) for s in g["steps"]):
+        rows = [ln.split(",") for ln in open(deck / f"surface_points.csv.{step:06d}").read().splitlines()[1:] if ln.strip()]
+        surf = np.array([[float(r[0]), float(r[1])] for r in rows]).reshape(-1, 2)
+        assert np.array_equal(surf, g[f"surf{step}"])
+        nodes = np.loadtxt(deck / f"nodes.csv.{step:06d}", delimiter=",", skiprows=1, usecols=range(9))
+        ref = np.column_stack([g[f"n{step}_x"], g[f"n{step}_vel"], g[f"n{step}_stress"], g[f"n{step}_strain"]])
+        assert np.abs(nodes - ref).max() <= 0.5e-8 * 1.0001 + 1e-8 * np.abs(ref).max() * 0, "F16.8 frames differ from the reference"
