@@ -766,7 +766,8 @@ constexpr int FILL_THREADS = 128;
 __global__ void __launch_bounds__(FILL_THREADS)
 k_fill_scan(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ n0,
        const int *__restrict__ n1, const GrowthRule *__restrict__ growth, ListPtrs L, int *__restrict__ bc_int,
-       float *__restrict__ n_int, const double *__restrict__ mor, int t0, int tn) {
+       float *__restrict__ n_int, const double *__restrict__ mor, const unsigned char *__restrict__ mcls, int t0,
+       int tn) {
   __shared__ int q0buf[QCAP][FILL_THREADS];  // cross-species partners (species in the top 2 bits)
   __shared__ int q1buf[QCAP][FILL_THREADS];  // same-species partners
   const int tid = threadIdx.x;
@@ -858,10 +859,12 @@ k_fill_scan(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
       const size_t a = o0 + (size_t)pos * SLICE;
       const int qid = S.order[sq][q];
       const float wf = (float)w;
-      const double h0 = (sq == SP_DUMMY) ? 0.0 : mor[qid] * (double)wf;
-      L.idx0[a] = qid;
-      L.h0lo[a] = __double2loint(h0);
-      L.h0hi[a] = __double2hiint(h0);
+      const double h0 = (sq == SP_DUMMY || mcls) ? 0.0 : mor[qid] * (double)wf;
+      L.idx0[a] = mcls ? (qid | ((int)mcls[qid] << 30)) : qid;  // mass/rho class of the partner, see ell_stream
+      if (L.h0lo) {  // not stored when mass/rho is uniform per species (the sweeps rebuild it from w)
+        L.h0lo[a] = __double2loint(h0);
+        L.h0hi[a] = __double2hiint(h0);
+      }
       L.w0[a] = wf;
       L.gx0[a] = (float)gx;
       L.gy0[a] = (float)gy;
@@ -892,7 +895,7 @@ k_fill_scan(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
         L.gyC[a] = (float)gy;
         L.xC[a] = (float)dx;                 // xij = real(x(1,i) - x(1,j)), main:856
         L.yC[a] = (float)dy;
-        L.hC[a] = (float)(0.5 * (hp + hq));  // main:863
+        if (L.hC) L.hC[a] = (float)(0.5 * (hp + hq));  // main:863 (not stored when h is uniform)
       } else {
         if (P.skf == 1 && mh == K.h)
           sph_kernel_fast<false>(K, r, dx, dy, w, gx, gy);
@@ -958,8 +961,8 @@ template <bool UNIFORM>
 __global__ void __launch_bounds__(128, SPSPH_FILL_MINB)
 k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ n0,
        const int *__restrict__ n1, const GrowthRule *__restrict__ growth, ListPtrs L, int *__restrict__ bc_int,
-       float *__restrict__ n_int, const double *__restrict__ mor, const int *__restrict__ cand0,
-       const int *__restrict__ cand1, int t0, int tn) {
+       float *__restrict__ n_int, const double *__restrict__ mor, const unsigned char *__restrict__ mcls,
+       const int *__restrict__ cand0, const int *__restrict__ cand1, int t0, int tn) {
   const int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= t0 + tn) return;
   int sp, k;
@@ -1039,7 +1042,7 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
         sph_kernel_fast<true>(K, r, dx, dy, w[u], gx[u], gy[u]);
       else
         sph_kernel(P, r, dx, dy, mh, w[u], gx[u], gy[u]);
-      h0[u] = (sq[u] == SP_DUMMY) ? 0.0 : mor[qid[u]] * (double)(float)w[u];
+      h0[u] = (sq[u] == SP_DUMMY || mcls) ? 0.0 : mor[qid[u]] * (double)(float)w[u];
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -1047,9 +1050,11 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
       if (e >= cnt0) break;
       const int pos = (e < s0) ? (cnt0 - s0) + e : (cnt0 - 1 - e);
       const size_t a = o0 + (size_t)pos * SLICE;
-      L.idx0[a] = qid[u];
-      L.h0lo[a] = __double2loint(h0[u]);
-      L.h0hi[a] = __double2hiint(h0[u]);
+      L.idx0[a] = mcls ? (qid[u] | ((int)mcls[qid[u]] << 30)) : qid[u];  // mass/rho class of the partner, see ell_stream
+      if (L.h0lo) {  // not stored when mass/rho is uniform per species (the sweeps rebuild it from w)
+        L.h0lo[a] = __double2loint(h0[u]);
+        L.h0hi[a] = __double2hiint(h0[u]);
+      }
       L.w0[a] = (float)w[u];
       L.gx0[a] = (float)gx[u];
       L.gy0[a] = (float)gy[u];
@@ -1104,7 +1109,7 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
         L.gyC[a] = (float)gy[u];
         L.xC[a] = (float)dxs[u];                 // xij = real(x(1,i) - x(1,j)), main:856
         L.yC[a] = (float)dys[u];
-        L.hC[a] = (float)(0.5 * (hp + hq[u]));   // main:863
+        if (L.hC) L.hC[a] = (float)(0.5 * (hp + hq[u]));   // main:863 (not stored when h is uniform)
       } else {
         L.idxD[a] = qid[u];
         L.wD[a] = (float)w[u];

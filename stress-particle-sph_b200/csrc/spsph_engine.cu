@@ -50,6 +50,11 @@ struct spsph_handle {
   std::string err;
   std::vector<void *> allocs;
   bool uploaded = false;
+  bool umor = false;  // mass/rho takes <= 4 values within the velocity particles and within the stress particles
+  MorPalette pal_node{}, pal_sp{};
+  unsigned char *mcls = nullptr;  // [ntotal2] palette class of every particle
+  bool uniform_h = false;         // one smoothing length for every particle, constant in time
+  float h_uniform = 0.f;          // (float)(0.5*(h + h)) of artificial_viscosity, main:863
   bool uniform_cubic = false;  // skf = 1 and one smoothing length for every particle (set at upload)
   bool have_lists = false;  // the pair lists of a completed step are on the device (free-surface detection)
 
@@ -349,8 +354,11 @@ int ensure_lists(spsph_handle *h, long long t0, long long tC, long long tD) {
     cudaFree(h->L.gy0);
     cudaFree(h->L.h0lo);
     cudaFree(h->L.h0hi);
-    CUDA_TRY(cudaMalloc((void **)&h->L.h0lo, (size_t)h->cap0 * 4));
-    CUDA_TRY(cudaMalloc((void **)&h->L.h0hi, (size_t)h->cap0 * 4));
+    h->L.h0lo = h->L.h0hi = nullptr;
+    if (!h->umor) {  // (m/rho)_partner * w is only stored when it is not a per-species constant times w
+      CUDA_TRY(cudaMalloc((void **)&h->L.h0lo, (size_t)h->cap0 * 4));
+      CUDA_TRY(cudaMalloc((void **)&h->L.h0hi, (size_t)h->cap0 * 4));
+    }
     CUDA_TRY(cudaMalloc((void **)&h->L.idx0, (size_t)h->cap0 * 4));
     CUDA_TRY(cudaMalloc((void **)&h->L.w0, (size_t)h->cap0 * 4));
     CUDA_TRY(cudaMalloc((void **)&h->L.gx0, (size_t)h->cap0 * 4));
@@ -366,7 +374,8 @@ int ensure_lists(spsph_handle *h, long long t0, long long tC, long long tD) {
     cudaFree(h->L.hC);
     CUDA_TRY(cudaMalloc((void **)&h->L.xC, (size_t)h->capC * 4));
     CUDA_TRY(cudaMalloc((void **)&h->L.yC, (size_t)h->capC * 4));
-    CUDA_TRY(cudaMalloc((void **)&h->L.hC, (size_t)h->capC * 4));
+    h->L.hC = nullptr;
+    if (!h->uniform_h) CUDA_TRY(cudaMalloc((void **)&h->L.hC, (size_t)h->capC * 4));  // else a constant
     CUDA_TRY(cudaMalloc((void **)&h->L.idxC, (size_t)h->capC * 4));
     CUDA_TRY(cudaMalloc((void **)&h->L.wC, (size_t)h->capC * 4));
     CUDA_TRY(cudaMalloc((void **)&h->L.gxC, (size_t)h->capC * 4));
@@ -626,17 +635,35 @@ int build_neighbours(spsph_handle *h) {
     if (ftn[k] == 0) continue;
     if (st.pad[0] || h->force_fill_scan)  // a particle has more partners than the candidate scratch holds: search again while filling
       k_fill_scan<<<(ftn[k] + 127) / 128, 128, 0, s>>>(P, ML, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int,
-                                                       h->n_int, h->mor, ft0[k], ftn[k]);
+                                                       h->n_int, h->mor, h->umor ? h->mcls : nullptr, ft0[k], ftn[k]);
     else if (h->uniform_cubic)
       k_fill<true><<<(ftn[k] + 127) / 128, 128, 0, s>>>(P, ML, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int,
-                                                        h->n_int, h->mor, h->cand0, h->cand1, ft0[k], ftn[k]);
+                                                        h->n_int, h->mor, h->umor ? h->mcls : nullptr, h->cand0, h->cand1, ft0[k],
+                                                        ftn[k]);
     else
       k_fill<false><<<(ftn[k] + 127) / 128, 128, 0, s>>>(P, ML, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int,
-                                                         h->n_int, h->mor, h->cand0, h->cand1, ft0[k], ftn[k]);
+                                                         h->n_int, h->mor, h->umor ? h->mcls : nullptr, h->cand0, h->cand1, ft0[k],
+                                                        ftn[k]);
   }
   mark(h, KID_FILL, h->dist ? 2 : 1);
   return 0;
 }
+
+// sweep A launches: the UMOR variants (uniform mass/rho per species, see k_sweep_a_sp) are chosen at run time
+#define SPSPH_LAUNCH_A_SP(FIRST, FROMB, GRID, STREAM, ST, DOBC)                                                       \
+  do {                                                                                                               \
+    if (h->umor)                                                                                                     \
+      k_sweep_a_sp<FIRST, FROMB, true><<<GRID, 128, 0, STREAM>>>(P, M, ord_s, h->L, h->n0, ST, adapt, DOBC, h->pal_node); \
+    else                                                                                                             \
+      k_sweep_a_sp<FIRST, FROMB, false><<<GRID, 128, 0, STREAM>>>(P, M, ord_s, h->L, h->n0, ST, adapt, DOBC, h->pal_node); \
+  } while (0)
+#define SPSPH_LAUNCH_A_NODE(FIRST, FROMB, EPSP, GRID, STREAM, ST, DOBC)                                                      \
+  do {                                                                                                                      \
+    if (h->umor)                                                                                                            \
+      k_sweep_a_node<FIRST, FROMB, EPSP, true><<<GRID, 128, 0, STREAM>>>(P, M, ord_n, h->L, h->n0, ST, adapt, DOBC, h->pal_sp); \
+    else                                                                                                                    \
+      k_sweep_a_node<FIRST, FROMB, EPSP, false><<<GRID, 128, 0, STREAM>>>(P, M, ord_n, h->L, h->n0, ST, adapt, DOBC, h->pal_sp); \
+  } while (0)
 
 int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   if (!h->uploaded) {
@@ -661,8 +688,8 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   // SPH_shift block, main:99-109: format B -> the other format-B buffer set
   if (p.sph_shift && itimestep > 1 && ((itimestep - 1) % p.shift_update == 0)) {
     const StatePtrs sw = state_ptrs(h, 1 - h->cur);
-    k_sweep_a_sp<true, true><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, sw, adapt, 0);
-    k_sweep_a_node<true, true, true><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, sw, adapt, 0);
+    SPSPH_LAUNCH_A_SP(true, true, GS, s, sw, 0);
+    SPSPH_LAUNCH_A_NODE(true, true, true, GN, s, sw, 0);
     if (p.cont_density) k_commit_node_rho<<<GN, 128, 0, s>>>(P, M, ord_n, sw);
     mark(h, KID_SWEEPA, 2);
     h->cur = 1 - h->cur;
@@ -703,12 +730,12 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     } else {
       fork();
       if (first_a || cd) {
-        k_sweep_a_sp<true, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
-        k_sweep_a_node<true, false, false><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+        SPSPH_LAUNCH_A_SP(true, false, GS, s, st, bc);
+        SPSPH_LAUNCH_A_NODE(true, false, false, GN, s2, st, bc);
         if (cd) k_commit_node_rho<<<GN, 128, 0, s>>>(P, M, ord_n, st);
       } else {
-        k_sweep_a_sp<false, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
-        k_sweep_a_node<false, false, false><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+        SPSPH_LAUNCH_A_SP(false, false, GS, s, st, bc);
+        SPSPH_LAUNCH_A_NODE(false, false, false, GN, s2, st, bc);
       }
       join();
     }
@@ -718,7 +745,12 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     const double f1n = last ? 0.0 : f1rk[stg + 1];
     const bool artv = (P.alpha > 0 || P.beta > 0);
     fork();
-    if (artv) k_artvisc<<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n1, st);
+    if (artv) {
+      if (h->uniform_h)
+        k_artvisc<true><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n1, st, h->h_uniform);
+      else
+        k_artvisc<false><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n1, st, 0.f);
+    }
     if (p.art_stress) {  // main:746
       k_art_force_prep<<<GN, 128, 0, s2>>>(P, M, ord_n, st);
       k_art_force<<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n1, st, h->art_w2);
@@ -743,12 +775,12 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   } else {
     fork();
     if (cd) {
-      k_sweep_a_sp<true, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
-      k_sweep_a_node<true, false, true><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+      SPSPH_LAUNCH_A_SP(true, false, GS, s, st, bc);
+      SPSPH_LAUNCH_A_NODE(true, false, true, GN, s, st, bc);
       k_commit_node_rho<<<GN, 128, 0, s>>>(P, M, ord_n, st);
     } else {
-      k_sweep_a_sp<false, false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, adapt, bc);
-      k_sweep_a_node<false, false, true><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, adapt, bc);
+      SPSPH_LAUNCH_A_SP(false, false, GS, s, st, bc);
+      SPSPH_LAUNCH_A_NODE(false, false, true, GN, s2, st, bc);
     }
     join();
   }
@@ -914,7 +946,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   const size_t n2 = (size_t)p->ntotal2, nt = (size_t)p->ntotal, nn = (size_t)p->nnode, ns = (size_t)p->nstress;
   int rc = 0;
   rc |= dalloc(h, &h->x, 2 * n2) | dalloc(h, &h->x00, 2 * n2) | dalloc(h, &h->rho, n2) | dalloc(h, &h->mass, n2);
-  rc |= dalloc(h, &h->hsml, n2) | dalloc(h, &h->mor, n2) | dalloc(h, &h->mrho, n2);
+  rc |= dalloc(h, &h->hsml, n2) | dalloc(h, &h->mor, n2) | dalloc(h, &h->mrho, n2) | dalloc(h, &h->mcls, n2);
   rc |= dalloc(h, &h->NA, 2 * nn) | dalloc(h, &h->SA, ns) | dalloc(h, &h->NSa, 4 * nn) | dalloc(h, &h->SVa, 2 * ns);
   rc |= dalloc(h, &h->av, 2 * nn) | dalloc(h, &h->fbound, 2 * nn) | dalloc(h, &h->aforce, 2 * nn) | dalloc(h, &h->RN, nn);
   if (p->cont_density)
@@ -991,8 +1023,39 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
     hmin = std::fmin(hmin, s->hsml[i]);
   }
   // hsml only changes on the device with cont_density and sle = 2 (main:709-712)
-  h->uniform_cubic = (h->hp.skf == 1 && hmin == hmax && !(h->hp.cont_density && h->hp.sle == 2));
+  const bool uh = (hmin == hmax && !(h->hp.cont_density && h->hp.sle == 2));
+  if (uh != h->uniform_h) h->capC = 0;  // list C was sized for the other mode
+  h->uniform_h = uh;
+  h->h_uniform = (float)(0.5 * (hmax + hmax));
+  h->uniform_cubic = (h->hp.skf == 1 && uh);
   if (h->hp.cont_density) CUDA_TRY(cudaMemsetAsync(h->divu, 0, (nt - nn) * sizeof(double), st));  // grad_u = 0, mat:930
+  {  // mass/rho palette per species: sweep A rebuilds (m/rho)*w from the partner's class and the streamed weight
+    bool u = !h->hp.cont_density && nn > 0 && nt > nn && n2 < (size_t)QID_MASK;  // two id bits carry the class
+    std::vector<unsigned char> cls(n2, 0);
+    double pal[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    int npal[2] = {0, 0};
+    for (size_t i = 0; u && i < nt; ++i) {
+      const int sp = i < nn ? 0 : 1;
+      const double v = s->mass[i] / s->rho[i];  // the reference's mass(j)/rho(j)
+      int c = 0;
+      while (c < npal[sp] && pal[sp][c] != v) ++c;
+      if (c == npal[sp]) {
+        if (c == 4) {
+          u = false;
+          break;
+        }
+        pal[sp][npal[sp]++] = v;
+      }
+      cls[i] = (unsigned char)c;
+    }
+    if (const char *e = getenv("SPSPH_NO_UMOR")) u = u && atoi(e) == 0;
+    if (u != h->umor) h->cap0 = 0;  // the list-0 arrays were sized for the other mode: start over
+    h->umor = u;
+    h->pal_node = MorPalette{pal[0][0], pal[0][1], pal[0][2], pal[0][3]};
+    h->pal_sp = MorPalette{pal[1][0], pal[1][1], pal[1][2], pal[1][3]};
+    if (u) CUDA_TRY(cudaMemcpyAsync(h->mcls, cls.data(), n2, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // cls is a local
+  }
   h->cur = 0;
   CUDA_TRY(up(h->stage_vel, s->vel, 2 * nt * 8));
   CUDA_TRY(up(h->stage_stress, s->stress, 4 * nt * 8));

@@ -136,7 +136,13 @@ __device__ __forceinline__ void cp_async_wait() {
 // (warp-uniform), `cnt` the calling lane's own list length. gather(q) -> R fetches the partner record (q < 0:
 // past the end); compute(q[4], pay[NARR-1][4], rec[4], nvalid) consumes one group of entries in list order
 // (pay: raw 32-bit payloads of arrays 1..NARR-1; entries u >= nvalid are past the end of this lane's list).
-template <int NARR, int NG, class R, int GR = ELL_GROUP, int SUB = ELL_SUB, class GatherF, class ComputeF>
+// The two top bits of a partner id of list 0 may carry the partner's mass/rho class (QCLASS_SHIFT, written by the fill
+// pass when the host found at most four distinct values per species); gather() always receives the plain id, and so
+// does compute() unless RAWQ asks for the stored word (sweep A, which turns the class into the factor (m/rho)*w).
+constexpr int QCLASS_SHIFT = 30;
+constexpr int QID_MASK = (1 << QCLASS_SHIFT) - 1;
+template <int NARR, int NG, class R, int GR = ELL_GROUP, int SUB = ELL_SUB, bool RAWQ = false, class GatherF,
+          class ComputeF>
 __device__ __forceinline__ void ell_stream(const int *const *arr, size_t slice_off, int rows, int cnt, int *smw,
                                            GatherF gather, ComputeF compute) {
   static_assert(GR % 4 == 0 && GR % SUB == 0, "group = whole 16-byte cp.async rows, consumed in SUB-entry parts");
@@ -167,8 +173,9 @@ __device__ __forceinline__ void ell_stream(const int *const *arr, size_t slice_o
       R cur[SUB];
 #pragma unroll
       for (int u = 0; u < SUB; ++u) {
-        q[u] = sl[(hh * SUB + u) * 32 + lane];
-        cur[u] = gather((g * GR + hh * SUB + u) < cnt ? q[u] : -1);
+        const int raw = sl[(hh * SUB + u) * 32 + lane];
+        q[u] = RAWQ ? raw : (raw & QID_MASK);
+        cur[u] = gather((g * GR + hh * SUB + u) < cnt ? (raw & QID_MASK) : -1);
       }
 #pragma unroll
       for (int a = 1; a < NARR; ++a)
@@ -301,10 +308,20 @@ __device__ __forceinline__ double h0_of(int lo, int hi) { return __hiloint2doubl
 //   FIRST: first sweep A of the step -> computes and stores cspm_norm (needs w and the partner's m, rho)
 // Streams {partner id, (m/rho)_partner*w [, w]} and gathers ONE 16-byte (node velocity) or 32-byte (stress) record.
 // ------------------------------------------------------------------------------------------------------
-template <bool FIRST, bool FROMB>
+// UMOR: mass/rho takes at most four distinct values within a species (lattice set-ups: interior, edge and corner
+// particles; the host checks it at upload). The fill pass then stores the partner's class in the two top bits of its
+// id instead of the 8-byte product (m/rho)*w, and the sweep rebuilds the product from the class and the streamed
+// weight -- bit-identical -- streaming 8 bytes per entry instead of 12.
+struct MorPalette {
+  double v0, v1, v2, v3;
+};
+__device__ __forceinline__ double palette_value(const MorPalette &p, unsigned c) {
+  return c == 0 ? p.v0 : (c == 1 ? p.v1 : (c == 2 ? p.v2 : p.v3));
+}
+template <bool FIRST, bool FROMB, bool UMOR>
 __global__ void __launch_bounds__(128, SPSPH_MINB)
 k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L, const int *__restrict__ n0,
-             StatePtrs st, int do_adapt, int do_bc) {
+             StatePtrs st, int do_adapt, int do_bc, MorPalette mor_u) {
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;  // species-sorted index of the stress particle
   if ((k0 & ~31) >= M.ns) return;                         // whole warp past the end
   const bool live = k0 < M.ns;
@@ -327,9 +344,10 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   }
   double vtx = 0.0, vty = 0.0, nrm = 0.0;
   {
-    constexpr int NARR = FIRST ? 4 : 3;
+    constexpr int NARR = UMOR ? 2 : (FIRST ? 4 : 3);
     __shared__ __align__(16) int smem[4 * ELL_SMEM_G(NARR, A_NG, A_GR)];
-    const int *arrs[4] = {L.idx0, L.h0lo, L.h0hi, reinterpret_cast<const int *>(L.w0)};
+    const int *arrs[4] = {L.idx0, UMOR ? reinterpret_cast<const int *>(L.w0) : L.h0lo, L.h0hi,
+                          reinterpret_cast<const int *>(L.w0)};
     const double *__restrict__ NAv = st.NA;
     const Rec4 *__restrict__ NBv = st.NBr;
     // FIRST also needs the partner's mass and density (cspm_norm, main:433): they ride in the same 32-byte record
@@ -337,7 +355,7 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
     struct RecN {
       double2 v, mr;
     };
-    ell_stream<NARR, A_NG, RecN, A_GR, A_GR>(
+    ell_stream<NARR, A_NG, RecN, A_GR, A_GR, UMOR>(
         arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM_G(NARR, A_NG, A_GR),
         [&](int q) {
           const int qq = (q < 0 || q >= P.nnode) ? 0 : q;
@@ -355,8 +373,13 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
         [&](const int(&q)[A_GR], const int(&pay)[NARR - 1][A_GR], const RecN(&r)[A_GR], int nvalid) {
 #pragma unroll
           for (int u = 0; u < A_GR; ++u) {
-            const bool ok = (u < nvalid) && (q[u] < P.nnode);  // dummy partners (type 9) take no part
-            double h2 = h0_of(pay[0][u], pay[1][u]);           // (mass(i)/rho(i))*w, main:431
+            const int qid = UMOR ? (q[u] & QID_MASK) : q[u];
+            const bool ok = (u < nvalid) && (qid < P.nnode);  // dummy partners (type 9) take no part
+            double h2;  // (mass(i)/rho(i))*w, main:431
+            if constexpr (UMOR)
+              h2 = palette_value(mor_u, (unsigned)q[u] >> QCLASS_SHIFT) * (double)__int_as_float(pay[0][u]);
+            else
+              h2 = h0_of(pay[0][u], pay[1][u]);
             if (FIRST && P.cont_density) {  // the density moves: the streamed product of the fill pass is stale
               const double rq = ok ? r[u].mr.y : 1.0;
               h2 = div_rn(r[u].mr.x, rq, __drcp_rn(rq)) * (double)__int_as_float(pay[NARR - 2][u]);
@@ -391,10 +414,10 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   strec(st.SB, ks, s.s1 / r2, s.s2 / r2, s.s3 / r2, st.mass[id]);
 }
 
-template <bool FIRST, bool FROMB, bool EPSP>
+template <bool FIRST, bool FROMB, bool EPSP, bool UMOR>
 __global__ void __launch_bounds__(128, SPSPH_MINB)
 k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n0,
-               StatePtrs st, int do_adapt, int do_bc) {
+               StatePtrs st, int do_adapt, int do_bc, MorPalette mor_u) {
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
   if ((k0 & ~31) >= M.nn) return;  // whole warp past the end
   const bool live = k0 < M.nn;
@@ -420,10 +443,11 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
       double ep;
       double2 mr;
     };
-    constexpr int NARR = FIRST ? 4 : 3;
+    constexpr int NARR = UMOR ? 2 : (FIRST ? 4 : 3);
     __shared__ __align__(16) int smem[4 * ELL_SMEM_G(NARR, A_NG, A_GR)];
-    const int *arrs[4] = {L.idx0, L.h0lo, L.h0hi, reinterpret_cast<const int *>(L.w0)};
-    ell_stream<NARR, A_NG, RecS, A_GR, A_GR>(
+    const int *arrs[4] = {L.idx0, UMOR ? reinterpret_cast<const int *>(L.w0) : L.h0lo, L.h0hi,
+                          reinterpret_cast<const int *>(L.w0)};
+    ell_stream<NARR, A_NG, RecS, A_GR, A_GR, UMOR>(
         arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM_G(NARR, A_NG, A_GR),
         [&](int q) {
           const int qs = (q < 0 || q >= P.ntotal) ? 0 : q - P.nnode;
@@ -436,8 +460,13 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
         [&](const int(&q)[A_GR], const int(&pay)[NARR - 1][A_GR], const RecS(&r)[A_GR], int nvalid) {
 #pragma unroll
           for (int u = 0; u < A_GR; ++u) {
-            const bool ok = (u < nvalid) && (q[u] < P.ntotal);  // dummy partners (type 6) take no part
-            double h1 = h0_of(pay[0][u], pay[1][u]);            // (mass(j)/rho(j))*w, main:430
+            const int qid = UMOR ? (q[u] & QID_MASK) : q[u];
+            const bool ok = (u < nvalid) && (qid < P.ntotal);  // dummy partners (type 6) take no part
+            double h1;  // (mass(j)/rho(j))*w, main:430
+            if constexpr (UMOR)
+              h1 = palette_value(mor_u, (unsigned)q[u] >> QCLASS_SHIFT) * (double)__int_as_float(pay[0][u]);
+            else
+              h1 = h0_of(pay[0][u], pay[1][u]);
             if (FIRST && P.cont_density) {  // the density moves: recompute the factor, and interpolate rho (main:437)
               const double rq = ok ? r[u].mr.y : 1.0;
               h1 = div_rn(r[u].mr.x, rq, __drcp_rn(rq)) * (double)__int_as_float(pay[NARR - 2][u]);
@@ -733,8 +762,12 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
 
 // artificial_viscosity, main:826-904 (fp32 locals and accumulators, list order): one thread per node over its
 // node-node list; xij, yij, h were rounded to fp32 when the list was built, so ONE 32-byte gather per entry.
+// UH: one smoothing length for every particle (host-checked at upload): h = 0.5*(h_i + h_j) is that constant and
+// is not streamed (24 instead of 28 bytes per entry).
+template <bool UH>
 __global__ void __launch_bounds__(128, SPSPH_MINB)
-k_artvisc(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n1, StatePtrs st) {
+k_artvisc(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n1, StatePtrs st,
+          float h_u) {
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
   if ((k0 & ~31) >= M.nn) return;  // whole warp past the end
   const bool live = k0 < M.nn;
@@ -748,18 +781,24 @@ k_artvisc(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, c
   const double rp = self.d;
   float acc1 = 0.f, acc2 = 0.f;
   constexpr int NG = 3;
-  __shared__ __align__(16) int smem[4 * ELL_SMEM(6, NG)];
+  constexpr int NARR = UH ? 5 : 6;
+  __shared__ __align__(16) int smem[4 * ELL_SMEM(NARR, NG)];
   const int *arrs[6] = {L.idxC, reinterpret_cast<const int *>(L.gxC), reinterpret_cast<const int *>(L.gyC),
                         reinterpret_cast<const int *>(L.xC), reinterpret_cast<const int *>(L.yC),
                         reinterpret_cast<const int *>(L.hC)};
-  ell_stream<6, NG, Rec4>(
-      arrs, (size_t)L.offC[t / SLICE], wrowsC, cntc, smem + (threadIdx.x >> 5) * ELL_SMEM(6, NG),
+  ell_stream<NARR, NG, Rec4>(
+      arrs, (size_t)L.offC[t / SLICE], wrowsC, cntc, smem + (threadIdx.x >> 5) * ELL_SMEM(NARR, NG),
       [&](int q) { return ldrec(st.NB, q < 0 ? 0 : q); },
-      [&](const int(&)[ELL_SUB], const int(&pay)[5][ELL_SUB], const Rec4(&r)[ELL_SUB], int nvalid) {
+      [&](const int(&)[ELL_SUB], const int(&pay)[NARR - 1][ELL_SUB], const Rec4(&r)[ELL_SUB], int nvalid) {
         float visc[ELL_SUB];
 #pragma unroll
         for (int u = 0; u < ELL_SUB; ++u) {  // independent per entry: interleaves
-          const float xij = __int_as_float(pay[2][u]), yij = __int_as_float(pay[3][u]), h = __int_as_float(pay[4][u]);
+          const float xij = __int_as_float(pay[2][u]), yij = __int_as_float(pay[3][u]);
+          float h;
+          if constexpr (UH)
+            h = h_u;
+          else
+            h = __int_as_float(pay[4][u]);
           const float rho2 = (float)(0.5 * (rp + r[u].d));
           const float cs = 600.f;
           float div_u = (float)((double)xij * (vp.x - r[u].a));
@@ -1335,7 +1374,7 @@ __global__ void k_free_surface(DevParams P, SlotMap M, SortArrays S, const int *
   {
     int e0 = 0, e1 = 0;
     auto skip_walls = [&]() {
-      while (e0 < cnt0 && L.idx0[o0 + (size_t)e0 * SLICE] >= P.ntotal) ++e0;
+      while (e0 < cnt0 && (L.idx0[o0 + (size_t)e0 * SLICE] & QID_MASK) >= P.ntotal) ++e0;
     };
     skip_walls();
     while (e0 < cnt0 || e1 < cnt1) {
@@ -1345,7 +1384,7 @@ __global__ void k_free_surface(DevParams P, SlotMap M, SortArrays S, const int *
       else if (e1 >= cnt1)
         take0 = true;
       else {
-        const int q0 = L.idx0[o0 + (size_t)e0 * SLICE];
+        const int q0 = L.idx0[o0 + (size_t)e0 * SLICE] & QID_MASK;
         const int q1 = sp == SP_NODE ? L.idxC[o1 + (size_t)e1 * SLICE] : L.idxD[o1 + (size_t)e1 * SLICE];
         take0 = before(key_of(q0), key_of(q1));
       }
@@ -1353,9 +1392,9 @@ __global__ void k_free_surface(DevParams P, SlotMap M, SortArrays S, const int *
         const size_t a = o0 + (size_t)e0 * SLICE;
         const float gx = L.gx0[a], gy = L.gy0[a];  // reference orientation: pair_i = stress particle
         if (sp == SP_STRESS)
-          step1(L.idx0[a], gx, gy);
+          step1(L.idx0[a] & QID_MASK, gx, gy);
         else
-          step1(L.idx0[a], -gx, -gy);
+          step1(L.idx0[a] & QID_MASK, -gx, -gy);
         ++e0;
         skip_walls();
       } else {
@@ -1394,7 +1433,7 @@ __global__ void k_free_surface(DevParams P, SlotMap M, SortArrays S, const int *
   };
   for (int e = 0; e < cnt1 && !covered; ++e) scan(sp == SP_NODE ? L.idxC[o1 + (size_t)e * SLICE] : L.idxD[o1 + (size_t)e * SLICE]);
   for (int e = 0; e < cnt0 && !covered; ++e) {
-    const int q = L.idx0[o0 + (size_t)e * SLICE];
+    const int q = L.idx0[o0 + (size_t)e * SLICE] & QID_MASK;
     if (q >= P.ntotal) scan(q);
   }
   if (bc_or_not[id] != 1) bc_or_not[id] = covered ? 0 : 2;
