@@ -47,9 +47,40 @@ CASES = {
     "bui_cont_density": ("bui", lambda n: dict(decks.bui_spec(maxtimestep=n), cont_density=True), 40, (40,)),
     "vs_cont_density_sle2": ("vs", lambda n: dict(decks.vertical_slope_spec(maxtimestep=n), cont_density=True), 40, (40,)),
     "sl_cont_density_sle2": ("sl", lambda n: dict(decks.strain_localisation_spec(maxtimestep=n), cont_density=True), 30, (30,)),
+    # Perzyna viscoplasticity with the other yield criteria of invar09 / yieldf09 (strain_localisation copy
+    # mat:2277-2296, 2423-2461): Tresca, Mohr-Coulomb, Drucker-Prager; yield stress lowered so that the sample
+    # yields over a wide zone within the run; exponential flow rule (nflow /= 1) and fnorm**delta with delta /= 1
+    "sl_tresca": ("sl", lambda n: _sl_perzyna(n, ncrit=1), 60, (60,)),
+    "sl_mohr_coulomb": ("sl", lambda n: _sl_perzyna(n, ncrit=3, frict=20.), 60, (60,)),
+    "sl_dp_perzyna": ("sl", lambda n: _sl_perzyna(n, ncrit=4, frict=20.), 60, (60,)),
+    "sl_vm_expflow": ("sl", lambda n: _sl_perzyna(n, ncrit=2, nflow=2, delta=1.5), 60, (60,)),
+    "sl_vm_powflow": ("sl", lambda n: _sl_perzyna(n, ncrit=2, delta=1.5), 60, (60,)),
+    # prescribed-traction free surface (ifsigman = 1: apply_stress_free, mat:1756-1839, on the nodes that
+    # get_nodes_on_free_surface marked at the end of the previous step) and XSPH together with boundary conditions
+    # (main:224-230 strips the BCs of the neighbours of free-surface nodes)
+    "sl_sigman": ("sl", lambda n: dict(_sl_perzyna(n, ncrit=2, free_right=True), ifsigman=1), 60, (60,)),
+    "vs_sigman": ("vs", lambda n: dict(_vs_free_right(n), ifsigman=1), 60, (60,)),
+    "sl_xsph": ("sl", lambda n: dict(_sl_perzyna(n, ncrit=2, free_right=True), xsph=True), 60, (60,)),
+    "sl_sigman_xsph": ("sl", lambda n: dict(_sl_perzyna(n, ncrit=2, free_right=True), ifsigman=1, xsph=True), 60, (60,)),
     # the inside approach pressed against its walls long enough for boundary_forces to act
     "bui_inside_sp1_long": ("bui", lambda n: decks.bui_spec(maxtimestep=n, mode="inside", npoints=1), 1510, 1500),
 }
+
+
+def _sl_perzyna(n, ncrit, frict=0., nflow=1, delta=1., yield0=1.5e5, free_right=False):
+    s = decks.strain_localisation_spec(maxtimestep=n)
+    s["props"] = [2, ncrit, 8.e07, 0.25, 1., 2.e3, yield0, -8.e06, frict, 50., delta, nflow]
+    if free_right:  # no boundary conditions on x = 0.5: get_nodes_on_free_surface marks that side (bc_or_not = 2)
+        s["segments"] = [g for g in s["segments"] if not (g[0] == 0.5 and g[2] == 0.5)]
+    return s
+
+
+def _vs_free_right(n):
+    """vertical slope with moving particles and without the zero-traction BCs of its cut face x = 10"""
+    s = decks.vertical_slope_spec(maxtimestep=n)
+    s["update_x"] = True
+    s["segments"] = [g for g in s["segments"] if not (g[0] == 10. and g[2] == 10.)]
+    return s
 
 
 def golden_path(case):
@@ -63,8 +94,8 @@ def spec_of(case):
 
 
 # cases whose options the CUDA engine does not implement yet: spsph_create must refuse them
-DEVICE_UNSUPPORTED = set()
+DEVICE_UNSUPPORTED = {"sl_tresca", "sl_mohr_coulomb", "sl_dp_perzyna", "sl_sigman", "vs_sigman", "sl_xsph", "sl_sigman_xsph"}
 # cases where the engine evaluates libm functions (atan, sin, cos, pow) with CUDA's implementations instead of
 # glibc's: agreement to the north star's 1e-9 relative L-inf instead of bit for bit
-DEVICE_TOLERANCE = {"bui_art_stress": 1e-9, "sl_art_stress": 1e-9}
+DEVICE_TOLERANCE = {"bui_art_stress": 1e-9, "sl_art_stress": 1e-9, "sl_vm_expflow": 1e-9, "sl_vm_powflow": 1e-9}
 

@@ -23,6 +23,7 @@
 //   artificial_viscosity main:826-904   get_spin_rate_tensor main:1021-1034
 //   Check_Out_Domain main:1170-1194     grid_find_NEW main:1199-1435 kernel main:1440-1538
 //   Pint_Update mat:1574-1634           BCs/Normal_BCs mat:1641-1770 update_strain mat:1864-1880
+//   apply_stress_free mat:1775-1858
 //   plastic_terms mat:1884-1954         drucker_prager mat:1958-2083 adapt_stress2 mat:2087-2161
 //   Get_Vivel/invar09/yieldf09/flowvp09/Get_Dmatx (strain_localisation copy) :2169-2576
 //   Get_derivative_intvars mat:2697-2760  gravity_force mat:2809-2871
@@ -311,6 +312,26 @@ struct Oracle {
         else if (bc_var == 2)
           S(2, ip) = bc_value;
       }
+    }
+    if (p.ifsigman == 1) apply_stress_free();
+  }
+
+  // ---- apply_stress_free, vertical_slope copy mat:1756-1839 (identical in all copies) -----------------
+  // Velocity particles that get_nodes_on_free_surface marked (bc_or_not == 2) at the end of the previous step and
+  // that are not next to a wall (bc_int /= 1) keep only the stress component tangential to the surface:
+  // sigma_tt = n_y^2 sxx - 2 n_x n_y sxy + n_x^2 syy, rotated back; szz <- n_x^2 sigma_tt.
+  void apply_stress_free() {
+    for (int ip = 1; ip <= nnode; ++ip) {
+      if (!(bc_or_not[ip - 1] == 2 && bc_int[ip - 1] != 1)) continue;
+      const double costh = normal[2 * (size_t)(ip - 1)], sinth = normal[2 * (size_t)(ip - 1) + 1];
+      if (std::isnan(costh) || std::isnan(sinth)) continue;
+      const double s2 = sinth * sinth, c2 = costh * costh, sc = sinth * costh;
+      const double sxx0 = S(1, ip), syy0 = S(2, ip), sxy0 = S(3, ip);
+      const double sigmatt = s2 * sxx0 - 2 * sc * sxy0 + c2 * syy0;
+      S(1, ip) = s2 * sigmatt;
+      S(2, ip) = c2 * sigmatt;
+      S(3, ip) = -sc * sigmatt;
+      S(4, ip) = c2 * sigmatt;
     }
   }
 

@@ -857,7 +857,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
     return fail("XSPH together with boundary conditions is not supported (XSPH_update strips the BC flag of particles "
                 "next to a free-surface node, main:224-230)");
   if (p->ntype_eco > 1 && !(p->ncrit == 2 || p->ncrit == 12))
-    return fail("only ncrit = 2 (von Mises) and ncrit = 12 (Drucker-Prager) are supported");
+    return fail("this yield criterion is not supported: only ncrit = 2 (von Mises) and ncrit = 12 (Drucker-Prager) are");
   if (p->ntype_eco > 1 && p->ncrit == 2 && !(p->props[6] > (double)0.001f))
     return fail("initial yield surface size too small (the reference STOPs, mat:2322-2332)");
   if (p->sph_shift && p->shift_update <= 0) return fail("shift_update must be positive");

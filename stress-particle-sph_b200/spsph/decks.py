@@ -53,7 +53,7 @@ def write_deck(directory, spec):
         dat += ["extra_model_parameters", _row(*spec["props_extra"])]  # 8 values (props 13..20)
     dat += ["ic_unks", "0"]
     bcs = spec.get("bcs", [])
-    dat += ["BCs_nprer_sigman", _row(len(bcs), 0)]
+    dat += ["BCs_nprer_sigman", _row(len(bcs), spec.get("ifsigman", 0))]
     if bcs:
         dat += ["bc_table"] + [_row(*b) for b in bcs]  # 8 values each: id var tvar a1 a0 w fi Tf
     segs = spec.get("segments", [])
