@@ -93,9 +93,14 @@ def spec_of(case):
     return which, spec_fn(nsteps)
 
 
-# cases whose options the CUDA engine does not implement yet: spsph_create must refuse them
-DEVICE_UNSUPPORTED = {"sl_tresca", "sl_mohr_coulomb", "sl_dp_perzyna", "sl_sigman", "vs_sigman", "sl_xsph", "sl_sigman_xsph"}
-# cases where the engine evaluates libm functions (atan, sin, cos, pow) with CUDA's implementations instead of
-# glibc's: agreement to the north star's 1e-9 relative L-inf instead of bit for bit
-DEVICE_TOLERANCE = {"bui_art_stress": 1e-9, "sl_art_stress": 1e-9, "sl_vm_expflow": 1e-9, "sl_vm_powflow": 1e-9}
-
+# cases whose options the CUDA engine does not implement: spsph_create must refuse them
+DEVICE_UNSUPPORTED = set()
+# cases where the engine evaluates libm functions (atan, asin, sin, cos, tan, exp, pow) with CUDA's implementations
+# instead of glibc's: agreement to the north star's 1e-9 relative L-inf instead of bit for bit
+DEVICE_TOLERANCE = {"bui_art_stress": 1e-9, "sl_art_stress": 1e-9, "sl_vm_expflow": 1e-9, "sl_vm_powflow": 1e-9,
+                    "sl_tresca": 1e-9, "sl_mohr_coulomb": 1e-9}
+# device paths written after this round's GPU budget was spent: their first run on hardware
+# is tests/test_zz_gpu_new_paths.py, the last file of the GPU suite, so that a surprise there cannot mask the
+# verified cases of tests/test_gpu_reference.py (the driver runs pytest with -x)
+DEVICE_UNVERIFIED = {"sl_tresca", "sl_mohr_coulomb", "sl_dp_perzyna", "sl_vm_expflow", "sl_vm_powflow", "sl_sigman",
+                     "vs_sigman", "sl_xsph", "sl_sigman_xsph"}

@@ -1323,6 +1323,7 @@ void *oracle_create(const spsph_params *p, const spsph_state *s) {
   copy_in(o->bc_or_not, s->bc_or_not, nt);
   copy_in(o->bc_info, s->bc_info, 8 * nt);
   o->grad_u.assign(4 * nt, 0.0);
+  o->normal.assign(2 * nt, 0.0);  // module array, first written by get_nodes_on_free_surface
   o->art_visc.assign(2 * nn, 0.0);
   o->f_bound.assign(2 * nn, 0.0);
   o->Ddev_strn.assign(nt, 0.0);
@@ -1394,6 +1395,67 @@ int oracle_pairs(void *h, int64_t *npairs, int32_t *pair_i, int32_t *pair_j, int
     dwdy[t] = c.dwdy;
   }
   return 0;
+}
+
+// ---- hooks for tests/test_oracle_cpu.py::test_device_math_transcription: single routines on caller-given inputs ----
+int oracle_plastic_terms(void *h, double time_sph, int32_t n, const double *stress, const double *grad, const double *epsp,
+                         double *f_drucker, double *Gs, double *der1) {
+  Oracle *o = (Oracle *)h;
+  if (n > o->ntotal) return 1;
+  o->time_sph = time_sph;
+  for (int i = 1; i <= n; ++i) {
+    o->GU(1, 1, i) = grad[4 * (i - 1)];
+    o->GU(1, 2, i) = grad[4 * (i - 1) + 1];
+    o->GU(2, 1, i) = grad[4 * (i - 1) + 2];
+    o->GU(2, 2, i) = grad[4 * (i - 1) + 3];
+    o->IV1(i) = epsp[i - 1];
+    o->f_drucker[i - 1] = f_drucker[i - 1];
+    if (!o->plastic_terms(i, stress + 4 * (i - 1), Gs + 4 * (i - 1), der1[i - 1])) return 1;
+    f_drucker[i - 1] = o->f_drucker[i - 1];
+  }
+  return 0;
+}
+
+int oracle_adapt_stress(void *h, int32_t n, double *stress) {  // adapt_stress2 on the first n particles
+  Oracle *o = (Oracle *)h;
+  if (n > o->ntotal) return 1;
+  const std::vector<double> keep = o->stress;
+  std::copy(stress, stress + 4 * (size_t)n, o->stress.begin());
+  o->adapt_stress2();
+  std::copy(o->stress.begin(), o->stress.begin() + 4 * (size_t)n, stress);
+  o->stress = keep;
+  return 0;
+}
+
+int oracle_stress_free(void *h, int32_t n, double *stress, const double *normal) {  // apply_stress_free, first n nodes
+  Oracle *o = (Oracle *)h;
+  if (n > o->nnode) return 1;
+  const std::vector<double> keep = o->stress;
+  const std::vector<int32_t> kb = o->bc_or_not, ki = o->bc_int;
+  o->normal.assign(2 * (size_t)o->ntotal, 0.0);
+  std::copy(stress, stress + 4 * (size_t)n, o->stress.begin());
+  std::copy(normal, normal + 2 * (size_t)n, o->normal.begin());
+  std::fill(o->bc_or_not.begin(), o->bc_or_not.end(), 0);
+  std::fill(o->bc_or_not.begin(), o->bc_or_not.begin() + n, 2);
+  std::fill(o->bc_int.begin(), o->bc_int.end(), 0);
+  o->apply_stress_free();
+  std::copy(o->stress.begin(), o->stress.begin() + 4 * (size_t)n, stress);
+  o->stress = keep;
+  o->bc_or_not = kb;
+  o->bc_int = ki;
+  return 0;
+}
+
+void oracle_kernel(void *h, int32_t n, const double *r, const double *dx, const double *dy, const double *hh, double *w,
+                   double *gx, double *gy) {
+  Oracle *o = (Oracle *)h;
+  for (int i = 0; i < n; ++i) {
+    const double d[2] = {dx[i], dy[i]};
+    double g[2];
+    o->kernel(r[i], d, hh[i], w[i], g);
+    gx[i] = g[0];
+    gy[i] = g[1];
+  }
 }
 
 const char *oracle_last_error(void *h) { return ((Oracle *)h)->err.c_str(); }

@@ -18,6 +18,7 @@ struct DevParams {
   int skf, scale_k, cspm, update_x, xsph, ncrit, ntype_eco, ntype_solid;
   int cont_density, sle;  // continuity density on the stress particles (main:706-713); sle = 2: smoothing length follows
   int no_bcs, bc_nloop;  // bc_nloop: Normal_BCs loop bound (ntotal or nnode), mat:1683
+  int ifsigman;          // 1: BCs also calls apply_stress_free (mat:1633-1637)
   int sp_sph, inside_approach, vel_vector, shift_update;
   int adapt;  // ncrit == 12
   int track_nint;  // n_int is only refreshed by artificial_viscosity / XSPH_update / isolated_nodes
@@ -28,6 +29,8 @@ struct DevParams {
   // Drucker-Prager constants of adapt_stress2 (fp64, mat:2096-2100), computed once on the host with the
   // same expressions (sqrt and division are correctly rounded on both sides)
   double dp_alpha2, dp_kc;
+  // sin(props(1,9)*0.017453292) of invar09 / yieldf09 (Mohr-Coulomb, Drucker-Prager Perzyna), host libm
+  double snphi;
   // per step (host-computed: time curves, exp/sin of Normal_BCs and gravity factor involve libm)
   int itimestep;
   double time_sph, dt;
@@ -170,8 +173,8 @@ __device__ __forceinline__ void adapt_stress(const DevParams &P, Stress4 &s) {
 }
 
 // ---- Normal_BCs for one particle, mat:1665-1770 ----
-__device__ __forceinline__ void apply_bcs(const DevParams &P, const int *__restrict__ bc_or_not,
-                                          const int *__restrict__ bc_info, int ip, double2 &v, Stress4 &s) {
+__device__ __forceinline__ void normal_bcs(const DevParams &P, const int *__restrict__ bc_or_not,
+                                           const int *__restrict__ bc_info, int ip, double2 &v, Stress4 &s) {
   if (P.no_bcs <= 0 || ip >= P.bc_nloop) return;
   if (bc_or_not[ip] != 1) return;
   const int *bi = bc_info + 8 * (size_t)ip;
@@ -192,6 +195,34 @@ __device__ __forceinline__ void apply_bcs(const DevParams &P, const int *__restr
       s.s3 = val;
     else if (var == 2)
       s.s2 = val;
+  }
+}
+
+// ---- apply_stress_free body for one marked velocity particle, vertical_slope copy mat:1795-1826: only the
+// stress component tangential to the free surface (unit normal nx, ny) survives ----
+__device__ __forceinline__ void stress_free(Stress4 &s, double nx, double ny) {
+  const double costh = nx, sinth = ny;
+  const double s2 = sinth * sinth, c2 = costh * costh, sc = sinth * costh;
+  const double sigmatt = s2 * s.s1 - 2 * sc * s.s3 + c2 * s.s2;
+  s.s1 = s2 * sigmatt;
+  s.s2 = c2 * sigmatt;
+  s.s3 = -sc * sigmatt;
+  s.s4 = c2 * sigmatt;
+}
+
+// ---- BCs for one particle, mat:1622-1640: Normal_BCs, then (ifsigman = 1) apply_stress_free on the velocity
+// particles that get_nodes_on_free_surface marked at the end of the previous step (bc_or_not = 2) and that are not
+// next to a wall (bc_int /= 1); fs_normal: their step-4 normals (k_fs_normals), NaN when no marked neighbour ----
+__device__ __forceinline__ void apply_bcs(const DevParams &P, const int *__restrict__ bc_or_not,
+                                          const int *__restrict__ bc_info, const int *__restrict__ bc_int,
+                                          const double *__restrict__ fs_normal, int ip, double2 &v, Stress4 &s) {
+  if (P.no_bcs <= 0) return;
+  normal_bcs(P, bc_or_not, bc_info, ip, v, s);
+  if (P.ifsigman == 1 && ip < P.nnode) {
+    if (bc_or_not[ip] == 2 && bc_int[ip] != 1) {
+      const double2 n = ld2(fs_normal, ip);
+      if (n.x == n.x && n.y == n.y) stress_free(s, n.x, n.y);  // isnan(normal) -> cycle, mat:1791
+    }
   }
 }
 
@@ -243,6 +274,21 @@ __device__ __forceinline__ void drucker_prager(const DevParams &P, const Stress4
   }
 }
 
+// ---- Gs = -De * vivel with the plane-strain De of Get_Dmatx (strain_localisation copy :2545-2576) ----
+__device__ __forceinline__ void perzyna_gs(const DevParams &P, const double vivel[4], double Gs[4]) {
+  const double young = P.props[2], poiss = P.props[3];
+  const double cst = young * (1.0 - poiss) / ((1.0 + poiss) * (1.0 - 2.0 * poiss));
+  const double off = cst * poiss / (1.0 - poiss);
+  const double d33 = (1.0 - 2.0 * poiss) * cst / (2.0 * (1.0 - poiss));
+  // Gs(i) = Gs(i) - Dmatx(i,j)*vivel(j), j = 1..4 in order, zero entries included (mat:1933-1937)
+  const double D[4][4] = {{cst, off, 0.0, off}, {off, cst, 0.0, off}, {0.0, 0.0, d33, 0.0}, {off, off, 0.0, cst}};
+  for (int a = 0; a < 4; ++a) {
+    double g = 0.0;
+    for (int b = 0; b < 4; ++b) g = g - D[a][b] * vivel[b];
+    Gs[a] = g;
+  }
+}
+
 // ---- Get_Vivel (von Mises branch, ncrit = 2) + Get_Dmatx: strain_localisation copy :2169-2576, fp64 ----
 // Returns Gs = -De * vivel and vivel. The trigonometric terms of invar09/yieldf09 only feed cons1..3 of
 // the other criteria and are not evaluated.
@@ -291,16 +337,155 @@ __device__ __forceinline__ void von_mises_perzyna(const DevParams &P, const Stre
       for (int s = 0; s < 4; ++s) vivel[s] = cmult * avect[s];
     }
   }
-  const double young = P.props[2], poiss = P.props[3];
-  const double cst = young * (1.0 - poiss) / ((1.0 + poiss) * (1.0 - 2.0 * poiss));
-  const double off = cst * poiss / (1.0 - poiss);
-  const double d33 = (1.0 - 2.0 * poiss) * cst / (2.0 * (1.0 - poiss));
-  // Gs(i) = Gs(i) - Dmatx(i,j)*vivel(j), j = 1..4 in order, zero entries included (mat:1933-1937)
-  const double D[4][4] = {{cst, off, 0.0, off}, {off, cst, 0.0, off}, {0.0, 0.0, d33, 0.0}, {off, off, 0.0, cst}};
-  for (int a = 0; a < 4; ++a) {
-    double g = 0.0;
-    for (int b = 0; b < 4; ++b) g = g - D[a][b] * vivel[b];
-    Gs[a] = g;
+  perzyna_gs(P, vivel, Gs);
+}
+
+// ---- Get_Vivel for the other yield criteria of invar09 / yieldf09 (strain_localisation copy :2277-2296,
+// 2423-2461): ncrit = 1 Tresca, 3 Mohr-Coulomb, 4 Drucker-Prager (Perzyna, linear hardening). Cam Clay (5) is
+// refused at spsph_create. The Lode-angle terms use CUDA's asin / sin / cos / tan (<= 2 ulp) where the reference
+// calls glibc's: agreement to the north star's 1e-9, not bit for bit (ncrit = 4 does not use them and is exact).
+// Kept out of line and fed by value so that the sweep kernel's register allocation and its vivel[] registers are
+// those of the von Mises / Drucker-Prager builds.
+__device__ __noinline__ double4 perzyna_vivel_general(int ncrit, double snphi, double fdatm0, double hards, double gamma,
+                                                      double delta, double nflow, double s1, double s2, double s3,
+                                                      double s4, double evpstn) {
+  double4 out = make_double4(0.0, 0.0, 0.0, 0.0);
+  const double root3 = (double)1.7320507764816284f;  // sqrt(3.00) in default REAL
+  const double smean = (s1 + s2 + s4) / 3.0;
+  double devia[5];
+  devia[1] = s1 - smean;
+  devia[2] = s2 - smean;
+  devia[3] = s3;
+  devia[4] = s4 - smean;
+  const double varj2 = devia[3] * devia[3] + 0.5 * (devia[1] * devia[1] + devia[2] * devia[2] + devia[4] * devia[4]);
+  const double varj3 = devia[4] * (devia[4] * devia[4] - varj2);
+  const double steff = sqrt(varj2);
+  double sint3;
+  if (steff != 0.0) {
+    sint3 = -3.0 * root3 * varj3 / (2.0 * varj2 * steff);
+    if (sint3 > 1.0) sint3 = 1.0;
+  } else {
+    sint3 = 0.0;
+  }
+  if (sint3 < -1.0) sint3 = -1.0;
+  if (sint3 > 1.0) sint3 = 1.0;
+  const double theta = asin(sint3) / 3.0;
+  double yield = 0.0;
+  if (ncrit == 1) {
+    yield = 2.0 * cos(theta) * steff;
+  } else if (ncrit == 2) {
+    yield = root3 * steff;
+  } else if (ncrit == 3) {
+    yield = smean * snphi + steff * (cos(theta) - sin(theta) * snphi / root3);
+  } else {  // ncrit == 4
+    yield = 6.0 * smean * snphi / (root3 * (3.0 - snphi)) + steff;
+  }
+  double fdatm = fdatm0 + hards * evpstn;
+  double fact = fabs(fdatm) / fabs(fdatm0);
+  if (fact < (double)0.1f) fact = (double)0.1f;
+  fdatm = fdatm0 * fact;
+  if (!(yield > fdatm)) return out;
+  // yieldf09
+  double veca2[4] = {0, 0, 0, 0}, veca3[4];
+  if (steff > 0) {
+    for (int s = 0; s < 4; ++s) veca2[s] = devia[s + 1] / (2.0 * steff);
+    veca2[2] = devia[3] / steff;
+  }
+  veca3[0] = devia[2] * devia[4] + varj2 / 3.0;
+  veca3[1] = devia[1] * devia[4] + varj2 / 3.0;
+  veca3[2] = -2.0 * devia[3] * devia[4];
+  veca3[3] = devia[1] * devia[2] - devia[3] * devia[3] + varj2 / 3.0;
+  const double veca1[4] = {1.0, 1.0, 0.0, 1.0};
+  double cons1 = 0.0, cons2 = 0.0, cons3 = 0.0;
+  if (ncrit == 1 || ncrit == 3) {
+    const double tanth = tan(theta), tant3 = tan(3.0 * theta), sinth = sin(theta), costh = cos(theta),
+                 cost3 = cos(3.0 * theta);
+    const double abthe = fabs(theta * 57.29577951308);
+    if (ncrit == 1) {
+      cons1 = 0.0;
+      if (abthe >= 29.0) {
+        cons2 = root3;
+        cons3 = 0.0;
+      } else {
+        cons2 = 2.0 * (costh + sinth * tant3);
+        cons3 = root3 * sinth / (varj2 * cost3);
+      }
+    } else {
+      cons1 = snphi / 3.0;
+      if (abthe >= 29.0) {
+        cons3 = 0.0;
+        double plumi = 1.0;
+        if (theta > 0.0) plumi = -1.0;
+        cons2 = 0.5 * (root3 + plumi * cons1 * root3);
+      } else {
+        cons2 = costh * ((1.0 + tanth * tant3) + cons1 * (tant3 - tanth) * root3);
+        cons3 = (root3 * sinth + 3.0 * cons1 * costh) / (2.0 * varj2 * cost3);
+      }
+    }
+  } else if (ncrit == 2) {
+    cons2 = root3;
+  } else {  // ncrit == 4
+    cons1 = 2.0 * snphi / (root3 * (3.0 - snphi));
+    cons2 = 1.0;
+  }
+  double avect[4];
+  for (int s = 0; s < 4; ++s) avect[s] = cons1 * veca1[s] + cons2 * veca2[s] + cons3 * veca3[s];
+  // flowvp09
+  const double allow = (double)0.01f;
+  const double fcurr = yield - fdatm;
+  const double fnorm = fcurr / fdatm;
+  if (fnorm >= allow) {
+    double cmult;
+    if (nflow != 1)
+      cmult = gamma * (exp(delta * fnorm) - 1.0);
+    else
+      cmult = gamma * ((delta == 1.0) ? fnorm : pow(fnorm, delta));
+    out.x = cmult * avect[0];
+    out.y = cmult * avect[1];
+    out.z = cmult * avect[2];
+    out.w = cmult * avect[3];
+  }
+  return out;
+}
+
+__device__ __forceinline__ void perzyna_other(const DevParams &P, const Stress4 &st, double evpstn, double Gs[4],
+                                              double vivel[4]) {
+  const double4 v = perzyna_vivel_general(P.ncrit, P.snphi, P.props[6], P.props[7], P.props[9], P.props[10], P.props[11],
+                                          st.s1, st.s2, st.s3, st.s4, evpstn);
+  vivel[0] = v.x;
+  vivel[1] = v.y;
+  vivel[2] = v.z;
+  vivel[3] = v.w;
+  perzyna_gs(P, vivel, Gs);
+}
+
+// ---- plastic_terms + Get_derivative_intvars for one stress particle, mat:1884-1954, 2697-2760 ----
+// sp: its stress; g11..g22: grad_u(1,1) grad_u(1,2) grad_u(2,1) grad_u(2,2); epsp: its accumulated deviatoric
+// viscoplastic strain (read for ncrit <= 5); fdp: its f_drucker (read and written for ncrit == 12).
+__device__ __forceinline__ void plastic_terms(const DevParams &P, const Stress4 &sp, double g11, double g12, double g21,
+                                              double g22, const double *epsp, double *fdp, double Gs[4], double &der1) {
+  if (P.ntype_eco > 1) {
+    Stress4 s2 = sp;
+    if (P.ntype_solid == 1) s2.s4 = P.props[3] * (s2.s1 + s2.s2);
+    double vivel[4] = {0.0, 0.0, 0.0, 0.0};
+    if (P.ncrit == 2) {
+      von_mises_perzyna(P, s2, *epsp, Gs, vivel);
+    } else if (P.ncrit <= 5) {
+      perzyna_other(P, s2, *epsp, Gs, vivel);
+    } else if (P.ncrit == 12) {
+      double G2[4];
+      double fd = *fdp;
+      drucker_prager(P, s2, g11, g12, g21, g22, fd, G2, vivel);
+      *fdp = fd;
+      Gs[0] = -G2[0];
+      Gs[1] = -G2[1];
+      Gs[2] = -G2[2];
+      Gs[3] = -G2[3];
+    }
+    if (P.ntype_solid == 0)
+      der1 = vivel[0];
+    else
+      der1 = sqrt((2.0 * (vivel[0] * vivel[0] + vivel[1] * vivel[1] + vivel[3] * vivel[3]) + vivel[2] * vivel[2]) / 3.0);
   }
 }
 

@@ -73,6 +73,11 @@ struct spsph_handle {
   double *displ = nullptr, *x_10 = nullptr, *disp_10 = nullptr;
   float *wallpos = nullptr, *horiz = nullptr, *n_int = nullptr;
   int *bc_int = nullptr, *bc_or_not = nullptr, *bc_info = nullptr, *if_out = nullptr;
+  // get_nodes_on_free_surface every step (instead of on demand at download): needed when its marks feed back into
+  // the time step -- apply_stress_free (ifsigman = 1) or XSPH stripping boundary conditions (main:224-230)
+  bool fs_each_step = false;
+  int *fs_cov = nullptr;        // (ntotal) covered in step 3 (f_int = -1)
+  double *fs_normal = nullptr;  // (2, nnode) step-4 normals
   int cur = 0;
   double *ivars = nullptr;  // device mirror of Internal_Vars(10, ntotal): rows 2..10 never change on the hot path
   std::vector<int32_t> h_itype;
@@ -247,6 +252,8 @@ StatePtrs state_ptrs(spsph_handle *h, int wb) {
   s.horiz = h->horiz;
   s.bc_or_not = h->bc_or_not;
   s.bc_info = h->bc_info;
+  s.bc_int = h->bc_int;
+  s.fs_normal = h->fs_normal;
   s.NA = h->NA;
   s.SA = h->SA;
   s.NSa = h->NSa;
@@ -788,6 +795,17 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   // positions, main:140-182
   k_move<<<GB, 128, 0, s>>>(P, M, S, h->L, h->n1, st, h->x, h->x00, h->displ);
   mark(h, KID_MOVE);
+  if (h->fs_each_step) {
+    // get_nodes_on_free_surface, main:152-154: after the position update, before the stress particles are re-seated;
+    // its marks (bc_or_not = 2) and normals feed the BCs of the next step
+    if (p.xsph) k_xsph_marks<<<GN, 128, 0, s>>>(P, M, S, h->L, h->n1, h->bc_or_not);
+    k_free_surface<<<GB, 128, 0, s>>>(P, M, S, h->pos_of, h->L, h->n0, h->n1, h->growth, h->x, h->mass, h->rho, h->hsml,
+                                      h->bc_or_not, h->fs_cov);
+    if (P.ifsigman)
+      k_fs_normals<<<GN, 128, 0, s>>>(P, M, S, h->pos_of, h->L, h->n0, h->n1, h->growth, h->x, h->mass, h->rho,
+                                      h->bc_or_not, h->fs_cov, h->fs_normal);
+    mark(h, KID_MOVE, P.ifsigman ? (p.xsph ? 3 : 2) : (p.xsph ? 2 : 1));
+  }
   if (p.update_x && std_sph) {  // main:166
     k_sp_follow<<<list_grid(h, P.nnode, 256), 256, 0, s>>>(P, h->x, local_list(h, P.nnode));
     mark(h, KID_SHIFT);
@@ -852,13 +870,10 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   };
   if (p->ndimn != 2 || p->nstre != 4) return fail("only ndimn = 2, nstre = 4 (plane strain) is supported");
   if (p->skf < 1 || p->skf > 3) return fail("skf must be 1 (cubic spline), 2 (Gauss) or 3 (quintic)");
-  if (p->ifsigman != 0) return fail("ifsigman = 1 (apply_stress_free) is not supported");
-  if (p->xsph && p->update_x && p->no_bcs > 0)
-    return fail("XSPH together with boundary conditions is not supported (XSPH_update strips the BC flag of particles "
-                "next to a free-surface node, main:224-230)");
-  if (p->ntype_eco > 1 && !(p->ncrit == 2 || p->ncrit == 12))
-    return fail("this yield criterion is not supported: only ncrit = 2 (von Mises) and ncrit = 12 (Drucker-Prager) are");
-  if (p->ntype_eco > 1 && p->ncrit == 2 && !(p->props[6] > (double)0.001f))
+  if (p->ntype_eco > 1 && !((p->ncrit >= 1 && p->ncrit <= 4) || p->ncrit == 12))
+    return fail("this yield criterion is not supported: ncrit must be 1 (Tresca), 2 (von Mises), 3 (Mohr-Coulomb), "
+                "4 (Drucker-Prager, Perzyna) or 12 (Drucker-Prager, Bui et al.); 5 (Cam Clay) is not built");
+  if (p->ntype_eco > 1 && p->ncrit <= 4 && !(p->props[6] > (double)0.001f))
     return fail("initial yield surface size too small (the reference STOPs, mat:2322-2332)");
   if (p->sph_shift && p->shift_update <= 0) return fail("shift_update must be positive");
   if (p->no_bcs > 16) return fail("too many BCs");
@@ -899,6 +914,9 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   P.ntype_eco = p->ntype_eco;
   P.ntype_solid = p->ntype_solid;
   P.no_bcs = p->no_bcs;
+  h->fs_each_step = p->update_x && p->no_bcs > 0 && (p->ifsigman == 1 || p->xsph);
+  // without update_x no particle is ever marked (main:140-154), apply_stress_free has nothing to act on
+  P.ifsigman = (h->fs_each_step && p->ifsigman == 1) ? 1 : 0;
   P.bc_nloop = p->bc_loop_ntotal ? p->ntotal : p->nnode;
   P.sp_sph = p->sp_sph;
   P.inside_approach = p->inside_approach;
@@ -928,6 +946,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
     P.xmin_dom[d] = p->xmin_domain[d];
     P.xmax_dom[d] = p->xmax_domain[d];
   }
+  P.snphi = std::sin(p->props[8] * (double)0.017453292f);  // invar09 :2287-2288, yieldf09 :2441, 2456
   {  // adapt_stress2 constants, mat:2096-2100 (fp64)
     const double tanfi = p->props[12], coh = p->props[13];
     P.dp_alpha2 = tanfi / (std::sqrt(9 + 12 * (tanfi * tanfi)));
@@ -964,6 +983,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   rc |= dalloc(h, &h->displ, 2 * nn) | dalloc(h, &h->x_10, 2 * nn) | dalloc(h, &h->disp_10, nn);
   rc |= dalloc(h, &h->wallpos, n2) | dalloc(h, &h->horiz, n2) | dalloc(h, &h->n_int, nn);
   rc |= dalloc(h, &h->bc_int, nn) | dalloc(h, &h->bc_or_not, nt) | dalloc(h, &h->bc_info, 8 * nt);
+  if (h->fs_each_step) rc |= dalloc(h, &h->fs_cov, nt) | dalloc(h, &h->fs_normal, 2 * nn);
   rc |= dalloc(h, &h->if_out, n2);
   rc |= dalloc(h, &h->G, 1);
   h->bbox_blocks = 148 * 8;
@@ -986,6 +1006,10 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   CUDA_TRY(cudaMemset(h->norm, 0, nt * sizeof(double)));
   CUDA_TRY(cudaMemset(h->fbound, 0, 2 * nn * sizeof(double)));
   CUDA_TRY(cudaMemset(h->aforce, 0, 2 * nn * sizeof(double)));
+  if (h->fs_each_step) {
+    CUDA_TRY(cudaMemset(h->fs_cov, 0, nt * sizeof(int)));
+    CUDA_TRY(cudaMemset(h->fs_normal, 0, 2 * nn * sizeof(double)));
+  }
   return 0;
 }
 
@@ -1190,7 +1214,7 @@ int spsph_download(spsph_handle *h, const spsph_state *s) {
     k_download_ivars<<<((int)nt + 255) / 256, 256, 0, st>>>((int)nt, h->epsp, h->ivars);
     CUDA_TRY(down(s->internal_vars, h->ivars, (size_t)SPSPH_NINT_VARS * nt * 8));
   }
-  if (s->bc_or_not && p.update_x && h->have_lists) {
+  if (s->bc_or_not && p.update_x && h->have_lists && !h->fs_each_step) {
     // get_nodes_on_free_surface (main:152-154 runs it at the end of every step; only bc_or_not leaves it)
     SlotMap ML = h->M;
     ML.nn = h->nloc[0];
@@ -1198,7 +1222,7 @@ int spsph_download(spsph_handle *h, const spsph_state *s) {
     ML.nd = h->nloc[2];
     const int T = ML.nnp + ML.nsp;
     k_free_surface<<<(T + 127) / 128, 128, 0, st>>>(h->P, ML, sort_arrays(h), h->pos_of, h->L, h->n0, h->n1, h->growth,
-                                                    h->x, h->mass, h->rho, h->hsml, h->bc_or_not);
+                                                    h->x, h->mass, h->rho, h->hsml, h->bc_or_not, nullptr);
     CUDA_TRY(cudaGetLastError());
   }
   CUDA_TRY(down(s->f_drucker, h->fdp, nt * 8));
@@ -1295,6 +1319,11 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
   }
   if (h->hp.cont_density) {
     h->err = "multi-GPU: cont_density = T is not supported (the halo records carry no density / smoothing length)";
+    return 1;
+  }
+  if (h->fs_each_step) {
+    h->err = "multi-GPU: ifsigman = 1 and XSPH with boundary conditions are not supported (the halo records carry no "
+             "free-surface marks)";
     return 1;
   }
   CUDA_TRY(cudaSetDevice(h->device));

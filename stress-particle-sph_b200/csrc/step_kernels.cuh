@@ -36,6 +36,8 @@ struct StatePtrs {
   const double2 *mrho;  // {mass, rho}: one gather where a sweep needs both (the cspm_norm pass)
   const float *wallpos, *horiz;
   const int *bc_or_not, *bc_info;
+  const int *bc_int;        // (nnode) velocity particle next to a wall particle (k_fill, main:506,579)
+  const double *fs_normal;  // (2, nnode) free-surface normals of apply_stress_free (k_fs_normals; ifsigman = 1 only)
   // format A
   double *NA;   // (2, nnode) velocity
   Rec4 *SA;     // [nstress] stress
@@ -258,7 +260,7 @@ __global__ void k_rk_begin(DevParams P, StatePtrs st, LocalList LL) {
     vn.y = v.y + 0. * (P.dt) * 0.0;
     sn = Stress4{0.0, 0.0, 0.0, 0.0};
     if (P.adapt) adapt_stress(P, sn);
-    apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
+    apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, vn, sn);
     st2(st.NA, id, vn);
     st4(st.NSa, id, sn);
   } else {
@@ -276,7 +278,7 @@ __global__ void k_rk_begin(DevParams P, StatePtrs st, LocalList LL) {
     sn.s3 = s.s3 + 0. * (P.dt) * 0.0;
     sn.s4 = s.s4 + 0. * (P.dt) * 0.0;
     if (P.adapt) adapt_stress(P, sn);
-    apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
+    apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, vn, sn);
     strec(st.SA, ks, sn.s1, sn.s2, sn.s3, sn.s4);
     st2(st.SVa, ks, vn);
     if (P.cont_density) {  // main:686-689 and the stage-1 block main:706-713 (f1rk = 0, f2rk = 1)
@@ -406,7 +408,7 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
     v.y = vty / nrm;
   }
   if (do_adapt) adapt_stress(P, s);
-  if (do_bc) apply_bcs(P, st.bc_or_not, st.bc_info, id, v, s);
+  if (do_bc) apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, v, s);
   strec(st.SVb, ks, v.x, v.y, st.mor[id], 0.0);
   st4(st.SFb, ks, s);
   const double rr = st.rho[id];
@@ -508,7 +510,7 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
     v.y = 0;
   }
   if (do_adapt) adapt_stress(P, s);
-  if (do_bc) apply_bcs(P, st.bc_or_not, st.bc_info, id, v, s);
+  if (do_bc) apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, v, s);
   double rnode = st.rho[id];
   if (FIRST && P.cont_density) {  // rho(1:nnode) = rho_temp/cspm_norm, main:464-465 (unconditional)
     rnode = trho / nrm;
@@ -671,27 +673,7 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   const double d4 = -(P.D41 * g11 + P.D42 * g22);
   // plastic_terms, mat:1884-1954
   double Gs[4] = {0.0, 0.0, 0.0, 0.0}, der1 = 0.0;
-  if (P.ntype_eco > 1) {
-    Stress4 s2 = sp_;
-    if (P.ntype_solid == 1) s2.s4 = P.props[3] * (s2.s1 + s2.s2);
-    double vivel[4] = {0.0, 0.0, 0.0, 0.0};
-    if (P.ncrit <= 5) {
-      von_mises_perzyna(P, s2, st.epsp[id], Gs, vivel);
-    } else if (P.ncrit == 12) {
-      double G2[4];
-      double fd = st.fdp[id];
-      drucker_prager(P, s2, g11, g12, g21, g22, fd, G2, vivel);
-      st.fdp[id] = fd;
-      Gs[0] = -G2[0];
-      Gs[1] = -G2[1];
-      Gs[2] = -G2[2];
-      Gs[3] = -G2[3];
-    }
-    if (P.ntype_solid == 0)
-      der1 = vivel[0];
-    else
-      der1 = sqrt((2.0 * (vivel[0] * vivel[0] + vivel[1] * vivel[1] + vivel[3] * vivel[3]) + vivel[2] * vivel[2]) / 3.0);
-  }
+  plastic_terms(P, sp_, g11, g12, g21, g22, st.epsp + id, st.fdp + id, Gs, der1);
   const double rke = st.RKe[ks] + der1 * f2;
   // Jaumann terms, main:751-757
   double sp1 = 0.0, sp2 = 0.0, sp3 = 0.0, sp4 = 0.0;
@@ -729,7 +711,7 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   }
   if (P.adapt) adapt_stress(P, sn);
   double2 vn = vp;
-  apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
+  apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, vn, sn);
   strec(st.SA, ks, sn.s1, sn.s2, sn.s3, sn.s4);
   st2(st.SVa, ks, vn);
   if (P.cont_density) {
@@ -976,7 +958,7 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
   }
   Stress4 sn = sp_;
   if (P.adapt) adapt_stress(P, sn);
-  apply_bcs(P, st.bc_or_not, st.bc_info, id, vn, sn);
+  apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, vn, sn);
   st2(st.NA, id, vn);
   st4(st.NSa, id, sn);
 }
@@ -1306,7 +1288,8 @@ __global__ void k_free_surface(DevParams P, SlotMap M, SortArrays S, const int *
                                const int *__restrict__ n0, const int *__restrict__ n1,
                                const GrowthRule *__restrict__ growth, const double *__restrict__ x,
                                const double *__restrict__ mass, const double *__restrict__ rho,
-                               const double *__restrict__ hsml, int *__restrict__ bc_or_not) {
+                               const double *__restrict__ hsml, int *__restrict__ bc_or_not,
+                               int *__restrict__ covered_out /* f_int = -1 marks for k_fs_normals, or null */) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= M.nnp + M.nsp) return;
   int sp, k;
@@ -1437,6 +1420,131 @@ __global__ void k_free_surface(DevParams P, SlotMap M, SortArrays S, const int *
     if (q >= P.ntotal) scan(q);
   }
   if (bc_or_not[id] != 1) bc_or_not[id] = covered ? 0 : 2;
+  if (covered_out) covered_out[id] = covered ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// XSPH_update's side effect on the BC flags, main:224-230: a velocity particle that is not on the free surface
+// (bc_or_not /= 2) and has a velocity-particle partner that is (bc_or_not == 2) is marked 3 -- a particle with
+// boundary conditions (1) thereby loses them when get_nodes_on_free_surface rewrites the flags at the end of the
+// step. The marks never create or destroy a 2, so the result does not depend on the pair order. Launched only for
+// XSPH together with boundary conditions, right before the per-step k_free_surface.
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_xsph_marks(DevParams P, SlotMap M, SortArrays S, ListPtrs L, const int *__restrict__ n1,
+                             int *bc_or_not) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M.nn) return;
+  const int id = S.order[SP_NODE][t];
+  if (S.cell[SP_NODE][t] < 0) return;  // out of the domain: no pairs
+  if (bc_or_not[id] == 2) return;
+  const int cnt1 = n1[t];
+  const size_t o1 = (size_t)L.offC[t / SLICE] + (t & 31);
+  for (int e = 0; e < cnt1; ++e) {
+    const int q = L.idxC[o1 + (size_t)e * SLICE];
+    if (bc_or_not[q] == 2) {
+      bc_or_not[id] = 3;
+      return;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// get_nodes_on_free_surface step 4, mat:1340-1411 (ifsigman = 1 only): the normal of every marked velocity particle
+// from the chords to its marked partners (pair types 1 and 3; fp32 coordinates, fp64 sums in traversal order),
+// normalised and oriented against grad(f_int) (fp32 sums in traversal order; f_int = -1 on the particles that step 3
+// found covered). Runs after k_free_surface of the same step: bc_or_not == 2 <=> subset == 1. A particle without a
+// marked partner gets 0/0 = NaN, which apply_stress_free skips (mat:1791).
+// Deviation: x**0.5 -> correctly rounded sqrt, as in k_free_surface.
+// ------------------------------------------------------------------------------------------------------
+__global__ void k_fs_normals(DevParams P, SlotMap M, SortArrays S, const int *__restrict__ pos_of, ListPtrs L,
+                             const int *__restrict__ n0, const int *__restrict__ n1,
+                             const GrowthRule *__restrict__ growth, const double *__restrict__ x,
+                             const double *__restrict__ mass, const double *__restrict__ rho,
+                             const int *__restrict__ bc_or_not, const int *__restrict__ covered,
+                             double *__restrict__ fs_normal) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= M.nn) return;
+  const int id = S.order[SP_NODE][t];
+  const int c = S.cell[SP_NODE][t];
+  if (bc_or_not[id] != 2) {
+    st2(fs_normal, id, make_double2(0.0, 0.0));
+    return;
+  }
+  const int cnt0 = c < 0 ? 0 : n0[t], cnt1 = c < 0 ? 0 : n1[t];  // out of the domain: no pairs -> 0/0
+  const int lane = t & 31, sl = t / SLICE;
+  const size_t o0 = (size_t)L.off0[sl] + lane;
+  const size_t o1 = (size_t)L.offC[sl] + lane;
+  const GrowthRule gr = *growth;
+  const okey_t kp = make_key(c < 0 ? 0 : c, SP_NODE, id);
+  const double2 xp = ld2(x, id);
+  const float xpf = (float)xp.x, ypf = (float)xp.y;
+  const float fp = covered[id] ? -1.f : 0.f;
+  auto species = [&](int q) { return q < P.nnode ? SP_NODE : (q < P.ntotal ? SP_STRESS : SP_DUMMY); };
+  auto key_of = [&](int q) {
+    const int sq = species(q);
+    return make_key(S.cell[sq][pos_of[q]], sq, q);
+  };
+  auto before = [&](okey_t ka, okey_t kb) {  // traversal precedence, as in k_free_surface
+    const bool oa = pair_is_old(gr, kp, ka), ob = pair_is_old(gr, kp, kb);
+    if (oa != ob) return !oa;
+    return oa ? ka < kb : ka > kb;
+  };
+  double nx = 0.0, ny = 0.0;
+  float neighbour = 0.f, gf1 = 0.f, gf2 = 0.f;
+  // q: partner; gx, gy: kernel gradient from this particle's perspective; first: this particle is pair_i
+  auto visit = [&](int q, float gx, float gy, bool first) {
+    const double2 xq = ld2(x, q);
+    if (bc_or_not[q] == 2) {
+      const float xqf = (float)xq.x, yqf = (float)xq.y;
+      const float x_vect = first ? (xqf - xpf) : (xpf - xqf);
+      const float y_vect = first ? (yqf - ypf) : (ypf - yqf);
+      nx = nx - (double)y_vect;
+      ny = ny + (double)x_vect;
+      neighbour = neighbour + 1.f;
+    }
+    const double mq = mass[q], rq = rho[q];
+    const float h1 = (float)(mq * (double)gx / rq), h2 = (float)(mq * (double)gy / rq);
+    const float fq = covered[q] ? -1.f : 0.f;
+    gf1 = gf1 + (fq - fp) * h1;
+    gf2 = gf2 + (fq - fp) * h2;
+  };
+  int e0 = 0, e1 = 0;
+  auto skip_walls = [&]() {
+    while (e0 < cnt0 && (L.idx0[o0 + (size_t)e0 * SLICE] & QID_MASK) >= P.ntotal) ++e0;
+  };
+  skip_walls();
+  while (e0 < cnt0 || e1 < cnt1) {
+    bool take0;
+    if (e0 >= cnt0)
+      take0 = false;
+    else if (e1 >= cnt1)
+      take0 = true;
+    else
+      take0 = before(key_of(L.idx0[o0 + (size_t)e0 * SLICE] & QID_MASK), key_of(L.idxC[o1 + (size_t)e1 * SLICE]));
+    if (take0) {
+      const size_t a = o0 + (size_t)e0 * SLICE;
+      // type 1: pair_i is the stress particle, the stored gradient is in its orientation
+      visit(L.idx0[a] & QID_MASK, -L.gx0[a], -L.gy0[a], false);
+      ++e0;
+      skip_walls();
+    } else {
+      const size_t a = o1 + (size_t)e1 * SLICE;
+      const int q = L.idxC[a];
+      visit(q, L.gxC[a], L.gyC[a], kp < key_of(q));  // type 3: pair_i is the creator, the smaller (cell, id) key
+      ++e1;
+    }
+  }
+  nx = nx / (double)neighbour;
+  ny = ny / (double)neighbour;
+  const float norm_vect = (float)sqrt(nx * nx + ny * ny);
+  nx = nx / (double)norm_vect;
+  ny = ny / (double)norm_vect;
+  const float p_scal = (float)((double)gf1 * nx + (double)gf2 * ny);
+  if (p_scal < 0) {
+    nx = -nx;
+    ny = -ny;
+  }
+  st2(fs_normal, id, make_double2(nx, ny));
 }
 
 __global__ void k_pair_stats(SlotMap M, const int *__restrict__ nall, int *__restrict__ out /* max,min,zero */) {

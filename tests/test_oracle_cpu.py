@@ -277,3 +277,118 @@ def test_fortran_shim_matches_header():
     assert c_members("spsph_state") == f_members("spsph_state")
     for name in set(re.findall(r"\b(spsph_[a-z_]+)\s*\(", hdr)):
         assert 'name="%s"' % name in f90, name
+
+
+def _devmath(tmp_path):
+    """the per-particle device functions of csrc/dev_common.cuh compiled for the host (tests/native/dev_math_host.cpp)"""
+    import ctypes as C
+    import subprocess
+    so = str(tmp_path / "devmath.so")
+    r = subprocess.run(["g++", "-O2", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared", "-w",
+                        "-D__noinline__=", "-I/usr/local/cuda/include",
+                        "-I" + os.path.join(ROOT, "stress-particle-sph_b200", "csrc"), "-I" + os.path.join(ROOT, "include"),
+                        "-o", so, os.path.join(ROOT, "tests", "native", "dev_math_host.cpp")], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return C.CDLL(so)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(__import__("ctypes").c_void_p)
+
+
+@pytest.mark.parametrize("ncrit,frict,nflow,delta", [(1, 0., 1, 1.), (2, 0., 1, 1.), (3, 20., 1, 1.), (4, 20., 1, 1.),
+                                                     (3, 35., 2, 1.5), (1, 0., 1, 1.5), (12, 0., 1, 1.)])
+def test_device_math_transcription_plastic_terms(ncrit, frict, nflow, delta, tmp_path):
+    """plastic_terms of csrc/dev_common.cuh (Perzyna with the four yield criteria of invar09, Drucker-Prager of Bui
+    et al.) == the oracle's restatement, bit for bit, on 200 000 random stress states around the yield surface
+    (host build of the device source: same libm on both sides)"""
+    import ctypes as C
+    import spsph
+    from spsph import decks
+    from oracle_binding import Oracle, lib
+    if ncrit == 12:
+        spec, variant = decks.bui_spec(dx=0.01), "bui"
+    else:
+        spec, variant = decks.strain_localisation_spec(dx=0.002), "sl"
+        spec["props"] = [2, ncrit, 8.e07, 0.25, 1., 2.e3, 1.5e5, -8.e06, frict, 50., delta, nflow]
+    decks.write_deck(str(tmp_path), spec)
+    prob = spsph.load(str(tmp_path), variant)
+    orc = Oracle(prob)
+    n = 200000
+    assert prob.params.ntotal >= n
+    rng = np.random.default_rng(ncrit * 100 + int(frict))
+    scale = 1.5e5 if ncrit != 12 else 2.0e4
+    stress = rng.normal(0.0, scale, (n, 4))
+    stress[: n // 10] *= 1e-3                       # nearly stress-free
+    stress[n // 10: n // 5, 2] = 0.0                # principal axes aligned with x, y
+    k = slice(n // 5, n // 4)                       # axisymmetric states: Lode angle at +-30 degrees (sint3 = +-1)
+    stress[k, 2] = 0.0
+    stress[k, 3] = stress[k, 1]
+    stress[n // 4: n // 4 + 100] = 0.0              # exactly zero stress
+    grad = rng.normal(0.0, 1.0, (n, 4))
+    epsp = np.abs(rng.normal(0.0, 5e-3, n))
+    epsp[::3] = 0.0
+    props = np.array(list(prob.params.props), dtype=np.float64)
+    for time_sph in (0.0, 1.0e-3):
+        fd_o = rng.normal(0.0, 1.0e4, n)
+        fd_d = fd_o.copy()
+        Gs_o, Gs_d = np.zeros((n, 4)), np.zeros((n, 4))
+        d_o, d_d = np.zeros(n), np.zeros(n)
+        rc = lib().oracle_plastic_terms(C.c_void_p(orc.h), C.c_double(time_sph), C.c_int32(n), _ptr(stress), _ptr(grad),
+                                        _ptr(epsp), _ptr(fd_o), _ptr(Gs_o), _ptr(d_o))
+        assert rc == 0
+        _devmath(tmp_path).devmath_plastic_terms(
+            C.c_int(ncrit), C.c_int(prob.params.ntype_eco), C.c_int(prob.params.ntype_solid), C.c_double(time_sph),
+            _ptr(props), C.c_int(n), _ptr(stress), _ptr(grad), _ptr(epsp), _ptr(fd_d), _ptr(Gs_d), _ptr(d_d))
+        assert np.array_equal(Gs_o, Gs_d, equal_nan=True)
+        assert np.array_equal(d_o, d_d, equal_nan=True)
+        assert np.array_equal(fd_o, fd_d)
+        if time_sph > 0:
+            assert (Gs_o != 0).any(axis=1).mean() > 0.2  # the plastic branch is exercised
+
+
+def test_device_math_transcription_adapt_stress_free_kernel(tmp_path):
+    """adapt_stress2, apply_stress_free and the three smoothing kernels of csrc/dev_common.cuh == the oracle's, bit for
+    bit, on random inputs (host build of the device source)"""
+    import ctypes as C
+    import spsph
+    from spsph import decks
+    from oracle_binding import Oracle, lib
+    decks.write_deck(str(tmp_path), decks.bui_spec(dx=0.02))
+    prob = spsph.load(str(tmp_path), "bui")
+    orc = Oracle(prob)
+    dm = _devmath(tmp_path)
+    n = min(prob.params.nnode, 20000)
+    rng = np.random.default_rng(7)
+    props = np.array(list(prob.params.props), dtype=np.float64)
+    stress = rng.normal(0.0, 2.0e4, (n, 4))
+    stress[: n // 4] += 3.0e4  # tension: apex cut-off branch
+    a, b = stress.copy(), stress.copy()
+    assert lib().oracle_adapt_stress(C.c_void_p(orc.h), C.c_int32(n), _ptr(a)) == 0
+    dm.devmath_adapt_stress(_ptr(props), C.c_int(n), _ptr(b))
+    assert np.array_equal(a, b) and not np.array_equal(a, stress)
+    th = rng.uniform(0, 2 * np.pi, n)
+    normal = np.column_stack([np.cos(th), np.sin(th)])
+    a, b = stress.copy(), stress.copy()
+    assert lib().oracle_stress_free(C.c_void_p(orc.h), C.c_int32(n), _ptr(a), _ptr(normal)) == 0
+    dm.devmath_stress_free(C.c_int(n), _ptr(b), _ptr(normal))
+    assert np.array_equal(a, b) and not np.array_equal(a, stress)
+    h = np.full(n, 1.2 * 0.02) * rng.uniform(0.9, 1.1, n)
+    r = rng.uniform(0.0, 3.2, n) * h
+    ang = rng.uniform(0, 2 * np.pi, n)
+    dx, dy = r * np.cos(ang), r * np.sin(ang)
+    lib().oracle_kernel.restype = None
+    for skf in (1, 2, 3):
+        orc.p.skf = skf
+        o2 = Oracle.__new__(Oracle)
+        o2.p = orc.p
+        st = prob.state()
+        o2.h = lib().oracle_create(C.byref(o2.p), C.byref(st))
+        wo, gxo, gyo = np.zeros(n), np.zeros(n), np.zeros(n)
+        wd, gxd, gyd = np.zeros(n), np.zeros(n), np.zeros(n)
+        lib().oracle_kernel(C.c_void_p(o2.h), C.c_int32(n), _ptr(r), _ptr(dx), _ptr(dy), _ptr(h), _ptr(wo), _ptr(gxo), _ptr(gyo))
+        dm.devmath_kernel(C.c_int(skf), C.c_double(prob.params.pi), C.c_int(n), _ptr(r), _ptr(dx), _ptr(dy), _ptr(h),
+                          _ptr(wd), _ptr(gxd), _ptr(gyd))
+        assert np.array_equal(wo, wd) and np.array_equal(gxo, gxd) and np.array_equal(gyo, gyd), skf
+        assert (wo != 0).mean() > 0.5
+        o2.close()
