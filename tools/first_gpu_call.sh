@@ -1,0 +1,25 @@
+#!/bin/bash
+# First GPU call of a round: everything that has to be confirmed on hardware before more is built on it.
+#   gpurun --timeout 2400 -- 'bash tools/first_gpu_call.sh'
+# 1. the device paths whose first hardware run is still pending (tests/test_zz_gpu_new_paths.py), one pytest
+#    process per case so that a crash in one cannot hide the others;
+# 2. the verified GPU suite (-x as the round driver runs it);
+# 3. the default bench line and the reference arm;
+# 4. the ncu launch list of one step (shares per kernel).
+# Everything lands in gpurun_out/first/.
+out=gpurun_out/first
+mkdir -p $out
+python __graft_entry__.py > $out/build.log 2>&1
+for c in sl_dp_perzyna sl_tresca sl_mohr_coulomb sl_vm_expflow sl_vm_powflow sl_xsph sl_sigman vs_sigman sl_sigman_xsph; do
+  timeout 600 python -m pytest tests/test_zz_gpu_new_paths.py -q -x -k "$c]" > $out/new_$c.log 2>&1
+  echo "$c: exit $?" | tee -a $out/new_paths_summary.txt
+done
+timeout 3000 python -m pytest tests -m gpu -x -q --deselect tests/test_zz_gpu_new_paths.py > $out/gpu_suite.log 2>&1
+echo "gpu suite: exit $?" | tee -a $out/new_paths_summary.txt
+tail -3 $out/gpu_suite.log
+timeout 900 python bench.py > $out/bench.json 2> $out/bench.err
+tail -c 1500 $out/bench.json
+timeout 900 python bench.py --impl reference --steps 10 --warmup 1 > $out/bench_reference.json 2> $out/bench_reference.err
+ncu --metrics gpu__time_duration.sum --clock-control none -s 49 -c 60 --csv --log-file $out/launches.csv \
+    python tools/run_steps.py --steps 2 > $out/launch_run.log 2>&1
+cat $out/new_paths_summary.txt
