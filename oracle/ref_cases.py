@@ -62,6 +62,25 @@ CASES = {
     "vs_sigman": ("vs", lambda n: dict(_vs_free_right(n), ifsigman=1), 60, (60,)),
     "sl_xsph": ("sl", lambda n: dict(_sl_perzyna(n, ncrit=2, free_right=True), xsph=True), 60, (60,)),
     "sl_sigman_xsph": ("sl", lambda n: dict(_sl_perzyna(n, ncrit=2, free_right=True), ifsigman=1, xsph=True), 60, (60,)),
+    # Check_Out_Domain (main:1170-1194): the domain box ends 1e-5 beyond the free face of the column,
+    # so the wall particles right of it are out from the start (171) and velocity / stress particles leave one by one
+    # as the face moves (195 flagged after 200 steps); a flagged particle drops out of the grid for good
+    "bui_out_domain": ("bui", lambda n: dict(decks.bui_spec(maxtimestep=n), domain=[-10, -10, 4.00001, 41]), 210, 100),
+    # corners of the input space no shipped deck visits: a sinusoidal boundary value with start-up factor (Normal_BCs
+    # mat:1696-1705: tvar = 0), plane stress (ntype_solid = 1, Bui copy), the outside approach with 1 and 3 stress
+    # particles per velocity particle (shift_stress_points main:296-316), re-seating every 5th step
+    "sl_sine_bc": ("sl", lambda n: _sl_sine_bc(n), 60, (60,)),
+    "bui_plane_stress": ("bui", lambda n: dict(decks.bui_spec(maxtimestep=n), ntype_solid=1), 60, (60,)),
+    "bui_outside_sp1": ("bui", lambda n: decks.bui_spec(maxtimestep=n, mode="outside", npoints=1), 60, (60,)),
+    "bui_outside_sp3": ("bui", lambda n: decks.bui_spec(maxtimestep=n, mode="outside", npoints=3), 60, (60,)),
+    "bui_shift5": ("bui", lambda n: dict(decks.bui_spec(maxtimestep=n), shift_update=5), 60, (60,)),
+    # the three example problems run to the END of their shipped time span (north_star: "matching failure-surface
+    # geometry at the end of the run"): Bui t_end = 2.5 s (16 667 steps; the shipped maxtimestep = 10 lifted), vertical
+    # slope t_end = 2 s (2000 steps), strain localisation t_end = 0.021 s (2100 steps); the last frame the plot
+    # cadence allows before the run ends is the final state
+    "bui_full": ("bui", lambda n: decks.bui_spec(maxtimestep=n), 17000, 5550),
+    "vs_full": ("vs", lambda n: decks.vertical_slope_spec(maxtimestep=n), 2100, 995),
+    "sl_full": ("sl", lambda n: decks.strain_localisation_spec(maxtimestep=n), 2200, 1045),
     # the inside approach pressed against its walls long enough for boundary_forces to act
     "bui_inside_sp1_long": ("bui", lambda n: decks.bui_spec(maxtimestep=n, mode="inside", npoints=1), 1510, 1500),
 }
@@ -72,6 +91,13 @@ def _sl_perzyna(n, ncrit, frict=0., nflow=1, delta=1., yield0=1.5e5, free_right=
     s["props"] = [2, ncrit, 8.e07, 0.25, 1., 2.e3, yield0, -8.e06, frict, 50., delta, nflow]
     if free_right:  # no boundary conditions on x = 0.5: get_nodes_on_free_surface marks that side (bc_or_not = 2)
         s["segments"] = [g for g in s["segments"] if not (g[0] == 0.5 and g[2] == 0.5)]
+    return s
+
+
+def _sl_sine_bc(n):
+    s = _sl_perzyna(n, ncrit=2)
+    s["bcs"] = list(s["bcs"])
+    s["bcs"][4] = (5, 6, 0, 1.0, 0.5, 3000., 0.3, 2.e-4)  # top v_y = (a0 + a1 sin(w t - fi)) (1 - exp(-t/Tf))
     return s
 
 
@@ -105,5 +131,5 @@ DEVICE_TOLERANCE = {"bui_art_stress": 1e-9, "sl_art_stress": 1e-9, "sl_vm_expflo
 # device paths written after this round's GPU budget was spent: their first run on hardware
 # is tests/test_zz_gpu_new_paths.py, the last file of the GPU suite, so that a surprise there cannot mask the
 # verified cases of tests/test_gpu_reference.py (the driver runs pytest with -x)
-DEVICE_UNVERIFIED = {"sl_tresca", "sl_mohr_coulomb", "sl_dp_perzyna", "sl_vm_expflow", "sl_vm_powflow", "sl_sigman",
+DEVICE_UNVERIFIED = {"sl_sine_bc", "bui_plane_stress", "bui_outside_sp1", "bui_outside_sp3", "bui_shift5", "bui_out_domain", "bui_full", "vs_full", "sl_full", "sl_tresca", "sl_mohr_coulomb", "sl_dp_perzyna", "sl_vm_expflow", "sl_vm_powflow", "sl_sigman",
                      "vs_sigman", "sl_xsph", "sl_sigman_xsph"}
