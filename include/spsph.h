@@ -133,6 +133,12 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
 int spsph_dist_flags(spsph_handle *h, int32_t *flags);
 /* particles per species (velocity, stress, wall) this rank processed in the last step: its slab + halo */
 int spsph_local_counts(spsph_handle *h, int32_t *nloc3);
+/* checkpoint support (the reference has none: SURVEY section 5). Everything a restart needs is in spsph_state except
+ * the length the reference's pair list has grown to (grid_find_NEW never shrinks it, main:1210,1361-1383); it decides
+ * in which order the next steps walk their pairs. spsph_upload resets it to 0 (a fresh run);
+ * restoring the value read at the checkpoint makes the restarted run continue bit for bit. */
+int spsph_get_list_capacity(spsph_handle *h, int64_t *m_pairs);
+int spsph_set_list_capacity(spsph_handle *h, int64_t m_pairs);
 int spsph_sync(spsph_handle *h);
 int spsph_destroy(spsph_handle *h);
 const char *spsph_last_error(spsph_handle *h);

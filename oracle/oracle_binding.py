@@ -33,6 +33,10 @@ def lib():
         L.oracle_last_error.restype = C.c_char_p
         L.oracle_last_error.argtypes = [C.c_void_p]
         L.oracle_destroy.argtypes = [C.c_void_p]
+        L.oracle_get_list_capacity.restype = C.c_int64
+        L.oracle_get_list_capacity.argtypes = [C.c_void_p]
+        L.oracle_set_list_capacity.restype = None
+        L.oracle_set_list_capacity.argtypes = [C.c_void_p, C.c_int64]
         _lib = L
     return _lib
 
@@ -75,6 +79,12 @@ class Oracle:
         lib().oracle_pairs(self.h, C.byref(n), *[out[f].ctypes.data for f in
                                                  ("pair_i", "pair_j", "pint_type", "w", "dwdx", "dwdy")])
         return out
+
+    def list_capacity(self):
+        return lib().oracle_get_list_capacity(self.h)
+
+    def set_list_capacity(self, m):
+        lib().oracle_set_list_capacity(self.h, int(m))
 
     def close(self):
         if self.h:

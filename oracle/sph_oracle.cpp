@@ -1458,6 +1458,10 @@ void oracle_kernel(void *h, int32_t n, const double *r, const double *dx, const 
   }
 }
 
+// list-capacity history (m_pairs), the one piece of a checkpoint that is not in spsph_state
+int64_t oracle_get_list_capacity(void *h) { return ((Oracle *)h)->m_pairs; }
+void oracle_set_list_capacity(void *h, int64_t m) { ((Oracle *)h)->m_pairs = m; }
+
 const char *oracle_last_error(void *h) { return ((Oracle *)h)->err.c_str(); }
 
 void oracle_destroy(void *h) { delete (Oracle *)h; }

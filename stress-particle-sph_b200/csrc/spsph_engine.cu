@@ -1179,6 +1179,22 @@ int spsph_profile_get(spsph_handle *h, int kid, const char **name, double *total
   return 0;
 }
 
+int spsph_get_list_capacity(spsph_handle *h, int64_t *m_pairs) {
+  if (!h || !m_pairs) return 1;
+  *m_pairs = (int64_t)h->m_pairs;
+  return 0;
+}
+
+int spsph_set_list_capacity(spsph_handle *h, int64_t m_pairs) {
+  if (!h) return 1;
+  if (!h->uploaded || m_pairs < 0) {
+    h->err = "spsph_set_list_capacity: call it after spsph_upload, with a non-negative length";
+    return 1;
+  }
+  h->m_pairs = (long long)m_pairs;
+  return 0;
+}
+
 int spsph_sync(spsph_handle *h) {
   if (!h) return 1;
   CUDA_TRY(cudaSetDevice(h->device));

@@ -135,6 +135,16 @@ module spsph_c_api
        type(c_ptr), value :: h
        integer(c_int32_t), intent(out) :: nloc3(3)
      end function
+     integer(c_int) function spsph_get_list_capacity(h, m_pairs) bind(C, name="spsph_get_list_capacity")
+       import :: c_ptr, c_int, c_int64_t
+       type(c_ptr), value :: h
+       integer(c_int64_t), intent(out) :: m_pairs
+     end function
+     integer(c_int) function spsph_set_list_capacity(h, m_pairs) bind(C, name="spsph_set_list_capacity")
+       import :: c_ptr, c_int, c_int64_t
+       type(c_ptr), value :: h
+       integer(c_int64_t), value :: m_pairs
+     end function
      integer(c_int) function spsph_sync(h) bind(C, name="spsph_sync")
        import :: c_ptr, c_int
        type(c_ptr), value :: h

@@ -33,6 +33,8 @@ def cuda_lib():
         L.spsph_pairs.argtypes = [H, C.POINTER(C.c_int64)] + [C.c_void_p] * 6
         L.spsph_last_run_ms.argtypes = [H, C.POINTER(C.c_float), C.POINTER(C.c_int64)]
         L.spsph_sync.argtypes = [H]
+        L.spsph_get_list_capacity.argtypes = [H, C.POINTER(C.c_int64)]
+        L.spsph_set_list_capacity.argtypes = [H, C.c_int64]
         L.spsph_dist_unique_id.argtypes = [C.c_char_p]
         L.spsph_dist_init.argtypes = [H, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_double), C.c_int32, C.c_int32]
         L.spsph_dist_flags.argtypes = [H, C.c_void_p]
@@ -49,7 +51,8 @@ def cuda_lib():
 
 EXPORTS = ["spsph_create", "spsph_upload", "spsph_step", "spsph_run", "spsph_download", "spsph_pair_stats",
            "spsph_pairs", "spsph_last_run_ms", "spsph_sync", "spsph_profile", "spsph_profile_get",
-           "spsph_dist_unique_id", "spsph_dist_init", "spsph_dist_flags", "spsph_local_counts", "spsph_destroy", "spsph_last_error", "spsph_version"]
+           "spsph_dist_unique_id", "spsph_dist_init", "spsph_dist_flags", "spsph_local_counts", "spsph_get_list_capacity",
+           "spsph_set_list_capacity", "spsph_destroy", "spsph_last_error", "spsph_version"]
 
 
 def dist_unique_id():
@@ -130,6 +133,15 @@ class Engine:
 
     def sync(self):
         self._chk(self.L.spsph_sync(self.h))
+
+    def list_capacity(self):
+        """length the reference's pair list has grown to (part of a checkpoint, see checkpoint.py)"""
+        n = C.c_int64()
+        self._chk(self.L.spsph_get_list_capacity(self.h, C.byref(n)))
+        return n.value
+
+    def set_list_capacity(self, m_pairs):
+        self._chk(self.L.spsph_set_list_capacity(self.h, int(m_pairs)))
 
     def download(self, arrays=None):
         if arrays is None:

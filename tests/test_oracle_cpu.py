@@ -392,3 +392,32 @@ def test_device_math_transcription_adapt_stress_free_kernel(tmp_path):
         assert np.array_equal(wo, wd) and np.array_equal(gxo, gxd) and np.array_equal(gyo, gyd), skf
         assert (wo != 0).mean() > 0.5
         o2.close()
+
+
+def test_restart_needs_the_list_capacity(tmp_path):
+    """the concept behind spsph.checkpoint (state arrays + list capacity), checked on the oracle: a Bui run restarted at
+    step 330 -- after the pair list has grown (step 301) and before it grows again -- continues bit for bit when
+    m_pairs is restored, and does not when it is left at 0 (the first restarted step would walk its list reversed)"""
+    import spsph
+    from spsph import checkpoint, decks
+    from oracle_binding import Oracle
+    decks.write_deck(str(tmp_path), decks.bui_spec(maxtimestep=1000))
+    prob = spsph.load(str(tmp_path), "bui")
+    dt = prob.blocks[0]["dt"]
+    a = Oracle(prob)
+    t_mid = a.run(1, 0.0, dt, 330)
+    mid, cap = a.download(), a.list_capacity()
+    assert cap > 0
+    a.run(331, t_mid, dt, 60)
+    ref = a.download()
+    for restore in (True, False):
+        p2 = prob.copy()
+        for k in checkpoint.DYNAMIC:  # the set-up arrays stay those of the deck reader
+            p2.arrays[k] = mid[k]
+        b = Oracle(p2)
+        if restore:
+            b.set_list_capacity(cap)
+        b.run(331, t_mid, dt, 60)
+        got = b.download()
+        same = all(np.array_equal(ref[k], got[k]) for k in ("x", "vel", "stress", "internal_vars", "f_drucker"))
+        assert same == restore
