@@ -73,6 +73,8 @@ CASES = {
     "bui_plane_stress": ("bui", lambda n: dict(decks.bui_spec(maxtimestep=n), ntype_solid=1), 60, (60,)),
     "bui_outside_sp1": ("bui", lambda n: decks.bui_spec(maxtimestep=n, mode="outside", npoints=1), 60, (60,)),
     "bui_outside_sp3": ("bui", lambda n: decks.bui_spec(maxtimestep=n, mode="outside", npoints=3), 60, (60,)),
+    # a wider kernel support (sml = 1.5 instead of 1.2: up to 88 partners per particle instead of 56)
+    "bui_sml15": ("bui", lambda n: dict(decks.bui_spec(maxtimestep=n), sml=1.5), 40, (40,)),
     "bui_shift5": ("bui", lambda n: dict(decks.bui_spec(maxtimestep=n), shift_update=5), 60, (60,)),
     # the three example problems run to the END of their shipped time span (north_star: "matching failure-surface
     # geometry at the end of the run"): Bui t_end = 2.5 s (16 667 steps; the shipped maxtimestep = 10 lifted), vertical
@@ -131,5 +133,5 @@ DEVICE_TOLERANCE = {"bui_art_stress": 1e-9, "sl_art_stress": 1e-9, "sl_vm_expflo
 # device paths written after this round's GPU budget was spent: their first run on hardware
 # is tests/test_zz_gpu_new_paths.py, the last file of the GPU suite, so that a surprise there cannot mask the
 # verified cases of tests/test_gpu_reference.py (the driver runs pytest with -x)
-DEVICE_UNVERIFIED = {"sl_sine_bc", "bui_plane_stress", "bui_outside_sp1", "bui_outside_sp3", "bui_shift5", "bui_out_domain", "bui_full", "vs_full", "sl_full", "sl_tresca", "sl_mohr_coulomb", "sl_dp_perzyna", "sl_vm_expflow", "sl_vm_powflow", "sl_sigman",
+DEVICE_UNVERIFIED = {"bui_sml15", "sl_sine_bc", "bui_plane_stress", "bui_outside_sp1", "bui_outside_sp3", "bui_shift5", "bui_out_domain", "bui_full", "vs_full", "sl_full", "sl_tresca", "sl_mohr_coulomb", "sl_dp_perzyna", "sl_vm_expflow", "sl_vm_powflow", "sl_sigman",
                      "vs_sigman", "sl_xsph", "sl_sigman_xsph"}

@@ -73,7 +73,7 @@ def test_goldens_cover_every_shipped_input_set():
     shipped = [c for c in CASES if not c.endswith("_long") and c.split("_", 1)[-1] not in (
         "refined", "wide", "gauss", "quintic", "art_stress", "cont_density", "cont_density_sle2", "tresca",
         "mohr_coulomb", "dp_perzyna", "vm_expflow", "vm_powflow", "sigman", "xsph", "sigman_xsph", "full", "out_domain", "sine_bc", "plane_stress", "outside_sp1",
-        "outside_sp3", "shift5")]
+        "outside_sp3", "shift5", "sml15")]
     assert len(shipped) == 14, shipped
     for c in CASES:
         assert os.path.exists(golden_path(c)), c
