@@ -2,7 +2,7 @@
 # First GPU call of a round: everything that has to be confirmed on hardware before more is built on it.
 #   gpurun --timeout 2400 -- 'bash tools/first_gpu_call.sh'
 # 1. the device paths whose first hardware run is still pending (tests/test_zz_gpu_new_paths.py), one pytest
-#    process per case so that a crash in one cannot hide the others;
+#    process per test id so that a crash in one cannot hide the others;
 # 2. the verified GPU suite (-x as the round driver runs it);
 # 3. the default bench line and the reference arm;
 # 4. the ncu launch list of one step (shares per kernel).
@@ -10,10 +10,12 @@
 out=gpurun_out/first
 mkdir -p $out
 python __graft_entry__.py > $out/build.log 2>&1
-for c in sl_dp_perzyna sl_tresca sl_mohr_coulomb sl_vm_expflow sl_vm_powflow sl_xsph sl_sigman vs_sigman sl_sigman_xsph; do
-  timeout 600 python -m pytest tests/test_zz_gpu_new_paths.py -q -x -k "$c]" > $out/new_$c.log 2>&1
-  echo "$c: exit $?" | tee -a $out/new_paths_summary.txt
-done
+python -m pytest tests/test_zz_gpu_new_paths.py --collect-only -q 2>/dev/null | grep "::" > $out/new_ids.txt
+while read -r id; do
+  name=$(echo "$id" | sed 's/.*:://; s/[^A-Za-z0-9_]/_/g')
+  timeout 900 python -m pytest "$id" -q -x > $out/new_$name.log 2>&1
+  echo "$id: exit $?" | tee -a $out/new_paths_summary.txt
+done < $out/new_ids.txt
 timeout 3000 python -m pytest tests -m gpu -x -q --deselect tests/test_zz_gpu_new_paths.py > $out/gpu_suite.log 2>&1
 echo "gpu suite: exit $?" | tee -a $out/new_paths_summary.txt
 tail -3 $out/gpu_suite.log
