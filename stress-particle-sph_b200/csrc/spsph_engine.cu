@@ -78,6 +78,10 @@ struct spsph_handle {
   bool fs_each_step = false;
   int *fs_cov = nullptr;        // (ntotal) covered in step 3 (f_int = -1)
   double *fs_normal = nullptr;  // (2, nnode) step-4 normals
+  // outside approach: positions between the position update and shift_stress_points, where the reference runs
+  // get_nodes_on_free_surface (main:152-160); the on-demand evaluation at download classifies on this snapshot
+  double *x_fs = nullptr;       // (2, ntotal2), single GPU only
+  bool x_fs_valid = false;
   int cur = 0;
   double *ivars = nullptr;  // device mirror of Internal_Vars(10, ntotal): rows 2..10 never change on the hot path
   std::vector<int32_t> h_itype;
@@ -810,6 +814,10 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     k_sp_follow<<<list_grid(h, P.nnode, 256), 256, 0, s>>>(P, h->x, local_list(h, P.nnode));
     mark(h, KID_SHIFT);
   }
+  if (h->x_fs && !h->dist) {
+    CUDA_TRY(cudaMemcpyAsync(h->x_fs, h->x, 2 * (size_t)P.ntotal2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    h->x_fs_valid = true;
+  }
   if (p.update_x && p.sp_sph && !p.inside_approach) {
     k_shift<<<list_grid(h, P.nnode, 256), 256, 0, s>>>(P, st.NB, h->x, h->x_10, h->disp_10, h->bc_int, h->n_int,
                                                        local_list(h, P.nnode));
@@ -984,6 +992,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   rc |= dalloc(h, &h->wallpos, n2) | dalloc(h, &h->horiz, n2) | dalloc(h, &h->n_int, nn);
   rc |= dalloc(h, &h->bc_int, nn) | dalloc(h, &h->bc_or_not, nt) | dalloc(h, &h->bc_info, 8 * nt);
   if (h->fs_each_step) rc |= dalloc(h, &h->fs_cov, nt) | dalloc(h, &h->fs_normal, 2 * nn);
+  if (p->update_x && p->sp_sph && !p->inside_approach && !h->fs_each_step) rc |= dalloc(h, &h->x_fs, 2 * n2);
   rc |= dalloc(h, &h->if_out, n2);
   rc |= dalloc(h, &h->G, 1);
   h->bbox_blocks = 148 * 8;
@@ -1120,6 +1129,7 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   }
   h->m_pairs = 0;
   h->have_lists = false;
+  h->x_fs_valid = false;
   h->uploaded = true;
   if (h->dist) {  // a fresh upload holds complete data on every rank: re-derive owned / ghost / remote
     k_dist_init_flags<<<((int)n2 + 255) / 256, 256, 0, st>>>(h->P, h->D, h->x, h->lflag);
@@ -1238,7 +1248,8 @@ int spsph_download(spsph_handle *h, const spsph_state *s) {
     ML.nd = h->nloc[2];
     const int T = ML.nnp + ML.nsp;
     k_free_surface<<<(T + 127) / 128, 128, 0, st>>>(h->P, ML, sort_arrays(h), h->pos_of, h->L, h->n0, h->n1, h->growth,
-                                                    h->x, h->mass, h->rho, h->hsml, h->bc_or_not, nullptr);
+                                                    h->x_fs_valid ? h->x_fs : h->x, h->mass, h->rho, h->hsml,
+                                                    h->bc_or_not, nullptr);
     CUDA_TRY(cudaGetLastError());
   }
   CUDA_TRY(down(s->f_drucker, h->fdp, nt * 8));
