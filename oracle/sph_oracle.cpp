@@ -58,6 +58,7 @@ struct Oracle {
   std::vector<float> wall_position, horizontal_or_not, n_int;
   // pair list: `created` in creation order; traversal order through order_of()
   std::vector<Pair> created;
+  std::vector<int32_t> last_cell;  // which_cell of the last grid_find (1-based reference cell id, 0: out of the domain)
   int64_t m_pairs = 0;       // list capacity = max pair count of all previous steps (main:1210)
   int64_t m_before = 0;      // m_pairs at the start of the current step
   double time_sph = 0, dt_sph = 0;
@@ -177,6 +178,7 @@ struct Oracle {
     }
     m_before = m_pairs;
     created.clear();
+    last_cell = which_cell;
     for (int idy = 1; idy <= ndivx[1]; ++idy)
       for (int idx = 1; idx <= ndivx[0]; ++idx) {
         const int idivt = ndivx[0] * (idy - 1) + idx;
@@ -1456,6 +1458,19 @@ void oracle_kernel(void *h, int32_t n, const double *r, const double *dx, const 
     gx[i] = g[0];
     gy[i] = g[1];
   }
+}
+
+// internals of the last step for tests/test_list_kernels_cpu.py (host emulation of the device's list kernels)
+void oracle_debug_grid(void *h, int32_t *cell, int64_t *m_before, int64_t *npairs) {
+  Oracle *o = (Oracle *)h;
+  std::copy(o->last_cell.begin(), o->last_cell.end(), cell);
+  *m_before = o->m_before;
+  *npairs = (int64_t)o->created.size();
+}
+void oracle_debug_surface(void *h, double *normal, double *subset) {
+  Oracle *o = (Oracle *)h;
+  std::copy(o->normal.begin(), o->normal.end(), normal);
+  std::copy(o->subset.begin(), o->subset.end(), subset);
 }
 
 // list-capacity history (m_pairs), the one piece of a checkpoint that is not in spsph_state

@@ -49,6 +49,7 @@ __device__ __forceinline__ bool slot_decode(const SlotMap &m, int t, int &sp, in
   return k < m.nd;
 }
 
+#ifndef SPSPH_HOST_EMU  // (tests/native/list_kernels_host.cpp compiles the guarded-in parts for the host)
 // Particles a kernel has to visit. Single GPU: all of them (ids == nullptr, identity). Multi-GPU: the compact
 // list of this rank's local (owned + ghost) particle numbers kept by dist_kernels.cuh, so that no per-step pass
 // is proportional to the global particle count.
@@ -378,6 +379,7 @@ __device__ __forceinline__ int unified_slot(const SortArrays &S, int c, int sp, 
   return u + (k - S.start[sp][c]);
 }
 
+#endif  // SPSPH_HOST_EMU
 // Growth rule of the reference's list: pairs whose creation index exceeds the old list
 // capacity M are visited first and reversed. Particles are compared by the creation-order key
 // (cell id, species, particle number) -- globally meaningful, so the same rule serves the multi-GPU slabs:
@@ -456,6 +458,7 @@ __device__ __forceinline__ void sph_kernel_fast(const KernelConsts &K, double r,
   }
 }
 
+#ifndef SPSPH_HOST_EMU  // (tests/native/list_kernels_host.cpp compiles the guarded-in parts for the host)
 // Acceptance test with a squared-distance prefilter: sqrt() only for candidates within 2e-15 (relative) of
 // the cut-off, where the reference's `sqrt(driac) < scale_k*mhsml` decides. Returns the squared distance.
 __device__ __forceinline__ bool pair_accept_fast(double scale_k, double2 pp, double hp, double2 pq, double hq,
@@ -738,6 +741,7 @@ __global__ void k_growth_threshold(DevParams P, SlotMap Mm, const GridInfo *__re
   out->kb = mth_forward_partner(P, G, S, c, sp, k, want);
 }
 
+#endif  // SPSPH_HOST_EMU
 struct ListPtrs {
   // list 0: node <- stress/dummy partners and stress <- node/dummy partners (types 1, 6, 9), reference
   //         orientation of the gradient (pair_i - pair_j after Pint_Update)
@@ -757,6 +761,7 @@ struct ListPtrs {
   const int *off0, *offC, *offD;  // per slice, exclusive scans of the slice widths
 };
 
+#ifndef SPSPH_HOST_EMU  // (tests/native/list_kernels_host.cpp compiles the guarded-in parts for the host)
 // Fill pass: writes every list entry at its traversal position.
 // Accepted candidates are first compacted into per-thread shared-memory queues (cheap, divergent scan), then
 // the kernel evaluation + stores run as dense loops with (nearly) all lanes active and row-aligned stores.
@@ -1178,4 +1183,5 @@ __global__ void k_export_pairs(DevParams P, SlotMap M, const GridInfo *__restric
     }
 }
 
+#endif  // SPSPH_HOST_EMU
 }  // namespace spsph

@@ -25,6 +25,7 @@
 
 namespace spsph {
 
+#ifndef SPSPH_HOST_EMU  // (tests/native/list_kernels_host.cpp compiles the guarded-in parts for the host)
 struct __align__(32) Rec4 {
   double a, b, c, d;
 };
@@ -141,8 +142,10 @@ __device__ __forceinline__ void cp_async_wait() {
 // The two top bits of a partner id of list 0 may carry the partner's mass/rho class (QCLASS_SHIFT, written by the fill
 // pass when the host found at most four distinct values per species); gather() always receives the plain id, and so
 // does compute() unless RAWQ asks for the stored word (sweep A, which turns the class into the factor (m/rho)*w).
+#endif  // SPSPH_HOST_EMU
 constexpr int QCLASS_SHIFT = 30;
 constexpr int QID_MASK = (1 << QCLASS_SHIFT) - 1;
+#ifndef SPSPH_HOST_EMU  // (tests/native/list_kernels_host.cpp compiles the guarded-in parts for the host)
 template <int NARR, int NG, class R, int GR = ELL_GROUP, int SUB = ELL_SUB, bool RAWQ = false, class GatherF,
           class ComputeF>
 __device__ __forceinline__ void ell_stream(const int *const *arr, size_t slice_off, int rows, int cnt, int *smw,
@@ -1269,6 +1272,7 @@ k_art_force(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L,
   st2(st.aforce, id, make_double2(t11 + t32, t31 + t22));
 }
 
+#endif  // SPSPH_HOST_EMU
 // ------------------------------------------------------------------------------------------------------
 // get_nodes_on_free_surface, mat:1116-1411, steps 1-3 and the bc_or_not rewrite (mat:1333-1349): which particles
 // lie on the free surface. Runs on demand (spsph_download) with the pair lists of the last step and the positions
@@ -1547,6 +1551,7 @@ __global__ void k_fs_normals(DevParams P, SlotMap M, SortArrays S, const int *__
   st2(fs_normal, id, make_double2(nx, ny));
 }
 
+#ifndef SPSPH_HOST_EMU  // (tests/native/list_kernels_host.cpp compiles the guarded-in parts for the host)
 __global__ void k_pair_stats(SlotMap M, const int *__restrict__ nall, int *__restrict__ out /* max,min,zero */) {
   int mx = 0, mn = 1000, nz = 0;
   const int n = M.total();
@@ -1571,4 +1576,5 @@ __global__ void k_pair_stats(SlotMap M, const int *__restrict__ nall, int *__res
   }
 }
 
+#endif  // SPSPH_HOST_EMU
 }  // namespace spsph
