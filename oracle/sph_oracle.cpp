@@ -58,6 +58,7 @@ struct Oracle {
   std::vector<float> wall_position, horizontal_or_not, n_int;
   // pair list: `created` in creation order; traversal order through order_of()
   std::vector<Pair> created;
+  std::vector<double> x_at_fs;     // positions get_nodes_on_free_surface saw in the last step (before the re-seating)
   std::vector<int32_t> last_cell;  // which_cell of the last grid_find (1-based reference cell id, 0: out of the domain)
   int64_t m_pairs = 0;       // list capacity = max pair count of all previous steps (main:1210)
   int64_t m_before = 0;      // m_pairs at the start of the current step
@@ -1267,6 +1268,7 @@ struct Oracle {
           x[k] = x0[k] + (double)vel_half * dt_sph;
         }
       }
+      x_at_fs = x;
       get_nodes_on_free_surface();  // main:152-154 (ndimn == 2 always here)
       if (p.sp_sph && !p.inside_approach) shift_stress_points();
       if (!p.sp_sph)
@@ -1466,6 +1468,10 @@ void oracle_debug_grid(void *h, int32_t *cell, int64_t *m_before, int64_t *npair
   std::copy(o->last_cell.begin(), o->last_cell.end(), cell);
   *m_before = o->m_before;
   *npairs = (int64_t)o->created.size();
+}
+void oracle_debug_x_fs(void *h, double *x) {
+  Oracle *o = (Oracle *)h;
+  std::copy(o->x_at_fs.begin(), o->x_at_fs.end(), x);
 }
 void oracle_debug_surface(void *h, double *normal, double *subset) {
   Oracle *o = (Oracle *)h;

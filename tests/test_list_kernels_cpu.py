@@ -181,3 +181,47 @@ def test_free_surface_kernels_match_oracle(emu, tmp_path, xsph):
         checked += 1
         marked_total += len(marked)
     assert checked >= 4 and marked_total > 50
+
+
+@pytest.mark.parametrize("mode_kw", [dict(mode="vel_vector"), dict(mode="outside"), dict(mode="inside", npoints=2)])
+def test_free_surface_classification_bui(emu, tmp_path, mode_kw):
+    """k_free_surface on the host == the oracle's classification of every velocity and stress particle of the Bui
+    column (wall partners, stress-stress gradients re-evaluated from the build positions), on the positions the
+    reference classifies on: after the position update, before shift_stress_points re-seats the stress particles"""
+    import spsph
+    from spsph import decks
+    from oracle_binding import Oracle, lib
+    decks.write_deck(str(tmp_path), decks.bui_spec(maxtimestep=1000, **mode_kw))
+    prob = spsph.load(str(tmp_path), "bui")
+    p = prob.params
+    dt = prob.blocks[0]["dt"]
+    orc = Oracle(prob)
+    L = lib()
+    L.oracle_debug_grid.restype = None
+    L.oracle_debug_x_fs.restype = None
+    t, checked = 0.0, 0
+    for step in range(1, 61):
+        before = orc.download()
+        orc.step(step, t, dt)
+        t = t + dt
+        if step not in (1, 2, 30, 60):
+            continue
+        after = orc.download()
+        cells = np.zeros(p.ntotal2, np.int32)
+        mb, npairs = C.c_int64(), C.c_int64()
+        L.oracle_debug_grid(C.c_void_p(orc.h), cells.ctypes.data_as(C.c_void_p), C.byref(mb), C.byref(npairs))
+        mode = 1 if mb.value == 0 else (0 if npairs.value <= mb.value else None)
+        if mode is None:
+            continue
+        x_fs = np.zeros((p.ntotal2, 2))
+        L.oracle_debug_x_fs(C.c_void_p(orc.h), x_fs.ctypes.data_as(C.c_void_p))
+        b = build(prob, cells, orc.pairs(), before["x"])
+        keep = []
+        bc = before["bc_or_not"].astype(np.int32).copy()
+        cov = np.zeros(p.ntotal, np.int32)
+        a = _args(prob, b, mode, x_fs, bc, cov, np.zeros((p.nnode, 2)), keep)
+        emu.emu_free_surface(C.byref(a))
+        assert np.array_equal(bc, after["bc_or_not"]), f"step {step}: {int((bc != after['bc_or_not']).sum())} flags differ"
+        assert (bc == 2).sum() > 50
+        checked += 1
+    assert checked >= 3
