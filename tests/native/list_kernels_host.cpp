@@ -34,6 +34,7 @@ extern "C" struct EmuArgs {
   // scalars
   int32_t nnode, nstress, ndummy, skf, growth_mode, pad;
   double pi;
+  uint64_t growth_ka, growth_kb;  // mode 2: creation keys (creator, partner) of the last old pair
   // species-sorted arrays (velocity, stress, wall particles)
   const int32_t *order[3];
   const int32_t *cell[3];
@@ -87,6 +88,8 @@ static void fill(const EmuArgs &a, DevParams &P, SlotMap &M, SortArrays &S, List
   L.offD = a.offD;
   std::memset(&g, 0, sizeof(g));
   g.mode = a.growth_mode;
+  g.ka = a.growth_ka;
+  g.kb = a.growth_kb;
 }
 
 template <class F>

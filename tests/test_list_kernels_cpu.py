@@ -18,6 +18,7 @@ sys.path.insert(0, os.path.join(ROOT, "oracle"))
 class EmuArgs(C.Structure):
     _fields_ = [("nnode", C.c_int32), ("nstress", C.c_int32), ("ndummy", C.c_int32), ("skf", C.c_int32),
                 ("growth_mode", C.c_int32), ("pad", C.c_int32), ("pi", C.c_double),
+                ("growth_ka", C.c_uint64), ("growth_kb", C.c_uint64),
                 ("order", C.c_void_p * 3), ("cell", C.c_void_p * 3), ("pos", C.c_void_p * 3), ("h", C.c_void_p * 3),
                 ("pos_of", C.c_void_p),
                 ("idx0", C.c_void_p), ("idxC", C.c_void_p), ("idxD", C.c_void_p), ("off0", C.c_void_p),
@@ -105,9 +106,28 @@ def build(prob, cells, pairs, x_built):
                 idxC=idxC, gxC=gxC, gyC=gyC, offC=offC, idxD=idxD, offD=offD, n1=n1)
 
 
-def _args(prob, b, mode, x, bc, cov, normal, keep):
+def growth_rule(prob, cells, pairs, m_before, npairs):
+    """(mode, ka, kb) of the device's GrowthRule (grid_kernels.cuh): 1 = every pair is new (first step, reversed),
+    0 = no growth (forward), 2 = split after the pair with creation index m_before, which is the LAST pair of the
+    traversal order (new pairs first and reversed, then the old ones ascending); keys = (cell, species, id)"""
+    if m_before == 0:
+        return 1, 0, 0
+    if npairs <= m_before:
+        return 0, 0, 0
+    p = prob.params
+
+    def key(i):  # i: 1-based particle number
+        i = int(i) - 1
+        sp = 0 if i < p.nnode else (1 if i < p.ntotal else 2)
+        return ((int(cells[i]) - 1) << 34) | (sp << 32) | i
+    k1, k2 = key(pairs["pair_i"][-1]), key(pairs["pair_j"][-1])
+    return 2, min(k1, k2), max(k1, k2)
+
+
+def _args(prob, b, rule, x, bc, cov, normal, keep):
     p = prob.params
     a = EmuArgs()
+    mode, a.growth_ka, a.growth_kb = rule
     a.nnode, a.nstress, a.ndummy, a.skf, a.growth_mode, a.pi = p.nnode, p.nstress, p.ndummy, p.skf, mode, p.pi
     ptr = lambda arr: (keep.append(arr), arr.ctypes.data)[1]  # noqa: E731
     for s in range(3):
@@ -155,22 +175,18 @@ def test_free_surface_kernels_match_oracle(emu, tmp_path, xsph):
         cells = np.zeros(p.ntotal2, np.int32)
         mb, npairs = C.c_int64(), C.c_int64()
         L.oracle_debug_grid(C.c_void_p(orc.h), cells.ctypes.data_as(C.c_void_p), C.byref(mb), C.byref(npairs))
-        if mb.value == 0:
-            mode = 1          # first step: every pair is new, the list is walked reversed
-        elif npairs.value <= mb.value:
-            mode = 0          # no growth: forward
-        else:
-            continue          # split order (needs the threshold pair's keys): covered by the GPU tests only
+        pairs = orc.pairs()
+        rule = growth_rule(prob, cells, pairs, mb.value, npairs.value)
         normal_o = np.zeros((p.ntotal, 2))
         subset_o = np.zeros(p.ntotal)
         L.oracle_debug_surface(C.c_void_p(orc.h), normal_o.ctypes.data_as(C.c_void_p), subset_o.ctypes.data_as(C.c_void_p))
-        b = build(prob, cells, orc.pairs(), before["x"])
+        b = build(prob, cells, pairs, before["x"])
         keep = []
         bc = before["bc_or_not"].astype(np.int32).copy()
         cov = np.zeros(p.ntotal, np.int32)
         normal_d = np.zeros((p.nnode, 2))
         x_now = np.ascontiguousarray(after["x"])  # inside approach: no re-seating after the classification
-        a = _args(prob, b, mode, x_now, bc, cov, normal_d, keep)
+        a = _args(prob, b, rule, x_now, bc, cov, normal_d, keep)
         if xsph:
             emu.emu_xsph_marks(C.byref(a))
         emu.emu_free_surface(C.byref(a))
@@ -199,29 +215,32 @@ def test_free_surface_classification_bui(emu, tmp_path, mode_kw):
     L = lib()
     L.oracle_debug_grid.restype = None
     L.oracle_debug_x_fs.restype = None
-    t, checked = 0.0, 0
-    for step in range(1, 61):
+    long_run = mode_kw.get("mode") == "vel_vector"  # run on until the pair list has grown twice (split traversal)
+    t, checked, grown = 0.0, 0, 0
+    cells = np.zeros(p.ntotal2, np.int32)
+    mb, npairs = C.c_int64(), C.c_int64()
+    for step in range(1, 341 if long_run else 61):
         before = orc.download()
         orc.step(step, t, dt)
         t = t + dt
-        if step not in (1, 2, 30, 60):
-            continue
-        after = orc.download()
-        cells = np.zeros(p.ntotal2, np.int32)
-        mb, npairs = C.c_int64(), C.c_int64()
         L.oracle_debug_grid(C.c_void_p(orc.h), cells.ctypes.data_as(C.c_void_p), C.byref(mb), C.byref(npairs))
-        mode = 1 if mb.value == 0 else (0 if npairs.value <= mb.value else None)
-        if mode is None:
+        growth = mb.value > 0 and npairs.value > mb.value
+        if not (step in (1, 2, 30, 60) or (growth and grown < 2)):
             continue
+        grown += growth
+        after = orc.download()
+        pairs = orc.pairs()
+        rule = growth_rule(prob, cells, pairs, mb.value, npairs.value)
         x_fs = np.zeros((p.ntotal2, 2))
         L.oracle_debug_x_fs(C.c_void_p(orc.h), x_fs.ctypes.data_as(C.c_void_p))
-        b = build(prob, cells, orc.pairs(), before["x"])
+        b = build(prob, cells, pairs, before["x"])
         keep = []
         bc = before["bc_or_not"].astype(np.int32).copy()
         cov = np.zeros(p.ntotal, np.int32)
-        a = _args(prob, b, mode, x_fs, bc, cov, np.zeros((p.nnode, 2)), keep)
+        a = _args(prob, b, rule, x_fs, bc, cov, np.zeros((p.nnode, 2)), keep)
         emu.emu_free_surface(C.byref(a))
-        assert np.array_equal(bc, after["bc_or_not"]), f"step {step}: {int((bc != after['bc_or_not']).sum())} flags differ"
+        assert np.array_equal(bc, after["bc_or_not"]), (
+            f"step {step} (growth rule {rule[0]}): {int((bc != after['bc_or_not']).sum())} flags differ")
         assert (bc == 2).sum() > 50
         checked += 1
-    assert checked >= 3
+    assert checked >= 4 and (grown == 2 or not long_run)
