@@ -67,6 +67,7 @@ struct Stress4 {
   double s1, s2, s3, s4;
 };
 // (4, n) arrays are 32-byte aligned per particle: one 256-bit access each (LDG/STG.E.ENL2.256 on sm_100a)
+#ifndef SPSPH_HOST_EMU  // device only (the host emulation of tests/native/ has its own version)
 __device__ __forceinline__ Stress4 ld4(const double *p, int i) {
   Stress4 s;
   asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];"
@@ -79,6 +80,15 @@ __device__ __forceinline__ void st4(double *p, int i, const Stress4 &s) {
                "d"(s.s4)
                : "memory");
 }
+#else
+inline Stress4 ld4(const double *p, int i) { return Stress4{p[4 * (size_t)i], p[4 * (size_t)i + 1], p[4 * (size_t)i + 2], p[4 * (size_t)i + 3]}; }
+inline void st4(double *p, int i, const Stress4 &s) {
+  p[4 * (size_t)i] = s.s1;
+  p[4 * (size_t)i + 1] = s.s2;
+  p[4 * (size_t)i + 2] = s.s3;
+  p[4 * (size_t)i + 3] = s.s4;
+}
+#endif  // SPSPH_HOST_EMU
 
 // ---- smoothing kernel, main:1440-1538 (ndimn = 2): cubic spline (skf = 1), Gauss (2), quintic (3); fp64
 // evaluation, caller rounds to fp32. dx,dy = x(pair_i) - x(pair_j); r = sqrt(dx*dx + dy*dy) as computed by the

@@ -49,7 +49,6 @@ __device__ __forceinline__ bool slot_decode(const SlotMap &m, int t, int &sp, in
   return k < m.nd;
 }
 
-#ifndef SPSPH_HOST_EMU  // (tests/native/list_kernels_host.cpp compiles the guarded-in parts for the host)
 // Particles a kernel has to visit. Single GPU: all of them (ids == nullptr, identity). Multi-GPU: the compact
 // list of this rank's local (owned + ghost) particle numbers kept by dist_kernels.cuh, so that no per-step pass
 // is proportional to the global particle count.
@@ -64,6 +63,7 @@ __device__ __forceinline__ int ll_id(const LocalList &l, int k) { return l.ids ?
   for (int K = blockIdx.x * blockDim.x + threadIdx.x, n_ll_ = ll_count(LL), I = 0;                      \
        K < n_ll_ && ((I = ll_id(LL, K)), true); K += gridDim.x * blockDim.x)
 
+#ifndef SPSPH_HOST_EMU  // device only (the host emulation of tests/native/ has its own version)
 // ------------------------------------------------------------------------------------------------------
 // Check_Out_Domain + bounding box / max h of the in-domain particles (min/max are order-independent).
 // ------------------------------------------------------------------------------------------------------
@@ -458,7 +458,7 @@ __device__ __forceinline__ void sph_kernel_fast(const KernelConsts &K, double r,
   }
 }
 
-#ifndef SPSPH_HOST_EMU  // (tests/native/list_kernels_host.cpp compiles the guarded-in parts for the host)
+#ifndef SPSPH_HOST_EMU  // device only (the host emulation of tests/native/ has its own version)
 // Acceptance test with a squared-distance prefilter: sqrt() only for candidates within 2e-15 (relative) of
 // the cut-off, where the reference's `sqrt(driac) < scale_k*mhsml` decides. Returns the squared distance.
 __device__ __forceinline__ bool pair_accept_fast(double scale_k, double2 pp, double hp, double2 pq, double hq,
@@ -761,7 +761,7 @@ struct ListPtrs {
   const int *off0, *offC, *offD;  // per slice, exclusive scans of the slice widths
 };
 
-#ifndef SPSPH_HOST_EMU  // (tests/native/list_kernels_host.cpp compiles the guarded-in parts for the host)
+#ifndef SPSPH_HOST_EMU  // device only (the host emulation of tests/native/ has its own version)
 // Fill pass: writes every list entry at its traversal position.
 // Accepted candidates are first compacted into per-thread shared-memory queues (cheap, divergent scan), then
 // the kernel evaluation + stores run as dense loops with (nearly) all lanes active and row-aligned stores.

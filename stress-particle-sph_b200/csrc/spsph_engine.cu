@@ -37,6 +37,30 @@ using namespace spsph;
     }                                                                                             \
   } while (0)
 
+#ifdef SPSPH_HOST_EMU
+// what build_neighbours produces on the device, handed over by the host-emulation harness instead (arrays of the
+// caller, read during the next spsph_step): species-sorted arrays, warp-sliced ELL lists, growth rule
+struct spsph_emu_lists {
+  int64_t n_pairs;
+  int32_t growth_mode, pad;
+  uint64_t growth_ka, growth_kb;
+  const int32_t *order[3], *cell[3];
+  const double *pos[3], *h[3];
+  const int32_t *pos_of;
+  int64_t tot0, totC, totD;
+  const int32_t *idx0;
+  const float *w0, *gx0, *gy0;
+  const int32_t *idxC;
+  const float *wC, *gxC, *gyC, *xC, *yC, *hC;
+  const int32_t *idxD;
+  const float *wD;
+  const int32_t *off0, *offC, *offD, *n0, *n1;
+  const int32_t *bc_int;
+  const float *n_int;
+  const int32_t *if_out;  // [ntotal2] Check_Out_Domain flags after this step's check (k_domain_bbox sets them on the device)
+};
+#endif
+
 struct spsph_handle {
   spsph_params hp{};
   DevParams P{};
@@ -82,6 +106,9 @@ struct spsph_handle {
   // get_nodes_on_free_surface (main:152-160); the on-demand evaluation at download classifies on this snapshot
   double *x_fs = nullptr;       // (2, ntotal2), single GPU only
   bool x_fs_valid = false;
+#ifdef SPSPH_HOST_EMU
+  const struct spsph_emu_lists *emu_lists = nullptr;  // this step's lists, handed over by the test harness
+#endif
   int cur = 0;
   double *ivars = nullptr;  // device mirror of Internal_Vars(10, ntotal): rows 2..10 never change on the hot path
   std::vector<int32_t> h_itype;
@@ -404,11 +431,14 @@ int ensure_lists(spsph_handle *h, long long t0, long long tC, long long tD) {
 // exclusive scan of `rows` rows of int32 (stride elements apart) over n = *n_ptr + n_add elements each
 void launch_scan(spsph_handle *h, const int *in, int *out, int rows, int stride, const int *n_ptr, int n_add,
                  long long *totals, int kid) {
+#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   dim3 g(SCAN_BLOCKS, rows);
   k_scan_reduce<<<g, SCAN_THREADS, 0, h->stream>>>(in, stride, n_ptr, n_add, h->scan_bsum);
   k_scan_sums<<<rows, SCAN_THREADS, 0, h->stream>>>(h->scan_bsum, totals);
   k_scan_apply<<<g, SCAN_THREADS, 0, h->stream>>>(in, out, stride, n_ptr, n_add, h->scan_bsum);
   mark(h, kid, 3);
+#else
+#endif  // SPSPH_HOST_EMU
 }
 
 // particles a per-particle kernel visits, and the grid for it
@@ -421,6 +451,7 @@ void launch_scan(spsph_handle *h, const int *in, int *out, int rows, int stride,
                  long long *totals, int kid);
 // order-preserving compaction of the local list (ids_in == nullptr: build from the flags of all particles)
 static int compact_local_list(spsph_handle *h, const int *ids_in, const int *n_in, int *ids_out, int *n_out) {
+#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   const int n2 = h->P.ntotal2;
   cudaStream_t s = h->stream;
   const int g = ids_in ? 148 * 8 : (n2 + 255) / 256;
@@ -430,6 +461,9 @@ static int compact_local_list(spsph_handle *h, const int *ids_in, const int *n_i
   k_list_scatter<<<g, 256, 0, s>>>(ids_in, n_in, n2, h->list_keep, h->list_pos, ids_out, n_out);
   CUDA_TRY(cudaGetLastError());
   return 0;
+#else
+  return 1;
+#endif  // SPSPH_HOST_EMU
 }
 static int rebuild_local_list(spsph_handle *h) {
   h->list_cur = 0;
@@ -447,6 +481,7 @@ static int halo_limit(const spsph_handle *h, int prev_count) {
   return l < h->D.cap ? (int)l : h->D.cap;
 }
 int halo_exchange(spsph_handle *h) {
+#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   const DevParams &P = h->P;
   h->D.lim[0] = halo_limit(h, h->halo_prev_send[0]);
   h->D.lim[1] = halo_limit(h, h->halo_prev_send[1]);
@@ -494,10 +529,14 @@ int halo_exchange(spsph_handle *h) {
   h->list_cur = 1 - h->list_cur;
   mark(h, KID_HALO, 9);
   return 0;
+#else
+  return 1;
+#endif  // SPSPH_HOST_EMU
 }
 
 // neighbour search up to and including the list fill; leaves the pair totals in h->status_h
 int build_neighbours(spsph_handle *h) {
+#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   const DevParams &P = h->P;
   const int n2 = P.ntotal2;
   const int TB = 256;
@@ -658,6 +697,72 @@ int build_neighbours(spsph_handle *h) {
   }
   mark(h, KID_FILL, h->dist ? 2 : 1);
   return 0;
+#else
+  // host emulation: the test harness hands over this step's sorted arrays and gather lists (built from the oracle's
+  // pair list in the layout k_count / k_fill write), see tests/test_step_emulation_cpu.py
+  const spsph_emu_lists *E = h->emu_lists;
+  if (!E) {
+    h->err = "host emulation: spsph_emu_set_lists must precede every spsph_step";
+    return 1;
+  }
+  h->emu_lists = nullptr;
+  const DevParams &P = h->P;
+  const size_t n2 = (size_t)P.ntotal2;
+  const int cnt[3] = {P.nnode, P.nstress, P.ndummy};
+  for (int sp = 0; sp < 3; ++sp) {
+    std::memcpy(h->order + sp * n2, E->order[sp], cnt[sp] * sizeof(int));
+    std::memcpy(h->scell + sp * n2, E->cell[sp], cnt[sp] * sizeof(int));
+    std::memcpy(h->spos + sp * n2, E->pos[sp], cnt[sp] * sizeof(double2));
+    std::memcpy(h->sh + sp * n2, E->h[sp], cnt[sp] * sizeof(double));
+  }
+  std::memcpy(h->pos_of, E->pos_of, n2 * sizeof(int));
+  for (int k = 0; k < 3; ++k) h->nloc[k] = cnt[k];
+  h->nloc_valid = true;
+  if (ensure_lists(h, E->tot0, E->totC, E->totD)) return 1;
+  const int T = h->M.nnp + h->M.nsp;
+  std::memcpy(h->n0, E->n0, T * sizeof(int));
+  std::memcpy(h->n1, E->n1, T * sizeof(int));
+  std::memcpy(h->oslice, E->off0, h->nslices * sizeof(int));
+  std::memcpy(h->oslice + h->nslices, E->offC, h->nslices * sizeof(int));
+  std::memcpy(h->oslice + 2 * h->nslices, E->offD, h->nslices * sizeof(int));
+  h->L.off0 = h->oslice;
+  h->L.offC = h->oslice + h->nslices;
+  h->L.offD = h->oslice + 2 * h->nslices;
+  for (long long a = 0; a < E->tot0; ++a) {
+    const int q = E->idx0[a];
+    h->L.idx0[a] = h->umor ? (q | ((int)h->mcls[q] << 30)) : q;
+    h->L.w0[a] = E->w0[a];
+    h->L.gx0[a] = E->gx0[a];
+    h->L.gy0[a] = E->gy0[a];
+    if (h->L.h0lo) {  // (m/rho)_partner * w, zero for wall partners (k_fill)
+      const double h0 = q >= P.ntotal ? 0.0 : h->mor[q] * (double)E->w0[a];
+      h->L.h0lo[a] = __double2loint(h0);
+      h->L.h0hi[a] = __double2hiint(h0);
+    }
+  }
+  for (long long a = 0; a < E->totC; ++a) {
+    h->L.idxC[a] = E->idxC[a];
+    h->L.wC[a] = E->wC[a];
+    h->L.gxC[a] = E->gxC[a];
+    h->L.gyC[a] = E->gyC[a];
+    h->L.xC[a] = E->xC[a];
+    h->L.yC[a] = E->yC[a];
+    if (h->L.hC) h->L.hC[a] = E->hC[a];
+  }
+  for (long long a = 0; a < E->totD; ++a) {
+    h->L.idxD[a] = E->idxD[a];
+    h->L.wD[a] = E->wD[a];
+  }
+  std::memcpy(h->bc_int, E->bc_int, P.nnode * sizeof(int));
+  std::memcpy(h->if_out, E->if_out, n2 * sizeof(int));
+  if (P.track_nint) std::memcpy(h->n_int, E->n_int, P.nnode * sizeof(float));
+  h->last_m_before = h->m_pairs;
+  h->last_n_pairs = E->n_pairs;
+  GrowthRule gr{E->growth_mode, 0, E->growth_ka, E->growth_kb};
+  *h->growth = gr;
+  if (E->n_pairs > h->m_pairs) h->m_pairs = E->n_pairs;
+  return 0;
+#endif  // SPSPH_HOST_EMU
 }
 
 // sweep A launches: the UMOR variants (uniform mass/rho per species, see k_sweep_a_sp) are chosen at run time
@@ -1000,11 +1105,15 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   rc |= dalloc(h, &h->which_cell, n2) | dalloc(h, &h->tmp_ids, 3 * n2) | dalloc(h, &h->order, 3 * n2);
   rc |= dalloc(h, &h->scell, 3 * n2) | dalloc(h, &h->pos_of, n2) | dalloc(h, &h->nout, 8) | dalloc(h, &h->bb6, 8);
   rc |= dalloc(h, &h->spos, 3 * n2) | dalloc(h, &h->sh, 3 * n2) | dalloc(h, &h->supos, 3 * n2);
+#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   rc |= dalloc(h, &h->scan_bsum, 4 * (size_t)SCAN_BLOCKS) | dalloc(h, &h->scan_totals, 8);
+#endif  // SPSPH_HOST_EMU
   const size_t T = (size_t)M.total();
   rc |= dalloc(h, &h->n0, T) | dalloc(h, &h->n1, T) | dalloc(h, &h->nall, T);
   rc |= dalloc(h, &h->nfwd_u, n2) | dalloc(h, &h->base_u, n2) | dalloc(h, &h->cand_overflow, 4);
+#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   rc |= dalloc(h, &h->cand0, (size_t)h->nslices * CAND_CAP * SLICE) | dalloc(h, &h->cand1, (size_t)h->nslices * CAND_CAP * SLICE);
+#endif  // SPSPH_HOST_EMU
   rc |= dalloc(h, &h->wslice, 3 * (size_t)h->nslices) | dalloc(h, &h->oslice, 3 * (size_t)h->nslices);
   rc |= dalloc(h, &h->growth, 1) | dalloc(h, &h->status_d, 1) | dalloc(h, &h->stats_d, 4);
   if (rc) return 1;
@@ -1131,11 +1240,13 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   h->have_lists = false;
   h->x_fs_valid = false;
   h->uploaded = true;
+#ifndef SPSPH_HOST_EMU
   if (h->dist) {  // a fresh upload holds complete data on every rank: re-derive owned / ghost / remote
     k_dist_init_flags<<<((int)n2 + 255) / 256, 256, 0, st>>>(h->P, h->D, h->x, h->lflag);
     if (rebuild_local_list(h)) return 1;
     CUDA_TRY(cudaStreamSynchronize(st));
   }
+#endif
   return 0;
 }
 
@@ -1205,6 +1316,14 @@ int spsph_set_list_capacity(spsph_handle *h, int64_t m_pairs) {
   return 0;
 }
 
+#ifdef SPSPH_HOST_EMU
+int spsph_emu_set_lists(spsph_handle *h, const spsph_emu_lists *lists) {
+  if (!h || !lists) return 1;
+  h->emu_lists = lists;
+  return 0;
+}
+#endif
+
 int spsph_sync(spsph_handle *h) {
   if (!h) return 1;
   CUDA_TRY(cudaSetDevice(h->device));
@@ -1267,6 +1386,7 @@ int spsph_download(spsph_handle *h, const spsph_state *s) {
 }
 
 int spsph_pair_stats(spsph_handle *h, int64_t *npairs, int32_t *maxiac, int32_t *miniac, int32_t *noiac) {
+#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   if (!h) return 1;
   CUDA_TRY(cudaSetDevice(h->device));
   const int init[4] = {0, 1000, 0, 0};
@@ -1284,10 +1404,14 @@ int spsph_pair_stats(spsph_handle *h, int64_t *npairs, int32_t *maxiac, int32_t 
   if (miniac) *miniac = out[1];
   if (noiac) *noiac = out[2];
   return 0;
+#else
+  return 1;
+#endif  // SPSPH_HOST_EMU
 }
 
 int spsph_pairs(spsph_handle *h, int64_t *npairs, int32_t *pair_i, int32_t *pair_j, int32_t *pint_type, float *w,
                 float *dwdx, float *dwdy) {
+#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   if (!h) return 1;
   const long long n = h->last_n_pairs;
   if (npairs) *npairs = n;
@@ -1324,6 +1448,9 @@ int spsph_pairs(spsph_handle *h, int64_t *npairs, int32_t *pair_i, int32_t *pair
   cudaFree(d_x);
   cudaFree(d_y);
   return 0;
+#else
+  return 1;
+#endif  // SPSPH_HOST_EMU
 }
 
 int spsph_dist_unique_id(char *id128) {
@@ -1339,6 +1466,7 @@ int spsph_dist_unique_id(char *id128) {
 
 int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *id128, const double *planes,
                     int32_t halo_cells, int32_t halo_capacity) {
+#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   if (!h || !planes || nranks < 1 || rank < 0 || rank >= nranks) return 1;
   if (!h->uploaded) {
     h->err = "spsph_dist_init must follow spsph_upload (every rank uploads the complete problem)";
@@ -1417,6 +1545,9 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
   if (rebuild_local_list(h)) return 1;
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;
+#else
+  return 1;
+#endif  // SPSPH_HOST_EMU
 }
 
 int spsph_local_counts(spsph_handle *h, int32_t *nloc3) {
@@ -1426,6 +1557,7 @@ int spsph_local_counts(spsph_handle *h, int32_t *nloc3) {
 }
 
 int spsph_dist_flags(spsph_handle *h, int32_t *flags) {
+#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   if (!h || !flags) return 1;
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1435,6 +1567,9 @@ int spsph_dist_flags(spsph_handle *h, int32_t *flags) {
   }
   CUDA_TRY(cudaMemcpy(flags, h->lflag, (size_t)h->hp.ntotal2 * sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
+#else
+  return 1;
+#endif  // SPSPH_HOST_EMU
 }
 
 int spsph_destroy(spsph_handle *h) {

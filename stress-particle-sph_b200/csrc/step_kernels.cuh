@@ -25,7 +25,6 @@
 
 namespace spsph {
 
-#ifndef SPSPH_HOST_EMU  // (tests/native/list_kernels_host.cpp compiles the guarded-in parts for the host)
 struct __align__(32) Rec4 {
   double a, b, c, d;
 };
@@ -78,6 +77,7 @@ struct StatePtrs {
 
 // 32-byte records move with one 256-bit access (LDG.E.ENL2.256 / STG.E.ENL2.256 on sm_100a): a gathered record
 // costs one L1 sector access instead of two 128-bit ones -- the L1 sector rate bounds the pair-sum kernels.
+#ifndef SPSPH_HOST_EMU  // device only (the host emulation of tests/native/ has its own version)
 __device__ __forceinline__ Rec4 ld256(const void *p) {
   Rec4 r;
   asm volatile("ld.global.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(r.a), "=d"(r.b), "=d"(r.c), "=d"(r.d) : "l"(p));
@@ -86,6 +86,10 @@ __device__ __forceinline__ Rec4 ld256(const void *p) {
 __device__ __forceinline__ void st256(void *p, double a, double b, double c, double d) {
   asm volatile("st.global.v4.f64 [%0], {%1,%2,%3,%4};" ::"l"(p), "d"(a), "d"(b), "d"(c), "d"(d) : "memory");
 }
+#else
+inline Rec4 ld256(const void *p) { return *static_cast<const Rec4 *>(p); }
+inline void st256(void *p, double a, double b, double c, double d) { *static_cast<Rec4 *>(p) = Rec4{a, b, c, d}; }
+#endif  // SPSPH_HOST_EMU
 __device__ __forceinline__ Rec4 ldrec(const Rec4 *p, int i) { return ld256(p + i); }
 __device__ __forceinline__ void strec(Rec4 *p, int i, double a, double b, double c, double d) {
   st256(p + i, a, b, c, d);
@@ -112,6 +116,7 @@ constexpr int ELL_GROUP = 4;  // rows per cp.async group
 constexpr int ELL_SUB = SPSPH_ELL_SUB;  // entries gathered + consumed together (in flight per thread)
 constexpr int ELL_NG = 4;     // groups in the ring (16 rows = 2 KB per array per warp in flight)
 
+#ifndef SPSPH_HOST_EMU  // device only (the host emulation of tests/native/ has its own version)
 // The list rows are read exactly once per sweep: L2 evict-first, so that the 0.7-1.3 GB streamed per sweep do
 // not push the gathered particle records (43-171 MB, re-read ~20-40 times each) out of the 126 MB L2.
 __device__ __forceinline__ unsigned long long l2_policy_evict_first() {
@@ -135,6 +140,7 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+#endif  // SPSPH_HOST_EMU
 // NARR arrays of 4-byte entries are streamed (array 0 holds the partner ids). `rows` is the slice width
 // (warp-uniform), `cnt` the calling lane's own list length. gather(q) -> R fetches the partner record (q < 0:
 // past the end); compute(q[4], pay[NARR-1][4], rec[4], nvalid) consumes one group of entries in list order
@@ -142,10 +148,9 @@ __device__ __forceinline__ void cp_async_wait() {
 // The two top bits of a partner id of list 0 may carry the partner's mass/rho class (QCLASS_SHIFT, written by the fill
 // pass when the host found at most four distinct values per species); gather() always receives the plain id, and so
 // does compute() unless RAWQ asks for the stored word (sweep A, which turns the class into the factor (m/rho)*w).
-#endif  // SPSPH_HOST_EMU
 constexpr int QCLASS_SHIFT = 30;
 constexpr int QID_MASK = (1 << QCLASS_SHIFT) - 1;
-#ifndef SPSPH_HOST_EMU  // (tests/native/list_kernels_host.cpp compiles the guarded-in parts for the host)
+#ifndef SPSPH_HOST_EMU  // device only (the host emulation of tests/native/ has its own version)
 template <int NARR, int NG, class R, int GR = ELL_GROUP, int SUB = ELL_SUB, bool RAWQ = false, class GatherF,
           class ComputeF>
 __device__ __forceinline__ void ell_stream(const int *const *arr, size_t slice_off, int rows, int cnt, int *smw,
@@ -193,6 +198,29 @@ __device__ __forceinline__ void ell_stream(const int *const *arr, size_t slice_o
   }
   cp_async_wait<0>();
 }
+#else
+// host emulation: the same entries in the same SUB-sized groups, read straight from the list arrays
+template <int NARR, int NG, class R, int GR = ELL_GROUP, int SUB = ELL_SUB, bool RAWQ = false, class GatherF,
+          class ComputeF>
+inline void ell_stream(const int *const *arr, size_t slice_off, int rows, int cnt, int *, GatherF gather,
+                       ComputeF compute) {
+  const int lane = threadIdx.x & 31;
+  const int ng = (rows + GR - 1) / GR;
+  for (int g = 0; g < ng; ++g)
+    for (int hh = 0; hh < GR / SUB; ++hh) {
+      int q[SUB], pay[NARR > 1 ? NARR - 1 : 1][SUB];
+      R cur[SUB];
+      for (int u = 0; u < SUB; ++u) {
+        const int row = g * GR + hh * SUB + u;
+        const int raw = row < cnt ? arr[0][slice_off + (size_t)row * 32 + lane] : 0;
+        q[u] = RAWQ ? raw : (raw & QID_MASK);
+        cur[u] = gather(row < cnt ? (raw & QID_MASK) : -1);
+        for (int a = 1; a < NARR; ++a) pay[a - 1][u] = row < cnt ? arr[a][slice_off + (size_t)row * 32 + lane] : 0;
+      }
+      compute(q, pay, cur, cnt - g * GR - hh * SUB);
+    }
+}
+#endif  // SPSPH_HOST_EMU
 __device__ __forceinline__ int warp_max_i(int v) {
   for (int o = 16; o > 0; o >>= 1) v = max(v, __shfl_xor_sync(0xffffffffu, v, o));
   return v;
@@ -1272,7 +1300,6 @@ k_art_force(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L,
   st2(st.aforce, id, make_double2(t11 + t32, t31 + t22));
 }
 
-#endif  // SPSPH_HOST_EMU
 // ------------------------------------------------------------------------------------------------------
 // get_nodes_on_free_surface, mat:1116-1411, steps 1-3 and the bc_or_not rewrite (mat:1333-1349): which particles
 // lie on the free surface. Runs on demand (spsph_download) with the pair lists of the last step and the positions
@@ -1551,7 +1578,6 @@ __global__ void k_fs_normals(DevParams P, SlotMap M, SortArrays S, const int *__
   st2(fs_normal, id, make_double2(nx, ny));
 }
 
-#ifndef SPSPH_HOST_EMU  // (tests/native/list_kernels_host.cpp compiles the guarded-in parts for the host)
 __global__ void k_pair_stats(SlotMap M, const int *__restrict__ nall, int *__restrict__ out /* max,min,zero */) {
   int mx = 0, mn = 1000, nz = 0;
   const int n = M.total();
@@ -1576,5 +1602,4 @@ __global__ void k_pair_stats(SlotMap M, const int *__restrict__ nall, int *__res
   }
 }
 
-#endif  // SPSPH_HOST_EMU
 }  // namespace spsph

@@ -7,24 +7,7 @@
 // arithmetic of these kernels against the oracle without a GPU. What it cannot: that k_count / k_fill produce these
 // lists (the GPU parity tests do that).
 //   g++ -O1 -ffp-contract=off -std=c++17 -fPIC -shared -w -D__noinline__= -I/usr/local/cuda/include -I<csrc> -I<include>
-#define SPSPH_HOST_EMU
-#include <cmath>
-#include <cstdint>
-#include <cstring>
-
-#include <cuda_runtime.h>
-
-struct EmuDim {
-  unsigned x, y, z;
-};
-static thread_local EmuDim emu_blockIdx, emu_blockDim, emu_threadIdx, emu_gridDim;
-#define blockIdx emu_blockIdx
-#define blockDim emu_blockDim
-#define threadIdx emu_threadIdx
-#define gridDim emu_gridDim
-static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
-static inline float __fsqrt_rn(float x) { return sqrtf(x); }
-static inline double __drcp_rn(double x) { return 1.0 / x; }
+#include "cuda_host_emu.h"
 
 #include "step_kernels.cuh"
 
