@@ -58,7 +58,7 @@ def emu_engine(tmp_path_factory):
     E._lib, E._CUDA_SO = saved
 
 
-def build_step(prob, cells, pairs, x_built, rule, npairs):
+def build_step(prob, cells, pairs, x_built, rule, npairs, hsml=None):
     """this step's species-sorted arrays and gather lists in the device layout, from the oracle's grid cells and
     ordered pair list (the payloads of csrc/grid_kernels.cuh::k_fill)"""
     p = prob.params
@@ -66,7 +66,7 @@ def build_step(prob, cells, pairs, x_built, rule, npairs):
     ids = np.arange(n2)
     species = np.where(ids < nn, 0, np.where(ids < nt, 1, 2))
     cell0 = cells.astype(np.int64) - 1
-    hs = prob.arrays["hsml"]
+    hs = prob.arrays["hsml"] if hsml is None else hsml  # sle = 2: the smoothing length the lists were built with
     order, cell, pos, hh = [], [], [], []
     pos_of = np.zeros(n2, np.int32)
     for sp in range(3):
@@ -128,8 +128,8 @@ def build_step(prob, cells, pairs, x_built, rule, npairs):
     return E, keep
 
 
-STATE_KEYS = ("x", "vel", "stress", "internal_vars", "f_drucker", "displ", "x_10", "disp_10", "n_int", "bc_int",
-              "if_out_domain", "bc_or_not")
+STATE_KEYS = ("x", "vel", "stress", "rho", "hsml", "internal_vars", "f_drucker", "displ", "x_10", "disp_10", "n_int",
+              "bc_int", "if_out_domain", "bc_or_not")
 
 
 def run_lockstep(emu_engine, prob, nsteps, check_at, label):
@@ -144,12 +144,13 @@ def run_lockstep(emu_engine, prob, nsteps, check_at, label):
     mb, npairs = C.c_int64(), C.c_int64()
     t = 0.0
     for step in range(1, nsteps + 1):
-        x_before = orc.download()["x"]
+        before = orc.download()
+        x_before = before["x"]
         orc.step(step, t, dt)
         L.oracle_debug_grid(C.c_void_p(orc.h), cells.ctypes.data_as(C.c_void_p), C.byref(mb), C.byref(npairs))
         pairs = orc.pairs()
         rule = growth_rule(prob, cells, pairs, mb.value, npairs.value)
-        E, keep = build_step(prob, cells, pairs, x_before, rule, npairs.value)
+        E, keep = build_step(prob, cells, pairs, x_before, rule, npairs.value, before["hsml"])
         assert emu_engine.cuda_lib().spsph_emu_set_lists(eng.h, C.byref(E)) == 0
         eng.step(step, t, dt)
         t = t + dt
@@ -226,7 +227,10 @@ EMU_CASES = [
     ("bui_art_stress", "bui", lambda: _bui(art_stress=True), 6),
     ("bui_gauss", "bui", lambda: _bui(skf=2), 6),
     ("bui_quintic", "bui", lambda: _bui(skf=3), 6),
+    ("bui_cont_density", "bui", lambda: _bui(cont_density=True), 8),
     ("vs", "vs", lambda: _vs(), 10),
+    ("vs_cont_density_sle2", "vs", lambda: _vs(cont_density=True), 8),
+    ("sl_cont_density_sle2", "sl", lambda: _sl(cont_density=True), 20),
     ("vs_sp2", "vs", lambda: _vs(npoints=2), 6),
     ("vs_standard", "vs", lambda: _vs(standard=True) if False else dict(_vs(), sp_sph=False), 6),
     ("vs_sigman", "vs", lambda: _vs(free_right=True, ifsigman=1, update_x=True), 12),
@@ -240,6 +244,10 @@ EMU_CASES = [
     ("sl_sigman", "sl", lambda: _sl(free_right=True, ifsigman=1), 20),
     ("sl_xsph", "sl", lambda: _sl(free_right=True, xsph=True, yield0=5.e3), 20),
     ("sl_sigman_xsph", "sl", lambda: _sl(free_right=True, ifsigman=1, xsph=True, yield0=5.e3), 20),
+    # the three decks exactly as shipped (BASELINE configs 0-2), first steps
+    ("shipped_bui", "bui", lambda: __import__("spsph").decks.bui_spec(maxtimestep=100), 3),
+    ("shipped_vs", "vs", lambda: __import__("spsph").decks.vertical_slope_spec(maxtimestep=100), 4),
+    ("shipped_sl", "sl", lambda: __import__("spsph").decks.strain_localisation_spec(maxtimestep=100), 2),
 ]
 
 
