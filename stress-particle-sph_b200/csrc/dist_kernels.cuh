@@ -33,7 +33,6 @@ struct DistGeom {
 
 // position that decides ownership: a stress particle of the outside approach follows its velocity particle,
 // because shift_stress_points (main:244-368) re-seats it from that particle's thread
-#ifndef SPSPH_HOST_EMU  // device only (the multi-GPU path is not emulated on the host)
 __device__ __forceinline__ double key_x(const DevParams &P, const DistGeom &D, const double *__restrict__ x, int i) {
   if (D.sp_follows_node && i >= P.nnode && i < P.ntotal) return x[2 * (size_t)((i - P.nnode) / P.npoints)];
   return x[2 * (size_t)i];
@@ -123,14 +122,12 @@ __global__ void k_halo_select(DevParams P, DistGeom D, const double *__restrict_
   }
 }
 
-#endif  // SPSPH_HOST_EMU
 struct HaloArrays {
   double *x, *epsp, *fdp, *x_10, *disp_10, *displ;
   int *if_out;
 };
 
 // message layout: record 0 = header {count}, records 1..count = particles
-#ifndef SPSPH_HOST_EMU  // device only (the multi-GPU path is not emulated on the host)
 __global__ void k_halo_pack(DevParams P, StatePtrs st, HaloArrays A, const int *__restrict__ cnt_ptr, int cap,
                             const int *__restrict__ ids, double *__restrict__ msg) {
   const int n = min(*cnt_ptr, cap);
@@ -259,7 +256,6 @@ __global__ void k_bbox_final(int nblocks, const double *__restrict__ partial, do
 // knows, for its owned particles, the number of pairs they open (nfwd_u, local exclusive scan base_u). The
 // search narrows row -> cell -> particle with one small collective per level; everything stays on the stream.
 // ------------------------------------------------------------------------------------------------------
-#endif  // SPSPH_HOST_EMU
 constexpr int GT_CAP = 1 << 16;  // rows / cells per row the search can handle
 constexpr int GT_PCAP = 256;     // pair-opening particles of one cell listed per rank
 
@@ -268,7 +264,6 @@ struct GtSel {
   int row, cell, err, pad;
 };
 
-#ifndef SPSPH_HOST_EMU  // device only (the multi-GPU path is not emulated on the host)
 __device__ __forceinline__ int unified_of_cell(const SortArrays &S, int c) {
   return S.start[0][c] + S.start[1][c] + S.start[2][c];
 }
@@ -404,5 +399,4 @@ __global__ void k_gt_finish(const long long *__restrict__ out2, const GtSel *__r
   if (sel->err || out2[2] != 1) *err = 1;
 }
 
-#endif  // SPSPH_HOST_EMU
 }  // namespace spsph

@@ -63,7 +63,6 @@ __device__ __forceinline__ int ll_id(const LocalList &l, int k) { return l.ids ?
   for (int K = blockIdx.x * blockDim.x + threadIdx.x, n_ll_ = ll_count(LL), I = 0;                      \
        K < n_ll_ && ((I = ll_id(LL, K)), true); K += gridDim.x * blockDim.x)
 
-#ifndef SPSPH_HOST_EMU  // device only (the host emulation of tests/native/ has its own version)
 // ------------------------------------------------------------------------------------------------------
 // Check_Out_Domain + bounding box / max h of the in-domain particles (min/max are order-independent).
 // ------------------------------------------------------------------------------------------------------
@@ -379,7 +378,6 @@ __device__ __forceinline__ int unified_slot(const SortArrays &S, int c, int sp, 
   return u + (k - S.start[sp][c]);
 }
 
-#endif  // SPSPH_HOST_EMU
 // Growth rule of the reference's list: pairs whose creation index exceeds the old list
 // capacity M are visited first and reversed. Particles are compared by the creation-order key
 // (cell id, species, particle number) -- globally meaningful, so the same rule serves the multi-GPU slabs:
@@ -458,7 +456,6 @@ __device__ __forceinline__ void sph_kernel_fast(const KernelConsts &K, double r,
   }
 }
 
-#ifndef SPSPH_HOST_EMU  // device only (the host emulation of tests/native/ has its own version)
 // Acceptance test with a squared-distance prefilter: sqrt() only for candidates within 2e-15 (relative) of
 // the cut-off, where the reference's `sqrt(driac) < scale_k*mhsml` decides. Returns the squared distance.
 __device__ __forceinline__ bool pair_accept_fast(double scale_k, double2 pp, double hp, double2 pq, double hq,
@@ -741,7 +738,6 @@ __global__ void k_growth_threshold(DevParams P, SlotMap Mm, const GridInfo *__re
   out->kb = mth_forward_partner(P, G, S, c, sp, k, want);
 }
 
-#endif  // SPSPH_HOST_EMU
 struct ListPtrs {
   // list 0: node <- stress/dummy partners and stress <- node/dummy partners (types 1, 6, 9), reference
   //         orientation of the gradient (pair_i - pair_j after Pint_Update)
@@ -761,7 +757,6 @@ struct ListPtrs {
   const int *off0, *offC, *offD;  // per slice, exclusive scans of the slice widths
 };
 
-#ifndef SPSPH_HOST_EMU  // device only (the host emulation of tests/native/ has its own version)
 // Fill pass: writes every list entry at its traversal position.
 // Accepted candidates are first compacted into per-thread shared-memory queues (cheap, divergent scan), then
 // the kernel evaluation + stores run as dense loops with (nearly) all lanes active and row-aligned stores.
@@ -1183,5 +1178,4 @@ __global__ void k_export_pairs(DevParams P, SlotMap M, const GridInfo *__restric
     }
 }
 
-#endif  // SPSPH_HOST_EMU
 }  // namespace spsph

@@ -431,14 +431,25 @@ int ensure_lists(spsph_handle *h, long long t0, long long tC, long long tD) {
 // exclusive scan of `rows` rows of int32 (stride elements apart) over n = *n_ptr + n_add elements each
 void launch_scan(spsph_handle *h, const int *in, int *out, int rows, int stride, const int *n_ptr, int n_add,
                  long long *totals, int kid) {
-#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
+#ifndef SPSPH_HOST_EMU
   dim3 g(SCAN_BLOCKS, rows);
   k_scan_reduce<<<g, SCAN_THREADS, 0, h->stream>>>(in, stride, n_ptr, n_add, h->scan_bsum);
   k_scan_sums<<<rows, SCAN_THREADS, 0, h->stream>>>(h->scan_bsum, totals);
   k_scan_apply<<<g, SCAN_THREADS, 0, h->stream>>>(in, out, stride, n_ptr, n_add, h->scan_bsum);
   mark(h, kid, 3);
 #else
-#endif  // SPSPH_HOST_EMU
+  const int n = (n_ptr ? *n_ptr : 0) + n_add;
+  for (int r = 0; r < rows; ++r) {
+    long long acc = 0;
+    for (int i = 0; i < n; ++i) {
+      const int v = in[(size_t)r * stride + i];
+      out[(size_t)r * stride + i] = (int)acc;
+      acc += v;
+    }
+    if (totals) totals[r] = acc;
+  }
+  mark(h, kid, 3);
+#endif
 }
 
 // particles a per-particle kernel visits, and the grid for it
@@ -535,8 +546,110 @@ int halo_exchange(spsph_handle *h) {
 }
 
 // neighbour search up to and including the list fill; leaves the pair totals in h->status_h
+#ifdef SPSPH_HOST_EMU
+// host emulation, lockstep mode: the test harness hands over this step's sorted arrays and gather lists (built from
+// the oracle's pair list in the layout k_count / k_fill write), see tests/test_step_emulation_cpu.py
+int emu_import_lists(spsph_handle *h) {
+  const spsph_emu_lists *E = h->emu_lists;
+  h->emu_lists = nullptr;
+  const DevParams &P = h->P;
+  const size_t n2 = (size_t)P.ntotal2;
+  const int cnt[3] = {P.nnode, P.nstress, P.ndummy};
+  for (int sp = 0; sp < 3; ++sp) {
+    std::memcpy(h->order + sp * n2, E->order[sp], cnt[sp] * sizeof(int));
+    std::memcpy(h->scell + sp * n2, E->cell[sp], cnt[sp] * sizeof(int));
+    std::memcpy(h->spos + sp * n2, E->pos[sp], cnt[sp] * sizeof(double2));
+    std::memcpy(h->sh + sp * n2, E->h[sp], cnt[sp] * sizeof(double));
+  }
+  std::memcpy(h->pos_of, E->pos_of, n2 * sizeof(int));
+  for (int k = 0; k < 3; ++k) h->nloc[k] = cnt[k];
+  h->nloc_valid = true;
+  if (ensure_lists(h, E->tot0, E->totC, E->totD)) return 1;
+  const int T = h->M.nnp + h->M.nsp;
+  std::memcpy(h->n0, E->n0, T * sizeof(int));
+  std::memcpy(h->n1, E->n1, T * sizeof(int));
+  std::memcpy(h->oslice, E->off0, h->nslices * sizeof(int));
+  std::memcpy(h->oslice + h->nslices, E->offC, h->nslices * sizeof(int));
+  std::memcpy(h->oslice + 2 * h->nslices, E->offD, h->nslices * sizeof(int));
+  h->L.off0 = h->oslice;
+  h->L.offC = h->oslice + h->nslices;
+  h->L.offD = h->oslice + 2 * h->nslices;
+  for (long long a = 0; a < E->tot0; ++a) {
+    const int q = E->idx0[a];
+    h->L.idx0[a] = h->umor ? (q | ((int)h->mcls[q] << 30)) : q;
+    h->L.w0[a] = E->w0[a];
+    h->L.gx0[a] = E->gx0[a];
+    h->L.gy0[a] = E->gy0[a];
+    if (h->L.h0lo) {  // (m/rho)_partner * w, zero for wall partners (k_fill)
+      const double h0 = q >= P.ntotal ? 0.0 : h->mor[q] * (double)E->w0[a];
+      h->L.h0lo[a] = __double2loint(h0);
+      h->L.h0hi[a] = __double2hiint(h0);
+    }
+  }
+  for (long long a = 0; a < E->totC; ++a) {
+    h->L.idxC[a] = E->idxC[a];
+    h->L.wC[a] = E->wC[a];
+    h->L.gxC[a] = E->gxC[a];
+    h->L.gyC[a] = E->gyC[a];
+    h->L.xC[a] = E->xC[a];
+    h->L.yC[a] = E->yC[a];
+    if (h->L.hC) h->L.hC[a] = E->hC[a];
+  }
+  for (long long a = 0; a < E->totD; ++a) {
+    h->L.idxD[a] = E->idxD[a];
+    h->L.wD[a] = E->wD[a];
+  }
+  std::memcpy(h->bc_int, E->bc_int, P.nnode * sizeof(int));
+  std::memcpy(h->if_out, E->if_out, n2 * sizeof(int));
+  if (P.track_nint) std::memcpy(h->n_int, E->n_int, P.nnode * sizeof(float));
+  h->last_m_before = h->m_pairs;
+  h->last_n_pairs = E->n_pairs;
+  GrowthRule gr{E->growth_mode, 0, E->growth_ka, E->growth_kb};
+  *h->growth = gr;
+  if (E->n_pairs > h->m_pairs) h->m_pairs = E->n_pairs;
+  return 0;
+}
+
+// host emulation, stand-alone mode: the cooperative pieces of the neighbour build done by plain host loops (the
+// per-particle kernels k_cell_id, k_scatter, k_rank, k_count, k_fill run thread by thread like all the others)
+void emu_bbox(spsph_handle *h) {  // k_domain_bbox + k_bbox_final: Check_Out_Domain, bounds and max h of the in-domain particles
+  const DevParams &P = h->P;
+  double xmn = 1.e+10, ymn = 1.e+10, xmx = -1.e+10, ymx = -1.e+10, hmx = 0.0, hmn = 1.e+300;
+  for (int i = 0; i < P.ntotal2; ++i) {
+    const double px = h->x[2 * (size_t)i], py = h->x[2 * (size_t)i + 1];
+    const double dxx = (px - P.xmin_dom[0]) * (px - P.xmax_dom[0]);
+    const double dyy = (py - P.xmin_dom[1]) * (py - P.xmax_dom[1]);
+    if (dxx > 0.0 || dyy > 0.0) h->if_out[i] = 1;
+    if (h->if_out[i]) continue;
+    xmn = std::fmin(xmn, px);
+    xmx = std::fmax(xmx, px);
+    ymn = std::fmin(ymn, py);
+    ymx = std::fmax(ymx, py);
+    hmx = std::fmax(hmx, h->hsml[i]);
+    hmn = std::fmin(hmn, h->hsml[i]);
+  }
+  const double bb[6] = {-xmn, -ymn, xmx, ymx, hmx, -hmn};  // the layout k_bbox_final writes (max-reducible)
+  std::memcpy(h->bb6, bb, sizeof(bb));
+}
+void emu_slice_widths(spsph_handle *h) {  // the warp-wide maxima at the end of k_count
+  for (int sl = 0; sl < h->nslices; ++sl) {
+    int m0 = 0, m1 = 0;
+    for (int l = 0; l < SLICE; ++l) {
+      m0 = std::max(m0, h->n0[sl * SLICE + l]);
+      m1 = std::max(m1, h->n1[sl * SLICE + l]);
+    }
+    const bool is_node = sl * SLICE < h->M.nnp;
+    h->wslice[sl] = m0 * SLICE;
+    h->wslice[h->nslices + sl] = is_node ? m1 * SLICE : 0;
+    h->wslice[2 * h->nslices + sl] = is_node ? 0 : m1 * SLICE;
+  }
+}
+#endif
+
 int build_neighbours(spsph_handle *h) {
-#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
+#ifdef SPSPH_HOST_EMU
+  if (h->emu_lists) return emu_import_lists(h);
+#endif
   const DevParams &P = h->P;
   const int n2 = P.ntotal2;
   const int TB = 256;
@@ -547,9 +660,13 @@ int build_neighbours(spsph_handle *h) {
   const int *lflag = h->dist ? h->lflag : nullptr;
   const LocalList LL = local_list(h, n2);
   const int GL = list_grid(h, n2, TB);
+#ifndef SPSPH_HOST_EMU
   k_domain_bbox<<<h->bbox_blocks, TB, 0, s>>>(P, h->x, h->hsml, h->if_out, lflag, LL, h->bbox_partial);
   mark(h, KID_BBOX);
   k_bbox_final<<<1, 32, 0, s>>>(h->bbox_blocks, h->bbox_partial, h->bb6);
+#else
+  emu_bbox(h);
+#endif
   if (h->dist)  // global grid bounds: the reference's cell grid (hence its pair order) is a global property
     NCCL_TRY(h->p_ncclAllReduce(h->bb6, h->bb6, 6, ncclDouble, ncclMax, h->comm, s));
   k_grid_params<<<1, 32, 0, s>>>(h->bb6, h->G, h->cell_capacity);
@@ -595,6 +712,9 @@ int build_neighbours(spsph_handle *h) {
     }
   }
   mark(h, KID_COUNT, h->dist ? 3 : 1);
+#ifdef SPSPH_HOST_EMU
+  emu_slice_widths(h);
+#endif
   launch_scan(h, h->wslice, h->oslice, 3, h->nslices, nullptr, h->nslices, h->scan_totals, KID_SCAN);
   if (h->dist)  // unified slots of local particles are the leading ones: scan only those
     launch_scan(h, h->nfwd_u, h->base_u, 1, n2, h->list_n + h->list_cur, 0, h->scan_totals + 3, KID_SCAN);
@@ -697,72 +817,6 @@ int build_neighbours(spsph_handle *h) {
   }
   mark(h, KID_FILL, h->dist ? 2 : 1);
   return 0;
-#else
-  // host emulation: the test harness hands over this step's sorted arrays and gather lists (built from the oracle's
-  // pair list in the layout k_count / k_fill write), see tests/test_step_emulation_cpu.py
-  const spsph_emu_lists *E = h->emu_lists;
-  if (!E) {
-    h->err = "host emulation: spsph_emu_set_lists must precede every spsph_step";
-    return 1;
-  }
-  h->emu_lists = nullptr;
-  const DevParams &P = h->P;
-  const size_t n2 = (size_t)P.ntotal2;
-  const int cnt[3] = {P.nnode, P.nstress, P.ndummy};
-  for (int sp = 0; sp < 3; ++sp) {
-    std::memcpy(h->order + sp * n2, E->order[sp], cnt[sp] * sizeof(int));
-    std::memcpy(h->scell + sp * n2, E->cell[sp], cnt[sp] * sizeof(int));
-    std::memcpy(h->spos + sp * n2, E->pos[sp], cnt[sp] * sizeof(double2));
-    std::memcpy(h->sh + sp * n2, E->h[sp], cnt[sp] * sizeof(double));
-  }
-  std::memcpy(h->pos_of, E->pos_of, n2 * sizeof(int));
-  for (int k = 0; k < 3; ++k) h->nloc[k] = cnt[k];
-  h->nloc_valid = true;
-  if (ensure_lists(h, E->tot0, E->totC, E->totD)) return 1;
-  const int T = h->M.nnp + h->M.nsp;
-  std::memcpy(h->n0, E->n0, T * sizeof(int));
-  std::memcpy(h->n1, E->n1, T * sizeof(int));
-  std::memcpy(h->oslice, E->off0, h->nslices * sizeof(int));
-  std::memcpy(h->oslice + h->nslices, E->offC, h->nslices * sizeof(int));
-  std::memcpy(h->oslice + 2 * h->nslices, E->offD, h->nslices * sizeof(int));
-  h->L.off0 = h->oslice;
-  h->L.offC = h->oslice + h->nslices;
-  h->L.offD = h->oslice + 2 * h->nslices;
-  for (long long a = 0; a < E->tot0; ++a) {
-    const int q = E->idx0[a];
-    h->L.idx0[a] = h->umor ? (q | ((int)h->mcls[q] << 30)) : q;
-    h->L.w0[a] = E->w0[a];
-    h->L.gx0[a] = E->gx0[a];
-    h->L.gy0[a] = E->gy0[a];
-    if (h->L.h0lo) {  // (m/rho)_partner * w, zero for wall partners (k_fill)
-      const double h0 = q >= P.ntotal ? 0.0 : h->mor[q] * (double)E->w0[a];
-      h->L.h0lo[a] = __double2loint(h0);
-      h->L.h0hi[a] = __double2hiint(h0);
-    }
-  }
-  for (long long a = 0; a < E->totC; ++a) {
-    h->L.idxC[a] = E->idxC[a];
-    h->L.wC[a] = E->wC[a];
-    h->L.gxC[a] = E->gxC[a];
-    h->L.gyC[a] = E->gyC[a];
-    h->L.xC[a] = E->xC[a];
-    h->L.yC[a] = E->yC[a];
-    if (h->L.hC) h->L.hC[a] = E->hC[a];
-  }
-  for (long long a = 0; a < E->totD; ++a) {
-    h->L.idxD[a] = E->idxD[a];
-    h->L.wD[a] = E->wD[a];
-  }
-  std::memcpy(h->bc_int, E->bc_int, P.nnode * sizeof(int));
-  std::memcpy(h->if_out, E->if_out, n2 * sizeof(int));
-  if (P.track_nint) std::memcpy(h->n_int, E->n_int, P.nnode * sizeof(float));
-  h->last_m_before = h->m_pairs;
-  h->last_n_pairs = E->n_pairs;
-  GrowthRule gr{E->growth_mode, 0, E->growth_ka, E->growth_kb};
-  *h->growth = gr;
-  if (E->n_pairs > h->m_pairs) h->m_pairs = E->n_pairs;
-  return 0;
-#endif  // SPSPH_HOST_EMU
 }
 
 // sweep A launches: the UMOR variants (uniform mass/rho per species, see k_sweep_a_sp) are chosen at run time
@@ -1105,15 +1159,11 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   rc |= dalloc(h, &h->which_cell, n2) | dalloc(h, &h->tmp_ids, 3 * n2) | dalloc(h, &h->order, 3 * n2);
   rc |= dalloc(h, &h->scell, 3 * n2) | dalloc(h, &h->pos_of, n2) | dalloc(h, &h->nout, 8) | dalloc(h, &h->bb6, 8);
   rc |= dalloc(h, &h->spos, 3 * n2) | dalloc(h, &h->sh, 3 * n2) | dalloc(h, &h->supos, 3 * n2);
-#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   rc |= dalloc(h, &h->scan_bsum, 4 * (size_t)SCAN_BLOCKS) | dalloc(h, &h->scan_totals, 8);
-#endif  // SPSPH_HOST_EMU
   const size_t T = (size_t)M.total();
   rc |= dalloc(h, &h->n0, T) | dalloc(h, &h->n1, T) | dalloc(h, &h->nall, T);
   rc |= dalloc(h, &h->nfwd_u, n2) | dalloc(h, &h->base_u, n2) | dalloc(h, &h->cand_overflow, 4);
-#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   rc |= dalloc(h, &h->cand0, (size_t)h->nslices * CAND_CAP * SLICE) | dalloc(h, &h->cand1, (size_t)h->nslices * CAND_CAP * SLICE);
-#endif  // SPSPH_HOST_EMU
   rc |= dalloc(h, &h->wslice, 3 * (size_t)h->nslices) | dalloc(h, &h->oslice, 3 * (size_t)h->nslices);
   rc |= dalloc(h, &h->growth, 1) | dalloc(h, &h->status_d, 1) | dalloc(h, &h->stats_d, 4);
   if (rc) return 1;
@@ -1386,7 +1436,6 @@ int spsph_download(spsph_handle *h, const spsph_state *s) {
 }
 
 int spsph_pair_stats(spsph_handle *h, int64_t *npairs, int32_t *maxiac, int32_t *miniac, int32_t *noiac) {
-#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   if (!h) return 1;
   CUDA_TRY(cudaSetDevice(h->device));
   const int init[4] = {0, 1000, 0, 0};
@@ -1395,7 +1444,11 @@ int spsph_pair_stats(spsph_handle *h, int64_t *npairs, int32_t *maxiac, int32_t 
   M.nn = h->nloc[0];
   M.ns = h->nloc[1];
   M.nd = h->nloc[2];
+#ifndef SPSPH_HOST_EMU
   k_pair_stats<<<148, 256, 0, h->stream>>>(M, h->nall, h->stats_d);
+#else
+  k_pair_stats<<<1, 1, 0, h->stream>>>(M, h->nall, h->stats_d);  // one thread sees everything: no warp reduction needed
+#endif
   int out[4];
   CUDA_TRY(cudaMemcpyAsync(out, h->stats_d, sizeof(out), cudaMemcpyDeviceToHost, h->stream));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -1404,14 +1457,10 @@ int spsph_pair_stats(spsph_handle *h, int64_t *npairs, int32_t *maxiac, int32_t 
   if (miniac) *miniac = out[1];
   if (noiac) *noiac = out[2];
   return 0;
-#else
-  return 1;
-#endif  // SPSPH_HOST_EMU
 }
 
 int spsph_pairs(spsph_handle *h, int64_t *npairs, int32_t *pair_i, int32_t *pair_j, int32_t *pint_type, float *w,
                 float *dwdx, float *dwdy) {
-#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   if (!h) return 1;
   const long long n = h->last_n_pairs;
   if (npairs) *npairs = n;
@@ -1448,9 +1497,6 @@ int spsph_pairs(spsph_handle *h, int64_t *npairs, int32_t *pair_i, int32_t *pair
   cudaFree(d_x);
   cudaFree(d_y);
   return 0;
-#else
-  return 1;
-#endif  // SPSPH_HOST_EMU
 }
 
 int spsph_dist_unique_id(char *id128) {

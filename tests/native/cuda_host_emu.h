@@ -28,6 +28,7 @@ static thread_local EmuDim emu_blockIdx, emu_blockDim, emu_threadIdx, emu_gridDi
 
 // ---- intrinsics -------------------------------------------------------------------------------------------------
 static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+static inline float __fmaf_rn(float a, float b, float c) { return std::fmaf(a, b, c); }
 static inline float __fsqrt_rn(float x) { return sqrtf(x); }
 static inline double __drcp_rn(double x) { return 1.0 / x; }
 static inline float __int_as_float(int v) {
@@ -67,6 +68,8 @@ template <class T>
 static inline T __shfl_sync(unsigned, T v, int, int = 32) { return v; }
 template <class T>
 static inline T __shfl_down_sync(unsigned, T v, int, int = 32) { return v; }
+template <class T>
+static inline T __shfl_up_sync(unsigned, T v, int, int = 32) { return v; }
 static inline int __any_sync(unsigned, int p) { return p != 0; }
 static inline int __all_sync(unsigned, int p) { return p != 0; }
 static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }

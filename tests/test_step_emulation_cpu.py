@@ -260,3 +260,43 @@ def test_emulated_step_matches_oracle(emu_engine, tmp_path, label, variant, spec
     final = run_lockstep(emu_engine, prob, nsteps, (1, 2, nsteps), label)
     if label.startswith("sl_"):
         assert (final["internal_vars"][prob.params.nnode:prob.params.ntotal, 0] > 0).sum() >= 5, "no plastic flow reached"
+
+
+def run_standalone(emu_engine, prob, nsteps, check_at, label, pairs_at=()):
+    """the emulated engine on its own: the neighbour build runs too (k_cell_id, k_scatter, k_rank, k_count, k_fill /
+    k_fill_scan, k_growth_threshold thread by thread; bounding box, prefix scans and slice widths by host loops)"""
+    from oracle_binding import Oracle
+    p = prob.params
+    dt = prob.blocks[0]["dt"]
+    orc = Oracle(prob)
+    eng = emu_engine.Engine(prob)
+    t = 0.0
+    for step in range(1, nsteps + 1):
+        orc.step(step, t, dt)
+        eng.step(step, t, dt)
+        t = t + dt
+        if step in pairs_at:
+            pa, pb = eng.pairs(), orc.pairs()
+            assert len(pa["pair_i"]) == len(pb["pair_i"]), f"{label}, step {step}: pair count"
+            for f in ("pair_i", "pair_j", "pint_type"):
+                assert np.array_equal(pa[f], pb[f]), f"{label}, step {step}: {f} differs"
+            for f in ("w", "dwdx", "dwdy"):
+                assert np.array_equal(pa[f].view(np.uint32), pb[f].view(np.uint32)), f"{label}, step {step}: {f} differs"
+            assert eng.pair_stats() == orc.pair_stats()
+        if step in check_at:
+            a, b = eng.download(), orc.download()
+            for k in STATE_KEYS:
+                x, y = a[k], b[k]
+                if k in ("x", "vel", "stress"):
+                    x, y = x[:p.ntotal], y[:p.ntotal]
+                assert np.array_equal(x, y), (f"{label}, step {step}: {k} differs from the oracle in "
+                                              f"{int((x != y).sum())} entries")
+    eng.close()
+
+
+def test_emulated_engine_standalone_bui(emu_engine, tmp_path):
+    import spsph
+    from spsph import decks
+    decks.write_deck(str(tmp_path), decks.bui_spec(dx=0.2, maxtimestep=1000))
+    prob = spsph.load(str(tmp_path), "bui")
+    run_standalone(emu_engine, prob, 6, (1, 2, 6), "Bui column, dx = 0.2, stand-alone", pairs_at=(1, 2, 3))
