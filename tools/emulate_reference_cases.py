@@ -4,7 +4,10 @@ at their full resolution and step count, in lockstep with the oracle (which supp
 the emulated engine's frames with the goldens of the reference's own executables -- the GPU parity test of
 tests/test_gpu_reference.py without a GPU (everything but the neighbour build and CUDA's libm).
 
-    python tools/emulate_reference_cases.py [case ...]        default: every case the emulation supports
+    python tools/emulate_reference_cases.py [--standalone] [case ...]     default: every case the emulation supports
+
+--standalone: the emulated engine builds its own neighbour lists (the complete device path; no list is imported from
+the oracle, which then only serves as a progress check); otherwise the oracle supplies each step's pair list.
 """
 import ctypes as C
 import os
@@ -35,7 +38,11 @@ class _Factory:
 def main():
     gen = T.emu_engine.__wrapped__(_Factory())  # the fixture's generator: builds the emulated engine library
     E = next(gen)
-    cases = sys.argv[1:] or [c for c in CASES if not c.endswith("_long") and not c.startswith("bui_inside") and c != "bui_full"]
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    standalone = "--standalone" in sys.argv
+    skip = (lambda c: False) if standalone else (
+        lambda c: c.endswith("_long") or c.startswith("bui_inside") or c == "bui_full")
+    cases = args or [c for c in CASES if not skip(c)]
     L = lib()
     L.oracle_debug_grid.restype = None
     bad = 0
@@ -54,6 +61,12 @@ def main():
         frames = [int(s) for s in g["steps"]]
         try:
             for step in range(1, frames[-1] + 1):
+                if standalone:
+                    eng.step(step, t, dt)
+                    t = t + dt
+                    if step in frames:
+                        compare_with_golden(case, g, step, eng.download(), p, "emulated CUDA engine (stand-alone)")
+                    continue
                 before = orc.download()
                 orc.step(step, t, dt)
                 L.oracle_debug_grid(C.c_void_p(orc.h), cells.ctypes.data_as(C.c_void_p), C.byref(mb), C.byref(npairs))
