@@ -117,9 +117,13 @@ static inline cudaError_t emu_ok() { return cudaSuccess; }
 #define cudaSetDevice(d) emu_ok()
 #define cudaGetLastError() emu_ok()
 #define cudaGetErrorString(e) "emulated"
+// cudaMalloc does not initialise: SPSPH_EMU_POISON=1 fills fresh "device" memory with 0xFF bytes (NaN as a double or a
+// float, -1 as an int) so that a kernel reading memory nobody wrote shows up in the parity tests (an initcheck)
 template <class T>
 static inline cudaError_t emu_malloc(T **p, size_t n) {
-  *p = (T *)std::calloc(n ? n : 1, 1);
+  static const bool poison = std::getenv("SPSPH_EMU_POISON") != nullptr;
+  *p = (T *)std::malloc(n ? n : 1);
+  if (*p) std::memset((void *)*p, poison ? 0xFF : 0, n ? n : 1);
   return *p ? cudaSuccess : cudaErrorMemoryAllocation;
 }
 #define cudaMalloc(p, n) emu_malloc(p, n)
