@@ -300,3 +300,22 @@ def test_emulated_engine_standalone_bui(emu_engine, tmp_path):
     decks.write_deck(str(tmp_path), decks.bui_spec(dx=0.2, maxtimestep=1000))
     prob = spsph.load(str(tmp_path), "bui")
     run_standalone(emu_engine, prob, 6, (1, 2, 6), "Bui column, dx = 0.2, stand-alone", pairs_at=(1, 2, 3))
+
+
+TINY = [("vs_2x2", "vs", lambda d: d.vertical_slope_spec(dx=10.0, maxtimestep=100), 30),
+        ("vs_3x3", "vs", lambda d: d.vertical_slope_spec(dx=5.0, maxtimestep=100), 30),
+        ("bui_3x2", "bui", lambda d: d.bui_spec(dx=2.0, maxtimestep=100), 50),
+        ("bui_5x3_inside_sp3", "bui", lambda d: d.bui_spec(dx=1.0, maxtimestep=100, mode="inside", npoints=3), 40),
+        ("bui_5x3_standard", "bui", lambda d: d.bui_spec(dx=1.0, maxtimestep=100, mode="standard"), 40),
+        ("sl_3x5", "sl", lambda d: d.strain_localisation_spec(dx=0.25, maxtimestep=100), 50)]
+
+
+@pytest.mark.parametrize("label,variant,spec_fn,nsteps", TINY, ids=[c[0] for c in TINY])
+def test_emulated_engine_tiny_problems(emu_engine, tmp_path, label, variant, spec_fn, nsteps):
+    """ragged edge of the layout: 4 - 45 particles, i.e. one partly filled 32-particle slice per species, list rows
+    shorter than one streaming group, cells with a single particle"""
+    import spsph
+    from spsph import decks
+    decks.write_deck(str(tmp_path), spec_fn(decks))
+    prob = spsph.load(str(tmp_path), variant)
+    run_standalone(emu_engine, prob, nsteps, (1, nsteps), label, pairs_at=(1, 2))
