@@ -47,11 +47,11 @@ def test_oracle_reproduces_reference_binary(case, tmp_path):
     import spsph
     from spsph import decks
     from oracle_binding import Oracle
-    if case == "bui_full" and not os.environ.get("SPSPH_FULL_RUNS"):
-        # 16 650 steps of the serial oracle take ~4 minutes: outside the default CPU suite (which runs the complete
-        # vertical-slope and strain-localisation problems). SPSPH_FULL_RUNS=1 runs it (done for every change of the
-        # oracle, result recorded in DESIGN.md); the GPU suite always does (tests/test_zz_gpu_new_paths.py).
-        pytest.skip("set SPSPH_FULL_RUNS=1 for the 16 650-step Bui run on the CPU oracle")
+    if case in ("bui_full", "sl_full") and not os.environ.get("SPSPH_FULL_RUNS"):
+        # 16 650 / 2 092 steps of the serial oracle take 5 / 1 minutes: outside the default CPU suite (which runs the
+        # complete vertical-slope problem). SPSPH_FULL_RUNS=1 runs them (done for every change of the oracle, result
+        # recorded in DESIGN.md); the GPU suite always does (tests/test_zz_gpu_new_paths.py).
+        pytest.skip("set SPSPH_FULL_RUNS=1 for the complete Bui and strain-localisation runs on the CPU oracle")
     g = np.load(golden_path(case))
     variant, spec = spec_of(case)
     assert str(g["variant"]) == variant
