@@ -421,3 +421,13 @@ def test_restart_needs_the_list_capacity(tmp_path):
         got = b.download()
         same = all(np.array_equal(ref[k], got[k]) for k in ("x", "vel", "stress", "internal_vars", "f_drucker"))
         assert same == restore
+
+
+def test_product_library_has_no_emulation_code():
+    """the host emulation (tests/native/) is test infrastructure: the product library is the nvcc build and carries
+    none of the SPSPH_HOST_EMU alternatives"""
+    import subprocess
+    so = os.path.join(ROOT, "stress-particle-sph_b200", "libspsph_cuda.so")
+    syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
+    assert "spsph_step" in syms
+    assert "emu" not in syms.lower()
