@@ -37,6 +37,9 @@ using namespace spsph;
     }                                                                                             \
   } while (0)
 
+#if defined(SPSPH_HOST_EMU) && !defined(SPSPH_EMU_SIMT)
+#define SPSPH_EMU_SERIAL 1  // threads run one after the other: cooperative kernels are replaced by host loops
+#endif
 #ifdef SPSPH_HOST_EMU
 // what build_neighbours produces on the device, handed over by the host-emulation harness instead (arrays of the
 // caller, read during the next spsph_step): species-sorted arrays, warp-sliced ELL lists, growth rule
@@ -431,7 +434,7 @@ int ensure_lists(spsph_handle *h, long long t0, long long tC, long long tD) {
 // exclusive scan of `rows` rows of int32 (stride elements apart) over n = *n_ptr + n_add elements each
 void launch_scan(spsph_handle *h, const int *in, int *out, int rows, int stride, const int *n_ptr, int n_add,
                  long long *totals, int kid) {
-#ifndef SPSPH_HOST_EMU
+#ifndef SPSPH_EMU_SERIAL
   dim3 g(SCAN_BLOCKS, rows);
   k_scan_reduce<<<g, SCAN_THREADS, 0, h->stream>>>(in, stride, n_ptr, n_add, h->scan_bsum);
   k_scan_sums<<<rows, SCAN_THREADS, 0, h->stream>>>(h->scan_bsum, totals);
@@ -660,7 +663,7 @@ int build_neighbours(spsph_handle *h) {
   const int *lflag = h->dist ? h->lflag : nullptr;
   const LocalList LL = local_list(h, n2);
   const int GL = list_grid(h, n2, TB);
-#ifndef SPSPH_HOST_EMU
+#ifndef SPSPH_EMU_SERIAL
   k_domain_bbox<<<h->bbox_blocks, TB, 0, s>>>(P, h->x, h->hsml, h->if_out, lflag, LL, h->bbox_partial);
   mark(h, KID_BBOX);
   k_bbox_final<<<1, 32, 0, s>>>(h->bbox_blocks, h->bbox_partial, h->bb6);
@@ -712,7 +715,7 @@ int build_neighbours(spsph_handle *h) {
     }
   }
   mark(h, KID_COUNT, h->dist ? 3 : 1);
-#ifdef SPSPH_HOST_EMU
+#ifdef SPSPH_EMU_SERIAL
   emu_slice_widths(h);
 #endif
   launch_scan(h, h->wslice, h->oslice, 3, h->nslices, nullptr, h->nslices, h->scan_totals, KID_SCAN);
@@ -1444,7 +1447,7 @@ int spsph_pair_stats(spsph_handle *h, int64_t *npairs, int32_t *maxiac, int32_t 
   M.nn = h->nloc[0];
   M.ns = h->nloc[1];
   M.nd = h->nloc[2];
-#ifndef SPSPH_HOST_EMU
+#ifndef SPSPH_EMU_SERIAL
   k_pair_stats<<<148, 256, 0, h->stream>>>(M, h->nall, h->stats_d);
 #else
   k_pair_stats<<<1, 1, 0, h->stream>>>(M, h->nall, h->stats_d);  // one thread sees everything: no warp reduction needed

@@ -140,6 +140,13 @@ __device__ __forceinline__ void cp_async_wait() {
   asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory");
 }
 
+#else
+inline unsigned long long l2_policy_evict_first() { return 0; }
+inline unsigned long long l2_policy_evict_last() { return 0; }
+inline void cp_async16(void *smem, const void *gmem, unsigned long long) { std::memcpy(smem, gmem, 16); }
+inline void cp_async_commit() {}
+template <int N>
+inline void cp_async_wait() {}
 #endif  // SPSPH_HOST_EMU
 // NARR arrays of 4-byte entries are streamed (array 0 holds the partner ids). `rows` is the slice width
 // (warp-uniform), `cnt` the calling lane's own list length. gather(q) -> R fetches the partner record (q < 0:
@@ -150,7 +157,7 @@ __device__ __forceinline__ void cp_async_wait() {
 // does compute() unless RAWQ asks for the stored word (sweep A, which turns the class into the factor (m/rho)*w).
 constexpr int QCLASS_SHIFT = 30;
 constexpr int QID_MASK = (1 << QCLASS_SHIFT) - 1;
-#ifndef SPSPH_HOST_EMU  // device only (the host emulation of tests/native/ has its own version)
+#if !defined(SPSPH_HOST_EMU) || defined(SPSPH_EMU_SIMT)  // device, and the lockstep (SIMT) host emulation
 template <int NARR, int NG, class R, int GR = ELL_GROUP, int SUB = ELL_SUB, bool RAWQ = false, class GatherF,
           class ComputeF>
 __device__ __forceinline__ void ell_stream(const int *const *arr, size_t slice_off, int rows, int cnt, int *smw,

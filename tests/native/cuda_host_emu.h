@@ -61,6 +61,7 @@ template <class T>
 static inline T __ldcs(const T *p) { return *p; }
 template <class T>
 static inline T __ldg(const T *p) { return *p; }
+#ifndef SPSPH_EMU_SIMT
 // one lane at a time: a warp-wide operation sees only the calling lane
 template <class T>
 static inline T __shfl_xor_sync(unsigned, T v, int, int = 32) { return v; }
@@ -75,6 +76,115 @@ static inline int __all_sync(unsigned, int p) { return p != 0; }
 static inline unsigned __ballot_sync(unsigned, int p) { return p ? 1u : 0u; }
 static inline void __syncwarp(unsigned = 0xffffffffu) {}
 static inline void __syncthreads() {}
+#else
+// ---- SIMT mode (SPSPH_EMU_SIMT): the threads of a block are fibers (ucontext) that switch at every warp / block
+// collective, so shuffles, votes, __syncwarp and __syncthreads have their real meaning; blocks still run one after
+// the other. A collective is: deposit my value, warp barrier, read the other lanes, warp barrier.
+#include <ucontext.h>
+#include <vector>
+struct EmuBlock {
+  int nthreads = 0, cur = -1;
+  std::vector<ucontext_t> ctx;
+  std::vector<char> done;
+  std::vector<char *> stack;
+  ucontext_t sched;
+  // warp barriers: arrivals and generation per warp; block barrier likewise
+  int warr[64] = {0}, wgen[64] = {0}, walive[64] = {0};
+  int barr = 0, bgen = 0, balive = 0;
+  uint64_t wbuf[64][32];
+};
+static EmuBlock emu_blk;
+static inline void emu_yield() { swapcontext(&emu_blk.ctx[emu_blk.cur], &emu_blk.sched); }
+static inline int emu_tid() { return emu_blk.cur; }
+static inline void emu_warp_barrier() {
+  const int w = emu_tid() >> 5;
+  const int gen = emu_blk.wgen[w];
+  if (++emu_blk.warr[w] >= emu_blk.walive[w]) {
+    emu_blk.warr[w] = 0;
+    ++emu_blk.wgen[w];
+    return;
+  }
+  while (emu_blk.wgen[w] == gen) emu_yield();
+}
+static inline void emu_block_barrier() {
+  const int gen = emu_blk.bgen;
+  if (++emu_blk.barr >= emu_blk.balive) {
+    emu_blk.barr = 0;
+    ++emu_blk.bgen;
+    return;
+  }
+  while (emu_blk.bgen == gen) emu_yield();
+}
+// a thread that returns leaves its warp and block: barriers waiting for it must be released
+static inline void emu_thread_exit() {
+  const int w = emu_tid() >> 5;
+  --emu_blk.walive[w];
+  --emu_blk.balive;
+  if (emu_blk.walive[w] > 0 && emu_blk.warr[w] >= emu_blk.walive[w]) {
+    emu_blk.warr[w] = 0;
+    ++emu_blk.wgen[w];
+  }
+  if (emu_blk.balive > 0 && emu_blk.barr >= emu_blk.balive) {
+    emu_blk.barr = 0;
+    ++emu_blk.bgen;
+  }
+}
+template <class T>
+static inline uint64_t emu_bits(T v) {
+  uint64_t u = 0;
+  std::memcpy(&u, &v, sizeof(T));
+  return u;
+}
+template <class T>
+static inline T emu_from_bits(uint64_t u) {
+  T v;
+  std::memcpy(&v, &u, sizeof(T));
+  return v;
+}
+// exchange: every lane deposits v; returns the value of lane `src` (own value if src is out of range or that lane has
+// exited, as the hardware returns an undefined value there and the kernels never use it)
+template <class T>
+static inline T emu_exchange(T v, int src) {
+  const int w = emu_tid() >> 5, lane = emu_tid() & 31;
+  emu_blk.wbuf[w][lane] = emu_bits(v);
+  emu_warp_barrier();
+  const int t = (w << 5) + src;
+  T r = v;
+  if (src >= 0 && src < 32 && t < emu_blk.nthreads && !emu_blk.done[t]) r = emu_from_bits<T>(emu_blk.wbuf[w][src]);
+  emu_warp_barrier();
+  return r;
+}
+template <class T>
+static inline T __shfl_xor_sync(unsigned, T v, int m, int = 32) { return emu_exchange(v, (emu_tid() & 31) ^ m); }
+template <class T>
+static inline T __shfl_sync(unsigned, T v, int src, int = 32) { return emu_exchange(v, src & 31); }
+template <class T>
+static inline T __shfl_down_sync(unsigned, T v, int d, int = 32) {
+  const int lane = emu_tid() & 31;
+  return emu_exchange(v, lane + d < 32 ? lane + d : lane);
+}
+template <class T>
+static inline T __shfl_up_sync(unsigned, T v, int d, int = 32) {
+  const int lane = emu_tid() & 31;
+  return emu_exchange(v, lane - d >= 0 ? lane - d : lane);
+}
+static inline unsigned __ballot_sync(unsigned, int p) {
+  const int w = emu_tid() >> 5, lane = emu_tid() & 31;
+  emu_blk.wbuf[w][lane] = p ? 1 : 0;
+  emu_warp_barrier();
+  unsigned m = 0;
+  for (int l = 0; l < 32; ++l) {
+    const int t = (w << 5) + l;
+    if (t < emu_blk.nthreads && !emu_blk.done[t] && emu_blk.wbuf[w][l]) m |= 1u << l;
+  }
+  emu_warp_barrier();
+  return m;
+}
+static inline int __any_sync(unsigned m, int p) { return __ballot_sync(m, p) != 0; }
+static inline int __all_sync(unsigned m, int p) { return __ballot_sync(m, !p) == 0; }
+static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_barrier(); }
+static inline void __syncthreads() { emu_block_barrier(); }
+#endif
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
 template <class T>
 static inline T atomicAdd(T *p, T v) {
@@ -97,6 +207,7 @@ static inline T atomicMin(T *p, T v) {
 using std::max;
 using std::min;
 
+#ifndef SPSPH_EMU_SIMT
 // ---- kernel launch: k<<<grid, block, smem, stream>>>(args) is rewritten to emu_launch(grid, block, k, args) ----------
 template <class K, class... A>
 static inline void emu_launch(unsigned grid, unsigned block, K kernel, A... args) {
@@ -109,6 +220,62 @@ static inline void emu_launch(unsigned grid, unsigned block, K kernel, A... args
       kernel(args...);
     }
 }
+
+#else
+// ---- kernel launch, SIMT mode: one fiber per thread of the block, round-robin between collectives --------------------
+#include <functional>
+static std::function<void()> emu_thread_body;
+static void emu_fiber_entry() {
+  emu_thread_body();
+  emu_blk.done[emu_blk.cur] = 1;
+  emu_thread_exit();
+  swapcontext(&emu_blk.ctx[emu_blk.cur], &emu_blk.sched);
+}
+static inline void emu_run_block(unsigned block) {
+  constexpr size_t STACK = 256 * 1024;
+  EmuBlock &B = emu_blk;
+  B.nthreads = (int)block;
+  if (B.ctx.size() < block) {
+    B.ctx.resize(block);
+    B.done.resize(block);
+    while (B.stack.size() < block) B.stack.push_back((char *)std::malloc(STACK));
+  }
+  for (int w = 0; w < 64; ++w) B.warr[w] = B.wgen[w] = B.walive[w] = 0;
+  B.barr = B.bgen = 0;
+  B.balive = (int)block;
+  for (unsigned t = 0; t < block; ++t) {
+    B.done[t] = 0;
+    ++B.walive[t >> 5];
+    getcontext(&B.ctx[t]);
+    B.ctx[t].uc_stack.ss_sp = B.stack[t];
+    B.ctx[t].uc_stack.ss_size = STACK;
+    B.ctx[t].uc_link = nullptr;
+    makecontext(&B.ctx[t], emu_fiber_entry, 0);
+  }
+  int remaining = (int)block;
+  while (remaining > 0) {
+    remaining = 0;
+    for (unsigned t = 0; t < block; ++t) {
+      if (B.done[t]) continue;
+      B.cur = (int)t;
+      emu_threadIdx = EmuDim{t, 0, 0};
+      swapcontext(&B.sched, &B.ctx[t]);
+      if (!B.done[t]) ++remaining;
+    }
+  }
+}
+template <class K, class... A>
+static inline void emu_launch(dim3 grid, unsigned block, K kernel, A... args) {
+  emu_gridDim = EmuDim{grid.x, grid.y, 1};
+  emu_blockDim = EmuDim{block, 1, 1};
+  emu_thread_body = [&]() { kernel(args...); };
+  for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned bx = 0; bx < grid.x; ++bx) {
+      emu_blockIdx = EmuDim{bx, by, 0};
+      emu_run_block(block);
+    }
+}
+#endif
 
 // ---- runtime: device memory is host memory ---------------------------------------------------------------------------
 #ifdef SPSPH_EMU_RUNTIME

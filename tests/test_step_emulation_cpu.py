@@ -36,6 +36,19 @@ class EmuLists(C.Structure):
                 ("bc_int", C.c_void_p), ("n_int", C.c_void_p), ("if_out", C.c_void_p)]
 
 
+def _build_emulated(d, extra=()):
+    cpp, so = str(d / "engine_host.cpp"), str(d / "libspsph_emu.so")
+    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "native", "make_engine_host.py"),
+                    os.path.join(ROOT, "stress-particle-sph_b200", "csrc", "spsph_engine.cu"), cpp], check=True,
+                   stdout=subprocess.DEVNULL)
+    r = subprocess.run(["g++", "-O1", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared", "-w",
+                        "-D__noinline__=", *extra, "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "tests", "native"),
+                        "-I" + os.path.join(ROOT, "stress-particle-sph_b200", "csrc"), "-I" + os.path.join(ROOT, "include"),
+                        "-o", so, cpp, "-ldl"], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    return so
+
+
 @pytest.fixture(scope="module")
 def emu_engine(tmp_path_factory):
     """spsph.Engine bound to the host-emulated build of the CUDA engine"""
@@ -319,3 +332,24 @@ def test_emulated_engine_tiny_problems(emu_engine, tmp_path, label, variant, spe
     decks.write_deck(str(tmp_path), spec_fn(decks))
     prob = spsph.load(str(tmp_path), variant)
     run_standalone(emu_engine, prob, nsteps, (1, nsteps), label, pairs_at=(1, 2))
+
+
+@pytest.mark.skipif(not os.environ.get("SPSPH_EMU_SIMT"), reason="set SPSPH_EMU_SIMT=1: lockstep (SIMT) emulation, ~25 s per step")
+def test_emulated_engine_simt_mode(tmp_path_factory, tmp_path):
+    """-DSPSPH_EMU_SIMT: the threads of a block are fibers that switch at every warp / block collective, so the device
+    code runs with NO host replacement except the inline PTX (cp.async = memcpy, 256-bit loads / stores): the real
+    ell_stream ring (cp.async groups, tail rows, __syncwarp), shuffles, votes, block scans, the bounding-box reduction,
+    the slice-width maxima of k_count and k_pair_stats. Slow (the fixed grids of the scans create ~2.6 M fibers per
+    step whatever the problem size), hence opt-in; broader runs: DESIGN.md section 7."""
+    import spsph
+    import spsph.engine as E
+    from spsph import decks
+    so = _build_emulated(tmp_path_factory.mktemp("emu_simt"), ("-DSPSPH_EMU_SIMT",))
+    saved = (E._lib, E._CUDA_SO)
+    E._lib, E._CUDA_SO = None, so
+    try:
+        decks.write_deck(str(tmp_path), decks.bui_spec(dx=0.2, maxtimestep=1000))
+        prob = spsph.load(str(tmp_path), "bui")
+        run_standalone(E, prob, 3, (1, 3), "Bui column, dx = 0.2, SIMT emulation", pairs_at=(1, 2))
+    finally:
+        E._lib, E._CUDA_SO = saved
