@@ -80,21 +80,48 @@ static inline void __syncthreads() {}
 // ---- SIMT mode (SPSPH_EMU_SIMT): the threads of a block are fibers (ucontext) that switch at every warp / block
 // collective, so shuffles, votes, __syncwarp and __syncthreads have their real meaning; blocks still run one after
 // the other. A collective is: deposit my value, warp barrier, read the other lanes, warp barrier.
-#include <ucontext.h>
 #include <vector>
+#if !defined(__x86_64__)
+#error "the SIMT emulation switches fibers with a few lines of x86-64 assembly"
+#endif
+// fiber switch: callee-saved registers and the stack pointer (ucontext's swapcontext costs two signal-mask system
+// calls per switch, which made a time step take 25 s)
+extern "C" void emu_switch(void **save_sp, void *load_sp);
+asm(R"(
+.text
+.globl emu_switch
+.type emu_switch,@function
+emu_switch:
+  pushq %rbp
+  pushq %rbx
+  pushq %r12
+  pushq %r13
+  pushq %r14
+  pushq %r15
+  movq %rsp, (%rdi)
+  movq %rsi, %rsp
+  popq %r15
+  popq %r14
+  popq %r13
+  popq %r12
+  popq %rbx
+  popq %rbp
+  ret
+.size emu_switch,.-emu_switch
+)");
 struct EmuBlock {
   int nthreads = 0, cur = -1;
-  std::vector<ucontext_t> ctx;
+  std::vector<void *> sp;  // saved stack pointer of every fiber
   std::vector<char> done;
   std::vector<char *> stack;
-  ucontext_t sched;
+  void *sched_sp = nullptr;
   // warp barriers: arrivals and generation per warp; block barrier likewise
   int warr[64] = {0}, wgen[64] = {0}, walive[64] = {0};
   int barr = 0, bgen = 0, balive = 0;
   uint64_t wbuf[64][32];
 };
 static EmuBlock emu_blk;
-static inline void emu_yield() { swapcontext(&emu_blk.ctx[emu_blk.cur], &emu_blk.sched); }
+static inline void emu_yield() { emu_switch(&emu_blk.sp[emu_blk.cur], emu_blk.sched_sp); }
 static inline int emu_tid() { return emu_blk.cur; }
 static inline void emu_warp_barrier() {
   const int w = emu_tid() >> 5;
@@ -229,14 +256,15 @@ static void emu_fiber_entry() {
   emu_thread_body();
   emu_blk.done[emu_blk.cur] = 1;
   emu_thread_exit();
-  swapcontext(&emu_blk.ctx[emu_blk.cur], &emu_blk.sched);
+  emu_switch(&emu_blk.sp[emu_blk.cur], emu_blk.sched_sp);  // never resumed
+  __builtin_trap();
 }
 static inline void emu_run_block(unsigned block) {
   constexpr size_t STACK = 256 * 1024;
   EmuBlock &B = emu_blk;
   B.nthreads = (int)block;
-  if (B.ctx.size() < block) {
-    B.ctx.resize(block);
+  if (B.sp.size() < block) {
+    B.sp.resize(block);
     B.done.resize(block);
     while (B.stack.size() < block) B.stack.push_back((char *)std::malloc(STACK));
   }
@@ -246,11 +274,14 @@ static inline void emu_run_block(unsigned block) {
   for (unsigned t = 0; t < block; ++t) {
     B.done[t] = 0;
     ++B.walive[t >> 5];
-    getcontext(&B.ctx[t]);
-    B.ctx[t].uc_stack.ss_sp = B.stack[t];
-    B.ctx[t].uc_stack.ss_size = STACK;
-    B.ctx[t].uc_link = nullptr;
-    makecontext(&B.ctx[t], emu_fiber_entry, 0);
+    // initial frame: six callee-saved registers, the entry address emu_switch "returns" to, a fake return address
+    // (the entry function then sees the stack alignment of an ordinary call)
+    uintptr_t top = ((uintptr_t)B.stack[t] + STACK) & ~(uintptr_t)15;
+    void **f = (void **)top;
+    *--f = nullptr;
+    *--f = (void *)&emu_fiber_entry;
+    for (int r = 0; r < 6; ++r) *--f = nullptr;
+    B.sp[t] = (void *)f;
   }
   int remaining = (int)block;
   while (remaining > 0) {
@@ -259,7 +290,7 @@ static inline void emu_run_block(unsigned block) {
       if (B.done[t]) continue;
       B.cur = (int)t;
       emu_threadIdx = EmuDim{t, 0, 0};
-      swapcontext(&B.sched, &B.ctx[t]);
+      emu_switch(&B.sched_sp, B.sp[t]);
       if (!B.done[t]) ++remaining;
     }
   }

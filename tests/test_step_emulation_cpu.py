@@ -334,22 +334,34 @@ def test_emulated_engine_tiny_problems(emu_engine, tmp_path, label, variant, spe
     run_standalone(emu_engine, prob, nsteps, (1, nsteps), label, pairs_at=(1, 2))
 
 
-@pytest.mark.skipif(not os.environ.get("SPSPH_EMU_SIMT"), reason="set SPSPH_EMU_SIMT=1: lockstep (SIMT) emulation, ~25 s per step")
-def test_emulated_engine_simt_mode(tmp_path_factory, tmp_path):
+SIMT_CASES = [("bui", "bui", lambda: _bui(), 5),
+              ("bui_inside_sp2", "bui", lambda: _bui(mode="inside", npoints=2), 4),
+              ("bui_sml15", "bui", lambda: _bui(sml=1.5), 3),
+              ("bui_out_domain", "bui", lambda: _bui(domain=[-10, -10, 4.00001, 41]), 4),
+              ("vs", "vs", lambda: _vs(), 4),
+              ("sl_sigman_xsph", "sl", lambda: _sl(free_right=True, ifsigman=1, xsph=True, yield0=5.e3), 4)]
+
+
+@pytest.fixture(scope="module")
+def emu_engine_simt(tmp_path_factory):
+    so = _build_emulated(tmp_path_factory.mktemp("emu_simt"), ("-DSPSPH_EMU_SIMT",))
+    import spsph.engine as E
+    saved = (E._lib, E._CUDA_SO)
+    E._lib, E._CUDA_SO = None, so
+    E.cuda_lib()
+    yield E
+    E._lib, E._CUDA_SO = saved
+
+
+@pytest.mark.parametrize("label,variant,spec_fn,nsteps", SIMT_CASES, ids=[c[0] for c in SIMT_CASES])
+def test_emulated_engine_simt_mode(emu_engine_simt, tmp_path, label, variant, spec_fn, nsteps):
     """-DSPSPH_EMU_SIMT: the threads of a block are fibers that switch at every warp / block collective, so the device
     code runs with NO host replacement except the inline PTX (cp.async = memcpy, 256-bit loads / stores): the real
     ell_stream ring (cp.async groups, tail rows, __syncwarp), shuffles, votes, block scans, the bounding-box reduction,
-    the slice-width maxima of k_count and k_pair_stats. Slow (the fixed grids of the scans create ~2.6 M fibers per
-    step whatever the problem size), hence opt-in; broader runs: DESIGN.md section 7."""
+    the slice-width maxima of k_count and k_pair_stats. About 1.5 s per step whatever the problem size (the fixed grids
+    of the scans and reductions create ~1.5 M fibers per step)."""
     import spsph
-    import spsph.engine as E
     from spsph import decks
-    so = _build_emulated(tmp_path_factory.mktemp("emu_simt"), ("-DSPSPH_EMU_SIMT",))
-    saved = (E._lib, E._CUDA_SO)
-    E._lib, E._CUDA_SO = None, so
-    try:
-        decks.write_deck(str(tmp_path), decks.bui_spec(dx=0.2, maxtimestep=1000))
-        prob = spsph.load(str(tmp_path), "bui")
-        run_standalone(E, prob, 3, (1, 3), "Bui column, dx = 0.2, SIMT emulation", pairs_at=(1, 2))
-    finally:
-        E._lib, E._CUDA_SO = saved
+    decks.write_deck(str(tmp_path), spec_fn())
+    prob = spsph.load(str(tmp_path), variant)
+    run_standalone(emu_engine_simt, prob, nsteps, (1, nsteps), label + ", SIMT emulation", pairs_at=(1, 2))

@@ -29,4 +29,11 @@ for case, n in (("bui", 30), ("vs", 20), ("sl", 5), ("bui_inside_sp1", 20), ("bu
     print("asan:", case, n, "steps clean", flush=True)
 PY
 LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0 python "$tmp/run.py"
+# 1b. the same under the lockstep (SIMT) emulation: the real cp.async list streaming (which reads whole groups of rows,
+#     i.e. past the end of a slice into the allocation slack), shuffles and block scans
+g++ -O1 -g -fsanitize=address -fno-omit-frame-pointer -ffp-contract=off -fno-fast-math -std=c++17 -fPIC -shared -w \
+    -DSPSPH_EMU_SIMT -D__noinline__= -I/usr/local/cuda/include -I"$root/tests/native" \
+    -I"$root/stress-particle-sph_b200/csrc" -I"$root/include" -o "$tmp/libspsph_asan.so" "$tmp/engine_host.cpp" -ldl
+sed -i 's/("bui", 30), ("vs", 20), ("sl", 5), ("bui_inside_sp1", 20), ("bui_standard", 10), ("sl_sigman_xsph", 10),/("bui", 4), ("vs", 4), ("bui_inside_sp1", 4), ("sl_sigman_xsph", 3),/; s/("bui_cont_density", 8), ("bui_art_stress", 6), ("bui_sml15", 6), ("bui_out_domain", 30), ("bui_long", 310)):/("bui_sml15", 3), ("bui_out_domain", 4)):/' "$tmp/run.py"
+LD_PRELOAD=$(gcc -print-file-name=libasan.so) ASAN_OPTIONS=detect_leaks=0:detect_stack_use_after_return=0 python "$tmp/run.py"
 SPSPH_EMU_POISON=1 python -m pytest "$root/tests/test_engine_emulated_reference_cpu.py" -q -x
