@@ -264,6 +264,15 @@ EMU_CASES = [
 ]
 
 
+# the default suite runs a representative third (the stand-alone and reference-golden tests cover every option again);
+# SPSPH_EMU_ALL=1 runs all of them
+_DEFAULT = {"bui", "bui_outside_sp3", "bui_plane_stress", "bui_out_domain", "bui_art_stress", "bui_cont_density", "vs",
+            "vs_sigman", "sl_tresca", "sl_mohr_coulomb", "sl_vm_expflow", "sl_sigman_xsph", "sl_cont_density_sle2",
+            "shipped_bui"}
+if not os.environ.get("SPSPH_EMU_ALL"):
+    EMU_CASES = [c for c in EMU_CASES if c[0] in _DEFAULT]
+
+
 @pytest.mark.parametrize("label,variant,spec_fn,nsteps", EMU_CASES, ids=[c[0] for c in EMU_CASES])
 def test_emulated_step_matches_oracle(emu_engine, tmp_path, label, variant, spec_fn, nsteps):
     import spsph
@@ -337,8 +346,6 @@ def test_emulated_engine_tiny_problems(emu_engine, tmp_path, label, variant, spe
 SIMT_CASES = [("bui", "bui", lambda: _bui(), 5),
               ("bui_inside_sp2", "bui", lambda: _bui(mode="inside", npoints=2), 4),
               ("bui_sml15", "bui", lambda: _bui(sml=1.5), 3),
-              ("bui_out_domain", "bui", lambda: _bui(domain=[-10, -10, 4.00001, 41]), 4),
-              ("vs", "vs", lambda: _vs(), 4),
               ("sl_sigman_xsph", "sl", lambda: _sl(free_right=True, ifsigman=1, xsph=True, yield0=5.e3), 4)]
 
 
