@@ -826,16 +826,16 @@ int build_neighbours(spsph_handle *h) {
 #define SPSPH_LAUNCH_A_SP(FIRST, FROMB, GRID, STREAM, ST, DOBC)                                                       \
   do {                                                                                                               \
     if (h->umor)                                                                                                     \
-      k_sweep_a_sp<FIRST, FROMB, true><<<GRID, 128, 0, STREAM>>>(P, M, ord_s, h->L, h->n0, ST, adapt, DOBC, h->pal_node); \
+      k_sweep_a_sp<FIRST, FROMB, true><<<GRID, SWEEP_T, 0, STREAM>>>(P, M, ord_s, h->L, h->n0, ST, adapt, DOBC, h->pal_node); \
     else                                                                                                             \
-      k_sweep_a_sp<FIRST, FROMB, false><<<GRID, 128, 0, STREAM>>>(P, M, ord_s, h->L, h->n0, ST, adapt, DOBC, h->pal_node); \
+      k_sweep_a_sp<FIRST, FROMB, false><<<GRID, SWEEP_T, 0, STREAM>>>(P, M, ord_s, h->L, h->n0, ST, adapt, DOBC, h->pal_node); \
   } while (0)
 #define SPSPH_LAUNCH_A_NODE(FIRST, FROMB, EPSP, GRID, STREAM, ST, DOBC)                                                      \
   do {                                                                                                                      \
     if (h->umor)                                                                                                            \
-      k_sweep_a_node<FIRST, FROMB, EPSP, true><<<GRID, 128, 0, STREAM>>>(P, M, ord_n, h->L, h->n0, ST, adapt, DOBC, h->pal_sp); \
+      k_sweep_a_node<FIRST, FROMB, EPSP, true><<<GRID, SWEEP_T, 0, STREAM>>>(P, M, ord_n, h->L, h->n0, ST, adapt, DOBC, h->pal_sp); \
     else                                                                                                                    \
-      k_sweep_a_node<FIRST, FROMB, EPSP, false><<<GRID, 128, 0, STREAM>>>(P, M, ord_n, h->L, h->n0, ST, adapt, DOBC, h->pal_sp); \
+      k_sweep_a_node<FIRST, FROMB, EPSP, false><<<GRID, SWEEP_T, 0, STREAM>>>(P, M, ord_n, h->L, h->n0, ST, adapt, DOBC, h->pal_sp); \
   } while (0)
 
 int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
@@ -854,15 +854,16 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   M.nn = h->nloc[0];
   M.ns = h->nloc[1];
   const int *lflag = h->dist ? h->lflag : nullptr;
-  const int GN = (M.nn + 127) / 128, GS = (M.ns + 127) / 128, GB = (M.nnp + M.nsp + 127) / 128;
+  const int GN = (M.nn + 127) / 128, GB = (M.nnp + M.nsp + 127) / 128;
+  const int GNW = (M.nn + SWEEP_T - 1) / SWEEP_T, GSW = (M.ns + SWEEP_T - 1) / SWEEP_T;  // pair-sum kernels
   const int adapt = P.adapt, bc = p.no_bcs > 0 ? 1 : 0;
   const int *ord_n = S.order[0], *ord_s = S.order[1];
   bool first_a = true;
   // SPH_shift block, main:99-109: format B -> the other format-B buffer set
   if (p.sph_shift && itimestep > 1 && ((itimestep - 1) % p.shift_update == 0)) {
     const StatePtrs sw = state_ptrs(h, 1 - h->cur);
-    SPSPH_LAUNCH_A_SP(true, true, GS, s, sw, 0);
-    SPSPH_LAUNCH_A_NODE(true, true, true, GN, s, sw, 0);
+    SPSPH_LAUNCH_A_SP(true, true, GSW, s, sw, 0);
+    SPSPH_LAUNCH_A_NODE(true, true, true, GNW, s, sw, 0);
     if (p.cont_density) k_commit_node_rho<<<GN, 128, 0, s>>>(P, M, ord_n, sw);
     mark(h, KID_SWEEPA, 2);
     h->cur = 1 - h->cur;
@@ -903,12 +904,12 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     } else {
       fork();
       if (first_a || cd) {
-        SPSPH_LAUNCH_A_SP(true, false, GS, s, st, bc);
-        SPSPH_LAUNCH_A_NODE(true, false, false, GN, s2, st, bc);
+        SPSPH_LAUNCH_A_SP(true, false, GSW, s, st, bc);
+        SPSPH_LAUNCH_A_NODE(true, false, false, GNW, s2, st, bc);
         if (cd) k_commit_node_rho<<<GN, 128, 0, s>>>(P, M, ord_n, st);
       } else {
-        SPSPH_LAUNCH_A_SP(false, false, GS, s, st, bc);
-        SPSPH_LAUNCH_A_NODE(false, false, false, GN, s2, st, bc);
+        SPSPH_LAUNCH_A_SP(false, false, GSW, s, st, bc);
+        SPSPH_LAUNCH_A_NODE(false, false, false, GNW, s2, st, bc);
       }
       join();
     }
@@ -920,9 +921,9 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     fork();
     if (artv) {
       if (h->uniform_h)
-        k_artvisc<true><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n1, st, h->h_uniform);
+        k_artvisc<true><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, h->n1, st, h->h_uniform);
       else
-        k_artvisc<false><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n1, st, 0.f);
+        k_artvisc<false><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, h->n1, st, 0.f);
     }
     if (p.art_stress) {  // main:746
       k_art_force_prep<<<GN, 128, 0, s2>>>(P, M, ord_n, st);
@@ -930,14 +931,14 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     }
     const double f2n = last ? 0.0 : f2rk[stg + 1];
     if (cd) {  // the node side reads the stress particles' density before their side integrates it
-      k_sweep_b_node<true><<<GN, 128, 0, s>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
-      k_sweep_b_sp<true><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last, f2n);
+      k_sweep_b_node<true><<<GNW, SWEEP_T, 0, s>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
+      k_sweep_b_sp<true><<<GSW, SWEEP_T, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last, f2n);
     } else if (stg == 0) {
-      k_sweep_b_sp<true><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last, f2n);
-      k_sweep_b_node<true><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
+      k_sweep_b_sp<true><<<GSW, SWEEP_T, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last, f2n);
+      k_sweep_b_node<true><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
     } else {
-      k_sweep_b_sp<false><<<GS, 128, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last, f2n);
-      k_sweep_b_node<false><<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
+      k_sweep_b_sp<false><<<GSW, SWEEP_T, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last, f2n);
+      k_sweep_b_node<false><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
     }
     join();
     mark(h, KID_SWEEPB, artv ? 3 : 2);
@@ -948,12 +949,12 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   } else {
     fork();
     if (cd) {
-      SPSPH_LAUNCH_A_SP(true, false, GS, s, st, bc);
-      SPSPH_LAUNCH_A_NODE(true, false, true, GN, s, st, bc);
+      SPSPH_LAUNCH_A_SP(true, false, GSW, s, st, bc);
+      SPSPH_LAUNCH_A_NODE(true, false, true, GNW, s, st, bc);
       k_commit_node_rho<<<GN, 128, 0, s>>>(P, M, ord_n, st);
     } else {
-      SPSPH_LAUNCH_A_SP(false, false, GS, s, st, bc);
-      SPSPH_LAUNCH_A_NODE(false, false, true, GN, s2, st, bc);
+      SPSPH_LAUNCH_A_SP(false, false, GSW, s, st, bc);
+      SPSPH_LAUNCH_A_NODE(false, false, true, GNW, s2, st, bc);
     }
     join();
   }

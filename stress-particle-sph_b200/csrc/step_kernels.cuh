@@ -109,6 +109,11 @@ constexpr int UNR = 4;  // list entries in flight per thread
 #ifndef SPSPH_MINB
 #define SPSPH_MINB 4      // min resident blocks per SM requested from ptxas for the sweep kernels
 #endif
+#ifndef SPSPH_SWEEP_T
+#define SPSPH_SWEEP_T 128  // threads per block of the five pair-sum kernels (tools/variant_timing.sh times 64 x 8 blocks)
+#endif
+constexpr int SWEEP_T = SPSPH_SWEEP_T;
+static_assert(SWEEP_T % 32 == 0 && SWEEP_T >= 32 && SWEEP_T <= 256, "whole warps; each warp owns its ring in shared memory");
 constexpr int ELL_GROUP = 4;  // rows per cp.async group
 #ifndef SPSPH_ELL_SUB
 #define SPSPH_ELL_SUB 4
@@ -359,7 +364,7 @@ __device__ __forceinline__ double palette_value(const MorPalette &p, unsigned c)
   return c == 0 ? p.v0 : (c == 1 ? p.v1 : (c == 2 ? p.v2 : p.v3));
 }
 template <bool FIRST, bool FROMB, bool UMOR>
-__global__ void __launch_bounds__(128, SPSPH_MINB)
+__global__ void __launch_bounds__(SWEEP_T, SPSPH_MINB)
 k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L, const int *__restrict__ n0,
              StatePtrs st, int do_adapt, int do_bc, MorPalette mor_u) {
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;  // species-sorted index of the stress particle
@@ -385,7 +390,7 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   double vtx = 0.0, vty = 0.0, nrm = 0.0;
   {
     constexpr int NARR = UMOR ? 2 : (FIRST ? 4 : 3);
-    __shared__ __align__(16) int smem[4 * ELL_SMEM_G(NARR, A_NG, A_GR)];
+    __shared__ __align__(16) int smem[(SWEEP_T / 32) * ELL_SMEM_G(NARR, A_NG, A_GR)];
     const int *arrs[4] = {L.idx0, UMOR ? reinterpret_cast<const int *>(L.w0) : L.h0lo, L.h0hi,
                           reinterpret_cast<const int *>(L.w0)};
     const double *__restrict__ NAv = st.NA;
@@ -455,7 +460,7 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
 }
 
 template <bool FIRST, bool FROMB, bool EPSP, bool UMOR>
-__global__ void __launch_bounds__(128, SPSPH_MINB)
+__global__ void __launch_bounds__(SWEEP_T, SPSPH_MINB)
 k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n0,
                StatePtrs st, int do_adapt, int do_bc, MorPalette mor_u) {
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -484,7 +489,7 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
       double2 mr;
     };
     constexpr int NARR = UMOR ? 2 : (FIRST ? 4 : 3);
-    __shared__ __align__(16) int smem[4 * ELL_SMEM_G(NARR, A_NG, A_GR)];
+    __shared__ __align__(16) int smem[(SWEEP_T / 32) * ELL_SMEM_G(NARR, A_NG, A_GR)];
     const int *arrs[4] = {L.idx0, UMOR ? reinterpret_cast<const int *>(L.w0) : L.h0lo, L.h0hi,
                           reinterpret_cast<const int *>(L.w0)};
     ell_stream<NARR, A_NG, RecS, A_GR, A_GR, UMOR>(
@@ -574,7 +579,7 @@ __global__ void k_commit_node_rho(DevParams P, SlotMap M, const int *__restrict_
 // next-stage predictor, or the final RK4 update when `last`): format B -> format A.
 // ------------------------------------------------------------------------------------------------------
 template <bool FIRST>
-__global__ void __launch_bounds__(128, SPSPH_MINB)
+__global__ void __launch_bounds__(SWEEP_T, SPSPH_MINB)
 k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L, const int *__restrict__ n0,
              StatePtrs st, double f1next, double f2, int last, double f2next) {
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -635,7 +640,7 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
       }
     };
   {
-    __shared__ __align__(16) int smem[4 * ELL_SMEM(3, ELL_NG)];
+    __shared__ __align__(16) int smem[(SWEEP_T / 32) * ELL_SMEM(3, ELL_NG)];
     const int *arrs[3] = {L.idx0, reinterpret_cast<const int *>(L.gx0), reinterpret_cast<const int *>(L.gy0)};
     ell_stream<3, ELL_NG, Rec4>(
         arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(3, ELL_NG),
@@ -785,7 +790,7 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
 // UH: one smoothing length for every particle (host-checked at upload): h = 0.5*(h_i + h_j) is that constant and
 // is not streamed (24 instead of 28 bytes per entry).
 template <bool UH>
-__global__ void __launch_bounds__(128, SPSPH_MINB)
+__global__ void __launch_bounds__(SWEEP_T, SPSPH_MINB)
 k_artvisc(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n1, StatePtrs st,
           float h_u) {
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -802,7 +807,7 @@ k_artvisc(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, c
   float acc1 = 0.f, acc2 = 0.f;
   constexpr int NG = 3;
   constexpr int NARR = UH ? 5 : 6;
-  __shared__ __align__(16) int smem[4 * ELL_SMEM(NARR, NG)];
+  __shared__ __align__(16) int smem[(SWEEP_T / 32) * ELL_SMEM(NARR, NG)];
   const int *arrs[6] = {L.idxC, reinterpret_cast<const int *>(L.gxC), reinterpret_cast<const int *>(L.gyC),
                         reinterpret_cast<const int *>(L.xC), reinterpret_cast<const int *>(L.yC),
                         reinterpret_cast<const int *>(L.hC)};
@@ -845,7 +850,7 @@ k_artvisc(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, c
 }
 
 template <bool FIRST>
-__global__ void __launch_bounds__(128, SPSPH_MINB)
+__global__ void __launch_bounds__(SWEEP_T, SPSPH_MINB)
 k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n0,
                StatePtrs st, double f1next, double f2, int last) {
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -901,7 +906,7 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
       a32 = a32 - mq * (gy * c3);
     };
   {
-    __shared__ __align__(16) int smem[4 * ELL_SMEM(3, ELL_NG)];
+    __shared__ __align__(16) int smem[(SWEEP_T / 32) * ELL_SMEM(3, ELL_NG)];
     const int *arrs[3] = {L.idx0, reinterpret_cast<const int *>(L.gx0), reinterpret_cast<const int *>(L.gy0)};
     ell_stream<3, ELL_NG, Rec4>(
         arrs, (size_t)L.off0[sl], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(3, ELL_NG),

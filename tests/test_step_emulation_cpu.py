@@ -372,3 +372,26 @@ def test_emulated_engine_simt_mode(emu_engine_simt, tmp_path, label, variant, sp
     decks.write_deck(str(tmp_path), spec_fn())
     prob = spsph.load(str(tmp_path), variant)
     run_standalone(emu_engine_simt, prob, nsteps, (1, nsteps), label + ", SIMT emulation", pairs_at=(1, 2))
+
+
+@pytest.fixture(scope="module")
+def emu_engine_simt_t64(tmp_path_factory):
+    so = _build_emulated(tmp_path_factory.mktemp("emu_simt_t64"), ("-DSPSPH_EMU_SIMT", "-DSPSPH_SWEEP_T=64", "-DSPSPH_MINB=8"))
+    import spsph.engine as E
+    saved = (E._lib, E._CUDA_SO)
+    E._lib, E._CUDA_SO = None, so
+    E.cuda_lib()
+    yield E
+    E._lib, E._CUDA_SO = saved
+
+
+@pytest.mark.parametrize("label,variant,spec_fn,nsteps", SIMT_CASES[::3], ids=[c[0] for c in SIMT_CASES[::3]])
+def test_emulated_engine_simt_mode_64_thread_sweeps(emu_engine_simt_t64, tmp_path, label, variant, spec_fn, nsteps):
+    """the build-time variant tools/variant_timing.sh times on the GPU (-DSPSPH_SWEEP_T=64: the pair-sum kernels in
+    64-thread blocks, two streaming rings per block) gives the same bits: block size is a scheduling choice only"""
+    import spsph
+    from spsph import decks
+    decks.write_deck(str(tmp_path), spec_fn())
+    prob = spsph.load(str(tmp_path), variant)
+    run_standalone(emu_engine_simt_t64, prob, nsteps, (1, nsteps), label + ", SIMT emulation, 64-thread sweeps",
+                   pairs_at=(1,))
