@@ -5,7 +5,9 @@
 #    process per test id so that a crash in one cannot hide the others;
 # 2. the verified GPU suite (-x as the round driver runs it);
 # 3. the default bench line and the reference arm;
-# 4. the ncu launch list of one step (shares per kernel).
+# 4. the ncu launch list of one step (shares per kernel);
+# 5. the build-time variants of the pair-sum kernels (tools/variant_timing.sh; run `bash tools/variant_timing.sh build`
+#    in the development container first so that the variant libraries travel with the snapshot).
 # Everything lands in gpurun_out/first/.
 out=gpurun_out/first
 mkdir -p $out
@@ -24,4 +26,5 @@ tail -c 1500 $out/bench.json
 timeout 900 python bench.py --impl reference --steps 10 --warmup 1 > $out/bench_reference.json 2> $out/bench_reference.err
 ncu --metrics gpu__time_duration.sum --clock-control none -s 49 -c 60 --csv --log-file $out/launches.csv \
     python tools/run_steps.py --steps 2 > $out/launch_run.log 2>&1
-cat $out/new_paths_summary.txt
+bash tools/variant_timing.sh $out/variants > $out/variants.log 2>&1
+cat $out/new_paths_summary.txt $out/variants/summary.txt
