@@ -118,6 +118,9 @@ constexpr int ELL_GROUP = 4;  // rows per cp.async group
 #ifndef SPSPH_ELL_SUB
 #define SPSPH_ELL_SUB 4
 #endif
+#ifndef SPSPH_ELL_PIPE
+#define SPSPH_ELL_PIPE 0  // 1: software-pipelined gathers in ell_stream (variant, see there)
+#endif
 constexpr int ELL_SUB = SPSPH_ELL_SUB;  // entries gathered + consumed together (in flight per thread)
 constexpr int ELL_NG = 4;     // groups in the ring (16 rows = 2 KB per array per warp in flight)
 
@@ -185,6 +188,58 @@ __device__ __forceinline__ void ell_stream(const int *const *arr, size_t slice_o
   };
 #pragma unroll
   for (int g = 0; g < NG; ++g) issue(g);
+#if SPSPH_ELL_PIPE
+  // Variant (tools/variant_timing.sh): the partner records of part s+1 are gathered BEFORE part s is consumed, so the
+  // gather latency overlaps the pair arithmetic inside one warp as well (the sweeps run at 16 warps per SM and wait on
+  // these gathers ~45 % of the time). Same entries, same order, same arithmetic: bit-identical results.
+  static_assert(NG >= 2, "the next group has to be resident while the current one is consumed");
+  constexpr int NS = GR / SUB;  // parts per group
+  const int nsub = ng * NS;
+  int qn[SUB];
+  R nxt[SUB];
+  auto fetch = [&](int sidx) {
+    const int g = sidx / NS, hh = sidx % NS;
+    const int *sl = smw + ((g % NG) * NARR) * (GR * 32);
+#pragma unroll
+    for (int u = 0; u < SUB; ++u) {
+      const int raw = sl[(hh * SUB + u) * 32 + lane];
+      qn[u] = RAWQ ? raw : (raw & QID_MASK);
+      nxt[u] = gather((g * GR + hh * SUB + u) < cnt ? (raw & QID_MASK) : -1);
+    }
+  };
+  cp_async_wait<NG - 1>();
+  __syncwarp();
+  fetch(0);
+  for (int sidx = 0; sidx < nsub; ++sidx) {
+    const int g = sidx / NS, hh = sidx % NS;
+    int q[SUB], pay[NARR > 1 ? NARR - 1 : 1][SUB];
+    R cur[SUB];
+#pragma unroll
+    for (int u = 0; u < SUB; ++u) {
+      q[u] = qn[u];
+      cur[u] = nxt[u];
+    }
+    if (sidx + 1 < nsub) {
+      if (hh == NS - 1) {  // the next part opens group g+1: NG+g groups are committed, g+2 of them must have landed
+        cp_async_wait<NG - 2>();
+        __syncwarp();
+      }
+      fetch(sidx + 1);
+    }
+    const int *sl = smw + ((g % NG) * NARR) * (GR * 32);
+#pragma unroll
+    for (int a = 1; a < NARR; ++a)
+#pragma unroll
+      for (int u = 0; u < SUB; ++u) pay[a - 1][u] = sl[a * (GR * 32) + (hh * SUB + u) * 32 + lane];
+    compute(q, pay, cur, cnt - g * GR - hh * SUB);
+    if (hh == NS - 1) {
+      __syncwarp();
+      issue(g + NG);
+    }
+  }
+  cp_async_wait<0>();
+  return;
+#endif
   for (int g = 0; g < ng; ++g) {
     cp_async_wait<NG - 1>();
     __syncwarp();
@@ -245,6 +300,10 @@ __device__ __forceinline__ int warp_max_i(int v) {
 #ifndef SPSPH_A_NG
 #define SPSPH_A_NG 4
 #endif
+#ifndef SPSPH_A_SUB
+#define SPSPH_A_SUB SPSPH_A_GR
+#endif
+constexpr int A_SUB = SPSPH_A_SUB;  // sweep A: entries gathered + consumed together
 constexpr int A_GR = SPSPH_A_GR, A_NG = SPSPH_A_NG;  // sweep A: rows per group (all in flight per thread), ring depth
 
 // state format conversions at the boundary of the time loop ---------------------------------------------
@@ -400,7 +459,7 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
     struct RecN {
       double2 v, mr;
     };
-    ell_stream<NARR, A_NG, RecN, A_GR, A_GR, UMOR>(
+    ell_stream<NARR, A_NG, RecN, A_GR, A_SUB, UMOR>(
         arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM_G(NARR, A_NG, A_GR),
         [&](int q) {
           const int qq = (q < 0 || q >= P.nnode) ? 0 : q;
@@ -415,9 +474,9 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
           }
           return o;
         },
-        [&](const int(&q)[A_GR], const int(&pay)[NARR - 1][A_GR], const RecN(&r)[A_GR], int nvalid) {
+        [&](const int(&q)[A_SUB], const int(&pay)[NARR - 1][A_SUB], const RecN(&r)[A_SUB], int nvalid) {
 #pragma unroll
-          for (int u = 0; u < A_GR; ++u) {
+          for (int u = 0; u < A_SUB; ++u) {
             const int qid = UMOR ? (q[u] & QID_MASK) : q[u];
             const bool ok = (u < nvalid) && (qid < P.nnode);  // dummy partners (type 9) take no part
             double h2;  // (mass(i)/rho(i))*w, main:431
@@ -492,7 +551,7 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
     __shared__ __align__(16) int smem[(SWEEP_T / 32) * ELL_SMEM_G(NARR, A_NG, A_GR)];
     const int *arrs[4] = {L.idx0, UMOR ? reinterpret_cast<const int *>(L.w0) : L.h0lo, L.h0hi,
                           reinterpret_cast<const int *>(L.w0)};
-    ell_stream<NARR, A_NG, RecS, A_GR, A_GR, UMOR>(
+    ell_stream<NARR, A_NG, RecS, A_GR, A_SUB, UMOR>(
         arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM_G(NARR, A_NG, A_GR),
         [&](int q) {
           const int qs = (q < 0 || q >= P.ntotal) ? 0 : q - P.nnode;
@@ -502,9 +561,9 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
           r.mr = FIRST ? st.mrho[qs + P.nnode] : make_double2(0.0, 0.0);
           return r;
         },
-        [&](const int(&q)[A_GR], const int(&pay)[NARR - 1][A_GR], const RecS(&r)[A_GR], int nvalid) {
+        [&](const int(&q)[A_SUB], const int(&pay)[NARR - 1][A_SUB], const RecS(&r)[A_SUB], int nvalid) {
 #pragma unroll
-          for (int u = 0; u < A_GR; ++u) {
+          for (int u = 0; u < A_SUB; ++u) {
             const int qid = UMOR ? (q[u] & QID_MASK) : q[u];
             const bool ok = (u < nvalid) && (qid < P.ntotal);  // dummy partners (type 6) take no part
             double h1;  // (mass(j)/rho(j))*w, main:430

@@ -27,7 +27,7 @@ def _built(tmp_path_factory):
                         os.path.join(ROOT, "stress-particle-sph_b200", "csrc", "spsph_engine.cu"), cpp], check=True,
                        stdout=subprocess.DEVNULL)
         subprocess.run(["g++", "-O1", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared", "-w",
-                        "-D__noinline__=", "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "tests", "native"),
+                        "-D__noinline__=", "-fno-gnu-unique", "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "tests", "native"),
                         "-I" + os.path.join(ROOT, "stress-particle-sph_b200", "csrc"), "-I" + os.path.join(ROOT, "include"),
                         "-o", so, cpp, "-ldl"], check=True)
         import spsph.engine as E

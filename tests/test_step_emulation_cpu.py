@@ -42,7 +42,7 @@ def _build_emulated(d, extra=()):
                     os.path.join(ROOT, "stress-particle-sph_b200", "csrc", "spsph_engine.cu"), cpp], check=True,
                    stdout=subprocess.DEVNULL)
     r = subprocess.run(["g++", "-O1", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared", "-w",
-                        "-D__noinline__=", *extra, "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "tests", "native"),
+                        "-D__noinline__=", "-fno-gnu-unique", *extra, "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "tests", "native"),
                         "-I" + os.path.join(ROOT, "stress-particle-sph_b200", "csrc"), "-I" + os.path.join(ROOT, "include"),
                         "-o", so, cpp, "-ldl"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -58,7 +58,7 @@ def emu_engine(tmp_path_factory):
                     os.path.join(ROOT, "stress-particle-sph_b200", "csrc", "spsph_engine.cu"), cpp], check=True,
                    stdout=subprocess.DEVNULL)
     r = subprocess.run(["g++", "-O1", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared", "-w",
-                        "-D__noinline__=", "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "tests", "native"),
+                        "-D__noinline__=", "-fno-gnu-unique", "-I/usr/local/cuda/include", "-I" + os.path.join(ROOT, "tests", "native"),
                         "-I" + os.path.join(ROOT, "stress-particle-sph_b200", "csrc"), "-I" + os.path.join(ROOT, "include"),
                         "-o", so, cpp, "-ldl"], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr[-3000:]
@@ -374,9 +374,15 @@ def test_emulated_engine_simt_mode(emu_engine_simt, tmp_path, label, variant, sp
     run_standalone(emu_engine_simt, prob, nsteps, (1, nsteps), label + ", SIMT emulation", pairs_at=(1, 2))
 
 
-@pytest.fixture(scope="module")
-def emu_engine_simt_t64(tmp_path_factory):
-    so = _build_emulated(tmp_path_factory.mktemp("emu_simt_t64"), ("-DSPSPH_EMU_SIMT", "-DSPSPH_SWEEP_T=64", "-DSPSPH_MINB=8"))
+VARIANT_FLAGS = {"t64": ("-DSPSPH_SWEEP_T=64", "-DSPSPH_MINB=8"),
+                 "pipe2": ("-DSPSPH_ELL_PIPE=1", "-DSPSPH_ELL_SUB=2", "-DSPSPH_A_SUB=2"),
+                 "pipe4_t32": ("-DSPSPH_ELL_PIPE=1", "-DSPSPH_SWEEP_T=32", "-DSPSPH_MINB=16")}
+
+
+@pytest.fixture(scope="module", params=list(VARIANT_FLAGS))
+def emu_engine_simt_variant(request, tmp_path_factory):
+    so = _build_emulated(tmp_path_factory.mktemp("emu_simt_" + request.param),
+                         ("-DSPSPH_EMU_SIMT",) + VARIANT_FLAGS[request.param])
     import spsph.engine as E
     saved = (E._lib, E._CUDA_SO)
     E._lib, E._CUDA_SO = None, so
@@ -386,12 +392,14 @@ def emu_engine_simt_t64(tmp_path_factory):
 
 
 @pytest.mark.parametrize("label,variant,spec_fn,nsteps", SIMT_CASES[::3], ids=[c[0] for c in SIMT_CASES[::3]])
-def test_emulated_engine_simt_mode_64_thread_sweeps(emu_engine_simt_t64, tmp_path, label, variant, spec_fn, nsteps):
-    """the build-time variant tools/variant_timing.sh times on the GPU (-DSPSPH_SWEEP_T=64: the pair-sum kernels in
-    64-thread blocks, two streaming rings per block) gives the same bits: block size is a scheduling choice only"""
+def test_emulated_engine_simt_mode_build_variants(emu_engine_simt_variant, tmp_path, label, variant, spec_fn, nsteps):
+    """the build-time variants tools/variant_timing.sh times on the GPU give the same bits on the SIMT emulation, where the
+    real ell_stream runs: 64- / 32-thread blocks for the pair-sum kernels (block size is a scheduling choice only) and
+    the software-pipelined gathers (-DSPSPH_ELL_PIPE=1: partner records of the next part requested before the current
+    part is consumed -- same entries, same order)"""
     import spsph
     from spsph import decks
     decks.write_deck(str(tmp_path), spec_fn())
     prob = spsph.load(str(tmp_path), variant)
-    run_standalone(emu_engine_simt_t64, prob, nsteps, (1, nsteps), label + ", SIMT emulation, 64-thread sweeps",
+    run_standalone(emu_engine_simt_variant, prob, nsteps, (1, nsteps), label + ", SIMT emulation, build variant",
                    pairs_at=(1,))

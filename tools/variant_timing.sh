@@ -13,7 +13,10 @@ VARIANTS=(
   "t64:-DSPSPH_SWEEP_T=64 -DSPSPH_MINB=8"      # same 16 warps per SM, finer tail
   "t32:-DSPSPH_SWEEP_T=32 -DSPSPH_MINB=16"     # one warp per block
   "t64m10:-DSPSPH_SWEEP_T=64 -DSPSPH_MINB=10"  # 20 warps per SM, 102 registers (spills: see the ptxas log)
-  "sub2:-DSPSPH_ELL_SUB=2"                     # two entries in flight per thread instead of four
+  "sub2:-DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2"     # two entries in flight per thread instead of four (80-120 registers)
+  "pipe2:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2"  # software-pipelined gathers: 2 consumed + 2 in flight
+  "pipe2t64:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_SWEEP_T=64 -DSPSPH_MINB=8"
+  "pipe2ng6:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_A_NG=6"
 )
 build_one() {
   local name=$1 flags=$2
