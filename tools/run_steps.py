@@ -17,15 +17,19 @@ ap.add_argument("--ncol", type=int, default=1632)
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--profile", action="store_true")
 ap.add_argument("--warmup", type=int, default=0)
+ap.add_argument("--deck", default=None, help="directory to write the deck into, reused when it already holds one")
 a = ap.parse_args()
-d = tempfile.mkdtemp()
+d = a.deck or tempfile.mkdtemp()
+reuse = bool(a.deck) and os.path.isdir(d) and len(os.listdir(d)) > 0
+os.makedirs(d, exist_ok=True)
 if a.kind == "refined_bui":
     spec, var = decks.refined_bui_spec(ncol=a.ncol), "bui"
 elif a.kind == "wide_slope":
     spec, var = decks.wide_slope_spec(ncol=a.ncol), "vs"
 else:
     spec, var = decks.SHIPPED[a.kind](), a.kind
-decks.write_deck(d, spec)
+if not reuse:
+    decks.write_deck(d, spec)
 prob = spsph.load(d, var)
 eng = spsph.Engine(prob)
 dt = prob.blocks[0]["dt"]

@@ -41,7 +41,7 @@ for v in "${VARIANTS[@]}"; do
   [ -f $so ] || continue
   SPSPH_CUDA_SO=$so timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/parity_$name.log 2>&1
   echo "$name parity exit $?" | tee -a $out/summary.txt
-  SPSPH_CUDA_SO=$so timeout 600 python tools/run_steps.py --warmup 3 --steps 10 --profile > $out/profile_$name.log 2>&1
+  SPSPH_CUDA_SO=$so timeout 600 python tools/run_steps.py --deck /tmp/spsph_variant_deck --warmup 3 --steps 10 --profile > $out/profile_$name.log 2>&1
   head -1 $out/profile_$name.log | tee -a $out/summary.txt
 done
 cat $out/summary.txt
