@@ -16,6 +16,7 @@ VARIANTS=(
   "sub2:-DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2"     # two entries in flight per thread instead of four (80-120 registers)
   "pipe2:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2"  # software-pipelined gathers: 2 consumed + 2 in flight
   "pipe2t64:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_SWEEP_T=64 -DSPSPH_MINB=8"
+  "pipe2a4:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2"   # sweep A (little arithmetic per entry) with 4 consumed + 4 in flight
   "pipe2ng6:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_A_NG=6"
 )
 build_one() {
