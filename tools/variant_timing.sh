@@ -17,6 +17,8 @@ VARIANTS=(
   "pipe2:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2"  # software-pipelined gathers: 2 consumed + 2 in flight
   "pipe2t64:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_SWEEP_T=64 -DSPSPH_MINB=8"
   "pipe2a4:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2"   # sweep A (little arithmetic per entry) with 4 consumed + 4 in flight
+  "sub2m5:-DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_MINB=5"   # 20 warps per SM at 96 registers, 0-28 B of spills
+  "pipe2m5:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_MINB=5"  # same, pipelined (32-80 B of spills in sweep B)
   "pipe2ng6:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_A_NG=6"
 )
 build_one() {
