@@ -18,6 +18,7 @@ VARIANTS=(
   "pipe2t64:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_SWEEP_T=64 -DSPSPH_MINB=8"
   "pipe2a4:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2"   # sweep A (little arithmetic per entry) with 4 consumed + 4 in flight
   "sub2m5:-DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_MINB=5"   # 20 warps per SM at 96 registers, 0-28 B of spills
+  "sub2m6:-DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_MINB=6"   # 24 warps per SM at 80 registers, 16-124 B of spills
   "pipe2m5:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_MINB=5"  # same, pipelined (32-80 B of spills in sweep B)
   "pipe2ng6:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_A_NG=6"
 )
