@@ -38,10 +38,13 @@ fi
 out=${1:-gpurun_out/variants}
 mkdir -p $out $vdir
 python __graft_entry__.py > $out/build.log 2>&1
+for v in "${VARIANTS[@]}"; do  # libraries that did not travel with the snapshot: built here, all at once
+  [ -f $vdir/libspsph_cuda_${v%%:*}.so ] || build_one "${v%%:*}" "${v#*:}" &
+done
+wait
 for v in "${VARIANTS[@]}"; do
   name=${v%%:*}
   so=$PWD/$vdir/libspsph_cuda_$name.so
-  [ -f $so ] || build_one "$name" "${v#*:}"
   [ -f $so ] || continue
   SPSPH_CUDA_SO=$so timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/parity_$name.log 2>&1
   echo "$name parity exit $?" | tee -a $out/summary.txt
