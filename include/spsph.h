@@ -138,6 +138,10 @@ int spsph_local_counts(spsph_handle *h, int32_t *nloc3);
  * in which order the next steps walk their pairs. spsph_upload resets it to 0 (a fresh run);
  * restoring the value read at the checkpoint makes the restarted run continue bit for bit. */
 int spsph_get_list_capacity(spsph_handle *h, int64_t *m_pairs);
+/* diagnostics: how many steps since spsph_create ran on the cell-tile kernels (acceptance masks + staged partner
+ * tiles) and how many on the id-list kernels (steps in which the reference's pair list grows, and option
+ * combinations the tile kernels do not cover). Both paths give bit-identical results. */
+int spsph_path_counts(spsph_handle *h, int64_t *tile_steps, int64_t *list_steps);
 int spsph_set_list_capacity(spsph_handle *h, int64_t m_pairs);
 int spsph_sync(spsph_handle *h);
 int spsph_destroy(spsph_handle *h);

@@ -16,6 +16,7 @@
 
 #include "spsph.h"
 #include "dist_kernels.cuh"
+#include "tile_kernels.cuh"
 
 using namespace spsph;
 
@@ -140,6 +141,22 @@ struct spsph_handle {
   StepStatus *status_d = nullptr, *status_h = nullptr;
   int *stats_d = nullptr;
 
+  // ---- cell-tile path (tile_kernels.cuh): acceptance masks + fp32 weights instead of partner-id lists ----
+  bool tile_cfg = false;    // the option combination is covered by the tile kernels (decided at upload)
+  bool tile_off = false;    // a stencil row outgrew the 64-bit masks: list path until the next upload
+  bool tile_env = true;     // SPSPH_TILE=0 forces the list path (tests compare the two)
+  bool tile_last = false;   // the last step ran on the tile path (the id lists are materialised on demand)
+  int tile_last_mode = 0;   // its traversal order: 0 forward, 1 reversed
+  TileLists TL{};
+  TileRecs TR{};
+  double *smor = nullptr, *srrho = nullptr;  // species-sorted per-step copies of mass/rho and RN(1/rho)
+  double2 *smrho = nullptr;                  // ... and {mass, rho}
+  long long tile_w0_cap = 0, tile_c_cap = 0; // allocated float4 groups
+  u64 *tile_acc = nullptr;                   // device: forward pair count of the step
+  int *tile_flags = nullptr;                 // device: [0] mask overflow, [1..3] longest lists, [4] slice overflow
+  TileStatus *tstat_d = nullptr, *tstat_h = nullptr;
+  long long tile_steps = 0, list_steps = 0;  // which path the steps took (spsph_path_counts)
+
   long long m_pairs = 0;       // max pair count of all previous steps (main:1210)
   long long last_n_pairs = 0;  // of the last step
   long long last_m_before = 0;
@@ -192,12 +209,12 @@ struct spsph_handle {
 
 enum KernelId {
   KID_BBOX = 0, KID_GRID, KID_ZERO, KID_CELLID, KID_SCAN, KID_SCATTER, KID_RANK, KID_COUNT, KID_STATUS, KID_THRESH,
-  KID_FILL, KID_RKBEGIN, KID_SWEEPA, KID_SWEEPB, KID_MOVE, KID_SHIFT, KID_HALO, KID_N
+  KID_FILL, KID_RKBEGIN, KID_SWEEPA, KID_SWEEPB, KID_MOVE, KID_SHIFT, KID_HALO, KID_TBUILD, KID_N
 };
 static const char *kKernelNames[KID_N] = {"k_domain_bbox", "k_grid_params", "k_zero_cells", "k_cell_id", "k_scan_*",
                                           "k_scatter", "k_rank", "k_count", "k_status", "k_growth_threshold", "k_fill",
                                           "k_rk_begin", "k_sweep_a", "k_sweep_b", "k_move", "k_shift",
-                                          "halo_exchange"};
+                                          "halo_exchange", "k_tile_build"};
 
 namespace {
 
@@ -649,10 +666,8 @@ void emu_slice_widths(spsph_handle *h) {  // the warp-wide maxima at the end of 
 }
 #endif
 
-int build_neighbours(spsph_handle *h) {
-#ifdef SPSPH_HOST_EMU
-  if (h->emu_lists) return emu_import_lists(h);
-#endif
+// cell grid + counting sort of the local particles (grid_find_NEW Tasks 1-2, main:1245-1305); shared by both paths
+int sort_particles(spsph_handle *h) {
   const DevParams &P = h->P;
   const int n2 = P.ntotal2;
   const int TB = 256;
@@ -677,9 +692,6 @@ int build_neighbours(spsph_handle *h) {
   k_zero_cells<<<296, TB, 0, s>>>(h->G, h->cell_cnt, h->cell_stride);
   k_zero_cells<<<296, TB, 0, s>>>(h->G, h->cell_fill, h->cell_stride);
   CUDA_TRY(cudaMemsetAsync(h->nout, 0, 6 * sizeof(int), s));
-  CUDA_TRY(cudaMemsetAsync(h->nfwd_u, 0, (size_t)n2 * sizeof(int), s));
-  CUDA_TRY(cudaMemsetAsync(h->wslice, 0, 3 * (size_t)h->nslices * sizeof(int), s));
-  CUDA_TRY(cudaMemsetAsync(h->cand_overflow, 0, sizeof(int), s));
   mark(h, KID_ZERO, 2);
   k_cell_id<<<GL, TB, 0, s>>>(P, h->G, h->x, h->if_out, LL, h->which_cell, h->cell_cnt, h->cell_stride, h->nout);
   mark(h, KID_CELLID);
@@ -688,17 +700,72 @@ int build_neighbours(spsph_handle *h) {
   mark(h, KID_SCATTER);
   k_rank<<<GL, TB, 0, s>>>(P, LL, h->G, h->x, h->hsml, h->which_cell, h->cell_start, h->cell_stride, h->tmp_ids,
                            h->order, h->spos, h->sh, h->scell, h->pos_of, h->supos, h->nout);
-  mark(h, KID_RANK);
-  const SortArrays S = sort_arrays(h);
-  // slots that can hold local particles: all of them, or (slab) last step's local count plus what two halo
-  // messages can add
-  int bound[3] = {h->M.nnp, h->M.nsp, h->M.ndp};
+  if (h->tile_cfg)  // species-sorted copies of the per-particle constants the tile kernels stage
+    k_rank_consts<<<GL, TB, 0, s>>>(P, LL, h->pos_of, h->mass, h->rho, h->mor, h->smor, h->smrho, h->srrho);
+  mark(h, KID_RANK, h->tile_cfg ? 2 : 1);
+  return 0;
+}
+
+// slots of one species that can hold local particles: all of them, or (slab) last step's local count plus what two
+// halo messages can add
+static void slot_bounds(const spsph_handle *h, int (&bound)[3]) {
+  bound[0] = h->M.nnp;
+  bound[1] = h->M.nsp;
+  bound[2] = h->M.ndp;
   if (h->dist && h->nloc_valid)
     for (int k = 0; k < 3; ++k) {
       const long long b = (long long)h->nloc[k] + halo_limit(h, h->halo_prev_recv[0]) +
                           halo_limit(h, h->halo_prev_recv[1]) + 32;
       if (b < bound[k]) bound[k] = (int)b;
     }
+}
+
+// slab runs: the read-back that follows the neighbour build also brings the halo counts (they size the next step's
+// messages) and the error flags of the exchange
+static int dist_status_enqueue(spsph_handle *h) {
+  cudaStream_t s = h->stream;
+  h->dist_h[0] = h->dist_h[1] = 0.0;
+  if (h->D.rank > 0) CUDA_TRY(cudaMemcpyAsync(h->dist_h, h->halo_recv[0], sizeof(double), cudaMemcpyDeviceToHost, s));
+  if (h->D.rank < h->D.nranks - 1)
+    CUDA_TRY(cudaMemcpyAsync(h->dist_h + 1, h->halo_recv[1], sizeof(double), cudaMemcpyDeviceToHost, s));
+  CUDA_TRY(cudaMemcpyAsync(h->dist_h + 2, h->halo_cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
+  return 0;
+}
+static int dist_status_apply(spsph_handle *h) {
+  const int *hc = reinterpret_cast<const int *>(h->dist_h + 2);  // halo_cnt[0..1], error flags [2..3]
+  if (hc[2]) {
+    h->err = "multi-GPU: halo message capacity exceeded (too many particles near a slab boundary)";
+    return 1;
+  }
+  if (hc[3]) {
+    h->err = "multi-GPU: the distributed list-growth search failed in the previous step (grid too large?)";
+    return 1;
+  }
+  for (int side = 0; side < 2; ++side) {
+    h->halo_prev_send[side] = hc[side];
+    h->halo_prev_recv[side] = (int)h->dist_h[side];
+  }
+  h->halo_prev_valid = true;
+  return 0;
+}
+
+// Neighbour lists of the list path: count pass, list sizing (one host round trip), growth rule, fill pass.
+// forced_mode >= 0: materialise the id lists of a step that ran on the tile path (free-surface detection at
+// download, spsph_pairs) with that traversal order; the step bookkeeping is left alone.
+int build_lists(spsph_handle *h, int forced_mode = -1) {
+#ifdef SPSPH_HOST_EMU
+  if (h->emu_lists) return emu_import_lists(h);
+#endif
+  const DevParams &P = h->P;
+  const int n2 = P.ntotal2;
+  cudaStream_t s = h->stream;
+  const int *lflag = h->dist ? h->lflag : nullptr;
+  CUDA_TRY(cudaMemsetAsync(h->nfwd_u, 0, (size_t)n2 * sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(h->wslice, 0, 3 * (size_t)h->nslices * sizeof(int), s));
+  CUDA_TRY(cudaMemsetAsync(h->cand_overflow, 0, sizeof(int), s));
+  const SortArrays S = sort_arrays(h);
+  int bound[3];
+  slot_bounds(h, bound);
   if (!h->dist) {  // single GPU: every slot is live, one launch over all of them
     const int tn = h->M.total();
     k_count<<<(tn + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->nfwd_u, h->nall, h->wslice,
@@ -723,7 +790,7 @@ int build_neighbours(spsph_handle *h) {
     launch_scan(h, h->nfwd_u, h->base_u, 1, n2, h->list_n + h->list_cur, 0, h->scan_totals + 3, KID_SCAN);
   else
     launch_scan(h, h->nfwd_u, h->base_u, 1, n2, nullptr, n2, h->scan_totals + 3, KID_SCAN);
-  if (h->dist) {  // every pair is counted once, at the owner of its earlier member
+  if (h->dist && forced_mode < 0) {  // every pair is counted once, at the owner of its earlier member
     CUDA_TRY(cudaMemcpyAsync(h->scan_totals + 6, h->scan_totals + 3, sizeof(long long), cudaMemcpyDeviceToDevice, s));
     NCCL_TRY(h->p_ncclAllReduce(h->scan_totals + 3, h->scan_totals + 3, 1, ncclInt64, ncclSum, h->comm, s));
   }
@@ -731,31 +798,10 @@ int build_neighbours(spsph_handle *h) {
                             h->status_d);
   mark(h, KID_STATUS);
   CUDA_TRY(cudaMemcpyAsync(h->status_h, h->status_d, sizeof(StepStatus), cudaMemcpyDeviceToHost, s));
-  if (h->dist) {  // the same round trip brings back the halo counts (they size the next step's messages)
-    h->dist_h[0] = h->dist_h[1] = 0.0;
-    if (h->D.rank > 0) CUDA_TRY(cudaMemcpyAsync(h->dist_h, h->halo_recv[0], sizeof(double), cudaMemcpyDeviceToHost, s));
-    if (h->D.rank < h->D.nranks - 1)
-      CUDA_TRY(cudaMemcpyAsync(h->dist_h + 1, h->halo_recv[1], sizeof(double), cudaMemcpyDeviceToHost, s));
-    CUDA_TRY(cudaMemcpyAsync(h->dist_h + 2, h->halo_cnt, 4 * sizeof(int), cudaMemcpyDeviceToHost, s));
-  }
+  if (h->dist && forced_mode < 0 && dist_status_enqueue(h)) return 1;
   CUDA_TRY(cudaStreamSynchronize(s));
   const StepStatus st = *h->status_h;
-  if (h->dist) {
-    const int *hc = reinterpret_cast<const int *>(h->dist_h + 2);  // halo_cnt[0..1], error flags [2..3]
-    if (hc[2]) {
-      h->err = "multi-GPU: halo message capacity exceeded (too many particles near a slab boundary)";
-      return 1;
-    }
-    if (hc[3]) {
-      h->err = "multi-GPU: the distributed list-growth search failed in the previous step (grid too large?)";
-      return 1;
-    }
-    for (int side = 0; side < 2; ++side) {
-      h->halo_prev_send[side] = hc[side];
-      h->halo_prev_recv[side] = (int)h->dist_h[side];
-    }
-    h->halo_prev_valid = true;
-  }
+  if (h->dist && forced_mode < 0 && dist_status_apply(h)) return 1;
   if (st.overflow) {
     h->err = "cell grid larger than the capacity derived from Xmin_Domain/Xmax_Domain";
     return 1;
@@ -771,10 +817,14 @@ int build_neighbours(spsph_handle *h) {
   h->L.offC = h->oslice + h->nslices;
   h->L.offD = h->oslice + 2 * h->nslices;
   // list-growth rule
-  h->last_m_before = h->m_pairs;
-  h->last_n_pairs = st.n_pairs;
   GrowthRule gr{0, 0, 0};
-  if (st.n_pairs > h->m_pairs) gr.mode = (h->m_pairs == 0) ? 1 : 2;
+  if (forced_mode >= 0) {
+    gr.mode = forced_mode;
+  } else {
+    h->last_m_before = h->m_pairs;
+    h->last_n_pairs = st.n_pairs;
+    if (st.n_pairs > h->m_pairs) gr.mode = (h->m_pairs == 0) ? 1 : 2;
+  }
   CUDA_TRY(cudaMemcpyAsync(h->growth, &gr, sizeof(gr), cudaMemcpyHostToDevice, s));
   if (h->profiling) mark(h, -1, 0);  // do not charge the host round trip to the next kernel
   if (gr.mode == 2 && h->dist) {
@@ -796,7 +846,7 @@ int build_neighbours(spsph_handle *h) {
     k_growth_threshold<<<1, 32, 0, s>>>(P, h->M, h->G, S, h->base_u, h->m_pairs, h->growth);
     mark(h, KID_THRESH);
   }
-  if (st.n_pairs > h->m_pairs) h->m_pairs = st.n_pairs;
+  if (forced_mode < 0 && st.n_pairs > h->m_pairs) h->m_pairs = st.n_pairs;
   SlotMap ML = h->M;  // only the slots of this rank's local particles hold data
   ML.nn = h->nloc[0];
   ML.ns = h->nloc[1];
@@ -819,6 +869,252 @@ int build_neighbours(spsph_handle *h) {
                                                         ftn[k]);
   }
   mark(h, KID_FILL, h->dist ? 2 : 1);
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Cell-tile path (tile_kernels.cuh)
+// ------------------------------------------------------------------------------------------------------
+// Which inputs the tile kernels cover; everything else runs on the list path of round 1 (same results).
+static bool tile_config_ok(const spsph_handle *h) {
+  const spsph_params &p = h->hp;
+  return p.sp_sph && !p.cont_density && !p.art_stress && !h->fs_each_step && h->uniform_cubic &&
+         (long long)h->M.nnp + h->M.nsp + h->M.ndp < (1ll << 30);
+}
+
+static int tile_alloc_weights(spsph_handle *h) {
+  TileLists &T = h->TL;
+  const long long g0 = ((long long)T.nsl_n * (T.capN0 >> 2) + (long long)(h->M.nsp / SLICE) * (T.capS0 >> 2)) * 32 + 64;
+  const long long gc = (long long)T.nsl_n * (T.capC >> 2) * 32 + 64;
+  if (g0 > h->tile_w0_cap) {
+    cudaFree(T.w0);
+    cudaFree(T.gx0);
+    cudaFree(T.gy0);
+    T.w0 = T.gx0 = T.gy0 = nullptr;
+    h->tile_w0_cap = 0;
+    CUDA_TRY(cudaMalloc((void **)&T.w0, (size_t)g0 * sizeof(float4)));
+    CUDA_TRY(cudaMalloc((void **)&T.gx0, (size_t)g0 * sizeof(float4)));
+    CUDA_TRY(cudaMalloc((void **)&T.gy0, (size_t)g0 * sizeof(float4)));
+    h->tile_w0_cap = g0;
+  }
+  if (gc > h->tile_c_cap) {
+    cudaFree(T.gxC);
+    cudaFree(T.gyC);
+    T.gxC = T.gyC = nullptr;
+    h->tile_c_cap = 0;
+    CUDA_TRY(cudaMalloc((void **)&T.gxC, (size_t)gc * sizeof(float4)));
+    CUDA_TRY(cudaMalloc((void **)&T.gyC, (size_t)gc * sizeof(float4)));
+    h->tile_c_cap = gc;
+  }
+  return 0;
+}
+
+// one-time allocations of the tile path (sizes depend on the particle counts only)
+static int tile_setup(spsph_handle *h) {
+  if (h->TL.mA) return 0;
+  const size_t nsl = (size_t)h->M.nnp + h->M.nsp, n2 = (size_t)h->P.ntotal2;
+  TileLists &T = h->TL;
+  T.nslots = (int)nsl;
+  T.nsl_n = h->M.nnp / SLICE;
+  T.capN0 = 48;
+  T.capS0 = 28;
+  T.capC = 28;
+  T.n0 = h->n0;
+  T.n1 = h->n1;
+  int rc = dalloc(h, &T.mA, 3 * nsl) | dalloc(h, &T.mS, 3 * nsl) | dalloc(h, &T.wsel, 3 * nsl) | dalloc(h, &T.mW, 3 * nsl);
+  rc |= dalloc(h, &h->smor, 2 * n2) | dalloc(h, &h->srrho, 2 * n2) | dalloc(h, &h->smrho, 2 * n2);
+  rc |= dalloc(h, &h->TR.NAs, (size_t)h->M.nnp) | dalloc(h, &h->TR.NBs, (size_t)h->M.nnp);
+  rc |= dalloc(h, &h->TR.SAs, (size_t)h->M.nsp) | dalloc(h, &h->TR.SBs, (size_t)h->M.nsp) | dalloc(h, &h->TR.SVs, (size_t)h->M.nsp);
+  rc |= dalloc(h, &h->tile_acc, 2) | dalloc(h, &h->tile_flags, 8) | dalloc(h, &h->tstat_d, 1);
+  if (rc) return 1;
+  CUDA_TRY(cudaMallocHost((void **)&h->tstat_h, sizeof(TileStatus)));
+  return tile_alloc_weights(h);
+}
+
+static SortedConsts sorted_consts(const spsph_handle *h) {
+  SortedConsts C;
+  const size_t n2 = (size_t)h->P.ntotal2;
+  for (int sp = 0; sp < 2; ++sp) {
+    C.mor[sp] = h->smor + sp * n2;
+    C.mrho[sp] = h->smrho + sp * n2;
+    C.rrho[sp] = h->srrho + sp * n2;
+  }
+  return C;
+}
+
+// One-pass neighbour build of the tile path. *use = false: this step has to take the list path (the pair list grew
+// after the first step -> split traversal order, or a stencil row outgrew the masks).
+int tile_build(spsph_handle *h, bool *use) {
+  *use = false;
+  const DevParams &P = h->P;
+  cudaStream_t s = h->stream;
+  const int *lflag = h->dist ? h->lflag : nullptr;
+  const SortArrays S = sort_arrays(h);
+  const SortedConsts C = sorted_consts(h);
+  const int rev = h->m_pairs == 0 ? 1 : 0;  // first step after an upload: every list node is new (main:1362-1368)
+  TileStatus st{};
+  for (int attempt = 0; attempt < 2; ++attempt) {
+    CUDA_TRY(cudaMemsetAsync(h->tile_acc, 0, 2 * sizeof(u64), s));
+    CUDA_TRY(cudaMemsetAsync(h->tile_flags, 0, 8 * sizeof(int), s));
+    int bound[3];
+    slot_bounds(h, bound);
+    if (bound[0] > 0)
+      k_tile_build<SP_NODE><<<(bound[0] + TB_T - 1) / TB_T, TB_T, 0, s>>>(
+          P, h->G, S, h->TL, C, h->M.nnp, rev, lflag, h->nout, h->nall, h->bc_int, h->n_int, h->norm, h->AE,
+          h->tile_acc, h->tile_flags);
+    if (bound[1] > 0)
+      k_tile_build<SP_STRESS><<<(bound[1] + TB_T - 1) / TB_T, TB_T, 0, s>>>(
+          P, h->G, S, h->TL, C, h->M.nnp, rev, lflag, h->nout, h->nall, h->bc_int, h->n_int, h->norm, h->AE,
+          h->tile_acc, h->tile_flags);
+    if (bound[2] > 0)
+      k_tile_build<SP_DUMMY><<<(bound[2] + TB_T - 1) / TB_T, TB_T, 0, s>>>(
+          P, h->G, S, h->TL, C, h->M.nnp, rev, lflag, h->nout, h->nall, h->bc_int, h->n_int, h->norm, h->AE,
+          h->tile_acc, h->tile_flags);
+    mark(h, KID_TBUILD, 3);
+    if (h->dist) {  // all ranks must take the same path: global pair count and overflow flags
+      NCCL_TRY(h->p_ncclAllReduce(h->tile_acc, h->tile_acc, 1, ncclInt64, ncclSum, h->comm, s));
+      NCCL_TRY(h->p_ncclAllReduce(h->tile_flags, h->tile_flags, 5, ncclInt32, ncclMax, h->comm, s));
+    }
+    k_tile_status<<<1, 32, 0, s>>>(h->G, h->cell_start, h->cell_stride, h->nout, h->tile_acc, h->tile_flags, h->tstat_d);
+    mark(h, KID_STATUS);
+    CUDA_TRY(cudaMemcpyAsync(h->tstat_h, h->tstat_d, sizeof(TileStatus), cudaMemcpyDeviceToHost, s));
+    if (h->dist && dist_status_enqueue(h)) return 1;
+    CUDA_TRY(cudaStreamSynchronize(s));
+    if (h->profiling) mark(h, -1, 0);  // do not charge the host round trip to the next kernel
+    st = *h->tstat_h;
+    if (h->dist && dist_status_apply(h)) return 1;
+    if (st.overflow) {
+      h->err = "cell grid larger than the capacity derived from Xmin_Domain/Xmax_Domain";
+      return 1;
+    }
+    for (int k = 0; k < 3; ++k) h->nloc[k] = st.nloc[k];
+    h->nloc_valid = true;
+    if (st.flags & 1) {  // more candidates in a stencil row than a mask holds: this problem stays on the list path
+      h->tile_off = true;
+      return 0;
+    }
+    if (!(st.flags & 2)) break;
+    if (attempt == 1) return 0;
+    // a list is longer than its slice: enlarge the slices and build again
+    auto fit = [](int need, int cap) { return need > cap ? ((need + need / 4 + 4 + 3) & ~3) : cap; };
+    h->TL.capN0 = fit(st.max_n0n, h->TL.capN0);
+    h->TL.capS0 = fit(st.max_n0s, h->TL.capS0);
+    h->TL.capC = fit(st.max_n1n, h->TL.capC);
+    if (tile_alloc_weights(h)) return 1;
+  }
+  // list-growth rule: forward order unless the list grew; a list that grows after the first step
+  // is walked in split order, which only the list path implements
+  if (st.n_pairs > h->m_pairs && h->m_pairs > 0) return 0;
+  h->last_m_before = h->m_pairs;
+  h->last_n_pairs = st.n_pairs;
+  h->tile_last_mode = rev;  // (no pairs at all in a first step: nothing is walked in either order)
+  if (st.n_pairs > h->m_pairs) h->m_pairs = st.n_pairs;
+  *use = true;
+  return 0;
+}
+
+int tile_step(spsph_handle *h, int itimestep) {
+  const DevParams &P = h->P;
+  const spsph_params &p = h->hp;
+  cudaStream_t s = h->stream;
+  const SortArrays S = sort_arrays(h);
+  const SortedConsts C = sorted_consts(h);
+  const TileLists &L = h->TL;
+  const TileRecs &R = h->TR;
+  SlotMap M = h->M;  // launch extents: only the particles this rank has to process (same slot layout)
+  M.nn = h->nloc[0];
+  M.ns = h->nloc[1];
+  const int rev = h->tile_last_mode;
+  const int GN = (M.nn + 127) / 128;
+  const int GSs = (M.ns + TS_T - 1) / TS_T, GNn = (M.nn + TN_T - 1) / TN_T, GNs = (M.nn + TS_T - 1) / TS_T;
+  const int adapt = P.adapt, bc = p.no_bcs > 0 ? 1 : 0;
+  cudaStream_t s2 = h->dual ? h->stream2 : s;
+  auto fork = [&]() {
+    if (s2 != s) {
+      cudaEventRecord(h->ev_fork, s);
+      cudaStreamWaitEvent(s2, h->ev_fork, 0);
+    }
+  };
+  auto join = [&]() {
+    if (s2 != s) {
+      cudaEventRecord(h->ev_join, s2);
+      cudaStreamWaitEvent(s, h->ev_join, 0);
+    }
+  };
+  // SPH_shift block, main:99-109: state between steps -> the other format-B buffer set
+  if (p.sph_shift && itimestep > 1 && ((itimestep - 1) % p.shift_update == 0)) {
+    const StatePtrs sw = state_ptrs(h, 1 - h->cur);
+    fork();
+    if (GSs) k_tile_a_sp<true><<<GSs, TS_T, 0, s>>>(P, M, h->G, S, L, C, R, sw, rev, adapt, 0, 0);
+    if (GNn) k_tile_a_node<true, true><<<GNn, TN_T, 0, s2>>>(P, M, h->G, S, L, C, R, sw, rev, adapt, 0, 0);
+    join();
+    mark(h, KID_SWEEPA, 2);
+    h->cur = 1 - h->cur;
+  }
+  const StatePtrs st = state_ptrs(h, h->cur);
+  const int extra = (p.inside_approach && p.ndummy2 > 0) ? 1 : 0;
+  if (extra) {  // boundary_forces (main:742): x is frozen during the 4 stages
+    k_bound_force<<<GN, 128, 0, s>>>(P, M, h->G, S, p.ndummy2, h->fbound);
+    mark(h, KID_MOVE);
+  }
+  // RK4, main:653-802
+  k_rk_begin<<<list_grid(h, P.ntotal, 256), 256, 0, s>>>(P, st, local_list(h, P.ntotal), h->pos_of, R.NAs, R.SAs);
+  mark(h, KID_RKBEGIN);
+  const double f1rk[4] = {0., 0.5, 0.5, 1.0}, f2rk[4] = {1., 2., 2., 1.0};
+  const bool artv = (P.alpha > 0 || P.beta > 0);
+  for (int stg = 0; stg < 4; ++stg) {
+    fork();
+    if (GSs) k_tile_a_sp<false><<<GSs, TS_T, 0, s>>>(P, M, h->G, S, L, C, R, st, rev, adapt, bc, 0);
+    if (GNn) k_tile_a_node<false, false><<<GNn, TN_T, 0, s2>>>(P, M, h->G, S, L, C, R, st, rev, adapt, bc, 0);
+    join();
+    mark(h, KID_SWEEPA, 2);
+    const int last = (stg == 3);
+    const double f1n = last ? 0.0 : f1rk[stg + 1];
+    fork();
+    if (GSs) k_tile_b_sp<<<GSs, TS_T, 0, s>>>(P, M, h->G, S, L, C, R, st, rev, f1n, f2rk[stg], last);
+    if (artv && GNs) k_tile_av<<<GNs, TS_T, 0, s2>>>(P, M, h->G, S, L, R, st, rev, h->h_uniform);
+    if (GNn) k_tile_b_node<<<GNn, TN_T, 0, s2>>>(P, M, h->G, S, L, R, st, rev, f1n, f2rk[stg], last, extra);
+    join();
+    mark(h, KID_SWEEPB, artv ? 3 : 2);
+  }
+  // final stress_point_update + adapt_stress2 + BCs, main:130-135
+  fork();
+  if (GSs) k_tile_a_sp<false><<<GSs, TS_T, 0, s>>>(P, M, h->G, S, L, C, R, st, rev, adapt, bc, 1);
+  if (GNn) k_tile_a_node<false, true><<<GNn, TN_T, 0, s2>>>(P, M, h->G, S, L, C, R, st, rev, adapt, bc, 1);
+  join();
+  mark(h, KID_SWEEPA, 2);
+  // positions, main:140-182
+  if (GNs + GSs)
+    k_tile_move<<<GNs + GSs, TS_T, 0, s>>>(P, M, h->G, S, L, C, R, st, rev, GNs, h->x, h->x00, h->displ);
+  mark(h, KID_MOVE);
+  if (h->x_fs && !h->dist) {
+    CUDA_TRY(cudaMemcpyAsync(h->x_fs, h->x, 2 * (size_t)P.ntotal2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
+    h->x_fs_valid = true;
+  }
+  if (p.update_x && p.sp_sph && !p.inside_approach) {
+    k_shift<<<list_grid(h, P.nnode, 256), 256, 0, s>>>(P, st.NB, h->x, h->x_10, h->disp_10, h->bc_int, h->n_int,
+                                                       local_list(h, P.nnode));
+    mark(h, KID_SHIFT);
+  }
+  CUDA_TRY(cudaGetLastError());
+  h->have_lists = false;
+  h->tile_last = true;
+  ++h->tile_steps;
+  if (h->profiling) prof_collect(h);
+  return 0;
+}
+
+// the id lists of the last step, built on demand after a tile step (free-surface detection at download, spsph_pairs)
+static int materialize_lists(spsph_handle *h) {
+  if (h->have_lists || !h->tile_last) return 0;
+  const long long keep_launches = h->launches;
+  const bool prof = h->profiling;
+  h->profiling = false;
+  const int rc = build_lists(h, h->tile_last_mode);
+  h->profiling = prof;
+  h->launches = keep_launches;
+  if (rc) return 1;
+  h->have_lists = true;
   return 0;
 }
 
@@ -845,7 +1141,21 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   }
   step_scalars(h, itimestep, time_sph, dt);
   if (h->dist && halo_exchange(h)) return 1;
-  if (build_neighbours(h)) return 1;
+  bool sorted = false;
+#ifdef SPSPH_HOST_EMU
+  if (h->emu_lists) sorted = true;  // lockstep emulation: the harness hands the sorted arrays and lists over
+#endif
+  if (!sorted) {
+    if (sort_particles(h)) return 1;
+    if (h->tile_cfg && h->tile_env && !h->tile_off) {
+      bool use_tile = false;
+      if (tile_build(h, &use_tile)) return 1;
+      if (use_tile) return tile_step(h, itimestep);
+    }
+  }
+  if (build_lists(h)) return 1;
+  h->tile_last = false;
+  ++h->list_steps;
   const DevParams &P = h->P;
   const spsph_params &p = h->hp;
   cudaStream_t s = h->stream;
@@ -876,7 +1186,7 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     mark(h, KID_MOVE);
   }
   // RK4, main:653-802
-  k_rk_begin<<<list_grid(h, P.ntotal, 256), 256, 0, s>>>(P, st, local_list(h, P.ntotal));
+  k_rk_begin<<<list_grid(h, P.ntotal, 256), 256, 0, s>>>(P, st, local_list(h, P.ntotal), nullptr, nullptr, nullptr);
   mark(h, KID_RKBEGIN);
   const double f1rk[4] = {0., 0.5, 0.5, 1.0}, f2rk[4] = {1., 2., 2., 1.0};
   // The node-side and the stress-particle-side kernel of a sweep touch disjoint outputs and only read the
@@ -1064,6 +1374,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming));
   if (const char *e = getenv("SPSPH_DUAL_STREAM")) h->dual = atoi(e) != 0;
+  if (const char *e = getenv("SPSPH_TILE")) h->tile_env = atoi(e) != 0;
   CUDA_TRY(cudaEventCreate(&h->ev0));
   CUDA_TRY(cudaEventCreate(&h->ev1));
 
@@ -1292,6 +1603,10 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   }
   h->m_pairs = 0;
   h->have_lists = false;
+  h->tile_last = false;
+  h->tile_off = false;
+  h->tile_cfg = h->tile_env && tile_config_ok(h);
+  if (h->tile_cfg && tile_setup(h)) return 1;
   h->x_fs_valid = false;
   h->uploaded = true;
 #ifndef SPSPH_HOST_EMU
@@ -1354,6 +1669,13 @@ int spsph_profile_get(spsph_handle *h, int kid, const char **name, double *total
   return 0;
 }
 
+int spsph_path_counts(spsph_handle *h, int64_t *tile_steps, int64_t *list_steps) {
+  if (!h) return 1;
+  if (tile_steps) *tile_steps = (int64_t)h->tile_steps;
+  if (list_steps) *list_steps = (int64_t)h->list_steps;
+  return 0;
+}
+
 int spsph_get_list_capacity(spsph_handle *h, int64_t *m_pairs) {
   if (!h || !m_pairs) return 1;
   *m_pairs = (int64_t)h->m_pairs;
@@ -1413,6 +1735,7 @@ int spsph_download(spsph_handle *h, const spsph_state *s) {
     k_download_ivars<<<((int)nt + 255) / 256, 256, 0, st>>>((int)nt, h->epsp, h->ivars);
     CUDA_TRY(down(s->internal_vars, h->ivars, (size_t)SPSPH_NINT_VARS * nt * 8));
   }
+  if (s->bc_or_not && p.update_x && !h->fs_each_step && materialize_lists(h)) return 1;
   if (s->bc_or_not && p.update_x && h->have_lists && !h->fs_each_step) {
     // get_nodes_on_free_surface (main:152-154 runs it at the end of every step; only bc_or_not leaves it)
     SlotMap ML = h->M;
@@ -1470,6 +1793,7 @@ int spsph_pairs(spsph_handle *h, int64_t *npairs, int32_t *pair_i, int32_t *pair
   if (npairs) *npairs = n;
   if (!pair_i) return 0;
   CUDA_TRY(cudaSetDevice(h->device));
+  if (materialize_lists(h)) return 1;  // creation indices (base_u) come from the count pass of the list path
   int *d_i = nullptr, *d_j = nullptr, *d_t = nullptr;
   float *d_w = nullptr, *d_x = nullptr, *d_y = nullptr;
   const size_t b = (size_t)(n > 0 ? n : 1) * 4;
@@ -1646,6 +1970,12 @@ int spsph_destroy(spsph_handle *h) {
   cudaFree(h->L.gyC);
   cudaFree(h->L.idxD);
   cudaFree(h->L.wD);
+  cudaFree(h->TL.w0);
+  cudaFree(h->TL.gx0);
+  cudaFree(h->TL.gy0);
+  cudaFree(h->TL.gxC);
+  cudaFree(h->TL.gyC);
+  if (h->tstat_h) cudaFreeHost(h->tstat_h);
   if (h->status_h) cudaFreeHost(h->status_h);
   if (h->dist_h) cudaFreeHost(h->dist_h);
   if (h->ev0) cudaEventDestroy(h->ev0);

@@ -347,7 +347,9 @@ __global__ void k_unpack_state(DevParams P, StatePtrs st, double *__restrict__ v
 // format B (state) -> format A (stage-1 input); saves vel0/stress0/vx0 and zeroes the RK accumulators.
 // Stress-particle velocities and node stresses start from zero (main:690).
 // ------------------------------------------------------------------------------------------------------
-__global__ void k_rk_begin(DevParams P, StatePtrs st, LocalList LL) {
+// pos_of != nullptr (cell-tile path): the partner-visible stage-1 records go to the species-sorted arrays NAs / SAs.
+__global__ void k_rk_begin(DevParams P, StatePtrs st, LocalList LL, const int *__restrict__ pos_of,
+                           double2 *__restrict__ NAs, Rec4 *__restrict__ SAs) {
   SPSPH_FOR_LOCAL(LL, kk, id) {
   if (id >= P.ntotal) continue;  // wall particle
   double2 vn;
@@ -363,7 +365,10 @@ __global__ void k_rk_begin(DevParams P, StatePtrs st, LocalList LL) {
     sn = Stress4{0.0, 0.0, 0.0, 0.0};
     if (P.adapt) adapt_stress(P, sn);
     apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, vn, sn);
-    st2(st.NA, id, vn);
+    if (pos_of)
+      NAs[pos_of[id]] = vn;
+    else
+      st2(st.NA, id, vn);
     st4(st.NSa, id, sn);
   } else {
     const int ks = id - P.nnode;
@@ -381,7 +386,10 @@ __global__ void k_rk_begin(DevParams P, StatePtrs st, LocalList LL) {
     sn.s4 = s.s4 + 0. * (P.dt) * 0.0;
     if (P.adapt) adapt_stress(P, sn);
     apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, vn, sn);
-    strec(st.SA, ks, sn.s1, sn.s2, sn.s3, sn.s4);
+    if (pos_of)
+      strec(SAs, pos_of[id], sn.s1, sn.s2, sn.s3, sn.s4);
+    else
+      strec(st.SA, ks, sn.s1, sn.s2, sn.s3, sn.s4);
     st2(st.SVa, ks, vn);
     if (P.cont_density) {  // main:686-689 and the stage-1 block main:706-713 (f1rk = 0, f2rk = 1)
       const double r0 = st.rho[id], h0 = st.hsml[id], m = st.mass[id];

@@ -1,0 +1,1420 @@
+// Cell-tile path of the time step: neighbour build and pair sums WITHOUT partner ids and without scattered gathers.
+//
+// Restricted to one particle, the reference's pair order is "partners sorted by (cell id, particle index)"
+// (grid_find_NEW main:1322-1396), and a row of the 3x3 cell stencil is ONE contiguous range of the
+// cell-sorted particle arrays. So instead of a list of partner ids (round 1: 4 bytes + one scattered 32-byte gather
+// per entry and sweep) a particle keeps, per stencil row, a 64-bit ACCEPTANCE MASK over that row's candidates; the
+// partner of list entry e is implied by the e-th set bit. The records the partners expose (velocity of a velocity
+// particle, stress of a stress particle, ...) are written in cell-sorted order by the kernel that precedes their
+// reader, so a block of consecutive sorted particles stages the three candidate ranges it needs in shared memory
+// with contiguous, coalesced loads and every lane then reads its partners from shared memory. What is still
+// streamed per entry are the reference's fp32 pair weights (w: 4 bytes in the interpolation sweeps, dwdx/dwdy: 8
+// bytes in the gradient sweeps; main:1376-1378), stored per lane in groups of four entries (one 16-byte load).
+//
+// Traversal order: ascending candidates (the reference's forward order) or, in the first step after an upload, fully
+// reversed (list nodes are prepended when new, main:1362-1368). Steps in which the pair list grows later on (split
+// order, a few per run) take the round-1 list path of step_kernels.cuh; so do option combinations this path does
+// not cover (see tile_eligible() in spsph_engine.cu). Every per-particle sum runs in the reference's order in one
+// thread: no atomics in any sum, results bit-identical to the list path.
+//
+// Reference rows: grid_find_NEW main:1199-1435 + kernel main:1440-1538 + Pint_Update mat:1574-1634 (k_tile_build),
+// stress_point_update main:403-482 (k_tile_a_*), get_derivatives main:487-648 + RK4 main:653-802 + plastic_terms
+// mat:1884-1954 (k_tile_b_*), artificial_viscosity main:826-904 (k_tile_av), XSPH_update main:189-239 and the
+// position update main:140-182 (k_tile_move).
+#pragma once
+#include "step_kernels.cuh"
+
+namespace spsph {
+
+typedef unsigned long long u64;
+
+struct TileLists {
+  // per list-owning thread slot t (velocity particles [0, nnp), stress particles [nnp, nnp + nsp)), one value per
+  // stencil row r = 0, 1, 2 (grid rows cy-1, cy, cy+1) at [r * nslots + t]; bit i of a row mask = candidate
+  // start[species][row*ndx + max(cx-1, 0)] + i of the species-sorted arrays
+  u64 *mA;       // cross-species partners (velocity <- stress, stress <- velocity): pair type 1
+  u64 *mS;       // same-species partners: types 3 (velocity-velocity) and 2 (stress-stress)
+  unsigned *mW;  // wall-particle partners: types 6 and 9
+  u64 *wsel;     // rows with wall partners: bit i = the i-th accepted entry of the row (cell, species, index order) is a wall particle
+  int *n0, *n1;  // entries of list 0 (cross-species + wall; bit 30: has wall partners) and of the same-species list
+  // fp32 pair weights, groups of four consecutive entries per lane: entries 4g..4g+3 of slot t at [(G0(t/32) + g)*32 + t%32]
+  float4 *w0, *gx0, *gy0;  // list 0: w, dwdx, dwdy in the reference's orientation after Pint_Update
+  float4 *gxC, *gyC;       // velocity-velocity list: own-perspective gradient (artificial_viscosity)
+  int capN0, capS0, capC;  // rows per 32-slot slice (multiples of 4): list 0 of velocity / stress particles, list C
+  int nsl_n;               // slices of velocity particles (nnp / 32)
+  int nslots;              // nnp + nsp
+};
+constexpr int TILE_WALL_FLAG = 1 << 30;
+
+__device__ __forceinline__ size_t ell0_base(const TileLists &L, int t) {
+  const int sl = t >> 5;
+  const size_t g0 = sl < L.nsl_n ? (size_t)sl * (L.capN0 >> 2)
+                                 : (size_t)L.nsl_n * (L.capN0 >> 2) + (size_t)(sl - L.nsl_n) * (L.capS0 >> 2);
+  return g0 * 32 + (t & 31);
+}
+__device__ __forceinline__ size_t ellC_base(const TileLists &L, int t) {
+  return (size_t)(t >> 5) * (L.capC >> 2) * 32 + (t & 31);
+}
+__device__ __forceinline__ int ell0_cap(const TileLists &L, int t) { return (t >> 5) < L.nsl_n ? L.capN0 : L.capS0; }
+
+// species-sorted copies of per-particle constants (written by k_rank_consts once per step): partners read them from a
+// staged tile like the state records
+struct SortedConsts {
+  const double *mor[2];     // mass/rho
+  const double2 *mrho[2];   // {mass, rho}
+  const double *rrho[2];    // RN(1/rho)
+};
+
+__global__ void k_rank_consts(DevParams P, LocalList LL, const int *__restrict__ pos_of, const double *__restrict__ mass,
+                              const double *__restrict__ rho, const double *__restrict__ mor, double *__restrict__ smor,
+                              double2 *__restrict__ smrho, double *__restrict__ srrho) {
+  SPSPH_FOR_LOCAL(LL, kk, i) {
+    if (i >= P.ntotal) continue;
+    const size_t a = (size_t)(i < P.nnode ? 0 : 1) * P.ntotal2 + pos_of[i];
+    const double r = rho[i];
+    smor[a] = mor[i];
+    smrho[a] = make_double2(mass[i], r);
+    srrho[a] = __drcp_rn(r);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Tile geometry of a block: its targets are consecutive species-sorted particles, so the candidates of all of them
+// are, per stencil row, one contiguous range of the partner species' sorted arrays.
+// ------------------------------------------------------------------------------------------------------
+struct TileGeom {
+  int base[3], off[3], cnt[3];  // per stencil row: first staged sorted index, offset in the staged array, count
+  int staged;                   // 0: the block reads its partners from global memory (row-straddling or oversized tile)
+};
+
+// c0, c1: cells of the block's first and last live target; start_q: cell table of the partner species
+__device__ __forceinline__ void tile_geom(const GridInfo *__restrict__ G, int c0, int c1, const int *__restrict__ start_q,
+                                          int cap, TileGeom &g) {
+  g.staged = 0;
+  for (int r = 0; r < 3; ++r) g.base[r] = g.off[r] = g.cnt[r] = 0;
+  if (c0 < 0 || c1 < 0) return;  // out-of-domain particles are parked behind the sorted ones: no partners
+  const int ndx = G->ndivx[0], ndy = G->ndivx[1];
+  const int cy0 = c0 / ndx, cy1 = c1 / ndx;
+  if (cy0 != cy1) return;  // the block straddles two grid rows
+  const int cxa = max(c0 - cy0 * ndx - 1, 0), cxb = min(c1 - cy0 * ndx + 1, ndx - 1);
+  int tot = 0;
+  for (int r = 0; r < 3; ++r) {
+    const int row = cy0 - 1 + r;
+    g.off[r] = tot;
+    if (row < 0 || row >= ndy) continue;
+    const int b = start_q[row * ndx + cxa], e = start_q[row * ndx + cxb + 1];
+    g.base[r] = b;
+    g.cnt[r] = e - b;
+    tot += (e - b + 1) & ~1;  // even offsets: 16-byte alignment of 8-byte arrays
+  }
+  g.staged = tot <= cap ? 1 : 0;
+}
+
+// first candidate (sorted index) of each stencil row of a particle in cell c
+__device__ __forceinline__ void lane_rows(const GridInfo *__restrict__ G, int c, const int *__restrict__ start_q, int (&b)[3]) {
+  b[0] = b[1] = b[2] = 0;
+  if (c < 0) return;
+  const int ndx = G->ndivx[0], ndy = G->ndivx[1];
+  const int cy = c / ndx, cx = c - cy * ndx;
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    const int row = cy - 1 + r;
+    if (row >= 0 && row < ndy) b[r] = start_q[row * ndx + max(cx - 1, 0)];
+  }
+}
+// index of mask bit 0 of each stencil row in the staged tile (or in the global sorted array when not staged)
+__device__ __forceinline__ void lane_bases(const GridInfo *__restrict__ G, int c, const int *__restrict__ start_q,
+                                           const TileGeom &g, int (&jb)[3]) {
+  lane_rows(G, c, start_q, jb);
+  if (g.staged) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) jb[r] = jb[r] - g.base[r] + g.off[r];
+  }
+}
+
+// cooperative copy of the three candidate ranges into shared memory; idx != nullptr: the source is indexed by particle
+// number (state between steps) and idx is the sorted order
+template <class T>
+__device__ __forceinline__ void stage_rows(T *__restrict__ sm, const T *__restrict__ g, const int *__restrict__ idx,
+                                           const TileGeom &tg) {
+  if (!tg.staged) return;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    for (int i = threadIdx.x; i < tg.cnt[r]; i += blockDim.x) {
+      const int j = tg.base[r] + i;
+      sm[tg.off[r] + i] = g[idx ? idx[j] : j];
+    }
+}
+// where a lane reads partner records: the staged tile, or global memory (sorted, or by particle number through idx)
+template <class T>
+struct Src {
+  const T *p;
+  const int *ix;
+  __device__ __forceinline__ T operator()(int j) const { return p[ix ? ix[j] : j]; }
+};
+template <class T>
+__device__ __forceinline__ Src<T> make_src(const T *sm, const T *g, const int *idx, const TileGeom &tg) {
+  return tg.staged ? Src<T>{sm, nullptr} : Src<T>{g, idx};
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Walking the accepted candidates of a particle in traversal order.
+// ------------------------------------------------------------------------------------------------------
+struct Walk3 {  // three row masks; forward: rows 0..2, bits ascending; reversed: rows 2..0, bits descending
+  u64 m0, m1, m2;
+  int j0, j1, j2;
+  __device__ __forceinline__ int next(bool rev) {
+    if (!rev) {
+      if (m0) {
+        const int b = __ffsll((long long)m0) - 1;
+        m0 &= m0 - 1;
+        return j0 + b;
+      }
+      if (m1) {
+        const int b = __ffsll((long long)m1) - 1;
+        m1 &= m1 - 1;
+        return j1 + b;
+      }
+      const int b = __ffsll((long long)m2) - 1;
+      m2 &= m2 - 1;
+      return j2 + b;
+    }
+    if (m2) {
+      const int b = 63 - __clzll((long long)m2);
+      m2 ^= 1ull << b;
+      return j2 + b;
+    }
+    if (m1) {
+      const int b = 63 - __clzll((long long)m1);
+      m1 ^= 1ull << b;
+      return j1 + b;
+    }
+    const int b = 63 - __clzll((long long)m0);
+    m0 ^= 1ull << b;
+    return j0 + b;
+  }
+};
+
+// list 0 of a particle with wall partners: within a stencil row the reference visits, cell by cell, the cross-species
+// partners of the cell and then its wall particles; `sel` holds that interleaving. Row data are loaded when the walk
+// enters the row (rare path: only particles next to a wall).
+struct WalkWall {
+  int r, left;
+  u64 a, sel;
+  unsigned w;
+  int ja, jw;
+  __device__ __forceinline__ void enter(const TileLists &L, int t, int row, const int (&jbA)[3], const int (&jbW)[3]) {
+    r = row;
+    a = L.mA[(size_t)row * L.nslots + t];
+    w = L.mW[(size_t)row * L.nslots + t];
+    sel = w ? L.wsel[(size_t)row * L.nslots + t] : 0ull;
+    left = __popcll(a) + __popc(w);
+    ja = jbA[row];
+    jw = jbW[row];
+  }
+  __device__ __forceinline__ void start(const TileLists &L, int t, bool rev, const int (&jbA)[3], const int (&jbW)[3]) {
+    enter(L, t, rev ? 2 : 0, jbA, jbW);
+  }
+  // returns the partner index; wall: it indexes the wall species
+  __device__ __forceinline__ int next(const TileLists &L, int t, bool rev, const int (&jbA)[3], const int (&jbW)[3],
+                                      bool &wall) {
+    while (left == 0) enter(L, t, rev ? r - 1 : r + 1, jbA, jbW);
+    int j;
+    if (!rev) {
+      wall = (sel & 1ull) != 0;
+      sel >>= 1;
+      if (wall) {
+        const int b = __ffs((int)w) - 1;
+        w &= w - 1;
+        j = jw + b;
+      } else {
+        const int b = __ffsll((long long)a) - 1;
+        a &= a - 1;
+        j = ja + b;
+      }
+    } else {
+      wall = ((sel >> (left - 1)) & 1ull) != 0;
+      if (wall) {
+        const int b = 31 - __clz((int)w);
+        w ^= 1u << b;
+        j = jw + b;
+      } else {
+        const int b = 63 - __clzll((long long)a);
+        a ^= 1ull << b;
+        j = ja + b;
+      }
+    }
+    --left;
+    return j;
+  }
+};
+
+__device__ __forceinline__ float f4c(const float4 &v, int u) { return u == 0 ? v.x : (u == 1 ? v.y : (u == 2 ? v.z : v.w)); }
+__device__ __forceinline__ float4 ldcs4(const float4 *p) { return __ldcs(p); }
+__device__ __forceinline__ int popc_range(u64 m, int lo, int hi) {  // set bits at positions [lo, hi)
+  if (hi <= lo) return 0;
+  const u64 hm = hi >= 64 ? ~0ull : ((1ull << hi) - 1ull);
+  const u64 lm = lo >= 64 ? ~0ull : ((1ull << lo) - 1ull);
+  return __popcll(m & hm & ~lm);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Neighbour build, one pass: acceptance masks, list lengths, pair count, fp32 weights; also the two per-step sums
+// that depend on geometry only -- cspm_norm of stress_point_update (main:430-433, 446-462) and the CSPM matrix of
+// get_derivatives (main:539-550, 596-605).
+// ------------------------------------------------------------------------------------------------------
+constexpr int TB_T = 64;  // targets per block
+constexpr int TB_CAP0 = 320, TB_CAP1 = 640, TB_CAP2 = 256;  // staged candidates per species
+
+struct TileStatus {  // read back by the host after the build
+  long long n_pairs;
+  int flags;  // bit 0: a stencil row has more candidates than a mask holds; bit 1: a list exceeds its slice capacity
+  int max_n0n, max_n0s, max_n1n;  // longest lists (size the slice capacities)
+  int ncell, overflow;
+  int nloc[3];
+  int pad;
+};
+
+template <int SP>
+__global__ void __launch_bounds__(TB_T)
+k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileLists L, SortedConsts C, int nnp, int rev,
+             const int *__restrict__ lflag, const int *__restrict__ nout, int *__restrict__ nall,
+             int *__restrict__ bc_int, float *__restrict__ n_int, double *__restrict__ norm, double *__restrict__ AE,
+             u64 *__restrict__ acc_pairs,
+             int *__restrict__ flags /* [0] mask overflow, [1..3] longest lists, [4] slice overflow */) {
+  constexpr bool LISTS = SP != SP_DUMMY;
+  constexpr int SQA = SP == SP_NODE ? SP_STRESS : SP_NODE;  // cross-species partner of a list-owning target
+  __shared__ float2 su0[LISTS ? TB_CAP0 : 1], su1[LISTS ? TB_CAP1 : 1], su2[LISTS ? TB_CAP2 : 1];
+  __shared__ double2 sx0[LISTS ? TB_CAP0 : 1], sx1[LISTS ? TB_CAP1 : 1], sx2[LISTS ? TB_CAP2 : 1];
+  __shared__ TileGeom tgs[3];
+  const int nlive = S.start[SP][G->ncell] + nout[SP];  // sorted particles of this species, incl. out-of-domain ones
+  const int kb0 = blockIdx.x * TB_T;
+  if (kb0 >= nlive) return;
+  const int kb1 = min(kb0 + TB_T, nlive) - 1;
+  if (threadIdx.x < 3) {
+    const int caps[3] = {TB_CAP0, TB_CAP1, TB_CAP2};
+    if (LISTS)
+      tile_geom(G, S.cell[SP][kb0], S.cell[SP][kb1], S.start[threadIdx.x], caps[threadIdx.x], tgs[threadIdx.x]);
+    else
+      tgs[threadIdx.x].staged = 0;
+  }
+  __syncthreads();
+  if (LISTS) {
+    stage_rows(su0, S.upos[0], nullptr, tgs[0]);
+    stage_rows(sx0, S.pos[0], nullptr, tgs[0]);
+    stage_rows(su1, S.upos[1], nullptr, tgs[1]);
+    stage_rows(sx1, S.pos[1], nullptr, tgs[1]);
+    stage_rows(su2, S.upos[2], nullptr, tgs[2]);
+    stage_rows(sx2, S.pos[2], nullptr, tgs[2]);
+    __syncthreads();
+  }
+  const int k0 = kb0 + threadIdx.x;
+  const bool live = k0 < nlive;
+  const int k = live ? k0 : kb0;
+  const int t = (SP == SP_NODE ? 0 : nnp) + k0;  // list slot (LISTS only)
+  const int id = S.order[SP][k];
+  const int c = live ? S.cell[SP][k] : -1;
+  const double2 pp = S.pos[SP][k];
+  const double hp = S.h[SP][k];
+  const float2 up = S.upos[SP][k];
+  const Prefilter pf = prefilter_bounds(P, G, hp);
+  const double sk = (double)P.scale_k;
+  int ovf = 0;
+  u64 mk[3][3];  // [species][row]
+  int jbs[3][3];
+  int cf = 0, ca = 0;
+  {
+    int ndx = 1, ndy = 1, cy = 0, cx = 0;
+    if (c >= 0) {
+      ndx = G->ndivx[0];
+      ndy = G->ndivx[1];
+      cy = c / ndx;
+      cx = c - cy * ndx;
+    }
+#pragma unroll
+    for (int sq = 0; sq < 3; ++sq) {
+      const Src<float2> U = make_src<float2>(sq == 0 ? su0 : (sq == 1 ? su1 : su2), S.upos[sq], nullptr, tgs[sq]);
+      const Src<double2> X = make_src<double2>(sq == 0 ? sx0 : (sq == 1 ? sx1 : sx2), S.pos[sq], nullptr, tgs[sq]);
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        mk[sq][r] = 0ull;
+        jbs[sq][r] = 0;
+        const int row = cy - 1 + r;
+        if (c < 0 || row < 0 || row >= ndy) continue;
+        const int b = S.start[sq][row * ndx + max(cx - 1, 0)], e = S.start[sq][row * ndx + min(cx + 1, ndx - 1) + 1];
+        const int len = e - b;
+        const int jb = tgs[sq].staged ? b - tgs[sq].base[r] + tgs[sq].off[r] : b;
+        jbs[sq][r] = jb;
+        if (len > (sq == SP_DUMMY && LISTS ? 32 : 64)) ovf |= 1;
+        const int n = min(len, 64);
+        u64 m = 0ull;
+        for (int i = 0; i < n; ++i) {
+          int cls = 2;
+          if (pf.on) cls = prefilter_test(pf, up, U(jb + i));
+          if (cls == 0) continue;
+          if (sq == SP && b + i == k) continue;
+          if (cls == 2) {
+            double dx, dy, d2, mh;
+            if (!pair_accept_fast(sk, pp, hp, X(jb + i), hp, dx, dy, d2, mh)) continue;
+          }
+          m |= 1ull << i;
+        }
+        mk[sq][r] = m;
+        const int na = __popcll(m);
+        ca += na;
+        // forward partners (creation order, main:1322-1341): later row, or own row from a threshold index on
+        if (r == 2)
+          cf += na;
+        else if (r == 1) {
+          const int fthr = (sq == SP) ? k + 1 : (sq > SP ? S.start[sq][c] : S.start[sq][c + 1]);
+          cf += popc_range(m, max(fthr - b, 0), 64);
+        }
+      }
+    }
+  }
+  // statistics: every pair is counted once, at the owner of its earlier member
+  const bool owned = !lflag || lflag[id] == 1;
+  {
+    u64 f = (live && c >= 0 && owned) ? (u64)cf : 0ull;
+    for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
+    if ((threadIdx.x & 31) == 0 && f) atomicAdd(acc_pairs, f);
+    if (live) nall[(SP == SP_NODE ? 0 : (SP == SP_STRESS ? nnp : L.nslots)) + k0] = owned ? (c >= 0 ? ca : 0) : -1;
+  }
+  if (!LISTS) {
+    if (__any_sync(0xffffffffu, ovf != 0) && (threadIdx.x & 31) == 0) atomicOr(&flags[0], 1);
+    return;
+  }
+  // ---- lists ----
+  u64 mA[3], mS[3], wsel[3] = {0ull, 0ull, 0ull};
+  unsigned mW[3];
+  int jA[3], jS[3], jW[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) {
+    mA[r] = mk[SQA][r];
+    mS[r] = mk[SP][r];
+    mW[r] = (unsigned)mk[SP_DUMMY][r];
+    jA[r] = jbs[SQA][r];
+    jS[r] = jbs[SP][r];
+    jW[r] = jbs[SP_DUMMY][r];
+  }
+  const bool wallp = (mW[0] | mW[1] | mW[2]) != 0u;
+  if (wallp) {  // interleaving of a row with wall partners: (cell, species, index) order, wall particles last in a cell
+    const int ndx = G->ndivx[0];
+    const int cy = c / ndx, cx = c - cy * ndx;
+    for (int r = 0; r < 3; ++r) {
+      if (!mW[r]) continue;
+      const int row = cy - 1 + r;
+      const int ca_ = row * ndx + max(cx - 1, 0), cb_ = row * ndx + min(cx + 1, ndx - 1);
+      const int bA = S.start[SQA][ca_], bW = S.start[SP_DUMMY][ca_];
+      int pos = 0;
+      u64 sel = 0ull;
+      for (int cq = ca_; cq <= cb_; ++cq) {
+        const int na = popc_range(mA[r], S.start[SQA][cq] - bA, S.start[SQA][cq + 1] - bA);
+        const int nw = popc_range((u64)mW[r], S.start[SP_DUMMY][cq] - bW, S.start[SP_DUMMY][cq + 1] - bW);
+        pos += na;
+        if (nw > 0) {
+          if (pos + nw > 64)
+            ovf |= 1;
+          else
+            sel |= ((nw >= 64 ? ~0ull : ((1ull << nw) - 1ull)) << pos);
+        }
+        pos += nw;
+      }
+      wsel[r] = sel;
+    }
+  }
+  const int cnt0 = __popcll(mA[0]) + __popcll(mA[1]) + __popcll(mA[2]) + __popc(mW[0]) + __popc(mW[1]) + __popc(mW[2]);
+  const int cnt1 = __popcll(mS[0]) + __popcll(mS[1]) + __popcll(mS[2]);
+  const int cap0 = ell0_cap(L, t);
+  if (cnt0 > cap0 || (SP == SP_NODE && cnt1 > L.capC)) ovf |= 2;
+  if (live) {
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      const size_t a = (size_t)r * L.nslots + t;
+      L.mA[a] = mA[r];
+      L.mS[a] = mS[r];
+      L.mW[a] = mW[r];
+      if (wallp) L.wsel[a] = wsel[r];
+    }
+    L.n0[t] = cnt0 | (wallp ? TILE_WALL_FLAG : 0);
+    L.n1[t] = cnt1;
+    if (SP == SP_NODE) {
+      bc_int[id] = wallp ? 1 : 0;                  // main:506,579
+      if (P.track_nint) n_int[id] = (float)cnt1;   // velocity-velocity interaction count (main:870-871 / 221-222)
+    }
+  }
+  {
+    int m0 = live ? cnt0 : 0, m1 = live ? cnt1 : 0;
+    m0 = warp_max_i(m0);
+    m1 = warp_max_i(m1);
+    const int o = warp_max_i(ovf);
+    if ((threadIdx.x & 31) == 0) {
+      if (o & 1) atomicOr(&flags[0], 1);
+      if (o & 2) atomicOr(&flags[4], 1);
+      atomicMax(&flags[SP == SP_NODE ? 1 : 2], m0);
+      if (SP == SP_NODE) atomicMax(&flags[3], m1);
+    }
+  }
+  // ---- weights, in traversal order; entries are evaluated in groups of four (independent division / sqrt chains) ----
+  const KernelConsts K = kernel_consts(P, hp);
+  const bool rv = rev != 0;
+  const Src<double2> XA = make_src<double2>(SQA == 0 ? sx0 : sx1, S.pos[SQA], nullptr, tgs[SQA]);
+  const Src<double2> XS = make_src<double2>(SP == 0 ? sx0 : sx1, S.pos[SP], nullptr, tgs[SP]);
+  const Src<double2> XW = make_src<double2>(sx2, S.pos[SP_DUMMY], nullptr, tgs[SP_DUMMY]);
+  const double2 *__restrict__ mrq = C.mrho[SQA];
+  const int *__restrict__ startA = S.start[SQA];
+  // global sorted index of a cross-species partner from its tile index (mass and density are read from global memory)
+  int gshift[3];
+#pragma unroll
+  for (int r = 0; r < 3; ++r) gshift[r] = tgs[SQA].staged ? tgs[SQA].base[r] - tgs[SQA].off[r] : 0;
+  (void)startA;
+  double nrm = 0.0, ae1 = 0.0, ae2 = 0.0, ae3 = 0.0, ae4 = 0.0;
+  {
+    const int n0w = (live && !(ovf & 2)) ? cnt0 : 0;
+    const int wrows = warp_max_i(n0w);
+    const bool anyw = __any_sync(0xffffffffu, wallp && n0w > 0);
+    Walk3 wk{mA[0], mA[1], mA[2], jA[0], jA[1], jA[2]};
+    WalkWall ww;
+    if (wallp && n0w > 0) ww.start(L, t, rv, jA, jW);
+    const size_t base = ell0_base(L, t);
+    for (int g = 0; g * 4 < wrows; ++g) {
+      float wv[4] = {0.f, 0.f, 0.f, 0.f}, gxv[4] = {0.f, 0.f, 0.f, 0.f}, gyv[4] = {0.f, 0.f, 0.f, 0.f};
+      double2 pq[4];
+      int jg[4];
+      bool isw[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        isw[u] = false;
+        jg[u] = -1;
+        pq[u] = pp;
+        if (g * 4 + u < n0w) {
+          int j;
+          if (anyw && wallp)
+            j = ww.next(L, t, rv, jA, jW, isw[u]);
+          else
+            j = wk.next(rv);
+          pq[u] = isw[u] ? XW(j) : XA(j);
+          if (!isw[u]) {  // global sorted index: which stencil row does the tile index belong to?
+            int gj = j;
+            if (tgs[SQA].staged) gj = j + (j >= tgs[SQA].off[2] ? gshift[2] : (j >= tgs[SQA].off[1] ? gshift[1] : gshift[0]));
+            jg[u] = gj;
+          }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (g * 4 + u >= n0w) continue;
+        double dx = pp.x - pq[u].x, dy = pp.y - pq[u].y;
+        double d2 = dx * dx;
+        d2 = d2 + dy * dy;
+        const double r = sqrt(d2);
+        // Pint_Update orientation (mat:1574-1634): pair_i = stress particle (type 1) or wall particle (types 6, 9)
+        const bool p_is_i = (SP == SP_STRESS && !isw[u]);
+        if (!p_is_i) {
+          dx = -dx;
+          dy = -dy;
+        }
+        double w, gx, gy;
+        sph_kernel_fast<true>(K, r, dx, dy, w, gx, gy);
+        wv[u] = (float)w;
+        gxv[u] = (float)gx;
+        gyv[u] = (float)gy;
+        if (!isw[u]) {
+          const double2 mr = mrq[jg[u]];
+          const double rr = __drcp_rn(mr.y);
+          nrm = nrm + div_rn((double)wv[u] * mr.x, mr.y, rr);  // cspm_norm, main:433
+          if (P.cspm) {  // CSPM matrix, main:539-550
+            const double gxd = (double)gxv[u], gyd = (double)gyv[u];
+            const double h1 = SP == SP_STRESS ? div_rn(gxd * mr.x, mr.y, rr) : div_rn(-gxd * mr.x, mr.y, rr);
+            const double h2 = SP == SP_STRESS ? div_rn(gyd * mr.x, mr.y, rr) : div_rn(-gyd * mr.x, mr.y, rr);
+            ae1 = ae1 + (pq[u].x - pp.x) * h1;
+            ae2 = ae2 + (pq[u].y - pp.y) * h1;
+            ae3 = ae3 + (pq[u].x - pp.x) * h2;
+            ae4 = ae4 + (pq[u].y - pp.y) * h2;
+          }
+        }
+      }
+      if (g * 4 < n0w) {
+        const size_t a = base + (size_t)g * 32;
+        L.w0[a] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+        L.gx0[a] = make_float4(gxv[0], gxv[1], gxv[2], gxv[3]);
+        L.gy0[a] = make_float4(gyv[0], gyv[1], gyv[2], gyv[3]);
+      }
+    }
+  }
+  if (SP == SP_NODE) {  // velocity-velocity list: gradient from this particle's perspective
+    const int n1w = (live && !(ovf & 2)) ? cnt1 : 0;
+    const int wrows = warp_max_i(n1w);
+    Walk3 wk{mS[0], mS[1], mS[2], jS[0], jS[1], jS[2]};
+    const size_t base = ellC_base(L, t);
+    for (int g = 0; g * 4 < wrows; ++g) {
+      float gxv[4] = {0.f, 0.f, 0.f, 0.f}, gyv[4] = {0.f, 0.f, 0.f, 0.f};
+      double2 pq[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        pq[u] = pp;
+        if (g * 4 + u < n1w) pq[u] = XS(wk.next(rv));
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (g * 4 + u >= n1w) continue;
+        const double dx = pp.x - pq[u].x, dy = pp.y - pq[u].y;
+        double d2 = dx * dx;
+        d2 = d2 + dy * dy;
+        const double r = sqrt(d2);
+        double w, gx, gy;
+        sph_kernel_fast<true>(K, r, dx, dy, w, gx, gy);
+        gxv[u] = (float)gx;
+        gyv[u] = (float)gy;
+      }
+      if (g * 4 < n1w) {
+        const size_t a = base + (size_t)g * 32;
+        L.gxC[a] = make_float4(gxv[0], gxv[1], gxv[2], gxv[3]);
+        L.gyC[a] = make_float4(gyv[0], gyv[1], gyv[2], gyv[3]);
+      }
+    }
+  }
+  if (!live) return;
+  norm[id] = nrm;
+  if (P.cspm) {  // inversion of the CSPM matrix, main:596-605
+    double ae5 = ae1 * ae4 - ae2 * ae3;
+    if (fabs(ae5) < P.ae_thr) {
+      ae5 = 1;
+      ae1 = 1;
+      ae2 = 0;
+      ae3 = 0;
+      ae4 = 1;
+    } else {
+      ae5 = 1 / ae5;
+    }
+    double *AEp = AE + 5 * (size_t)id;
+    AEp[0] = ae1;
+    AEp[1] = ae2;
+    AEp[2] = ae3;
+    AEp[3] = ae4;
+    AEp[4] = ae5;
+  }
+}
+
+__global__ void k_tile_status(const GridInfo *__restrict__ G, const int *__restrict__ start, int cell_stride,
+                              const int *__restrict__ nout, const u64 *__restrict__ acc_pairs,
+                              const int *__restrict__ flags, TileStatus *st) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st->n_pairs = (long long)*acc_pairs;
+  st->flags = (flags[0] ? 1 : 0) | (flags[4] ? 2 : 0);
+  st->max_n0n = flags[1];
+  st->max_n0s = flags[2];
+  st->max_n1n = flags[3];
+  st->ncell = G->ncell;
+  st->overflow = G->overflow;
+  for (int sp = 0; sp < 3; ++sp) st->nloc[sp] = start[sp * cell_stride + G->ncell] + nout[sp];
+}
+
+// sorted partner-visible records of one step (written in species-sorted order by the kernel preceding their reader)
+struct TileRecs {
+  double2 *NAs;  // [nn] velocity of a velocity particle: input of sweep A (stress side)
+  Rec4 *SAs;     // [ns] stress of a stress particle: input of sweep A (velocity side)
+  Rec4 *NBs;     // [nn] {vx, vy, m, rho}: input of sweep B (stress side), artificial viscosity, XSPH
+  Rec4 *SBs;     // [ns] {s1/rho^2, s2/rho^2, s3/rho^2, m}: input of sweep B (velocity side)
+  double2 *SVs;  // [ns] velocity of a stress particle after the final interpolation: XSPH
+};
+
+// targets per block of the pair-sum kernels: a tile of stress particles (two per velocity particle in the Bui layout)
+// is twice as large as a tile of velocity particles, so the velocity-particle side uses half the block
+constexpr int TS_T = 128;  // stress-particle side, artificial viscosity, position update
+constexpr int TN_T = 64;   // velocity-particle side of sweeps A and B
+#ifndef SPSPH_TILE_WARPS
+#define SPSPH_TILE_WARPS 16  // resident warps per SM requested from ptxas
+#endif
+#define TILE_MINB(T_) (SPSPH_TILE_WARPS * 32 / (T_))
+
+// block prologue shared by the pair-sum kernels: tile geometry of the partner species
+#define TILE_PROLOGUE(T_, TSP, QSP, CAP)                                                                   \
+  __shared__ TileGeom tg;                                                                                  \
+  const int kb0 = blockIdx.x * (T_);                                                                       \
+  const int nlive = (TSP) == SP_NODE ? M.nn : M.ns;                                                        \
+  if (kb0 >= nlive) return;                                                                                \
+  if (threadIdx.x == 0)                                                                                    \
+    tile_geom(G, S.cell[TSP][kb0], S.cell[TSP][min(kb0 + (T_), nlive) - 1], S.start[QSP], CAP, tg);        \
+  __syncthreads();
+
+// ------------------------------------------------------------------------------------------------------
+// Sweep A, stress-particle side (stress_point_update main:403-482: velocity of a stress particle from its velocity
+// particles; + adapt_stress2 / BCs that follow it). FROMB: input is the state between steps (SPH_shift, main:99-109).
+// ------------------------------------------------------------------------------------------------------
+constexpr int TA_SP_CAP = 384;
+template <bool FROMB>
+__global__ void __launch_bounds__(TS_T, TILE_MINB(TS_T))
+k_tile_a_sp(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, TileLists L, SortedConsts C,
+            TileRecs R, StatePtrs st, int rev, int do_adapt, int do_bc, int final_sweep) {
+  TILE_PROLOGUE(TS_T, SP_STRESS, SP_NODE, TA_SP_CAP)
+  __shared__ double2 sv[TA_SP_CAP];
+  __shared__ double smo[TA_SP_CAP];
+  if (tg.staged) {
+    if (FROMB) {
+      for (int r = 0; r < 3; ++r)
+        for (int i = threadIdx.x; i < tg.cnt[r]; i += blockDim.x) {
+          const Rec4 q = ldrec(st.NBr, S.order[0][tg.base[r] + i]);
+          sv[tg.off[r] + i] = make_double2(q.a, q.b);
+        }
+    } else {
+      stage_rows(sv, (const double2 *)R.NAs, nullptr, tg);
+    }
+    stage_rows(smo, C.mor[0], nullptr, tg);
+    __syncthreads();
+  }
+  const int k0 = kb0 + threadIdx.x;
+  const bool live = k0 < nlive;
+  const int k = live ? k0 : kb0;
+  const int t = M.nnp + k0;
+  const int id = S.order[1][k];
+  const int ks = id - P.nnode;
+  const int n0r = live ? L.n0[t] : 0;
+  const int cnt = n0r & ~TILE_WALL_FLAG;
+  const bool wallp = (n0r & TILE_WALL_FLAG) != 0;
+  const int wrows = warp_max_i(cnt);
+  const bool rv = rev != 0;
+  int jA[3], jW[3] = {0, 0, 0};
+  lane_bases(G, live ? S.cell[1][k] : -1, S.start[0], tg, jA);
+  double2 v;
+  Stress4 s;
+  if (FROMB) {
+    const Rec4 r = ldrec(st.SVbr, ks);
+    v = make_double2(r.a, r.b);
+    s = ld4(st.SFbr, ks);
+  } else {
+    v = ld2(st.SVa, ks);
+    const Rec4 r = R.SAs[k];
+    s = Stress4{r.a, r.b, r.c, r.d};
+  }
+  double vtx = 0.0, vty = 0.0;
+  {
+    Walk3 wk{0ull, 0ull, 0ull, jA[0], jA[1], jA[2]};
+    if (cnt > 0) {
+      wk.m0 = L.mA[t];
+      wk.m1 = L.mA[(size_t)L.nslots + t];
+      wk.m2 = L.mA[2 * (size_t)L.nslots + t];
+    }
+    WalkWall ww;
+    const bool anyw = __any_sync(0xffffffffu, wallp);
+    if (wallp) ww.start(L, t, rv, jA, jW);
+    const size_t base = ell0_base(L, t);
+    const int ng = (wrows + 3) >> 2;
+    float4 wn = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ng > 0) wn = ldcs4(L.w0 + base);
+    for (int g = 0; g < ng; ++g) {
+      const float4 wc = wn;
+      if (g + 1 < ng) wn = ldcs4(L.w0 + base + (size_t)(g + 1) * 32);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (g * 4 + u >= cnt) continue;
+        bool isw = false;
+        int j;
+        if (anyw && wallp)
+          j = ww.next(L, t, rv, jA, jW, isw);
+        else
+          j = wk.next(rv);
+        if (isw) continue;  // wall partners (type 9) take no part
+        double2 vq;
+        double mo;
+        if (tg.staged) {
+          vq = sv[j];
+          mo = smo[j];
+        } else {
+          if (FROMB) {
+            const Rec4 q = ldrec(st.NBr, S.order[0][j]);
+            vq = make_double2(q.a, q.b);
+          } else {
+            vq = R.NAs[j];
+          }
+          mo = C.mor[0][j];
+        }
+        const double h2 = mo * (double)f4c(wc, u);  // (mass(i)/rho(i))*w, main:431
+        vtx = vtx + vq.x * h2;
+        vty = vty + vq.y * h2;
+      }
+    }
+  }
+  if (!live) return;
+  const double nrm = st.norm[id];
+  if (nrm != 0) {
+    v.x = vtx / nrm;
+    v.y = vty / nrm;
+  }
+  if (do_adapt) adapt_stress(P, s);
+  if (do_bc) apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, v, s);
+  strec(st.SVb, ks, v.x, v.y, st.mor[id], 0.0);
+  st4(st.SFb, ks, s);
+  const double rr = st.rho[id];
+  const double r2 = rr * rr;
+  R.SBs[k] = Rec4{s.s1 / r2, s.s2 / r2, s.s3 / r2, st.mass[id]};
+  if (final_sweep) R.SVs[k] = v;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Sweep A, velocity-particle side (stress and plastic strain of a velocity particle from its stress particles).
+// ------------------------------------------------------------------------------------------------------
+constexpr int TA_N_CAP = 608;
+template <bool FROMB, bool EPSP>
+__global__ void __launch_bounds__(TN_T, TILE_MINB(TN_T))
+k_tile_a_node(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, TileLists L, SortedConsts C,
+              TileRecs R, StatePtrs st, int rev, int do_adapt, int do_bc, int final_sweep) {
+  TILE_PROLOGUE(TN_T, SP_NODE, SP_STRESS, TA_N_CAP)
+  __shared__ Rec4 ss[TA_N_CAP];
+  __shared__ double smo[TA_N_CAP];
+  __shared__ double sep[EPSP ? TA_N_CAP : 1];
+  if (tg.staged) {
+    if (FROMB) {
+      for (int r = 0; r < 3; ++r)
+        for (int i = threadIdx.x; i < tg.cnt[r]; i += blockDim.x)
+          ss[tg.off[r] + i] = ld256(st.SFbr + 4 * (size_t)(S.order[1][tg.base[r] + i] - P.nnode));
+    } else {
+      stage_rows(ss, (const Rec4 *)R.SAs, nullptr, tg);
+    }
+    stage_rows(smo, C.mor[1], nullptr, tg);
+    if (EPSP) stage_rows(sep, (const double *)st.epsp, S.order[1], tg);
+    __syncthreads();
+  }
+  const int k0 = kb0 + threadIdx.x;
+  const bool live = k0 < nlive;
+  const int k = live ? k0 : kb0;
+  const int t = k0;
+  const int id = S.order[0][k];
+  const int n0r = live ? L.n0[t] : 0;
+  const int cnt = n0r & ~TILE_WALL_FLAG;
+  const bool wallp = (n0r & TILE_WALL_FLAG) != 0;
+  const int wrows = warp_max_i(cnt);
+  const bool rv = rev != 0;
+  int jA[3], jW[3] = {0, 0, 0};
+  lane_bases(G, live ? S.cell[0][k] : -1, S.start[1], tg, jA);
+  double2 v;
+  Stress4 s;
+  if (FROMB) {
+    const Rec4 r = ldrec(st.NBr, id);
+    v = make_double2(r.a, r.b);
+    s = ld4(st.NSbr, id);
+  } else {
+    v = R.NAs[k];
+    s = ld4(st.NSa, id);
+  }
+  double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, te = 0.0;
+  {
+    Walk3 wk{0ull, 0ull, 0ull, jA[0], jA[1], jA[2]};
+    if (cnt > 0) {
+      wk.m0 = L.mA[t];
+      wk.m1 = L.mA[(size_t)L.nslots + t];
+      wk.m2 = L.mA[2 * (size_t)L.nslots + t];
+    }
+    WalkWall ww;
+    const bool anyw = __any_sync(0xffffffffu, wallp);
+    if (wallp) ww.start(L, t, rv, jA, jW);
+    const size_t base = ell0_base(L, t);
+    const int ng = (wrows + 3) >> 2;
+    float4 wn = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ng > 0) wn = ldcs4(L.w0 + base);
+    for (int g = 0; g < ng; ++g) {
+      const float4 wc = wn;
+      if (g + 1 < ng) wn = ldcs4(L.w0 + base + (size_t)(g + 1) * 32);
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (g * 4 + u >= cnt) continue;
+        bool isw = false;
+        int j;
+        if (anyw && wallp)
+          j = ww.next(L, t, rv, jA, jW, isw);
+        else
+          j = wk.next(rv);
+        if (isw) continue;  // wall partners (type 6) take no part
+        Rec4 q;
+        double mo, ep = 0.0;
+        if (tg.staged) {
+          q = ss[j];
+          mo = smo[j];
+          if (EPSP) ep = sep[j];
+        } else {
+          const int qid = S.order[1][j];
+          q = FROMB ? ld256(st.SFbr + 4 * (size_t)(qid - P.nnode)) : ldrec(R.SAs, j);
+          mo = C.mor[1][j];
+          if (EPSP) ep = st.epsp[qid];
+        }
+        const double h1 = mo * (double)f4c(wc, u);  // (mass(j)/rho(j))*w, main:430
+        t1 = t1 + q.a * h1;
+        t2 = t2 + q.b * h1;
+        t3 = t3 + q.c * h1;
+        t4 = t4 + q.d * h1;
+        if (EPSP) te = te + ep * h1;
+      }
+    }
+  }
+  if (!live) return;
+  const double nrm = st.norm[id];
+  if (nrm != 0) {
+    s.s1 = t1 / nrm;
+    s.s2 = t2 / nrm;
+    s.s3 = t3 / nrm;
+    s.s4 = t4 / nrm;
+    if (EPSP) st.epsp[id] = te / nrm;
+  } else {
+    v.x = 0;
+    v.y = 0;
+  }
+  if (do_adapt) adapt_stress(P, s);
+  if (do_bc) apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, v, s);
+  const double2 mr = C.mrho[0][k];
+  R.NBs[k] = Rec4{v.x, v.y, mr.x, mr.y};
+  if (final_sweep || FROMB) strec(st.NB, id, v.x, v.y, mr.x, mr.y);  // state between steps / input of k_rk_begin
+  st4(st.NSb, id, s);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Sweep B, stress-particle side: velocity gradient (main:519-525, wall term main:552-575), CSPM correction, div1,
+// plastic_terms, Jaumann terms, RK4 stage accumulation and next-stage predictor (or the final update).
+// ------------------------------------------------------------------------------------------------------
+constexpr int TB_SP_CAP = 384;
+__global__ void __launch_bounds__(TS_T, TILE_MINB(TS_T))
+k_tile_b_sp(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, TileLists L, SortedConsts C,
+            TileRecs R, StatePtrs st, int rev, double f1next, double f2, int last) {
+  TILE_PROLOGUE(TS_T, SP_STRESS, SP_NODE, TB_SP_CAP)
+  __shared__ Rec4 sn_[TB_SP_CAP];
+  __shared__ double srr[TB_SP_CAP];
+  if (tg.staged) {
+    stage_rows(sn_, (const Rec4 *)R.NBs, nullptr, tg);
+    stage_rows(srr, C.rrho[0], nullptr, tg);
+    __syncthreads();
+  }
+  const int k0 = kb0 + threadIdx.x;
+  const bool live = k0 < nlive;
+  const int k = live ? k0 : kb0;
+  const int t = M.nnp + k0;
+  const int id = S.order[1][k];
+  const int ks = id - P.nnode;
+  const int n0r = live ? L.n0[t] : 0;
+  const int cnt = n0r & ~TILE_WALL_FLAG;
+  const bool wallp = (n0r & TILE_WALL_FLAG) != 0;
+  const int wrows = warp_max_i(cnt);
+  const bool rv = rev != 0;
+  int jA[3], jW[3] = {0, 0, 0};
+  const int cl = live ? S.cell[1][k] : -1;
+  lane_bases(G, cl, S.start[0], tg, jA);
+  if (wallp) lane_rows(G, cl, S.start[2], jW);
+  const Rec4 selfv = ldrec(st.SVb, ks);
+  const double2 vp = make_double2(selfv.a, selfv.b);
+  const Stress4 sp_ = ld4(st.SFb, ks);
+  double g11 = 0.0, g12 = 0.0, g21 = 0.0, g22 = 0.0;  // grad1_tmp(d,k): d velocity component, k direction
+  {
+    Walk3 wk{0ull, 0ull, 0ull, jA[0], jA[1], jA[2]};
+    if (cnt > 0) {
+      wk.m0 = L.mA[t];
+      wk.m1 = L.mA[(size_t)L.nslots + t];
+      wk.m2 = L.mA[2 * (size_t)L.nslots + t];
+    }
+    WalkWall ww;
+    const bool anyw = __any_sync(0xffffffffu, wallp);
+    if (wallp) ww.start(L, t, rv, jA, jW);
+    const size_t base = ell0_base(L, t);
+    const int ng = (wrows + 3) >> 2;
+    float4 xn = make_float4(0.f, 0.f, 0.f, 0.f), yn = xn;
+    if (ng > 0) {
+      xn = ldcs4(L.gx0 + base);
+      yn = ldcs4(L.gy0 + base);
+    }
+    for (int g = 0; g < ng; ++g) {
+      const float4 xc = xn, yc = yn;
+      if (g + 1 < ng) {
+        xn = ldcs4(L.gx0 + base + (size_t)(g + 1) * 32);
+        yn = ldcs4(L.gy0 + base + (size_t)(g + 1) * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (g * 4 + u >= cnt) continue;
+        bool isw = false;
+        int j;
+        if (anyw && wallp)
+          j = ww.next(L, t, rv, jA, jW, isw);
+        else
+          j = wk.next(rv);
+        const double gx = (double)f4c(xc, u), gy = (double)f4c(yc, u);
+        if (!isw) {  // type 1: velocity particle {vx, vy, m, rho}
+          Rec4 q;
+          double rr;
+          if (tg.staged) {
+            q = sn_[j];
+            rr = srr[j];
+          } else {
+            q = ldrec(R.NBs, j);
+            rr = C.rrho[0][j];
+          }
+          const double h1 = div_rn(gx * q.c, q.d, rr);  // dwdx*mass(i)/rho(i), main:514
+          const double h2 = div_rn(gy * q.c, q.d, rr);
+          const double dvx = q.a - vp.x, dvy = q.b - vp.y;
+          g11 = g11 + dvx * h1;
+          g12 = g12 + dvx * h2;
+          g21 = g21 + dvy * h1;
+          g22 = g22 + dvy * h2;
+        } else {  // type 9: wall particle (no-slip mirror velocity), main:552-575
+          const int q = S.order[2][j];
+          const double2 xp = ld2(st.x, id);
+          const double beta_max = 1.5, vel_wall = 0.0;
+          const double wall = (double)st.wallpos[q];
+          const double2 xq = ld2(st.x, q);
+          double da, db;
+          if (st.horiz[q] == 1.f) {
+            da = fabs(xp.y - wall);
+            db = fabs(xq.y - wall);
+          } else {
+            da = fabs(xp.x - wall);
+            db = fabs(xq.x - wall);
+          }
+          const double bq = 1 + (db / da);
+          const double beta = (bq < beta_max) ? bq : beta_max;
+          const double dvx = vp.x * (1 - beta) + beta * vel_wall;
+          const double dvy = vp.y * (1 - beta) + beta * vel_wall;
+          const double mq = st.mass[q], rq = st.rho[q];
+          const double h1 = gx * mq / rq;
+          const double h2 = gy * mq / rq;
+          g11 = g11 + (vp.x - dvx) * h1;
+          g12 = g12 + (vp.x - dvx) * h2;
+          g21 = g21 + (vp.y - dvy) * h1;
+          g22 = g22 + (vp.y - dvy) * h2;
+        }
+      }
+    }
+  }
+  if (!live) return;
+  if (P.cspm) {
+    const double *AEp = st.AE + 5 * (size_t)id;
+    const double ae1 = AEp[0], ae2 = AEp[1], ae3 = AEp[2], ae4 = AEp[3], ae5 = AEp[4];
+    // main:619-622: the second statement sees the already-corrected first column
+    g11 = ae5 * (ae1 * g11 + ae2 * g12);
+    g12 = ae5 * (ae3 * g11 + ae4 * g12);
+    g21 = ae5 * (ae1 * g21 + ae2 * g22);
+    g22 = ae5 * (ae3 * g21 + ae4 * g22);
+  }
+  // div1, main:633-636
+  const double d1 = -(P.D11 * g11 + P.D12 * g22);
+  const double d2 = -(P.D12 * g11 + P.D22 * g22);
+  const double d3 = -(P.D33 * g21 + P.D33 * g12);
+  const double d4 = -(P.D41 * g11 + P.D42 * g22);
+  // plastic_terms, mat:1884-1954
+  double Gs[4] = {0.0, 0.0, 0.0, 0.0}, der1 = 0.0;
+  plastic_terms(P, sp_, g11, g12, g21, g22, st.epsp + id, st.fdp + id, Gs, der1);
+  const double rke = st.RKe[ks] + der1 * f2;
+  // Jaumann terms, main:751-757
+  double sp1 = 0.0, sp2 = 0.0, sp3 = 0.0, sp4 = 0.0;
+  if (P.update_x) {
+    const double o1 = 0.5 * (g12 - g21), o2 = -0.5 * (g12 - g21);
+    sp1 = 2 * o1 * sp_.s3;
+    sp2 = 2 * o2 * sp_.s3;
+    sp3 = o2 * sp_.s1 + o1 * sp_.s2;
+  }
+  const double r1 = -d1 + sp1 + Gs[0];
+  const double r2 = -d2 + sp2 + Gs[1];
+  const double r3 = -d3 + sp3 + Gs[2];
+  const double r4 = -d4 + sp4 + Gs[3];
+  Stress4 rk = ld4(st.RKs, ks);
+  rk.s1 = rk.s1 + f2 * r1;
+  rk.s2 = rk.s2 + f2 * r2;
+  rk.s3 = rk.s3 + f2 * r3;
+  rk.s4 = rk.s4 + f2 * r4;
+  const Stress4 s0 = ld4(st.stress0, ks);
+  Stress4 sn;
+  if (!last) {
+    st4(st.RKs, ks, rk);
+    st.RKe[ks] = rke;
+    sn.s1 = s0.s1 + f1next * (P.dt) * r1;
+    sn.s2 = s0.s2 + f1next * (P.dt) * r2;
+    sn.s3 = s0.s3 + f1next * (P.dt) * r3;
+    sn.s4 = s0.s4 + f1next * (P.dt) * r4;
+  } else {
+    sn.s1 = s0.s1 + (P.dt / 6) * rk.s1;
+    sn.s2 = s0.s2 + (P.dt / 6) * rk.s2;
+    sn.s3 = s0.s3 + (P.dt / 6) * rk.s3;
+    sn.s4 = s0.s4 + (P.dt / 6) * rk.s4;
+    // update_strain, mat:1864-1880 with Ddev_strn = RK_dev_strain/6 (main:799)
+    st.epsp[id] = st.epsp[id] + P.dt * (rke / 6);
+  }
+  if (P.adapt) adapt_stress(P, sn);
+  double2 vn = vp;
+  apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, vn, sn);
+  R.SAs[k] = Rec4{sn.s1, sn.s2, sn.s3, sn.s4};
+  st2(st.SVa, ks, vn);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Sweep B, velocity-particle side: (1/rho) grad sigma (main:529-536, wall term main:577-588), CSPM correction, div2,
+// gravity / damping, artificial viscosity of the stage, RK4 accumulation and predictor.
+// ------------------------------------------------------------------------------------------------------
+constexpr int TB_N_CAP = 608;
+__global__ void __launch_bounds__(TN_T, TILE_MINB(TN_T))
+k_tile_b_node(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, TileLists L, TileRecs R,
+              StatePtrs st, int rev, double f1next, double f2, int last, int extra_forces) {
+  TILE_PROLOGUE(TN_T, SP_NODE, SP_STRESS, TB_N_CAP)
+  __shared__ Rec4 ssb[TB_N_CAP];
+  if (tg.staged) {
+    stage_rows(ssb, (const Rec4 *)R.SBs, nullptr, tg);
+    __syncthreads();
+  }
+  const int k0 = kb0 + threadIdx.x;
+  const bool live = k0 < nlive;
+  const int k = live ? k0 : kb0;
+  const int t = k0;
+  const int id = S.order[0][k];
+  const int n0r = live ? L.n0[t] : 0;
+  const int cnt = n0r & ~TILE_WALL_FLAG;
+  const bool wallp = (n0r & TILE_WALL_FLAG) != 0;
+  const int wrows = warp_max_i(cnt);
+  const bool rv = rev != 0;
+  int jA[3], jW[3] = {0, 0, 0};
+  const int cl = live ? S.cell[0][k] : -1;
+  lane_bases(G, cl, S.start[1], tg, jA);
+  if (wallp) lane_rows(G, cl, S.start[2], jW);
+  const Rec4 self = R.NBs[k];  // {vx, vy, m, rho}
+  const double2 vp = make_double2(self.a, self.b);
+  const double rp = self.d;
+  const Stress4 sp_ = ld4(st.NSb, id);
+  const double r2p = rp * rp;
+  const double so1 = sp_.s1 / r2p, so2 = sp_.s2 / r2p, so3 = sp_.s3 / r2p;  // stress(1:3,i)/rho(i)**2
+  double a11 = 0.0, a12 = 0.0, a21 = 0.0, a22 = 0.0, a31 = 0.0, a32 = 0.0;  // grad2_tmp(s,k)
+  {
+    Walk3 wk{0ull, 0ull, 0ull, jA[0], jA[1], jA[2]};
+    if (cnt > 0) {
+      wk.m0 = L.mA[t];
+      wk.m1 = L.mA[(size_t)L.nslots + t];
+      wk.m2 = L.mA[2 * (size_t)L.nslots + t];
+    }
+    WalkWall ww;
+    const bool anyw = __any_sync(0xffffffffu, wallp);
+    if (wallp) ww.start(L, t, rv, jA, jW);
+    const size_t base = ell0_base(L, t);
+    const int ng = (wrows + 3) >> 2;
+    float4 xn = make_float4(0.f, 0.f, 0.f, 0.f), yn = xn;
+    if (ng > 0) {
+      xn = ldcs4(L.gx0 + base);
+      yn = ldcs4(L.gy0 + base);
+    }
+    for (int g = 0; g < ng; ++g) {
+      const float4 xc = xn, yc = yn;
+      if (g + 1 < ng) {
+        xn = ldcs4(L.gx0 + base + (size_t)(g + 1) * 32);
+        yn = ldcs4(L.gy0 + base + (size_t)(g + 1) * 32);
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (g * 4 + u >= cnt) continue;
+        bool isw = false;
+        int j;
+        if (anyw && wallp)
+          j = ww.next(L, t, rv, jA, jW, isw);
+        else
+          j = wk.next(rv);
+        const double gx = (double)f4c(xc, u), gy = (double)f4c(yc, u);
+        double q1, q2, q3, mq;
+        if (!isw) {  // type 1: stress particle {s1/rho^2, s2/rho^2, s3/rho^2, m}
+          const Rec4 q = tg.staged ? ssb[j] : ldrec(R.SBs, j);
+          q1 = q.a;
+          q2 = q.b;
+          q3 = q.c;
+          mq = q.d;
+        } else {  // type 6: the wall particle takes the velocity particle's stress (main:580)
+          const int q = S.order[2][j];
+          const double rq = st.rho[q];
+          mq = st.mass[q];
+          q1 = sp_.s1 / (rq * rq);
+          q2 = sp_.s2 / (rq * rq);
+          q3 = sp_.s3 / (rq * rq);
+        }
+        const double c1 = so1 + q1, c2 = so2 + q2, c3 = so3 + q3;
+        a11 = a11 - mq * (gx * c1);
+        a12 = a12 - mq * (gy * c1);
+        a21 = a21 - mq * (gx * c2);
+        a22 = a22 - mq * (gy * c2);
+        a31 = a31 - mq * (gx * c3);
+        a32 = a32 - mq * (gy * c3);
+      }
+    }
+  }
+  if (!live) return;
+  if (P.cspm) {
+    const double *AEp = st.AE + 5 * (size_t)id;
+    const double ae1 = AEp[0], ae2 = AEp[1], ae3 = AEp[2], ae4 = AEp[3], ae5 = AEp[4];
+    // main:623-626: only stress components 1..ndimn are corrected
+    a11 = ae5 * (ae1 * a11 + ae2 * a12);
+    a12 = ae5 * (ae3 * a11 + ae4 * a12);
+    a21 = ae5 * (ae1 * a21 + ae2 * a22);
+    a22 = ae5 * (ae3 * a21 + ae4 * a22);
+  }
+  const double dv1 = -(a11 + a32);  // div2, main:641-642
+  const double dv2 = -(a31 + a22);
+  // gravity_force, mat:2809-2871
+  const double sg1 = P.grav[0] - P.damping * vp.x;
+  const double sg2 = P.grav[1] - P.damping * vp.y;
+  // artificial viscosity of this stage (k_tile_av), zero when alpha = beta = 0 (art_visc stays 0, main:688)
+  double av1 = 0.0, av2 = 0.0;
+  if (P.alpha > 0 || P.beta > 0) {
+    const double2 a = ld2(st.av, id);
+    av1 = a.x;
+    av2 = a.y;
+  }
+  double2 fb = make_double2(0.0, 0.0), af = make_double2(0.0, 0.0);
+  if (extra_forces) {
+    fb = ld2(st.fbound, id);  // f_bound (main:764): zero unless boundary_forces ran
+    af = ld2(st.aforce, id);  // art_force: zero unless art_stress = T
+  }
+  const double r1 = -dv1 + sg1 + av1 + fb.x + af.x;
+  const double r2 = -dv2 + sg2 + av2 + fb.y + af.y;
+  double2 rk = ld2(st.RKv, id);
+  rk.x = rk.x + f2 * r1;
+  rk.y = rk.y + f2 * r2;
+  const double2 v0 = ld2(st.vel0, id);
+  double2 vn;
+  if (!last) {
+    st2(st.RKv, id, rk);
+    vn.x = v0.x + f1next * (P.dt) * r1;
+    vn.y = v0.y + f1next * (P.dt) * r2;
+  } else {
+    vn.x = v0.x + (P.dt / 6) * rk.x;
+    vn.y = v0.y + (P.dt / 6) * rk.y;
+  }
+  Stress4 sn = sp_;
+  if (P.adapt) adapt_stress(P, sn);
+  apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, vn, sn);
+  R.NAs[k] = vn;
+  st4(st.NSa, id, sn);
+}
+
+// ------------------------------------------------------------------------------------------------------
+// artificial_viscosity, main:826-904 (fp32 locals and accumulators in list order) over the velocity-velocity masks;
+// xij, yij are re-derived from the staged positions (the list path stored their fp32 roundings).
+// ------------------------------------------------------------------------------------------------------
+constexpr int TAV_CAP = 512;
+__global__ void __launch_bounds__(TS_T, TILE_MINB(TS_T))
+k_tile_av(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, TileLists L, TileRecs R, StatePtrs st,
+          int rev, float h_u) {
+  TILE_PROLOGUE(TS_T, SP_NODE, SP_NODE, TAV_CAP)
+  __shared__ Rec4 sn_[TAV_CAP];
+  __shared__ double2 sx[TAV_CAP];
+  if (tg.staged) {
+    stage_rows(sn_, (const Rec4 *)R.NBs, nullptr, tg);
+    stage_rows(sx, S.pos[0], nullptr, tg);
+    __syncthreads();
+  }
+  const int k0 = kb0 + threadIdx.x;
+  const bool live = k0 < nlive;
+  const int k = live ? k0 : kb0;
+  const int t = k0;
+  const int id = S.order[0][k];
+  const int cnt = live ? L.n1[t] : 0;
+  const int wrows = warp_max_i(cnt);
+  const bool rv = rev != 0;
+  int jS[3];
+  lane_bases(G, live ? S.cell[0][k] : -1, S.start[0], tg, jS);
+  const Rec4 self = R.NBs[k];
+  const double2 vp = make_double2(self.a, self.b);
+  const double rp = self.d;
+  const double2 pp = S.pos[0][k];
+  float acc1 = 0.f, acc2 = 0.f;
+  {
+    Walk3 wk{0ull, 0ull, 0ull, jS[0], jS[1], jS[2]};
+    if (cnt > 0) {
+      wk.m0 = L.mS[t];
+      wk.m1 = L.mS[(size_t)L.nslots + t];
+      wk.m2 = L.mS[2 * (size_t)L.nslots + t];
+    }
+    const size_t base = ellC_base(L, t);
+    const int ng = (wrows + 3) >> 2;
+    float4 xn = make_float4(0.f, 0.f, 0.f, 0.f), yn = xn;
+    if (ng > 0) {
+      xn = ldcs4(L.gxC + base);
+      yn = ldcs4(L.gyC + base);
+    }
+    for (int g = 0; g < ng; ++g) {
+      const float4 xc = xn, yc = yn;
+      if (g + 1 < ng) {
+        xn = ldcs4(L.gxC + base + (size_t)(g + 1) * 32);
+        yn = ldcs4(L.gyC + base + (size_t)(g + 1) * 32);
+      }
+      float visc[4];
+      double mqs[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {  // independent per entry: the division chains interleave
+        visc[u] = 0.f;
+        mqs[u] = 0.0;
+        if (g * 4 + u >= cnt) continue;
+        const int j = wk.next(rv);
+        Rec4 q;
+        double2 pq;
+        if (tg.staged) {
+          q = sn_[j];
+          pq = sx[j];
+        } else {
+          q = ldrec(R.NBs, j);
+          pq = S.pos[0][j];
+        }
+        mqs[u] = q.c;
+        const float xij = (float)(pp.x - pq.x), yij = (float)(pp.y - pq.y);  // main:856-857
+        const float h = h_u;
+        const float rho2 = (float)(0.5 * (rp + q.d));
+        const float cs = 600.f;
+        float div_u = (float)((double)xij * (vp.x - q.a));
+        div_u = (float)((double)div_u + (double)yij * (vp.y - q.b));
+        const float sq = sqrtf(xij * xij + yij * yij);
+        const float theta = (h * div_u) / (sq * sq + 0.01f * (h * h));
+        const double rho2d = (double)rho2;
+        const double num = -P.alpha * (double)cs * (double)theta + P.beta * (double)(theta * theta);
+        const float vv = (float)div_rn(num, rho2d, __drcp_rn(rho2d));
+        visc[u] = (div_u < 0) ? vv : 0.f;
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {  // ordered fp32 accumulation
+        if (g * 4 + u >= cnt) continue;
+        const float gxf = f4c(xc, u), gyf = f4c(yc, u);
+        acc1 = (float)((double)acc1 + (double)(visc[u] * gxf) * mqs[u]);
+        acc2 = (float)((double)acc2 + (double)(visc[u] * gyf) * mqs[u]);
+      }
+    }
+  }
+  if (!live) return;
+  st2(st.av, id, make_double2((double)(-acc1), (double)(-acc2)));  // art_visc = -art_visc_temp, main:901
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Position update, main:140-182: XSPH_update (main:189-239; w re-evaluated from the staged positions instead of
+// streamed: the same-species weights have no other reader) or the fp32 mid-velocity rule; displ.
+// One launch, warp-uniform role: velocity particles first, then stress particles.
+// ------------------------------------------------------------------------------------------------------
+constexpr int TMV_CAP = 640;
+__global__ void __launch_bounds__(TS_T, TILE_MINB(TS_T))
+k_tile_move(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, TileLists L, SortedConsts C,
+            TileRecs R, StatePtrs st, int rev, int nb_node, double *__restrict__ x, const double *__restrict__ x00,
+            double *__restrict__ displ) {
+  const bool is_node = (int)blockIdx.x < nb_node;  // block-uniform
+  const int sp = is_node ? SP_NODE : SP_STRESS;
+  __shared__ TileGeom tg;
+  __shared__ double2 sv[TMV_CAP], sx[TMV_CAP];
+  __shared__ double smo[TMV_CAP];
+  const int kb0 = (is_node ? blockIdx.x : blockIdx.x - nb_node) * TS_T;
+  const int nlive = is_node ? M.nn : M.ns;
+  if (kb0 >= nlive) return;
+  const bool xs = P.update_x && P.xsph;
+  if (threadIdx.x == 0) {
+    if (xs)
+      tile_geom(G, S.cell[sp][kb0], S.cell[sp][min(kb0 + TS_T, nlive) - 1], S.start[sp], TMV_CAP, tg);
+    else
+      tg.staged = 0;
+  }
+  __syncthreads();
+  if (xs && tg.staged) {
+    if (is_node) {
+      for (int r = 0; r < 3; ++r)
+        for (int i = threadIdx.x; i < tg.cnt[r]; i += blockDim.x) {
+          const Rec4 q = R.NBs[tg.base[r] + i];
+          sv[tg.off[r] + i] = make_double2(q.a, q.b);
+        }
+    } else {
+      stage_rows(sv, (const double2 *)R.SVs, nullptr, tg);
+    }
+    stage_rows(sx, S.pos[sp], nullptr, tg);
+    stage_rows(smo, C.mor[sp], nullptr, tg);
+    __syncthreads();
+  }
+  const int k0 = kb0 + threadIdx.x;
+  const bool live = k0 < nlive;
+  const int k = live ? k0 : kb0;
+  const int t = is_node ? k0 : M.nnp + k0;
+  const int id = S.order[sp][k];
+  double2 vp;
+  if (is_node) {
+    const Rec4 r = R.NBs[k];
+    vp = make_double2(r.a, r.b);
+  } else {
+    vp = R.SVs[k];
+  }
+  double sx_ = 0.0, sy_ = 0.0;
+  if (xs) {
+    const int cnt = live ? L.n1[t] : 0;
+    int jS[3];
+    lane_bases(G, live ? S.cell[sp][k] : -1, S.start[sp], tg, jS);
+    Walk3 wk{0ull, 0ull, 0ull, jS[0], jS[1], jS[2]};
+    if (cnt > 0) {
+      wk.m0 = L.mS[t];
+      wk.m1 = L.mS[(size_t)L.nslots + t];
+      wk.m2 = L.mS[2 * (size_t)L.nslots + t];
+    }
+    const double2 pp = S.pos[sp][k];
+    const KernelConsts K = kernel_consts(P, S.h[sp][k]);
+    const bool rv = rev != 0;
+    const int wrows = warp_max_i(cnt);
+    for (int e0 = 0; e0 < wrows; e0 += 4) {
+      double2 vq[4], pq[4];
+      double mo[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        vq[u] = vp;
+        pq[u] = pp;
+        mo[u] = 0.0;
+        if (e0 + u >= cnt) continue;
+        const int j = wk.next(rv);
+        if (tg.staged) {
+          vq[u] = sv[j];
+          pq[u] = sx[j];
+          mo[u] = smo[j];
+        } else {
+          if (is_node) {
+            const Rec4 q = ldrec(R.NBs, j);
+            vq[u] = make_double2(q.a, q.b);
+          } else {
+            vq[u] = R.SVs[j];
+          }
+          pq[u] = S.pos[sp][j];
+          mo[u] = C.mor[sp][j];
+        }
+      }
+      double wd[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double dx = pp.x - pq[u].x, dy = pp.y - pq[u].y;
+        double d2 = dx * dx;
+        d2 = d2 + dy * dy;
+        const double r = sqrt(d2);
+        double w, gx, gy;
+        sph_kernel_fast<false>(K, r, dx, dy, w, gx, gy);
+        wd[u] = (double)(float)w;  // pairs%w is fp32 (main:1376)
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        if (e0 + u >= cnt) continue;
+        sx_ = sx_ + mo[u] * (vq[u].x - vp.x) * wd[u];
+        sy_ = sy_ + mo[u] * (vq[u].y - vp.y) * wd[u];
+      }
+    }
+  }
+  if (!live) return;
+  const double2 xp = ld2(x, id);
+  if (P.update_x) {
+    double2 xn;
+    if (P.xsph) {
+      const double eps = 0.5;
+      xn.x = xp.x + P.dt * (vp.x + eps * sx_);
+      xn.y = xp.y + P.dt * (vp.y + eps * sy_);
+    } else {
+      const double2 v0 = ld2(st.vx0, id);
+      const float hx = (float)(0.5 * (v0.x + vp.x));  // real :: vel_half, main:89,145
+      const float hy = (float)(0.5 * (v0.y + vp.y));
+      xn.x = xp.x + (double)hx * P.dt;
+      xn.y = xp.y + (double)hy * P.dt;
+    }
+    st2(x, id, xn);
+    if (is_node) {
+      const double2 x0 = ld2(x00, id);
+      st2(displ, id, make_double2(xn.x - x0.x, xn.y - x0.y));  // main:171
+    }
+  } else if (is_node) {
+    const double2 v0 = ld2(st.vx0, id);
+    double2 d = ld2(displ, id);
+    d.x = d.x + 0.5 * (v0.x + vp.x) * P.dt;  // main:180
+    d.y = d.y + 0.5 * (v0.y + vp.y) * P.dt;
+    st2(displ, id, d);
+  }
+}
+
+}  // namespace spsph

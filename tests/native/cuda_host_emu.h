@@ -213,6 +213,17 @@ static inline void __syncwarp(unsigned = 0xffffffffu) { emu_warp_barrier(); }
 static inline void __syncthreads() { emu_block_barrier(); }
 #endif
 static inline int __popc(unsigned v) { return __builtin_popcount(v); }
+static inline int __popcll(unsigned long long v) { return __builtin_popcountll(v); }
+static inline int __ffs(int v) { return __builtin_ffs(v); }
+static inline int __ffsll(long long v) { return __builtin_ffsll(v); }
+static inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
+static inline int __clzll(long long v) { return v ? __builtin_clzll((unsigned long long)v) : 64; }
+template <class T>
+static inline T atomicOr(T *p, T v) {
+  const T o = *p;
+  *p = o | v;
+  return o;
+}
 template <class T>
 static inline T atomicAdd(T *p, T v) {
   const T o = *p;
