@@ -35,6 +35,7 @@ def cuda_lib():
         L.spsph_sync.argtypes = [H]
         L.spsph_get_list_capacity.argtypes = [H, C.POINTER(C.c_int64)]
         L.spsph_set_list_capacity.argtypes = [H, C.c_int64]
+        L.spsph_path_counts.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.spsph_dist_unique_id.argtypes = [C.c_char_p]
         L.spsph_dist_init.argtypes = [H, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_double), C.c_int32, C.c_int32]
         L.spsph_dist_flags.argtypes = [H, C.c_void_p]
@@ -52,7 +53,7 @@ def cuda_lib():
 EXPORTS = ["spsph_create", "spsph_upload", "spsph_step", "spsph_run", "spsph_download", "spsph_pair_stats",
            "spsph_pairs", "spsph_last_run_ms", "spsph_sync", "spsph_profile", "spsph_profile_get",
            "spsph_dist_unique_id", "spsph_dist_init", "spsph_dist_flags", "spsph_local_counts", "spsph_get_list_capacity",
-           "spsph_set_list_capacity", "spsph_destroy", "spsph_last_error", "spsph_version"]
+           "spsph_set_list_capacity", "spsph_path_counts", "spsph_destroy", "spsph_last_error", "spsph_version"]
 
 
 def dist_unique_id():
@@ -139,6 +140,12 @@ class Engine:
         n = C.c_int64()
         self._chk(self.L.spsph_get_list_capacity(self.h, C.byref(n)))
         return n.value
+
+    def path_counts(self):
+        """(steps on the cell-tile kernels, steps on the id-list kernels) since the engine was created"""
+        a, b = C.c_int64(), C.c_int64()
+        self._chk(self.L.spsph_path_counts(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
 
     def set_list_capacity(self, m_pairs):
         self._chk(self.L.spsph_set_list_capacity(self.h, int(m_pairs)))

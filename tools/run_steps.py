@@ -39,7 +39,7 @@ if a.profile:
 eng.run(1 + a.warmup, t0, dt, a.steps)
 ms, n = eng.last_run()
 print(f"{a.kind} ncol={a.ncol}: {prob.params.ntotal} particles, {a.steps} steps, {ms / a.steps:.3f} ms/step, "
-      f"{n} launches, {eng.pair_stats()}")
+      f"{n} launches, {eng.pair_stats()}, tile/list steps {eng.path_counts()}")
 if a.profile:
     for k, (t, c) in eng.profile_get().items():
         if c:
