@@ -153,7 +153,9 @@ struct spsph_handle {
   double2 *smrho = nullptr;                  // ... and {mass, rho}
   long long tile_w0_cap = 0, tile_c_cap = 0; // allocated float4 groups
   u64 *tile_acc = nullptr;                   // device: forward pair count of the step
-  int *tile_flags = nullptr;                 // device: [0] mask overflow, [1..3] longest lists, [4] slice overflow
+  int *tile_flags = nullptr;                 // device: [0] mask overflow, [1..4] longest lists, [5] slice overflow
+  GeomTables GT{};                           // per-block tile geometry of the pair-sum kernels, rebuilt every step
+  long long tile_s_cap = 0;
   TileStatus *tstat_d = nullptr, *tstat_h = nullptr;
   long long tile_steps = 0, list_steps = 0;  // which path the steps took (spsph_path_counts)
 
@@ -886,12 +888,16 @@ static int tile_alloc_weights(spsph_handle *h) {
   TileLists &T = h->TL;
   const long long g0 = ((long long)T.nsl_n * (T.capN0 >> 2) + (long long)(h->M.nsp / SLICE) * (T.capS0 >> 2)) * 32 + 64;
   const long long gc = (long long)T.nsl_n * (T.capC >> 2) * 32 + 64;
+  const long long gs = ((long long)T.nsl_n * (T.capC >> 2) + (long long)(h->M.nsp / SLICE) * (T.capD >> 2)) * 32 + 64;
   if (g0 > h->tile_w0_cap) {
     cudaFree(T.w0);
     cudaFree(T.gx0);
     cudaFree(T.gy0);
+    cudaFree(T.code0);
     T.w0 = T.gx0 = T.gy0 = nullptr;
+    T.code0 = nullptr;
     h->tile_w0_cap = 0;
+    CUDA_TRY(cudaMalloc((void **)&T.code0, (size_t)g0 * sizeof(unsigned)));
     CUDA_TRY(cudaMalloc((void **)&T.w0, (size_t)g0 * sizeof(float4)));
     CUDA_TRY(cudaMalloc((void **)&T.gx0, (size_t)g0 * sizeof(float4)));
     CUDA_TRY(cudaMalloc((void **)&T.gy0, (size_t)g0 * sizeof(float4)));
@@ -906,12 +912,19 @@ static int tile_alloc_weights(spsph_handle *h) {
     CUDA_TRY(cudaMalloc((void **)&T.gyC, (size_t)gc * sizeof(float4)));
     h->tile_c_cap = gc;
   }
+  if (gs > h->tile_s_cap) {
+    cudaFree(T.codeS);
+    T.codeS = nullptr;
+    h->tile_s_cap = 0;
+    CUDA_TRY(cudaMalloc((void **)&T.codeS, (size_t)gs * sizeof(unsigned)));
+    h->tile_s_cap = gs;
+  }
   return 0;
 }
 
 // one-time allocations of the tile path (sizes depend on the particle counts only)
 static int tile_setup(spsph_handle *h) {
-  if (h->TL.mA) return 0;
+  if (h->TL.rowA) return 0;
   const size_t nsl = (size_t)h->M.nnp + h->M.nsp, n2 = (size_t)h->P.ntotal2;
   TileLists &T = h->TL;
   T.nslots = (int)nsl;
@@ -919,9 +932,12 @@ static int tile_setup(spsph_handle *h) {
   T.capN0 = 48;
   T.capS0 = 28;
   T.capC = 28;
+  T.capD = 44;
   T.n0 = h->n0;
   T.n1 = h->n1;
-  int rc = dalloc(h, &T.mA, 3 * nsl) | dalloc(h, &T.mS, 3 * nsl) | dalloc(h, &T.wsel, 3 * nsl) | dalloc(h, &T.mW, 3 * nsl);
+  int rc = dalloc(h, &T.rowA, 3 * nsl) | dalloc(h, &T.rowS, 3 * nsl) | dalloc(h, &T.mW, 3 * nsl);
+  rc |= dalloc(h, &h->GT.g[0], (size_t)h->M.nsp / TS_T + 2) | dalloc(h, &h->GT.g[1], (size_t)h->M.nnp / TN_T + 2);
+  rc |= dalloc(h, &h->GT.g[2], (size_t)h->M.nnp / TS_T + 2) | dalloc(h, &h->GT.g[3], (size_t)h->M.nsp / TS_T + 2);
   rc |= dalloc(h, &h->smor, 2 * n2) | dalloc(h, &h->srrho, 2 * n2) | dalloc(h, &h->smrho, 2 * n2);
   rc |= dalloc(h, &h->TR.NAs, (size_t)h->M.nnp) | dalloc(h, &h->TR.NBs, (size_t)h->M.nnp);
   rc |= dalloc(h, &h->TR.SAs, (size_t)h->M.nsp) | dalloc(h, &h->TR.SBs, (size_t)h->M.nsp) | dalloc(h, &h->TR.SVs, (size_t)h->M.nsp);
@@ -952,6 +968,8 @@ int tile_build(spsph_handle *h, bool *use) {
   const SortArrays S = sort_arrays(h);
   const SortedConsts C = sorted_consts(h);
   const int rev = h->m_pairs == 0 ? 1 : 0;  // first step after an upload: every list node is new (main:1362-1368)
+  const int want_c = (P.alpha > 0 || P.beta > 0) ? 1 : 0;  // velocity-velocity gradients: artificial viscosity
+  const int want_s = (P.update_x && P.xsph) ? 1 : 0;       // same-species entries: XSPH
   TileStatus st{};
   for (int attempt = 0; attempt < 2; ++attempt) {
     CUDA_TRY(cudaMemsetAsync(h->tile_acc, 0, 2 * sizeof(u64), s));
@@ -960,20 +978,20 @@ int tile_build(spsph_handle *h, bool *use) {
     slot_bounds(h, bound);
     if (bound[0] > 0)
       k_tile_build<SP_NODE><<<(bound[0] + TB_T - 1) / TB_T, TB_T, 0, s>>>(
-          P, h->G, S, h->TL, C, h->M.nnp, rev, lflag, h->nout, h->nall, h->bc_int, h->n_int, h->norm, h->AE,
+          P, h->G, S, h->TL, C, h->M.nnp, rev, want_c, want_s, lflag, h->nout, h->nall, h->bc_int, h->n_int, h->norm, h->AE,
           h->tile_acc, h->tile_flags);
     if (bound[1] > 0)
       k_tile_build<SP_STRESS><<<(bound[1] + TB_T - 1) / TB_T, TB_T, 0, s>>>(
-          P, h->G, S, h->TL, C, h->M.nnp, rev, lflag, h->nout, h->nall, h->bc_int, h->n_int, h->norm, h->AE,
+          P, h->G, S, h->TL, C, h->M.nnp, rev, want_c, want_s, lflag, h->nout, h->nall, h->bc_int, h->n_int, h->norm, h->AE,
           h->tile_acc, h->tile_flags);
     if (bound[2] > 0)
       k_tile_build<SP_DUMMY><<<(bound[2] + TB_T - 1) / TB_T, TB_T, 0, s>>>(
-          P, h->G, S, h->TL, C, h->M.nnp, rev, lflag, h->nout, h->nall, h->bc_int, h->n_int, h->norm, h->AE,
+          P, h->G, S, h->TL, C, h->M.nnp, rev, want_c, want_s, lflag, h->nout, h->nall, h->bc_int, h->n_int, h->norm, h->AE,
           h->tile_acc, h->tile_flags);
     mark(h, KID_TBUILD, 3);
     if (h->dist) {  // all ranks must take the same path: global pair count and overflow flags
       NCCL_TRY(h->p_ncclAllReduce(h->tile_acc, h->tile_acc, 1, ncclInt64, ncclSum, h->comm, s));
-      NCCL_TRY(h->p_ncclAllReduce(h->tile_flags, h->tile_flags, 5, ncclInt32, ncclMax, h->comm, s));
+      NCCL_TRY(h->p_ncclAllReduce(h->tile_flags, h->tile_flags, 6, ncclInt32, ncclMax, h->comm, s));
     }
     k_tile_status<<<1, 32, 0, s>>>(h->G, h->cell_start, h->cell_stride, h->nout, h->tile_acc, h->tile_flags, h->tstat_d);
     mark(h, KID_STATUS);
@@ -999,8 +1017,14 @@ int tile_build(spsph_handle *h, bool *use) {
     auto fit = [](int need, int cap) { return need > cap ? ((need + need / 4 + 4 + 3) & ~3) : cap; };
     h->TL.capN0 = fit(st.max_n0n, h->TL.capN0);
     h->TL.capS0 = fit(st.max_n0s, h->TL.capS0);
-    h->TL.capC = fit(st.max_n1n, h->TL.capC);
+    if (want_c || want_s) h->TL.capC = fit(st.max_n1n, h->TL.capC);
+    if (want_s) h->TL.capD = fit(st.max_n1s, h->TL.capD);
     if (tile_alloc_weights(h)) return 1;
+  }
+  {  // tile geometry of every block of the pair-sum kernels
+    const int nb = std::max((h->M.nsp + TS_T - 1) / TS_T, (h->M.nnp + TN_T - 1) / TN_T);
+    k_tile_geoms<<<dim3((nb + 127) / 128, 4), 128, 0, s>>>(h->G, S, h->nout, h->GT, TB_SP_CAP, TB_N_CAP, TAV_CAP, TMV_CAP);
+    mark(h, KID_TBUILD);
   }
   // list-growth rule: forward order unless the list grew; a list that grows after the first step
   // is walked in split order, which only the list path implements
@@ -1045,8 +1069,8 @@ int tile_step(spsph_handle *h, int itimestep) {
   if (p.sph_shift && itimestep > 1 && ((itimestep - 1) % p.shift_update == 0)) {
     const StatePtrs sw = state_ptrs(h, 1 - h->cur);
     fork();
-    if (GSs) k_tile_a_sp<true><<<GSs, TS_T, 0, s>>>(P, M, h->G, S, L, C, R, sw, rev, adapt, 0, 0);
-    if (GNn) k_tile_a_node<true, true><<<GNn, TN_T, 0, s2>>>(P, M, h->G, S, L, C, R, sw, rev, adapt, 0, 0);
+    if (GSs) k_tile_a_sp<true><<<GSs, TS_T, 0, s>>>(P, M, S, L, C, R, sw, h->GT.g[0], adapt, 0, 0);
+    if (GNn) k_tile_a_node<true, true><<<GNn, TN_T, 0, s2>>>(P, M, S, L, C, R, sw, h->GT.g[1], adapt, 0, 0);
     join();
     mark(h, KID_SWEEPA, 2);
     h->cur = 1 - h->cur;
@@ -1064,28 +1088,28 @@ int tile_step(spsph_handle *h, int itimestep) {
   const bool artv = (P.alpha > 0 || P.beta > 0);
   for (int stg = 0; stg < 4; ++stg) {
     fork();
-    if (GSs) k_tile_a_sp<false><<<GSs, TS_T, 0, s>>>(P, M, h->G, S, L, C, R, st, rev, adapt, bc, 0);
-    if (GNn) k_tile_a_node<false, false><<<GNn, TN_T, 0, s2>>>(P, M, h->G, S, L, C, R, st, rev, adapt, bc, 0);
+    if (GSs) k_tile_a_sp<false><<<GSs, TS_T, 0, s>>>(P, M, S, L, C, R, st, h->GT.g[0], adapt, bc, 0);
+    if (GNn) k_tile_a_node<false, false><<<GNn, TN_T, 0, s2>>>(P, M, S, L, C, R, st, h->GT.g[1], adapt, bc, 0);
     join();
     mark(h, KID_SWEEPA, 2);
     const int last = (stg == 3);
     const double f1n = last ? 0.0 : f1rk[stg + 1];
     fork();
-    if (GSs) k_tile_b_sp<<<GSs, TS_T, 0, s>>>(P, M, h->G, S, L, C, R, st, rev, f1n, f2rk[stg], last);
-    if (artv && GNs) k_tile_av<<<GNs, TS_T, 0, s2>>>(P, M, h->G, S, L, R, st, rev, h->h_uniform);
-    if (GNn) k_tile_b_node<<<GNn, TN_T, 0, s2>>>(P, M, h->G, S, L, R, st, rev, f1n, f2rk[stg], last, extra);
+    if (GSs) k_tile_b_sp<<<GSs, TS_T, 0, s>>>(P, M, h->G, S, L, C, R, st, h->GT.g[0], rev, f1n, f2rk[stg], last);
+    if (artv && GNs) k_tile_av<<<GNs, TS_T, 0, s2>>>(P, M, S, L, R, st, h->GT.g[2], h->h_uniform);
+    if (GNn) k_tile_b_node<<<GNn, TN_T, 0, s2>>>(P, M, h->G, S, L, R, st, h->GT.g[1], rev, f1n, f2rk[stg], last, extra);
     join();
     mark(h, KID_SWEEPB, artv ? 3 : 2);
   }
   // final stress_point_update + adapt_stress2 + BCs, main:130-135
   fork();
-  if (GSs) k_tile_a_sp<false><<<GSs, TS_T, 0, s>>>(P, M, h->G, S, L, C, R, st, rev, adapt, bc, 1);
-  if (GNn) k_tile_a_node<false, true><<<GNn, TN_T, 0, s2>>>(P, M, h->G, S, L, C, R, st, rev, adapt, bc, 1);
+  if (GSs) k_tile_a_sp<false><<<GSs, TS_T, 0, s>>>(P, M, S, L, C, R, st, h->GT.g[0], adapt, bc, 1);
+  if (GNn) k_tile_a_node<false, true><<<GNn, TN_T, 0, s2>>>(P, M, S, L, C, R, st, h->GT.g[1], adapt, bc, 1);
   join();
   mark(h, KID_SWEEPA, 2);
   // positions, main:140-182
   if (GNs + GSs)
-    k_tile_move<<<GNs + GSs, TS_T, 0, s>>>(P, M, h->G, S, L, C, R, st, rev, GNs, h->x, h->x00, h->displ);
+    k_tile_move<<<GNs + GSs, TS_T, 0, s>>>(P, M, S, L, C, R, st, h->GT.g[2], h->GT.g[3], GNs, h->x, h->x00, h->displ);
   mark(h, KID_MOVE);
   if (h->x_fs && !h->dist) {
     CUDA_TRY(cudaMemcpyAsync(h->x_fs, h->x, 2 * (size_t)P.ntotal2 * sizeof(double), cudaMemcpyDeviceToDevice, s));
@@ -1970,6 +1994,8 @@ int spsph_destroy(spsph_handle *h) {
   cudaFree(h->L.gyC);
   cudaFree(h->L.idxD);
   cudaFree(h->L.wD);
+  cudaFree(h->TL.code0);
+  cudaFree(h->TL.codeS);
   cudaFree(h->TL.w0);
   cudaFree(h->TL.gx0);
   cudaFree(h->TL.gy0);

@@ -2,9 +2,9 @@
 //
 // Restricted to one particle, the reference's pair order is "partners sorted by (cell id, particle index)"
 // (grid_find_NEW main:1322-1396), and a row of the 3x3 cell stencil is ONE contiguous range of the
-// cell-sorted particle arrays. So instead of a list of partner ids (round 1: 4 bytes + one scattered 32-byte gather
-// per entry and sweep) a particle keeps, per stencil row, a 64-bit ACCEPTANCE MASK over that row's candidates; the
-// partner of list entry e is implied by the e-th set bit. The records the partners expose (velocity of a velocity
+// cell-sorted particle arrays. So instead of a partner id (round 1: 4 bytes + one scattered 32-byte gather per entry
+// and sweep) a list entry is ONE BYTE: stencil row (2 bits) + position of the partner among that row's candidates
+// (6 bits); the build derives it from per-row 64-bit acceptance masks. The records the partners expose (velocity of a velocity
 // particle, stress of a stress particle, ...) are written in cell-sorted order by the kernel that precedes their
 // reader, so a block of consecutive sorted particles stages the three candidate ranges it needs in shared memory
 // with contiguous, coalesced loads and every lane then reads its partners from shared memory. What is still
@@ -29,22 +29,25 @@ namespace spsph {
 typedef unsigned long long u64;
 
 struct TileLists {
-  // per list-owning thread slot t (velocity particles [0, nnp), stress particles [nnp, nnp + nsp)), one value per
-  // stencil row r = 0, 1, 2 (grid rows cy-1, cy, cy+1) at [r * nslots + t]; bit i of a row mask = candidate
-  // start[species][row*ndx + max(cx-1, 0)] + i of the species-sorted arrays
-  u64 *mA;       // cross-species partners (velocity <- stress, stress <- velocity): pair type 1
-  u64 *mS;       // same-species partners: types 3 (velocity-velocity) and 2 (stress-stress)
-  unsigned *mW;  // wall-particle partners: types 6 and 9
-  u64 *wsel;     // rows with wall partners: bit i = the i-th accepted entry of the row (cell, species, index order) is a wall particle
-  int *n0, *n1;  // entries of list 0 (cross-species + wall; bit 30: has wall partners) and of the same-species list
-  // fp32 pair weights, groups of four consecutive entries per lane: entries 4g..4g+3 of slot t at [(G0(t/32) + g)*32 + t%32]
-  float4 *w0, *gx0, *gy0;  // list 0: w, dwdx, dwdy in the reference's orientation after Pint_Update
+  // per list-owning thread slot t (velocity particles [0, nnp), stress particles [nnp, nnp + nsp)); stencil row
+  // r = 0, 1, 2 (grid rows cy-1, cy, cy+1) at [r * nslots + t]
+  int *rowA;     // first cross-species candidate of the row: start[partner species][row*ndx + max(cx-1, 0)]
+  int *rowS;     // first same-species candidate of the row
+  unsigned *mW;  // acceptance mask over the row's wall particles (read only by particles with wall partners)
+  int *n0, *n1;  // entries of list 0 (cross-species + wall, bit 30: has wall partners) and of the same-species list
+  // list entries in traversal order, groups of four consecutive entries per lane: entries 4g..4g+3 of slot t at
+  // [(G(t/32) + g)*32 + t%32]. code byte: row << 6 | candidate position within the row; 0xC0: wall particle (the
+  // wall partners are the set bits of mW in the same traversal order)
+  unsigned *code0, *codeS;
+  float4 *w0, *gx0, *gy0;  // list 0: w, dwdx, dwdy (fp32, main:1376-1378) in the reference's orientation after Pint_Update
   float4 *gxC, *gyC;       // velocity-velocity list: own-perspective gradient (artificial_viscosity)
-  int capN0, capS0, capC;  // rows per 32-slot slice (multiples of 4): list 0 of velocity / stress particles, list C
+  int capN0, capS0;        // rows per 32-slot slice (multiples of 4): list 0 of velocity / stress particles
+  int capC, capD;          // ... same-species list of velocity / stress particles
   int nsl_n;               // slices of velocity particles (nnp / 32)
   int nslots;              // nnp + nsp
 };
 constexpr int TILE_WALL_FLAG = 1 << 30;
+constexpr unsigned TILE_CODE_WALL = 0xC0u;
 
 __device__ __forceinline__ size_t ell0_base(const TileLists &L, int t) {
   const int sl = t >> 5;
@@ -52,10 +55,14 @@ __device__ __forceinline__ size_t ell0_base(const TileLists &L, int t) {
                                  : (size_t)L.nsl_n * (L.capN0 >> 2) + (size_t)(sl - L.nsl_n) * (L.capS0 >> 2);
   return g0 * 32 + (t & 31);
 }
-__device__ __forceinline__ size_t ellC_base(const TileLists &L, int t) {
-  return (size_t)(t >> 5) * (L.capC >> 2) * 32 + (t & 31);
+__device__ __forceinline__ size_t ellS_base(const TileLists &L, int t) {
+  const int sl = t >> 5;
+  const size_t g0 = sl < L.nsl_n ? (size_t)sl * (L.capC >> 2)
+                                 : (size_t)L.nsl_n * (L.capC >> 2) + (size_t)(sl - L.nsl_n) * (L.capD >> 2);
+  return g0 * 32 + (t & 31);
 }
 __device__ __forceinline__ int ell0_cap(const TileLists &L, int t) { return (t >> 5) < L.nsl_n ? L.capN0 : L.capS0; }
+__device__ __forceinline__ int ellS_cap(const TileLists &L, int t) { return (t >> 5) < L.nsl_n ? L.capC : L.capD; }
 
 // species-sorted copies of per-particle constants (written by k_rank_consts once per step): partners read them from a
 // staged tile like the state records
@@ -122,16 +129,6 @@ __device__ __forceinline__ void lane_rows(const GridInfo *__restrict__ G, int c,
     if (row >= 0 && row < ndy) b[r] = start_q[row * ndx + max(cx - 1, 0)];
   }
 }
-// index of mask bit 0 of each stencil row in the staged tile (or in the global sorted array when not staged)
-__device__ __forceinline__ void lane_bases(const GridInfo *__restrict__ G, int c, const int *__restrict__ start_q,
-                                           const TileGeom &g, int (&jb)[3]) {
-  lane_rows(G, c, start_q, jb);
-  if (g.staged) {
-#pragma unroll
-    for (int r = 0; r < 3; ++r) jb[r] = jb[r] - g.base[r] + g.off[r];
-  }
-}
-
 // cooperative copy of the three candidate ranges into shared memory; idx != nullptr: the source is indexed by particle
 // number (state between steps) and idx is the sorted order
 template <class T>
@@ -157,100 +154,46 @@ __device__ __forceinline__ Src<T> make_src(const T *sm, const T *g, const int *i
   return tg.staged ? Src<T>{sm, nullptr} : Src<T>{g, idx};
 }
 
-// ------------------------------------------------------------------------------------------------------
-// Walking the accepted candidates of a particle in traversal order.
-// ------------------------------------------------------------------------------------------------------
-struct Walk3 {  // three row masks; forward: rows 0..2, bits ascending; reversed: rows 2..0, bits descending
-  u64 m0, m1, m2;
-  int j0, j1, j2;
-  __device__ __forceinline__ int next(bool rev) {
-    if (!rev) {
-      if (m0) {
-        const int b = __ffsll((long long)m0) - 1;
-        m0 &= m0 - 1;
-        return j0 + b;
-      }
-      if (m1) {
-        const int b = __ffsll((long long)m1) - 1;
-        m1 &= m1 - 1;
-        return j1 + b;
-      }
-      const int b = __ffsll((long long)m2) - 1;
-      m2 &= m2 - 1;
-      return j2 + b;
-    }
-    if (m2) {
-      const int b = 63 - __clzll((long long)m2);
-      m2 ^= 1ull << b;
-      return j2 + b;
-    }
-    if (m1) {
-      const int b = 63 - __clzll((long long)m1);
-      m1 ^= 1ull << b;
-      return j1 + b;
-    }
-    const int b = 63 - __clzll((long long)m0);
-    m0 ^= 1ull << b;
-    return j0 + b;
-  }
-};
 
-// list 0 of a particle with wall partners: within a stencil row the reference visits, cell by cell, the cross-species
-// partners of the cell and then its wall particles; `sel` holds that interleaving. Row data are loaded when the walk
-// enters the row (rare path: only particles next to a wall).
-struct WalkWall {
-  int r, left;
-  u64 a, sel;
-  unsigned w;
-  int ja, jw;
-  __device__ __forceinline__ void enter(const TileLists &L, int t, int row, const int (&jbA)[3], const int (&jbW)[3]) {
-    r = row;
-    a = L.mA[(size_t)row * L.nslots + t];
-    w = L.mW[(size_t)row * L.nslots + t];
-    sel = w ? L.wsel[(size_t)row * L.nslots + t] : 0ull;
-    left = __popcll(a) + __popc(w);
-    ja = jbA[row];
-    jw = jbW[row];
-  }
-  __device__ __forceinline__ void start(const TileLists &L, int t, bool rev, const int (&jbA)[3], const int (&jbW)[3]) {
-    enter(L, t, rev ? 2 : 0, jbA, jbW);
-  }
-  // returns the partner index; wall: it indexes the wall species
-  __device__ __forceinline__ int next(const TileLists &L, int t, bool rev, const int (&jbA)[3], const int (&jbW)[3],
-                                      bool &wall) {
-    while (left == 0) enter(L, t, rev ? r - 1 : r + 1, jbA, jbW);
-    int j;
-    if (!rev) {
-      wall = (sel & 1ull) != 0;
-      sel >>= 1;
-      if (wall) {
-        const int b = __ffs((int)w) - 1;
-        w &= w - 1;
-        j = jw + b;
+// asynchronous copies global -> shared (LDGSTS): the staged tile does not pass through registers, and the copies
+// overlap the loads of the block's own records
+#ifndef SPSPH_HOST_EMU  // device only (the host emulation of tests/native/ copies synchronously)
+__device__ __forceinline__ void cp_async_16(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
+#else
+inline void cp_async_16(void *smem, const void *gmem) { std::memcpy(smem, gmem, 16); }
+inline void cp_async_8(void *smem, const void *gmem) { std::memcpy(smem, gmem, 8); }
+inline void cp_async_wait_all() {}
+#endif
+// the three candidate ranges of a SORTED array, element size 8, 16 or 32 bytes
+template <class T>
+__device__ __forceinline__ void stage_rows_async(T *__restrict__ sm, const T *__restrict__ g, const TileGeom &tg) {
+  static_assert(sizeof(T) == 8 || sizeof(T) == 16 || sizeof(T) == 32, "record sizes of the tile arrays");
+  if (!tg.staged) return;
+#pragma unroll
+  for (int r = 0; r < 3; ++r)
+    for (int i = threadIdx.x; i < tg.cnt[r]; i += blockDim.x) {
+      const char *src = reinterpret_cast<const char *>(g + tg.base[r] + i);
+      char *dst = reinterpret_cast<char *>(sm + tg.off[r] + i);
+      if (sizeof(T) == 8) {
+        cp_async_8(dst, src);
       } else {
-        const int b = __ffsll((long long)a) - 1;
-        a &= a - 1;
-        j = ja + b;
-      }
-    } else {
-      wall = ((sel >> (left - 1)) & 1ull) != 0;
-      if (wall) {
-        const int b = 31 - __clz((int)w);
-        w ^= 1u << b;
-        j = jw + b;
-      } else {
-        const int b = 63 - __clzll((long long)a);
-        a ^= 1ull << b;
-        j = ja + b;
+        cp_async_16(dst, src);
+        if (sizeof(T) == 32) cp_async_16(dst + 16, src + 16);
       }
     }
-    --left;
-    return j;
-  }
-};
+}
 
 __device__ __forceinline__ float f4c(const float4 &v, int u) { return u == 0 ? v.x : (u == 1 ? v.y : (u == 2 ? v.z : v.w)); }
 __device__ __forceinline__ float4 ldcs4(const float4 *p) { return __ldcs(p); }
+__device__ __forceinline__ unsigned ldcs1(const unsigned *p) { return __ldcs(p); }
 __device__ __forceinline__ int popc_range(u64 m, int lo, int hi) {  // set bits at positions [lo, hi)
   if (hi <= lo) return 0;
   const u64 hm = hi >= 64 ? ~0ull : ((1ull << hi) - 1ull);
@@ -258,34 +201,99 @@ __device__ __forceinline__ int popc_range(u64 m, int lo, int hi) {  // set bits 
   return __popcll(m & hm & ~lm);
 }
 
+__device__ __forceinline__ u64 bits_range(int lo, int hi) {  // mask of bit positions [lo, hi)
+  if (hi <= lo) return 0ull;
+  const u64 hm = hi >= 64 ? ~0ull : ((1ull << hi) - 1ull);
+  const u64 lm = lo >= 64 ? ~0ull : ((1ull << lo) - 1ull);
+  return hm & ~lm;
+}
+// wall partners of a particle in traversal order: the set bits of its three wall masks (rare path: particles next
+// to a wall); returns the index into the species-sorted wall arrays
+struct WalkWall {
+  unsigned m;
+  int r;
+  __device__ __forceinline__ void start(bool rev) {
+    m = 0u;
+    r = rev ? 3 : -1;
+  }
+  __device__ __forceinline__ int next(const TileLists &L, int t, bool rev, const int (&jW)[3]) {
+    while (m == 0u) {
+      r += rev ? -1 : 1;
+      m = L.mW[(size_t)r * L.nslots + t];
+    }
+    int b;
+    if (!rev) {
+      b = __ffs((int)m) - 1;
+      m &= m - 1;
+    } else {
+      b = 31 - __clz((int)m);
+      m ^= 1u << b;
+    }
+    return (r == 0 ? jW[0] : (r == 1 ? jW[1] : jW[2])) + b;
+  }
+};
+
 // ------------------------------------------------------------------------------------------------------
-// Neighbour build, one pass: acceptance masks, list lengths, pair count, fp32 weights; also the two per-step sums
-// that depend on geometry only -- cspm_norm of stress_point_update (main:430-433, 446-462) and the CSPM matrix of
-// get_derivatives (main:539-550, 596-605).
+// Tile geometry of every block of the pair-sum kernels, computed once per step: a block then starts with ONE
+// uniform load instead of a chain of dependent ones (cell of its first / last target -> cell table -> ranges).
+//   kind 0: stress-particle targets, velocity-particle partners (sweeps A and B, stress side)
+//   kind 1: velocity-particle targets, stress-particle partners (sweeps A and B, velocity side)
+//   kind 2: velocity-particle targets and partners (artificial viscosity, XSPH)
+//   kind 3: stress-particle targets and partners (XSPH)
+// ------------------------------------------------------------------------------------------------------
+constexpr int TS_T = 128;  // targets per block: stress-particle side, artificial viscosity, position update
+constexpr int TN_T = 64;   // velocity-particle side of sweeps A and B (a tile of stress particles is twice as large)
+struct GeomTables {
+  TileGeom *g[4];
+};
+__device__ __forceinline__ void geom_kind(int kind, int &tsp, int &qsp, int &T) {
+  tsp = (kind == 0 || kind == 3) ? SP_STRESS : SP_NODE;
+  qsp = (kind == 0 || kind == 2) ? SP_NODE : SP_STRESS;
+  T = kind == 1 ? TN_T : TS_T;
+}
+__global__ void k_tile_geoms(const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ nout, GeomTables GT,
+                             int cap0, int cap1, int cap2, int cap3) {
+  const int kind = blockIdx.y;
+  int tsp, qsp, T;
+  geom_kind(kind, tsp, qsp, T);
+  const int nlive = S.start[tsp][G->ncell] + nout[tsp];
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b * T >= nlive) return;
+  const int cap = kind == 0 ? cap0 : (kind == 1 ? cap1 : (kind == 2 ? cap2 : cap3));
+  TileGeom g;
+  tile_geom(G, S.cell[tsp][b * T], S.cell[tsp][min(b * T + T, nlive) - 1], S.start[qsp], cap, g);
+  GT.g[kind][b] = g;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// Neighbour build, one pass: acceptance masks -> entry codes, list lengths, pair count, fp32 weights; also the two
+// per-step sums that depend on geometry only -- cspm_norm of stress_point_update (main:430-433, 446-462) and the CSPM
+// matrix of get_derivatives (main:539-550, 596-605).
 // ------------------------------------------------------------------------------------------------------
 constexpr int TB_T = 64;  // targets per block
 constexpr int TB_CAP0 = 320, TB_CAP1 = 640, TB_CAP2 = 256;  // staged candidates per species
+constexpr int TB_CODES = 64;  // entries per list the code scratch holds
 
 struct TileStatus {  // read back by the host after the build
   long long n_pairs;
-  int flags;  // bit 0: a stencil row has more candidates than a mask holds; bit 1: a list exceeds its slice capacity
-  int max_n0n, max_n0s, max_n1n;  // longest lists (size the slice capacities)
+  int flags;  // bit 0: a stencil row / a list has more entries than the masks and codes hold; bit 1: a list exceeds its slice capacity
+  int max_n0n, max_n0s, max_n1n, max_n1s;  // longest lists (size the slice capacities)
   int ncell, overflow;
   int nloc[3];
-  int pad;
 };
 
 template <int SP>
 __global__ void __launch_bounds__(TB_T)
 k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileLists L, SortedConsts C, int nnp, int rev,
-             const int *__restrict__ lflag, const int *__restrict__ nout, int *__restrict__ nall,
+             int want_c, int want_s, const int *__restrict__ lflag, const int *__restrict__ nout, int *__restrict__ nall,
              int *__restrict__ bc_int, float *__restrict__ n_int, double *__restrict__ norm, double *__restrict__ AE,
              u64 *__restrict__ acc_pairs,
-             int *__restrict__ flags /* [0] mask overflow, [1..3] longest lists, [4] slice overflow */) {
+             int *__restrict__ flags /* [0] mask overflow, [1..4] longest lists, [5] slice overflow */) {
   constexpr bool LISTS = SP != SP_DUMMY;
   constexpr int SQA = SP == SP_NODE ? SP_STRESS : SP_NODE;  // cross-species partner of a list-owning target
   __shared__ float2 su0[LISTS ? TB_CAP0 : 1], su1[LISTS ? TB_CAP1 : 1], su2[LISTS ? TB_CAP2 : 1];
   __shared__ double2 sx0[LISTS ? TB_CAP0 : 1], sx1[LISTS ? TB_CAP1 : 1], sx2[LISTS ? TB_CAP2 : 1];
+  __shared__ unsigned scode0[LISTS ? (TB_CODES / 4) * TB_T : 1], scodeS[LISTS ? (TB_CODES / 4) * TB_T : 1];
   __shared__ TileGeom tgs[3];
   const int nlive = S.start[SP][G->ncell] + nout[SP];  // sorted particles of this species, incl. out-of-domain ones
   const int kb0 = blockIdx.x * TB_T;
@@ -298,16 +306,6 @@ k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileList
     else
       tgs[threadIdx.x].staged = 0;
   }
-  __syncthreads();
-  if (LISTS) {
-    stage_rows(su0, S.upos[0], nullptr, tgs[0]);
-    stage_rows(sx0, S.pos[0], nullptr, tgs[0]);
-    stage_rows(su1, S.upos[1], nullptr, tgs[1]);
-    stage_rows(sx1, S.pos[1], nullptr, tgs[1]);
-    stage_rows(su2, S.upos[2], nullptr, tgs[2]);
-    stage_rows(sx2, S.pos[2], nullptr, tgs[2]);
-    __syncthreads();
-  }
   const int k0 = kb0 + threadIdx.x;
   const bool live = k0 < nlive;
   const int k = live ? k0 : kb0;
@@ -317,58 +315,70 @@ k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileList
   const double2 pp = S.pos[SP][k];
   const double hp = S.h[SP][k];
   const float2 up = S.upos[SP][k];
+  __syncthreads();
+  if (LISTS) {
+    stage_rows_async(su0, S.upos[0], tgs[0]);
+    stage_rows_async(sx0, S.pos[0], tgs[0]);
+    stage_rows_async(su1, S.upos[1], tgs[1]);
+    stage_rows_async(sx1, S.pos[1], tgs[1]);
+    stage_rows_async(su2, S.upos[2], tgs[2]);
+    stage_rows_async(sx2, S.pos[2], tgs[2]);
+    cp_async_wait_all();
+    __syncthreads();
+  }
   const Prefilter pf = prefilter_bounds(P, G, hp);
   const double sk = (double)P.scale_k;
   int ovf = 0;
-  u64 mk[3][3];  // [species][row]
-  int jbs[3][3];
+  u64 mk[3][3];   // acceptance masks [species][row]
+  int jbs[3][3];  // index of bit 0 in the staged tile (or the global sorted array)
+  int gbs[3][3];  // ... in the global sorted array
   int cf = 0, ca = 0;
-  {
-    int ndx = 1, ndy = 1, cy = 0, cx = 0;
-    if (c >= 0) {
-      ndx = G->ndivx[0];
-      ndy = G->ndivx[1];
-      cy = c / ndx;
-      cx = c - cy * ndx;
-    }
+  int ndx = 1, ndy = 1, cy = 0, cx = 0;
+  if (c >= 0) {
+    ndx = G->ndivx[0];
+    ndy = G->ndivx[1];
+    cy = c / ndx;
+    cx = c - cy * ndx;
+  }
 #pragma unroll
-    for (int sq = 0; sq < 3; ++sq) {
-      const Src<float2> U = make_src<float2>(sq == 0 ? su0 : (sq == 1 ? su1 : su2), S.upos[sq], nullptr, tgs[sq]);
-      const Src<double2> X = make_src<double2>(sq == 0 ? sx0 : (sq == 1 ? sx1 : sx2), S.pos[sq], nullptr, tgs[sq]);
+  for (int sq = 0; sq < 3; ++sq) {
+    const Src<float2> U = make_src<float2>(sq == 0 ? su0 : (sq == 1 ? su1 : su2), S.upos[sq], nullptr, tgs[sq]);
+    const Src<double2> X = make_src<double2>(sq == 0 ? sx0 : (sq == 1 ? sx1 : sx2), S.pos[sq], nullptr, tgs[sq]);
 #pragma unroll
-      for (int r = 0; r < 3; ++r) {
-        mk[sq][r] = 0ull;
-        jbs[sq][r] = 0;
-        const int row = cy - 1 + r;
-        if (c < 0 || row < 0 || row >= ndy) continue;
-        const int b = S.start[sq][row * ndx + max(cx - 1, 0)], e = S.start[sq][row * ndx + min(cx + 1, ndx - 1) + 1];
-        const int len = e - b;
-        const int jb = tgs[sq].staged ? b - tgs[sq].base[r] + tgs[sq].off[r] : b;
-        jbs[sq][r] = jb;
-        if (len > (sq == SP_DUMMY && LISTS ? 32 : 64)) ovf |= 1;
-        const int n = min(len, 64);
-        u64 m = 0ull;
-        for (int i = 0; i < n; ++i) {
-          int cls = 2;
-          if (pf.on) cls = prefilter_test(pf, up, U(jb + i));
-          if (cls == 0) continue;
-          if (sq == SP && b + i == k) continue;
-          if (cls == 2) {
-            double dx, dy, d2, mh;
-            if (!pair_accept_fast(sk, pp, hp, X(jb + i), hp, dx, dy, d2, mh)) continue;
-          }
-          m |= 1ull << i;
+    for (int r = 0; r < 3; ++r) {
+      mk[sq][r] = 0ull;
+      jbs[sq][r] = 0;
+      gbs[sq][r] = 0;
+      const int row = cy - 1 + r;
+      if (c < 0 || row < 0 || row >= ndy) continue;
+      const int b = S.start[sq][row * ndx + max(cx - 1, 0)], e = S.start[sq][row * ndx + min(cx + 1, ndx - 1) + 1];
+      const int len = e - b;
+      const int jb = tgs[sq].staged ? b - tgs[sq].base[r] + tgs[sq].off[r] : b;
+      jbs[sq][r] = jb;
+      gbs[sq][r] = b;
+      if (len > (sq == SP_DUMMY && LISTS ? 32 : 64)) ovf |= 1;
+      const int n = min(len, 64);
+      u64 m = 0ull;
+      for (int i = 0; i < n; ++i) {
+        int cls = 2;
+        if (pf.on) cls = prefilter_test(pf, up, U(jb + i));
+        if (cls == 0) continue;
+        if (sq == SP && b + i == k) continue;
+        if (cls == 2) {
+          double dx, dy, d2, mh;
+          if (!pair_accept_fast(sk, pp, hp, X(jb + i), hp, dx, dy, d2, mh)) continue;
         }
-        mk[sq][r] = m;
-        const int na = __popcll(m);
-        ca += na;
-        // forward partners (creation order, main:1322-1341): later row, or own row from a threshold index on
-        if (r == 2)
-          cf += na;
-        else if (r == 1) {
-          const int fthr = (sq == SP) ? k + 1 : (sq > SP ? S.start[sq][c] : S.start[sq][c + 1]);
-          cf += popc_range(m, max(fthr - b, 0), 64);
-        }
+        m |= 1ull << i;
+      }
+      mk[sq][r] = m;
+      const int na = __popcll(m);
+      ca += na;
+      // forward partners (creation order, main:1322-1341): later row, or own row from a threshold index on
+      if (r == 2)
+        cf += na;
+      else if (r == 1) {
+        const int fthr = (sq == SP) ? k + 1 : (sq > SP ? S.start[sq][c] : S.start[sq][c + 1]);
+        cf += popc_range(m, max(fthr - b, 0), 64);
       }
     }
   }
@@ -384,57 +394,82 @@ k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileList
     if (__any_sync(0xffffffffu, ovf != 0) && (threadIdx.x & 31) == 0) atomicOr(&flags[0], 1);
     return;
   }
-  // ---- lists ----
-  u64 mA[3], mS[3], wsel[3] = {0ull, 0ull, 0ull};
+  // ---- entry codes in traversal order: ascending (row, candidate); within a row with wall partners the reference
+  // visits, cell by cell, the cross-species partners of the cell and then its wall particles ((cell, species, index)
+  // order); reversed order: the mirror image ----
+  const bool rv = rev != 0;
   unsigned mW[3];
-  int jA[3], jS[3], jW[3];
 #pragma unroll
-  for (int r = 0; r < 3; ++r) {
-    mA[r] = mk[SQA][r];
-    mS[r] = mk[SP][r];
-    mW[r] = (unsigned)mk[SP_DUMMY][r];
-    jA[r] = jbs[SQA][r];
-    jS[r] = jbs[SP][r];
-    jW[r] = jbs[SP_DUMMY][r];
-  }
+  for (int r = 0; r < 3; ++r) mW[r] = (unsigned)mk[SP_DUMMY][r];
   const bool wallp = (mW[0] | mW[1] | mW[2]) != 0u;
-  if (wallp) {  // interleaving of a row with wall partners: (cell, species, index) order, wall particles last in a cell
-    const int ndx = G->ndivx[0];
-    const int cy = c / ndx, cx = c - cy * ndx;
-    for (int r = 0; r < 3; ++r) {
-      if (!mW[r]) continue;
+  const int cnt0 = __popcll(mk[SQA][0]) + __popcll(mk[SQA][1]) + __popcll(mk[SQA][2]) + __popc(mW[0]) + __popc(mW[1]) +
+                   __popc(mW[2]);
+  const int cnt1 = __popcll(mk[SP][0]) + __popcll(mk[SP][1]) + __popcll(mk[SP][2]);
+  if (cnt0 > TB_CODES || cnt1 > TB_CODES) ovf |= 1;
+  // same-species entries: velocity-velocity for artificial viscosity (want_c: with gradients) and XSPH, stress-stress
+  // for XSPH only
+  const bool want1 = SP == SP_NODE ? (want_c != 0 || want_s != 0) : want_s != 0;
+  auto put = [&](unsigned *sc, int e, unsigned code) {
+    if (e < TB_CODES) reinterpret_cast<unsigned char *>(sc + (e >> 2) * TB_T + threadIdx.x)[e & 3] = (unsigned char)code;
+  };
+  auto emit_bits = [&](unsigned *sc, int &e, u64 m, unsigned rowtag) {  // all set bits of m in traversal order
+    while (m) {
+      int b;
+      if (!rv) {
+        b = __ffsll((long long)m) - 1;
+        m &= m - 1;
+      } else {
+        b = 63 - __clzll((long long)m);
+        m ^= 1ull << b;
+      }
+      put(sc, e++, rowtag | (unsigned)b);
+    }
+  };
+  {
+    int e = 0;
+    for (int rr = 0; rr < 3; ++rr) {
+      const int r = rv ? 2 - rr : rr;
+      const u64 ma = r == 0 ? mk[SQA][0] : (r == 1 ? mk[SQA][1] : mk[SQA][2]);
+      const unsigned mw = r == 0 ? mW[0] : (r == 1 ? mW[1] : mW[2]);
+      if (!mw) {
+        emit_bits(scode0, e, ma, (unsigned)r << 6);
+        continue;
+      }
       const int row = cy - 1 + r;
       const int ca_ = row * ndx + max(cx - 1, 0), cb_ = row * ndx + min(cx + 1, ndx - 1);
       const int bA = S.start[SQA][ca_], bW = S.start[SP_DUMMY][ca_];
-      int pos = 0;
-      u64 sel = 0ull;
-      for (int cq = ca_; cq <= cb_; ++cq) {
-        const int na = popc_range(mA[r], S.start[SQA][cq] - bA, S.start[SQA][cq + 1] - bA);
-        const int nw = popc_range((u64)mW[r], S.start[SP_DUMMY][cq] - bW, S.start[SP_DUMMY][cq + 1] - bW);
-        pos += na;
-        if (nw > 0) {
-          if (pos + nw > 64)
-            ovf |= 1;
-          else
-            sel |= ((nw >= 64 ? ~0ull : ((1ull << nw) - 1ull)) << pos);
+      for (int cc = 0; cc <= cb_ - ca_; ++cc) {
+        const int cq = rv ? cb_ - cc : ca_ + cc;
+        const int a0 = S.start[SQA][cq] - bA, a1 = S.start[SQA][cq + 1] - bA;
+        const int w0_ = S.start[SP_DUMMY][cq] - bW, w1_ = S.start[SP_DUMMY][cq + 1] - bW;
+        const u64 am = ma & bits_range(a0, a1);
+        const int nw = popc_range((u64)mw, w0_, w1_);
+        if (!rv) {
+          emit_bits(scode0, e, am, (unsigned)r << 6);
+          for (int q = 0; q < nw; ++q) put(scode0, e++, TILE_CODE_WALL);
+        } else {
+          for (int q = 0; q < nw; ++q) put(scode0, e++, TILE_CODE_WALL);
+          emit_bits(scode0, e, am, (unsigned)r << 6);
         }
-        pos += nw;
       }
-      wsel[r] = sel;
+    }
+    if (want1) {
+      int e1 = 0;
+      for (int rr = 0; rr < 3; ++rr) {
+        const int r = rv ? 2 - rr : rr;
+        emit_bits(scodeS, e1, r == 0 ? mk[SP][0] : (r == 1 ? mk[SP][1] : mk[SP][2]), (unsigned)r << 6);
+      }
     }
   }
-  const int cnt0 = __popcll(mA[0]) + __popcll(mA[1]) + __popcll(mA[2]) + __popc(mW[0]) + __popc(mW[1]) + __popc(mW[2]);
-  const int cnt1 = __popcll(mS[0]) + __popcll(mS[1]) + __popcll(mS[2]);
-  const int cap0 = ell0_cap(L, t);
-  if (cnt0 > cap0 || (SP == SP_NODE && cnt1 > L.capC)) ovf |= 2;
+  const int cap0 = ell0_cap(L, t), cap1 = ellS_cap(L, t);
+  if (cnt0 > cap0 || (want1 && cnt1 > cap1)) ovf |= 2;
   if (live) {
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
       const size_t a = (size_t)r * L.nslots + t;
-      L.mA[a] = mA[r];
-      L.mS[a] = mS[r];
-      L.mW[a] = mW[r];
-      if (wallp) L.wsel[a] = wsel[r];
+      L.rowA[a] = gbs[SQA][r];
+      L.rowS[a] = gbs[SP][r];
+      if (wallp) L.mW[a] = mW[r];
     }
     L.n0[t] = cnt0 | (wallp ? TILE_WALL_FLAG : 0);
     L.n1[t] = cnt1;
@@ -450,34 +485,28 @@ k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileList
     const int o = warp_max_i(ovf);
     if ((threadIdx.x & 31) == 0) {
       if (o & 1) atomicOr(&flags[0], 1);
-      if (o & 2) atomicOr(&flags[4], 1);
+      if (o & 2) atomicOr(&flags[5], 1);
       atomicMax(&flags[SP == SP_NODE ? 1 : 2], m0);
-      if (SP == SP_NODE) atomicMax(&flags[3], m1);
+      atomicMax(&flags[SP == SP_NODE ? 3 : 4], m1);
     }
   }
+  const bool ok_w = live && ovf == 0;
   // ---- weights, in traversal order; entries are evaluated in groups of four (independent division / sqrt chains) ----
   const KernelConsts K = kernel_consts(P, hp);
-  const bool rv = rev != 0;
   const Src<double2> XA = make_src<double2>(SQA == 0 ? sx0 : sx1, S.pos[SQA], nullptr, tgs[SQA]);
   const Src<double2> XS = make_src<double2>(SP == 0 ? sx0 : sx1, S.pos[SP], nullptr, tgs[SP]);
   const Src<double2> XW = make_src<double2>(sx2, S.pos[SP_DUMMY], nullptr, tgs[SP_DUMMY]);
   const double2 *__restrict__ mrq = C.mrho[SQA];
-  const int *__restrict__ startA = S.start[SQA];
-  // global sorted index of a cross-species partner from its tile index (mass and density are read from global memory)
-  int gshift[3];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) gshift[r] = tgs[SQA].staged ? tgs[SQA].base[r] - tgs[SQA].off[r] : 0;
-  (void)startA;
   double nrm = 0.0, ae1 = 0.0, ae2 = 0.0, ae3 = 0.0, ae4 = 0.0;
   {
-    const int n0w = (live && !(ovf & 2)) ? cnt0 : 0;
+    const int n0w = ok_w ? cnt0 : 0;
     const int wrows = warp_max_i(n0w);
-    const bool anyw = __any_sync(0xffffffffu, wallp && n0w > 0);
-    Walk3 wk{mA[0], mA[1], mA[2], jA[0], jA[1], jA[2]};
     WalkWall ww;
-    if (wallp && n0w > 0) ww.start(L, t, rv, jA, jW);
+    ww.start(rv);
+    const int jW[3] = {jbs[SP_DUMMY][0], jbs[SP_DUMMY][1], jbs[SP_DUMMY][2]};
     const size_t base = ell0_base(L, t);
     for (int g = 0; g * 4 < wrows; ++g) {
+      const unsigned cw = g < TB_CODES / 4 ? scode0[g * TB_T + threadIdx.x] : 0u;
       float wv[4] = {0.f, 0.f, 0.f, 0.f}, gxv[4] = {0.f, 0.f, 0.f, 0.f}, gyv[4] = {0.f, 0.f, 0.f, 0.f};
       double2 pq[4];
       int jg[4];
@@ -485,19 +514,17 @@ k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileList
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
         isw[u] = false;
-        jg[u] = -1;
+        jg[u] = 0;
         pq[u] = pp;
         if (g * 4 + u < n0w) {
-          int j;
-          if (anyw && wallp)
-            j = ww.next(L, t, rv, jA, jW, isw[u]);
-          else
-            j = wk.next(rv);
-          pq[u] = isw[u] ? XW(j) : XA(j);
-          if (!isw[u]) {  // global sorted index: which stencil row does the tile index belong to?
-            int gj = j;
-            if (tgs[SQA].staged) gj = j + (j >= tgs[SQA].off[2] ? gshift[2] : (j >= tgs[SQA].off[1] ? gshift[1] : gshift[0]));
-            jg[u] = gj;
+          const unsigned cd = (cw >> (8 * u)) & 0xffu;
+          const int r = (int)(cd >> 6), b = (int)(cd & 63u);
+          if (r == 3) {
+            isw[u] = true;
+            pq[u] = XW(ww.next(L, t, rv, jW));
+          } else {
+            pq[u] = XA((r == 0 ? jbs[SQA][0] : (r == 1 ? jbs[SQA][1] : jbs[SQA][2])) + b);
+            jg[u] = (r == 0 ? gbs[SQA][0] : (r == 1 ? gbs[SQA][1] : gbs[SQA][2])) + b;
           }
         }
       }
@@ -536,42 +563,50 @@ k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileList
       }
       if (g * 4 < n0w) {
         const size_t a = base + (size_t)g * 32;
+        L.code0[a] = cw;
         L.w0[a] = make_float4(wv[0], wv[1], wv[2], wv[3]);
         L.gx0[a] = make_float4(gxv[0], gxv[1], gxv[2], gxv[3]);
         L.gy0[a] = make_float4(gyv[0], gyv[1], gyv[2], gyv[3]);
       }
     }
   }
-  if (SP == SP_NODE) {  // velocity-velocity list: gradient from this particle's perspective
-    const int n1w = (live && !(ovf & 2)) ? cnt1 : 0;
+  if (want1) {  // same-species list: codes; velocity particles also the gradient from their own perspective
+    const int n1w = ok_w ? cnt1 : 0;
     const int wrows = warp_max_i(n1w);
-    Walk3 wk{mS[0], mS[1], mS[2], jS[0], jS[1], jS[2]};
-    const size_t base = ellC_base(L, t);
+    const size_t base = ellS_base(L, t);
     for (int g = 0; g * 4 < wrows; ++g) {
-      float gxv[4] = {0.f, 0.f, 0.f, 0.f}, gyv[4] = {0.f, 0.f, 0.f, 0.f};
-      double2 pq[4];
+      const unsigned cw = g < TB_CODES / 4 ? scodeS[g * TB_T + threadIdx.x] : 0u;
+      if (SP == SP_NODE && want_c) {
+        float gxv[4] = {0.f, 0.f, 0.f, 0.f}, gyv[4] = {0.f, 0.f, 0.f, 0.f};
+        double2 pq[4];
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        pq[u] = pp;
-        if (g * 4 + u < n1w) pq[u] = XS(wk.next(rv));
-      }
+        for (int u = 0; u < 4; ++u) {
+          pq[u] = pp;
+          if (g * 4 + u < n1w) {
+            const unsigned cd = (cw >> (8 * u)) & 0xffu;
+            const int r = (int)(cd >> 6), b = (int)(cd & 63u);
+            pq[u] = XS((r == 0 ? jbs[SP][0] : (r == 1 ? jbs[SP][1] : jbs[SP][2])) + b);
+          }
+        }
 #pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (g * 4 + u >= n1w) continue;
-        const double dx = pp.x - pq[u].x, dy = pp.y - pq[u].y;
-        double d2 = dx * dx;
-        d2 = d2 + dy * dy;
-        const double r = sqrt(d2);
-        double w, gx, gy;
-        sph_kernel_fast<true>(K, r, dx, dy, w, gx, gy);
-        gxv[u] = (float)gx;
-        gyv[u] = (float)gy;
+        for (int u = 0; u < 4; ++u) {
+          if (g * 4 + u >= n1w) continue;
+          const double dx = pp.x - pq[u].x, dy = pp.y - pq[u].y;
+          double d2 = dx * dx;
+          d2 = d2 + dy * dy;
+          const double r = sqrt(d2);
+          double w, gx, gy;
+          sph_kernel_fast<true>(K, r, dx, dy, w, gx, gy);
+          gxv[u] = (float)gx;
+          gyv[u] = (float)gy;
+        }
+        if (g * 4 < n1w) {
+          const size_t a = base + (size_t)g * 32;
+          L.gxC[a] = make_float4(gxv[0], gxv[1], gxv[2], gxv[3]);
+          L.gyC[a] = make_float4(gyv[0], gyv[1], gyv[2], gyv[3]);
+        }
       }
-      if (g * 4 < n1w) {
-        const size_t a = base + (size_t)g * 32;
-        L.gxC[a] = make_float4(gxv[0], gxv[1], gxv[2], gxv[3]);
-        L.gyC[a] = make_float4(gyv[0], gyv[1], gyv[2], gyv[3]);
-      }
+      if (g * 4 < n1w) L.codeS[base + (size_t)g * 32] = cw;
     }
   }
   if (!live) return;
@@ -601,10 +636,11 @@ __global__ void k_tile_status(const GridInfo *__restrict__ G, const int *__restr
                               const int *__restrict__ flags, TileStatus *st) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   st->n_pairs = (long long)*acc_pairs;
-  st->flags = (flags[0] ? 1 : 0) | (flags[4] ? 2 : 0);
+  st->flags = (flags[0] ? 1 : 0) | (flags[5] ? 2 : 0);
   st->max_n0n = flags[1];
   st->max_n0s = flags[2];
   st->max_n1n = flags[3];
+  st->max_n1s = flags[4];
   st->ncell = G->ncell;
   st->overflow = G->overflow;
   for (int sp = 0; sp < 3; ++sp) st->nloc[sp] = start[sp * cell_stride + G->ncell] + nout[sp];
@@ -619,24 +655,98 @@ struct TileRecs {
   double2 *SVs;  // [ns] velocity of a stress particle after the final interpolation: XSPH
 };
 
-// targets per block of the pair-sum kernels: a tile of stress particles (two per velocity particle in the Bui layout)
-// is twice as large as a tile of velocity particles, so the velocity-particle side uses half the block
-constexpr int TS_T = 128;  // stress-particle side, artificial viscosity, position update
-constexpr int TN_T = 64;   // velocity-particle side of sweeps A and B
 #ifndef SPSPH_TILE_WARPS
 #define SPSPH_TILE_WARPS 16  // resident warps per SM requested from ptxas
 #endif
 #define TILE_MINB(T_) (SPSPH_TILE_WARPS * 32 / (T_))
 
-// block prologue shared by the pair-sum kernels: tile geometry of the partner species
-#define TILE_PROLOGUE(T_, TSP, QSP, CAP)                                                                   \
-  __shared__ TileGeom tg;                                                                                  \
-  const int kb0 = blockIdx.x * (T_);                                                                       \
-  const int nlive = (TSP) == SP_NODE ? M.nn : M.ns;                                                        \
-  if (kb0 >= nlive) return;                                                                                \
-  if (threadIdx.x == 0)                                                                                    \
-    tile_geom(G, S.cell[TSP][kb0], S.cell[TSP][min(kb0 + (T_), nlive) - 1], S.start[QSP], CAP, tg);        \
-  __syncthreads();
+// per-lane state of a list walk: its length, the tile index of candidate 0 of each stencil row, code / weight cursor
+struct LaneList {
+  int cnt;
+  bool wallp;
+  int j0, j1, j2;
+  size_t base;
+};
+// cross-species list (list 0) of slot t
+__device__ __forceinline__ LaneList lane_list0(const TileLists &L, int t, bool live, const TileGeom &tg) {
+  LaneList q;
+  const int n0r = live ? L.n0[t] : 0;
+  q.cnt = n0r & ~TILE_WALL_FLAG;
+  q.wallp = (n0r & TILE_WALL_FLAG) != 0;
+  q.j0 = q.j1 = q.j2 = 0;
+  q.base = 0;
+  if (q.cnt == 0) return q;
+  q.j0 = L.rowA[t];
+  q.j1 = L.rowA[(size_t)L.nslots + t];
+  q.j2 = L.rowA[2 * (size_t)L.nslots + t];
+  if (tg.staged) {
+    q.j0 += tg.off[0] - tg.base[0];
+    q.j1 += tg.off[1] - tg.base[1];
+    q.j2 += tg.off[2] - tg.base[2];
+  }
+  q.base = ell0_base(L, t);
+  return q;
+}
+// same-species list of slot t
+__device__ __forceinline__ LaneList lane_listS(const TileLists &L, int t, bool live, const TileGeom &tg) {
+  LaneList q;
+  q.cnt = live ? L.n1[t] : 0;
+  q.wallp = false;
+  q.j0 = q.j1 = q.j2 = 0;
+  q.base = 0;
+  if (q.cnt == 0) return q;
+  q.j0 = L.rowS[t];
+  q.j1 = L.rowS[(size_t)L.nslots + t];
+  q.j2 = L.rowS[2 * (size_t)L.nslots + t];
+  if (tg.staged) {
+    q.j0 += tg.off[0] - tg.base[0];
+    q.j1 += tg.off[1] - tg.base[1];
+    q.j2 += tg.off[2] - tg.base[2];
+  }
+  q.base = ellS_base(L, t);
+  return q;
+}
+// tile index of the partner of an entry code
+__device__ __forceinline__ int code_index(const LaneList &q, unsigned cd) {
+  const unsigned r = cd >> 6;
+  return (r == 0 ? q.j0 : (r == 1 ? q.j1 : q.j2)) + (int)(cd & 63u);
+}
+
+// Walk of a list: NA float4 weight arrays + the code words, groups of four entries, prefetched two groups ahead.
+// body(u, code, w...) is called for every entry of this lane in traversal order.
+template <int NA, class Body>
+__device__ __forceinline__ void walk_list(const unsigned *__restrict__ code, const float4 *__restrict__ a0,
+                                          const float4 *__restrict__ a1, const LaneList &q, Body body) {
+  const int ng = (q.cnt + 3) >> 2;  // per lane: a lane only touches the groups it owns
+  if (ng == 0) return;
+  unsigned c0 = 0u, c1 = 0u, c2 = 0u;
+  float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0, x2 = x0, y0 = x0, y1 = x0, y2 = x0;
+  c0 = ldcs1(code + q.base);
+  if (NA > 0) x0 = ldcs4(a0 + q.base);
+  if (NA > 1) y0 = ldcs4(a1 + q.base);
+  if (ng > 1) {
+    c1 = ldcs1(code + q.base + 32);
+    if (NA > 0) x1 = ldcs4(a0 + q.base + 32);
+    if (NA > 1) y1 = ldcs4(a1 + q.base + 32);
+  }
+  for (int g = 0; g < ng; ++g) {
+    if (g + 2 < ng) {
+      const size_t a = q.base + (size_t)(g + 2) * 32;
+      c2 = ldcs1(code + a);
+      if (NA > 0) x2 = ldcs4(a0 + a);
+      if (NA > 1) y2 = ldcs4(a1 + a);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u)
+      if (g * 4 + u < q.cnt) body((c0 >> (8 * u)) & 0xffu, f4c(x0, u), f4c(y0, u));
+    c0 = c1;
+    c1 = c2;
+    x0 = x1;
+    x1 = x2;
+    y0 = y1;
+    y1 = y2;
+  }
+}
 
 // ------------------------------------------------------------------------------------------------------
 // Sweep A, stress-particle side (stress_point_update main:403-482: velocity of a stress particle from its velocity
@@ -645,37 +755,32 @@ constexpr int TN_T = 64;   // velocity-particle side of sweeps A and B
 constexpr int TA_SP_CAP = 384;
 template <bool FROMB>
 __global__ void __launch_bounds__(TS_T, TILE_MINB(TS_T))
-k_tile_a_sp(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, TileLists L, SortedConsts C,
-            TileRecs R, StatePtrs st, int rev, int do_adapt, int do_bc, int final_sweep) {
-  TILE_PROLOGUE(TS_T, SP_STRESS, SP_NODE, TA_SP_CAP)
+k_tile_a_sp(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C, TileRecs R, StatePtrs st,
+            const TileGeom *__restrict__ geoms, int do_adapt, int do_bc, int final_sweep) {
   __shared__ double2 sv[TA_SP_CAP];
   __shared__ double smo[TA_SP_CAP];
-  if (tg.staged) {
-    if (FROMB) {
-      for (int r = 0; r < 3; ++r)
-        for (int i = threadIdx.x; i < tg.cnt[r]; i += blockDim.x) {
-          const Rec4 q = ldrec(st.NBr, S.order[0][tg.base[r] + i]);
-          sv[tg.off[r] + i] = make_double2(q.a, q.b);
-        }
-    } else {
-      stage_rows(sv, (const double2 *)R.NAs, nullptr, tg);
-    }
-    stage_rows(smo, C.mor[0], nullptr, tg);
-    __syncthreads();
-  }
+  const int kb0 = blockIdx.x * TS_T;
+  if (kb0 >= M.ns) return;
+  const TileGeom tg = geoms[blockIdx.x];
   const int k0 = kb0 + threadIdx.x;
-  const bool live = k0 < nlive;
+  const bool live = k0 < M.ns;
   const int k = live ? k0 : kb0;
   const int t = M.nnp + k0;
   const int id = S.order[1][k];
   const int ks = id - P.nnode;
-  const int n0r = live ? L.n0[t] : 0;
-  const int cnt = n0r & ~TILE_WALL_FLAG;
-  const bool wallp = (n0r & TILE_WALL_FLAG) != 0;
-  const int wrows = warp_max_i(cnt);
-  const bool rv = rev != 0;
-  int jA[3], jW[3] = {0, 0, 0};
-  lane_bases(G, live ? S.cell[1][k] : -1, S.start[0], tg, jA);
+  const LaneList q = lane_list0(L, t, live, tg);
+  if (tg.staged) {
+    if (FROMB) {
+      for (int r = 0; r < 3; ++r)
+        for (int i = threadIdx.x; i < tg.cnt[r]; i += blockDim.x) {
+          const Rec4 p = ldrec(st.NBr, S.order[0][tg.base[r] + i]);
+          sv[tg.off[r] + i] = make_double2(p.a, p.b);
+        }
+    } else {
+      stage_rows_async(sv, (const double2 *)R.NAs, tg);
+    }
+    stage_rows_async(smo, C.mor[0], tg);
+  }
   double2 v;
   Stress4 s;
   if (FROMB) {
@@ -687,67 +792,39 @@ k_tile_a_sp(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
     const Rec4 r = R.SAs[k];
     s = Stress4{r.a, r.b, r.c, r.d};
   }
-  double vtx = 0.0, vty = 0.0;
-  {
-    Walk3 wk{0ull, 0ull, 0ull, jA[0], jA[1], jA[2]};
-    if (cnt > 0) {
-      wk.m0 = L.mA[t];
-      wk.m1 = L.mA[(size_t)L.nslots + t];
-      wk.m2 = L.mA[2 * (size_t)L.nslots + t];
-    }
-    WalkWall ww;
-    const bool anyw = __any_sync(0xffffffffu, wallp);
-    if (wallp) ww.start(L, t, rv, jA, jW);
-    const size_t base = ell0_base(L, t);
-    const int ng = (wrows + 3) >> 2;
-    float4 wn = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ng > 0) wn = ldcs4(L.w0 + base);
-    for (int g = 0; g < ng; ++g) {
-      const float4 wc = wn;
-      if (g + 1 < ng) wn = ldcs4(L.w0 + base + (size_t)(g + 1) * 32);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (g * 4 + u >= cnt) continue;
-        bool isw = false;
-        int j;
-        if (anyw && wallp)
-          j = ww.next(L, t, rv, jA, jW, isw);
-        else
-          j = wk.next(rv);
-        if (isw) continue;  // wall partners (type 9) take no part
-        double2 vq;
-        double mo;
-        if (tg.staged) {
-          vq = sv[j];
-          mo = smo[j];
-        } else {
-          if (FROMB) {
-            const Rec4 q = ldrec(st.NBr, S.order[0][j]);
-            vq = make_double2(q.a, q.b);
-          } else {
-            vq = R.NAs[j];
-          }
-          mo = C.mor[0][j];
-        }
-        const double h2 = mo * (double)f4c(wc, u);  // (mass(i)/rho(i))*w, main:431
-        vtx = vtx + vq.x * h2;
-        vty = vty + vq.y * h2;
-      }
-    }
-  }
-  if (!live) return;
   const double nrm = st.norm[id];
+  const double own_mor = st.mor[id], own_rho = st.rho[id], own_m = st.mass[id];
+  cp_async_wait_all();
+  __syncthreads();
+  const bool staged = tg.staged != 0;
+  const double2 *__restrict__ vsrc = staged ? sv : (const double2 *)R.NAs;
+  const double *__restrict__ msrc = staged ? smo : C.mor[0];
+  double vtx = 0.0, vty = 0.0;
+  walk_list<1>(L.code0, L.w0, nullptr, q, [&](unsigned cd, float w, float) {
+    if (cd >= TILE_CODE_WALL) return;  // wall partners (type 9) take no part
+    const int j = code_index(q, cd);
+    double2 vq;
+    if (FROMB && !staged) {
+      const Rec4 p = ldrec(st.NBr, S.order[0][j]);
+      vq = make_double2(p.a, p.b);
+    } else {
+      vq = vsrc[j];
+    }
+    const double h2 = msrc[j] * (double)w;  // (mass(i)/rho(i))*w, main:431
+    vtx = vtx + vq.x * h2;
+    vty = vty + vq.y * h2;
+  });
+  if (!live) return;
   if (nrm != 0) {
     v.x = vtx / nrm;
     v.y = vty / nrm;
   }
   if (do_adapt) adapt_stress(P, s);
   if (do_bc) apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, v, s);
-  strec(st.SVb, ks, v.x, v.y, st.mor[id], 0.0);
+  strec(st.SVb, ks, v.x, v.y, own_mor, 0.0);
   st4(st.SFb, ks, s);
-  const double rr = st.rho[id];
-  const double r2 = rr * rr;
-  R.SBs[k] = Rec4{s.s1 / r2, s.s2 / r2, s.s3 / r2, st.mass[id]};
+  const double r2 = own_rho * own_rho;
+  R.SBs[k] = Rec4{s.s1 / r2, s.s2 / r2, s.s3 / r2, own_m};
   if (final_sweep) R.SVs[k] = v;
 }
 
@@ -757,36 +834,31 @@ k_tile_a_sp(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
 constexpr int TA_N_CAP = 608;
 template <bool FROMB, bool EPSP>
 __global__ void __launch_bounds__(TN_T, TILE_MINB(TN_T))
-k_tile_a_node(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, TileLists L, SortedConsts C,
-              TileRecs R, StatePtrs st, int rev, int do_adapt, int do_bc, int final_sweep) {
-  TILE_PROLOGUE(TN_T, SP_NODE, SP_STRESS, TA_N_CAP)
+k_tile_a_node(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C, TileRecs R, StatePtrs st,
+              const TileGeom *__restrict__ geoms, int do_adapt, int do_bc, int final_sweep) {
   __shared__ Rec4 ss[TA_N_CAP];
   __shared__ double smo[TA_N_CAP];
   __shared__ double sep[EPSP ? TA_N_CAP : 1];
+  const int kb0 = blockIdx.x * TN_T;
+  if (kb0 >= M.nn) return;
+  const TileGeom tg = geoms[blockIdx.x];
+  const int k0 = kb0 + threadIdx.x;
+  const bool live = k0 < M.nn;
+  const int k = live ? k0 : kb0;
+  const int t = k0;
+  const int id = S.order[0][k];
+  const LaneList q = lane_list0(L, t, live, tg);
   if (tg.staged) {
     if (FROMB) {
       for (int r = 0; r < 3; ++r)
         for (int i = threadIdx.x; i < tg.cnt[r]; i += blockDim.x)
           ss[tg.off[r] + i] = ld256(st.SFbr + 4 * (size_t)(S.order[1][tg.base[r] + i] - P.nnode));
     } else {
-      stage_rows(ss, (const Rec4 *)R.SAs, nullptr, tg);
+      stage_rows_async(ss, (const Rec4 *)R.SAs, tg);
     }
-    stage_rows(smo, C.mor[1], nullptr, tg);
+    stage_rows_async(smo, C.mor[1], tg);
     if (EPSP) stage_rows(sep, (const double *)st.epsp, S.order[1], tg);
-    __syncthreads();
   }
-  const int k0 = kb0 + threadIdx.x;
-  const bool live = k0 < nlive;
-  const int k = live ? k0 : kb0;
-  const int t = k0;
-  const int id = S.order[0][k];
-  const int n0r = live ? L.n0[t] : 0;
-  const int cnt = n0r & ~TILE_WALL_FLAG;
-  const bool wallp = (n0r & TILE_WALL_FLAG) != 0;
-  const int wrows = warp_max_i(cnt);
-  const bool rv = rev != 0;
-  int jA[3], jW[3] = {0, 0, 0};
-  lane_bases(G, live ? S.cell[0][k] : -1, S.start[1], tg, jA);
   double2 v;
   Stress4 s;
   if (FROMB) {
@@ -797,57 +869,35 @@ k_tile_a_node(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays
     v = R.NAs[k];
     s = ld4(st.NSa, id);
   }
-  double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, te = 0.0;
-  {
-    Walk3 wk{0ull, 0ull, 0ull, jA[0], jA[1], jA[2]};
-    if (cnt > 0) {
-      wk.m0 = L.mA[t];
-      wk.m1 = L.mA[(size_t)L.nslots + t];
-      wk.m2 = L.mA[2 * (size_t)L.nslots + t];
-    }
-    WalkWall ww;
-    const bool anyw = __any_sync(0xffffffffu, wallp);
-    if (wallp) ww.start(L, t, rv, jA, jW);
-    const size_t base = ell0_base(L, t);
-    const int ng = (wrows + 3) >> 2;
-    float4 wn = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ng > 0) wn = ldcs4(L.w0 + base);
-    for (int g = 0; g < ng; ++g) {
-      const float4 wc = wn;
-      if (g + 1 < ng) wn = ldcs4(L.w0 + base + (size_t)(g + 1) * 32);
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (g * 4 + u >= cnt) continue;
-        bool isw = false;
-        int j;
-        if (anyw && wallp)
-          j = ww.next(L, t, rv, jA, jW, isw);
-        else
-          j = wk.next(rv);
-        if (isw) continue;  // wall partners (type 6) take no part
-        Rec4 q;
-        double mo, ep = 0.0;
-        if (tg.staged) {
-          q = ss[j];
-          mo = smo[j];
-          if (EPSP) ep = sep[j];
-        } else {
-          const int qid = S.order[1][j];
-          q = FROMB ? ld256(st.SFbr + 4 * (size_t)(qid - P.nnode)) : ldrec(R.SAs, j);
-          mo = C.mor[1][j];
-          if (EPSP) ep = st.epsp[qid];
-        }
-        const double h1 = mo * (double)f4c(wc, u);  // (mass(j)/rho(j))*w, main:430
-        t1 = t1 + q.a * h1;
-        t2 = t2 + q.b * h1;
-        t3 = t3 + q.c * h1;
-        t4 = t4 + q.d * h1;
-        if (EPSP) te = te + ep * h1;
-      }
-    }
-  }
-  if (!live) return;
   const double nrm = st.norm[id];
+  const double2 mr = C.mrho[0][k];
+  cp_async_wait_all();
+  __syncthreads();
+  const bool staged = tg.staged != 0;
+  const Rec4 *__restrict__ ssrc = staged ? ss : (const Rec4 *)R.SAs;
+  const double *__restrict__ msrc = staged ? smo : C.mor[1];
+  double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, te = 0.0;
+  walk_list<1>(L.code0, L.w0, nullptr, q, [&](unsigned cd, float w, float) {
+    if (cd >= TILE_CODE_WALL) return;  // wall partners (type 6) take no part
+    const int j = code_index(q, cd);
+    Rec4 p;
+    double ep = 0.0;
+    if (staged) {
+      p = ssrc[j];
+      if (EPSP) ep = sep[j];
+    } else {
+      const int qid = (FROMB || EPSP) ? S.order[1][j] : 0;
+      p = FROMB ? ld256(st.SFbr + 4 * (size_t)(qid - P.nnode)) : ssrc[j];
+      if (EPSP) ep = st.epsp[qid];
+    }
+    const double h1 = msrc[j] * (double)w;  // (mass(j)/rho(j))*w, main:430
+    t1 = t1 + p.a * h1;
+    t2 = t2 + p.b * h1;
+    t3 = t3 + p.c * h1;
+    t4 = t4 + p.d * h1;
+    if (EPSP) te = te + ep * h1;
+  });
+  if (!live) return;
   if (nrm != 0) {
     s.s1 = t1 / nrm;
     s.s2 = t2 / nrm;
@@ -860,7 +910,6 @@ k_tile_a_node(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays
   }
   if (do_adapt) adapt_stress(P, s);
   if (do_bc) apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, v, s);
-  const double2 mr = C.mrho[0][k];
   R.NBs[k] = Rec4{v.x, v.y, mr.x, mr.y};
   if (final_sweep || FROMB) strec(st.NB, id, v.x, v.y, mr.x, mr.y);  // state between steps / input of k_rk_begin
   st4(st.NSb, id, s);
@@ -873,113 +922,74 @@ k_tile_a_node(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays
 constexpr int TB_SP_CAP = 384;
 __global__ void __launch_bounds__(TS_T, TILE_MINB(TS_T))
 k_tile_b_sp(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, TileLists L, SortedConsts C,
-            TileRecs R, StatePtrs st, int rev, double f1next, double f2, int last) {
-  TILE_PROLOGUE(TS_T, SP_STRESS, SP_NODE, TB_SP_CAP)
+            TileRecs R, StatePtrs st, const TileGeom *__restrict__ geoms, int rev, double f1next, double f2, int last) {
   __shared__ Rec4 sn_[TB_SP_CAP];
   __shared__ double srr[TB_SP_CAP];
-  if (tg.staged) {
-    stage_rows(sn_, (const Rec4 *)R.NBs, nullptr, tg);
-    stage_rows(srr, C.rrho[0], nullptr, tg);
-    __syncthreads();
-  }
+  const int kb0 = blockIdx.x * TS_T;
+  if (kb0 >= M.ns) return;
+  const TileGeom tg = geoms[blockIdx.x];
   const int k0 = kb0 + threadIdx.x;
-  const bool live = k0 < nlive;
+  const bool live = k0 < M.ns;
   const int k = live ? k0 : kb0;
   const int t = M.nnp + k0;
   const int id = S.order[1][k];
   const int ks = id - P.nnode;
-  const int n0r = live ? L.n0[t] : 0;
-  const int cnt = n0r & ~TILE_WALL_FLAG;
-  const bool wallp = (n0r & TILE_WALL_FLAG) != 0;
-  const int wrows = warp_max_i(cnt);
-  const bool rv = rev != 0;
-  int jA[3], jW[3] = {0, 0, 0};
-  const int cl = live ? S.cell[1][k] : -1;
-  lane_bases(G, cl, S.start[0], tg, jA);
-  if (wallp) lane_rows(G, cl, S.start[2], jW);
+  const LaneList q = lane_list0(L, t, live, tg);
+  stage_rows_async(sn_, (const Rec4 *)R.NBs, tg);
+  stage_rows_async(srr, C.rrho[0], tg);
   const Rec4 selfv = ldrec(st.SVb, ks);
   const double2 vp = make_double2(selfv.a, selfv.b);
   const Stress4 sp_ = ld4(st.SFb, ks);
+  int jW[3] = {0, 0, 0};
+  if (q.wallp) lane_rows(G, S.cell[1][k], S.start[2], jW);
+  WalkWall ww;
+  ww.start(rev != 0);
+  cp_async_wait_all();
+  __syncthreads();
+  const bool staged = tg.staged != 0;
+  const Rec4 *__restrict__ nsrc = staged ? sn_ : (const Rec4 *)R.NBs;
+  const double *__restrict__ rsrc = staged ? srr : C.rrho[0];
   double g11 = 0.0, g12 = 0.0, g21 = 0.0, g22 = 0.0;  // grad1_tmp(d,k): d velocity component, k direction
-  {
-    Walk3 wk{0ull, 0ull, 0ull, jA[0], jA[1], jA[2]};
-    if (cnt > 0) {
-      wk.m0 = L.mA[t];
-      wk.m1 = L.mA[(size_t)L.nslots + t];
-      wk.m2 = L.mA[2 * (size_t)L.nslots + t];
-    }
-    WalkWall ww;
-    const bool anyw = __any_sync(0xffffffffu, wallp);
-    if (wallp) ww.start(L, t, rv, jA, jW);
-    const size_t base = ell0_base(L, t);
-    const int ng = (wrows + 3) >> 2;
-    float4 xn = make_float4(0.f, 0.f, 0.f, 0.f), yn = xn;
-    if (ng > 0) {
-      xn = ldcs4(L.gx0 + base);
-      yn = ldcs4(L.gy0 + base);
-    }
-    for (int g = 0; g < ng; ++g) {
-      const float4 xc = xn, yc = yn;
-      if (g + 1 < ng) {
-        xn = ldcs4(L.gx0 + base + (size_t)(g + 1) * 32);
-        yn = ldcs4(L.gy0 + base + (size_t)(g + 1) * 32);
+  walk_list<2>(L.code0, L.gx0, L.gy0, q, [&](unsigned cd, float gxf, float gyf) {
+    const double gx = (double)gxf, gy = (double)gyf;
+    if (cd < TILE_CODE_WALL) {  // type 1: velocity particle {vx, vy, m, rho}
+      const int j = code_index(q, cd);
+      const Rec4 p = nsrc[j];
+      const double rr = rsrc[j];
+      const double h1 = div_rn(gx * p.c, p.d, rr);  // dwdx*mass(i)/rho(i), main:514
+      const double h2 = div_rn(gy * p.c, p.d, rr);
+      const double dvx = p.a - vp.x, dvy = p.b - vp.y;
+      g11 = g11 + dvx * h1;
+      g12 = g12 + dvx * h2;
+      g21 = g21 + dvy * h1;
+      g22 = g22 + dvy * h2;
+    } else {  // type 9: wall particle (no-slip mirror velocity), main:552-575
+      const int pq = S.order[2][ww.next(L, t, rev != 0, jW)];
+      const double2 xp = ld2(st.x, id);
+      const double beta_max = 1.5, vel_wall = 0.0;
+      const double wall = (double)st.wallpos[pq];
+      const double2 xq = ld2(st.x, pq);
+      double da, db;
+      if (st.horiz[pq] == 1.f) {
+        da = fabs(xp.y - wall);
+        db = fabs(xq.y - wall);
+      } else {
+        da = fabs(xp.x - wall);
+        db = fabs(xq.x - wall);
       }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (g * 4 + u >= cnt) continue;
-        bool isw = false;
-        int j;
-        if (anyw && wallp)
-          j = ww.next(L, t, rv, jA, jW, isw);
-        else
-          j = wk.next(rv);
-        const double gx = (double)f4c(xc, u), gy = (double)f4c(yc, u);
-        if (!isw) {  // type 1: velocity particle {vx, vy, m, rho}
-          Rec4 q;
-          double rr;
-          if (tg.staged) {
-            q = sn_[j];
-            rr = srr[j];
-          } else {
-            q = ldrec(R.NBs, j);
-            rr = C.rrho[0][j];
-          }
-          const double h1 = div_rn(gx * q.c, q.d, rr);  // dwdx*mass(i)/rho(i), main:514
-          const double h2 = div_rn(gy * q.c, q.d, rr);
-          const double dvx = q.a - vp.x, dvy = q.b - vp.y;
-          g11 = g11 + dvx * h1;
-          g12 = g12 + dvx * h2;
-          g21 = g21 + dvy * h1;
-          g22 = g22 + dvy * h2;
-        } else {  // type 9: wall particle (no-slip mirror velocity), main:552-575
-          const int q = S.order[2][j];
-          const double2 xp = ld2(st.x, id);
-          const double beta_max = 1.5, vel_wall = 0.0;
-          const double wall = (double)st.wallpos[q];
-          const double2 xq = ld2(st.x, q);
-          double da, db;
-          if (st.horiz[q] == 1.f) {
-            da = fabs(xp.y - wall);
-            db = fabs(xq.y - wall);
-          } else {
-            da = fabs(xp.x - wall);
-            db = fabs(xq.x - wall);
-          }
-          const double bq = 1 + (db / da);
-          const double beta = (bq < beta_max) ? bq : beta_max;
-          const double dvx = vp.x * (1 - beta) + beta * vel_wall;
-          const double dvy = vp.y * (1 - beta) + beta * vel_wall;
-          const double mq = st.mass[q], rq = st.rho[q];
-          const double h1 = gx * mq / rq;
-          const double h2 = gy * mq / rq;
-          g11 = g11 + (vp.x - dvx) * h1;
-          g12 = g12 + (vp.x - dvx) * h2;
-          g21 = g21 + (vp.y - dvy) * h1;
-          g22 = g22 + (vp.y - dvy) * h2;
-        }
-      }
+      const double bq = 1 + (db / da);
+      const double beta = (bq < beta_max) ? bq : beta_max;
+      const double dvx = vp.x * (1 - beta) + beta * vel_wall;
+      const double dvy = vp.y * (1 - beta) + beta * vel_wall;
+      const double mq = st.mass[pq], rq = st.rho[pq];
+      const double h1 = gx * mq / rq;
+      const double h2 = gy * mq / rq;
+      g11 = g11 + (vp.x - dvx) * h1;
+      g12 = g12 + (vp.x - dvx) * h2;
+      g21 = g21 + (vp.y - dvy) * h1;
+      g22 = g22 + (vp.y - dvy) * h2;
     }
-  }
+  });
   if (!live) return;
   if (P.cspm) {
     const double *AEp = st.AE + 5 * (size_t)id;
@@ -1047,92 +1057,58 @@ k_tile_b_sp(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
 constexpr int TB_N_CAP = 608;
 __global__ void __launch_bounds__(TN_T, TILE_MINB(TN_T))
 k_tile_b_node(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, TileLists L, TileRecs R,
-              StatePtrs st, int rev, double f1next, double f2, int last, int extra_forces) {
-  TILE_PROLOGUE(TN_T, SP_NODE, SP_STRESS, TB_N_CAP)
+              StatePtrs st, const TileGeom *__restrict__ geoms, int rev, double f1next, double f2, int last,
+              int extra_forces) {
   __shared__ Rec4 ssb[TB_N_CAP];
-  if (tg.staged) {
-    stage_rows(ssb, (const Rec4 *)R.SBs, nullptr, tg);
-    __syncthreads();
-  }
+  const int kb0 = blockIdx.x * TN_T;
+  if (kb0 >= M.nn) return;
+  const TileGeom tg = geoms[blockIdx.x];
   const int k0 = kb0 + threadIdx.x;
-  const bool live = k0 < nlive;
+  const bool live = k0 < M.nn;
   const int k = live ? k0 : kb0;
   const int t = k0;
   const int id = S.order[0][k];
-  const int n0r = live ? L.n0[t] : 0;
-  const int cnt = n0r & ~TILE_WALL_FLAG;
-  const bool wallp = (n0r & TILE_WALL_FLAG) != 0;
-  const int wrows = warp_max_i(cnt);
-  const bool rv = rev != 0;
-  int jA[3], jW[3] = {0, 0, 0};
-  const int cl = live ? S.cell[0][k] : -1;
-  lane_bases(G, cl, S.start[1], tg, jA);
-  if (wallp) lane_rows(G, cl, S.start[2], jW);
+  const LaneList q = lane_list0(L, t, live, tg);
+  stage_rows_async(ssb, (const Rec4 *)R.SBs, tg);
   const Rec4 self = R.NBs[k];  // {vx, vy, m, rho}
   const double2 vp = make_double2(self.a, self.b);
   const double rp = self.d;
   const Stress4 sp_ = ld4(st.NSb, id);
+  int jW[3] = {0, 0, 0};
+  if (q.wallp) lane_rows(G, S.cell[0][k], S.start[2], jW);
+  WalkWall ww;
+  ww.start(rev != 0);
   const double r2p = rp * rp;
   const double so1 = sp_.s1 / r2p, so2 = sp_.s2 / r2p, so3 = sp_.s3 / r2p;  // stress(1:3,i)/rho(i)**2
+  cp_async_wait_all();
+  __syncthreads();
+  const Rec4 *__restrict__ ssrc = tg.staged ? ssb : (const Rec4 *)R.SBs;
   double a11 = 0.0, a12 = 0.0, a21 = 0.0, a22 = 0.0, a31 = 0.0, a32 = 0.0;  // grad2_tmp(s,k)
-  {
-    Walk3 wk{0ull, 0ull, 0ull, jA[0], jA[1], jA[2]};
-    if (cnt > 0) {
-      wk.m0 = L.mA[t];
-      wk.m1 = L.mA[(size_t)L.nslots + t];
-      wk.m2 = L.mA[2 * (size_t)L.nslots + t];
+  walk_list<2>(L.code0, L.gx0, L.gy0, q, [&](unsigned cd, float gxf, float gyf) {
+    const double gx = (double)gxf, gy = (double)gyf;
+    double q1, q2, q3, mq;
+    if (cd < TILE_CODE_WALL) {  // type 1: stress particle {s1/rho^2, s2/rho^2, s3/rho^2, m}
+      const Rec4 p = ssrc[code_index(q, cd)];
+      q1 = p.a;
+      q2 = p.b;
+      q3 = p.c;
+      mq = p.d;
+    } else {  // type 6: the wall particle takes the velocity particle's stress (main:580)
+      const int pq = S.order[2][ww.next(L, t, rev != 0, jW)];
+      const double rq = st.rho[pq];
+      mq = st.mass[pq];
+      q1 = sp_.s1 / (rq * rq);
+      q2 = sp_.s2 / (rq * rq);
+      q3 = sp_.s3 / (rq * rq);
     }
-    WalkWall ww;
-    const bool anyw = __any_sync(0xffffffffu, wallp);
-    if (wallp) ww.start(L, t, rv, jA, jW);
-    const size_t base = ell0_base(L, t);
-    const int ng = (wrows + 3) >> 2;
-    float4 xn = make_float4(0.f, 0.f, 0.f, 0.f), yn = xn;
-    if (ng > 0) {
-      xn = ldcs4(L.gx0 + base);
-      yn = ldcs4(L.gy0 + base);
-    }
-    for (int g = 0; g < ng; ++g) {
-      const float4 xc = xn, yc = yn;
-      if (g + 1 < ng) {
-        xn = ldcs4(L.gx0 + base + (size_t)(g + 1) * 32);
-        yn = ldcs4(L.gy0 + base + (size_t)(g + 1) * 32);
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (g * 4 + u >= cnt) continue;
-        bool isw = false;
-        int j;
-        if (anyw && wallp)
-          j = ww.next(L, t, rv, jA, jW, isw);
-        else
-          j = wk.next(rv);
-        const double gx = (double)f4c(xc, u), gy = (double)f4c(yc, u);
-        double q1, q2, q3, mq;
-        if (!isw) {  // type 1: stress particle {s1/rho^2, s2/rho^2, s3/rho^2, m}
-          const Rec4 q = tg.staged ? ssb[j] : ldrec(R.SBs, j);
-          q1 = q.a;
-          q2 = q.b;
-          q3 = q.c;
-          mq = q.d;
-        } else {  // type 6: the wall particle takes the velocity particle's stress (main:580)
-          const int q = S.order[2][j];
-          const double rq = st.rho[q];
-          mq = st.mass[q];
-          q1 = sp_.s1 / (rq * rq);
-          q2 = sp_.s2 / (rq * rq);
-          q3 = sp_.s3 / (rq * rq);
-        }
-        const double c1 = so1 + q1, c2 = so2 + q2, c3 = so3 + q3;
-        a11 = a11 - mq * (gx * c1);
-        a12 = a12 - mq * (gy * c1);
-        a21 = a21 - mq * (gx * c2);
-        a22 = a22 - mq * (gy * c2);
-        a31 = a31 - mq * (gx * c3);
-        a32 = a32 - mq * (gy * c3);
-      }
-    }
-  }
+    const double c1 = so1 + q1, c2 = so2 + q2, c3 = so3 + q3;
+    a11 = a11 - mq * (gx * c1);
+    a12 = a12 - mq * (gy * c1);
+    a21 = a21 - mq * (gx * c2);
+    a22 = a22 - mq * (gy * c2);
+    a31 = a31 - mq * (gx * c3);
+    a32 = a32 - mq * (gy * c3);
+  });
   if (!live) return;
   if (P.cspm) {
     const double *AEp = st.AE + 5 * (size_t)id;
@@ -1183,96 +1159,54 @@ k_tile_b_node(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays
 }
 
 // ------------------------------------------------------------------------------------------------------
-// artificial_viscosity, main:826-904 (fp32 locals and accumulators in list order) over the velocity-velocity masks;
+// artificial_viscosity, main:826-904 (fp32 locals and accumulators in list order) over the velocity-velocity list;
 // xij, yij are re-derived from the staged positions (the list path stored their fp32 roundings).
 // ------------------------------------------------------------------------------------------------------
 constexpr int TAV_CAP = 512;
 __global__ void __launch_bounds__(TS_T, TILE_MINB(TS_T))
-k_tile_av(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, TileLists L, TileRecs R, StatePtrs st,
-          int rev, float h_u) {
-  TILE_PROLOGUE(TS_T, SP_NODE, SP_NODE, TAV_CAP)
+k_tile_av(DevParams P, SlotMap M, SortArrays S, TileLists L, TileRecs R, StatePtrs st,
+          const TileGeom *__restrict__ geoms, float h_u) {
   __shared__ Rec4 sn_[TAV_CAP];
   __shared__ double2 sx[TAV_CAP];
-  if (tg.staged) {
-    stage_rows(sn_, (const Rec4 *)R.NBs, nullptr, tg);
-    stage_rows(sx, S.pos[0], nullptr, tg);
-    __syncthreads();
-  }
+  const int kb0 = blockIdx.x * TS_T;
+  if (kb0 >= M.nn) return;
+  const TileGeom tg = geoms[blockIdx.x];
   const int k0 = kb0 + threadIdx.x;
-  const bool live = k0 < nlive;
+  const bool live = k0 < M.nn;
   const int k = live ? k0 : kb0;
   const int t = k0;
   const int id = S.order[0][k];
-  const int cnt = live ? L.n1[t] : 0;
-  const int wrows = warp_max_i(cnt);
-  const bool rv = rev != 0;
-  int jS[3];
-  lane_bases(G, live ? S.cell[0][k] : -1, S.start[0], tg, jS);
+  const LaneList q = lane_listS(L, t, live, tg);
+  stage_rows_async(sn_, (const Rec4 *)R.NBs, tg);
+  stage_rows_async(sx, S.pos[0], tg);
   const Rec4 self = R.NBs[k];
   const double2 vp = make_double2(self.a, self.b);
   const double rp = self.d;
   const double2 pp = S.pos[0][k];
+  cp_async_wait_all();
+  __syncthreads();
+  const Rec4 *__restrict__ nsrc = tg.staged ? sn_ : (const Rec4 *)R.NBs;
+  const double2 *__restrict__ xsrc = tg.staged ? sx : S.pos[0];
   float acc1 = 0.f, acc2 = 0.f;
-  {
-    Walk3 wk{0ull, 0ull, 0ull, jS[0], jS[1], jS[2]};
-    if (cnt > 0) {
-      wk.m0 = L.mS[t];
-      wk.m1 = L.mS[(size_t)L.nslots + t];
-      wk.m2 = L.mS[2 * (size_t)L.nslots + t];
-    }
-    const size_t base = ellC_base(L, t);
-    const int ng = (wrows + 3) >> 2;
-    float4 xn = make_float4(0.f, 0.f, 0.f, 0.f), yn = xn;
-    if (ng > 0) {
-      xn = ldcs4(L.gxC + base);
-      yn = ldcs4(L.gyC + base);
-    }
-    for (int g = 0; g < ng; ++g) {
-      const float4 xc = xn, yc = yn;
-      if (g + 1 < ng) {
-        xn = ldcs4(L.gxC + base + (size_t)(g + 1) * 32);
-        yn = ldcs4(L.gyC + base + (size_t)(g + 1) * 32);
-      }
-      float visc[4];
-      double mqs[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {  // independent per entry: the division chains interleave
-        visc[u] = 0.f;
-        mqs[u] = 0.0;
-        if (g * 4 + u >= cnt) continue;
-        const int j = wk.next(rv);
-        Rec4 q;
-        double2 pq;
-        if (tg.staged) {
-          q = sn_[j];
-          pq = sx[j];
-        } else {
-          q = ldrec(R.NBs, j);
-          pq = S.pos[0][j];
-        }
-        mqs[u] = q.c;
-        const float xij = (float)(pp.x - pq.x), yij = (float)(pp.y - pq.y);  // main:856-857
-        const float h = h_u;
-        const float rho2 = (float)(0.5 * (rp + q.d));
-        const float cs = 600.f;
-        float div_u = (float)((double)xij * (vp.x - q.a));
-        div_u = (float)((double)div_u + (double)yij * (vp.y - q.b));
-        const float sq = sqrtf(xij * xij + yij * yij);
-        const float theta = (h * div_u) / (sq * sq + 0.01f * (h * h));
-        const double rho2d = (double)rho2;
-        const double num = -P.alpha * (double)cs * (double)theta + P.beta * (double)(theta * theta);
-        const float vv = (float)div_rn(num, rho2d, __drcp_rn(rho2d));
-        visc[u] = (div_u < 0) ? vv : 0.f;
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {  // ordered fp32 accumulation
-        if (g * 4 + u >= cnt) continue;
-        const float gxf = f4c(xc, u), gyf = f4c(yc, u);
-        acc1 = (float)((double)acc1 + (double)(visc[u] * gxf) * mqs[u]);
-        acc2 = (float)((double)acc2 + (double)(visc[u] * gyf) * mqs[u]);
-      }
-    }
-  }
+  walk_list<2>(L.codeS, L.gxC, L.gyC, q, [&](unsigned cd, float gxf, float gyf) {
+    const int j = code_index(q, cd);
+    const Rec4 p = nsrc[j];
+    const double2 pq = xsrc[j];
+    const float xij = (float)(pp.x - pq.x), yij = (float)(pp.y - pq.y);  // main:856-857
+    const float h = h_u;
+    const float rho2 = (float)(0.5 * (rp + p.d));
+    const float cs = 600.f;
+    float div_u = (float)((double)xij * (vp.x - p.a));
+    div_u = (float)((double)div_u + (double)yij * (vp.y - p.b));
+    const float sq = sqrtf(xij * xij + yij * yij);
+    const float theta = (h * div_u) / (sq * sq + 0.01f * (h * h));
+    const double rho2d = (double)rho2;
+    const double num = -P.alpha * (double)cs * (double)theta + P.beta * (double)(theta * theta);
+    const float vv = (float)div_rn(num, rho2d, __drcp_rn(rho2d));
+    const float visc = (div_u < 0) ? vv : 0.f;
+    acc1 = (float)((double)acc1 + (double)(visc * gxf) * p.c);  // ordered fp32 accumulation
+    acc2 = (float)((double)acc2 + (double)(visc * gyf) * p.c);
+  });
   if (!live) return;
   st2(st.av, id, make_double2((double)(-acc1), (double)(-acc2)));  // art_visc = -art_visc_temp, main:901
 }
@@ -1280,48 +1214,48 @@ k_tile_av(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, 
 // ------------------------------------------------------------------------------------------------------
 // Position update, main:140-182: XSPH_update (main:189-239; w re-evaluated from the staged positions instead of
 // streamed: the same-species weights have no other reader) or the fp32 mid-velocity rule; displ.
-// One launch, warp-uniform role: velocity particles first, then stress particles.
+// One launch, block-uniform role: velocity particles first, then stress particles.
 // ------------------------------------------------------------------------------------------------------
 constexpr int TMV_CAP = 640;
 __global__ void __launch_bounds__(TS_T, TILE_MINB(TS_T))
-k_tile_move(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, TileLists L, SortedConsts C,
-            TileRecs R, StatePtrs st, int rev, int nb_node, double *__restrict__ x, const double *__restrict__ x00,
-            double *__restrict__ displ) {
+k_tile_move(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C, TileRecs R, StatePtrs st,
+            const TileGeom *__restrict__ geoms_n, const TileGeom *__restrict__ geoms_s, int nb_node,
+            double *__restrict__ x, const double *__restrict__ x00, double *__restrict__ displ) {
   const bool is_node = (int)blockIdx.x < nb_node;  // block-uniform
   const int sp = is_node ? SP_NODE : SP_STRESS;
-  __shared__ TileGeom tg;
   __shared__ double2 sv[TMV_CAP], sx[TMV_CAP];
   __shared__ double smo[TMV_CAP];
-  const int kb0 = (is_node ? blockIdx.x : blockIdx.x - nb_node) * TS_T;
+  const int bq = is_node ? blockIdx.x : blockIdx.x - nb_node;
+  const int kb0 = bq * TS_T;
   const int nlive = is_node ? M.nn : M.ns;
   if (kb0 >= nlive) return;
   const bool xs = P.update_x && P.xsph;
-  if (threadIdx.x == 0) {
-    if (xs)
-      tile_geom(G, S.cell[sp][kb0], S.cell[sp][min(kb0 + TS_T, nlive) - 1], S.start[sp], TMV_CAP, tg);
-    else
-      tg.staged = 0;
-  }
-  __syncthreads();
-  if (xs && tg.staged) {
-    if (is_node) {
-      for (int r = 0; r < 3; ++r)
-        for (int i = threadIdx.x; i < tg.cnt[r]; i += blockDim.x) {
-          const Rec4 q = R.NBs[tg.base[r] + i];
-          sv[tg.off[r] + i] = make_double2(q.a, q.b);
-        }
-    } else {
-      stage_rows(sv, (const double2 *)R.SVs, nullptr, tg);
-    }
-    stage_rows(sx, S.pos[sp], nullptr, tg);
-    stage_rows(smo, C.mor[sp], nullptr, tg);
-    __syncthreads();
-  }
+  TileGeom tg;
+  tg.staged = 0;
+  if (xs) tg = (is_node ? geoms_n : geoms_s)[bq];
   const int k0 = kb0 + threadIdx.x;
   const bool live = k0 < nlive;
   const int k = live ? k0 : kb0;
   const int t = is_node ? k0 : M.nnp + k0;
   const int id = S.order[sp][k];
+  LaneList q;
+  q.cnt = 0;
+  if (xs) {
+    q = lane_listS(L, t, live, tg);
+    if (tg.staged) {
+      if (is_node) {
+        for (int r = 0; r < 3; ++r)
+          for (int i = threadIdx.x; i < tg.cnt[r]; i += blockDim.x) {
+            const Rec4 p = R.NBs[tg.base[r] + i];
+            sv[tg.off[r] + i] = make_double2(p.a, p.b);
+          }
+      } else {
+        stage_rows_async(sv, (const double2 *)R.SVs, tg);
+      }
+      stage_rows_async(sx, S.pos[sp], tg);
+      stage_rows_async(smo, C.mor[sp], tg);
+    }
+  }
   double2 vp;
   if (is_node) {
     const Rec4 r = R.NBs[k];
@@ -1329,67 +1263,41 @@ k_tile_move(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
   } else {
     vp = R.SVs[k];
   }
+  const double2 pp = S.pos[sp][k];
+  const double2 xp = ld2(x, id);
+  cp_async_wait_all();
+  __syncthreads();
   double sx_ = 0.0, sy_ = 0.0;
   if (xs) {
-    const int cnt = live ? L.n1[t] : 0;
-    int jS[3];
-    lane_bases(G, live ? S.cell[sp][k] : -1, S.start[sp], tg, jS);
-    Walk3 wk{0ull, 0ull, 0ull, jS[0], jS[1], jS[2]};
-    if (cnt > 0) {
-      wk.m0 = L.mS[t];
-      wk.m1 = L.mS[(size_t)L.nslots + t];
-      wk.m2 = L.mS[2 * (size_t)L.nslots + t];
-    }
-    const double2 pp = S.pos[sp][k];
+    const bool staged = tg.staged != 0;
+    const double2 *__restrict__ xsrc = staged ? sx : S.pos[sp];
+    const double *__restrict__ msrc = staged ? smo : C.mor[sp];
     const KernelConsts K = kernel_consts(P, S.h[sp][k]);
-    const bool rv = rev != 0;
-    const int wrows = warp_max_i(cnt);
-    for (int e0 = 0; e0 < wrows; e0 += 4) {
-      double2 vq[4], pq[4];
-      double mo[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        vq[u] = vp;
-        pq[u] = pp;
-        mo[u] = 0.0;
-        if (e0 + u >= cnt) continue;
-        const int j = wk.next(rv);
-        if (tg.staged) {
-          vq[u] = sv[j];
-          pq[u] = sx[j];
-          mo[u] = smo[j];
-        } else {
-          if (is_node) {
-            const Rec4 q = ldrec(R.NBs, j);
-            vq[u] = make_double2(q.a, q.b);
-          } else {
-            vq[u] = R.SVs[j];
-          }
-          pq[u] = S.pos[sp][j];
-          mo[u] = C.mor[sp][j];
-        }
+    walk_list<0>(L.codeS, nullptr, nullptr, q, [&](unsigned cd, float, float) {
+      const int j = code_index(q, cd);
+      double2 vq;
+      if (staged) {
+        vq = sv[j];
+      } else if (is_node) {
+        const Rec4 p = ldrec(R.NBs, j);
+        vq = make_double2(p.a, p.b);
+      } else {
+        vq = R.SVs[j];
       }
-      double wd[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        const double dx = pp.x - pq[u].x, dy = pp.y - pq[u].y;
-        double d2 = dx * dx;
-        d2 = d2 + dy * dy;
-        const double r = sqrt(d2);
-        double w, gx, gy;
-        sph_kernel_fast<false>(K, r, dx, dy, w, gx, gy);
-        wd[u] = (double)(float)w;  // pairs%w is fp32 (main:1376)
-      }
-#pragma unroll
-      for (int u = 0; u < 4; ++u) {
-        if (e0 + u >= cnt) continue;
-        sx_ = sx_ + mo[u] * (vq[u].x - vp.x) * wd[u];
-        sy_ = sy_ + mo[u] * (vq[u].y - vp.y) * wd[u];
-      }
-    }
+      const double2 pq = xsrc[j];
+      const double dx = pp.x - pq.x, dy = pp.y - pq.y;
+      double d2 = dx * dx;
+      d2 = d2 + dy * dy;
+      const double r = sqrt(d2);
+      double w, gx, gy;
+      sph_kernel_fast<false>(K, r, dx, dy, w, gx, gy);
+      const double wd = (double)(float)w;  // pairs%w is fp32 (main:1376)
+      const double mo = msrc[j];
+      sx_ = sx_ + mo * (vq.x - vp.x) * wd;
+      sy_ = sy_ + mo * (vq.y - vp.y) * wd;
+    });
   }
   if (!live) return;
-  const double2 xp = ld2(x, id);
   if (P.update_x) {
     double2 xn;
     if (P.xsph) {
