@@ -938,6 +938,7 @@ static int tile_setup(spsph_handle *h) {
   int rc = dalloc(h, &T.rowA, 3 * nsl) | dalloc(h, &T.rowS, 3 * nsl) | dalloc(h, &T.mW, 3 * nsl);
   rc |= dalloc(h, &h->GT.g[0], (size_t)h->M.nsp / TS_T + 2) | dalloc(h, &h->GT.g[1], (size_t)h->M.nnp / TN_T + 2);
   rc |= dalloc(h, &h->GT.g[2], (size_t)h->M.nnp / TS_T + 2) | dalloc(h, &h->GT.g[3], (size_t)h->M.nsp / TS_T + 2);
+  rc |= dalloc(h, &h->GT.g[4], (size_t)h->M.nnp / TN_T + 2);
   rc |= dalloc(h, &h->smor, 2 * n2) | dalloc(h, &h->srrho, 2 * n2) | dalloc(h, &h->smrho, 2 * n2);
   rc |= dalloc(h, &h->TR.NAs, (size_t)h->M.nnp) | dalloc(h, &h->TR.NBs, (size_t)h->M.nnp);
   rc |= dalloc(h, &h->TR.SAs, (size_t)h->M.nsp) | dalloc(h, &h->TR.SBs, (size_t)h->M.nsp) | dalloc(h, &h->TR.SVs, (size_t)h->M.nsp);
@@ -1023,7 +1024,8 @@ int tile_build(spsph_handle *h, bool *use) {
   }
   {  // tile geometry of every block of the pair-sum kernels
     const int nb = std::max((h->M.nsp + TS_T - 1) / TS_T, (h->M.nnp + TN_T - 1) / TN_T);
-    k_tile_geoms<<<dim3((nb + 127) / 128, 4), 128, 0, s>>>(h->G, S, h->nout, h->GT, TB_SP_CAP, TB_N_CAP, TAV_CAP, TMV_CAP);
+    k_tile_geoms<<<dim3((nb + 127) / 128, 5), 128, 0, s>>>(h->G, S, h->nout, h->GT, TB_SP_CAP, TB_N_CAP, TMV_CAP, TMV_CAP,
+                                                           TAV_CAP);
     mark(h, KID_TBUILD);
   }
   // list-growth rule: forward order unless the list grew; a list that grows after the first step
@@ -1096,7 +1098,7 @@ int tile_step(spsph_handle *h, int itimestep) {
     const double f1n = last ? 0.0 : f1rk[stg + 1];
     fork();
     if (GSs) k_tile_b_sp<<<GSs, TS_T, 0, s>>>(P, M, h->G, S, L, C, R, st, h->GT.g[0], rev, f1n, f2rk[stg], last);
-    if (artv && GNs) k_tile_av<<<GNs, TS_T, 0, s2>>>(P, M, S, L, R, st, h->GT.g[2], h->h_uniform);
+    if (artv && GNn) k_tile_av<<<GNn, TN_T, 0, s2>>>(P, M, S, L, R, st, h->GT.g[4], h->h_uniform);
     if (GNn) k_tile_b_node<<<GNn, TN_T, 0, s2>>>(P, M, h->G, S, L, R, st, h->GT.g[1], rev, f1n, f2rk[stg], last, extra);
     join();
     mark(h, KID_SWEEPB, artv ? 3 : 2);

@@ -166,8 +166,13 @@ __device__ __forceinline__ void cp_async_8(void *smem, const void *gmem) {
   const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
   asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(sa), "l"(gmem) : "memory");
 }
+__device__ __forceinline__ void cp_async_4(void *smem, const void *gmem) {
+  const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;\n" ::: "memory"); }
 #else
+inline void cp_async_4(void *smem, const void *gmem) { std::memcpy(smem, gmem, 4); }
 inline void cp_async_16(void *smem, const void *gmem) { std::memcpy(smem, gmem, 16); }
 inline void cp_async_8(void *smem, const void *gmem) { std::memcpy(smem, gmem, 8); }
 inline void cp_async_wait_all() {}
@@ -238,28 +243,29 @@ struct WalkWall {
 // uniform load instead of a chain of dependent ones (cell of its first / last target -> cell table -> ranges).
 //   kind 0: stress-particle targets, velocity-particle partners (sweeps A and B, stress side)
 //   kind 1: velocity-particle targets, stress-particle partners (sweeps A and B, velocity side)
-//   kind 2: velocity-particle targets and partners (artificial viscosity, XSPH)
+//   kind 2: velocity-particle targets and partners (XSPH)
 //   kind 3: stress-particle targets and partners (XSPH)
+//   kind 4: velocity-particle targets and partners, half-size blocks (artificial viscosity)
 // ------------------------------------------------------------------------------------------------------
 constexpr int TS_T = 128;  // targets per block: stress-particle side, artificial viscosity, position update
 constexpr int TN_T = 64;   // velocity-particle side of sweeps A and B (a tile of stress particles is twice as large)
 struct GeomTables {
-  TileGeom *g[4];
+  TileGeom *g[5];
 };
 __device__ __forceinline__ void geom_kind(int kind, int &tsp, int &qsp, int &T) {
   tsp = (kind == 0 || kind == 3) ? SP_STRESS : SP_NODE;
-  qsp = (kind == 0 || kind == 2) ? SP_NODE : SP_STRESS;
-  T = kind == 1 ? TN_T : TS_T;
+  qsp = (kind == 0 || kind == 2 || kind == 4) ? SP_NODE : SP_STRESS;
+  T = (kind == 1 || kind == 4) ? TN_T : TS_T;
 }
 __global__ void k_tile_geoms(const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ nout, GeomTables GT,
-                             int cap0, int cap1, int cap2, int cap3) {
+                             int cap0, int cap1, int cap2, int cap3, int cap4) {
   const int kind = blockIdx.y;
   int tsp, qsp, T;
   geom_kind(kind, tsp, qsp, T);
   const int nlive = S.start[tsp][G->ncell] + nout[tsp];
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b * T >= nlive) return;
-  const int cap = kind == 0 ? cap0 : (kind == 1 ? cap1 : (kind == 2 ? cap2 : cap3));
+  const int cap = kind == 0 ? cap0 : (kind == 1 ? cap1 : (kind == 2 ? cap2 : (kind == 3 ? cap3 : cap4)));
   TileGeom g;
   tile_geom(G, S.cell[tsp][b * T], S.cell[tsp][min(b * T + T, nlive) - 1], S.start[qsp], cap, g);
   GT.g[kind][b] = g;
@@ -293,7 +299,8 @@ k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileList
   constexpr int SQA = SP == SP_NODE ? SP_STRESS : SP_NODE;  // cross-species partner of a list-owning target
   __shared__ float2 su0[LISTS ? TB_CAP0 : 1], su1[LISTS ? TB_CAP1 : 1], su2[LISTS ? TB_CAP2 : 1];
   __shared__ double2 sx0[LISTS ? TB_CAP0 : 1], sx1[LISTS ? TB_CAP1 : 1], sx2[LISTS ? TB_CAP2 : 1];
-  __shared__ unsigned scode0[LISTS ? (TB_CODES / 4) * TB_T : 1], scodeS[LISTS ? (TB_CODES / 4) * TB_T : 1];
+  // entry codes of the block's targets in creation order, one byte per entry: [entry][thread]
+  __shared__ unsigned char scode0[LISTS ? TB_CODES * TB_T : 4], scodeS[LISTS ? TB_CODES * TB_T : 4];
   __shared__ TileGeom tgs[3];
   const int nlive = S.start[SP][G->ncell] + nout[SP];  // sorted particles of this species, incl. out-of-domain ones
   const int kb0 = blockIdx.x * TB_T;
@@ -328,59 +335,101 @@ k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileList
   }
   const Prefilter pf = prefilter_bounds(P, G, hp);
   const double sk = (double)P.scale_k;
-  int ovf = 0;
-  u64 mk[3][3];   // acceptance masks [species][row]
-  int jbs[3][3];  // index of bit 0 in the staged tile (or the global sorted array)
-  int gbs[3][3];  // ... in the global sorted array
-  int cf = 0, ca = 0;
-  int ndx = 1, ndy = 1, cy = 0, cx = 0;
-  if (c >= 0) {
-    ndx = G->ndivx[0];
-    ndy = G->ndivx[1];
-    cy = c / ndx;
-    cx = c - cy * ndx;
-  }
+  // where the candidates are read: the staged tile or the global sorted arrays (generic pointers, set once)
+  const float2 *U[3];
+  const double2 *X[3];
 #pragma unroll
   for (int sq = 0; sq < 3; ++sq) {
-    const Src<float2> U = make_src<float2>(sq == 0 ? su0 : (sq == 1 ? su1 : su2), S.upos[sq], nullptr, tgs[sq]);
-    const Src<double2> X = make_src<double2>(sq == 0 ? sx0 : (sq == 1 ? sx1 : sx2), S.pos[sq], nullptr, tgs[sq]);
-#pragma unroll
-    for (int r = 0; r < 3; ++r) {
-      mk[sq][r] = 0ull;
-      jbs[sq][r] = 0;
-      gbs[sq][r] = 0;
-      const int row = cy - 1 + r;
-      if (c < 0 || row < 0 || row >= ndy) continue;
-      const int b = S.start[sq][row * ndx + max(cx - 1, 0)], e = S.start[sq][row * ndx + min(cx + 1, ndx - 1) + 1];
-      const int len = e - b;
-      const int jb = tgs[sq].staged ? b - tgs[sq].base[r] + tgs[sq].off[r] : b;
-      jbs[sq][r] = jb;
-      gbs[sq][r] = b;
-      if (len > (sq == SP_DUMMY && LISTS ? 32 : 64)) ovf |= 1;
-      const int n = min(len, 64);
-      u64 m = 0ull;
-      for (int i = 0; i < n; ++i) {
-        int cls = 2;
-        if (pf.on) cls = prefilter_test(pf, up, U(jb + i));
-        if (cls == 0) continue;
-        if (sq == SP && b + i == k) continue;
-        if (cls == 2) {
-          double dx, dy, d2, mh;
-          if (!pair_accept_fast(sk, pp, hp, X(jb + i), hp, dx, dy, d2, mh)) continue;
-        }
-        m |= 1ull << i;
+    const bool stg = LISTS && tgs[sq].staged;
+    U[sq] = stg ? (sq == 0 ? su0 : (sq == 1 ? su1 : su2)) : S.upos[sq];
+    X[sq] = stg ? (sq == 0 ? sx0 : (sq == 1 ? sx1 : sx2)) : S.pos[sq];
+  }
+  const bool rv = rev != 0;
+  // same-species entries: velocity-velocity for artificial viscosity (want_c: with gradients) and XSPH, stress-stress
+  // for XSPH only
+  const bool want1 = LISTS && (SP == SP_NODE ? (want_c != 0 || want_s != 0) : want_s != 0);
+  int ovf = 0;
+  int cnt0 = 0, cnt1 = 0;  // entries of list 0 (cross-species + wall) and of the same-species list
+  int cf = 0;              // forward partners (pairs this particle opens in creation order, main:1322-1341)
+  unsigned mW[3] = {0u, 0u, 0u};
+  int jbs[3][3], gbs[3][3];  // [species][row]: tile index / global sorted index of candidate 0
+  // One candidate range. Accepted candidates get their code appended (creation order).
+  //   fwd_from: candidates from this position on are forward partners; iself: position of the particle itself or -1
+  auto scan = [&](int sq, int jb, int i0, int i1, unsigned rowtag, int fwd_from, int iself, unsigned char *sc, int &n,
+                  bool store, unsigned *wmask) {
+    const float2 *__restrict__ Uq = U[sq] + jb;
+    for (int i = i0; i < i1; ++i) {
+      const float2 uq = Uq[i];
+      const float du = up.x - uq.x, dv = up.y - uq.y;
+      const float d2 = __fmaf_rn(du, du, dv * dv);
+      bool acc = pf.on && d2 < pf.lo;
+      if (!acc && (!pf.on || d2 <= pf.hi)) {  // undecided by the fp32 prefilter: the reference's own test
+        double dx, dy, dd, mh;
+        acc = pair_accept_fast(sk, pp, hp, X[sq][jb + i], hp, dx, dy, dd, mh);
       }
-      mk[sq][r] = m;
-      const int na = __popcll(m);
-      ca += na;
-      // forward partners (creation order, main:1322-1341): later row, or own row from a threshold index on
-      if (r == 2)
-        cf += na;
-      else if (r == 1) {
-        const int fthr = (sq == SP) ? k + 1 : (sq > SP ? S.start[sq][c] : S.start[sq][c + 1]);
-        cf += popc_range(m, max(fthr - b, 0), 64);
+      if (i == iself) acc = false;
+      if (acc) {
+        if (store && n < TB_CODES) sc[n * TB_T + threadIdx.x] = (unsigned char)(wmask ? TILE_CODE_WALL : (rowtag | (unsigned)i));
+        if (wmask) *wmask |= 1u << i;
+        ++n;
+        cf += (i >= fwd_from) ? 1 : 0;
       }
     }
+  };
+  if (c >= 0) {
+    const int ndx = G->ndivx[0], ndy = G->ndivx[1];
+    const int cy = c / ndx, cx = c - cy * ndx;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int sq = 0; sq < 3; ++sq) jbs[sq][r] = gbs[sq][r] = 0;
+      const int row = cy - 1 + r;
+      if (row < 0 || row >= ndy) continue;
+      const int ca_ = row * ndx + max(cx - 1, 0), cb_ = row * ndx + min(cx + 1, ndx - 1);
+      int b[3], len[3], fw[3];
+#pragma unroll
+      for (int sq = 0; sq < 3; ++sq) {
+        b[sq] = S.start[sq][ca_];
+        len[sq] = S.start[sq][cb_ + 1] - b[sq];
+        gbs[sq][r] = b[sq];
+        jbs[sq][r] = (LISTS && tgs[sq].staged) ? b[sq] - tgs[sq].base[r] + tgs[sq].off[r] : b[sq];
+        // creation order: later row, or own row from a threshold index on (own cell: species, then index)
+        fw[sq] = r == 2 ? 0 : (r == 0 ? (1 << 30) : ((sq == SP ? k + 1 : (sq > SP ? S.start[sq][c] : S.start[sq][c + 1])) - b[sq]));
+        if (len[sq] > ((sq == SP_DUMMY && LISTS) ? 32 : 64)) {
+          ovf |= 1;
+          len[sq] = 0;
+        }
+      }
+      const int iself = r == 1 ? k - b[SP] : -1;
+      if (!LISTS) {  // wall particle: counts only
+        int n = 0;
+        scan(0, jbs[0][r], 0, len[0], 0u, fw[0], SP == 0 ? iself : -1, nullptr, n, false, nullptr);
+        scan(1, jbs[1][r], 0, len[1], 0u, fw[1], SP == 1 ? iself : -1, nullptr, n, false, nullptr);
+        scan(2, jbs[2][r], 0, len[2], 0u, fw[2], SP == 2 ? iself : -1, nullptr, n, false, nullptr);
+        cnt0 += n;
+        continue;
+      }
+      const unsigned rowtag = (unsigned)r << 6;
+      if (len[SP_DUMMY] == 0) {
+        scan(SQA, jbs[SQA][r], 0, len[SQA], rowtag, fw[SQA], -1, scode0, cnt0, true, nullptr);
+      } else {
+        // wall particles in this row: (cell, species, index) order -- cell by cell, the cross-species partners of the
+        // cell and then its wall particles
+        for (int cq = ca_; cq <= cb_; ++cq) {
+          scan(SQA, jbs[SQA][r], S.start[SQA][cq] - b[SQA], min(S.start[SQA][cq + 1] - b[SQA], len[SQA]), rowtag, fw[SQA],
+               -1, scode0, cnt0, true, nullptr);
+          scan(SP_DUMMY, jbs[SP_DUMMY][r], S.start[SP_DUMMY][cq] - b[SP_DUMMY],
+               min(S.start[SP_DUMMY][cq + 1] - b[SP_DUMMY], len[SP_DUMMY]), rowtag, fw[SP_DUMMY], -1, scode0, cnt0, true,
+               &mW[r]);
+        }
+      }
+      scan(SP, jbs[SP][r], 0, len[SP], rowtag, fw[SP], iself, scodeS, cnt1, want1, nullptr);
+    }
+  } else {
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int sq = 0; sq < 3; ++sq) jbs[sq][r] = gbs[sq][r] = 0;
   }
   // statistics: every pair is counted once, at the owner of its earlier member
   const bool owned = !lflag || lflag[id] == 1;
@@ -388,79 +437,14 @@ k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileList
     u64 f = (live && c >= 0 && owned) ? (u64)cf : 0ull;
     for (int o = 16; o > 0; o >>= 1) f += __shfl_xor_sync(0xffffffffu, f, o);
     if ((threadIdx.x & 31) == 0 && f) atomicAdd(acc_pairs, f);
-    if (live) nall[(SP == SP_NODE ? 0 : (SP == SP_STRESS ? nnp : L.nslots)) + k0] = owned ? (c >= 0 ? ca : 0) : -1;
+    if (live) nall[(SP == SP_NODE ? 0 : (SP == SP_STRESS ? nnp : L.nslots)) + k0] = owned ? (c >= 0 ? cnt0 + cnt1 : 0) : -1;
   }
   if (!LISTS) {
     if (__any_sync(0xffffffffu, ovf != 0) && (threadIdx.x & 31) == 0) atomicOr(&flags[0], 1);
     return;
   }
-  // ---- entry codes in traversal order: ascending (row, candidate); within a row with wall partners the reference
-  // visits, cell by cell, the cross-species partners of the cell and then its wall particles ((cell, species, index)
-  // order); reversed order: the mirror image ----
-  const bool rv = rev != 0;
-  unsigned mW[3];
-#pragma unroll
-  for (int r = 0; r < 3; ++r) mW[r] = (unsigned)mk[SP_DUMMY][r];
   const bool wallp = (mW[0] | mW[1] | mW[2]) != 0u;
-  const int cnt0 = __popcll(mk[SQA][0]) + __popcll(mk[SQA][1]) + __popcll(mk[SQA][2]) + __popc(mW[0]) + __popc(mW[1]) +
-                   __popc(mW[2]);
-  const int cnt1 = __popcll(mk[SP][0]) + __popcll(mk[SP][1]) + __popcll(mk[SP][2]);
-  if (cnt0 > TB_CODES || cnt1 > TB_CODES) ovf |= 1;
-  // same-species entries: velocity-velocity for artificial viscosity (want_c: with gradients) and XSPH, stress-stress
-  // for XSPH only
-  const bool want1 = SP == SP_NODE ? (want_c != 0 || want_s != 0) : want_s != 0;
-  auto put = [&](unsigned *sc, int e, unsigned code) {
-    if (e < TB_CODES) reinterpret_cast<unsigned char *>(sc + (e >> 2) * TB_T + threadIdx.x)[e & 3] = (unsigned char)code;
-  };
-  auto emit_bits = [&](unsigned *sc, int &e, u64 m, unsigned rowtag) {  // all set bits of m in traversal order
-    while (m) {
-      int b;
-      if (!rv) {
-        b = __ffsll((long long)m) - 1;
-        m &= m - 1;
-      } else {
-        b = 63 - __clzll((long long)m);
-        m ^= 1ull << b;
-      }
-      put(sc, e++, rowtag | (unsigned)b);
-    }
-  };
-  {
-    int e = 0;
-    for (int rr = 0; rr < 3; ++rr) {
-      const int r = rv ? 2 - rr : rr;
-      const u64 ma = r == 0 ? mk[SQA][0] : (r == 1 ? mk[SQA][1] : mk[SQA][2]);
-      const unsigned mw = r == 0 ? mW[0] : (r == 1 ? mW[1] : mW[2]);
-      if (!mw) {
-        emit_bits(scode0, e, ma, (unsigned)r << 6);
-        continue;
-      }
-      const int row = cy - 1 + r;
-      const int ca_ = row * ndx + max(cx - 1, 0), cb_ = row * ndx + min(cx + 1, ndx - 1);
-      const int bA = S.start[SQA][ca_], bW = S.start[SP_DUMMY][ca_];
-      for (int cc = 0; cc <= cb_ - ca_; ++cc) {
-        const int cq = rv ? cb_ - cc : ca_ + cc;
-        const int a0 = S.start[SQA][cq] - bA, a1 = S.start[SQA][cq + 1] - bA;
-        const int w0_ = S.start[SP_DUMMY][cq] - bW, w1_ = S.start[SP_DUMMY][cq + 1] - bW;
-        const u64 am = ma & bits_range(a0, a1);
-        const int nw = popc_range((u64)mw, w0_, w1_);
-        if (!rv) {
-          emit_bits(scode0, e, am, (unsigned)r << 6);
-          for (int q = 0; q < nw; ++q) put(scode0, e++, TILE_CODE_WALL);
-        } else {
-          for (int q = 0; q < nw; ++q) put(scode0, e++, TILE_CODE_WALL);
-          emit_bits(scode0, e, am, (unsigned)r << 6);
-        }
-      }
-    }
-    if (want1) {
-      int e1 = 0;
-      for (int rr = 0; rr < 3; ++rr) {
-        const int r = rv ? 2 - rr : rr;
-        emit_bits(scodeS, e1, r == 0 ? mk[SP][0] : (r == 1 ? mk[SP][1] : mk[SP][2]), (unsigned)r << 6);
-      }
-    }
-  }
+  if (cnt0 > TB_CODES || (want1 && cnt1 > TB_CODES)) ovf |= 1;
   const int cap0 = ell0_cap(L, t), cap1 = ellS_cap(L, t);
   if (cnt0 > cap0 || (want1 && cnt1 > cap1)) ovf |= 2;
   if (live) {
@@ -491,22 +475,28 @@ k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileList
     }
   }
   const bool ok_w = live && ovf == 0;
+  // the code word of entries 4g..4g+3 in TRAVERSAL order: creation order, or its mirror image in the first step
+  auto code_word = [&](const unsigned char *sc, int g, int cnt) {
+    unsigned cw = 0u;
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int e = g * 4 + u;
+      if (e < cnt) cw |= (unsigned)sc[(rv ? cnt - 1 - e : e) * TB_T + threadIdx.x] << (8 * u);
+    }
+    return cw;
+  };
   // ---- weights, in traversal order; entries are evaluated in groups of four (independent division / sqrt chains) ----
   const KernelConsts K = kernel_consts(P, hp);
-  const Src<double2> XA = make_src<double2>(SQA == 0 ? sx0 : sx1, S.pos[SQA], nullptr, tgs[SQA]);
-  const Src<double2> XS = make_src<double2>(SP == 0 ? sx0 : sx1, S.pos[SP], nullptr, tgs[SP]);
-  const Src<double2> XW = make_src<double2>(sx2, S.pos[SP_DUMMY], nullptr, tgs[SP_DUMMY]);
   const double2 *__restrict__ mrq = C.mrho[SQA];
   double nrm = 0.0, ae1 = 0.0, ae2 = 0.0, ae3 = 0.0, ae4 = 0.0;
   {
     const int n0w = ok_w ? cnt0 : 0;
-    const int wrows = warp_max_i(n0w);
     WalkWall ww;
     ww.start(rv);
     const int jW[3] = {jbs[SP_DUMMY][0], jbs[SP_DUMMY][1], jbs[SP_DUMMY][2]};
     const size_t base = ell0_base(L, t);
-    for (int g = 0; g * 4 < wrows; ++g) {
-      const unsigned cw = g < TB_CODES / 4 ? scode0[g * TB_T + threadIdx.x] : 0u;
+    for (int g = 0; g * 4 < n0w; ++g) {
+      const unsigned cw = code_word(scode0, g, n0w);
       float wv[4] = {0.f, 0.f, 0.f, 0.f}, gxv[4] = {0.f, 0.f, 0.f, 0.f}, gyv[4] = {0.f, 0.f, 0.f, 0.f};
       double2 pq[4];
       int jg[4];
@@ -521,9 +511,9 @@ k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileList
           const int r = (int)(cd >> 6), b = (int)(cd & 63u);
           if (r == 3) {
             isw[u] = true;
-            pq[u] = XW(ww.next(L, t, rv, jW));
+            pq[u] = X[SP_DUMMY][ww.next(L, t, rv, jW)];
           } else {
-            pq[u] = XA((r == 0 ? jbs[SQA][0] : (r == 1 ? jbs[SQA][1] : jbs[SQA][2])) + b);
+            pq[u] = X[SQA][(r == 0 ? jbs[SQA][0] : (r == 1 ? jbs[SQA][1] : jbs[SQA][2])) + b];
             jg[u] = (r == 0 ? gbs[SQA][0] : (r == 1 ? gbs[SQA][1] : gbs[SQA][2])) + b;
           }
         }
@@ -561,21 +551,18 @@ k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileList
           }
         }
       }
-      if (g * 4 < n0w) {
-        const size_t a = base + (size_t)g * 32;
-        L.code0[a] = cw;
-        L.w0[a] = make_float4(wv[0], wv[1], wv[2], wv[3]);
-        L.gx0[a] = make_float4(gxv[0], gxv[1], gxv[2], gxv[3]);
-        L.gy0[a] = make_float4(gyv[0], gyv[1], gyv[2], gyv[3]);
-      }
+      const size_t a = base + (size_t)g * 32;
+      L.code0[a] = cw;
+      L.w0[a] = make_float4(wv[0], wv[1], wv[2], wv[3]);
+      L.gx0[a] = make_float4(gxv[0], gxv[1], gxv[2], gxv[3]);
+      L.gy0[a] = make_float4(gyv[0], gyv[1], gyv[2], gyv[3]);
     }
   }
   if (want1) {  // same-species list: codes; velocity particles also the gradient from their own perspective
     const int n1w = ok_w ? cnt1 : 0;
-    const int wrows = warp_max_i(n1w);
     const size_t base = ellS_base(L, t);
-    for (int g = 0; g * 4 < wrows; ++g) {
-      const unsigned cw = g < TB_CODES / 4 ? scodeS[g * TB_T + threadIdx.x] : 0u;
+    for (int g = 0; g * 4 < n1w; ++g) {
+      const unsigned cw = code_word(scodeS, g, n1w);
       if (SP == SP_NODE && want_c) {
         float gxv[4] = {0.f, 0.f, 0.f, 0.f}, gyv[4] = {0.f, 0.f, 0.f, 0.f};
         double2 pq[4];
@@ -585,7 +572,7 @@ k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileList
           if (g * 4 + u < n1w) {
             const unsigned cd = (cw >> (8 * u)) & 0xffu;
             const int r = (int)(cd >> 6), b = (int)(cd & 63u);
-            pq[u] = XS((r == 0 ? jbs[SP][0] : (r == 1 ? jbs[SP][1] : jbs[SP][2])) + b);
+            pq[u] = X[SP][(r == 0 ? jbs[SP][0] : (r == 1 ? jbs[SP][1] : jbs[SP][2])) + b];
           }
         }
 #pragma unroll
@@ -600,13 +587,11 @@ k_tile_build(DevParams P, const GridInfo *__restrict__ G, SortArrays S, TileList
           gxv[u] = (float)gx;
           gyv[u] = (float)gy;
         }
-        if (g * 4 < n1w) {
-          const size_t a = base + (size_t)g * 32;
-          L.gxC[a] = make_float4(gxv[0], gxv[1], gxv[2], gxv[3]);
-          L.gyC[a] = make_float4(gyv[0], gyv[1], gyv[2], gyv[3]);
-        }
+        const size_t a = base + (size_t)g * 32;
+        L.gxC[a] = make_float4(gxv[0], gxv[1], gxv[2], gxv[3]);
+        L.gyC[a] = make_float4(gyv[0], gyv[1], gyv[2], gyv[3]);
       }
-      if (g * 4 < n1w) L.codeS[base + (size_t)g * 32] = cw;
+      L.codeS[base + (size_t)g * 32] = cw;
     }
   }
   if (!live) return;
@@ -655,6 +640,9 @@ struct TileRecs {
   double2 *SVs;  // [ns] velocity of a stress particle after the final interpolation: XSPH
 };
 
+// groups of four entries staged per lane: cross-species list of a stress / velocity particle, velocity-velocity list,
+// same-species list in the position update (typical lengths in the Bui layout: 18, 36, 17, 35 entries)
+constexpr int LG_SP0 = 7, LG_N0 = 10, LG_NC = 7, LG_SS = 11;
 #ifndef SPSPH_TILE_WARPS
 #define SPSPH_TILE_WARPS 16  // resident warps per SM requested from ptxas
 #endif
@@ -712,39 +700,50 @@ __device__ __forceinline__ int code_index(const LaneList &q, unsigned cd) {
   return (r == 0 ? q.j0 : (r == 1 ? q.j1 : q.j2)) + (int)(cd & 63u);
 }
 
-// Walk of a list: NA float4 weight arrays + the code words, groups of four entries, prefetched two groups ahead.
-// body(u, code, w...) is called for every entry of this lane in traversal order.
-template <int NA, class Body>
-__device__ __forceinline__ void walk_list(const unsigned *__restrict__ code, const float4 *__restrict__ a0,
-                                          const float4 *__restrict__ a1, const LaneList &q, Body body) {
-  const int ng = (q.cnt + 3) >> 2;  // per lane: a lane only touches the groups it owns
-  if (ng == 0) return;
-  unsigned c0 = 0u, c1 = 0u, c2 = 0u;
-  float4 x0 = make_float4(0.f, 0.f, 0.f, 0.f), x1 = x0, x2 = x0, y0 = x0, y1 = x0, y2 = x0;
-  c0 = ldcs1(code + q.base);
-  if (NA > 0) x0 = ldcs4(a0 + q.base);
-  if (NA > 1) y0 = ldcs4(a1 + q.base);
-  if (ng > 1) {
-    c1 = ldcs1(code + q.base + 32);
-    if (NA > 0) x1 = ldcs4(a0 + q.base + 32);
-    if (NA > 1) y1 = ldcs4(a1 + q.base + 32);
-  }
+// A block's list entries staged in shared memory: every lane copies ITS OWN groups (codes + NA float4 weight arrays)
+// with cp.async right at the start of the block, together with the partner tile, so that all global loads of the
+// pair sum are in flight at once and the walk itself runs out of shared memory. LG groups are staged; a lane with a
+// longer list reads the rest from global memory.
+template <int NA, int T, int LG>
+struct ListSmem {
+  unsigned c[LG][T];
+  float4 x[NA > 0 ? LG : 1][T];
+  float4 y[NA > 1 ? LG : 1][T];
+};
+template <int NA, int T, int LG>
+__device__ __forceinline__ void list_stage(ListSmem<NA, T, LG> &sm, const unsigned *__restrict__ code,
+                                           const float4 *__restrict__ a0, const float4 *__restrict__ a1,
+                                           const LaneList &q) {
+  const int ng = min((q.cnt + 3) >> 2, LG);
   for (int g = 0; g < ng; ++g) {
-    if (g + 2 < ng) {
-      const size_t a = q.base + (size_t)(g + 2) * 32;
-      c2 = ldcs1(code + a);
-      if (NA > 0) x2 = ldcs4(a0 + a);
-      if (NA > 1) y2 = ldcs4(a1 + a);
+    const size_t a = q.base + (size_t)g * 32;
+    cp_async_4(&sm.c[g][threadIdx.x], code + a);
+    if (NA > 0) cp_async_16(&sm.x[g][threadIdx.x], a0 + a);
+    if (NA > 1) cp_async_16(&sm.y[g][threadIdx.x], a1 + a);
+  }
+}
+// body(code, w0, w1) is called for every entry of this lane in traversal order
+template <int NA, int T, int LG, class Body>
+__device__ __forceinline__ void walk_list(const ListSmem<NA, T, LG> &sm, const unsigned *__restrict__ code,
+                                          const float4 *__restrict__ a0, const float4 *__restrict__ a1,
+                                          const LaneList &q, Body body) {
+  const int ng = (q.cnt + 3) >> 2;
+  for (int g = 0; g < ng; ++g) {
+    unsigned c;
+    float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
+    if (g < LG) {
+      c = sm.c[g][threadIdx.x];
+      if (NA > 0) x = sm.x[g][threadIdx.x];
+      if (NA > 1) y = sm.y[g][threadIdx.x];
+    } else {
+      const size_t a = q.base + (size_t)g * 32;
+      c = ldcs1(code + a);
+      if (NA > 0) x = ldcs4(a0 + a);
+      if (NA > 1) y = ldcs4(a1 + a);
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
-      if (g * 4 + u < q.cnt) body((c0 >> (8 * u)) & 0xffu, f4c(x0, u), f4c(y0, u));
-    c0 = c1;
-    c1 = c2;
-    x0 = x1;
-    x1 = x2;
-    y0 = y1;
-    y1 = y2;
+      if (g * 4 + u < q.cnt) body((c >> (8 * u)) & 0xffu, f4c(x, u), f4c(y, u));
   }
 }
 
@@ -759,6 +758,7 @@ k_tile_a_sp(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C, T
             const TileGeom *__restrict__ geoms, int do_adapt, int do_bc, int final_sweep) {
   __shared__ double2 sv[TA_SP_CAP];
   __shared__ double smo[TA_SP_CAP];
+  __shared__ ListSmem<1, TS_T, LG_SP0> sl;
   const int kb0 = blockIdx.x * TS_T;
   if (kb0 >= M.ns) return;
   const TileGeom tg = geoms[blockIdx.x];
@@ -769,6 +769,7 @@ k_tile_a_sp(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C, T
   const int id = S.order[1][k];
   const int ks = id - P.nnode;
   const LaneList q = lane_list0(L, t, live, tg);
+  list_stage(sl, L.code0, L.w0, nullptr, q);
   if (tg.staged) {
     if (FROMB) {
       for (int r = 0; r < 3; ++r)
@@ -800,7 +801,7 @@ k_tile_a_sp(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C, T
   const double2 *__restrict__ vsrc = staged ? sv : (const double2 *)R.NAs;
   const double *__restrict__ msrc = staged ? smo : C.mor[0];
   double vtx = 0.0, vty = 0.0;
-  walk_list<1>(L.code0, L.w0, nullptr, q, [&](unsigned cd, float w, float) {
+  walk_list(sl, L.code0, L.w0, nullptr, q, [&](unsigned cd, float w, float) {
     if (cd >= TILE_CODE_WALL) return;  // wall partners (type 9) take no part
     const int j = code_index(q, cd);
     double2 vq;
@@ -839,6 +840,7 @@ k_tile_a_node(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C,
   __shared__ Rec4 ss[TA_N_CAP];
   __shared__ double smo[TA_N_CAP];
   __shared__ double sep[EPSP ? TA_N_CAP : 1];
+  __shared__ ListSmem<1, TN_T, LG_N0> sl;
   const int kb0 = blockIdx.x * TN_T;
   if (kb0 >= M.nn) return;
   const TileGeom tg = geoms[blockIdx.x];
@@ -848,6 +850,7 @@ k_tile_a_node(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C,
   const int t = k0;
   const int id = S.order[0][k];
   const LaneList q = lane_list0(L, t, live, tg);
+  list_stage(sl, L.code0, L.w0, nullptr, q);
   if (tg.staged) {
     if (FROMB) {
       for (int r = 0; r < 3; ++r)
@@ -877,7 +880,7 @@ k_tile_a_node(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C,
   const Rec4 *__restrict__ ssrc = staged ? ss : (const Rec4 *)R.SAs;
   const double *__restrict__ msrc = staged ? smo : C.mor[1];
   double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, te = 0.0;
-  walk_list<1>(L.code0, L.w0, nullptr, q, [&](unsigned cd, float w, float) {
+  walk_list(sl, L.code0, L.w0, nullptr, q, [&](unsigned cd, float w, float) {
     if (cd >= TILE_CODE_WALL) return;  // wall partners (type 6) take no part
     const int j = code_index(q, cd);
     Rec4 p;
@@ -925,6 +928,7 @@ k_tile_b_sp(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
             TileRecs R, StatePtrs st, const TileGeom *__restrict__ geoms, int rev, double f1next, double f2, int last) {
   __shared__ Rec4 sn_[TB_SP_CAP];
   __shared__ double srr[TB_SP_CAP];
+  __shared__ ListSmem<2, TS_T, LG_SP0> sl;
   const int kb0 = blockIdx.x * TS_T;
   if (kb0 >= M.ns) return;
   const TileGeom tg = geoms[blockIdx.x];
@@ -935,6 +939,7 @@ k_tile_b_sp(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
   const int id = S.order[1][k];
   const int ks = id - P.nnode;
   const LaneList q = lane_list0(L, t, live, tg);
+  list_stage(sl, L.code0, L.gx0, L.gy0, q);
   stage_rows_async(sn_, (const Rec4 *)R.NBs, tg);
   stage_rows_async(srr, C.rrho[0], tg);
   const Rec4 selfv = ldrec(st.SVb, ks);
@@ -950,7 +955,7 @@ k_tile_b_sp(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
   const Rec4 *__restrict__ nsrc = staged ? sn_ : (const Rec4 *)R.NBs;
   const double *__restrict__ rsrc = staged ? srr : C.rrho[0];
   double g11 = 0.0, g12 = 0.0, g21 = 0.0, g22 = 0.0;  // grad1_tmp(d,k): d velocity component, k direction
-  walk_list<2>(L.code0, L.gx0, L.gy0, q, [&](unsigned cd, float gxf, float gyf) {
+  walk_list(sl, L.code0, L.gx0, L.gy0, q, [&](unsigned cd, float gxf, float gyf) {
     const double gx = (double)gxf, gy = (double)gyf;
     if (cd < TILE_CODE_WALL) {  // type 1: velocity particle {vx, vy, m, rho}
       const int j = code_index(q, cd);
@@ -1054,12 +1059,13 @@ k_tile_b_sp(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
 // Sweep B, velocity-particle side: (1/rho) grad sigma (main:529-536, wall term main:577-588), CSPM correction, div2,
 // gravity / damping, artificial viscosity of the stage, RK4 accumulation and predictor.
 // ------------------------------------------------------------------------------------------------------
-constexpr int TB_N_CAP = 608;
+constexpr int TB_N_CAP = 544;
 __global__ void __launch_bounds__(TN_T, TILE_MINB(TN_T))
 k_tile_b_node(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, TileLists L, TileRecs R,
               StatePtrs st, const TileGeom *__restrict__ geoms, int rev, double f1next, double f2, int last,
               int extra_forces) {
   __shared__ Rec4 ssb[TB_N_CAP];
+  __shared__ ListSmem<2, TN_T, LG_N0> sl;
   const int kb0 = blockIdx.x * TN_T;
   if (kb0 >= M.nn) return;
   const TileGeom tg = geoms[blockIdx.x];
@@ -1069,6 +1075,7 @@ k_tile_b_node(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays
   const int t = k0;
   const int id = S.order[0][k];
   const LaneList q = lane_list0(L, t, live, tg);
+  list_stage(sl, L.code0, L.gx0, L.gy0, q);
   stage_rows_async(ssb, (const Rec4 *)R.SBs, tg);
   const Rec4 self = R.NBs[k];  // {vx, vy, m, rho}
   const double2 vp = make_double2(self.a, self.b);
@@ -1084,7 +1091,7 @@ k_tile_b_node(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays
   __syncthreads();
   const Rec4 *__restrict__ ssrc = tg.staged ? ssb : (const Rec4 *)R.SBs;
   double a11 = 0.0, a12 = 0.0, a21 = 0.0, a22 = 0.0, a31 = 0.0, a32 = 0.0;  // grad2_tmp(s,k)
-  walk_list<2>(L.code0, L.gx0, L.gy0, q, [&](unsigned cd, float gxf, float gyf) {
+  walk_list(sl, L.code0, L.gx0, L.gy0, q, [&](unsigned cd, float gxf, float gyf) {
     const double gx = (double)gxf, gy = (double)gyf;
     double q1, q2, q3, mq;
     if (cd < TILE_CODE_WALL) {  // type 1: stress particle {s1/rho^2, s2/rho^2, s3/rho^2, m}
@@ -1162,13 +1169,14 @@ k_tile_b_node(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays
 // artificial_viscosity, main:826-904 (fp32 locals and accumulators in list order) over the velocity-velocity list;
 // xij, yij are re-derived from the staged positions (the list path stored their fp32 roundings).
 // ------------------------------------------------------------------------------------------------------
-constexpr int TAV_CAP = 512;
-__global__ void __launch_bounds__(TS_T, TILE_MINB(TS_T))
+constexpr int TAV_CAP = 288;
+__global__ void __launch_bounds__(TN_T, TILE_MINB(TN_T))
 k_tile_av(DevParams P, SlotMap M, SortArrays S, TileLists L, TileRecs R, StatePtrs st,
           const TileGeom *__restrict__ geoms, float h_u) {
   __shared__ Rec4 sn_[TAV_CAP];
   __shared__ double2 sx[TAV_CAP];
-  const int kb0 = blockIdx.x * TS_T;
+  __shared__ ListSmem<2, TN_T, LG_NC> sl;
+  const int kb0 = blockIdx.x * TN_T;
   if (kb0 >= M.nn) return;
   const TileGeom tg = geoms[blockIdx.x];
   const int k0 = kb0 + threadIdx.x;
@@ -1177,6 +1185,7 @@ k_tile_av(DevParams P, SlotMap M, SortArrays S, TileLists L, TileRecs R, StatePt
   const int t = k0;
   const int id = S.order[0][k];
   const LaneList q = lane_listS(L, t, live, tg);
+  list_stage(sl, L.codeS, L.gxC, L.gyC, q);
   stage_rows_async(sn_, (const Rec4 *)R.NBs, tg);
   stage_rows_async(sx, S.pos[0], tg);
   const Rec4 self = R.NBs[k];
@@ -1188,7 +1197,7 @@ k_tile_av(DevParams P, SlotMap M, SortArrays S, TileLists L, TileRecs R, StatePt
   const Rec4 *__restrict__ nsrc = tg.staged ? sn_ : (const Rec4 *)R.NBs;
   const double2 *__restrict__ xsrc = tg.staged ? sx : S.pos[0];
   float acc1 = 0.f, acc2 = 0.f;
-  walk_list<2>(L.codeS, L.gxC, L.gyC, q, [&](unsigned cd, float gxf, float gyf) {
+  walk_list(sl, L.codeS, L.gxC, L.gyC, q, [&](unsigned cd, float gxf, float gyf) {
     const int j = code_index(q, cd);
     const Rec4 p = nsrc[j];
     const double2 pq = xsrc[j];
@@ -1225,6 +1234,7 @@ k_tile_move(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C, T
   const int sp = is_node ? SP_NODE : SP_STRESS;
   __shared__ double2 sv[TMV_CAP], sx[TMV_CAP];
   __shared__ double smo[TMV_CAP];
+  __shared__ ListSmem<0, TS_T, LG_SS> sl;
   const int bq = is_node ? blockIdx.x : blockIdx.x - nb_node;
   const int kb0 = bq * TS_T;
   const int nlive = is_node ? M.nn : M.ns;
@@ -1242,6 +1252,7 @@ k_tile_move(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C, T
   q.cnt = 0;
   if (xs) {
     q = lane_listS(L, t, live, tg);
+    list_stage(sl, L.codeS, nullptr, nullptr, q);
     if (tg.staged) {
       if (is_node) {
         for (int r = 0; r < 3; ++r)
@@ -1273,7 +1284,7 @@ k_tile_move(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C, T
     const double2 *__restrict__ xsrc = staged ? sx : S.pos[sp];
     const double *__restrict__ msrc = staged ? smo : C.mor[sp];
     const KernelConsts K = kernel_consts(P, S.h[sp][k]);
-    walk_list<0>(L.codeS, nullptr, nullptr, q, [&](unsigned cd, float, float) {
+    walk_list(sl, L.codeS, nullptr, nullptr, q, [&](unsigned cd, float, float) {
       const int j = code_index(q, cd);
       double2 vq;
       if (staged) {
