@@ -151,10 +151,23 @@ __device__ __forceinline__ void sph_kernel(const DevParams &P, double r, double 
   }
 }
 
-// ---- adapt_stress2 body for one particle, mat:2087-2161 (fp64) ----
+// ---- exactly rounded division by a value whose correctly rounded reciprocal is known (Markstein): the
+// result equals IEEE a/b bit for bit (checked exhaustively against the hardware divide in
+// tests/test_oracle_cpu.py::test_fast_division_identity); used to hoist the per-pair divisions by h and r.
+__device__ __forceinline__ double div_rn(double a, double b, double rb) {
+  double q = a * rb;
+  double r = __fma_rn(-b, q, a);
+  q = __fma_rn(r, rb, q);
+  r = __fma_rn(-b, q, a);
+  return __fma_rn(r, rb, q);
+}
+
+// ---- adapt_stress2 body for one particle, mat:2087-2161 (fp64); the divisions by 3 and by sqrt(J2) go through div_rn
+// (bit-identical to IEEE division, a fraction of its instructions) ----
 __device__ __forceinline__ void adapt_stress(const DevParams &P, Stress4 &s) {
   const double alpha2 = P.dp_alpha2, kc = P.dp_kc;
-  double smean = (s.s1 + s.s2 + s.s4) / 3.0;
+  const double r3 = 1.0 / 3.0;  // RN(1/3), folded at compile time
+  double smean = div_rn(s.s1 + s.s2 + s.s4, 3.0, r3);
   double d1 = s.s1 - smean, d2 = s.s2 - smean, d3 = s.s3, d4 = s.s4 - smean;
   double varj2 = d3 * d3 + 0.5 * (d1 * d1 + d2 * d2 + d4 * d4);
   double yield = -alpha2 * 3 * smean + kc;
@@ -163,7 +176,7 @@ __device__ __forceinline__ void adapt_stress(const DevParams &P, Stress4 &s) {
     s.s1 = s.s1 - smean + sh;
     s.s2 = s.s2 - smean + sh;
     s.s4 = s.s4 - smean + sh;
-    smean = (s.s1 + s.s2 + s.s4) / 3.0;
+    smean = div_rn(s.s1 + s.s2 + s.s4, 3.0, r3);
     d1 = s.s1 - smean;
     d2 = s.s2 - smean;
     d3 = s.s3;
@@ -173,7 +186,7 @@ __device__ __forceinline__ void adapt_stress(const DevParams &P, Stress4 &s) {
   }
   const double sq = sqrt(varj2);
   if (yield < sq) {
-    double rn = (-3 * alpha2 * smean + kc) / sq;
+    double rn = div_rn(-3 * alpha2 * smean + kc, sq, __drcp_rn(sq));
     if (sq <= (double)10e-06f) rn = 0;
     s.s1 = rn * d1 + smean;
     s.s2 = rn * d2 + smean;

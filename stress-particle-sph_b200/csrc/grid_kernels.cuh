@@ -404,17 +404,6 @@ __device__ __forceinline__ okey_t sorted_key(const SortArrays &S, int sq, int q)
   return make_key(cp[q], sq, op[q]);
 }
 
-// ---- exactly rounded division by a value whose correctly rounded reciprocal is known (Markstein): the
-// result equals IEEE a/b bit for bit (checked exhaustively against the hardware divide in
-// tests/test_oracle_cpu.py::test_fast_division_identity); used to hoist the per-pair divisions by h and r.
-__device__ __forceinline__ double div_rn(double a, double b, double rb) {
-  double q = a * rb;
-  double r = __fma_rn(-b, q, a);
-  q = __fma_rn(r, rb, q);
-  r = __fma_rn(-b, q, a);
-  return __fma_rn(r, rb, q);
-}
-
 struct KernelConsts {  // per-thread constants of `kernel` (main:1468-1492) for a fixed smoothing length h
   double h, rh, hh, rhh, factor, f6, m63;
 };

@@ -22,6 +22,8 @@
 // mat:1884-1954 (k_tile_b_*), artificial_viscosity main:826-904 (k_tile_av), XSPH_update main:189-239 and the
 // position update main:140-182 (k_tile_move).
 #pragma once
+#include <type_traits>
+
 #include "step_kernels.cuh"
 
 namespace spsph {
@@ -642,7 +644,19 @@ struct TileRecs {
 
 // groups of four entries staged per lane: cross-species list of a stress / velocity particle, velocity-velocity list,
 // same-species list in the position update (typical lengths in the Bui layout: 18, 36, 17, 35 entries)
-constexpr int LG_SP0 = 7, LG_N0 = 10, LG_NC = 7, LG_SS = 11;
+#ifndef SPSPH_LG_SP0
+#define SPSPH_LG_SP0 7
+#endif
+#ifndef SPSPH_LG_N0
+#define SPSPH_LG_N0 10
+#endif
+#ifndef SPSPH_LG_NC
+#define SPSPH_LG_NC 7
+#endif
+#ifndef SPSPH_LG_SS
+#define SPSPH_LG_SS 11
+#endif
+constexpr int LG_SP0 = SPSPH_LG_SP0, LG_N0 = SPSPH_LG_N0, LG_NC = SPSPH_LG_NC, LG_SS = SPSPH_LG_SS;  // 0: not staged
 #ifndef SPSPH_TILE_WARPS
 #define SPSPH_TILE_WARPS 16  // resident warps per SM requested from ptxas
 #endif
@@ -706,14 +720,15 @@ __device__ __forceinline__ int code_index(const LaneList &q, unsigned cd) {
 // longer list reads the rest from global memory.
 template <int NA, int T, int LG>
 struct ListSmem {
-  unsigned c[LG][T];
-  float4 x[NA > 0 ? LG : 1][T];
-  float4 y[NA > 1 ? LG : 1][T];
+  unsigned c[LG > 0 ? LG : 1][LG > 0 ? T : 1];
+  float4 x[(NA > 0 && LG > 0) ? LG : 1][(NA > 0 && LG > 0) ? T : 1];
+  float4 y[(NA > 1 && LG > 0) ? LG : 1][(NA > 1 && LG > 0) ? T : 1];
 };
 template <int NA, int T, int LG>
 __device__ __forceinline__ void list_stage(ListSmem<NA, T, LG> &sm, const unsigned *__restrict__ code,
                                            const float4 *__restrict__ a0, const float4 *__restrict__ a1,
                                            const LaneList &q) {
+  if (LG == 0) return;
   const int ng = min((q.cnt + 3) >> 2, LG);
   for (int g = 0; g < ng; ++g) {
     const size_t a = q.base + (size_t)g * 32;
@@ -722,28 +737,56 @@ __device__ __forceinline__ void list_stage(ListSmem<NA, T, LG> &sm, const unsign
     if (NA > 1) cp_async_16(&sm.y[g][threadIdx.x], a1 + a);
   }
 }
-// body(code, w0, w1) is called for every entry of this lane in traversal order
+// body(nowall, code, w0, w1) is called for every entry of this lane in traversal order. Full groups of a lane without
+// wall partners run as straight-line code (nowall = std::true_type: no branch per entry), so the four entries'
+// load / conversion / division chains interleave; ragged tails and lanes next to a wall take the guarded form.
+// LG = 0: nothing is staged, the groups are read from global memory two groups ahead.
 template <int NA, int T, int LG, class Body>
 __device__ __forceinline__ void walk_list(const ListSmem<NA, T, LG> &sm, const unsigned *__restrict__ code,
                                           const float4 *__restrict__ a0, const float4 *__restrict__ a1,
                                           const LaneList &q, Body body) {
   const int ng = (q.cnt + 3) >> 2;
+  if (ng == 0) return;
+  const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  unsigned c1 = 0u, c2 = 0u;
+  float4 x1 = z4, x2 = z4, y1 = z4, y2 = z4;
+  auto gload = [&](int g, unsigned &c, float4 &x, float4 &y) {
+    const size_t a = q.base + (size_t)g * 32;
+    c = ldcs1(code + a);
+    if (NA > 0) x = ldcs4(a0 + a);
+    if (NA > 1) y = ldcs4(a1 + a);
+  };
+  if (LG == 0) {
+    gload(0, c1, x1, y1);
+    if (ng > 1) gload(1, c2, x2, y2);
+  }
   for (int g = 0; g < ng; ++g) {
     unsigned c;
-    float4 x = make_float4(0.f, 0.f, 0.f, 0.f), y = x;
-    if (g < LG) {
+    float4 x = z4, y = z4;
+    if (LG == 0) {
+      c = c1;
+      x = x1;
+      y = y1;
+      c1 = c2;
+      x1 = x2;
+      y1 = y2;
+      if (g + 2 < ng) gload(g + 2, c2, x2, y2);
+    } else if (g < LG) {
       c = sm.c[g][threadIdx.x];
       if (NA > 0) x = sm.x[g][threadIdx.x];
       if (NA > 1) y = sm.y[g][threadIdx.x];
     } else {
-      const size_t a = q.base + (size_t)g * 32;
-      c = ldcs1(code + a);
-      if (NA > 0) x = ldcs4(a0 + a);
-      if (NA > 1) y = ldcs4(a1 + a);
+      gload(g, c, x, y);
     }
+    const int nv = q.cnt - g * 4;
+    if (nv >= 4 && !q.wallp) {
 #pragma unroll
-    for (int u = 0; u < 4; ++u)
-      if (g * 4 + u < q.cnt) body((c >> (8 * u)) & 0xffu, f4c(x, u), f4c(y, u));
+      for (int u = 0; u < 4; ++u) body(std::true_type{}, (c >> (8 * u)) & 0xffu, f4c(x, u), f4c(y, u));
+    } else {
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (u < nv) body(std::false_type{}, (c >> (8 * u)) & 0xffu, f4c(x, u), f4c(y, u));
+    }
   }
 }
 
@@ -801,8 +844,8 @@ k_tile_a_sp(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C, T
   const double2 *__restrict__ vsrc = staged ? sv : (const double2 *)R.NAs;
   const double *__restrict__ msrc = staged ? smo : C.mor[0];
   double vtx = 0.0, vty = 0.0;
-  walk_list(sl, L.code0, L.w0, nullptr, q, [&](unsigned cd, float w, float) {
-    if (cd >= TILE_CODE_WALL) return;  // wall partners (type 9) take no part
+  walk_list(sl, L.code0, L.w0, nullptr, q, [&](auto nowall, unsigned cd, float w, float) {
+    if (!decltype(nowall)::value && cd >= TILE_CODE_WALL) return;  // wall partners (type 9) take no part
     const int j = code_index(q, cd);
     double2 vq;
     if (FROMB && !staged) {
@@ -817,15 +860,16 @@ k_tile_a_sp(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C, T
   });
   if (!live) return;
   if (nrm != 0) {
-    v.x = vtx / nrm;
-    v.y = vty / nrm;
+    const double rn = __drcp_rn(nrm);
+    v.x = div_rn(vtx, nrm, rn);
+    v.y = div_rn(vty, nrm, rn);
   }
   if (do_adapt) adapt_stress(P, s);
   if (do_bc) apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, v, s);
   strec(st.SVb, ks, v.x, v.y, own_mor, 0.0);
   st4(st.SFb, ks, s);
-  const double r2 = own_rho * own_rho;
-  R.SBs[k] = Rec4{s.s1 / r2, s.s2 / r2, s.s3 / r2, own_m};
+  const double r2 = own_rho * own_rho, rr2 = __drcp_rn(r2);
+  R.SBs[k] = Rec4{div_rn(s.s1, r2, rr2), div_rn(s.s2, r2, rr2), div_rn(s.s3, r2, rr2), own_m};
   if (final_sweep) R.SVs[k] = v;
 }
 
@@ -880,8 +924,8 @@ k_tile_a_node(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C,
   const Rec4 *__restrict__ ssrc = staged ? ss : (const Rec4 *)R.SAs;
   const double *__restrict__ msrc = staged ? smo : C.mor[1];
   double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, te = 0.0;
-  walk_list(sl, L.code0, L.w0, nullptr, q, [&](unsigned cd, float w, float) {
-    if (cd >= TILE_CODE_WALL) return;  // wall partners (type 6) take no part
+  walk_list(sl, L.code0, L.w0, nullptr, q, [&](auto nowall, unsigned cd, float w, float) {
+    if (!decltype(nowall)::value && cd >= TILE_CODE_WALL) return;  // wall partners (type 6) take no part
     const int j = code_index(q, cd);
     Rec4 p;
     double ep = 0.0;
@@ -902,11 +946,12 @@ k_tile_a_node(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C,
   });
   if (!live) return;
   if (nrm != 0) {
-    s.s1 = t1 / nrm;
-    s.s2 = t2 / nrm;
-    s.s3 = t3 / nrm;
-    s.s4 = t4 / nrm;
-    if (EPSP) st.epsp[id] = te / nrm;
+    const double rn = __drcp_rn(nrm);
+    s.s1 = div_rn(t1, nrm, rn);
+    s.s2 = div_rn(t2, nrm, rn);
+    s.s3 = div_rn(t3, nrm, rn);
+    s.s4 = div_rn(t4, nrm, rn);
+    if (EPSP) st.epsp[id] = div_rn(te, nrm, rn);
   } else {
     v.x = 0;
     v.y = 0;
@@ -949,15 +994,20 @@ k_tile_b_sp(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
   if (q.wallp) lane_rows(G, S.cell[1][k], S.start[2], jW);
   WalkWall ww;
   ww.start(rev != 0);
+  // operands of the stage epilogue: requested now, consumed after the pair sum
+  double ep_ = st.epsp[id], fd_ = st.fdp[id];
+  const double rke0 = st.RKe[ks];
+  Stress4 rk = ld4(st.RKs, ks);
+  const Stress4 s0 = ld4(st.stress0, ks);
   cp_async_wait_all();
   __syncthreads();
   const bool staged = tg.staged != 0;
   const Rec4 *__restrict__ nsrc = staged ? sn_ : (const Rec4 *)R.NBs;
   const double *__restrict__ rsrc = staged ? srr : C.rrho[0];
   double g11 = 0.0, g12 = 0.0, g21 = 0.0, g22 = 0.0;  // grad1_tmp(d,k): d velocity component, k direction
-  walk_list(sl, L.code0, L.gx0, L.gy0, q, [&](unsigned cd, float gxf, float gyf) {
+  walk_list(sl, L.code0, L.gx0, L.gy0, q, [&](auto nowall, unsigned cd, float gxf, float gyf) {
     const double gx = (double)gxf, gy = (double)gyf;
-    if (cd < TILE_CODE_WALL) {  // type 1: velocity particle {vx, vy, m, rho}
+    if (decltype(nowall)::value || cd < TILE_CODE_WALL) {  // type 1: velocity particle {vx, vy, m, rho}
       const int j = code_index(q, cd);
       const Rec4 p = nsrc[j];
       const double rr = rsrc[j];
@@ -1012,8 +1062,9 @@ k_tile_b_sp(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
   const double d4 = -(P.D41 * g11 + P.D42 * g22);
   // plastic_terms, mat:1884-1954
   double Gs[4] = {0.0, 0.0, 0.0, 0.0}, der1 = 0.0;
-  plastic_terms(P, sp_, g11, g12, g21, g22, st.epsp + id, st.fdp + id, Gs, der1);
-  const double rke = st.RKe[ks] + der1 * f2;
+  plastic_terms(P, sp_, g11, g12, g21, g22, &ep_, &fd_, Gs, der1);
+  if (P.ncrit == 12) st.fdp[id] = fd_;  // f_drucker is read and rewritten by drucker_prager only
+  const double rke = rke0 + der1 * f2;
   // Jaumann terms, main:751-757
   double sp1 = 0.0, sp2 = 0.0, sp3 = 0.0, sp4 = 0.0;
   if (P.update_x) {
@@ -1026,12 +1077,10 @@ k_tile_b_sp(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
   const double r2 = -d2 + sp2 + Gs[1];
   const double r3 = -d3 + sp3 + Gs[2];
   const double r4 = -d4 + sp4 + Gs[3];
-  Stress4 rk = ld4(st.RKs, ks);
   rk.s1 = rk.s1 + f2 * r1;
   rk.s2 = rk.s2 + f2 * r2;
   rk.s3 = rk.s3 + f2 * r3;
   rk.s4 = rk.s4 + f2 * r4;
-  const Stress4 s0 = ld4(st.stress0, ks);
   Stress4 sn;
   if (!last) {
     st4(st.RKs, ks, rk);
@@ -1046,7 +1095,7 @@ k_tile_b_sp(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
     sn.s3 = s0.s3 + (P.dt / 6) * rk.s3;
     sn.s4 = s0.s4 + (P.dt / 6) * rk.s4;
     // update_strain, mat:1864-1880 with Ddev_strn = RK_dev_strain/6 (main:799)
-    st.epsp[id] = st.epsp[id] + P.dt * (rke / 6);
+    st.epsp[id] = ep_ + P.dt * (rke / 6);
   }
   if (P.adapt) adapt_stress(P, sn);
   double2 vn = vp;
@@ -1085,16 +1134,26 @@ k_tile_b_node(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays
   if (q.wallp) lane_rows(G, S.cell[0][k], S.start[2], jW);
   WalkWall ww;
   ww.start(rev != 0);
-  const double r2p = rp * rp;
-  const double so1 = sp_.s1 / r2p, so2 = sp_.s2 / r2p, so3 = sp_.s3 / r2p;  // stress(1:3,i)/rho(i)**2
+  const double r2p = rp * rp, rr2p = __drcp_rn(r2p);
+  const double so1 = div_rn(sp_.s1, r2p, rr2p), so2 = div_rn(sp_.s2, r2p, rr2p),
+               so3 = div_rn(sp_.s3, r2p, rr2p);  // stress(1:3,i)/rho(i)**2
+  // operands of the stage epilogue: requested now, consumed after the pair sum
+  double2 avp = make_double2(0.0, 0.0), fb = make_double2(0.0, 0.0), af = make_double2(0.0, 0.0);
+  if (P.alpha > 0 || P.beta > 0) avp = ld2(st.av, id);  // artificial viscosity of this stage (k_tile_av)
+  if (extra_forces) {
+    fb = ld2(st.fbound, id);  // f_bound (main:764): zero unless boundary_forces ran
+    af = ld2(st.aforce, id);  // art_force: zero unless art_stress = T
+  }
+  double2 rk = ld2(st.RKv, id);
+  const double2 v0 = ld2(st.vel0, id);
   cp_async_wait_all();
   __syncthreads();
   const Rec4 *__restrict__ ssrc = tg.staged ? ssb : (const Rec4 *)R.SBs;
   double a11 = 0.0, a12 = 0.0, a21 = 0.0, a22 = 0.0, a31 = 0.0, a32 = 0.0;  // grad2_tmp(s,k)
-  walk_list(sl, L.code0, L.gx0, L.gy0, q, [&](unsigned cd, float gxf, float gyf) {
+  walk_list(sl, L.code0, L.gx0, L.gy0, q, [&](auto nowall, unsigned cd, float gxf, float gyf) {
     const double gx = (double)gxf, gy = (double)gyf;
     double q1, q2, q3, mq;
-    if (cd < TILE_CODE_WALL) {  // type 1: stress particle {s1/rho^2, s2/rho^2, s3/rho^2, m}
+    if (decltype(nowall)::value || cd < TILE_CODE_WALL) {  // type 1: stress particle {s1/rho^2, s2/rho^2, s3/rho^2, m}
       const Rec4 p = ssrc[code_index(q, cd)];
       q1 = p.a;
       q2 = p.b;
@@ -1131,24 +1190,11 @@ k_tile_b_node(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays
   // gravity_force, mat:2809-2871
   const double sg1 = P.grav[0] - P.damping * vp.x;
   const double sg2 = P.grav[1] - P.damping * vp.y;
-  // artificial viscosity of this stage (k_tile_av), zero when alpha = beta = 0 (art_visc stays 0, main:688)
-  double av1 = 0.0, av2 = 0.0;
-  if (P.alpha > 0 || P.beta > 0) {
-    const double2 a = ld2(st.av, id);
-    av1 = a.x;
-    av2 = a.y;
-  }
-  double2 fb = make_double2(0.0, 0.0), af = make_double2(0.0, 0.0);
-  if (extra_forces) {
-    fb = ld2(st.fbound, id);  // f_bound (main:764): zero unless boundary_forces ran
-    af = ld2(st.aforce, id);  // art_force: zero unless art_stress = T
-  }
-  const double r1 = -dv1 + sg1 + av1 + fb.x + af.x;
-  const double r2 = -dv2 + sg2 + av2 + fb.y + af.y;
-  double2 rk = ld2(st.RKv, id);
+  // artificial viscosity of this stage is zero when alpha = beta = 0 (art_visc stays 0, main:688)
+  const double r1 = -dv1 + sg1 + avp.x + fb.x + af.x;
+  const double r2 = -dv2 + sg2 + avp.y + fb.y + af.y;
   rk.x = rk.x + f2 * r1;
   rk.y = rk.y + f2 * r2;
-  const double2 v0 = ld2(st.vel0, id);
   double2 vn;
   if (!last) {
     st2(st.RKv, id, rk);
@@ -1197,7 +1243,7 @@ k_tile_av(DevParams P, SlotMap M, SortArrays S, TileLists L, TileRecs R, StatePt
   const Rec4 *__restrict__ nsrc = tg.staged ? sn_ : (const Rec4 *)R.NBs;
   const double2 *__restrict__ xsrc = tg.staged ? sx : S.pos[0];
   float acc1 = 0.f, acc2 = 0.f;
-  walk_list(sl, L.codeS, L.gxC, L.gyC, q, [&](unsigned cd, float gxf, float gyf) {
+  walk_list(sl, L.codeS, L.gxC, L.gyC, q, [&](auto, unsigned cd, float gxf, float gyf) {
     const int j = code_index(q, cd);
     const Rec4 p = nsrc[j];
     const double2 pq = xsrc[j];
@@ -1284,7 +1330,7 @@ k_tile_move(DevParams P, SlotMap M, SortArrays S, TileLists L, SortedConsts C, T
     const double2 *__restrict__ xsrc = staged ? sx : S.pos[sp];
     const double *__restrict__ msrc = staged ? smo : C.mor[sp];
     const KernelConsts K = kernel_consts(P, S.h[sp][k]);
-    walk_list(sl, L.codeS, nullptr, nullptr, q, [&](unsigned cd, float, float) {
+    walk_list(sl, L.codeS, nullptr, nullptr, q, [&](auto, unsigned cd, float, float) {
       const int j = code_index(q, cd);
       double2 vq;
       if (staged) {

@@ -9,18 +9,13 @@
 cd "$(dirname "$0")/.."
 vdir=stress-particle-sph_b200/variants
 VARIANTS=(
-  "base:"
-  "t64:-DSPSPH_SWEEP_T=64 -DSPSPH_MINB=8"      # same 16 warps per SM, finer tail
-  "t32:-DSPSPH_SWEEP_T=32 -DSPSPH_MINB=16"     # one warp per block
-  "t64m10:-DSPSPH_SWEEP_T=64 -DSPSPH_MINB=10"  # 20 warps per SM, 102 registers (spills: see the ptxas log)
-  "sub2:-DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2"     # two entries in flight per thread instead of four (80-120 registers)
-  "pipe2:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2"  # software-pipelined gathers: 2 consumed + 2 in flight
-  "pipe2t64:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_SWEEP_T=64 -DSPSPH_MINB=8"
-  "pipe2a4:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2"   # sweep A (little arithmetic per entry) with 4 consumed + 4 in flight
-  "sub2m5:-DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_MINB=5"   # 20 warps per SM at 96 registers, 0-28 B of spills
-  "sub2m6:-DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_MINB=6"   # 24 warps per SM at 80 registers, 16-124 B of spills
-  "pipe2m5:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_MINB=5"  # same, pipelined (32-80 B of spills in sweep B)
-  "pipe2ng6:-DSPSPH_ELL_PIPE=1 -DSPSPH_ELL_SUB=2 -DSPSPH_A_SUB=2 -DSPSPH_A_NG=6"
+  "base:"                                               # every list staged in shared memory (LG_SP0=7 LG_N0=10 LG_NC=7 LG_SS=11)
+  "n0reg:-DSPSPH_LG_N0=0"                               # velocity-particle side of sweeps A / B: lists read two groups ahead into registers
+  "n0ncreg:-DSPSPH_LG_N0=0 -DSPSPH_LG_NC=0"             # ... and the artificial-viscosity list
+  "allreg:-DSPSPH_LG_N0=0 -DSPSPH_LG_NC=0 -DSPSPH_LG_SP0=0 -DSPSPH_LG_SS=0"  # nothing staged but the partner tiles
+  "w20:-DSPSPH_TILE_WARPS=20"                           # 20 resident warps per SM requested (102 registers)
+  "w24:-DSPSPH_TILE_WARPS=24 -DSPSPH_LG_N0=0 -DSPSPH_LG_NC=0"  # 24 warps (80 registers)
+  "list:"                                               # same library as base, run with SPSPH_TILE=0: the id-list path
 )
 build_one() {
   local name=$1 flags=$2
@@ -46,9 +41,12 @@ for v in "${VARIANTS[@]}"; do
   name=${v%%:*}
   so=$PWD/$vdir/libspsph_cuda_$name.so
   [ -f $so ] || continue
+  [ $name = list ] && export SPSPH_TILE=0
   SPSPH_CUDA_SO=$so timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $out/parity_$name.log 2>&1
   echo "$name parity exit $?" | tee -a $out/summary.txt
   SPSPH_CUDA_SO=$so timeout 600 python tools/run_steps.py --deck /tmp/spsph_variant_deck --warmup 3 --steps 10 --profile > $out/profile_$name.log 2>&1
   head -1 $out/profile_$name.log | tee -a $out/summary.txt
+  grep -E "k_sweep_a|k_sweep_b|k_move|k_tile_build" $out/profile_$name.log | awk '{printf "    %s %s", $1, $2} END {print ""}' | tee -a $out/summary.txt
+  unset SPSPH_TILE
 done
 cat $out/summary.txt
