@@ -131,6 +131,18 @@ int spsph_dist_unique_id(char *id128);
 int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *id128, const double *planes,
                     int32_t halo_cells, int32_t halo_capacity);
 int spsph_dist_flags(spsph_handle *h, int32_t *flags);
+/* Row-wise transfer of the TIME-VARYING state (a slab rank moves its slab + halo only instead of the whole problem).
+ * ids: n ascending 0-based particle numbers. Every non-NULL array of `s` holds the rows of those particles in that
+ * order, with the row width of the full array: x 2, vel 2, stress 4, if_out_domain 1 (n rows); internal_vars 10,
+ * f_drucker 1, bc_or_not 1 (rows of the ids below ntotal); displ 2, x_10 2, disp_10 1, n_int 1, bc_int 1 (rows of the
+ * ids below nnode). The set-up arrays (mass, rho, hsml, itype, wall data, bc_info, x00) are not touched: they come
+ * from the spsph_upload that started the run. spsph_upload_rows resets the pair-list length like spsph_upload; in a
+ * multi-GPU run the uploaded rows become this rank's local particles (owned where their key position lies in the
+ * slab, ghost inside the halo distance) and every other particle is remote, so ids must cover slab + halo
+ * (spsph.dist.local_ids). The driver-side counterpart: each rank reads / writes only its own rows of the Fortran
+ * arrays (1_SPH_2018.f90:132,156). */
+int spsph_upload_rows(spsph_handle *h, const spsph_state *s, const int32_t *ids, int32_t n);
+int spsph_download_rows(spsph_handle *h, const spsph_state *s, const int32_t *ids, int32_t n);
 /* particles per species (velocity, stress, wall) this rank processed in the last step: its slab + halo */
 int spsph_local_counts(spsph_handle *h, int32_t *nloc3);
 /* checkpoint support (the reference has none: SURVEY section 5). Everything a restart needs is in spsph_state except

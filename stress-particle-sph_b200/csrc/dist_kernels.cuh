@@ -51,6 +51,21 @@ __global__ void k_dist_init_flags(DevParams P, DistGeom D, const double *__restr
   lflag[i] = f;
 }
 
+// flags after a row-wise upload (spsph_upload_rows): only the uploaded rows can be local
+__global__ void k_dist_flags_rows(DevParams P, DistGeom D, const double *__restrict__ x, const int *__restrict__ ids, int n,
+                                  int *__restrict__ lflag) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int i = ids[k];
+  const double xk = key_x(P, D, x, i), xi = x[2 * (size_t)i];
+  int f = LF_REMOTE;
+  if (xk >= D.lo && xk < D.hi)
+    f = LF_OWNED;
+  else if (xi >= D.lo - D.H && xi < D.hi + D.H)
+    f = LF_GHOST;
+  lflag[i] = f;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // The local list: particle numbers with lflag != LF_REMOTE, in no particular order (every consumer is
 // order-independent: min/max, per-cell counts, the deterministic in-cell ranking of k_rank). Built once from the

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <type_traits>
 #include <vector>
 
 #include <dlfcn.h>
@@ -144,7 +145,7 @@ struct spsph_handle {
   // ---- cell-tile path (tile_kernels.cuh): acceptance masks + fp32 weights instead of partner-id lists ----
   bool tile_cfg = false;    // the option combination is covered by the tile kernels (decided at upload)
   bool tile_off = false;    // a stencil row outgrew the 64-bit masks: list path until the next upload
-  bool tile_env = true;     // SPSPH_TILE=0 forces the list path (tests compare the two)
+  bool tile_env = false;    // SPSPH_TILE=1 selects the cell-tile path where the options allow it (default: id lists)
   bool tile_last = false;   // the last step ran on the tile path (the id lists are materialised on demand)
   int tile_last_mode = 0;   // its traversal order: 0 forward, 1 reversed
   TileLists TL{};
@@ -158,6 +159,11 @@ struct spsph_handle {
   long long tile_s_cap = 0;
   TileStatus *tstat_d = nullptr, *tstat_h = nullptr;
   long long tile_steps = 0, list_steps = 0;  // which path the steps took (spsph_path_counts)
+
+  // row-wise transfers (spsph_upload_rows / spsph_download_rows): device copy of the row ids + one staging buffer
+  int *rows_ids = nullptr;
+  char *rows_buf = nullptr;
+  size_t rows_cap = 0;
 
   long long m_pairs = 0;       // max pair count of all previous steps (main:1210)
   long long last_n_pairs = 0;  // of the last step
@@ -233,6 +239,72 @@ __global__ void k_upload_derive(int n2, int nt, const double *__restrict__ mass,
 __global__ void k_download_ivars(int nt, const double *__restrict__ epsp, double *__restrict__ ivars) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i < nt) ivars[(size_t)SPSPH_NINT_VARS * i] = epsp[i];
+}
+
+
+// ---- row-wise transfers: rows k = 0..n-1 of a compact array <-> particle ids[k] of the device arrays ----
+template <class T>
+__global__ void k_rows_scatter(int n, int width, const int *__restrict__ ids, int id_base, const T *__restrict__ src,
+                               T *__restrict__ dst) {
+  const long long m = (long long)n * width;
+  for (long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x; a < m; a += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(a / width), c = (int)(a - (long long)k * width);
+    dst[(size_t)(ids[k] - id_base) * width + c] = src[a];
+  }
+}
+template <class T>
+__global__ void k_rows_gather(int n, int width, const int *__restrict__ ids, int id_base, const T *__restrict__ src,
+                              T *__restrict__ dst) {
+  const long long m = (long long)n * width;
+  for (long long a = blockIdx.x * (long long)blockDim.x + threadIdx.x; a < m; a += (long long)gridDim.x * blockDim.x) {
+    const int k = (int)(a / width), c = (int)(a - (long long)k * width);
+    dst[a] = src[(size_t)(ids[k] - id_base) * width + c];
+  }
+}
+// compact reference-layout vel (2, n) / stress (4, n) rows -> state between steps (format B), and back
+__global__ void k_rows_pack(DevParams P, int n, const int *__restrict__ ids, const double *__restrict__ vel,
+                            const double *__restrict__ stress, StatePtrs st) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int id = ids[k];
+  if (id >= P.ntotal) return;
+  const double2 v = ld2(vel, k);
+  const Stress4 s = ld4(stress, k);
+  if (id < P.nnode) {
+    strec(st.NB, id, v.x, v.y, st.mass[id], st.rho[id]);
+    st4(st.NSb, id, s);
+  } else {
+    const int ks = id - P.nnode;
+    const double r = st.rho[id];
+    const double r2 = r * r;
+    strec(st.SB, ks, s.s1 / r2, s.s2 / r2, s.s3 / r2, st.mass[id]);
+    st4(st.SFb, ks, s);
+    strec(st.SVb, ks, v.x, v.y, st.mor[id], 0.0);
+  }
+}
+__global__ void k_rows_unpack(DevParams P, int n, const int *__restrict__ ids, StatePtrs st, double *__restrict__ vel,
+                              double *__restrict__ stress) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n) return;
+  const int id = ids[k];
+  double2 v = make_double2(0.0, 0.0);
+  Stress4 s{0.0, 0.0, 0.0, 0.0};  // wall particles carry no velocity / stress on the device
+  if (id < P.nnode) {
+    const Rec4 r = ldrec(st.NB, id);
+    v = make_double2(r.a, r.b);
+    s = ld4(st.NSb, id);
+  } else if (id < P.ntotal) {
+    const Rec4 r = ldrec(st.SVb, id - P.nnode);
+    v = make_double2(r.a, r.b);
+    s = ld4(st.SFb, id - P.nnode);
+  }
+  if (vel) st2(vel, k, v);
+  if (stress) st4(stress, k, s);
+}
+__global__ void k_rows_epsp(int n, const int *__restrict__ ids, int ntotal, const double *__restrict__ ivars,
+                            double *__restrict__ epsp) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n && ids[k] < ntotal) epsp[ids[k]] = ivars[(size_t)SPSPH_NINT_VARS * ids[k]];
 }
 
 template <class T>
@@ -402,50 +474,45 @@ void step_scalars(spsph_handle *h, int itimestep, double time_sph, double dt) {
   }
 }
 
+// (re)allocation of one 4-byte list array: on failure the old buffer is gone, the pointer is null and the caller
+// zeroes the capacity, so that nothing can write through a stale pointer or free it twice
+template <class T>
+static cudaError_t realloc4(T **p, long long n, bool wanted = true) {
+  cudaFree(*p);
+  *p = nullptr;
+  if (!wanted) return cudaSuccess;
+  return cudaMalloc((void **)p, (size_t)n * 4);
+}
 int ensure_lists(spsph_handle *h, long long t0, long long tC, long long tD) {
   // 1024 entries of slack: the sweeps stream whole groups of rows and may read (never use) up to 7 rows past a slice
-  auto grow = [&](long long need, long long &cap) {
-    return need + 1024 > cap ? (cap = need + need / 8 + 2048, true) : false;
-  };
-  if (grow(t0, h->cap0)) {
-    cudaFree(h->L.idx0);
-    cudaFree(h->L.w0);
-    cudaFree(h->L.gx0);
-    cudaFree(h->L.gy0);
-    cudaFree(h->L.h0lo);
-    cudaFree(h->L.h0hi);
-    h->L.h0lo = h->L.h0hi = nullptr;
-    if (!h->umor) {  // (m/rho)_partner * w is only stored when it is not a per-species constant times w
-      CUDA_TRY(cudaMalloc((void **)&h->L.h0lo, (size_t)h->cap0 * 4));
-      CUDA_TRY(cudaMalloc((void **)&h->L.h0hi, (size_t)h->cap0 * 4));
-    }
-    CUDA_TRY(cudaMalloc((void **)&h->L.idx0, (size_t)h->cap0 * 4));
-    CUDA_TRY(cudaMalloc((void **)&h->L.w0, (size_t)h->cap0 * 4));
-    CUDA_TRY(cudaMalloc((void **)&h->L.gx0, (size_t)h->cap0 * 4));
-    CUDA_TRY(cudaMalloc((void **)&h->L.gy0, (size_t)h->cap0 * 4));
+  auto need_cap = [](long long need, long long cap) { return need + 1024 > cap ? need + need / 8 + 2048 : 0ll; };
+  if (const long long c = need_cap(t0, h->cap0)) {
+    h->cap0 = 0;
+    // (m/rho)_partner * w is only stored when it is not a per-species constant times w
+    CUDA_TRY(realloc4(&h->L.h0lo, c, !h->umor));
+    CUDA_TRY(realloc4(&h->L.h0hi, c, !h->umor));
+    CUDA_TRY(realloc4(&h->L.idx0, c));
+    CUDA_TRY(realloc4(&h->L.w0, c));
+    CUDA_TRY(realloc4(&h->L.gx0, c));
+    CUDA_TRY(realloc4(&h->L.gy0, c));
+    h->cap0 = c;
   }
-  if (grow(tC, h->capC)) {
-    cudaFree(h->L.idxC);
-    cudaFree(h->L.wC);
-    cudaFree(h->L.gxC);
-    cudaFree(h->L.gyC);
-    cudaFree(h->L.xC);
-    cudaFree(h->L.yC);
-    cudaFree(h->L.hC);
-    CUDA_TRY(cudaMalloc((void **)&h->L.xC, (size_t)h->capC * 4));
-    CUDA_TRY(cudaMalloc((void **)&h->L.yC, (size_t)h->capC * 4));
-    h->L.hC = nullptr;
-    if (!h->uniform_h) CUDA_TRY(cudaMalloc((void **)&h->L.hC, (size_t)h->capC * 4));  // else a constant
-    CUDA_TRY(cudaMalloc((void **)&h->L.idxC, (size_t)h->capC * 4));
-    CUDA_TRY(cudaMalloc((void **)&h->L.wC, (size_t)h->capC * 4));
-    CUDA_TRY(cudaMalloc((void **)&h->L.gxC, (size_t)h->capC * 4));
-    CUDA_TRY(cudaMalloc((void **)&h->L.gyC, (size_t)h->capC * 4));
+  if (const long long c = need_cap(tC, h->capC)) {
+    h->capC = 0;
+    CUDA_TRY(realloc4(&h->L.xC, c));
+    CUDA_TRY(realloc4(&h->L.yC, c));
+    CUDA_TRY(realloc4(&h->L.hC, c, !h->uniform_h));  // else a constant
+    CUDA_TRY(realloc4(&h->L.idxC, c));
+    CUDA_TRY(realloc4(&h->L.wC, c));
+    CUDA_TRY(realloc4(&h->L.gxC, c));
+    CUDA_TRY(realloc4(&h->L.gyC, c));
+    h->capC = c;
   }
-  if (grow(tD, h->capD)) {
-    cudaFree(h->L.idxD);
-    cudaFree(h->L.wD);
-    CUDA_TRY(cudaMalloc((void **)&h->L.idxD, (size_t)h->capD * 4));
-    CUDA_TRY(cudaMalloc((void **)&h->L.wD, (size_t)h->capD * 4));
+  if (const long long c = need_cap(tD, h->capD)) {
+    h->capD = 0;
+    CUDA_TRY(realloc4(&h->L.idxD, c));
+    CUDA_TRY(realloc4(&h->L.wD, c));
+    h->capD = c;
   }
   return 0;
 }
@@ -1388,6 +1455,14 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   if (!p->inside_approach && p->nstress != p->nnode * p->npoints) return fail("nstress != npoints*nnode");
   if (!p->sp_sph && (p->nstress != p->nnode || p->sph_shift)) return fail("standard SPH needs nstress == nnode");
   if (p->ndummy2 < 0 || p->ndummy2 > p->ndummy) return fail("ndummy2 out of range");
+  if (p->no_bcs < 0) return fail("no_bcs must not be negative");
+  if (p->ntcurves < 0 || p->ntcurves > SPSPH_MAX_TCURVES) return fail("ntcurves exceeds SPSPH_MAX_TCURVES");
+  for (int k = 0; k < p->ntcurves; ++k)
+    if (p->nptstcurves[k] < 0 || p->nptstcurves[k] > SPSPH_MAX_TCURVE_PTS)
+      return fail("a time curve has more points than SPSPH_MAX_TCURVE_PTS");
+  if (p->npoints < 1 || p->npoints > 3) return fail("npoints must be 1, 2 or 3");
+  if (p->vel_vector && p->sp_sph && !p->inside_approach && p->npoints != 2)
+    return fail("vel_vector re-seating needs two stress particles per velocity particle (main:284-293)");
 
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -1726,6 +1801,153 @@ int spsph_emu_set_lists(spsph_handle *h, const spsph_emu_lists *lists) {
 }
 #endif
 
+// ---- row-wise transfers of the time-varying state ----
+static int rows_prepare(spsph_handle *h, const int32_t *ids, int32_t n, int *n_node, int *n_part) {
+  const spsph_params &p = h->hp;
+  if (!h->uploaded) {
+    h->err = "row-wise transfers need a complete spsph_upload first (it carries the set-up arrays)";
+    return 1;
+  }
+  if (n < 0 || (n > 0 && !ids)) {
+    h->err = "row-wise transfer: bad id list";
+    return 1;
+  }
+  int nn = 0, nt = 0;
+  for (int k = 0; k < n; ++k) {
+    if (ids[k] < 0 || ids[k] >= p.ntotal2 || (k > 0 && ids[k] <= ids[k - 1])) {
+      h->err = "row-wise transfer: ids must be ascending particle numbers in [0, ntotal2)";
+      return 1;
+    }
+    nn += ids[k] < p.nnode;
+    nt += ids[k] < p.ntotal;
+  }
+  *n_node = nn;
+  *n_part = nt;
+  const size_t need = (size_t)(n > 0 ? n : 1) * 256;  // every array of a row set at once (< 200 bytes per row)
+  if (need > h->rows_cap) {
+    cudaFree(h->rows_buf);
+    cudaFree(h->rows_ids);
+    h->rows_buf = nullptr;
+    h->rows_ids = nullptr;
+    h->rows_cap = 0;
+    CUDA_TRY(cudaMalloc((void **)&h->rows_buf, need + need / 8));
+    CUDA_TRY(cudaMalloc((void **)&h->rows_ids, ((size_t)n + n / 8 + 16) * sizeof(int)));
+    h->rows_cap = need + need / 8;
+  }
+  CUDA_TRY(cudaMemcpyAsync(h->rows_ids, ids, (size_t)n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
+  return 0;
+}
+
+int spsph_upload_rows(spsph_handle *h, const spsph_state *s, const int32_t *ids, int32_t n) {
+  if (!h || !s) return 1;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int nn = 0, nt = 0;
+  if (rows_prepare(h, ids, n, &nn, &nt)) return 1;
+  const spsph_params &p = h->hp;
+  if (!s->x || !s->vel || !s->stress) {
+    h->err = "spsph_upload_rows: x, vel and stress rows are required";
+    return 1;
+  }
+  cudaStream_t st = h->stream;
+  char *buf = h->rows_buf;
+  const int G = 148 * 8;
+  size_t off = 0;
+  auto put = [&](auto *dst, const auto *src, int rows, int width, int id_base) -> int {
+    using T = std::remove_cv_t<std::remove_pointer_t<decltype(src)>>;
+    if (!src || rows == 0) return 0;
+    const size_t bytes = (size_t)rows * width * sizeof(T);
+    T *d = reinterpret_cast<T *>(buf + off);
+    off += (bytes + 255) & ~(size_t)255;
+    CUDA_TRY(cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st));
+    k_rows_scatter<T><<<G, 256, 0, st>>>(rows, width, h->rows_ids, id_base, d, dst);
+    return 0;
+  };
+  if (put(h->x, (const double *)s->x, n, 2, 0)) return 1;
+  {  // vel / stress: compact rows -> format B
+    double *dv = reinterpret_cast<double *>(buf + off);
+    off += ((size_t)n * 2 * 8 + 255) & ~(size_t)255;
+    double *ds = reinterpret_cast<double *>(buf + off);
+    off += ((size_t)n * 4 * 8 + 255) & ~(size_t)255;
+    CUDA_TRY(cudaMemcpyAsync(dv, s->vel, (size_t)n * 2 * 8, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(ds, s->stress, (size_t)n * 4 * 8, cudaMemcpyHostToDevice, st));
+    h->cur = h->cur;  // rows go into the current format-B buffer set
+    if (n > 0) k_rows_pack<<<(n + 255) / 256, 256, 0, st>>>(h->P, n, h->rows_ids, dv, ds, state_ptrs(h, h->cur));
+  }
+  if (s->internal_vars && nt > 0) {
+    if (put(h->ivars, (const double *)s->internal_vars, nt, SPSPH_NINT_VARS, 0)) return 1;
+    k_rows_epsp<<<(nt + 255) / 256, 256, 0, st>>>(nt, h->rows_ids, p.ntotal, h->ivars, h->epsp);
+  }
+  if (put(h->fdp, (const double *)s->f_drucker, nt, 1, 0)) return 1;
+  if (put(h->displ, (const double *)s->displ, nn, 2, 0)) return 1;
+  if (put(h->x_10, (const double *)s->x_10, nn, 2, 0)) return 1;
+  if (put(h->disp_10, (const double *)s->disp_10, nn, 1, 0)) return 1;
+  if (put(h->n_int, (const float *)s->n_int, nn, 1, 0)) return 1;
+  if (put(h->bc_int, (const int *)s->bc_int, nn, 1, 0)) return 1;
+  if (put(h->if_out, (const int *)s->if_out_domain, n, 1, 0)) return 1;
+  if (put(h->bc_or_not, (const int *)s->bc_or_not, nt, 1, 0)) return 1;
+  CUDA_TRY(cudaGetLastError());
+  h->m_pairs = 0;
+  h->have_lists = false;
+  h->tile_last = false;
+  h->x_fs_valid = false;
+#ifndef SPSPH_HOST_EMU
+  if (h->dist) {  // the uploaded rows are this rank's local particles; everything else is remote
+    CUDA_TRY(cudaMemsetAsync(h->lflag, 0, (size_t)p.ntotal2 * sizeof(int), st));
+    if (n > 0) k_dist_flags_rows<<<(n + 255) / 256, 256, 0, st>>>(h->P, h->D, h->x, h->rows_ids, n, h->lflag);
+    if (rebuild_local_list(h)) return 1;
+  }
+#endif
+  CUDA_TRY(cudaStreamSynchronize(st));  // the caller may reuse its arrays as soon as the call returns
+  return 0;
+}
+
+int spsph_download_rows(spsph_handle *h, const spsph_state *s, const int32_t *ids, int32_t n) {
+  if (!h || !s) return 1;
+  CUDA_TRY(cudaSetDevice(h->device));
+  int nn = 0, nt = 0;
+  if (rows_prepare(h, ids, n, &nn, &nt)) return 1;
+  cudaStream_t st = h->stream;
+  char *buf = h->rows_buf;
+  const int G = 148 * 8;
+  size_t off = 0;
+  auto get = [&](auto *dst, const auto *src, int rows, int width) -> int {
+    using T = std::remove_cv_t<std::remove_pointer_t<decltype(src)>>;
+    if (!dst || rows == 0) return 0;
+    const size_t bytes = (size_t)rows * width * sizeof(T);
+    T *d = reinterpret_cast<T *>(buf + off);
+    off += (bytes + 255) & ~(size_t)255;
+    k_rows_gather<T><<<G, 256, 0, st>>>(rows, width, h->rows_ids, 0, src, d);
+    CUDA_TRY(cudaMemcpyAsync(dst, d, bytes, cudaMemcpyDeviceToHost, st));
+    return 0;
+  };
+  if (get(s->x, (const double *)h->x, n, 2)) return 1;
+  if ((s->vel || s->stress) && n > 0) {
+    double *dv = reinterpret_cast<double *>(buf + off);
+    off += ((size_t)n * 2 * 8 + 255) & ~(size_t)255;
+    double *ds = reinterpret_cast<double *>(buf + off);
+    off += ((size_t)n * 4 * 8 + 255) & ~(size_t)255;
+    k_rows_unpack<<<(n + 255) / 256, 256, 0, st>>>(h->P, n, h->rows_ids, state_ptrs(h, h->cur), s->vel ? dv : nullptr,
+                                                   s->stress ? ds : nullptr);
+    if (s->vel) CUDA_TRY(cudaMemcpyAsync(s->vel, dv, (size_t)n * 2 * 8, cudaMemcpyDeviceToHost, st));
+    if (s->stress) CUDA_TRY(cudaMemcpyAsync(s->stress, ds, (size_t)n * 4 * 8, cudaMemcpyDeviceToHost, st));
+  }
+  if (s->internal_vars && nt > 0) {
+    k_download_ivars<<<(h->hp.ntotal + 255) / 256, 256, 0, st>>>(h->hp.ntotal, h->epsp, h->ivars);
+    if (get(s->internal_vars, (const double *)h->ivars, nt, SPSPH_NINT_VARS)) return 1;
+  }
+  if (get(s->f_drucker, (const double *)h->fdp, nt, 1)) return 1;
+  if (get(s->displ, (const double *)h->displ, nn, 2)) return 1;
+  if (get(s->x_10, (const double *)h->x_10, nn, 2)) return 1;
+  if (get(s->disp_10, (const double *)h->disp_10, nn, 1)) return 1;
+  if (get(s->n_int, (const float *)h->n_int, nn, 1)) return 1;
+  if (get(s->bc_int, (const int *)h->bc_int, nn, 1)) return 1;
+  if (get(s->if_out_domain, (const int *)h->if_out, n, 1)) return 1;
+  if (get(s->bc_or_not, (const int *)h->bc_or_not, nt, 1)) return 1;  // (as stored: no free-surface pass here)
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
 int spsph_sync(spsph_handle *h) {
   if (!h) return 1;
   CUDA_TRY(cudaSetDevice(h->device));
@@ -1815,42 +2037,37 @@ int spsph_pair_stats(spsph_handle *h, int64_t *npairs, int32_t *maxiac, int32_t 
 int spsph_pairs(spsph_handle *h, int64_t *npairs, int32_t *pair_i, int32_t *pair_j, int32_t *pint_type, float *w,
                 float *dwdx, float *dwdy) {
   if (!h) return 1;
+  if (h->dist) {  // the creation indices of a slab run are rank-local: there is no global ordered list to export
+    h->err = "spsph_pairs is not available in a multi-GPU run (use spsph_pair_stats for the global pair count)";
+    return 1;
+  }
   const long long n = h->last_n_pairs;
   if (npairs) *npairs = n;
   if (!pair_i) return 0;
   CUDA_TRY(cudaSetDevice(h->device));
   if (materialize_lists(h)) return 1;  // creation indices (base_u) come from the count pass of the list path
-  int *d_i = nullptr, *d_j = nullptr, *d_t = nullptr;
-  float *d_w = nullptr, *d_x = nullptr, *d_y = nullptr;
+  void *d[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
   const size_t b = (size_t)(n > 0 ? n : 1) * 4;
-  CUDA_TRY(cudaMalloc((void **)&d_i, b));
-  CUDA_TRY(cudaMalloc((void **)&d_j, b));
-  CUDA_TRY(cudaMalloc((void **)&d_t, b));
-  CUDA_TRY(cudaMalloc((void **)&d_w, b));
-  CUDA_TRY(cudaMalloc((void **)&d_x, b));
-  CUDA_TRY(cudaMalloc((void **)&d_y, b));
-  const int T = h->M.total();
-  SlotMap ML = h->M;  // only the slots of this rank's local particles hold data
-  ML.nn = h->nloc[0];
-  ML.ns = h->nloc[1];
-  ML.nd = h->nloc[2];
-  // NB: valid until the next spsph_step (positions in the sorted arrays are those of the last search)
-  k_export_pairs<<<(T + 127) / 128, 128, 0, h->stream>>>(h->P, ML, h->G, sort_arrays(h), h->base_u, n,
-                                                         h->last_m_before, d_i, d_j, d_t, d_w, d_x, d_y);
-  CUDA_TRY(cudaMemcpyAsync(pair_i, d_i, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(pair_j, d_j, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(pint_type, d_t, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(w, d_w, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(dwdx, d_x, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaMemcpyAsync(dwdy, d_y, (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
-  CUDA_TRY(cudaStreamSynchronize(h->stream));
-  cudaFree(d_i);
-  cudaFree(d_j);
-  cudaFree(d_t);
-  cudaFree(d_w);
-  cudaFree(d_x);
-  cudaFree(d_y);
-  return 0;
+  auto body = [&]() -> int {
+    for (int k = 0; k < 6; ++k) CUDA_TRY(cudaMalloc(&d[k], b));
+    const int T = h->M.total();
+    SlotMap ML = h->M;  // only the slots of this rank's local particles hold data
+    ML.nn = h->nloc[0];
+    ML.ns = h->nloc[1];
+    ML.nd = h->nloc[2];
+    // NB: valid until the next spsph_step (positions in the sorted arrays are those of the last search)
+    k_export_pairs<<<(T + 127) / 128, 128, 0, h->stream>>>(h->P, ML, h->G, sort_arrays(h), h->base_u, n, h->last_m_before,
+                                                           (int *)d[0], (int *)d[1], (int *)d[2], (float *)d[3],
+                                                           (float *)d[4], (float *)d[5]);
+    void *host[6] = {pair_i, pair_j, pint_type, w, dwdx, dwdy};
+    for (int k = 0; k < 6; ++k)
+      CUDA_TRY(cudaMemcpyAsync(host[k], d[k], (size_t)n * 4, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(cudaStreamSynchronize(h->stream));
+    return 0;
+  };
+  const int rc = body();
+  for (int k = 0; k < 6; ++k) cudaFree(d[k]);
+  return rc;
 }
 
 int spsph_dist_unique_id(char *id128) {
@@ -1919,7 +2136,8 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
   D.nranks = nranks;
   D.lo = planes[rank];
   D.hi = planes[rank + 1];
-  D.H = (double)halo_cells * 2.0 * hmax;
+  // every dependent sweep reads partners up to the kernel cut-off away: scale_k * h (2 h cubic spline, 3 h Gauss / quintic)
+  D.H = (double)halo_cells * (double)h->P.scale_k * hmax;
   D.sp_follows_node = (!p.inside_approach) ? 1 : 0;  // outside approach and standard SPH
   D.cap = halo_capacity;
   if (nranks > 1 && (D.hi - D.lo) < D.H && rank > 0 && rank < nranks - 1) {
@@ -2003,6 +2221,8 @@ int spsph_destroy(spsph_handle *h) {
   cudaFree(h->TL.gy0);
   cudaFree(h->TL.gxC);
   cudaFree(h->TL.gyC);
+  cudaFree(h->rows_buf);
+  cudaFree(h->rows_ids);
   if (h->tstat_h) cudaFreeHost(h->tstat_h);
   if (h->status_h) cudaFreeHost(h->status_h);
   if (h->dist_h) cudaFreeHost(h->dist_h);

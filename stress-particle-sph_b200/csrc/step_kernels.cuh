@@ -513,17 +513,18 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
     st.norm[id] = nrm;
   else
     nrm = st.norm[id];
-  if (nrm != 0) {
-    v.x = vtx / nrm;
-    v.y = vty / nrm;
+  if (nrm != 0) {  // one reciprocal, exactly rounded quotients (div_rn == IEEE division)
+    const double rn = __drcp_rn(nrm);
+    v.x = div_rn(vtx, nrm, rn);
+    v.y = div_rn(vty, nrm, rn);
   }
   if (do_adapt) adapt_stress(P, s);
   if (do_bc) apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, v, s);
   strec(st.SVb, ks, v.x, v.y, st.mor[id], 0.0);
   st4(st.SFb, ks, s);
   const double rr = st.rho[id];
-  const double r2 = rr * rr;
-  strec(st.SB, ks, s.s1 / r2, s.s2 / r2, s.s3 / r2, st.mass[id]);
+  const double r2 = rr * rr, rr2 = __drcp_rn(r2);
+  strec(st.SB, ks, div_rn(s.s1, r2, rr2), div_rn(s.s2, r2, rr2), div_rn(s.s3, r2, rr2), st.mass[id]);
 }
 
 template <bool FIRST, bool FROMB, bool EPSP, bool UMOR>
@@ -610,11 +611,12 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
   else
     nrm = st.norm[id];
   if (nrm != 0) {
-    s.s1 = t1 / nrm;
-    s.s2 = t2 / nrm;
-    s.s3 = t3 / nrm;
-    s.s4 = t4 / nrm;
-    if (EPSP) st.epsp[id] = te / nrm;
+    const double rn = __drcp_rn(nrm);
+    s.s1 = div_rn(t1, nrm, rn);
+    s.s2 = div_rn(t2, nrm, rn);
+    s.s3 = div_rn(t3, nrm, rn);
+    s.s4 = div_rn(t4, nrm, rn);
+    if (EPSP) st.epsp[id] = div_rn(te, nrm, rn);
   } else {
     v.x = 0;
     v.y = 0;
@@ -933,8 +935,9 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
   const double2 vp = make_double2(self.a, self.b);
   const double rp = self.d;
   const Stress4 sp_ = ld4(st.NSb, id);
-  const double r2p = rp * rp;
-  const double so1 = sp_.s1 / r2p, so2 = sp_.s2 / r2p, so3 = sp_.s3 / r2p;  // stress(1:3,i)/rho(i)**2
+  const double r2p = rp * rp, rr2p = __drcp_rn(r2p);
+  const double so1 = div_rn(sp_.s1, r2p, rr2p), so2 = div_rn(sp_.s2, r2p, rr2p),
+               so3 = div_rn(sp_.s3, r2p, rr2p);  // stress(1:3,i)/rho(i)**2
   double2 xp = make_double2(0.0, 0.0);
   if (FIRST && P.cspm) xp = ld2(st.x, id);
   double ae1 = 0.0, ae2 = 0.0, ae3 = 0.0, ae4 = 0.0, ae5 = 1.0;

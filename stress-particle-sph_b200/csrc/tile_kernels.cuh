@@ -648,10 +648,10 @@ struct TileRecs {
 #define SPSPH_LG_SP0 7
 #endif
 #ifndef SPSPH_LG_N0
-#define SPSPH_LG_N0 10
+#define SPSPH_LG_N0 0
 #endif
 #ifndef SPSPH_LG_NC
-#define SPSPH_LG_NC 7
+#define SPSPH_LG_NC 0
 #endif
 #ifndef SPSPH_LG_SS
 #define SPSPH_LG_SS 11

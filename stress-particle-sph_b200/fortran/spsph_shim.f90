@@ -140,6 +140,25 @@ module spsph_c_api
        type(c_ptr), value :: h
        integer(c_int64_t), intent(out) :: m_pairs
      end function
+     integer(c_int) function spsph_upload_rows(h, s, ids, n) bind(C, name="spsph_upload_rows")
+       import :: c_ptr, c_int, c_int32_t, spsph_state
+       type(c_ptr), value :: h
+       type(spsph_state), intent(in) :: s
+       integer(c_int32_t), intent(in) :: ids(*)
+       integer(c_int32_t), value :: n
+     end function
+     integer(c_int) function spsph_download_rows(h, s, ids, n) bind(C, name="spsph_download_rows")
+       import :: c_ptr, c_int, c_int32_t, spsph_state
+       type(c_ptr), value :: h
+       type(spsph_state), intent(in) :: s
+       integer(c_int32_t), intent(in) :: ids(*)
+       integer(c_int32_t), value :: n
+     end function
+     integer(c_int) function spsph_path_counts(h, tile_steps, list_steps) bind(C, name="spsph_path_counts")
+       import :: c_ptr, c_int, c_int64_t
+       type(c_ptr), value :: h
+       integer(c_int64_t), intent(out) :: tile_steps, list_steps
+     end function
      integer(c_int) function spsph_set_list_capacity(h, m_pairs) bind(C, name="spsph_set_list_capacity")
        import :: c_ptr, c_int, c_int64_t
        type(c_ptr), value :: h

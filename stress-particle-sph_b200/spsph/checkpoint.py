@@ -22,6 +22,10 @@ DYNAMIC = ("x", "vel", "stress", "internal_vars", "f_drucker", "displ", "x_10", 
 def save(path, engine, itimestep, time_sph):
     if engine.p.cont_density or (engine.p.ifsigman == 1 and engine.p.no_bcs > 0 and engine.p.update_x):
         raise ValueError("checkpoint: cont_density = T and ifsigman = 1 keep state outside spsph_state")
+    if getattr(engine, "in_dist_mode", False):
+        # a slab rank only holds its own particles (the rest of its download is stale): merge the ranks' downloads with
+        # spsph.dist.merge_owned and checkpoint the merged state from one single-GPU engine instead
+        raise ValueError("checkpoint: this engine is one slab of a multi-GPU run; save the merged state (dist.merge_owned)")
     arrays = engine.download()
     np.savez(path, itimestep=np.int64(itimestep), time_sph=np.float64(time_sph),
              list_capacity=np.int64(engine.list_capacity()), ntotal2=np.int64(engine.p.ntotal2),

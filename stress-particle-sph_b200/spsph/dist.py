@@ -32,7 +32,10 @@ def plan_slabs(problem, nranks, safety=2.0, balance="processed"):
     ux = np.unique(xn)
     halo_cells = dependent_sweeps(p) + 2
     hmax = float(problem.arrays["hsml"].max())
-    H = halo_cells * 2.0 * hmax
+    # a dependent sweep reads partners up to the kernel cut-off away: 2 h for the cubic spline, 3 h for the Gauss and
+    # quintic kernels (main:1228-1238; the cell edge stays 2 h) -- the same expression as spsph_dist_init
+    scale_k = 2.0 if p.skf == 1 else 3.0
+    H = halo_cells * scale_k * hmax
 
     def snap(v):  # midpoint between the two distinct columns around v
         k = int(np.searchsorted(ux, v))
@@ -102,6 +105,20 @@ def initial_flags(problem, plan, rank):
     f[(xi >= lo - H) & (xi < hi + H)] = GHOST
     f[(xk >= lo) & (xk < hi)] = OWNED
     return f
+
+
+def local_ids(problem, plan, rank, x=None):
+    """particle numbers a rank has to hold (owned + ghost), ascending: the row set of spsph_upload_rows"""
+    if x is None:
+        return np.flatnonzero(initial_flags(problem, plan, rank) != REMOTE).astype(np.int32)
+    p = problem.params
+    lo, hi, H = plan["planes"][rank], plan["planes"][rank + 1], plan["H"]
+    xi = x[:, 0]
+    xk = xi.copy()
+    if p.sp_sph and not p.inside_approach:
+        xk[p.nnode:p.ntotal] = xi[np.arange(p.nstress) // p.npoints]
+    keep = ((xi >= lo - H) & (xi < hi + H)) | ((xk >= lo) & (xk < hi))
+    return np.flatnonzero(keep).astype(np.int32)
 
 
 def merge_owned(per_rank_arrays, per_rank_flags, params):

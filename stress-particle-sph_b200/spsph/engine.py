@@ -36,6 +36,8 @@ def cuda_lib():
         L.spsph_get_list_capacity.argtypes = [H, C.POINTER(C.c_int64)]
         L.spsph_set_list_capacity.argtypes = [H, C.c_int64]
         L.spsph_path_counts.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
+        L.spsph_upload_rows.argtypes = [H, C.POINTER(_abi.State), C.c_void_p, C.c_int32]
+        L.spsph_download_rows.argtypes = [H, C.POINTER(_abi.State), C.c_void_p, C.c_int32]
         L.spsph_dist_unique_id.argtypes = [C.c_char_p]
         L.spsph_dist_init.argtypes = [H, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_double), C.c_int32, C.c_int32]
         L.spsph_dist_flags.argtypes = [H, C.c_void_p]
@@ -53,7 +55,36 @@ def cuda_lib():
 EXPORTS = ["spsph_create", "spsph_upload", "spsph_step", "spsph_run", "spsph_download", "spsph_pair_stats",
            "spsph_pairs", "spsph_last_run_ms", "spsph_sync", "spsph_profile", "spsph_profile_get",
            "spsph_dist_unique_id", "spsph_dist_init", "spsph_dist_flags", "spsph_local_counts", "spsph_get_list_capacity",
-           "spsph_set_list_capacity", "spsph_path_counts", "spsph_destroy", "spsph_last_error", "spsph_version"]
+           "spsph_set_list_capacity", "spsph_path_counts", "spsph_upload_rows",
+           "spsph_download_rows", "spsph_destroy", "spsph_last_error", "spsph_version"]
+
+
+# row sets of the time-varying state: (rows of all ids, of ids < ntotal, of ids < nnode)
+_ROWS_ALL = ("x", "vel", "stress", "if_out_domain")
+_ROWS_PART = ("internal_vars", "f_drucker", "bc_or_not")
+_ROWS_NODE = ("displ", "x_10", "disp_10", "n_int", "bc_int")
+
+
+def _row_selector(p, ids, key):
+    if key in _ROWS_ALL:
+        return ids
+    if key in _ROWS_PART:
+        return ids[ids < p.ntotal]
+    if key in _ROWS_NODE:
+        return ids[ids < p.nnode]
+    raise KeyError(f"{key} is not part of the time-varying state")
+
+
+def row_arrays(p, arrays, ids, keys=_ROWS_ALL + _ROWS_PART + _ROWS_NODE):
+    """compact copies of the rows `ids` of full arrays, in the layout spsph_upload_rows expects"""
+    ids = np.asarray(ids, dtype=np.int32)
+    return {k: np.ascontiguousarray(arrays[k][_row_selector(p, ids, k)]) for k in keys if k in arrays}
+
+
+def alloc_rows(p, ids, keys):
+    ids = np.asarray(ids, dtype=np.int32)
+    spec = {name: (dt, shape(p)) for name, _, dt, shape in _abi.STATE_FIELDS}
+    return {k: np.zeros((len(_row_selector(p, ids, k)),) + tuple(spec[k][1][1:]), spec[k][0]) for k in keys}
 
 
 def dist_unique_id():
@@ -85,6 +116,21 @@ class Engine:
     def upload(self, arrays):
         st = _abi.state_from_arrays(arrays)
         self._chk(self.L.spsph_upload(self.h, C.byref(st)))
+
+    def upload_rows(self, rows, ids):
+        """time-varying state of the particles `ids` (ascending int32): rows = dict of compact arrays (see row_arrays)"""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        st = _abi.state_from_arrays(rows)
+        self._chk(self.L.spsph_upload_rows(self.h, C.byref(st), ids.ctypes.data, len(ids)))
+
+    def download_rows(self, ids, rows=None, keys=("x", "vel", "stress", "internal_vars", "displ")):
+        """-> dict of compact arrays holding the rows of the particles `ids` (ascending int32)"""
+        ids = np.ascontiguousarray(ids, dtype=np.int32)
+        if rows is None:
+            rows = alloc_rows(self.p, ids, keys)
+        st = _abi.state_from_arrays(rows)
+        self._chk(self.L.spsph_download_rows(self.h, C.byref(st), ids.ctypes.data, len(ids)))
+        return rows
 
     def step(self, itimestep, time_sph, dt):
         self._chk(self.L.spsph_step(self.h, itimestep, time_sph, dt))
@@ -118,6 +164,7 @@ class Engine:
         """join the x-slab decomposition (spsph.dist.plan_slabs); unique_id: 128 bytes from dist_unique_id()"""
         planes = np.ascontiguousarray(plan["planes"], dtype=np.float64)
         assert len(planes) == nranks + 1 and len(unique_id) == 128
+        self.in_dist_mode = True
         self._chk(self.L.spsph_dist_init(self.h, rank, nranks, bytes(unique_id),
                                          planes.ctypes.data_as(C.POINTER(C.c_double)), int(plan["halo_cells"]),
                                          int(plan["halo_capacity"])))

@@ -248,15 +248,16 @@ using std::min;
 #ifndef SPSPH_EMU_SIMT
 // ---- kernel launch: k<<<grid, block, smem, stream>>>(args) is rewritten to emu_launch(grid, block, k, args) ----------
 template <class K, class... A>
-static inline void emu_launch(unsigned grid, unsigned block, K kernel, A... args) {
-  emu_gridDim = EmuDim{grid, 1, 1};
+static inline void emu_launch(dim3 grid, unsigned block, K kernel, A... args) {
+  emu_gridDim = EmuDim{grid.x, grid.y, 1};
   emu_blockDim = EmuDim{block, 1, 1};
-  for (unsigned b = 0; b < grid; ++b)
-    for (unsigned t = 0; t < block; ++t) {
-      emu_blockIdx = EmuDim{b, 0, 0};
-      emu_threadIdx = EmuDim{t, 0, 0};
-      kernel(args...);
-    }
+  for (unsigned by = 0; by < grid.y; ++by)
+    for (unsigned b = 0; b < grid.x; ++b)
+      for (unsigned t = 0; t < block; ++t) {
+        emu_blockIdx = EmuDim{b, by, 0};
+        emu_threadIdx = EmuDim{t, 0, 0};
+        kernel(args...);
+      }
 }
 
 #else

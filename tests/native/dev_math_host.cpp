@@ -7,6 +7,10 @@
 #include <cmath>
 #include <cstring>
 
+// the two intrinsics of div_rn (exactly rounded division by a value with a known reciprocal) on the host
+static inline double __fma_rn(double a, double b, double c) { return std::fma(a, b, c); }
+static inline double __drcp_rn(double x) { return 1.0 / x; }
+
 #include "dev_common.cuh"
 
 using namespace spsph;
