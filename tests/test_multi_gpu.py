@@ -47,3 +47,55 @@ def test_two_slabs_match_oracle(tmp_path, deck_dir, kind, steps):
         assert np.array_equal(a, b), f"{kind}: {k} differs, max |diff| {np.abs(a - b).max():.3e}"
     # both ranks really own a share
     assert all((r_["flags"] == 1).sum() > 0.2 * prob.params.ntotal2 for r_ in ranks)
+
+
+def test_bench_two_slabs_records_parity_and_weak_scaling(tmp_path):
+    """bench.py --gpus 2 (reduced sizes): the line carries a bit-for-bit slab parity check against the single-GPU engine
+    and against the reference executable's golden, the weak-scaling sub-record, and an e2e leg that moves rank-local rows"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import json
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29534", os.path.join(ROOT, "bench.py"), "--gpus", "2", "--steps", "5",
+           "--warmup", "3", "--ncol", "408", "--no-cpu", "--weak-ncol", "200", "--weak-steps", "4", "--parity-ncol", "136",
+           "--parity-steps", "30"]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=1200)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    line = json.loads([ln for ln in r.stdout.splitlines() if ln.startswith("{")][-1])
+    pc = line["parity_check"]
+    assert pc["ranks"] == 2 and pc["bitwise_equal_single_gpu"] is True and pc["pair_count_equal"] is True, pc
+    assert pc["reference_executable_golden"]["bitwise_equal"] is True, pc
+    assert line["weak_scaling"]["value"] > 0 and line["e2e"]["value"] > 0
+    assert "spsph_upload_rows" in line["config"]["e2e_protocol"]
+
+
+def test_two_slabs_gauss_kernel_halo(tmp_path):
+    """Gauss kernel (cut-off 3 h on cells of 2 h): the halo distance follows the cut-off"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import spsph
+    from spsph import decks, dist
+    from oracle_binding import Oracle
+    out = str(tmp_path / "dist")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29535", os.path.join(ROOT, "tools", "dist_worker.py"), "--kind", "vs_gauss",
+           "--steps", "30", "--out", out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    d = str(tmp_path / "deck")
+    spec = decks.vertical_slope_spec()
+    spec["skf"] = 2
+    decks.write_deck(d, spec)
+    prob = spsph.load(d, "vs")
+    orc = Oracle(prob)
+    orc.run(1, 0.0, prob.blocks[0]["dt"], 30)
+    ref = orc.download()
+    ranks = [np.load(os.path.join(out, f"rank{k}.npz")) for k in range(2)]
+    keys = ("x", "vel", "stress", "internal_vars", "f_drucker", "displ")
+    merged = dist.merge_owned([{k: r_[k] for k in keys} for r_ in ranks], [r_["flags"] for r_ in ranks], prob.params)
+    nt = prob.params.ntotal
+    for k in keys:
+        a, b = merged[k], ref[k]
+        if k in ("x", "vel", "stress"):
+            a, b = a[:nt], b[:nt]
+        assert np.allclose(a, b, rtol=1e-9, atol=1e-300), f"vs_gauss: {k} differs"

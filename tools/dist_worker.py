@@ -33,6 +33,9 @@ def main():
         spec, var = decks.refined_bui_spec(ncol=a.ncol), "bui"
     elif a.kind == "wide_slope":
         spec, var = decks.wide_slope_spec(ncol=a.ncol, nslab=world), "vs"
+    elif a.kind == "vs_gauss":
+        spec, var = decks.vertical_slope_spec(), "vs"
+        spec["skf"] = 2
     else:
         spec, var = decks.SHIPPED[a.kind](), a.kind
     decks.write_deck(d, spec)
