@@ -26,6 +26,17 @@ def tile_path(monkeypatch):
     monkeypatch.setenv("SPSPH_TILE", "1")  # read by spsph_create
 
 
+SETUP_KEYS = ("rho", "mass", "hsml", "itype", "wall_position", "horizontal_or_not", "bc_info")
+
+
+def _full_state(prob, snap):
+    """a download completed with the set-up arrays spsph_download does not return (wall geometry, BC tables)"""
+    full = dict(snap)
+    for k in SETUP_KEYS:
+        full[k] = prob.arrays[k]
+    return full
+
+
 def _run(prob, nsteps, label, check_at=(), pairs_at=(), min_tile_share=0.9):
     import spsph
     from oracle_binding import Oracle
@@ -94,7 +105,7 @@ def test_tile_path_restart_from_download(deck_dir):
     snap, cap = a.download(), a.list_capacity()
     a.run(6, t, dt, 5)
     b = spsph.Engine(prob)
-    b.upload(snap)
+    b.upload(_full_state(prob, snap))
     b.set_list_capacity(cap)
     b.run(6, t, dt, 5)
     _compare(b.download(), a.download(), prob.params.ntotal, "restart on the tile path")
@@ -144,7 +155,7 @@ def test_row_wise_transfers_single_gpu(deck_dir, monkeypatch):
         assert np.array_equal(x, y), k
     # a fresh engine fed row-wise continues like one fed by spsph_upload
     b, c = spsph.Engine(prob), spsph.Engine(prob)
-    b.upload(snap)
+    b.upload(_full_state(prob, snap))
     c.upload_rows(row_arrays(p, snap, ids_all), ids_all)
     b.run(8, t, dt, 5)
     c.run(8, t, dt, 5)
