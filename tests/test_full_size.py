@@ -64,3 +64,20 @@ def test_refined_bui_4m_bitwise_and_properties(deck_dir):
     vy = a["vel"][:p.nnode, 1]
     assert vy.min() < 0 and vy.max() <= 1e-12
     eng.close()
+
+
+def test_refined_bui_1m_20_steps_bitwise(deck_dir):
+    """1.0 M particles x 20 steps against the oracle, bit for bit (about 90 s of CPU time for the serial oracle): the
+    large configuration beyond its first two steps"""
+    import spsph
+    from oracle_binding import Oracle
+    prob = spsph.load(deck_dir("refined_bui_spec", ncol=816), "bui")
+    assert prob.params.ntotal == 817 * 409 * 3
+    dt = prob.blocks[0]["dt"]
+    eng, orc = spsph.Engine(prob), Oracle(prob)
+    eng.run(1, 0.0, dt, 20)
+    orc.run(1, 0.0, dt, 20)
+    assert eng.pair_stats() == orc.pair_stats()
+    _bitwise(eng.download(), orc.download(), prob.params.ntotal, "refined Bui 1M, 20 steps")
+    eng.close()
+    orc.close()
