@@ -126,10 +126,9 @@ DEVICE_UNSUPPORTED = set()
 # cases where the engine evaluates libm functions (atan, asin, sin, cos, tan, exp, pow) with CUDA's implementations
 # instead of glibc's: agreement to the north star's 1e-9 relative L-inf instead of bit for bit
 DEVICE_TOLERANCE = {"bui_art_stress": 1e-9, "sl_art_stress": 1e-9, "sl_vm_expflow": 1e-9, "sl_vm_powflow": 1e-9,
-                    "sl_tresca": 1e-9, "sl_mohr_coulomb": 1e-9,
-                    # k_fs_normals: fp64 sums of fp32 chords and the sqrt-for-pow substitution; bit-exactness is
-                    # expected but not confirmed on hardware yet, the contractual 1e-9 until then
-                    "sl_sigman": 1e-9, "vs_sigman": 1e-9, "sl_sigman_xsph": 1e-9}
+                    "sl_tresca": 1e-9, "sl_mohr_coulomb": 1e-9}
+# (sl_sigman, vs_sigman, sl_sigman_xsph -- apply_stress_free with k_fs_normals -- carried 1e-9 until their first
+# hardware run; round 2 confirmed them bit-exact on the B200, tools/strict_cases.py, and they are now asserted bitwise)
 # device paths written after this round's GPU budget was spent: their first run on hardware
 # is tests/test_zz_gpu_new_paths.py, the last file of the GPU suite, so that a surprise there cannot mask the
 # verified cases of tests/test_gpu_reference.py (the driver runs pytest with -x)

@@ -481,7 +481,10 @@ static cudaError_t realloc4(T **p, long long n, bool wanted = true) {
   cudaFree(*p);
   *p = nullptr;
   if (!wanted) return cudaSuccess;
-  return cudaMalloc((void **)p, (size_t)n * 4);
+  const cudaError_t e = cudaMalloc((void **)p, (size_t)n * 4);
+  // the sweeps copy whole groups of list rows, including slots past the end of a lane's list that nobody writes:
+  // zero them once so that those (unused) reads are reads of initialised memory (compute-sanitizer initcheck)
+  return e != cudaSuccess ? e : cudaMemset(*p, 0, (size_t)n * 4);
 }
 int ensure_lists(spsph_handle *h, long long t0, long long tC, long long tD) {
   // 1024 entries of slack: the sweeps stream whole groups of rows and may read (never use) up to 7 rows past a slice

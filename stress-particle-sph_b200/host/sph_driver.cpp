@@ -11,6 +11,7 @@
 #include <string>
 #include <vector>
 
+#include "sph_gid.hpp"
 #include "sph_problem.hpp"
 
 static int variant_of(const char *s) {
@@ -21,9 +22,11 @@ static int variant_of(const char *s) {
   return -1;
 }
 
-// OutputRes, ParaView part: nodes.csv.NNNNNN, stress_points.csv.NNNNNN (column selection by the *_out flags)
-static void output_res(const spsph::Problem &P, int itimestep_sph, const std::string &out) {
+// OutputRes: the GiD frame (sph_gid.cpp), then the ParaView part: nodes.csv.NNNNNN, stress_points.csv.NNNNNN (column
+// selection by the *_out flags)
+static void output_res(spsph::Problem &P, int itimestep_sph, double time_sph, const std::string &out) {
   const spsph_params &p = P.p;
+  spsph::gid_append_results(P, P.view(), time_sph, out + "/" + P.name);
   char tag[16];
   std::snprintf(tag, sizeof tag, "%06d", itimestep_sph);
   auto row = [&](FILE *f, int i, bool node) {
@@ -101,13 +104,14 @@ int main(int argc, char **argv) {
   spsph_state st = P.view();
   if (spsph_upload(h, &st)) return die("spsph_upload");
 
+  spsph::gid_write_mesh(P, P.x.data(), out + "/" + P.name);  // Init_sph -> OutputMesh, main:42-44
   // main loop, 1_SPH_2018.f90:134-199 (fp32 output-cadence counters as in 6_SPH_time_vars_2018.f90:40-45)
   double time_sph = 0.0;
   int itimestep_sph = 0;
   long total = 0;
   for (const spsph::TimeBlock &b : P.blocks) {
     const double dt = b.dt;
-    output_res(P, itimestep_sph, out);  // initial frame, 1_SPH_2018.f90:156
+    output_res(P, itimestep_sph, time_sph, out);  // initial frame, 1_SPH_2018.f90:156
     const float time_print = (float)(b.print_step * dt), time_plot = (float)(b.plot_step * dt);
     float t_print_reset = 0.f, t_plot_reset = 0.f;
     double time = time_sph;
@@ -123,7 +127,7 @@ int main(int argc, char **argv) {
       const bool stop = (max_steps >= 0 && total >= max_steps);  // --max-steps (not in the reference) ends with a frame
       if (t_plot_reset >= time_plot || stop) {
         if (spsph_download(h, &st)) return die("spsph_download");
-        output_res(P, itimestep_sph, out);
+        output_res(P, itimestep_sph, time_sph, out);
         t_plot_reset = 0.f;
       }
       if (t_print_reset >= time_print) {  // Out_print_sph, main:51-73

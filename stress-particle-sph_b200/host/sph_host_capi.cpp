@@ -2,6 +2,7 @@
 #include <cstring>
 #include <string>
 
+#include "sph_gid.hpp"
 #include "sph_problem.hpp"
 
 extern "C" {
@@ -42,6 +43,24 @@ int spsph_problem_block(void *h, int k, double *dt, double *time_end, int *maxti
 }
 
 const char *spsph_problem_name(void *h) { return ((spsph::Problem *)h)->name.c_str(); }
+
+// GiD writers of the host driver (sph_gid.hpp): mesh + result header from the positions x, one result frame from a state
+int spsph_problem_gid_mesh(void *h, const double *x, const char *path_prefix) {
+  try {
+    spsph::gid_write_mesh(*(spsph::Problem *)h, x, path_prefix);
+    return 0;
+  } catch (const std::exception &) {
+    return 1;
+  }
+}
+int spsph_problem_gid_results(void *h, const spsph_state *s, double time_sph, const char *path_prefix) {
+  try {
+    spsph::gid_append_results(*(spsph::Problem *)h, *s, time_sph, path_prefix);
+    return 0;
+  } catch (const std::exception &) {
+    return 1;
+  }
+}
 
 void spsph_problem_free(void *h) { delete (spsph::Problem *)h; }
 

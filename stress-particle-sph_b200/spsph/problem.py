@@ -31,6 +31,8 @@ def host_lib():
         lib.spsph_problem_name.restype = C.c_char_p
         lib.spsph_problem_name.argtypes = [C.c_void_p]
         lib.spsph_problem_free.argtypes = [C.c_void_p]
+        lib.spsph_problem_gid_mesh.argtypes = [C.c_void_p, C.c_void_p, C.c_char_p]
+        lib.spsph_problem_gid_results.argtypes = [C.c_void_p, C.POINTER(_abi.State), C.c_double, C.c_char_p]
         _lib = lib
     return _lib
 
@@ -83,3 +85,32 @@ def load(directory, variant):
     finally:
         lib.spsph_problem_free(h)
     return Problem(p, arrays, blocks, name)
+
+
+class GidWriter:
+    """<name>.post.msh / <name>.post.res of the reference driver (OutputMesh, OutputRes: host/sph_gid.cpp) for the deck
+    in `directory`; frames are appended from downloaded states"""
+
+    def __init__(self, directory, variant, path_prefix):
+        lib = host_lib()
+        v = _abi.VARIANTS[variant] if isinstance(variant, str) else int(variant)
+        err = C.create_string_buffer(512)
+        self._h = lib.spsph_problem_load(os.fsencode(directory), v, err, 512)
+        if not self._h:
+            raise RuntimeError("spsph_problem_load: " + err.value.decode())
+        self.prefix = os.fsencode(path_prefix)
+
+    def mesh(self, x):
+        x = np.ascontiguousarray(x, dtype=np.float64)
+        if host_lib().spsph_problem_gid_mesh(self._h, x.ctypes.data, self.prefix):
+            raise RuntimeError("gid mesh writer failed")
+
+    def frame(self, arrays, time_sph):
+        st = _abi.state_from_arrays(arrays)
+        if host_lib().spsph_problem_gid_results(self._h, C.byref(st), float(time_sph), self.prefix):
+            raise RuntimeError("gid result writer failed")
+
+    def close(self):
+        if self._h:
+            host_lib().spsph_problem_free(self._h)
+            self._h = None
