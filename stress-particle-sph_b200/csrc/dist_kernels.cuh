@@ -21,6 +21,12 @@ namespace spsph {
 enum : int { LF_REMOTE = 0, LF_OWNED = 1, LF_GHOST = 2, LF_STALE = 3 };
 // doubles per exchanged particle: id, x(2), vel(2), stress(4), eps_p, f_drucker, x_10(2), disp_10, displ(2), out flag, spare
 constexpr int HALO_REC = 18;
+// extended record (DistGeom::ext != 0): + rho, hsml, div u (continuity density: the density of a stress particle is
+// integrated, its smoothing length follows with sle = 2, and density_update reads the last velocity divergence,
+// main:706-713, 807-821) + bc_or_not, free-surface normal (get_nodes_on_free_surface every step: apply_stress_free
+// and XSPH next to boundary conditions read the marks of the previous step, mat:1756-1839, main:224-230)
+constexpr int HALO_REC_EXT = 24;
+enum : int { HALO_EXT_DENSITY = 1, HALO_EXT_MARKS = 2 };
 
 struct DistGeom {
   int rank, nranks;
@@ -29,6 +35,8 @@ struct DistGeom {
   int sp_follows_node;  // outside approach: a stress particle is owned by the rank that owns its node
   int cap;        // record capacity of one halo message buffer
   int lim[2];     // records this step's message to the left / right neighbour may hold (<= cap)
+  int rec;        // doubles per record: HALO_REC, or HALO_REC_EXT when ext != 0
+  int ext;        // HALO_EXT_* bits: what the extended part of a record carries
 };
 
 // position that decides ownership: a stress particle of the outside approach follows its velocity particle,
@@ -140,16 +148,36 @@ __global__ void k_halo_select(DevParams P, DistGeom D, const double *__restrict_
 struct HaloArrays {
   double *x, *epsp, *fdp, *x_10, *disp_10, *displ;
   int *if_out;
+  // extended record
+  double *rho, *hsml, *mor, *divu;
+  double2 *mrho;
+  int *bc_or_not;
+  double *fs_normal;
 };
 
 // message layout: record 0 = header {count}, records 1..count = particles
-__global__ void k_halo_pack(DevParams P, StatePtrs st, HaloArrays A, const int *__restrict__ cnt_ptr, int cap,
+__global__ void k_halo_pack(DevParams P, DistGeom D, StatePtrs st, HaloArrays A, const int *__restrict__ cnt_ptr, int cap,
                             const int *__restrict__ ids, double *__restrict__ msg) {
   const int n = min(*cnt_ptr, cap);
   if (blockIdx.x == 0 && threadIdx.x == 0) msg[0] = (double)n;
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
     const int i = ids[k];
-    double *o = msg + (size_t)HALO_REC * (k + 1);
+    double *o = msg + (size_t)D.rec * (k + 1);
+    if (D.ext) {
+      for (int q = HALO_REC; q < HALO_REC_EXT; ++q) o[q] = 0.0;
+      if (D.ext & HALO_EXT_DENSITY) {
+        o[18] = A.rho[i];
+        o[19] = A.hsml[i];
+        if (i >= P.nnode && i < P.ntotal) o[20] = A.divu[i - P.nnode];
+      }
+      if ((D.ext & HALO_EXT_MARKS) && i < P.ntotal) {
+        o[21] = (double)A.bc_or_not[i];
+        if (i < P.nnode) {
+          o[22] = A.fs_normal[2 * (size_t)i];
+          o[23] = A.fs_normal[2 * (size_t)i + 1];
+        }
+      }
+    }
     o[0] = (double)i;
     o[1] = A.x[2 * (size_t)i];
     o[2] = A.x[2 * (size_t)i + 1];
@@ -194,13 +222,30 @@ __global__ void k_halo_unpack(DevParams P, DistGeom D, StatePtrs st, HaloArrays 
                               int *__restrict__ lflag, int *__restrict__ list_ids, int *__restrict__ list_n) {
   const int n = (int)msg[0];
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const double *o = msg + (size_t)HALO_REC * (k + 1);
+    const double *o = msg + (size_t)D.rec * (k + 1);
     const int i = (int)o[0];
     A.x[2 * (size_t)i] = o[1];
     A.x[2 * (size_t)i + 1] = o[2];
     A.if_out[i] = (int)o[16];
+    double rho_i = st.rho[i], mor_i = st.mor[i];
+    if (D.ext & HALO_EXT_DENSITY) {  // the density (and smoothing length) travel with the particle
+      rho_i = o[18];
+      mor_i = st.mass[i] / rho_i;
+      A.rho[i] = rho_i;
+      A.hsml[i] = o[19];
+      A.mor[i] = mor_i;
+      A.mrho[i] = make_double2(st.mass[i], rho_i);
+      if (i >= P.nnode && i < P.ntotal) A.divu[i - P.nnode] = o[20];
+    }
+    if ((D.ext & HALO_EXT_MARKS) && i < P.ntotal) {
+      A.bc_or_not[i] = (int)o[21];
+      if (i < P.nnode) {
+        A.fs_normal[2 * (size_t)i] = o[22];
+        A.fs_normal[2 * (size_t)i + 1] = o[23];
+      }
+    }
     if (i < P.nnode) {
-      strec(st.NB, i, o[3], o[4], st.mass[i], st.rho[i]);
+      strec(st.NB, i, o[3], o[4], st.mass[i], rho_i);
       st4(st.NSb, i, Stress4{o[5], o[6], o[7], o[8]});
       st.epsp[i] = o[9];
       st.fdp[i] = o[10];
@@ -211,10 +256,10 @@ __global__ void k_halo_unpack(DevParams P, DistGeom D, StatePtrs st, HaloArrays 
       A.displ[2 * (size_t)i + 1] = o[15];
     } else if (i < P.ntotal) {
       const int ks = i - P.nnode;
-      strec(st.SVb, ks, o[3], o[4], st.mor[i], 0.0);
+      strec(st.SVb, ks, o[3], o[4], mor_i, 0.0);
       const Stress4 s{o[5], o[6], o[7], o[8]};
       st4(st.SFb, ks, s);
-      const double r = st.rho[i];
+      const double r = rho_i;
       const double r2 = r * r;
       strec(st.SB, ks, s.s1 / r2, s.s2 / r2, s.s3 / r2, st.mass[i]);
       st.epsp[i] = o[9];
@@ -230,7 +275,7 @@ __global__ void k_halo_own(DevParams P, DistGeom D, const double *__restrict__ x
                            int *__restrict__ lflag) {
   const int n = (int)msg[0];
   for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
-    const int i = (int)msg[(size_t)HALO_REC * (k + 1)];
+    const int i = (int)msg[(size_t)D.rec * (k + 1)];
     const double xk = key_x(P, D, x, i);
     if (xk >= D.lo && xk < D.hi) lflag[i] = LF_OWNED;
   }

@@ -592,18 +592,19 @@ int halo_exchange(spsph_handle *h) {
   cudaStream_t s = h->stream;
   const int n2 = P.ntotal2;
   const StatePtrs st = state_ptrs(h, h->cur);
-  const HaloArrays A{h->x, h->epsp, h->fdp, h->x_10, h->disp_10, h->displ, h->if_out};
+  const HaloArrays A{h->x,   h->epsp, h->fdp,  h->x_10, h->disp_10,   h->displ,    h->if_out,
+                     h->rho, h->hsml, h->mor,  h->divu, h->mrho,      h->bc_or_not, h->fs_normal};
   if (h->profiling) mark(h, -1, 0);
   CUDA_TRY(cudaMemsetAsync(h->halo_cnt, 0, 2 * sizeof(int), s));
   const LocalList LL = local_list(h, n2);
   k_halo_select<<<list_grid(h, n2, 256), 256, 0, s>>>(P, D, h->x, h->lflag, LL, h->halo_cnt, h->halo_ids[0],
                                                        h->halo_ids[1], h->halo_cnt + 2);
   for (int side = 0; side < 2; ++side)
-    k_halo_pack<<<148, 256, 0, s>>>(P, st, A, h->halo_cnt + side, D.lim[side], h->halo_ids[side], h->halo_send[side]);
+    k_halo_pack<<<148, 256, 0, s>>>(P, D, st, A, h->halo_cnt + side, D.lim[side], h->halo_ids[side], h->halo_send[side]);
   const int left = D.rank - 1, right = D.rank + 1;
-  const size_t msg_s[2] = {(size_t)HALO_REC * (D.lim[0] + 1), (size_t)HALO_REC * (D.lim[1] + 1)};
-  const size_t msg_r[2] = {(size_t)HALO_REC * (halo_limit(h, h->halo_prev_recv[0]) + 1),
-                           (size_t)HALO_REC * (halo_limit(h, h->halo_prev_recv[1]) + 1)};
+  const size_t msg_s[2] = {(size_t)D.rec * (D.lim[0] + 1), (size_t)D.rec * (D.lim[1] + 1)};
+  const size_t msg_r[2] = {(size_t)D.rec * (halo_limit(h, h->halo_prev_recv[0]) + 1),
+                           (size_t)D.rec * (halo_limit(h, h->halo_prev_recv[1]) + 1)};
   NCCL_TRY(h->p_ncclGroupStart());
   if (left >= 0) {
     NCCL_TRY(h->p_ncclSend(h->halo_send[0], msg_s[0], ncclDouble, left, h->comm, s));
@@ -2092,15 +2093,6 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
     h->err = "spsph_dist_init must follow spsph_upload (every rank uploads the complete problem)";
     return 1;
   }
-  if (h->hp.cont_density) {
-    h->err = "multi-GPU: cont_density = T is not supported (the halo records carry no density / smoothing length)";
-    return 1;
-  }
-  if (h->fs_each_step) {
-    h->err = "multi-GPU: ifsigman = 1 and XSPH with boundary conditions are not supported (the halo records carry no "
-             "free-surface marks)";
-    return 1;
-  }
   CUDA_TRY(cudaSetDevice(h->device));
   const spsph_params &p = h->hp;
   h->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
@@ -2143,12 +2135,15 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
   D.H = (double)halo_cells * (double)h->P.scale_k * hmax;
   D.sp_follows_node = (!p.inside_approach) ? 1 : 0;  // outside approach and standard SPH
   D.cap = halo_capacity;
+  // continuity density and per-step free-surface marks travel in an extended halo record
+  D.ext = (p.cont_density ? HALO_EXT_DENSITY : 0) | (h->fs_each_step ? HALO_EXT_MARKS : 0);
+  D.rec = D.ext ? HALO_REC_EXT : HALO_REC;
   if (nranks > 1 && (D.hi - D.lo) < D.H && rank > 0 && rank < nranks - 1) {
     h->err = "multi-GPU: slab thinner than the halo distance";
     return 1;
   }
   const size_t n2 = (size_t)p.ntotal2;
-  const size_t msg = (size_t)HALO_REC * ((size_t)D.cap + 1);
+  const size_t msg = (size_t)D.rec * ((size_t)D.cap + 1);
   if (dalloc(h, &h->lflag, n2) || dalloc(h, &h->halo_cnt, 4)) return 1;
   if (dalloc(h, &h->list_ids[0], n2) || dalloc(h, &h->list_ids[1], n2) || dalloc(h, &h->list_n, 2) ||
       dalloc(h, &h->list_keep, n2) || dalloc(h, &h->list_pos, n2))

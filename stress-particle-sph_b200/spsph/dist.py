@@ -18,6 +18,10 @@ def dependent_sweeps(params):
         n += 1                     # interpolation at the start of the step (main:99-109)
     if params.update_x and params.xsph:
         n += 1                     # XSPH_update reads partner velocities (main:189-239)
+    if params.update_x and params.no_bcs > 0 and (params.ifsigman == 1 or params.xsph):
+        # get_nodes_on_free_surface runs every step (spsph_create: fs_each_step): it reads the partners' new positions,
+        # then the step-4 normals read the partners' fresh marks and covered flags (mat:1116-1411) -- plus one spare
+        n += 3
     return n
 
 

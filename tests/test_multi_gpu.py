@@ -99,3 +99,38 @@ def test_two_slabs_gauss_kernel_halo(tmp_path):
         if k in ("x", "vel", "stress"):
             a, b = a[:nt], b[:nt]
         assert np.allclose(a, b, rtol=1e-9, atol=1e-300), f"vs_gauss: {k} differs"
+
+
+@pytest.mark.parametrize("case", ["bui_cont_density", "vs_cont_density_sle2", "sl_sigman_xsph", "vs_sigman"])
+def test_two_slabs_extended_halo_record(tmp_path, case):
+    """continuity density (+ smoothing-length update) and per-step free-surface marks (apply_stress_free, XSPH next to
+    boundary conditions) on two slabs: the density, smoothing length, velocity divergence, marks and normals travel in
+    the extended halo record; owned particles equal the single-domain oracle bit for bit"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import spsph
+    from spsph import decks, dist
+    from oracle_binding import Oracle
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from ref_cases import spec_of
+    steps = 30
+    out = str(tmp_path / "dist")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29536", os.path.join(ROOT, "tools", "dist_worker.py"), "--kind", "case:" + case,
+           "--steps", str(steps), "--out", out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    variant, spec = spec_of(case)
+    d = str(tmp_path / "deck")
+    decks.write_deck(d, spec)
+    prob = spsph.load(d, variant)
+    orc = Oracle(prob)
+    orc.run(1, 0.0, prob.blocks[0]["dt"], steps)
+    ref = orc.download()
+    ranks = [np.load(os.path.join(out, f"rank{k}.npz")) for k in range(2)]
+    keys = ("x", "vel", "stress", "internal_vars", "f_drucker", "displ", "rho", "hsml")
+    merged = dist.merge_owned([{k: r_[k] for k in keys} for r_ in ranks], [r_["flags"] for r_ in ranks], prob.params)
+    nt = prob.params.ntotal
+    for k in keys:
+        a, b = merged[k][:nt], ref[k][:nt]
+        assert np.array_equal(a, b), f"{case}: {k} differs in {int((a != b).sum())} entries, max |diff| {np.abs(a - b).max():.3e}"

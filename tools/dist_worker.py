@@ -33,6 +33,10 @@ def main():
         spec, var = decks.refined_bui_spec(ncol=a.ncol), "bui"
     elif a.kind == "wide_slope":
         spec, var = decks.wide_slope_spec(ncol=a.ncol, nslab=world), "vs"
+    elif a.kind.startswith("case:"):  # a golden case of oracle/ref_cases.py (option combinations no shipped deck uses)
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        from ref_cases import spec_of
+        var, spec = spec_of(a.kind[5:])
     elif a.kind == "vs_gauss":
         spec, var = decks.vertical_slope_spec(), "vs"
         spec["skf"] = 2
@@ -52,7 +56,7 @@ def main():
     flags = eng.dist_flags()
     os.makedirs(a.out, exist_ok=True)
     np.savez(os.path.join(a.out, f"rank{rank}.npz"), flags=flags, ms=ms, npairs=eng.pair_stats()["npairs"],
-             **{k: arrs[k] for k in ("x", "vel", "stress", "internal_vars", "f_drucker", "displ")})
+             **{k: arrs[k] for k in ("x", "vel", "stress", "internal_vars", "f_drucker", "displ", "rho", "hsml")})
     td.barrier()
     eng.close()
     td.destroy_process_group()
