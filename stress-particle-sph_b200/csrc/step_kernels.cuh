@@ -483,6 +483,21 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
           return o;
         },
         [&](const int(&q)[A_SUB], const int(&pay)[NARR - 1][A_SUB], const RecN(&r)[A_SUB], int nvalid) {
+          if (UMOR && !FIRST) {
+            // full group without a wall partner (the common case): straight-line code, no per-entry predicates
+            bool plain = nvalid >= A_SUB;
+#pragma unroll
+            for (int u = 0; u < A_SUB; ++u) plain = plain && ((q[u] & QID_MASK) < P.nnode);
+            if (plain) {
+#pragma unroll
+              for (int u = 0; u < A_SUB; ++u) {
+                const double h2 = palette_value(mor_u, (unsigned)q[u] >> QCLASS_SHIFT) * (double)__int_as_float(pay[0][u]);
+                vtx = vtx + r[u].v.x * h2;
+                vty = vty + r[u].v.y * h2;
+              }
+              return;
+            }
+          }
 #pragma unroll
           for (int u = 0; u < A_SUB; ++u) {
             const int qid = UMOR ? (q[u] & QID_MASK) : q[u];
@@ -571,6 +586,24 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
           return r;
         },
         [&](const int(&q)[A_SUB], const int(&pay)[NARR - 1][A_SUB], const RecS(&r)[A_SUB], int nvalid) {
+          if (UMOR && !FIRST) {
+            // full group without a wall partner (the common case): straight-line code, no per-entry predicates
+            bool plain = nvalid >= A_SUB;
+#pragma unroll
+            for (int u = 0; u < A_SUB; ++u) plain = plain && ((q[u] & QID_MASK) < P.ntotal);
+            if (plain) {
+#pragma unroll
+              for (int u = 0; u < A_SUB; ++u) {
+                const double h1 = palette_value(mor_u, (unsigned)q[u] >> QCLASS_SHIFT) * (double)__int_as_float(pay[0][u]);
+                t1 = t1 + r[u].s.a * h1;
+                t2 = t2 + r[u].s.b * h1;
+                t3 = t3 + r[u].s.c * h1;
+                t4 = t4 + r[u].s.d * h1;
+                if (EPSP) te = te + r[u].ep * h1;
+              }
+              return;
+            }
+          }
 #pragma unroll
           for (int u = 0; u < A_SUB; ++u) {
             const int qid = UMOR ? (q[u] & QID_MASK) : q[u];
@@ -732,6 +765,17 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
             const double rr = __drcp_rn(r[u].d);
             h1[u] = div_rn(gx * r[u].c, r[u].d, rr);  // dwdx*mass(i)/rho(i), main:514
             h2[u] = div_rn(gy * r[u].c, r[u].d, rr);
+          }
+          if (nvalid >= ELL_SUB) {  // full group: no per-entry predicates
+#pragma unroll
+            for (int u = 0; u < ELL_SUB; ++u) {
+              const double dvx = r[u].a - vp.x, dvy = r[u].b - vp.y;
+              g11 = g11 + dvx * h1[u];
+              g12 = g12 + dvx * h2[u];
+              g21 = g21 + dvy * h1[u];
+              g22 = g22 + dvy * h2[u];
+            }
+            return;
           }
 #pragma unroll
           for (int u = 0; u < ELL_SUB; ++u) {
@@ -989,6 +1033,20 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
 #pragma unroll
             for (int u = 0; u < ELL_SUB; ++u)
               if (u < nvalid) entry_slow(q[u], pay[0][u], pay[1][u], r[u]);
+            return;
+          }
+          if (nvalid >= ELL_SUB) {  // full group: no per-entry predicates
+#pragma unroll
+            for (int u = 0; u < ELL_SUB; ++u) {
+              const double gx = (double)__int_as_float(pay[0][u]), gy = (double)__int_as_float(pay[1][u]);
+              const double c1 = so1 + r[u].a, c2 = so2 + r[u].b, c3 = so3 + r[u].c, mq = r[u].d;
+              a11 = a11 - mq * (gx * c1);
+              a12 = a12 - mq * (gy * c1);
+              a21 = a21 - mq * (gx * c2);
+              a22 = a22 - mq * (gy * c2);
+              a31 = a31 - mq * (gx * c3);
+              a32 = a32 - mq * (gy * c3);
+            }
             return;
           }
 #pragma unroll
