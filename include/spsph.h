@@ -131,6 +131,10 @@ int spsph_dist_unique_id(char *id128);
 int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *id128, const double *planes,
                     int32_t halo_cells, int32_t halo_capacity);
 int spsph_dist_flags(spsph_handle *h, int32_t *flags);
+/* Dynamic re-slabbing (load balance as the material flows): new slab planes for the following steps, the
+ * same array on every rank. The particles whose slab changes travel with the next halo exchange exactly like
+ * migrants, so a plane may move by at most half the halo distance per call (call again after a step for more). */
+int spsph_dist_set_planes(spsph_handle *h, const double *planes);
 /* Row-wise transfer of the TIME-VARYING state (a slab rank moves its slab + halo only instead of the whole problem).
  * ids: n ascending 0-based particle numbers. Every non-NULL array of `s` holds the rows of those particles in that
  * order, with the row width of the full array: x 2, vel 2, stress 4, if_out_domain 1 (n rows); internal_vars 10,

@@ -2166,6 +2166,35 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
 #endif  // SPSPH_HOST_EMU
 }
 
+int spsph_dist_set_planes(spsph_handle *h, const double *planes) {
+#ifndef SPSPH_HOST_EMU
+  if (!h || !planes) return 1;
+  if (!h->dist) {
+    h->err = "spsph_dist_set_planes: not a multi-GPU run";
+    return 1;
+  }
+  DistGeom &D = h->D;
+  const double lo = planes[D.rank], hi = planes[D.rank + 1];
+  // A particle whose slab changes must already sit in the new owner's halo (it travels with the next exchange, as
+  // a migrant does): one call may move a plane by less than the halo distance, keeping a margin of two cells.
+  const double lim = 0.5 * D.H;
+  if ((D.rank > 0 && std::fabs(lo - D.lo) > lim) || (D.rank < D.nranks - 1 && std::fabs(hi - D.hi) > lim)) {
+    h->err = "spsph_dist_set_planes: a slab plane may move by at most half the halo distance per call";
+    return 1;
+  }
+  if (!(lo < hi) || (D.nranks > 2 && D.rank > 0 && D.rank < D.nranks - 1 && (hi - lo) < D.H)) {
+    h->err = "spsph_dist_set_planes: slab thinner than the halo distance";
+    return 1;
+  }
+  D.lo = lo;
+  D.hi = hi;
+  h->halo_prev_valid = false;  // the next messages also carry the particles that change slab: full-capacity transfers
+  return 0;
+#else
+  return 1;
+#endif
+}
+
 int spsph_local_counts(spsph_handle *h, int32_t *nloc3) {
   if (!h || !nloc3) return 1;
   for (int k = 0; k < 3; ++k) nloc3[k] = h->nloc[k];

@@ -140,6 +140,11 @@ module spsph_c_api
        type(c_ptr), value :: h
        integer(c_int64_t), intent(out) :: m_pairs
      end function
+     integer(c_int) function spsph_dist_set_planes(h, planes) bind(C, name="spsph_dist_set_planes")
+       import :: c_ptr, c_int, c_double
+       type(c_ptr), value :: h
+       real(c_double), intent(in) :: planes(*)
+     end function
      integer(c_int) function spsph_upload_rows(h, s, ids, n) bind(C, name="spsph_upload_rows")
        import :: c_ptr, c_int, c_int32_t, spsph_state
        type(c_ptr), value :: h

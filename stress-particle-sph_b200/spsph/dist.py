@@ -125,6 +125,32 @@ def local_ids(problem, plan, rank, x=None):
     return np.flatnonzero(keep).astype(np.int32)
 
 
+def rebalance(planes, owned_counts, H, gain=0.5):
+    """Dynamic re-slabbing: shifts the interior planes towards equal owned velocity-particle counts. planes: current
+    planes (nranks + 1), owned_counts: velocity particles every rank owns now (the same list on every rank, e.g. from
+    an all-gather of Engine.dist_flags() counts). A plane moves by at most 0.4 H per call (spsph_dist_set_planes
+    accepts 0.5 H); the estimate assumes a uniform density inside the two slabs a plane separates."""
+    planes = np.array(planes, dtype=np.float64)
+    n = np.asarray(owned_counts, dtype=np.float64)
+    nr = len(n)
+    new = planes.copy()
+    target = n.sum() / nr
+    excess = 0.0  # particles that should move rightwards across plane r
+    for r in range(1, nr):
+        excess += n[r - 1] - target
+        # width per particle of the slab the plane moves into (the end slabs are unbounded: use their neighbour)
+        src = r - 1 if excess > 0 else r
+        lo, hi = planes[src], planes[src + 1]
+        if not np.isfinite(lo) or not np.isfinite(hi):
+            src = min(max(src + (1 if not np.isfinite(lo) else -1), 1), nr - 2) if nr > 2 else src
+            lo, hi = planes[src], planes[src + 1]
+        if not (np.isfinite(lo) and np.isfinite(hi)) or n[src] <= 0:
+            continue
+        shift = -gain * excess * (hi - lo) / n[src]
+        new[r] = planes[r] + float(np.clip(shift, -0.4 * H, 0.4 * H))
+    return new
+
+
 def merge_owned(per_rank_arrays, per_rank_flags, params):
     """assemble the global state from every rank's download: entry i comes from the rank that owns particle i"""
     out = {k: v.copy() for k, v in per_rank_arrays[0].items()}

@@ -41,6 +41,7 @@ def cuda_lib():
         L.spsph_dist_unique_id.argtypes = [C.c_char_p]
         L.spsph_dist_init.argtypes = [H, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_double), C.c_int32, C.c_int32]
         L.spsph_dist_flags.argtypes = [H, C.c_void_p]
+        L.spsph_dist_set_planes.argtypes = [H, C.POINTER(C.c_double)]
         L.spsph_local_counts.argtypes = [H, C.c_void_p]
         L.spsph_profile.argtypes = [H, C.c_int]
         L.spsph_profile_get.argtypes = [H, C.c_int, C.POINTER(C.c_char_p), C.POINTER(C.c_double), C.POINTER(C.c_int64)]
@@ -54,7 +55,7 @@ def cuda_lib():
 
 EXPORTS = ["spsph_create", "spsph_upload", "spsph_step", "spsph_run", "spsph_download", "spsph_pair_stats",
            "spsph_pairs", "spsph_last_run_ms", "spsph_sync", "spsph_profile", "spsph_profile_get",
-           "spsph_dist_unique_id", "spsph_dist_init", "spsph_dist_flags", "spsph_local_counts", "spsph_get_list_capacity",
+           "spsph_dist_unique_id", "spsph_dist_init", "spsph_dist_flags", "spsph_dist_set_planes", "spsph_local_counts", "spsph_get_list_capacity",
            "spsph_set_list_capacity", "spsph_path_counts", "spsph_upload_rows",
            "spsph_download_rows", "spsph_destroy", "spsph_last_error", "spsph_version"]
 
@@ -168,6 +169,11 @@ class Engine:
         self._chk(self.L.spsph_dist_init(self.h, rank, nranks, bytes(unique_id),
                                          planes.ctypes.data_as(C.POINTER(C.c_double)), int(plan["halo_cells"]),
                                          int(plan["halo_capacity"])))
+
+    def set_planes(self, planes):
+        """new slab planes for the following steps (dynamic re-slabbing; see spsph.dist.rebalance)"""
+        planes = np.ascontiguousarray(planes, dtype=np.float64)
+        self._chk(self.L.spsph_dist_set_planes(self.h, planes.ctypes.data_as(C.POINTER(C.c_double))))
 
     def local_counts(self):
         n = np.zeros(3, np.int32)

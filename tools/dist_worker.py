@@ -21,6 +21,9 @@ def main():
     ap.add_argument("--ncol", type=int, default=0)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--out", required=True)
+    ap.add_argument("--replan", type=int, default=0,
+                    help="every N steps: re-slab (spsph_dist_set_planes); the interior planes are pushed back and forth by "
+                         "0.3 halo distances and then rebalanced on the owned counts (spsph.dist.rebalance)")
     a = ap.parse_args()
     import torch
     import torch.distributed as td
@@ -50,7 +53,22 @@ def main():
     eng = spsph.Engine(prob, device=local)
     eng.dist_init(rank, world, uid[0], plan)
     dt = prob.blocks[0]["dt"]
-    eng.run(1, 0.0, dt, a.steps)
+    if a.replan > 0:
+        planes, t, done, k = np.array(plan["planes"]), 0.0, 0, 0
+        while done < a.steps:
+            n = min(a.replan, a.steps - done)
+            t = eng.run(1 + done, t, dt, n)
+            done += n
+            if done < a.steps:
+                cnt = [None] * world
+                td.all_gather_object(cnt, int((eng.dist_flags()[:prob.params.nnode] == 1).sum()))
+                new = dist.rebalance(planes, cnt, plan["H"])
+                new[1:-1] += (0.3 if k % 2 == 0 else -0.3) * plan["H"] - (new[1:-1] - planes[1:-1])  # forced swing
+                planes = new
+                eng.set_planes(planes)
+                k += 1
+    else:
+        eng.run(1, 0.0, dt, a.steps)
     ms, launches = eng.last_run()
     arrs = eng.download()
     flags = eng.dist_flags()
