@@ -403,3 +403,34 @@ def test_emulated_engine_simt_mode_build_variants(emu_engine_simt_variant, tmp_p
     prob = spsph.load(str(tmp_path), variant)
     run_standalone(emu_engine_simt_variant, prob, nsteps, (1, nsteps), label + ", SIMT emulation, build variant",
                    pairs_at=(1,))
+
+
+TILE_CASES = [("bui", "bui", lambda: _bui(), 5),
+              ("bui_inside_sp2", "bui", lambda: _bui(mode="inside", npoints=2), 3),
+              ("sl", "sl", lambda: _sl(), 3)]
+
+
+@pytest.mark.parametrize("label,variant,spec_fn,nsteps", TILE_CASES, ids=[c[0] for c in TILE_CASES])
+def test_emulated_engine_simt_mode_tile_path(emu_engine_simt, tmp_path, monkeypatch, label, variant, spec_fn, nsteps):
+    """the cell-tile path (csrc/tile_kernels.cuh, SPSPH_TILE=1) on the SIMT emulation: one-pass build with entry codes,
+    shared-memory partner tiles (cp.async = memcpy here), reversed first step and forward steps, walls, XSPH,
+    artificial viscosity, CSPM -- state, ordered pair list (re-created on demand from the id lists) and statistics equal
+    the oracle's bit for bit, and every step really ran on the tile kernels"""
+    import ctypes as C
+    import spsph
+    from spsph import decks
+    monkeypatch.setenv("SPSPH_TILE", "1")
+    decks.write_deck(str(tmp_path), spec_fn())
+    prob = spsph.load(str(tmp_path), variant)
+    counts = []
+    real_engine = emu_engine_simt.Engine
+
+    class Counting(real_engine):
+        def close(self):
+            if getattr(self, "h", None):
+                counts.append(self.path_counts())
+            super().close()
+
+    monkeypatch.setattr(emu_engine_simt, "Engine", Counting)
+    run_standalone(emu_engine_simt, prob, nsteps, (1, nsteps), label + ", SIMT emulation, tile path", pairs_at=(1, 2))
+    assert counts and counts[0] == (nsteps, 0), counts
