@@ -163,3 +163,33 @@ def test_two_slabs_dynamic_reslabbing(tmp_path, deck_dir):
     for k in keys:
         a, b = merged[k][:nt], ref[k][:nt]
         assert np.array_equal(a, b), f"re-slabbing: {k} differs in {int((a != b).sum())} entries"
+
+
+def test_two_slabs_tile_path(tmp_path, deck_dir, monkeypatch):
+    """the cell-tile path (SPSPH_TILE=1) on two slabs: 120 steps of the Bui column, owned particles bit-identical to the
+    single-domain oracle"""
+    if _ngpu() < 2:
+        pytest.skip("needs 2 GPUs")
+    import spsph
+    from spsph import dist
+    from oracle_binding import Oracle
+    monkeypatch.setenv("SPSPH_TILE", "1")
+    out = str(tmp_path / "dist")
+    steps = 120
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr",
+           "127.0.0.1", "--master-port", "29538", os.path.join(ROOT, "tools", "dist_worker.py"), "--kind", "bui",
+           "--steps", str(steps), "--out", out]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    prob = spsph.load(deck_dir("bui"), "bui")
+    orc = Oracle(prob)
+    orc.run(1, 0.0, prob.blocks[0]["dt"], steps)
+    ref = orc.download()
+    ranks = [np.load(os.path.join(out, f"rank{k}.npz")) for k in range(2)]
+    assert int(ranks[0]["tile_steps"]) >= steps - 2, "the slab run did not use the tile kernels"
+    keys = ("x", "vel", "stress", "internal_vars", "f_drucker", "displ")
+    merged = dist.merge_owned([{k: r_[k] for k in keys} for r_ in ranks], [r_["flags"] for r_ in ranks], prob.params)
+    nt = prob.params.ntotal
+    for k in keys:
+        a, b = merged[k][:nt], ref[k][:nt]
+        assert np.array_equal(a, b), f"tile path on two slabs: {k} differs in {int((a != b).sum())} entries"

@@ -74,6 +74,7 @@ def main():
     flags = eng.dist_flags()
     os.makedirs(a.out, exist_ok=True)
     np.savez(os.path.join(a.out, f"rank{rank}.npz"), flags=flags, ms=ms, npairs=eng.pair_stats()["npairs"],
+             tile_steps=eng.path_counts()[0],
              **{k: arrs[k] for k in ("x", "vel", "stress", "internal_vars", "f_drucker", "displ", "rho", "hsml")})
     td.barrier()
     eng.close()
