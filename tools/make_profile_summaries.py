@@ -104,7 +104,20 @@ def kernel_summaries():
 
 
 os.makedirs(dst, exist_ok=True)
-launch_summary()
+if os.path.exists(os.path.join(src, "launches.csv")):
+    launch_summary()
+    print(open(os.path.join(dst, TAG + "_launch_summary.txt")).read())
 kernel_summaries()
-shutil.copy(os.path.join(src, "profile.log"), os.path.join(dst, "r1_event_profile.txt"))
-print(open(os.path.join(dst, TAG + "_launch_summary.txt")).read())
+if os.path.exists(os.path.join(src, "profile.log")):
+    shutil.copy(os.path.join(src, "profile.log"), os.path.join(dst, TAG + "_event_profile.txt"))
+for mode in ("list", "tile"):  # per-kernel metric tables of one step on either path (tools/gpu_metrics_pass.sh)
+    f = os.path.join(src, f"metrics_{mode}.csv")
+    if os.path.exists(f):
+        txt = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "metrics_table.py"), f], capture_output=True,
+                             text=True).stdout
+        which = "id-list path (default)" if mode == "list" else "cell-tile path (SPSPH_TILE=1)"
+        head = (f"{ROUND} -- one ncu metrics pass over every kernel of one time step, {which},\n"
+                "4 002 483-particle refined Bui column, 1 B200 (tools/gpu_metrics_pass.sh; serialised, cold-cache launches).\n"
+                "Minst/l = warp instructions per launch, issue% = issue slots active, warps% = resident warps of 64 per SM,\n"
+                "fp64% = fp64 pipe active, GB/l = DRAM bytes read + written per launch, GB/s = that over the launch time.\n\n")
+        open(os.path.join(dst, f"{TAG}_kernel_metrics_{mode}.txt"), "w").write(head + txt)
