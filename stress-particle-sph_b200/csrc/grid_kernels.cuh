@@ -504,6 +504,9 @@ constexpr int CAND_CAP = 64;
 #ifndef SPSPH_COUNT_MINB
 #define SPSPH_COUNT_MINB 8
 #endif
+#ifndef SPSPH_COUNT_LEAN
+#define SPSPH_COUNT_LEAN 1  // 0: the general candidate loop only (round-2 mid-point kernel, kept for A/B timing)
+#endif
 __global__ void __launch_bounds__(128, SPSPH_COUNT_MINB)
 k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, int *__restrict__ n0, int *__restrict__ n1,
         int *__restrict__ nfwd_u /* unified order */, int *__restrict__ nall, int *__restrict__ w0 /* slice widths */,
@@ -585,6 +588,101 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
           take(sq, q, fthr);
         }
       };
+#if SPSPH_COUNT_LEAN
+      // Lean scan (the common case: fp32 prefilter valid, list-owning particle). The same candidates in the same
+      // order as the general loop below, but the range of one (row | cell, species) is cut beforehand at the
+      // particle itself and at the first forward partner, so that the candidate loop carries no per-candidate
+      // index tests or counters: 4 candidates per trip, classification into predicates, one rare branch for
+      // candidates inside the fp32 uncertainty band, predicated stores. Forward partners are counted by difference.
+      if (pf.on && owner_of_lists) {
+        const float plo = pf.lo, phi = pf.hi;
+        // a group of four goes the careful way when any of its squared distances lies within [plo, phi], tested as
+        // |d2 - pmid| <= phalf with the half-width widened beyond the fp32 rounding of pmid and of the difference
+        const float pmid = 0.5f * (plo + phi), phalf = 0.5f * (phi - plo) * 1.001f + 4.e-6f * phi;
+        for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy) {
+          const RowRange rr = row_range(ndx, cx, jy);
+          const bool merged = (S.start[2][rr.cb + 1] - S.start[2][rr.ca]) == 0;  // no wall particles in this row
+          const int nsq = merged ? 2 : 3;
+          for (int cq0 = rr.ca; cq0 <= rr.cb;) {
+            const int cq1 = merged ? rr.cb : cq0;
+#pragma unroll 1
+            for (int sq = 0; sq < nsq; ++sq) {
+              const int *__restrict__ stq = sq == 0 ? S.start[0] : (sq == 1 ? S.start[1] : S.start[2]);
+              const int b = stq[cq0], e = stq[cq1 + 1];
+              if (b == e) continue;
+              const bool same = sq == sp;
+              int m;  // first forward partner of the range
+              if (jy > cy)
+                m = b;
+              else if (jy < cy)
+                m = e;
+              else
+                m = min(max(same ? k + 1 : (sq > sp ? stq[c] : stq[c + 1]), b), e);
+              const int back_end = (same && jy == cy && k >= b && k < e) ? k : m;  // the particle itself: m == k + 1
+              const float2 *__restrict__ uq = sq == 0 ? S.upos[0] : (sq == 1 ? S.upos[1] : S.upos[2]);
+              int *__restrict__ cp = (same ? cand1 : cand0) + cb;
+              const int tag = same ? 0 : (sq << 30);
+              int cc = same ? c1 : c0;
+              auto exact = [&](int q) {
+                const double2 *__restrict__ pq = sq == 0 ? S.pos[0] : (sq == 1 ? S.pos[1] : S.pos[2]);
+                const double *__restrict__ hq = sq == 0 ? S.h[0] : (sq == 1 ? S.h[1] : S.h[2]);
+                double dx, dy, d2, mh;
+                return pair_accept_fast(sk, pp, hp, pq[q], uni ? hp : hq[q], dx, dy, d2, mh);
+              };
+              auto seg = [&](int lo, int hi) {
+                int q = lo;
+                for (;;) {
+                  // fast groups: four candidates, all of them clear of the uncertainty band
+                  for (; q + 4 <= hi && cc + 4 <= CAND_CAP; q += 4) {
+                    float2 a[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) a[u] = uq[q + u];
+                    float d2[4], off[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                      const float du = up.x - a[u].x, dv = up.y - a[u].y;
+                      d2[u] = __fmaf_rn(du, du, dv * dv);
+                      off[u] = fabsf(d2[u] - pmid);
+                    }
+                    if (fminf(fminf(off[0], off[1]), fminf(off[2], off[3])) <= phalf) break;  // rare: one by one
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                      if (d2[u] < plo) {
+                        cp[(size_t)cc * SLICE] = tag | (q + u);
+                        ++cc;
+                      }
+                  }
+                  if (q >= hi) break;
+                  // up to four candidates one by one: a group that touches the band, the tail of the range, and
+                  // every candidate once the scratch is nearly full
+                  const int qe = min(q + 4, hi);
+#pragma unroll 1
+                  for (; q < qe; ++q) {
+                    const float2 a = uq[q];
+                    const float du = up.x - a.x, dv = up.y - a.y;
+                    const float d2 = __fmaf_rn(du, du, dv * dv);
+                    if (d2 > phi) continue;
+                    if (!(d2 < plo) && !exact(q)) continue;
+                    if (cc < CAND_CAP) cp[(size_t)cc * SLICE] = tag | q;
+                    ++cc;
+                  }
+                }
+              };
+              seg(b, back_end);
+              const int cmid = cc;
+              seg(m, e);
+              cf += cc - cmid;
+              if (same)
+                c1 = cc;
+              else
+                c0 = cc;
+            }
+            cq0 = cq1 + 1;
+          }
+        }
+        ca = c0 + c1;
+      } else
+#endif
       for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy) {
         const RowRange rr = row_range(ndx, cx, jy);
         // forward partners (creation order): later row, or same row from a threshold index on (per species)
