@@ -8,7 +8,11 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <algorithm>
 #include <string>
+#ifndef SPSPH_HOST_EMU
+#include <thread>
+#endif
 #include <type_traits>
 #include <vector>
 
@@ -1401,6 +1405,39 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
 
 }  // namespace
 
+
+// host-side passes over the particles of an upload: a few threads, contiguous chunks in index order
+static int host_threads(size_t n) {
+#ifdef SPSPH_HOST_EMU
+  (void)n;
+  return 1;
+#else
+  if (n < (1u << 18)) return 1;
+  unsigned hw = std::thread::hardware_concurrency();
+  if (hw == 0) hw = 1;
+  if (const char *e = getenv("SPSPH_HOST_THREADS")) hw = (unsigned)std::max(1, atoi(e));
+  return (int)std::min<unsigned>(hw, 8u);
+#endif
+}
+template <class F>
+static void parallel_chunks(size_t n, int nthr, F fn) {
+  const size_t per = (n + nthr - 1) / nthr;
+  auto run = [&](int c) {
+    const size_t i0 = std::min(n, (size_t)c * per), i1 = std::min(n, i0 + per);
+    fn(c, i0, i1);
+  };
+#ifndef SPSPH_HOST_EMU
+  if (nthr > 1) {
+    std::vector<std::thread> th;
+    for (int c = 1; c < nthr; ++c) th.emplace_back(run, c);
+    run(0);
+    for (auto &t : th) t.join();
+    return;
+  }
+#endif
+  for (int c = 0; c < nthr; ++c) run(c);
+}
+
 extern "C" {
 
 const char *spsph_version(void) { return "spsph-b200 0.1 (sm_100a)"; }
@@ -1610,71 +1647,27 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
     return 1;
   }
   CUDA_TRY(cudaSetDevice(h->device));
-  // particle order contract: nodes, stress particles, dummies (mat:961-1026)
-  for (size_t i = 0; i < n2; ++i) {
-    const int want = i < nn ? 2 : (i < nt ? 1 : 25);
-    if (s->itype[i] != want) {
-      h->err = "spsph_upload: itype does not follow the order nodes(2), stress particles(1), dummies(25)";
-      return 1;
-    }
-  }
-  h->h_itype.assign(s->itype, s->itype + n2);
+  // Every plain copy is queued first: the DMA engine works through them while the host analyses the input below
+  // (on an error return the device state is incomplete: the run has to be uploaded again before it can step)
+  h->uploaded = false;
   cudaStream_t st = h->stream;
   auto up = [&](void *d, const void *src, size_t bytes) {
     if (!src) return cudaMemsetAsync(d, 0, bytes, st);
     return cudaMemcpyAsync(d, src, bytes, cudaMemcpyHostToDevice, st);
   };
   CUDA_TRY(up(h->x, s->x, 2 * n2 * 8));
-  CUDA_TRY(up(h->x00, s->x00 ? s->x00 : s->x, 2 * n2 * 8));
+  CUDA_TRY(up(h->hsml, s->hsml, n2 * 8));
+  CUDA_TRY(up(h->if_out, s->if_out_domain, n2 * 4));
   CUDA_TRY(up(h->rho, s->rho, n2 * 8));
   CUDA_TRY(up(h->mass, s->mass, n2 * 8));
-  CUDA_TRY(up(h->hsml, s->hsml, n2 * 8));
-  double hmax = 0.0, hmin = 1.e300;
-  for (size_t i = 0; i < n2; ++i) {
-    hmax = std::fmax(hmax, s->hsml[i]);
-    hmin = std::fmin(hmin, s->hsml[i]);
-  }
-  // hsml only changes on the device with cont_density and sle = 2 (main:709-712)
-  const bool uh = (hmin == hmax && !(h->hp.cont_density && h->hp.sle == 2));
-  if (uh != h->uniform_h) h->capC = 0;  // list C was sized for the other mode
-  h->uniform_h = uh;
-  h->h_uniform = (float)(0.5 * (hmax + hmax));
-  h->uniform_cubic = (h->hp.skf == 1 && uh);
-  if (h->hp.cont_density) CUDA_TRY(cudaMemsetAsync(h->divu, 0, (nt - nn) * sizeof(double), st));  // grad_u = 0, mat:930
-  {  // mass/rho palette per species: sweep A rebuilds (m/rho)*w from the partner's class and the streamed weight
-    bool u = !h->hp.cont_density && nn > 0 && nt > nn && n2 < (size_t)QID_MASK;  // two id bits carry the class
-    std::vector<unsigned char> cls(n2, 0);
-    double pal[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
-    int npal[2] = {0, 0};
-    for (size_t i = 0; u && i < nt; ++i) {
-      const int sp = i < nn ? 0 : 1;
-      const double v = s->mass[i] / s->rho[i];  // the reference's mass(j)/rho(j)
-      int c = 0;
-      while (c < npal[sp] && pal[sp][c] != v) ++c;
-      if (c == npal[sp]) {
-        if (c == 4) {
-          u = false;
-          break;
-        }
-        pal[sp][npal[sp]++] = v;
-      }
-      cls[i] = (unsigned char)c;
-    }
-    if (const char *e = getenv("SPSPH_NO_UMOR")) u = u && atoi(e) == 0;
-    if (u != h->umor) h->cap0 = 0;  // the list-0 arrays were sized for the other mode: start over
-    h->umor = u;
-    h->pal_node = MorPalette{pal[0][0], pal[0][1], pal[0][2], pal[0][3]};
-    h->pal_sp = MorPalette{pal[1][0], pal[1][1], pal[1][2], pal[1][3]};
-    if (u) CUDA_TRY(cudaMemcpyAsync(h->mcls, cls.data(), n2, cudaMemcpyHostToDevice, st));
-    CUDA_TRY(cudaStreamSynchronize(st));  // cls is a local
-  }
-  h->cur = 0;
   CUDA_TRY(up(h->stage_vel, s->vel, 2 * nt * 8));
   CUDA_TRY(up(h->stage_stress, s->stress, 4 * nt * 8));
   CUDA_TRY(up(h->ivars, s->internal_vars, (size_t)SPSPH_NINT_VARS * nt * 8));
   k_upload_derive<<<((int)n2 + 255) / 256, 256, 0, st>>>((int)n2, (int)nt, h->mass, h->rho, h->mor, h->mrho, h->ivars,
                                                           h->epsp);
+  h->cur = 0;
   k_pack_state<<<((int)nt + 255) / 256, 256, 0, st>>>(h->P, h->stage_vel, h->stage_stress, state_ptrs(h, 0));
+  CUDA_TRY(up(h->x00, s->x00 ? s->x00 : s->x, 2 * n2 * 8));
   CUDA_TRY(up(h->fdp, s->f_drucker, nt * 8));
   CUDA_TRY(up(h->displ, s->displ, 2 * nn * 8));
   CUDA_TRY(up(h->x_10, s->x_10 ? s->x_10 : s->x, 2 * nn * 8));
@@ -1683,9 +1676,104 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   CUDA_TRY(up(h->horiz, s->horizontal_or_not, n2 * 4));
   CUDA_TRY(up(h->n_int, s->n_int, nn * 4));
   CUDA_TRY(up(h->bc_int, s->bc_int, nn * 4));
-  CUDA_TRY(up(h->if_out, s->if_out_domain, n2 * 4));
   CUDA_TRY(up(h->bc_or_not, s->bc_or_not, nt * 4));
   CUDA_TRY(up(h->bc_info, s->bc_info, 8 * nt * 4));
+  // Host-side analysis of the input in ONE pass over the particles, on a few threads: the particle order contract
+  // (nodes, stress particles, dummies: mat:961-1026), the range of the smoothing lengths, and the mass/rho palette per
+  // species (sweep A rebuilds (m/rho)*w from the partner's class and the streamed weight). The chunks are merged in
+  // order, so the classes are numbered by first appearance whatever the thread count.
+  struct Chunk {
+    bool bad_itype = false, pal_over = false;
+    double hmax = 0.0, hmin = 1.e300;
+    double pal[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+    int npal[2] = {0, 0};
+  };
+  const bool want_pal = !h->hp.cont_density && nn > 0 && nt > nn && n2 < (size_t)QID_MASK;  // two id bits carry the class
+  const int nthr = host_threads(n2);
+  std::vector<Chunk> chunks(nthr);
+  std::vector<double> mor_h(want_pal ? nt : 0);  // the reference's mass(j)/rho(j), kept for the class pass
+  parallel_chunks(n2, nthr, [&](int c, size_t i0, size_t i1) {
+    Chunk &ck = chunks[c];
+    double lm = 0.0, lr = 0.0, lv = 0.0;  // last quotient: lattice set-ups repeat the same mass and density
+    bool have = false;
+    for (size_t i = i0; i < i1; ++i) {
+      const int want = i < nn ? 2 : (i < nt ? 1 : 25);
+      if (s->itype[i] != want) ck.bad_itype = true;
+      ck.hmax = std::fmax(ck.hmax, s->hsml[i]);
+      ck.hmin = std::fmin(ck.hmin, s->hsml[i]);
+      if (want_pal && i < nt) {
+        const double m = s->mass[i], r = s->rho[i];
+        if (!have || m != lm || r != lr) {
+          lm = m;
+          lr = r;
+          lv = m / r;
+          have = true;
+        }
+        mor_h[i] = lv;
+        if (!ck.pal_over) {
+          const int sp = i < nn ? 0 : 1;
+          int k = 0;
+          while (k < ck.npal[sp] && ck.pal[sp][k] != lv) ++k;
+          if (k == ck.npal[sp]) {
+            if (k == 4)
+              ck.pal_over = true;
+            else
+              ck.pal[sp][ck.npal[sp]++] = lv;
+          }
+        }
+      }
+    }
+  });
+  double hmax = 0.0, hmin = 1.e300;
+  bool u = want_pal;
+  double pal[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
+  int npal[2] = {0, 0};
+  for (const Chunk &ck : chunks) {
+    if (ck.bad_itype) {
+      h->err = "spsph_upload: itype does not follow the order nodes(2), stress particles(1), dummies(25)";
+      return 1;
+    }
+    hmax = std::fmax(hmax, ck.hmax);
+    hmin = std::fmin(hmin, ck.hmin);
+    if (ck.pal_over) u = false;
+    for (int sp = 0; u && sp < 2; ++sp)
+      for (int k = 0; u && k < ck.npal[sp]; ++k) {
+        int j = 0;
+        while (j < npal[sp] && pal[sp][j] != ck.pal[sp][k]) ++j;
+        if (j == npal[sp]) {
+          if (j == 4)
+            u = false;
+          else
+            pal[sp][npal[sp]++] = ck.pal[sp][k];
+        }
+      }
+  }
+  if (!u) std::memset(pal, 0, sizeof(pal));
+  if (const char *e = getenv("SPSPH_NO_UMOR")) u = u && atoi(e) == 0;
+  h->h_itype.assign(s->itype, s->itype + n2);
+  // hsml only changes on the device with cont_density and sle = 2 (main:709-712)
+  const bool uh = (hmin == hmax && !(h->hp.cont_density && h->hp.sle == 2));
+  if (uh != h->uniform_h) h->capC = 0;  // list C was sized for the other mode
+  h->uniform_h = uh;
+  h->h_uniform = (float)(0.5 * (hmax + hmax));
+  h->uniform_cubic = (h->hp.skf == 1 && uh);
+  if (h->hp.cont_density) CUDA_TRY(cudaMemsetAsync(h->divu, 0, (nt - nn) * sizeof(double), st));  // grad_u = 0, mat:930
+  if (u != h->umor) h->cap0 = 0;  // the list-0 arrays were sized for the other mode: start over
+  h->umor = u;
+  h->pal_node = MorPalette{pal[0][0], pal[0][1], pal[0][2], pal[0][3]};
+  h->pal_sp = MorPalette{pal[1][0], pal[1][1], pal[1][2], pal[1][3]};
+  std::vector<unsigned char> cls;  // lives until the final synchronize of this call
+  if (u) {
+    cls.assign(n2, 0);
+    parallel_chunks(nt, nthr, [&](int, size_t i0, size_t i1) {
+      for (size_t i = i0; i < i1; ++i) {
+        const double *pl = pal[i < nn ? 0 : 1];
+        const double v = mor_h[i];
+        cls[i] = (unsigned char)(v == pl[0] ? 0 : (v == pl[1] ? 1 : (v == pl[2] ? 2 : 3)));
+      }
+    });
+    CUDA_TRY(cudaMemcpyAsync(h->mcls, cls.data(), n2, cudaMemcpyHostToDevice, st));
+  }
   CUDA_TRY(cudaStreamSynchronize(st));  // the caller may reuse its arrays as soon as upload returns
   // cell-table capacity: the in-domain bounding box can never exceed the control domain (main:1187-1192)
   if (!h->cell_cnt) {
