@@ -500,6 +500,11 @@ __device__ __forceinline__ RowRange row_range(int ndx, int cx, int jy) {
 // a fixed-capacity scratch (CAND_CAP rows per 32-particle slice) so that the fill pass does not have to search
 // again; a particle with more partners than that raises `overflow` and the step falls back to k_fill_scan.
 constexpr int CAND_CAP = 64;
+// Scratch layout: four consecutive entries of a lane form one 16-byte group, the groups of a slice's 32 lanes side by
+// side (k_fill reads a whole group with one coalesced 16-byte load per lane and requests the next group one trip
+// ahead). Offsets are relative to cand_base(t).
+__host__ __device__ __forceinline__ size_t cand_base(int t) { return (size_t)(t / SLICE) * CAND_CAP * SLICE + (size_t)(t & 31) * 4; }
+__host__ __device__ __forceinline__ size_t cand_off(int c) { return ((size_t)(c >> 2) << 7) + (size_t)(c & 3); }
 
 #ifndef SPSPH_COUNT_MINB
 #define SPSPH_COUNT_MINB 8
@@ -537,17 +542,17 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
       const float2 up = uposp[k];
       const int ndx = G->ndivx[0], ndy = G->ndivx[1];
       const int cy = c / ndx, cx = c - cy * ndx;
-      const size_t cb = (size_t)(t / SLICE) * CAND_CAP * SLICE + (t & 31);
+      const size_t cb = cand_base(t);
       const bool owner_of_lists = sp != SP_DUMMY;
       auto take = [&](int sq, int q, int fthr) {  // accepted partner, in list order
         ++ca;
         cf += (q >= fthr) ? 1 : 0;
         if (owner_of_lists) {
           if (sq == sp) {
-            if (c1 < CAND_CAP) cand1[cb + (size_t)c1 * SLICE] = q;
+            if (c1 < CAND_CAP) cand1[cb + cand_off(c1)] = q;
             ++c1;
           } else {  // node<->stress (type 1) and node/stress<->dummy (types 6, 9)
-            if (c0 < CAND_CAP) cand0[cb + (size_t)c0 * SLICE] = (sq << 30) | q;
+            if (c0 < CAND_CAP) cand0[cb + cand_off(c0)] = (sq << 30) | q;
             ++c0;
           }
         }
@@ -629,18 +634,29 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
                 double dx, dy, d2, mh;
                 return pair_accept_fast(sk, pp, hp, pq[q], uni ? hp : hq[q], dx, dy, d2, mh);
               };
+              auto one = [&](int q) {  // one candidate, the careful way
+                const float2 a = uq[q];
+                const float du = up.x - a.x, dv = up.y - a.y;
+                const float d2 = __fmaf_rn(du, du, dv * dv);
+                if (d2 > phi) return;
+                if (!(d2 < plo) && !exact(q)) return;
+                if (cc < CAND_CAP) cp[cand_off(cc)] = tag | q;
+                ++cc;
+              };
               auto seg = [&](int lo, int hi) {
                 int q = lo;
+                // candidates come in 16-byte pairs: start on a pair boundary
+                if (q < hi && (reinterpret_cast<size_t>(uq + q) & 8)) one(q++);
                 for (;;) {
                   // fast groups: four candidates, all of them clear of the uncertainty band
                   for (; q + 4 <= hi && cc + 4 <= CAND_CAP; q += 4) {
-                    float2 a[4];
-#pragma unroll
-                    for (int u = 0; u < 4; ++u) a[u] = uq[q + u];
+                    const float4 a01 = *reinterpret_cast<const float4 *>(uq + q);
+                    const float4 a23 = *reinterpret_cast<const float4 *>(uq + q + 2);
+                    const float ax[4] = {a01.x, a01.z, a23.x, a23.z}, ay[4] = {a01.y, a01.w, a23.y, a23.w};
                     float d2[4], off[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
-                      const float du = up.x - a[u].x, dv = up.y - a[u].y;
+                      const float du = up.x - ax[u], dv = up.y - ay[u];
                       d2[u] = __fmaf_rn(du, du, dv * dv);
                       off[u] = fabsf(d2[u] - pmid);
                     }
@@ -648,7 +664,7 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                       if (d2[u] < plo) {
-                        cp[(size_t)cc * SLICE] = tag | (q + u);
+                        cp[cand_off(cc)] = tag | (q + u);
                         ++cc;
                       }
                   }
@@ -657,15 +673,7 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
                   // every candidate once the scratch is nearly full
                   const int qe = min(q + 4, hi);
 #pragma unroll 1
-                  for (; q < qe; ++q) {
-                    const float2 a = uq[q];
-                    const float du = up.x - a.x, dv = up.y - a.y;
-                    const float d2 = __fmaf_rn(du, du, dv * dv);
-                    if (d2 > phi) continue;
-                    if (!(d2 < plo) && !exact(q)) continue;
-                    if (cc < CAND_CAP) cp[(size_t)cc * SLICE] = tag | q;
-                    ++cc;
-                  }
+                  for (; q < qe; ++q) one(q);
                 }
               };
               seg(b, back_end);
@@ -1070,7 +1078,7 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
   const int lane = t & 31, sl = t / SLICE;
   const size_t o0 = (size_t)L.off0[sl] + lane;
   const size_t o1 = (size_t)(sp == SP_NODE ? L.offC[sl] : L.offD[sl]) + lane;
-  const size_t cb = (size_t)sl * CAND_CAP * SLICE + lane;
+  const size_t cb = cand_base(t);
   const double2 pp = posp[k];
   const double hp = hpp[k];
   const bool uni = UNIFORM || G->uniform_h != 0;
@@ -1083,23 +1091,32 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
       s0 = 0;
       s1 = 0;
       for (int e = 0; e < cnt0; ++e) {
-        const int pk = cand0[cb + (size_t)e * SLICE];
+        const int pk = cand0[cb + cand_off(e)];
         s0 += pair_is_old(gr, up, sorted_key(S, (int)((unsigned)pk >> 30), pk & 0x3fffffff)) ? 1 : 0;
       }
-      for (int e = 0; e < cnt1; ++e) s1 += pair_is_old(gr, up, sorted_key(S, sp, cand1[cb + (size_t)e * SLICE])) ? 1 : 0;
+      for (int e = 0; e < cnt1; ++e) s1 += pair_is_old(gr, up, sorted_key(S, sp, cand1[cb + cand_off(e)])) ? 1 : 0;
     }
   }
   constexpr int U = SPSPH_FILL_U;
+  static_assert(4 % U == 0, "a 16-byte group of the candidate scratch is consumed in whole parts");
   int has_dummy = 0;
   // list 0: cross-species partners, reference orientation of the gradient (pair_i - pair_j after Pint_Update)
-  for (int e0 = 0; e0 < cnt0; e0 += U) {
+  const int4 *__restrict__ g0 = reinterpret_cast<const int4 *>(cand0 + cb);  // group g of this lane at g0[32 * g]
+  int4 nx0 = cnt0 > 0 ? g0[0] : make_int4(0, 0, 0, 0);
+  for (int eg = 0; eg < cnt0; eg += 4) {
+    const int4 cur = nx0;
+    if (eg + 4 < cnt0) nx0 = g0[(size_t)((eg >> 2) + 1) * SLICE];  // requested one trip ahead
+    const int pk4[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+   for (int hh = 0; hh < 4; hh += U) {
+    const int e0 = eg + hh;
+    if (e0 >= cnt0) break;
     int sq[U], q[U], qid[U];
     double2 pq[U];
     double hq[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int e = min(e0 + u, cnt0 - 1);
-      const int pk = cand0[cb + (size_t)e * SLICE];
+      const int pk = (e0 + u < cnt0) ? pk4[hh + u] : pk4[hh];  // past the end: repeat a valid entry (not stored)
       sq[u] = (int)((unsigned)pk >> 30);
       q[u] = pk & 0x3fffffff;
     }
@@ -1147,14 +1164,24 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
       L.gy0[a] = (float)gy[u];
       if (sq[u] == SP_DUMMY) has_dummy = 1;
     }
+   }
   }
   // list C / D: same-species partners, own-perspective gradient (nodes) or weight only (stress particles)
-  for (int e0 = 0; e0 < cnt1; e0 += U) {
+  const int4 *__restrict__ g1 = reinterpret_cast<const int4 *>(cand1 + cb);
+  int4 nx1 = cnt1 > 0 ? g1[0] : make_int4(0, 0, 0, 0);
+  for (int eg = 0; eg < cnt1; eg += 4) {
+    const int4 cur = nx1;
+    if (eg + 4 < cnt1) nx1 = g1[(size_t)((eg >> 2) + 1) * SLICE];
+    const int pk4[4] = {cur.x, cur.y, cur.z, cur.w};
+#pragma unroll
+   for (int hh = 0; hh < 4; hh += U) {
+    const int e0 = eg + hh;
+    if (e0 >= cnt1) break;
     int q[U], qid[U];
     double2 pq[U];
     double hq[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) q[u] = cand1[cb + (size_t)min(e0 + u, cnt1 - 1) * SLICE];
+    for (int u = 0; u < U; ++u) q[u] = (e0 + u < cnt1) ? pk4[hh + u] : pk4[hh];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       pq[u] = posp[q[u]];
@@ -1202,6 +1229,7 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
         L.wD[a] = (float)w[u];
       }
     }
+   }
   }
   if (sp == SP_NODE) bc_int[id] = has_dummy;  // main:506,579
 }
