@@ -500,11 +500,11 @@ __device__ __forceinline__ RowRange row_range(int ndx, int cx, int jy) {
 // a fixed-capacity scratch (CAND_CAP rows per 32-particle slice) so that the fill pass does not have to search
 // again; a particle with more partners than that raises `overflow` and the step falls back to k_fill_scan.
 constexpr int CAND_CAP = 64;
-// Scratch layout: four consecutive entries of a lane form one 16-byte group, the groups of a slice's 32 lanes side by
-// side (k_fill reads a whole group with one coalesced 16-byte load per lane and requests the next group one trip
-// ahead). Offsets are relative to cand_base(t).
-__host__ __device__ __forceinline__ size_t cand_base(int t) { return (size_t)(t / SLICE) * CAND_CAP * SLICE + (size_t)(t & 31) * 4; }
-__host__ __device__ __forceinline__ size_t cand_off(int c) { return ((size_t)(c >> 2) << 7) + (size_t)(c & 3); }
+// Scratch layout: entry c of lane l of a slice at row c, column l (the lanes of a warp that append at the same time
+// share a 128-byte row; measured: 16-byte groups per lane cost k_count +0.6 ms in scattered 4-byte stores for -0.1 ms
+// in k_fill). Offsets are relative to cand_base(t).
+__host__ __device__ __forceinline__ size_t cand_base(int t) { return (size_t)(t / SLICE) * CAND_CAP * SLICE + (size_t)(t & 31); }
+__host__ __device__ __forceinline__ size_t cand_off(int c) { return (size_t)c * SLICE; }
 
 #ifndef SPSPH_COUNT_MINB
 #define SPSPH_COUNT_MINB 8
@@ -1098,27 +1098,24 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
     }
   }
   constexpr int U = SPSPH_FILL_U;
-  static_assert(4 % U == 0, "a 16-byte group of the candidate scratch is consumed in whole parts");
   int has_dummy = 0;
   // list 0: cross-species partners, reference orientation of the gradient (pair_i - pair_j after Pint_Update)
-  const int4 *__restrict__ g0 = reinterpret_cast<const int4 *>(cand0 + cb);  // group g of this lane at g0[32 * g]
-  int4 nx0 = cnt0 > 0 ? g0[0] : make_int4(0, 0, 0, 0);
-  for (int eg = 0; eg < cnt0; eg += 4) {
-    const int4 cur = nx0;
-    if (eg + 4 < cnt0) nx0 = g0[(size_t)((eg >> 2) + 1) * SLICE];  // requested one trip ahead
-    const int pk4[4] = {cur.x, cur.y, cur.z, cur.w};
+  // the entries of the next trip are requested before this trip's arithmetic (the scratch comes from DRAM)
+  int pkn[U];
 #pragma unroll
-   for (int hh = 0; hh < 4; hh += U) {
-    const int e0 = eg + hh;
-    if (e0 >= cnt0) break;
+  for (int u = 0; u < U; ++u) pkn[u] = cnt0 > 0 ? cand0[cb + cand_off(min(u, cnt0 - 1))] : 0;
+  for (int e0 = 0; e0 < cnt0; e0 += U) {
     int sq[U], q[U], qid[U];
     double2 pq[U];
     double hq[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const int pk = (e0 + u < cnt0) ? pk4[hh + u] : pk4[hh];  // past the end: repeat a valid entry (not stored)
-      sq[u] = (int)((unsigned)pk >> 30);
-      q[u] = pk & 0x3fffffff;
+      sq[u] = (int)((unsigned)pkn[u] >> 30);
+      q[u] = pkn[u] & 0x3fffffff;
+    }
+    if (e0 + U < cnt0) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) pkn[u] = cand0[cb + cand_off(min(e0 + U + u, cnt0 - 1))];
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -1164,24 +1161,20 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
       L.gy0[a] = (float)gy[u];
       if (sq[u] == SP_DUMMY) has_dummy = 1;
     }
-   }
   }
   // list C / D: same-species partners, own-perspective gradient (nodes) or weight only (stress particles)
-  const int4 *__restrict__ g1 = reinterpret_cast<const int4 *>(cand1 + cb);
-  int4 nx1 = cnt1 > 0 ? g1[0] : make_int4(0, 0, 0, 0);
-  for (int eg = 0; eg < cnt1; eg += 4) {
-    const int4 cur = nx1;
-    if (eg + 4 < cnt1) nx1 = g1[(size_t)((eg >> 2) + 1) * SLICE];
-    const int pk4[4] = {cur.x, cur.y, cur.z, cur.w};
 #pragma unroll
-   for (int hh = 0; hh < 4; hh += U) {
-    const int e0 = eg + hh;
-    if (e0 >= cnt1) break;
+  for (int u = 0; u < U; ++u) pkn[u] = cnt1 > 0 ? cand1[cb + cand_off(min(u, cnt1 - 1))] : 0;
+  for (int e0 = 0; e0 < cnt1; e0 += U) {
     int q[U], qid[U];
     double2 pq[U];
     double hq[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) q[u] = (e0 + u < cnt1) ? pk4[hh + u] : pk4[hh];
+    for (int u = 0; u < U; ++u) q[u] = pkn[u];
+    if (e0 + U < cnt1) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) pkn[u] = cand1[cb + cand_off(min(e0 + U + u, cnt1 - 1))];
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       pq[u] = posp[q[u]];
@@ -1229,7 +1222,6 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
         L.wD[a] = (float)w[u];
       }
     }
-   }
   }
   if (sp == SP_NODE) bc_int[id] = has_dummy;  // main:506,579
 }
