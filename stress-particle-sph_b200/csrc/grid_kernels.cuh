@@ -496,28 +496,27 @@ __device__ __forceinline__ RowRange row_range(int ndx, int cx, int jy) {
 }
 
 // Count pass: per thread slot the lengths of its gather lists, its forward pair count (creation index) and its
-// total interaction count (countiac, main:1355-1356). The accepted partners are recorded as ACCEPTANCE MASKS: one
-// 64-bit word per (stencil row, partner species) over the row's contiguous candidate range of that species
-// (bit j = candidate b + j accepted, the particle itself excluded), 72 bytes per particle, written with coalesced
-// 8-byte stores. The fill pass walks the set bits in the reference's (cell, species, index) order, so it neither
-// searches again nor reads a per-entry scratch (round-2 mid-point: a 4-byte-per-entry scratch, whose scattered
-// stores bound this kernel). A row range with more than 64 candidates raises `overflow` (counts stay exact) and
-// the step falls back to k_fill_scan.
-constexpr int NMASK = 9;        // (stencil row 0..2) x (partner species 0..2)
-constexpr int MASK_BITS = 64;
-__host__ __device__ __forceinline__ size_t mask_base(int t) { return (size_t)(t / SLICE) * NMASK * SLICE + (size_t)(t & 31); }
-__device__ __forceinline__ unsigned long long bits_from(int f) {  // bits f.. of a 64-bit word (f >= 64: none)
-  return f >= MASK_BITS ? 0ull : (~0ull << (f < 0 ? 0 : f));
-}
+// total interaction count (countiac, main:1355-1356). The accepted partners are also recorded, in list order, in
+// a fixed-capacity scratch (CAND_CAP rows per 32-particle slice) so that the fill pass does not have to search
+// again; a particle with more partners than that raises `overflow` and the step falls back to k_fill_scan.
+constexpr int CAND_CAP = 64;
+// Scratch layout: entry c of lane l of a slice at row c, column l (the lanes of a warp that append at the same time
+// share a 128-byte row; measured: 16-byte groups per lane cost k_count +0.6 ms in scattered 4-byte stores for -0.1 ms
+// in k_fill). Offsets are relative to cand_base(t).
+__host__ __device__ __forceinline__ size_t cand_base(int t) { return (size_t)(t / SLICE) * CAND_CAP * SLICE + (size_t)(t & 31); }
+__host__ __device__ __forceinline__ size_t cand_off(int c) { return (size_t)c * SLICE; }
 
 #ifndef SPSPH_COUNT_MINB
 #define SPSPH_COUNT_MINB 8
 #endif
+#ifndef SPSPH_COUNT_LEAN
+#define SPSPH_COUNT_LEAN 1  // 0: the general candidate loop only (round-2 mid-point kernel, kept for A/B timing)
+#endif
 __global__ void __launch_bounds__(128, SPSPH_COUNT_MINB)
 k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, int *__restrict__ n0, int *__restrict__ n1,
         int *__restrict__ nfwd_u /* unified order */, int *__restrict__ nall, int *__restrict__ w0 /* slice widths */,
-        int *__restrict__ wC, int *__restrict__ wD, const int *__restrict__ lflag,
-        unsigned long long *__restrict__ masks, int *__restrict__ overflow, const int *__restrict__ nout, int t0, int tn) {
+        int *__restrict__ wC, int *__restrict__ wD, const int *__restrict__ lflag, int *__restrict__ cand0,
+        int *__restrict__ cand1, int *__restrict__ overflow, const int *__restrict__ nout, int t0, int tn) {
   // slots [t0, t0 + tn): all of them on a single GPU; on a slab one launch per species over the leading slots that
   // can hold local particles (slices that are not visited keep the zero width of the host memset)
   const int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
@@ -543,59 +542,114 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
       const float2 up = uposp[k];
       const int ndx = G->ndivx[0], ndy = G->ndivx[1];
       const int cy = c / ndx, cx = c - cy * ndx;
+      const size_t cb = cand_base(t);
       const bool owner_of_lists = sp != SP_DUMMY;
-      const size_t mb = mask_base(t);
-      const float plo = pf.lo, phi = pf.hi;
-      // a group of four goes the careful way when any of its squared distances lies within [plo, phi], tested as
-      // |d2 - pmid| <= phalf with the half-width widened beyond the fp32 rounding of pmid and of the difference
-      const float pmid = 0.5f * (plo + phi), phalf = 0.5f * (phi - plo) * 1.001f + 4.e-6f * phi;
-      int over = 0;
-      for (int jr = 0; jr < 3; ++jr) {
-        const int jy = cy - 1 + jr;
-        const bool row_ok = jy >= 0 && jy < ndy;
-        const RowRange rr = row_range(ndx, cx, row_ok ? jy : cy);
+      auto take = [&](int sq, int q, int fthr) {  // accepted partner, in list order
+        ++ca;
+        cf += (q >= fthr) ? 1 : 0;
+        if (owner_of_lists) {
+          if (sq == sp) {
+            if (c1 < CAND_CAP) cand1[cb + cand_off(c1)] = q;
+            ++c1;
+          } else {  // node<->stress (type 1) and node/stress<->dummy (types 6, 9)
+            if (c0 < CAND_CAP) cand0[cb + cand_off(c0)] = (sq << 30) | q;
+            ++c0;
+          }
+        }
+      };
+      auto scan = [&](int sq, int b, int e, int fthr) {
+        const float2 *__restrict__ uq = sq == 0 ? S.upos[0] : (sq == 1 ? S.upos[1] : S.upos[2]);
+        const double2 *__restrict__ pq = sq == 0 ? S.pos[0] : (sq == 1 ? S.pos[1] : S.pos[2]);
+        const double *__restrict__ hq = sq == 0 ? S.h[0] : (sq == 1 ? S.h[1] : S.h[2]);
+        auto exact = [&](int q) {
+          double dx, dy, d2, mh;
+          return pair_accept_fast(sk, pp, hp, pq[q], uni ? hp : hq[q], dx, dy, d2, mh);
+        };
+        int q = b;
+        if (pf.on) {
+          // four candidates per iteration: independent loads, one combined "anything to do" test
+          for (; q + 4 <= e; q += 4) {
+            float2 u4[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) u4[u] = uq[q + u];
+            int cls[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) cls[u] = prefilter_test(pf, up, u4[u]);
+            if ((cls[0] | cls[1] | cls[2] | cls[3]) == 0) continue;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              if (cls[u] == 0 || (sq == sp && q + u == k)) continue;
+              if (cls[u] == 2 && !exact(q + u)) continue;
+              take(sq, q + u, fthr);
+            }
+          }
+        }
+        for (; q < e; ++q) {
+          if (sq == sp && q == k) continue;
+          int cls = 2;
+          if (pf.on) cls = prefilter_test(pf, up, uq[q]);
+          if (cls == 0) continue;
+          if (cls == 2 && !exact(q)) continue;
+          take(sq, q, fthr);
+        }
+      };
+#if SPSPH_COUNT_LEAN
+      // Lean scan (the common case: fp32 prefilter valid, list-owning particle). The same candidates in the same
+      // order as the general loop below, but the range of one (row | cell, species) is cut beforehand at the
+      // particle itself and at the first forward partner, so that the candidate loop carries no per-candidate
+      // index tests or counters: 4 candidates per trip, classification into predicates, one rare branch for
+      // candidates inside the fp32 uncertainty band, predicated stores. Forward partners are counted by difference.
+      if (pf.on && owner_of_lists) {
+        const float plo = pf.lo, phi = pf.hi;
+        // a group of four goes the careful way when any of its squared distances lies within [plo, phi], tested as
+        // |d2 - pmid| <= phalf with the half-width widened beyond the fp32 rounding of pmid and of the difference
+        const float pmid = 0.5f * (plo + phi), phalf = 0.5f * (phi - plo) * 1.001f + 4.e-6f * phi;
+        for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy) {
+          const RowRange rr = row_range(ndx, cx, jy);
+          const bool merged = (S.start[2][rr.cb + 1] - S.start[2][rr.ca]) == 0;  // no wall particles in this row
+          const int nsq = merged ? 2 : 3;
+          for (int cq0 = rr.ca; cq0 <= rr.cb;) {
+            const int cq1 = merged ? rr.cb : cq0;
 #pragma unroll 1
-        for (int sq = 0; sq < 3; ++sq) {
-          unsigned long long mk0 = 0;  // the mask that is stored: the first 64 candidates of the range
-          if (row_ok) {
-            const int *__restrict__ stq = sq == 0 ? S.start[0] : (sq == 1 ? S.start[1] : S.start[2]);
-            const int b = stq[rr.ca], e = stq[rr.cb + 1];
-            if (e - b > MASK_BITS) over = 1;
-            const bool same = sq == sp;
-            // forward partners (creation order): later row, or same row from a threshold index on (per species)
-            int f;
-            if (jy > cy)
-              f = b;
-            else if (jy < cy)
-              f = e;
-            else
-              f = same ? k + 1 : (sq > sp ? stq[c] : stq[c + 1]);
-            const float2 *__restrict__ uq = sq == 0 ? S.upos[0] : (sq == 1 ? S.upos[1] : S.upos[2]);
-            auto exact = [&](int q) {
-              const double2 *__restrict__ pq = sq == 0 ? S.pos[0] : (sq == 1 ? S.pos[1] : S.pos[2]);
-              const double *__restrict__ hq = sq == 0 ? S.h[0] : (sq == 1 ? S.h[1] : S.h[2]);
-              double dx, dy, d2, mh;
-              return pair_accept_fast(sk, pp, hp, pq[q], uni ? hp : hq[q], dx, dy, d2, mh);
-            };
-#pragma unroll 1
-            for (int b0 = b; b0 < e; b0 += MASK_BITS) {  // one trip, unless the range overflows a mask
-              const int e0 = min(e, b0 + MASK_BITS);
-              unsigned long long mk = 0;
-              int q = b0;
-              if (pf.on) {
-                auto one = [&](int qq) {  // one candidate, the careful way
-                  const float2 a = uq[qq];
-                  const float du = up.x - a.x, dv = up.y - a.y;
-                  const float d2 = __fmaf_rn(du, du, dv * dv);
-                  if (d2 > phi) return;
-                  if (!(d2 < plo) && !exact(qq)) return;
-                  mk |= 1ull << (qq - b0);
-                };
+            for (int sq = 0; sq < nsq; ++sq) {
+              const int *__restrict__ stq = sq == 0 ? S.start[0] : (sq == 1 ? S.start[1] : S.start[2]);
+              const int b = stq[cq0], e = stq[cq1 + 1];
+              if (b == e) continue;
+              const bool same = sq == sp;
+              int m;  // first forward partner of the range
+              if (jy > cy)
+                m = b;
+              else if (jy < cy)
+                m = e;
+              else
+                m = min(max(same ? k + 1 : (sq > sp ? stq[c] : stq[c + 1]), b), e);
+              const int back_end = (same && jy == cy && k >= b && k < e) ? k : m;  // the particle itself: m == k + 1
+              const float2 *__restrict__ uq = sq == 0 ? S.upos[0] : (sq == 1 ? S.upos[1] : S.upos[2]);
+              int *__restrict__ cp = (same ? cand1 : cand0) + cb;
+              const int tag = same ? 0 : (sq << 30);
+              int cc = same ? c1 : c0;
+              auto exact = [&](int q) {
+                const double2 *__restrict__ pq = sq == 0 ? S.pos[0] : (sq == 1 ? S.pos[1] : S.pos[2]);
+                const double *__restrict__ hq = sq == 0 ? S.h[0] : (sq == 1 ? S.h[1] : S.h[2]);
+                double dx, dy, d2, mh;
+                return pair_accept_fast(sk, pp, hp, pq[q], uni ? hp : hq[q], dx, dy, d2, mh);
+              };
+              auto one = [&](int q) {  // one candidate, the careful way
+                const float2 a = uq[q];
+                const float du = up.x - a.x, dv = up.y - a.y;
+                const float d2 = __fmaf_rn(du, du, dv * dv);
+                if (d2 > phi) return;
+                if (!(d2 < plo) && !exact(q)) return;
+                if (cc < CAND_CAP) cp[cand_off(cc)] = tag | q;
+                ++cc;
+              };
+              auto seg = [&](int lo, int hi) {
+                int q = lo;
                 // candidates come in 16-byte pairs: start on a pair boundary
-                if (q < e0 && (reinterpret_cast<size_t>(uq + q) & 8)) one(q++);
+                if (q < hi && (reinterpret_cast<size_t>(uq + q) & 8)) one(q++);
                 for (;;) {
                   // fast groups: four candidates, all of them clear of the uncertainty band
-                  for (; q + 4 <= e0; q += 4) {
+                  for (; q + 4 <= hi && cc + 4 <= CAND_CAP; q += 4) {
                     const float4 a01 = *reinterpret_cast<const float4 *>(uq + q);
                     const float4 a23 = *reinterpret_cast<const float4 *>(uq + q + 2);
                     const float ax[4] = {a01.x, a01.z, a23.x, a23.z}, ay[4] = {a01.y, a01.w, a23.y, a23.w};
@@ -607,36 +661,65 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
                       off[u] = fabsf(d2[u] - pmid);
                     }
                     if (fminf(fminf(off[0], off[1]), fminf(off[2], off[3])) <= phalf) break;  // rare: one by one
-                    unsigned nib = 0;
 #pragma unroll
-                    for (int u = 0; u < 4; ++u) nib |= ((unsigned)__float_as_int(d2[u] - plo) >> 31) << u;  // d2 < plo
-                    mk |= (unsigned long long)nib << (q - b0);
+                    for (int u = 0; u < 4; ++u)
+                      if (d2[u] < plo) {
+                        cp[cand_off(cc)] = tag | (q + u);
+                        ++cc;
+                      }
                   }
-                  if (q >= e0) break;
-                  // up to four candidates one by one: a group that touches the band, or the tail of the range
-                  const int qe = min(q + 4, e0);
+                  if (q >= hi) break;
+                  // up to four candidates one by one: a group that touches the band, the tail of the range, and
+                  // every candidate once the scratch is nearly full
+                  const int qe = min(q + 4, hi);
 #pragma unroll 1
                   for (; q < qe; ++q) one(q);
                 }
-              } else {
-                for (; q < e0; ++q)
-                  if (exact(q)) mk |= 1ull << (q - b0);
-              }
-              if (same && k >= b0 && k < e0) mk &= ~(1ull << (k - b0));  // the particle itself
-              const int cnt = __popcll(mk);
+              };
+              seg(b, back_end);
+              const int cmid = cc;
+              seg(m, e);
+              cf += cc - cmid;
               if (same)
-                c1 += cnt;
+                c1 = cc;
               else
-                c0 += cnt;
-              cf += __popcll(mk & bits_from(f - b0));
-              if (b0 == b) mk0 = mk;
+                c0 = cc;
             }
+            cq0 = cq1 + 1;
           }
-          if (owner_of_lists) masks[mb + (size_t)(jr * 3 + sq) * SLICE] = mk0;
+        }
+        ca = c0 + c1;
+      } else
+#endif
+      for (int jy = max(cy - 1, 0); jy <= min(cy + 1, ndy - 1); ++jy) {
+        const RowRange rr = row_range(ndx, cx, jy);
+        // forward partners (creation order): later row, or same row from a threshold index on (per species)
+        int fthr[3];
+#pragma unroll
+        for (int sq = 0; sq < 3; ++sq) {
+          if (jy > cy)
+            fthr[sq] = S.start[sq][rr.ca];
+          else if (jy < cy)
+            fthr[sq] = S.start[sq][rr.cb + 1];
+          else
+            fthr[sq] = (sq == sp) ? k + 1 : (sq > sp ? S.start[sq][c] : S.start[sq][c + 1]);
+        }
+        const int nd_row = S.start[2][rr.cb + 1] - S.start[2][rr.ca];
+        if (nd_row == 0) {
+          // no wall particles in this row: every list takes partners of a single species, whose order
+          // (cell id, particle index) is the order of the merged range
+          scan(0, S.start[0][rr.ca], S.start[0][rr.cb + 1], fthr[0]);
+          scan(1, S.start[1][rr.ca], S.start[1][rr.cb + 1], fthr[1]);
+        } else {
+          // wall particles interleave with the other species cell by cell: (cell id, species, index) order
+          for (int cq = rr.ca; cq <= rr.cb; ++cq) {
+            scan(0, S.start[0][cq], S.start[0][cq + 1], fthr[0]);
+            scan(1, S.start[1][cq], S.start[1][cq + 1], fthr[1]);
+            scan(2, S.start[2][cq], S.start[2][cq + 1], fthr[2]);
+          }
         }
       }
-      ca = c0 + c1;
-      if (over) *overflow = 1;
+      if (c0 > CAND_CAP || c1 > CAND_CAP) *overflow = 1;
       // creation index / statistics count every pair once: at the owner of its earlier member
       const bool owned = !lflag || lflag[(sp == 0 ? S.order[0] : (sp == 1 ? S.order[1] : S.order[2]))[k]] == 1;
       nfwd_u[unified_slot(S, c, sp, k)] = owned ? cf : 0;
@@ -959,92 +1042,8 @@ k_fill_scan(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
   if (sp == SP_NODE) bc_int[id] = has_dummy;  // main:506,579
 }
 
-// Walk over the accepted partners of one gather list, in the reference's (cell id, species, index) order, from the
-// acceptance masks of k_count. LIST0: the cross-species partners (the other moving species, plus wall particles,
-// which interleave with it cell by cell); otherwise the same-species partners. next() returns (species << 30) |
-// species-sorted index; the caller knows the list length (n0 / n1) and never asks for more.
-struct MaskWalk {
-  const unsigned long long *mrow;  // this lane's masks: word (jr * 3 + sq) at mrow[(jr * 3 + sq) * SLICE]
-  const int *st_a, *st_d;          // cell tables of the list's moving species and of the wall particles
-  int ndx, ndy, cx, cy, sq_a;
-  bool with_walls;                 // LIST0
-  int jr, sub;                     // current stencil row; LIST0 rows with wall partners: sub-run 0..5 = (cell, a | wall)
-  unsigned long long cur;          // bits still to deliver of the current run
-  int base, tag;                   // index of bit 0, species tag of the current run
-  unsigned long long ma, md;       // the current row's masks (moving species, walls)
-  int ba, bd;                      // their first candidates
-  RowRange rr;
-  bool split;                      // the current row is delivered cell by cell
-
-  __device__ __forceinline__ void init(const unsigned long long *m, const SortArrays &S, int ndx_, int ndy_, int cx_,
-                                       int cy_, int sq_a_, bool list0) {
-    mrow = m;
-    sq_a = sq_a_;
-    st_a = sq_a == 0 ? S.start[0] : S.start[1];
-    st_d = S.start[2];
-    ndx = ndx_;
-    ndy = ndy_;
-    cx = cx_;
-    cy = cy_;
-    with_walls = list0;
-    jr = -1;
-    sub = 0;
-    cur = 0;
-    base = 0;
-    tag = 0;
-    split = false;
-    ma = md = 0;
-    ba = bd = 0;
-    rr = RowRange{0, 0};
-  }
-  // bits of `m` (bit 0 = candidate b) that belong to cell cq of the species whose cell table is st
-  __device__ __forceinline__ unsigned long long cell_bits(unsigned long long m, const int *st, int b, int cq) const {
-    const int lo = st[cq] - b, hi = st[cq + 1] - b;
-    return m & bits_from(lo) & ~bits_from(hi);
-  }
-  __device__ __forceinline__ bool advance() {  // next non-trivial run; false: the list is exhausted
-    for (;;) {
-      if (split && sub < 6) {
-        const int cq = rr.ca + (sub >> 1);
-        const bool wall = sub & 1;
-        ++sub;
-        if (cq > rr.cb) continue;
-        cur = wall ? cell_bits(md, st_d, bd, cq) : cell_bits(ma, st_a, ba, cq);
-        base = wall ? bd : ba;
-        tag = wall ? (SP_DUMMY << 30) : (sq_a << 30);
-        if (cur) return true;
-        continue;
-      }
-      if (++jr > 2) return false;
-      const int jy = cy - 1 + jr;
-      split = false;
-      if (jy < 0 || jy >= ndy) continue;
-      rr = row_range(ndx, cx, jy);
-      ma = mrow[(size_t)(jr * 3 + sq_a) * SLICE];
-      ba = st_a[rr.ca];
-      md = with_walls ? mrow[(size_t)(jr * 3 + SP_DUMMY) * SLICE] : 0ull;
-      if (md) {  // wall partners in this row: (cell id, species, index) order = cell by cell
-        bd = st_d[rr.ca];
-        split = true;
-        sub = 0;
-        continue;
-      }
-      cur = ma;
-      base = ba;
-      tag = sq_a << 30;
-      if (cur) return true;
-    }
-  }
-  __device__ __forceinline__ int next() {
-    if (cur == 0 && !advance()) return -1;
-    const int j = __ffsll((long long)cur) - 1;
-    cur &= cur - 1;
-    return tag | (base + j);
-  }
-};
-
-// Fill pass, fast path: the accepted partners were recorded by k_count (acceptance masks, walked in list order by
-// MaskWalk), so every thread evaluates the kernel for its entries in a dense loop, two entries in flight (measured best).
+// Fill pass, fast path: the accepted partners were recorded by k_count (cand0 / cand1, list order), so every
+// thread evaluates the kernel for its entries in a dense loop, two entries in flight at 8 blocks per SM (measured best).
 #ifndef SPSPH_FILL_MINB
 #define SPSPH_FILL_MINB 8
 #endif
@@ -1058,7 +1057,7 @@ __global__ void __launch_bounds__(128, SPSPH_FILL_MINB)
 k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, const int *__restrict__ n0,
        const int *__restrict__ n1, const GrowthRule *__restrict__ growth, ListPtrs L, int *__restrict__ bc_int,
        float *__restrict__ n_int, const double *__restrict__ mor, const unsigned char *__restrict__ mcls,
-       const unsigned long long *__restrict__ masks, int t0, int tn) {
+       const int *__restrict__ cand0, const int *__restrict__ cand1, int t0, int tn) {
   const int t = t0 + blockIdx.x * blockDim.x + threadIdx.x;
   if (t >= t0 + tn) return;
   int sp, k;
@@ -1079,10 +1078,7 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
   const int lane = t & 31, sl = t / SLICE;
   const size_t o0 = (size_t)L.off0[sl] + lane;
   const size_t o1 = (size_t)(sp == SP_NODE ? L.offC[sl] : L.offD[sl]) + lane;
-  const unsigned long long *__restrict__ mrow = masks + mask_base(t);
-  const int ndx = G->ndivx[0], ndy = G->ndivx[1];
-  const int cy = c / ndx, cx = c - cy * ndx;
-  const int sq_other = sp == SP_NODE ? SP_STRESS : SP_NODE;
+  const size_t cb = cand_base(t);
   const double2 pp = posp[k];
   const double hp = hpp[k];
   const bool uni = UNIFORM || G->uniform_h != 0;
@@ -1094,31 +1090,32 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
     if (up >= gr.ka) {
       s0 = 0;
       s1 = 0;
-      MaskWalk w;
-      w.init(mrow, S, ndx, ndy, cx, cy, sq_other, true);
       for (int e = 0; e < cnt0; ++e) {
-        const int pk = w.next();
+        const int pk = cand0[cb + cand_off(e)];
         s0 += pair_is_old(gr, up, sorted_key(S, (int)((unsigned)pk >> 30), pk & 0x3fffffff)) ? 1 : 0;
       }
-      w.init(mrow, S, ndx, ndy, cx, cy, sp, false);
-      for (int e = 0; e < cnt1; ++e) s1 += pair_is_old(gr, up, sorted_key(S, sp, w.next() & 0x3fffffff)) ? 1 : 0;
+      for (int e = 0; e < cnt1; ++e) s1 += pair_is_old(gr, up, sorted_key(S, sp, cand1[cb + cand_off(e)])) ? 1 : 0;
     }
   }
   constexpr int U = SPSPH_FILL_U;
   int has_dummy = 0;
   // list 0: cross-species partners, reference orientation of the gradient (pair_i - pair_j after Pint_Update)
-  MaskWalk mw;
-  mw.init(mrow, S, ndx, ndy, cx, cy, sq_other, true);
+  // the entries of the next trip are requested before this trip's arithmetic (the scratch comes from DRAM)
+  int pkn[U];
+#pragma unroll
+  for (int u = 0; u < U; ++u) pkn[u] = cnt0 > 0 ? cand0[cb + cand_off(min(u, cnt0 - 1))] : 0;
   for (int e0 = 0; e0 < cnt0; e0 += U) {
     int sq[U], q[U], qid[U];
     double2 pq[U];
     double hq[U];
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      // past the end: repeat the trip's first entry (evaluated, not stored)
-      const int pk = (u == 0 || e0 + u < cnt0) ? mw.next() : ((sq[0] << 30) | q[0]);
-      sq[u] = (int)((unsigned)pk >> 30);
-      q[u] = pk & 0x3fffffff;
+      sq[u] = (int)((unsigned)pkn[u] >> 30);
+      q[u] = pkn[u] & 0x3fffffff;
+    }
+    if (e0 + U < cnt0) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) pkn[u] = cand0[cb + cand_off(min(e0 + U + u, cnt0 - 1))];
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
@@ -1166,13 +1163,18 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
     }
   }
   // list C / D: same-species partners, own-perspective gradient (nodes) or weight only (stress particles)
-  mw.init(mrow, S, ndx, ndy, cx, cy, sp, false);
+#pragma unroll
+  for (int u = 0; u < U; ++u) pkn[u] = cnt1 > 0 ? cand1[cb + cand_off(min(u, cnt1 - 1))] : 0;
   for (int e0 = 0; e0 < cnt1; e0 += U) {
     int q[U], qid[U];
     double2 pq[U];
     double hq[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) q[u] = (u == 0 || e0 + u < cnt1) ? (mw.next() & 0x3fffffff) : q[0];
+    for (int u = 0; u < U; ++u) q[u] = pkn[u];
+    if (e0 + U < cnt1) {
+#pragma unroll
+      for (int u = 0; u < U; ++u) pkn[u] = cand1[cb + cand_off(min(e0 + U + u, cnt1 - 1))];
+    }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       pq[u] = posp[q[u]];

@@ -136,8 +136,7 @@ struct spsph_handle {
   long long *scan_totals = nullptr;  // [0..2] list storage, [3] pairs, [4..6] cells
   // lists
   int *n0 = nullptr, *n1 = nullptr, *nall = nullptr, *nfwd_u = nullptr, *base_u = nullptr;
-  unsigned long long *masks = nullptr;  // acceptance masks of k_count (NMASK words per list-owning slot)
-  int *cand_overflow = nullptr;         // a stencil row with more candidates than a mask has bits
+  int *cand0 = nullptr, *cand1 = nullptr, *cand_overflow = nullptr;  // accepted partners recorded by k_count
   bool force_fill_scan = false;  // SPSPH_FORCE_FILL_SCAN=1: always take the overflow path (tests)
   int *wslice = nullptr, *oslice = nullptr;  // 3 rows x nslices
   int nslices = 0;
@@ -847,8 +846,8 @@ int build_lists(spsph_handle *h, int forced_mode = -1) {
   if (!h->dist) {  // single GPU: every slot is live, one launch over all of them
     const int tn = h->M.total();
     k_count<<<(tn + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->nfwd_u, h->nall, h->wslice,
-                                             h->wslice + h->nslices, h->wslice + 2 * h->nslices, lflag, h->masks,
-                                             h->cand_overflow, h->nout, 0, tn);
+                                             h->wslice + h->nslices, h->wslice + 2 * h->nslices, lflag, h->cand0,
+                                             h->cand1, h->cand_overflow, h->nout, 0, tn);
   } else {  // slab: one launch per species over the leading slots that can hold local particles
     const int t0s[3] = {0, h->M.nnp, h->M.nnp + h->M.nsp};
     for (int k = 0; k < 3; ++k) {
@@ -856,7 +855,7 @@ int build_lists(spsph_handle *h, int forced_mode = -1) {
       if (tn > 0)
         k_count<<<(tn + 127) / 128, 128, 0, s>>>(P, h->M, h->G, S, h->n0, h->n1, h->nfwd_u, h->nall, h->wslice,
                                                  h->wslice + h->nslices, h->wslice + 2 * h->nslices, lflag,
-                                                 h->masks, h->cand_overflow, h->nout, t0s[k], tn);
+                                                 h->cand0, h->cand1, h->cand_overflow, h->nout, t0s[k], tn);
     }
   }
   mark(h, KID_COUNT, h->dist ? 3 : 1);
@@ -939,11 +938,11 @@ int build_lists(spsph_handle *h, int forced_mode = -1) {
                                                        h->n_int, h->mor, h->umor ? h->mcls : nullptr, ft0[k], ftn[k]);
     else if (h->uniform_cubic)
       k_fill<true><<<(ftn[k] + 127) / 128, 128, 0, s>>>(P, ML, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int,
-                                                        h->n_int, h->mor, h->umor ? h->mcls : nullptr, h->masks, ft0[k],
+                                                        h->n_int, h->mor, h->umor ? h->mcls : nullptr, h->cand0, h->cand1, ft0[k],
                                                         ftn[k]);
     else
       k_fill<false><<<(ftn[k] + 127) / 128, 128, 0, s>>>(P, ML, h->G, S, h->n0, h->n1, h->growth, h->L, h->bc_int,
-                                                         h->n_int, h->mor, h->umor ? h->mcls : nullptr, h->masks, ft0[k],
+                                                         h->n_int, h->mor, h->umor ? h->mcls : nullptr, h->cand0, h->cand1, ft0[k],
                                                         ftn[k]);
   }
   mark(h, KID_FILL, h->dist ? 2 : 1);
@@ -1621,7 +1620,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   const size_t T = (size_t)M.total();
   rc |= dalloc(h, &h->n0, T) | dalloc(h, &h->n1, T) | dalloc(h, &h->nall, T);
   rc |= dalloc(h, &h->nfwd_u, n2) | dalloc(h, &h->base_u, n2) | dalloc(h, &h->cand_overflow, 4);
-  rc |= dalloc(h, &h->masks, (size_t)h->nslices * NMASK * SLICE);
+  rc |= dalloc(h, &h->cand0, (size_t)h->nslices * CAND_CAP * SLICE) | dalloc(h, &h->cand1, (size_t)h->nslices * CAND_CAP * SLICE);
   rc |= dalloc(h, &h->wslice, 3 * (size_t)h->nslices) | dalloc(h, &h->oslice, 3 * (size_t)h->nslices);
   rc |= dalloc(h, &h->growth, 1) | dalloc(h, &h->status_d, 1) | dalloc(h, &h->stats_d, 4);
   if (rc) return 1;
