@@ -501,8 +501,9 @@ __device__ __forceinline__ RowRange row_range(int ndx, int cx, int jy) {
 // again; a particle with more partners than that raises `overflow` and the step falls back to k_fill_scan.
 constexpr int CAND_CAP = 64;
 // Scratch layout: entry c of lane l of a slice at row c, column l (the lanes of a warp that append at the same time
-// share a 128-byte row; measured: 16-byte groups per lane cost k_count +0.6 ms in scattered 4-byte stores for -0.1 ms
-// in k_fill). Offsets are relative to cand_base(t).
+// share a 128-byte row). Measured alternatives on the 4 M column (k_count + k_fill = 1.00 + 1.49 ms with this layout):
+// 16-byte groups per lane 1.59 + 1.49 (scattered 4-byte stores); acceptance masks instead of a scratch, one 64-bit
+// word per (stencil row, species), walked bit by bit in k_fill: 0.87 + 1.98. Offsets are relative to cand_base(t).
 __host__ __device__ __forceinline__ size_t cand_base(int t) { return (size_t)(t / SLICE) * CAND_CAP * SLICE + (size_t)(t & 31); }
 __host__ __device__ __forceinline__ size_t cand_off(int c) { return (size_t)c * SLICE; }
 
