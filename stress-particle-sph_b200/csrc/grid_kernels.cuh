@@ -15,10 +15,14 @@
 namespace spsph {
 
 constexpr int SLICE = 32;
+// The two top bits of a partner id of list 0 may carry the partner's mass/rho class (see step_kernels.cuh, ell_stream)
+constexpr int QCLASS_SHIFT = 30;
+constexpr int QID_MASK = (1 << QCLASS_SHIFT) - 1;
 
 struct SortArrays {  // per species s in {node, stress, dummy}; species-sorted index k
   const int *start[3];      // [ncell+1] first sorted index of each cell
   const int *order[3];      // [n_s] original 0-based particle id
+  const int *ordc[3];       // [n_s] the same id with the particle's mass/rho class in the two top bits (0 without palette)
   const double2 *pos[3];    // [n_s] positions
   const float2 *upos[3];    // [n_s] positions in cell units relative to the grid origin (fp32 prefilter only)
   const double *h[3];       // [n_s] smoothing lengths
@@ -322,7 +326,8 @@ __global__ void k_rank(DevParams P, LocalList LL, const GridInfo *__restrict__ G
                        const int *__restrict__ start, int cell_stride, const int *__restrict__ tmp,
                        int *__restrict__ order, double2 *__restrict__ spos, double *__restrict__ sh,
                        int *__restrict__ scell, int *__restrict__ pos_of /* [ntotal2] species-sorted index */,
-                       float2 *__restrict__ supos, const int *__restrict__ nout) {
+                       float2 *__restrict__ supos, const int *__restrict__ nout, const unsigned char *__restrict__ mcls,
+                       int *__restrict__ ordc) {
   // one thread per (local) particle
   SPSPH_FOR_LOCAL(LL, kk, i) {
     const int sp = species_of(P, i);
@@ -339,6 +344,7 @@ __global__ void k_rank(DevParams P, LocalList LL, const GridInfo *__restrict__ G
       k = b + r;
     }
     order[row + k] = i;
+    ordc[row + k] = mcls ? (i | ((int)mcls[i] << 30)) : i;  // what k_fill stores as partner id of list 0 (QCLASS_SHIFT)
     const double2 xi = ld2(x, i);
     supos[row + k] =
         make_float2((float)((xi.x - G->xmin[0]) / G->deltx[0]), (float)((xi.y - G->xmin[1]) / G->deltx[1]));
@@ -508,7 +514,10 @@ __host__ __device__ __forceinline__ size_t cand_base(int t) { return (size_t)(t 
 __host__ __device__ __forceinline__ size_t cand_off(int c) { return (size_t)c * SLICE; }
 
 #ifndef SPSPH_COUNT_MINB
-#define SPSPH_COUNT_MINB 8
+#define SPSPH_COUNT_MINB 6  // measured on the 4 M column: 6 blocks (78 registers, no spills) 0.97 ms, 8: 1.00, 10: 1.19
+#endif
+#ifndef SPSPH_COUNT_PAIR
+#define SPSPH_COUNT_PAIR 0  // 1: candidate positions loaded as 16-byte pairs (measured slower: 1.31 vs 1.00 ms)
 #endif
 #ifndef SPSPH_COUNT_LEAN
 #define SPSPH_COUNT_LEAN 1  // 0: the general candidate loop only (round-2 mid-point kernel, kept for A/B timing)
@@ -553,7 +562,7 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
             if (c1 < CAND_CAP) cand1[cb + cand_off(c1)] = q;
             ++c1;
           } else {  // node<->stress (type 1) and node/stress<->dummy (types 6, 9)
-            if (c0 < CAND_CAP) cand0[cb + cand_off(c0)] = (sq << 30) | q;
+            if (c0 < CAND_CAP) cand0[cb + cand_off(c0)] = sq * P.ntotal2 + q;
             ++c0;
           }
         }
@@ -627,7 +636,7 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
               const int back_end = (same && jy == cy && k >= b && k < e) ? k : m;  // the particle itself: m == k + 1
               const float2 *__restrict__ uq = sq == 0 ? S.upos[0] : (sq == 1 ? S.upos[1] : S.upos[2]);
               int *__restrict__ cp = (same ? cand1 : cand0) + cb;
-              const int tag = same ? 0 : (sq << 30);
+              const int tag = same ? 0 : sq * P.ntotal2;  // cross-species partners: index into the unified sorted arrays
               int cc = same ? c1 : c0;
               auto exact = [&](int q) {
                 const double2 *__restrict__ pq = sq == 0 ? S.pos[0] : (sq == 1 ? S.pos[1] : S.pos[2]);
@@ -641,19 +650,31 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
                 const float d2 = __fmaf_rn(du, du, dv * dv);
                 if (d2 > phi) return;
                 if (!(d2 < plo) && !exact(q)) return;
-                if (cc < CAND_CAP) cp[cand_off(cc)] = tag | q;
+                if (cc < CAND_CAP) cp[cand_off(cc)] = tag + q;
                 ++cc;
               };
               auto seg = [&](int lo, int hi) {
                 int q = lo;
+#if SPSPH_COUNT_PAIR
                 // candidates come in 16-byte pairs: start on a pair boundary
                 if (q < hi && (reinterpret_cast<size_t>(uq + q) & 8)) one(q++);
+#endif
                 for (;;) {
                   // fast groups: four candidates, all of them clear of the uncertainty band
                   for (; q + 4 <= hi && cc + 4 <= CAND_CAP; q += 4) {
+#if SPSPH_COUNT_PAIR
                     const float4 a01 = *reinterpret_cast<const float4 *>(uq + q);
                     const float4 a23 = *reinterpret_cast<const float4 *>(uq + q + 2);
                     const float ax[4] = {a01.x, a01.z, a23.x, a23.z}, ay[4] = {a01.y, a01.w, a23.y, a23.w};
+#else
+                    float ax[4], ay[4];
+#pragma unroll
+                    for (int u = 0; u < 4; ++u) {
+                      const float2 a = uq[q + u];
+                      ax[u] = a.x;
+                      ay[u] = a.y;
+                    }
+#endif
                     float d2[4], off[4];
 #pragma unroll
                     for (int u = 0; u < 4; ++u) {
@@ -665,7 +686,7 @@ k_count(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, in
 #pragma unroll
                     for (int u = 0; u < 4; ++u)
                       if (d2[u] < plo) {
-                        cp[cand_off(cc)] = tag | (q + u);
+                        cp[cand_off(cc)] = tag + (q + u);
                         ++cc;
                       }
                   }
@@ -1046,7 +1067,7 @@ k_fill_scan(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S
 // Fill pass, fast path: the accepted partners were recorded by k_count (cand0 / cand1, list order), so every
 // thread evaluates the kernel for its entries in a dense loop, two entries in flight at 8 blocks per SM (measured best).
 #ifndef SPSPH_FILL_MINB
-#define SPSPH_FILL_MINB 8
+#define SPSPH_FILL_MINB 7
 #endif
 #ifndef SPSPH_FILL_U
 #define SPSPH_FILL_U 2
@@ -1077,8 +1098,10 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
   }
   const GrowthRule gr = *growth;
   const int lane = t & 31, sl = t / SLICE;
-  const size_t o0 = (size_t)L.off0[sl] + lane;
-  const size_t o1 = (size_t)(sp == SP_NODE ? L.offC[sl] : L.offD[sl]) + lane;
+  // list offsets fit 32 bits (the host refuses lists of 2^31 entries): one IMAD.WIDE per store address
+  const int o0 = L.off0[sl] + lane;
+  const int o1 = (sp == SP_NODE ? L.offC[sl] : L.offD[sl]) + lane;
+  const int n2 = P.ntotal2;  // row stride of the unified sorted arrays: cross-species scratch entries are sq * n2 + q
   const size_t cb = cand_base(t);
   const double2 pp = posp[k];
   const double hp = hpp[k];
@@ -1093,7 +1116,8 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
       s1 = 0;
       for (int e = 0; e < cnt0; ++e) {
         const int pk = cand0[cb + cand_off(e)];
-        s0 += pair_is_old(gr, up, sorted_key(S, (int)((unsigned)pk >> 30), pk & 0x3fffffff)) ? 1 : 0;
+        const int sq = pk >= 2 * n2 ? 2 : (pk >= n2 ? 1 : 0);
+        s0 += pair_is_old(gr, up, sorted_key(S, sq, pk - sq * n2)) ? 1 : 0;
       }
       for (int e = 0; e < cnt1; ++e) s1 += pair_is_old(gr, up, sorted_key(S, sp, cand1[cb + cand_off(e)])) ? 1 : 0;
     }
@@ -1106,25 +1130,20 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
 #pragma unroll
   for (int u = 0; u < U; ++u) pkn[u] = cnt0 > 0 ? cand0[cb + cand_off(min(u, cnt0 - 1))] : 0;
   for (int e0 = 0; e0 < cnt0; e0 += U) {
-    int sq[U], q[U], qid[U];
+    int pk[U], idw[U];
     double2 pq[U];
     double hq[U];
 #pragma unroll
-    for (int u = 0; u < U; ++u) {
-      sq[u] = (int)((unsigned)pkn[u] >> 30);
-      q[u] = pkn[u] & 0x3fffffff;
-    }
+    for (int u = 0; u < U; ++u) pk[u] = pkn[u];
     if (e0 + U < cnt0) {
 #pragma unroll
       for (int u = 0; u < U; ++u) pkn[u] = cand0[cb + cand_off(min(e0 + U + u, cnt0 - 1))];
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
-      const double2 *__restrict__ pqa = sq[u] == 0 ? S.pos[0] : (sq[u] == 1 ? S.pos[1] : S.pos[2]);
-      const int *__restrict__ oqa = sq[u] == 0 ? S.order[0] : (sq[u] == 1 ? S.order[1] : S.order[2]);
-      pq[u] = pqa[q[u]];
-      qid[u] = oqa[q[u]];
-      hq[u] = uni ? hp : (sq[u] == 0 ? S.h[0] : (sq[u] == 1 ? S.h[1] : S.h[2]))[q[u]];
+      pq[u] = S.pos[0][pk[u]];
+      idw[u] = S.ordc[0][pk[u]];  // partner id, with its mass/rho class in the top bits when the palette is on
+      hq[u] = uni ? hp : S.h[0][pk[u]];
     }
     double w[U], gx[U], gy[U], h0[U];
 #pragma unroll
@@ -1135,7 +1154,7 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
       const double mh = (hp + hq[u]) / 2.;
       const double r = sqrt(d2);
       // Pint_Update orientation: pair_i = stress particle (type 1) or dummy (types 6, 9)
-      const bool p_is_i = (sp == SP_STRESS && sq[u] == SP_NODE);
+      const bool p_is_i = (sp == SP_STRESS && pk[u] < n2);
       if (!p_is_i) {
         dx = -dx;
         dy = -dy;
@@ -1144,15 +1163,15 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
         sph_kernel_fast<true>(K, r, dx, dy, w[u], gx[u], gy[u]);
       else
         sph_kernel(P, r, dx, dy, mh, w[u], gx[u], gy[u]);
-      h0[u] = (sq[u] == SP_DUMMY || mcls) ? 0.0 : mor[qid[u]] * (double)(float)w[u];
+      h0[u] = (pk[u] >= 2 * n2 || mcls) ? 0.0 : mor[idw[u] & QID_MASK] * (double)(float)w[u];
     }
 #pragma unroll
     for (int u = 0; u < U; ++u) {
       const int e = e0 + u;
       if (e >= cnt0) break;
       const int pos = (e < s0) ? (cnt0 - s0) + e : (cnt0 - 1 - e);
-      const size_t a = o0 + (size_t)pos * SLICE;
-      L.idx0[a] = mcls ? (qid[u] | ((int)mcls[qid[u]] << 30)) : qid[u];  // mass/rho class of the partner, see ell_stream
+      const int a = o0 + pos * SLICE;
+      L.idx0[a] = idw[u];  // with the mass/rho class of the partner, see ell_stream
       if (L.h0lo) {  // not stored when mass/rho is uniform per species (the sweeps rebuild it from w)
         L.h0lo[a] = __double2loint(h0[u]);
         L.h0hi[a] = __double2hiint(h0[u]);
@@ -1160,7 +1179,7 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
       L.w0[a] = (float)w[u];
       L.gx0[a] = (float)gx[u];
       L.gy0[a] = (float)gy[u];
-      if (sq[u] == SP_DUMMY) has_dummy = 1;
+      if (pk[u] >= 2 * n2) has_dummy = 1;
     }
   }
   // list C / D: same-species partners, own-perspective gradient (nodes) or weight only (stress particles)
@@ -1209,7 +1228,7 @@ k_fill(DevParams P, SlotMap M, const GridInfo *__restrict__ G, SortArrays S, con
       const int e = e0 + u;
       if (e >= cnt1) break;
       const int pos = (e < s1) ? (cnt1 - s1) + e : (cnt1 - 1 - e);
-      const size_t a = o1 + (size_t)pos * SLICE;
+      const int a = o1 + pos * SLICE;
       if (sp == SP_NODE) {
         L.idxC[a] = qid[u];
         L.wC[a] = (float)w[u];

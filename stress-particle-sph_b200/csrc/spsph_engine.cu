@@ -128,6 +128,7 @@ struct spsph_handle {
   int bbox_blocks = 0;
   int cell_capacity = 0, cell_stride = 0;
   int *cell_cnt = nullptr, *cell_start = nullptr, *cell_fill = nullptr;
+  int *ordc = nullptr;  // order with the mass/rho class in the top bits (k_rank; what k_fill stores in list 0)
   int *which_cell = nullptr, *tmp_ids = nullptr, *order = nullptr, *scell = nullptr, *pos_of = nullptr, *nout = nullptr;
   double2 *spos = nullptr;
   float2 *supos = nullptr;
@@ -360,6 +361,7 @@ SortArrays sort_arrays(spsph_handle *h) {
   for (int s = 0; s < 3; ++s) {
     S.start[s] = h->cell_start + (size_t)s * h->cell_stride;
     S.order[s] = h->order + s * n2;
+    S.ordc[s] = h->ordc + s * n2;
     S.pos[s] = h->spos + s * n2;
     S.upos[s] = h->supos + s * n2;
     S.h[s] = h->sh + s * n2;
@@ -654,6 +656,10 @@ int emu_import_lists(spsph_handle *h) {
   const int cnt[3] = {P.nnode, P.nstress, P.ndummy};
   for (int sp = 0; sp < 3; ++sp) {
     std::memcpy(h->order + sp * n2, E->order[sp], cnt[sp] * sizeof(int));
+    for (int k = 0; k < cnt[sp]; ++k) {
+      const int i = E->order[sp][k];
+      h->ordc[sp * n2 + k] = h->umor ? (i | ((int)h->mcls[i] << 30)) : i;
+    }
     std::memcpy(h->scell + sp * n2, E->cell[sp], cnt[sp] * sizeof(int));
     std::memcpy(h->spos + sp * n2, E->pos[sp], cnt[sp] * sizeof(double2));
     std::memcpy(h->sh + sp * n2, E->h[sp], cnt[sp] * sizeof(double));
@@ -776,7 +782,8 @@ int sort_particles(spsph_handle *h) {
   k_scatter<<<GL, TB, 0, s>>>(P, LL, h->which_cell, h->cell_start, h->cell_fill, h->cell_stride, h->tmp_ids);
   mark(h, KID_SCATTER);
   k_rank<<<GL, TB, 0, s>>>(P, LL, h->G, h->x, h->hsml, h->which_cell, h->cell_start, h->cell_stride, h->tmp_ids,
-                           h->order, h->spos, h->sh, h->scell, h->pos_of, h->supos, h->nout);
+                           h->order, h->spos, h->sh, h->scell, h->pos_of, h->supos, h->nout,
+                           h->umor ? h->mcls : nullptr, h->ordc);
   if (h->tile_cfg)  // species-sorted copies of the per-particle constants the tile kernels stage
     k_rank_consts<<<GL, TB, 0, s>>>(P, LL, h->pos_of, h->mass, h->rho, h->mor, h->smor, h->smrho, h->srrho);
   mark(h, KID_RANK, h->tile_cfg ? 2 : 1);
@@ -1493,6 +1500,8 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   if (p->sph_shift && p->shift_update <= 0) return fail("shift_update must be positive");
   if (p->no_bcs > 16) return fail("too many BCs");
   if (p->nnode + p->nstress != p->ntotal || p->ntotal + p->ndummy != p->ntotal2) return fail("inconsistent counts");
+  // indices into the species-sorted arrays (3 rows of ntotal2) and partner ids with two class bits are 32-bit
+  if ((long long)p->ntotal2 * 3 >= (1ll << 31)) return fail("more than 7.1e8 particles on one device");
   if (!p->inside_approach && p->nstress != p->nnode * p->npoints) return fail("nstress != npoints*nnode");
   if (!p->sp_sph && (p->nstress != p->nnode || p->sph_shift)) return fail("standard SPH needs nstress == nnode");
   if (p->ndummy2 < 0 || p->ndummy2 > p->ndummy) return fail("ndummy2 out of range");
@@ -1613,7 +1622,7 @@ int spsph_create(spsph_handle **out, const spsph_params *p, int device) {
   rc |= dalloc(h, &h->G, 1);
   h->bbox_blocks = 148 * 8;
   rc |= dalloc(h, &h->bbox_partial, 6 * (size_t)h->bbox_blocks);
-  rc |= dalloc(h, &h->which_cell, n2) | dalloc(h, &h->tmp_ids, 3 * n2) | dalloc(h, &h->order, 3 * n2);
+  rc |= dalloc(h, &h->which_cell, n2) | dalloc(h, &h->tmp_ids, 3 * n2) | dalloc(h, &h->order, 3 * n2) | dalloc(h, &h->ordc, 3 * n2);
   rc |= dalloc(h, &h->scell, 3 * n2) | dalloc(h, &h->pos_of, n2) | dalloc(h, &h->nout, 8) | dalloc(h, &h->bb6, 8);
   rc |= dalloc(h, &h->spos, 3 * n2) | dalloc(h, &h->sh, 3 * n2) | dalloc(h, &h->supos, 3 * n2);
   rc |= dalloc(h, &h->scan_bsum, 4 * (size_t)SCAN_BLOCKS) | dalloc(h, &h->scan_totals, 8);

@@ -163,8 +163,6 @@ inline void cp_async_wait() {}
 // The two top bits of a partner id of list 0 may carry the partner's mass/rho class (QCLASS_SHIFT, written by the fill
 // pass when the host found at most four distinct values per species); gather() always receives the plain id, and so
 // does compute() unless RAWQ asks for the stored word (sweep A, which turns the class into the factor (m/rho)*w).
-constexpr int QCLASS_SHIFT = 30;
-constexpr int QID_MASK = (1 << QCLASS_SHIFT) - 1;
 #if !defined(SPSPH_HOST_EMU) || defined(SPSPH_EMU_SIMT)  // device, and the lockstep (SIMT) host emulation
 template <int NARR, int NG, class R, int GR = ELL_GROUP, int SUB = ELL_SUB, bool RAWQ = false, class GatherF,
           class ComputeF>
