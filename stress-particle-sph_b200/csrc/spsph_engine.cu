@@ -401,6 +401,8 @@ StatePtrs state_ptrs(spsph_handle *h, int wb) {
   s.av = h->av;
   s.fbound = h->fbound;
   s.aforce = h->aforce;
+  s.has_fbound = (h->hp.inside_approach && h->hp.ndummy2 > 0) ? 1 : 0;
+  s.has_aforce = h->hp.art_stress ? 1 : 0;
   s.RN = h->RN;
   s.rho_w = h->rho;
   s.hsml_w = h->hsml;

@@ -52,6 +52,7 @@ struct StatePtrs {
   double *av;   // (2, nnode) artificial viscosity acceleration of the current stage (k_artvisc -> k_sweep_b_node)
   double *fbound;  // (2, nnode) boundary_forces of the current step (zero unless the inside approach has walls)
   double *aforce;  // (2, nnode) artificial_force of the current stage (zero unless art_stress = T)
+  int has_fbound, has_aforce;  // 0: the array holds zeros (the feature is off): sweep B does not read it
   Rec4 *RN;        // [nnode] artificial-stress terms R(1:3) of a node (k_art_force_prep -> k_art_force)
   // continuity density (cont_density = T): the density of the stress particles is integrated by RK4, that of the
   // velocity particles interpolated by every stress_point_update; with sle = 2 the smoothing length follows
@@ -304,6 +305,43 @@ __device__ __forceinline__ int warp_max_i(int v) {
 constexpr int A_SUB = SPSPH_A_SUB;  // sweep A: entries gathered + consumed together
 constexpr int A_GR = SPSPH_A_GR, A_NG = SPSPH_A_NG;  // sweep A: rows per group (all in flight per thread), ring depth
 
+// Per-kernel build switches of the five pair-sum kernels: entries gathered + consumed together (registers) and the
+// resident blocks per SM requested from ptxas. Defaults = the values measured best on the 4 M-particle column
+// (per kernel, against 4 entries / 4 blocks: k_sweep_b_sp 2 / 6 -0.08 ms per step, k_artvisc 2 / 6 -0.09, k_sweep_a_sp
+// 2 / 8 -0.03; the velocity-particle sides are best left at 4 / 4).
+#ifndef SPSPH_ASP_SUB
+#define SPSPH_ASP_SUB 2
+#endif
+#ifndef SPSPH_AN_SUB
+#define SPSPH_AN_SUB SPSPH_A_SUB
+#endif
+#ifndef SPSPH_BSP_SUB
+#define SPSPH_BSP_SUB 2
+#endif
+#ifndef SPSPH_BN_SUB
+#define SPSPH_BN_SUB SPSPH_ELL_SUB
+#endif
+#ifndef SPSPH_AV_SUB
+#define SPSPH_AV_SUB 2
+#endif
+#ifndef SPSPH_ASP_MINB
+#define SPSPH_ASP_MINB 8
+#endif
+#ifndef SPSPH_AN_MINB
+#define SPSPH_AN_MINB SPSPH_MINB
+#endif
+#ifndef SPSPH_BSP_MINB
+#define SPSPH_BSP_MINB 6
+#endif
+#ifndef SPSPH_BN_MINB
+#define SPSPH_BN_MINB SPSPH_MINB
+#endif
+#ifndef SPSPH_AV_MINB
+#define SPSPH_AV_MINB 6
+#endif
+constexpr int ASP_SUB = SPSPH_ASP_SUB, AN_SUB = SPSPH_AN_SUB, BSP_SUB = SPSPH_BSP_SUB, BN_SUB = SPSPH_BN_SUB,
+              AV_SUB = SPSPH_AV_SUB;
+
 // state format conversions at the boundary of the time loop ---------------------------------------------
 // pack: reference-layout vel/stress (upload) -> format B
 __global__ void k_pack_state(DevParams P, const double *__restrict__ vel, const double *__restrict__ stress,
@@ -429,7 +467,7 @@ __device__ __forceinline__ double palette_value(const MorPalette &p, unsigned c)
   return c == 0 ? p.v0 : (c == 1 ? p.v1 : (c == 2 ? p.v2 : p.v3));
 }
 template <bool FIRST, bool FROMB, bool UMOR>
-__global__ void __launch_bounds__(SWEEP_T, SPSPH_MINB)
+__global__ void __launch_bounds__(SWEEP_T, SPSPH_ASP_MINB)
 k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L, const int *__restrict__ n0,
              StatePtrs st, int do_adapt, int do_bc, MorPalette mor_u) {
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;  // species-sorted index of the stress particle
@@ -441,14 +479,12 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   const int ks = id - P.nnode;
   const int cnt = live ? n0[t] : 0;
   const int wrows = warp_max_i(cnt);
+  // the particle's own velocity survives only where cspm_norm == 0 (no velocity-particle partner): read it there
   double2 v;
   Stress4 s;
   if (FROMB) {
-    const Rec4 r = ldrec(st.SVbr, ks);
-    v = make_double2(r.a, r.b);
     s = ld4(st.SFbr, ks);
   } else {
-    v = ld2(st.SVa, ks);
     const Rec4 r = ldrec(st.SA, ks);
     s = Stress4{r.a, r.b, r.c, r.d};
   }
@@ -465,7 +501,7 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
     struct RecN {
       double2 v, mr;
     };
-    ell_stream<NARR, A_NG, RecN, A_GR, A_SUB, UMOR>(
+    ell_stream<NARR, A_NG, RecN, A_GR, ASP_SUB, UMOR>(
         arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM_G(NARR, A_NG, A_GR),
         [&](int q) {
           const int qq = (q < 0 || q >= P.nnode) ? 0 : q;
@@ -480,15 +516,15 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
           }
           return o;
         },
-        [&](const int(&q)[A_SUB], const int(&pay)[NARR - 1][A_SUB], const RecN(&r)[A_SUB], int nvalid) {
+        [&](const int(&q)[ASP_SUB], const int(&pay)[NARR - 1][ASP_SUB], const RecN(&r)[ASP_SUB], int nvalid) {
           if (UMOR && !FIRST) {
             // full group without a wall partner (the common case): straight-line code, no per-entry predicates
-            bool plain = nvalid >= A_SUB;
+            bool plain = nvalid >= ASP_SUB;
 #pragma unroll
-            for (int u = 0; u < A_SUB; ++u) plain = plain && ((q[u] & QID_MASK) < P.nnode);
+            for (int u = 0; u < ASP_SUB; ++u) plain = plain && ((q[u] & QID_MASK) < P.nnode);
             if (plain) {
 #pragma unroll
-              for (int u = 0; u < A_SUB; ++u) {
+              for (int u = 0; u < ASP_SUB; ++u) {
                 const double h2 = palette_value(mor_u, (unsigned)q[u] >> QCLASS_SHIFT) * (double)__int_as_float(pay[0][u]);
                 vtx = vtx + r[u].v.x * h2;
                 vty = vty + r[u].v.y * h2;
@@ -497,7 +533,7 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
             }
           }
 #pragma unroll
-          for (int u = 0; u < A_SUB; ++u) {
+          for (int u = 0; u < ASP_SUB; ++u) {
             const int qid = UMOR ? (q[u] & QID_MASK) : q[u];
             const bool ok = (u < nvalid) && (qid < P.nnode);  // dummy partners (type 9) take no part
             double h2;  // (mass(i)/rho(i))*w, main:431
@@ -530,6 +566,11 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
     const double rn = __drcp_rn(nrm);
     v.x = div_rn(vtx, nrm, rn);
     v.y = div_rn(vty, nrm, rn);
+  } else if (FROMB) {
+    const Rec4 r = ldrec(st.SVbr, ks);
+    v = make_double2(r.a, r.b);
+  } else {
+    v = ld2(st.SVa, ks);
   }
   if (do_adapt) adapt_stress(P, s);
   if (do_bc) apply_bcs(P, st.bc_or_not, st.bc_info, st.bc_int, st.fs_normal, id, v, s);
@@ -541,7 +582,7 @@ k_sweep_a_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
 }
 
 template <bool FIRST, bool FROMB, bool EPSP, bool UMOR>
-__global__ void __launch_bounds__(SWEEP_T, SPSPH_MINB)
+__global__ void __launch_bounds__(SWEEP_T, SPSPH_AN_MINB)
 k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n0,
                StatePtrs st, int do_adapt, int do_bc, MorPalette mor_u) {
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -552,15 +593,14 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
   const int id = order_n[k];
   const int cnt = live ? n0[t] : 0;
   const int wrows = warp_max_i(cnt);
+  // the particle's own stress survives only where cspm_norm == 0 (no stress-particle partner): read it there
   double2 v;
   Stress4 s;
   if (FROMB) {
     const Rec4 r = ldrec(st.NBr, id);
     v = make_double2(r.a, r.b);
-    s = ld4(st.NSbr, id);
   } else {
     v = ld2(st.NA, id);
-    s = ld4(st.NSa, id);
   }
   double t1 = 0.0, t2 = 0.0, t3 = 0.0, t4 = 0.0, te = 0.0, nrm = 0.0, trho = 0.0;
   {
@@ -573,7 +613,7 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
     __shared__ __align__(16) int smem[(SWEEP_T / 32) * ELL_SMEM_G(NARR, A_NG, A_GR)];
     const int *arrs[4] = {L.idx0, UMOR ? reinterpret_cast<const int *>(L.w0) : L.h0lo, L.h0hi,
                           reinterpret_cast<const int *>(L.w0)};
-    ell_stream<NARR, A_NG, RecS, A_GR, A_SUB, UMOR>(
+    ell_stream<NARR, A_NG, RecS, A_GR, AN_SUB, UMOR>(
         arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM_G(NARR, A_NG, A_GR),
         [&](int q) {
           const int qs = (q < 0 || q >= P.ntotal) ? 0 : q - P.nnode;
@@ -583,15 +623,15 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
           r.mr = FIRST ? st.mrho[qs + P.nnode] : make_double2(0.0, 0.0);
           return r;
         },
-        [&](const int(&q)[A_SUB], const int(&pay)[NARR - 1][A_SUB], const RecS(&r)[A_SUB], int nvalid) {
+        [&](const int(&q)[AN_SUB], const int(&pay)[NARR - 1][AN_SUB], const RecS(&r)[AN_SUB], int nvalid) {
           if (UMOR && !FIRST) {
             // full group without a wall partner (the common case): straight-line code, no per-entry predicates
-            bool plain = nvalid >= A_SUB;
+            bool plain = nvalid >= AN_SUB;
 #pragma unroll
-            for (int u = 0; u < A_SUB; ++u) plain = plain && ((q[u] & QID_MASK) < P.ntotal);
+            for (int u = 0; u < AN_SUB; ++u) plain = plain && ((q[u] & QID_MASK) < P.ntotal);
             if (plain) {
 #pragma unroll
-              for (int u = 0; u < A_SUB; ++u) {
+              for (int u = 0; u < AN_SUB; ++u) {
                 const double h1 = palette_value(mor_u, (unsigned)q[u] >> QCLASS_SHIFT) * (double)__int_as_float(pay[0][u]);
                 t1 = t1 + r[u].s.a * h1;
                 t2 = t2 + r[u].s.b * h1;
@@ -603,7 +643,7 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
             }
           }
 #pragma unroll
-          for (int u = 0; u < A_SUB; ++u) {
+          for (int u = 0; u < AN_SUB; ++u) {
             const int qid = UMOR ? (q[u] & QID_MASK) : q[u];
             const bool ok = (u < nvalid) && (qid < P.ntotal);  // dummy partners (type 6) take no part
             double h1;  // (mass(j)/rho(j))*w, main:430
@@ -649,6 +689,7 @@ k_sweep_a_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
     s.s4 = div_rn(t4, nrm, rn);
     if (EPSP) st.epsp[id] = div_rn(te, nrm, rn);
   } else {
+    s = FROMB ? ld4(st.NSbr, id) : ld4(st.NSa, id);
     v.x = 0;
     v.y = 0;
   }
@@ -679,7 +720,7 @@ __global__ void k_commit_node_rho(DevParams P, SlotMap M, const int *__restrict_
 // next-stage predictor, or the final RK4 update when `last`): format B -> format A.
 // ------------------------------------------------------------------------------------------------------
 template <bool FIRST>
-__global__ void __launch_bounds__(SWEEP_T, SPSPH_MINB)
+__global__ void __launch_bounds__(SWEEP_T, SPSPH_BSP_MINB)
 k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L, const int *__restrict__ n0,
              StatePtrs st, double f1next, double f2, int last, double f2next) {
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -742,31 +783,31 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   {
     __shared__ __align__(16) int smem[(SWEEP_T / 32) * ELL_SMEM(3, ELL_NG)];
     const int *arrs[3] = {L.idx0, reinterpret_cast<const int *>(L.gx0), reinterpret_cast<const int *>(L.gy0)};
-    ell_stream<3, ELL_NG, Rec4>(
+    ell_stream<3, ELL_NG, Rec4, ELL_GROUP, BSP_SUB>(
         arrs, (size_t)L.off0[t / SLICE], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(3, ELL_NG),
         [&](int q) { return ldrec(st.NB, (q < 0 || q >= P.nnode) ? 0 : q); },
-        [&](const int(&q)[ELL_SUB], const int(&pay)[2][ELL_SUB], const Rec4(&r)[ELL_SUB], int nvalid) {
+        [&](const int(&q)[BSP_SUB], const int(&pay)[2][BSP_SUB], const Rec4(&r)[BSP_SUB], int nvalid) {
           bool special = false;  // wall partner in this group (type 9), or the once-per-step CSPM matrix pass
 #pragma unroll
-          for (int u = 0; u < ELL_SUB; ++u) special |= (u < nvalid) && (q[u] >= P.nnode);
+          for (int u = 0; u < BSP_SUB; ++u) special |= (u < nvalid) && (q[u] >= P.nnode);
           if ((FIRST && P.cspm) || __any_sync(0xffffffffu, special)) {
 #pragma unroll
-            for (int u = 0; u < ELL_SUB; ++u)
+            for (int u = 0; u < BSP_SUB; ++u)
               if (u < nvalid) entry_slow(q[u], pay[0][u], pay[1][u], r[u]);
             return;
           }
           // branch-free path: the four entries' division chains are independent and interleave
-          double h1[ELL_SUB], h2[ELL_SUB];
+          double h1[BSP_SUB], h2[BSP_SUB];
 #pragma unroll
-          for (int u = 0; u < ELL_SUB; ++u) {
+          for (int u = 0; u < BSP_SUB; ++u) {
             const double gx = (double)__int_as_float(pay[0][u]), gy = (double)__int_as_float(pay[1][u]);
             const double rr = __drcp_rn(r[u].d);
             h1[u] = div_rn(gx * r[u].c, r[u].d, rr);  // dwdx*mass(i)/rho(i), main:514
             h2[u] = div_rn(gy * r[u].c, r[u].d, rr);
           }
-          if (nvalid >= ELL_SUB) {  // full group: no per-entry predicates
+          if (nvalid >= BSP_SUB) {  // full group: no per-entry predicates
 #pragma unroll
-            for (int u = 0; u < ELL_SUB; ++u) {
+            for (int u = 0; u < BSP_SUB; ++u) {
               const double dvx = r[u].a - vp.x, dvy = r[u].b - vp.y;
               g11 = g11 + dvx * h1[u];
               g12 = g12 + dvx * h2[u];
@@ -776,7 +817,7 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
             return;
           }
 #pragma unroll
-          for (int u = 0; u < ELL_SUB; ++u) {
+          for (int u = 0; u < BSP_SUB; ++u) {
             const bool ok = u < nvalid;
             const double dvx = r[u].a - vp.x, dvy = r[u].b - vp.y;
             const double n11 = g11 + dvx * h1[u], n12 = g12 + dvx * h2[u], n21 = g21 + dvy * h1[u],
@@ -901,7 +942,7 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
 // UH: one smoothing length for every particle (host-checked at upload): h = 0.5*(h_i + h_j) is that constant and
 // is not streamed (24 instead of 28 bytes per entry).
 template <bool UH>
-__global__ void __launch_bounds__(SWEEP_T, SPSPH_MINB)
+__global__ void __launch_bounds__(SWEEP_T, SPSPH_AV_MINB)
 k_artvisc(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n1, StatePtrs st,
           float h_u) {
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -922,13 +963,13 @@ k_artvisc(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, c
   const int *arrs[6] = {L.idxC, reinterpret_cast<const int *>(L.gxC), reinterpret_cast<const int *>(L.gyC),
                         reinterpret_cast<const int *>(L.xC), reinterpret_cast<const int *>(L.yC),
                         reinterpret_cast<const int *>(L.hC)};
-  ell_stream<NARR, NG, Rec4>(
+  ell_stream<NARR, NG, Rec4, ELL_GROUP, AV_SUB>(
       arrs, (size_t)L.offC[t / SLICE], wrowsC, cntc, smem + (threadIdx.x >> 5) * ELL_SMEM(NARR, NG),
       [&](int q) { return ldrec(st.NB, q < 0 ? 0 : q); },
-      [&](const int(&)[ELL_SUB], const int(&pay)[NARR - 1][ELL_SUB], const Rec4(&r)[ELL_SUB], int nvalid) {
-        float visc[ELL_SUB];
+      [&](const int(&)[AV_SUB], const int(&pay)[NARR - 1][AV_SUB], const Rec4(&r)[AV_SUB], int nvalid) {
+        float visc[AV_SUB];
 #pragma unroll
-        for (int u = 0; u < ELL_SUB; ++u) {  // independent per entry: interleaves
+        for (int u = 0; u < AV_SUB; ++u) {  // independent per entry: interleaves
           const float xij = __int_as_float(pay[2][u]), yij = __int_as_float(pay[3][u]);
           float h;
           if constexpr (UH)
@@ -948,7 +989,7 @@ k_artvisc(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, c
           visc[u] = (div_u < 0) ? vv : 0.f;
         }
 #pragma unroll
-        for (int u = 0; u < ELL_SUB; ++u) {  // ordered fp32 accumulation
+        for (int u = 0; u < AV_SUB; ++u) {  // ordered fp32 accumulation
           const float gxf = __int_as_float(pay[0][u]), gyf = __int_as_float(pay[1][u]);
           const float a1 = (float)((double)acc1 + (double)(visc[u] * gxf) * r[u].c);
           const float a2 = (float)((double)acc2 + (double)(visc[u] * gyf) * r[u].c);
@@ -961,7 +1002,7 @@ k_artvisc(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, c
 }
 
 template <bool FIRST>
-__global__ void __launch_bounds__(SWEEP_T, SPSPH_MINB)
+__global__ void __launch_bounds__(SWEEP_T, SPSPH_BN_MINB)
 k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n0,
                StatePtrs st, double f1next, double f2, int last) {
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1020,22 +1061,22 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
   {
     __shared__ __align__(16) int smem[(SWEEP_T / 32) * ELL_SMEM(3, ELL_NG)];
     const int *arrs[3] = {L.idx0, reinterpret_cast<const int *>(L.gx0), reinterpret_cast<const int *>(L.gy0)};
-    ell_stream<3, ELL_NG, Rec4>(
+    ell_stream<3, ELL_NG, Rec4, ELL_GROUP, BN_SUB>(
         arrs, (size_t)L.off0[sl], wrows, cnt, smem + (threadIdx.x >> 5) * ELL_SMEM(3, ELL_NG),
         [&](int q) { return ldrec(st.SB, (q < 0 || q >= P.ntotal) ? 0 : q - P.nnode); },
-        [&](const int(&q)[ELL_SUB], const int(&pay)[2][ELL_SUB], const Rec4(&r)[ELL_SUB], int nvalid) {
+        [&](const int(&q)[BN_SUB], const int(&pay)[2][BN_SUB], const Rec4(&r)[BN_SUB], int nvalid) {
           bool special = false;  // wall partner in this group (type 6), or the once-per-step CSPM matrix pass
 #pragma unroll
-          for (int u = 0; u < ELL_SUB; ++u) special |= (u < nvalid) && (q[u] >= P.ntotal);
+          for (int u = 0; u < BN_SUB; ++u) special |= (u < nvalid) && (q[u] >= P.ntotal);
           if ((FIRST && P.cspm) || __any_sync(0xffffffffu, special)) {
 #pragma unroll
-            for (int u = 0; u < ELL_SUB; ++u)
+            for (int u = 0; u < BN_SUB; ++u)
               if (u < nvalid) entry_slow(q[u], pay[0][u], pay[1][u], r[u]);
             return;
           }
-          if (nvalid >= ELL_SUB) {  // full group: no per-entry predicates
+          if (nvalid >= BN_SUB) {  // full group: no per-entry predicates
 #pragma unroll
-            for (int u = 0; u < ELL_SUB; ++u) {
+            for (int u = 0; u < BN_SUB; ++u) {
               const double gx = (double)__int_as_float(pay[0][u]), gy = (double)__int_as_float(pay[1][u]);
               const double c1 = so1 + r[u].a, c2 = so2 + r[u].b, c3 = so3 + r[u].c, mq = r[u].d;
               a11 = a11 - mq * (gx * c1);
@@ -1048,7 +1089,7 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
             return;
           }
 #pragma unroll
-          for (int u = 0; u < ELL_SUB; ++u) {
+          for (int u = 0; u < BN_SUB; ++u) {
             const bool ok = u < nvalid;
             const double gx = (double)__int_as_float(pay[0][u]), gy = (double)__int_as_float(pay[1][u]);
             const double c1 = so1 + r[u].a, c2 = so2 + r[u].b, c3 = so3 + r[u].c, mq = r[u].d;
@@ -1108,8 +1149,9 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
     av1 = a.x;
     av2 = a.y;
   }
-  const double2 fb = ld2(st.fbound, id);  // f_bound (main:764): zero unless boundary_forces ran
-  const double2 af = ld2(st.aforce, id);  // art_force: zero unless art_stress = T
+  // f_bound (main:764): zero unless boundary_forces ran; art_force: zero unless art_stress = T
+  const double2 fb = st.has_fbound ? ld2(st.fbound, id) : make_double2(0.0, 0.0);
+  const double2 af = st.has_aforce ? ld2(st.aforce, id) : make_double2(0.0, 0.0);
   const double r1 = -dv1 + sg1 + av1 + fb.x + af.x;
   const double r2 = -dv2 + sg2 + av2 + fb.y + af.y;
   double2 rk = ld2(st.RKv, id);
