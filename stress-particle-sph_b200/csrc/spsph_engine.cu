@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <algorithm>
+#include <chrono>
 #include <string>
 #ifndef SPSPH_HOST_EMU
 #include <thread>
@@ -86,6 +87,8 @@ struct spsph_handle {
   bool umor = false;  // mass/rho takes <= 4 values within the velocity particles and within the stress particles
   MorPalette pal_node{}, pal_sp{};
   unsigned char *mcls = nullptr;  // [ntotal2] palette class of every particle
+  std::vector<double> up_mor;        // host scratch of spsph_upload (mass/rho per particle)
+  std::vector<unsigned char> up_cls;  // host scratch of spsph_upload (palette classes)
   bool uniform_h = false;         // one smoothing length for every particle, constant in time
   float h_uniform = 0.f;          // (float)(0.5*(h + h)) of artificial_viscosity, main:863
   bool uniform_cubic = false;  // skf = 1 and one smoothing length for every particle (set at upload)
@@ -1658,6 +1661,13 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
     return 1;
   }
   CUDA_TRY(cudaSetDevice(h->device));
+  const bool up_timing = getenv("SPSPH_UPLOAD_TIMING") != nullptr;
+  const auto up_t0 = std::chrono::steady_clock::now();
+  auto up_lap = [&](const char *what) {
+    if (up_timing)
+      fprintf(stderr, "spsph_upload: %-28s at %7.2f ms\n", what,
+              std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - up_t0).count());
+  };
   // Every plain copy is queued first: the DMA engine works through them while the host analyses the input below
   // (on an error return the device state is incomplete: the run has to be uploaded again before it can step)
   h->uploaded = false;
@@ -1689,6 +1699,7 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   CUDA_TRY(up(h->bc_int, s->bc_int, nn * 4));
   CUDA_TRY(up(h->bc_or_not, s->bc_or_not, nt * 4));
   CUDA_TRY(up(h->bc_info, s->bc_info, 8 * nt * 4));
+  up_lap("copies queued");
   // Host-side analysis of the input in ONE pass over the particles, on a few threads: the particle order contract
   // (nodes, stress particles, dummies: mat:961-1026), the range of the smoothing lengths, and the mass/rho palette per
   // species (sweep A rebuilds (m/rho)*w from the partner's class and the streamed weight). The chunks are merged in
@@ -1702,25 +1713,31 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   const bool want_pal = !h->hp.cont_density && nn > 0 && nt > nn && n2 < (size_t)QID_MASK;  // two id bits carry the class
   const int nthr = host_threads(n2);
   std::vector<Chunk> chunks(nthr);
-  std::vector<double> mor_h(want_pal ? nt : 0);  // the reference's mass(j)/rho(j), kept for the class pass
-  parallel_chunks(n2, nthr, [&](int c, size_t i0, size_t i1) {
-    Chunk &ck = chunks[c];
+  std::vector<double> &mor_h = h->up_mor;  // the reference's mass(j)/rho(j), kept for the class pass
+  if (want_pal && mor_h.size() < nt) mor_h.resize(nt);  // host scratch of the handle: page-faulted once, not per upload
+  const int32_t *it_h = s->itype;
+  const double *hs_h = s->hsml, *ms_h = s->mass, *rh_h = s->rho;
+  double *mor_p = want_pal ? mor_h.data() : nullptr;
+  parallel_chunks(n2, nthr, [&, it_h, hs_h, ms_h, rh_h, mor_p](int c, size_t i0, size_t i1) {
+    Chunk ck;  // thread-local: neighbouring entries of `chunks` share cache lines
     double lm = 0.0, lr = 0.0, lv = 0.0;  // last quotient: lattice set-ups repeat the same mass and density
     bool have = false;
+    double hmx = 0.0, hmn = 1.e300;
     for (size_t i = i0; i < i1; ++i) {
       const int want = i < nn ? 2 : (i < nt ? 1 : 25);
-      if (s->itype[i] != want) ck.bad_itype = true;
-      ck.hmax = std::fmax(ck.hmax, s->hsml[i]);
-      ck.hmin = std::fmin(ck.hmin, s->hsml[i]);
-      if (want_pal && i < nt) {
-        const double m = s->mass[i], r = s->rho[i];
+      if (it_h[i] != want) ck.bad_itype = true;
+      const double hh = hs_h[i];
+      hmx = hh > hmx ? hh : hmx;
+      hmn = hh < hmn ? hh : hmn;
+      if (mor_p && i < nt) {
+        const double m = ms_h[i], r = rh_h[i];
         if (!have || m != lm || r != lr) {
           lm = m;
           lr = r;
           lv = m / r;
           have = true;
         }
-        mor_h[i] = lv;
+        mor_p[i] = lv;
         if (!ck.pal_over) {
           const int sp = i < nn ? 0 : 1;
           int k = 0;
@@ -1734,7 +1751,11 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
         }
       }
     }
+    ck.hmax = hmx;
+    ck.hmin = hmn;
+    chunks[c] = ck;
   });
+  up_lap("analysis pass done");
   double hmax = 0.0, hmin = 1.e300;
   bool u = want_pal;
   double pal[2][4] = {{0, 0, 0, 0}, {0, 0, 0, 0}};
@@ -1762,6 +1783,7 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   if (!u) std::memset(pal, 0, sizeof(pal));
   if (const char *e = getenv("SPSPH_NO_UMOR")) u = u && atoi(e) == 0;
   h->h_itype.assign(s->itype, s->itype + n2);
+  up_lap("itype kept");
   // hsml only changes on the device with cont_density and sle = 2 (main:709-712)
   const bool uh = (hmin == hmax && !(h->hp.cont_density && h->hp.sle == 2));
   if (uh != h->uniform_h) h->capC = 0;  // list C was sized for the other mode
@@ -1773,9 +1795,10 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
   h->umor = u;
   h->pal_node = MorPalette{pal[0][0], pal[0][1], pal[0][2], pal[0][3]};
   h->pal_sp = MorPalette{pal[1][0], pal[1][1], pal[1][2], pal[1][3]};
-  std::vector<unsigned char> cls;  // lives until the final synchronize of this call
+  std::vector<unsigned char> &cls = h->up_cls;  // host scratch of the handle
   if (u) {
-    cls.assign(n2, 0);
+    if (cls.size() < n2) cls.resize(n2);
+    std::memset(cls.data() + nt, 0, n2 - nt);  // wall particles: class 0
     parallel_chunks(nt, nthr, [&](int, size_t i0, size_t i1) {
       for (size_t i = i0; i < i1; ++i) {
         const double *pl = pal[i < nn ? 0 : 1];
@@ -1785,7 +1808,9 @@ int spsph_upload(spsph_handle *h, const spsph_state *s) {
     });
     CUDA_TRY(cudaMemcpyAsync(h->mcls, cls.data(), n2, cudaMemcpyHostToDevice, st));
   }
+  up_lap("classes queued");
   CUDA_TRY(cudaStreamSynchronize(st));  // the caller may reuse its arrays as soon as upload returns
+  up_lap("stream drained");
   // cell-table capacity: the in-domain bounding box can never exceed the control domain (main:1187-1192)
   if (!h->cell_cnt) {
     if (!(hmax > 0.0)) {
