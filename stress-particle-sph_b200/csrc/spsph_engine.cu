@@ -1339,6 +1339,7 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     mark(h, KID_SWEEPA, 2);
     first_a = false;
     const int last = (stg == 3);
+    const int sflags = (last ? 1 : 0) | (stg == 0 ? 2 : 0);  // k_sweep_b_*: last stage / accumulators start from zero
     const double f1n = last ? 0.0 : f1rk[stg + 1];
     const bool artv = (P.alpha > 0 || P.beta > 0);
     fork();
@@ -1354,14 +1355,14 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     }
     const double f2n = last ? 0.0 : f2rk[stg + 1];
     if (cd) {  // the node side reads the stress particles' density before their side integrates it
-      k_sweep_b_node<true><<<GNW, SWEEP_T, 0, s>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
-      k_sweep_b_sp<true><<<GSW, SWEEP_T, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last, f2n);
+      k_sweep_b_node<true><<<GNW, SWEEP_T, 0, s>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], sflags);
+      k_sweep_b_sp<true><<<GSW, SWEEP_T, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], sflags, f2n);
     } else if (stg == 0) {
-      k_sweep_b_sp<true><<<GSW, SWEEP_T, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last, f2n);
-      k_sweep_b_node<true><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
+      k_sweep_b_sp<true><<<GSW, SWEEP_T, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], sflags, f2n);
+      k_sweep_b_node<true><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], sflags);
     } else {
-      k_sweep_b_sp<false><<<GSW, SWEEP_T, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], last, f2n);
-      k_sweep_b_node<false><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], last);
+      k_sweep_b_sp<false><<<GSW, SWEEP_T, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], sflags, f2n);
+      k_sweep_b_node<false><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], sflags);
     }
     join();
     mark(h, KID_SWEEPB, artv ? 3 : 2);

@@ -115,7 +115,10 @@ constexpr int UNR = 4;  // list entries in flight per thread
 #endif
 constexpr int SWEEP_T = SPSPH_SWEEP_T;
 static_assert(SWEEP_T % 32 == 0 && SWEEP_T >= 32 && SWEEP_T <= 256, "whole warps; each warp owns its ring in shared memory");
-constexpr int ELL_GROUP = 4;  // rows per cp.async group
+#ifndef SPSPH_ELL_GROUP
+#define SPSPH_ELL_GROUP 4
+#endif
+constexpr int ELL_GROUP = SPSPH_ELL_GROUP;  // rows per cp.async group
 #ifndef SPSPH_ELL_SUB
 #define SPSPH_ELL_SUB 4
 #endif
@@ -123,7 +126,10 @@ constexpr int ELL_GROUP = 4;  // rows per cp.async group
 #define SPSPH_ELL_PIPE 0  // 1: software-pipelined gathers in ell_stream (variant, see there)
 #endif
 constexpr int ELL_SUB = SPSPH_ELL_SUB;  // entries gathered + consumed together (in flight per thread)
-constexpr int ELL_NG = 4;     // groups in the ring (16 rows = 2 KB per array per warp in flight)
+#ifndef SPSPH_ELL_NG
+#define SPSPH_ELL_NG 4
+#endif
+constexpr int ELL_NG = SPSPH_ELL_NG;     // groups in the ring (16 rows = 2 KB per array per warp in flight)
 
 #ifndef SPSPH_HOST_EMU  // device only (the host emulation of tests/native/ has its own version)
 // The list rows are read exactly once per sweep: L2 evict-first, so that the 0.7-1.3 GB streamed per sweep do
@@ -395,7 +401,7 @@ __global__ void k_rk_begin(DevParams P, StatePtrs st, LocalList LL, const int *_
     const double2 v = make_double2(r.a, r.b);
     st2(st.vx0, id, v);
     st2(st.vel0, id, v);
-    st2(st.RKv, id, make_double2(0.0, 0.0));
+    if (pos_of) st2(st.RKv, id, make_double2(0.0, 0.0));  // id-list path: stage 1 of sweep B starts from zero itself
     vn.x = v.x + 0. * (P.dt) * 0.0;  // vel0 + f1rk(1)*dt*RHS_2 with RHS_2 = 0
     vn.y = v.y + 0. * (P.dt) * 0.0;
     sn = Stress4{0.0, 0.0, 0.0, 0.0};
@@ -413,8 +419,10 @@ __global__ void k_rk_begin(DevParams P, StatePtrs st, LocalList LL, const int *_
     const Stress4 s = ld4(st.SFb, ks);
     st2(st.vx0, id, v);
     st4(st.stress0, ks, s);
-    st4(st.RKs, ks, Stress4{0.0, 0.0, 0.0, 0.0});
-    st.RKe[ks] = 0.0;
+    if (pos_of) {
+      st4(st.RKs, ks, Stress4{0.0, 0.0, 0.0, 0.0});
+      st.RKe[ks] = 0.0;
+    }
     vn = make_double2(0.0, 0.0);
     sn.s1 = s.s1 + 0. * (P.dt) * 0.0;
     sn.s2 = s.s2 + 0. * (P.dt) * 0.0;
@@ -722,7 +730,9 @@ __global__ void k_commit_node_rho(DevParams P, SlotMap M, const int *__restrict_
 template <bool FIRST>
 __global__ void __launch_bounds__(SWEEP_T, SPSPH_BSP_MINB)
 k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L, const int *__restrict__ n0,
-             StatePtrs st, double f1next, double f2, int last, double f2next) {
+             StatePtrs st, double f1next, double f2, int stage_flags, double f2next) {
+  const int last = stage_flags & 1;      // last RK4 stage: final update instead of the next predictor
+  const bool stage1 = stage_flags & 2;   // first RK4 stage: the accumulators start from zero (not read, main:686)
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
   if ((k0 & ~31) >= M.ns) return;  // whole warp past the end
   const bool live = k0 < M.ns;
@@ -735,8 +745,10 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   const Rec4 selfv = ldrec(st.SVb, ks);
   const double2 vp = make_double2(selfv.a, selfv.b);
   const Stress4 sp_ = ld4(st.SFb, ks);
+  // own position: the CSPM matrix pass needs it for every entry, the wall-partner terms only next to a wall (there
+  // it is read where it is used instead of by every stress particle in every stage)
   double2 xp = make_double2(0.0, 0.0);
-  if ((FIRST && P.cspm) || P.ndummy > 0) xp = ld2(st.x, id);
+  if (FIRST && P.cspm) xp = ld2(st.x, id);
   double ae1 = 0.0, ae2 = 0.0, ae3 = 0.0, ae4 = 0.0, ae5 = 1.0;
   double g11 = 0.0, g12 = 0.0, g21 = 0.0, g22 = 0.0;  // grad1_tmp(d,k): d velocity component, k direction
     auto entry_slow = [&](int q, int a1, int a2, const Rec4 &r) {
@@ -759,12 +771,13 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
         const double beta_max = 1.5, vel_wall = 0.0;
         const double wall = (double)st.wallpos[q];
         const double2 xq = ld2(st.x, q);
+        const double2 xo = (FIRST && P.cspm) ? xp : ld2(st.x, id);
         double da, db;
         if (st.horiz[q] == 1.f) {
-          da = fabs(xp.y - wall);
+          da = fabs(xo.y - wall);
           db = fabs(xq.y - wall);
         } else {
-          da = fabs(xp.x - wall);
+          da = fabs(xo.x - wall);
           db = fabs(xq.x - wall);
         }
         const double bq = 1 + (db / da);
@@ -869,7 +882,7 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   // plastic_terms, mat:1884-1954
   double Gs[4] = {0.0, 0.0, 0.0, 0.0}, der1 = 0.0;
   plastic_terms(P, sp_, g11, g12, g21, g22, st.epsp + id, st.fdp + id, Gs, der1);
-  const double rke = st.RKe[ks] + der1 * f2;
+  const double rke = (stage1 ? 0.0 : st.RKe[ks]) + der1 * f2;
   // Jaumann terms, main:751-757
   double sp1 = 0.0, sp2 = 0.0, sp3 = 0.0, sp4 = 0.0;
   if (P.update_x) {
@@ -882,7 +895,7 @@ k_sweep_b_sp(DevParams P, SlotMap M, const int *__restrict__ order_s, ListPtrs L
   const double r2 = -d2 + sp2 + Gs[1];
   const double r3 = -d3 + sp3 + Gs[2];
   const double r4 = -d4 + sp4 + Gs[3];
-  Stress4 rk = ld4(st.RKs, ks);
+  Stress4 rk = stage1 ? Stress4{0.0, 0.0, 0.0, 0.0} : ld4(st.RKs, ks);
   rk.s1 = rk.s1 + f2 * r1;
   rk.s2 = rk.s2 + f2 * r2;
   rk.s3 = rk.s3 + f2 * r3;
@@ -1004,7 +1017,9 @@ k_artvisc(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, c
 template <bool FIRST>
 __global__ void __launch_bounds__(SWEEP_T, SPSPH_BN_MINB)
 k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs L, const int *__restrict__ n0,
-               StatePtrs st, double f1next, double f2, int last) {
+               StatePtrs st, double f1next, double f2, int stage_flags) {
+  const int last = stage_flags & 1;     // see k_sweep_b_sp
+  const bool stage1 = stage_flags & 2;
   const int k0 = blockIdx.x * blockDim.x + threadIdx.x;
   if ((k0 & ~31) >= M.nn) return;  // whole warp past the end
   const bool live = k0 < M.nn;
@@ -1154,7 +1169,7 @@ k_sweep_b_node(DevParams P, SlotMap M, const int *__restrict__ order_n, ListPtrs
   const double2 af = st.has_aforce ? ld2(st.aforce, id) : make_double2(0.0, 0.0);
   const double r1 = -dv1 + sg1 + av1 + fb.x + af.x;
   const double r2 = -dv2 + sg2 + av2 + fb.y + af.y;
-  double2 rk = ld2(st.RKv, id);
+  double2 rk = stage1 ? make_double2(0.0, 0.0) : ld2(st.RKv, id);
   rk.x = rk.x + f2 * r1;
   rk.y = rk.y + f2 * r2;
   const double2 v0 = ld2(st.vel0, id);

@@ -1,7 +1,7 @@
 #!/bin/bash
 # bench.py at N ranks of one box: gpurun --gpus N -- 'bash tools/gpu_scale.sh N'
 n=${1:-2}
-out=gpurun_out/scale_r2
+out=${2:-gpurun_out/scale_r3}
 mkdir -p $out
 python __graft_entry__.py > $out/build_n$n.log 2>&1
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $n --master-addr 127.0.0.1 --master-port 29551 \
