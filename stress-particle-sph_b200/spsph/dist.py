@@ -151,6 +151,39 @@ def rebalance(planes, owned_counts, H, gain=0.5):
     return new
 
 
+def rebalance_cost(problem, planes, cost_ms, H, x_nodes=None, gain=0.8, iters=60):
+    """Cost-weighted re-slabbing: moves the interior planes so that every rank's MEASURED pair work becomes equal (a rank
+    that holds a wall pays more per particle than an interior one). planes: current planes (nranks + 1); cost_ms: what
+    every rank spent in its per-particle kernels per step (the same list on every rank, e.g. an all-gather of the sums of
+    Engine.profile_get() without the entries that contain waits); x_nodes: current x of the velocity particles (default:
+    the problem's initial positions). Model: a rank's cost = its measured cost per processed velocity particle x the
+    velocity particles in [lo - H, hi + H]. A plane moves by at most 0.4 H in total (spsph_dist_set_planes accepts 0.5 H)."""
+    p = problem.params
+    planes0 = np.array(planes, dtype=np.float64)
+    nr = len(planes0) - 1
+    if nr < 2:
+        return planes0
+    xn = np.sort(np.asarray(problem.arrays["x"][:p.nnode, 0] if x_nodes is None else x_nodes, dtype=np.float64))
+
+    def processed(pl):
+        lo = np.where(np.isfinite(pl[:-1]), pl[:-1] - H, -np.inf)
+        hi = np.where(np.isfinite(pl[1:]), pl[1:] + H, np.inf)
+        return (np.searchsorted(xn, hi) - np.searchsorted(xn, lo)).astype(np.float64)
+
+    n0 = np.maximum(processed(planes0), 1.0)
+    c = np.asarray(cost_ms, dtype=np.float64) / n0  # ms per processed velocity particle, kept fixed
+    span = max(xn[-1] - xn[0], 1e-300)
+    lam = len(xn) / span                           # velocity particles per unit x (lattice set-ups: uniform in x)
+    pl = planes0.copy()
+    for _ in range(iters):
+        cost = c * processed(pl)
+        for r in range(1, nr):
+            # the more expensive side gives particles to the cheaper one
+            d = gain * (cost[r] - cost[r - 1]) / ((c[r] + c[r - 1]) * lam)
+            pl[r] = float(np.clip(pl[r] + d, planes0[r] - 0.4 * H, planes0[r] + 0.4 * H))
+    return pl
+
+
 def merge_owned(per_rank_arrays, per_rank_flags, params):
     """assemble the global state from every rank's download: entry i comes from the rank that owns particle i"""
     out = {k: v.copy() for k, v in per_rank_arrays[0].items()}

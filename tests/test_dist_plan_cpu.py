@@ -68,3 +68,35 @@ def test_dependent_sweep_count(deck_dir):
     from spsph import dist
     assert dist.dependent_sweeps(spsph.load(deck_dir("bui"), "bui").params) == 11   # shift + 8 + final + XSPH
     assert dist.dependent_sweeps(spsph.load(deck_dir("vs"), "vs").params) == 9
+
+
+def test_cost_weighted_planes(tmp_path):
+    """spsph.dist.rebalance_cost: a rank that pays more per particle (the side wall) hands particles to its neighbours;
+    the modelled maximum cost drops, no plane moves further than spsph_dist_set_planes accepts, the order is kept"""
+    sys.path.insert(0, os.path.join(ROOT, "stress-particle-sph_b200"))
+    import spsph
+    from spsph import decks, dist
+    d = str(tmp_path / "deck")
+    decks.write_deck(d, decks.refined_bui_spec(ncol=408, maxtimestep=5))
+    prob = spsph.load(d, "bui")
+    plan = dist.plan_slabs(prob, 8)
+    planes, H = np.array(plan["planes"]), plan["H"]
+    xn = np.sort(prob.arrays["x"][:prob.params.nnode, 0])
+
+    def processed(pl):
+        lo = np.where(np.isfinite(pl[:-1]), pl[:-1] - H, -np.inf)
+        hi = np.where(np.isfinite(pl[1:]), pl[1:] + H, np.inf)
+        return (np.searchsorted(xn, hi) - np.searchsorted(xn, lo)).astype(float)
+
+    n0 = processed(planes)
+    per_particle = np.array([1.08, 1.0, 1.0, 1.0, 1.0, 1.0, 1.0, 0.96])  # ms per processed particle, relative
+    cost0 = per_particle * n0
+    new = dist.rebalance_cost(prob, planes, cost0, H)
+    cost1 = per_particle * processed(new)
+    assert cost1.max() < cost0.max() * 0.985, (cost0, cost1)
+    assert cost1[:-1].max() / cost1[:-1].min() < 1.07  # (the last slab takes what is left and may hit the 0.4 H bound)
+    assert np.all(np.abs(new[1:-1] - planes[1:-1]) <= 0.4 * H + 1e-12)
+    assert np.all(np.diff(new[1:-1]) > H)
+    # every rank already costs the same: nothing moves
+    same = dist.rebalance_cost(prob, planes, np.full(8, 1.0), H)
+    assert np.allclose(same[1:-1], planes[1:-1], atol=0.02 * H)
