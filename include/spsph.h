@@ -147,6 +147,22 @@ int spsph_dist_set_planes(spsph_handle *h, const double *planes);
  * arrays (1_SPH_2018.f90:132,156). */
 int spsph_upload_rows(spsph_handle *h, const spsph_state *s, const int32_t *ids, int32_t n);
 int spsph_download_rows(spsph_handle *h, const spsph_state *s, const int32_t *ids, int32_t n);
+/* Output frame packed on the device (host formats): what OutputRes prints per particle
+ * (3_SPH_material_2018.f90:2919-3060: ParaView rows "x, y, [vel], [stress], [strain], [disp_10], [density], [sml]"
+ * selected by the *_out switches; GiD results :2930-3008 "disp", "vel", "sigma..", "plastic strain") gathered into one
+ * row-major (count, ncols) table of doubles for the particles first .. first+count-1 (0-based reference numbering) and
+ * copied out in a single transfer, instead of a spsph_download of every array. cols: ncols <= SPSPH_FRAME_MAX_COLS
+ * column codes in the order the writer prints them. Columns that exist only for velocity particles (DISP10, DISPLX/Y)
+ * read 0 for the others; wall particles carry x, y, RHO, HSML only. BC_OR_NOT (2 = node on the free surface, as
+ * written to surface_points.csv, mat:3061-3078) runs get_nodes_on_free_surface first, like spsph_download. */
+enum {
+  SPSPH_COL_X = 0, SPSPH_COL_Y, SPSPH_COL_VX, SPSPH_COL_VY, SPSPH_COL_SXX, SPSPH_COL_SYY, SPSPH_COL_SXY,
+  SPSPH_COL_SZZ, SPSPH_COL_EPSP, SPSPH_COL_DISP10, SPSPH_COL_RHO, SPSPH_COL_HSML, SPSPH_COL_DISPLX,
+  SPSPH_COL_DISPLY, SPSPH_COL_FDRUCKER, SPSPH_COL_BC_OR_NOT, SPSPH_COL_COUNT
+};
+#define SPSPH_FRAME_MAX_COLS 16
+int spsph_download_frame(spsph_handle *h, const int32_t *cols, int32_t ncols, int32_t first, int32_t count,
+                         double *out);
 /* particles per species (velocity, stress, wall) this rank processed in the last step: its slab + halo */
 int spsph_local_counts(spsph_handle *h, int32_t *nloc3);
 /* checkpoint support (the reference has none: SURVEY section 5). Everything a restart needs is in spsph_state except

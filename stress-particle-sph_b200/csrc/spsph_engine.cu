@@ -172,6 +172,8 @@ struct spsph_handle {
   int *rows_ids = nullptr;
   char *rows_buf = nullptr;
   size_t rows_cap = 0;
+  double *frame_buf = nullptr;  // spsph_download_frame: the packed (count, ncols) table
+  size_t frame_cap = 0;
 
   long long m_pairs = 0;       // max pair count of all previous steps (main:1210)
   long long last_n_pairs = 0;  // of the last step
@@ -1955,6 +1957,7 @@ static int rows_prepare(spsph_handle *h, const int32_t *ids, int32_t n, int *n_n
   const size_t need = (size_t)(n > 0 ? n : 1) * 256;  // every array of a row set at once (< 200 bytes per row)
   if (need > h->rows_cap) {
     cudaFree(h->rows_buf);
+  cudaFree(h->frame_buf);
     cudaFree(h->rows_ids);
     h->rows_buf = nullptr;
     h->rows_ids = nullptr;
@@ -2084,6 +2087,73 @@ int spsph_sync(spsph_handle *h) {
   return 0;
 }
 
+// get_nodes_on_free_surface (main:152-154 runs it at the end of every step; only bc_or_not leaves it): evaluated when
+// somebody asks for the marks, with the last step's pair lists, unless the configuration needs it every step anyway
+static int free_surface_on_demand(spsph_handle *h) {
+  if (!h->hp.update_x || h->fs_each_step) return 0;
+  if (materialize_lists(h)) return 1;
+  if (!h->have_lists) return 0;
+  SlotMap ML = h->M;
+  ML.nn = h->nloc[0];
+  ML.ns = h->nloc[1];
+  ML.nd = h->nloc[2];
+  const int T = ML.nnp + ML.nsp;
+  k_free_surface<<<(T + 127) / 128, 128, 0, h->stream>>>(h->P, ML, sort_arrays(h), h->pos_of, h->L, h->n0, h->n1,
+                                                         h->growth, h->x_fs_valid ? h->x_fs : h->x, h->mass, h->rho,
+                                                         h->hsml, h->bc_or_not, nullptr);
+  CUDA_TRY(cudaGetLastError());
+  return 0;
+}
+
+int spsph_download_frame(spsph_handle *h, const int32_t *cols, int32_t ncols, int32_t first, int32_t count,
+                         double *out) {
+  if (!h) return 1;
+  if (!h->uploaded) {
+    h->err = "spsph_download_frame: nothing uploaded yet";
+    return 1;
+  }
+  if (!cols || ncols < 1 || ncols > SPSPH_FRAME_MAX_COLS) {
+    h->err = "spsph_download_frame: 1 .. SPSPH_FRAME_MAX_COLS column codes are required";
+    return 1;
+  }
+  if (first < 0 || count < 0 || (long long)first + count > h->hp.ntotal2 || (count > 0 && !out)) {
+    h->err = "spsph_download_frame: particle range outside [0, ntotal2) or no output table";
+    return 1;
+  }
+  static_assert(SPSPH_COL_COUNT <= 16 && SPSPH_FRAME_MAX_COLS <= 16, "FrameCols packs 4 bits per column");
+  FrameCols C;
+  C.n = ncols;
+  C.codes = 0;
+  bool marks = false;
+  for (int k = 0; k < ncols; ++k) {
+    if (cols[k] < 0 || cols[k] >= SPSPH_COL_COUNT) {
+      h->err = "spsph_download_frame: unknown column code";
+      return 1;
+    }
+    C.codes |= (unsigned long long)cols[k] << (4 * k);
+    marks |= cols[k] == SPSPH_COL_BC_OR_NOT;
+  }
+  CUDA_TRY(cudaSetDevice(h->device));
+  if (count == 0) return 0;
+  if (marks && free_surface_on_demand(h)) return 1;
+  const long long nelem = (long long)count * ncols;
+  const size_t bytes = (size_t)nelem * sizeof(double);
+  if (bytes > h->frame_cap) {
+    cudaFree(h->frame_buf);
+    h->frame_buf = nullptr;
+    h->frame_cap = 0;
+    CUDA_TRY(cudaMalloc((void **)&h->frame_buf, bytes + bytes / 8));
+    h->frame_cap = bytes + bytes / 8;
+  }
+  cudaStream_t st = h->stream;
+  k_pack_frame<<<(unsigned)((nelem + 255) / 256), 256, 0, st>>>(h->P, state_ptrs(h, h->cur), C, h->displ, h->disp_10,
+                                                                first, nelem, h->frame_buf);
+  CUDA_TRY(cudaGetLastError());
+  CUDA_TRY(cudaMemcpyAsync(out, h->frame_buf, bytes, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return 0;
+}
+
 int spsph_download(spsph_handle *h, const spsph_state *s) {
   if (!h || !s) return 1;
   const spsph_params &p = h->hp;
@@ -2112,19 +2182,7 @@ int spsph_download(spsph_handle *h, const spsph_state *s) {
     k_download_ivars<<<((int)nt + 255) / 256, 256, 0, st>>>((int)nt, h->epsp, h->ivars);
     CUDA_TRY(down(s->internal_vars, h->ivars, (size_t)SPSPH_NINT_VARS * nt * 8));
   }
-  if (s->bc_or_not && p.update_x && !h->fs_each_step && materialize_lists(h)) return 1;
-  if (s->bc_or_not && p.update_x && h->have_lists && !h->fs_each_step) {
-    // get_nodes_on_free_surface (main:152-154 runs it at the end of every step; only bc_or_not leaves it)
-    SlotMap ML = h->M;
-    ML.nn = h->nloc[0];
-    ML.ns = h->nloc[1];
-    ML.nd = h->nloc[2];
-    const int T = ML.nnp + ML.nsp;
-    k_free_surface<<<(T + 127) / 128, 128, 0, st>>>(h->P, ML, sort_arrays(h), h->pos_of, h->L, h->n0, h->n1, h->growth,
-                                                    h->x_fs_valid ? h->x_fs : h->x, h->mass, h->rho, h->hsml,
-                                                    h->bc_or_not, nullptr);
-    CUDA_TRY(cudaGetLastError());
-  }
+  if (s->bc_or_not && free_surface_on_demand(h)) return 1;
   CUDA_TRY(down(s->f_drucker, h->fdp, nt * 8));
   CUDA_TRY(down(s->x00, h->x00, 2 * n2 * 8));
   CUDA_TRY(down(s->displ, h->displ, 2 * nn * 8));

@@ -384,6 +384,51 @@ __global__ void k_unpack_state(DevParams P, StatePtrs st, double *__restrict__ v
   }
 }
 
+// Output frame packed on the device (OutputRes, mat:2919-3060: the ParaView rows "x, y, [vel], [stress], [strain],
+// [disp_10], [density], [sml]"; GiD results mat:2930-3008): one thread per (particle, column) element of a
+// row-major (count, ncols) table, so a frame leaves the device in ONE copy holding only the columns the writers print.
+// Velocity-particle-only columns read 0 for stress particles, wall particles carry positions / rho / h only.
+struct FrameCols {
+  int n;
+  unsigned long long codes;  // 4 bits per column (SPSPH_COL_COUNT <= 16, SPSPH_FRAME_MAX_COLS = 16)
+};
+__global__ void k_pack_frame(DevParams P, StatePtrs st, FrameCols C, const double *__restrict__ displ,
+                             const double *__restrict__ disp_10, int first, long long nelem, double *__restrict__ out) {
+  const long long e = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= nelem) return;
+  const int id = first + (int)(e / C.n);
+  const int c = (int)(C.codes >> (4 * (int)(e % C.n))) & 15;
+  const bool node = id < P.nnode, part = id < P.ntotal;
+  double v = 0.0;
+  switch (c) {
+    case SPSPH_COL_X: v = st.x[2 * (size_t)id]; break;
+    case SPSPH_COL_Y: v = st.x[2 * (size_t)id + 1]; break;
+    case SPSPH_COL_VX:
+    case SPSPH_COL_VY:
+      if (part) {
+        const Rec4 r = node ? ldrec(st.NB, id) : ldrec(st.SVb, id - P.nnode);
+        v = c == SPSPH_COL_VX ? r.a : r.b;
+      }
+      break;
+    case SPSPH_COL_SXX:
+    case SPSPH_COL_SYY:
+    case SPSPH_COL_SXY:
+    case SPSPH_COL_SZZ:
+      if (part) v = (node ? st.NSb + 4 * (size_t)id : st.SFb + 4 * (size_t)(id - P.nnode))[c - SPSPH_COL_SXX];
+      break;
+    case SPSPH_COL_EPSP: if (part) v = st.epsp[id]; break;
+    case SPSPH_COL_FDRUCKER: if (part) v = st.fdp[id]; break;
+    case SPSPH_COL_DISP10: if (node) v = disp_10[id]; break;
+    case SPSPH_COL_DISPLX: if (node) v = displ[2 * (size_t)id]; break;
+    case SPSPH_COL_DISPLY: if (node) v = displ[2 * (size_t)id + 1]; break;
+    case SPSPH_COL_RHO: v = st.rho[id]; break;
+    case SPSPH_COL_HSML: v = st.hsml[id]; break;
+    case SPSPH_COL_BC_OR_NOT: if (part) v = (double)st.bc_or_not[id]; break;
+    default: break;
+  }
+  out[e] = v;
+}
+
 // ------------------------------------------------------------------------------------------------------
 // RK4 prologue (main:681-690 + first predictor main:700-701 with f1rk = 0 + adapt_stress2/BCs main:715-716):
 // format B (state) -> format A (stage-1 input); saves vel0/stress0/vx0 and zeroes the RK accumulators.

@@ -159,6 +159,16 @@ module spsph_c_api
        integer(c_int32_t), intent(in) :: ids(*)
        integer(c_int32_t), value :: n
      end function
+     ! output frame packed on the device: out(ncols, count) in Fortran order == the C side's (count, ncols) rows;
+     ! cols = SPSPH_COL_* codes (0 x, 1 y, 2 vx, 3 vy, 4-7 stress, 8 plastic strain, 9 disp_10, 10 rho, 11 hsml,
+     ! 12-13 displ, 14 f_drucker, 15 bc_or_not), first = 0-based particle number
+     integer(c_int) function spsph_download_frame(h, cols, ncols, first, count, out) bind(C, name="spsph_download_frame")
+       import :: c_ptr, c_int, c_int32_t, c_double
+       type(c_ptr), value :: h
+       integer(c_int32_t), intent(in) :: cols(*)
+       integer(c_int32_t), value :: ncols, first, count
+       real(c_double), intent(out) :: out(*)
+     end function
      integer(c_int) function spsph_path_counts(h, tile_steps, list_steps) bind(C, name="spsph_path_counts")
        import :: c_ptr, c_int, c_int64_t
        type(c_ptr), value :: h

@@ -5,6 +5,7 @@
 // same C-ABI through fortran/spsph_shim.f90.
 //
 // usage: sph_driver <deck directory> <variant: code|bui|vs|sl> [--max-steps N] [--out DIR] [--device D]
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -69,6 +70,49 @@ static void output_res(spsph::Problem &P, int itimestep_sph, double time_sph, co
   std::fclose(f);
 }
 
+// What the writers above print, fetched as ONE table packed on the device (spsph_download_frame) instead of a
+// spsph_download of every array: 15 columns per velocity particle, 11 per stress particle, against the 40 doubles per
+// particle of the full state. The rows are spread over the Problem's arrays, which the writers read.
+static int download_frame(spsph_handle *h, spsph::Problem &P) {
+  const spsph_params &p = P.p;
+  static const int32_t node_cols[] = {SPSPH_COL_X,    SPSPH_COL_Y,      SPSPH_COL_VX,     SPSPH_COL_VY,       SPSPH_COL_SXX,
+                                      SPSPH_COL_SYY,  SPSPH_COL_SXY,    SPSPH_COL_SZZ,    SPSPH_COL_EPSP,     SPSPH_COL_DISP10,
+                                      SPSPH_COL_RHO,  SPSPH_COL_HSML,   SPSPH_COL_DISPLX, SPSPH_COL_DISPLY,   SPSPH_COL_BC_OR_NOT};
+  static const int32_t sp_cols[] = {SPSPH_COL_X,   SPSPH_COL_Y,   SPSPH_COL_VX,   SPSPH_COL_VY,  SPSPH_COL_SXX, SPSPH_COL_SYY,
+                                    SPSPH_COL_SXY, SPSPH_COL_SZZ, SPSPH_COL_EPSP, SPSPH_COL_RHO, SPSPH_COL_HSML};
+  const int wn = sizeof node_cols / sizeof *node_cols, ws = sizeof sp_cols / sizeof *sp_cols;
+  const int nn = p.nnode, ns = p.ntotal - p.nnode;
+  static std::vector<double> tab;
+  tab.resize(std::max((size_t)nn * wn, (size_t)ns * ws) + 1);
+  auto common = [&](const double *r, size_t i) {
+    P.x[2 * i] = r[0];
+    P.x[2 * i + 1] = r[1];
+    P.vel[2 * i] = r[2];
+    P.vel[2 * i + 1] = r[3];
+    for (int c = 0; c < 4; ++c) P.stress[4 * i + c] = r[4 + c];
+    P.internal_vars[(size_t)SPSPH_NINT_VARS * i] = r[8];
+  };
+  if (spsph_download_frame(h, node_cols, wn, 0, nn, tab.data())) return 1;
+  for (size_t i = 0; i < (size_t)nn; ++i) {
+    const double *r = &tab[i * wn];
+    common(r, i);
+    P.disp_10[i] = r[9];
+    P.rho[i] = r[10];
+    P.hsml[i] = r[11];
+    P.displ[2 * i] = r[12];
+    P.displ[2 * i + 1] = r[13];
+    P.bc_or_not[i] = (int)r[14];
+  }
+  if (spsph_download_frame(h, sp_cols, ws, nn, ns, tab.data())) return 1;
+  for (size_t k = 0; k < (size_t)ns; ++k) {
+    const double *r = &tab[k * ws];
+    common(r, nn + k);
+    P.rho[nn + k] = r[9];
+    P.hsml[nn + k] = r[10];
+  }
+  return 0;
+}
+
 int main(int argc, char **argv) {
   if (argc < 3) {
     std::fprintf(stderr, "usage: %s <deck dir> <code|bui|vs|sl> [--max-steps N] [--out DIR] [--device D]\n", argv[0]);
@@ -126,7 +170,7 @@ int main(int argc, char **argv) {
       if (time > b.time_end) break;  // 1_SPH_2018.f90:82: leaves the block before any output
       const bool stop = (max_steps >= 0 && total >= max_steps);  // --max-steps (not in the reference) ends with a frame
       if (t_plot_reset >= time_plot || stop) {
-        if (spsph_download(h, &st)) return die("spsph_download");
+        if (download_frame(h, P)) return die("spsph_download_frame");
         output_res(P, itimestep_sph, time_sph, out);
         t_plot_reset = 0.f;
       }

@@ -38,6 +38,7 @@ def cuda_lib():
         L.spsph_path_counts.argtypes = [H, C.POINTER(C.c_int64), C.POINTER(C.c_int64)]
         L.spsph_upload_rows.argtypes = [H, C.POINTER(_abi.State), C.c_void_p, C.c_int32]
         L.spsph_download_rows.argtypes = [H, C.POINTER(_abi.State), C.c_void_p, C.c_int32]
+        L.spsph_download_frame.argtypes = [H, C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p]
         L.spsph_dist_unique_id.argtypes = [C.c_char_p]
         L.spsph_dist_init.argtypes = [H, C.c_int32, C.c_int32, C.c_char_p, C.POINTER(C.c_double), C.c_int32, C.c_int32]
         L.spsph_dist_flags.argtypes = [H, C.c_void_p]
@@ -57,8 +58,12 @@ EXPORTS = ["spsph_create", "spsph_upload", "spsph_step", "spsph_run", "spsph_dow
            "spsph_pairs", "spsph_last_run_ms", "spsph_sync", "spsph_profile", "spsph_profile_get",
            "spsph_dist_unique_id", "spsph_dist_init", "spsph_dist_flags", "spsph_dist_set_planes", "spsph_local_counts", "spsph_get_list_capacity",
            "spsph_set_list_capacity", "spsph_path_counts", "spsph_upload_rows",
-           "spsph_download_rows", "spsph_destroy", "spsph_last_error", "spsph_version"]
+           "spsph_download_rows", "spsph_download_frame", "spsph_destroy", "spsph_last_error", "spsph_version"]
 
+
+# column codes of spsph_download_frame (include/spsph.h, SPSPH_COL_*)
+FRAME_COLS = {n: k for k, n in enumerate(["x", "y", "vx", "vy", "sxx", "syy", "sxy", "szz", "epsp", "disp_10", "rho",
+                                          "hsml", "displ_x", "displ_y", "f_drucker", "bc_or_not"])}
 
 # row sets of the time-varying state: (rows of all ids, of ids < ntotal, of ids < nnode)
 _ROWS_ALL = ("x", "vel", "stress", "if_out_domain")
@@ -132,6 +137,18 @@ class Engine:
         st = _abi.state_from_arrays(rows)
         self._chk(self.L.spsph_download_rows(self.h, C.byref(st), ids.ctypes.data, len(ids)))
         return rows
+
+    def download_frame(self, cols, first=0, count=None, out=None):
+        """output frame packed on the device: (count, len(cols)) float64 table of the columns `cols` (names or codes of
+        FRAME_COLS, in the order a writer prints them) for the particles first .. first+count-1, one transfer"""
+        codes = np.ascontiguousarray([FRAME_COLS[c] if isinstance(c, str) else int(c) for c in cols], dtype=np.int32)
+        if count is None:
+            count = self.p.ntotal2 - first
+        if out is None:
+            out = np.zeros((count, len(codes)), np.float64)
+        assert out.dtype == np.float64 and out.flags["C_CONTIGUOUS"] and out.size == count * len(codes)
+        self._chk(self.L.spsph_download_frame(self.h, codes.ctypes.data, len(codes), first, count, out.ctypes.data))
+        return out
 
     def step(self, itimestep, time_sph, dt):
         self._chk(self.L.spsph_step(self.h, itimestep, time_sph, dt))

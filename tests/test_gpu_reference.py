@@ -44,8 +44,9 @@ def test_engine_reproduces_reference_binary(case, tmp_path):
 
 def test_driver_frames_match_reference_cadence(tmp_path):
     """host/sph_driver.cpp (the PROGRAM SPH_2018 stand-in) plots at the steps the reference executable plots (its
-    output clock is an fp32 accumulation: frames land at steps 301 and 602 for plot_step = 300) and lists the same
-    free-surface nodes in surface_points.csv"""
+    output clock is an fp32 accumulation: frames land at steps 301 and 602 for plot_step = 300), prints the reference's
+    node and stress-particle rows and lists the same free-surface nodes in surface_points.csv; its frames come from
+    spsph_download_frame (device-side packing)"""
     import subprocess
     from spsph import decks
     g = np.load(golden_path("bui_long"))
@@ -67,3 +68,6 @@ def test_driver_frames_match_reference_cadence(tmp_path):
         nodes = np.loadtxt(deck / f"nodes.csv.{step:06d}", delimiter=",", skiprows=1, usecols=range(9))
         ref = np.column_stack([g[f"n{step}_x"], g[f"n{step}_vel"], g[f"n{step}_stress"], g[f"n{step}_strain"]])
         assert np.abs(nodes - ref).max() <= 0.5e-8 * 1.0001 + 1e-8 * np.abs(ref).max() * 0, "F16.8 frames differ from the reference"
+        sps = np.loadtxt(deck / f"stress_points.csv.{step:06d}", delimiter=",", usecols=range(9))
+        ref = np.column_stack([g[f"s{step}_x"], g[f"s{step}_vel"], g[f"s{step}_stress"], g[f"s{step}_strain"]])
+        assert np.abs(sps - ref).max() <= 0.5e-8 * 1.0001, "F16.8 stress-particle frames differ from the reference"

@@ -2,6 +2,7 @@
 import ctypes as C
 import os
 import re
+import sys
 
 import numpy as np
 import pytest
@@ -431,3 +432,17 @@ def test_product_library_has_no_emulation_code():
     syms = subprocess.run(["nm", "-D", "--defined-only", so], capture_output=True, text=True, check=True).stdout
     assert "spsph_step" in syms
     assert "emu" not in syms.lower()
+
+
+def test_sass_identical_without_emulation_guards():
+    """the #ifdef SPSPH_HOST_EMU / SPSPH_EMU_* alternatives inside csrc/ are invisible to nvcc: a build from copies of
+    the sources with every such conditional resolved and deleted has the same SASS, function by function, as the
+    product library (tools/sass_guard_check.py; the committed record is profiles/r2_sass_guard_check.txt)"""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import sass_guard_check
+    text, n = sass_guard_check.strip_guards(
+        "a\n#ifdef SPSPH_HOST_EMU\nb\n#else\nc\n#endif\n#if defined(SPSPH_HOST_EMU) && !defined(SPSPH_EMU_SIMT)\nd\n"
+        "#endif\n#if !defined(SPSPH_HOST_EMU) || defined(SPSPH_EMU_SIMT)\ne\n#ifdef OTHER\nf\n#endif\n#endif\n")
+    assert (text.split(), n) == (["a", "c", "e", "#ifdef", "OTHER", "f", "#endif"], 3)
+    ok, report = sass_guard_check.check()
+    assert ok, report
