@@ -567,7 +567,6 @@ void launch_scan(spsph_handle *h, const int *in, int *out, int rows, int stride,
                  long long *totals, int kid);
 // order-preserving compaction of the local list (ids_in == nullptr: build from the flags of all particles)
 static int compact_local_list(spsph_handle *h, const int *ids_in, const int *n_in, int *ids_out, int *n_out) {
-#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   const int n2 = h->P.ntotal2;
   cudaStream_t s = h->stream;
   const int g = ids_in ? 148 * 8 : (n2 + 255) / 256;
@@ -577,9 +576,6 @@ static int compact_local_list(spsph_handle *h, const int *ids_in, const int *n_i
   k_list_scatter<<<g, 256, 0, s>>>(ids_in, n_in, n2, h->list_keep, h->list_pos, ids_out, n_out);
   CUDA_TRY(cudaGetLastError());
   return 0;
-#else
-  return 1;
-#endif  // SPSPH_HOST_EMU
 }
 static int rebuild_local_list(spsph_handle *h) {
   h->list_cur = 0;
@@ -597,7 +593,6 @@ static int halo_limit(const spsph_handle *h, int prev_count) {
   return l < h->D.cap ? (int)l : h->D.cap;
 }
 int halo_exchange(spsph_handle *h) {
-#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   const DevParams &P = h->P;
   h->D.lim[0] = halo_limit(h, h->halo_prev_send[0]);
   h->D.lim[1] = halo_limit(h, h->halo_prev_send[1]);
@@ -646,9 +641,6 @@ int halo_exchange(spsph_handle *h) {
   h->list_cur = 1 - h->list_cur;
   mark(h, KID_HALO, 9);
   return 0;
-#else
-  return 1;
-#endif  // SPSPH_HOST_EMU
 }
 
 // neighbour search up to and including the list fill; leaves the pair totals in h->status_h
@@ -726,11 +718,13 @@ void emu_bbox(spsph_handle *h) {  // k_domain_bbox + k_bbox_final: Check_Out_Dom
   const DevParams &P = h->P;
   double xmn = 1.e+10, ymn = 1.e+10, xmx = -1.e+10, ymx = -1.e+10, hmx = 0.0, hmn = 1.e+300;
   for (int i = 0; i < P.ntotal2; ++i) {
+    const int lf = h->dist ? h->lflag[i] : 1;  // slab run: remote particles are skipped, only owned ones enter the bounds
+    if (lf == 0) continue;
     const double px = h->x[2 * (size_t)i], py = h->x[2 * (size_t)i + 1];
     const double dxx = (px - P.xmin_dom[0]) * (px - P.xmax_dom[0]);
     const double dyy = (py - P.xmin_dom[1]) * (py - P.xmax_dom[1]);
     if (dxx > 0.0 || dyy > 0.0) h->if_out[i] = 1;
-    if (h->if_out[i]) continue;
+    if (h->if_out[i] || lf != 1) continue;
     xmn = std::fmin(xmn, px);
     xmx = std::fmax(xmx, px);
     ymn = std::fmin(ymn, py);
@@ -2257,8 +2251,15 @@ int spsph_pairs(spsph_handle *h, int64_t *npairs, int32_t *pair_i, int32_t *pair
   return rc;
 }
 
+// the NCCL library: libnccl.so.2 from the loader's search path (torch's bundled copy when the caller imported torch),
+// or the file SPSPH_NCCL_SO names (another NCCL build; the CPU tests put a file-based stand-in there)
+static const char *nccl_library() {
+  const char *e = std::getenv("SPSPH_NCCL_SO");
+  return (e && *e) ? e : "libnccl.so.2";
+}
+
 int spsph_dist_unique_id(char *id128) {
-  void *lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  void *lib = dlopen(nccl_library(), RTLD_NOW | RTLD_GLOBAL);
   if (!lib) return 1;
   auto f = (ncclResult_t(*)(ncclUniqueId *))dlsym(lib, "ncclGetUniqueId");
   if (!f) return 1;
@@ -2270,7 +2271,6 @@ int spsph_dist_unique_id(char *id128) {
 
 int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *id128, const double *planes,
                     int32_t halo_cells, int32_t halo_capacity) {
-#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   if (!h || !planes || nranks < 1 || rank < 0 || rank >= nranks) return 1;
   if (!h->uploaded) {
     h->err = "spsph_dist_init must follow spsph_upload (every rank uploads the complete problem)";
@@ -2278,9 +2278,9 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
   }
   CUDA_TRY(cudaSetDevice(h->device));
   const spsph_params &p = h->hp;
-  h->nccl_lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+  h->nccl_lib = dlopen(nccl_library(), RTLD_NOW | RTLD_GLOBAL);
   if (!h->nccl_lib) {
-    h->err = std::string("cannot load libnccl.so.2: ") + dlerror();
+    h->err = std::string("cannot load ") + nccl_library() + ": " + dlerror();
     return 1;
   }
 #define NCCL_SYM(name)                                                            \
@@ -2344,13 +2344,9 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
   if (rebuild_local_list(h)) return 1;
   CUDA_TRY(cudaStreamSynchronize(h->stream));
   return 0;
-#else
-  return 1;
-#endif  // SPSPH_HOST_EMU
 }
 
 int spsph_dist_set_planes(spsph_handle *h, const double *planes) {
-#ifndef SPSPH_HOST_EMU
   if (!h || !planes) return 1;
   if (!h->dist) {
     h->err = "spsph_dist_set_planes: not a multi-GPU run";
@@ -2373,9 +2369,6 @@ int spsph_dist_set_planes(spsph_handle *h, const double *planes) {
   D.hi = hi;
   h->halo_prev_valid = false;  // the next messages also carry the particles that change slab: full-capacity transfers
   return 0;
-#else
-  return 1;
-#endif
 }
 
 int spsph_local_counts(spsph_handle *h, int32_t *nloc3) {
@@ -2385,7 +2378,6 @@ int spsph_local_counts(spsph_handle *h, int32_t *nloc3) {
 }
 
 int spsph_dist_flags(spsph_handle *h, int32_t *flags) {
-#ifndef SPSPH_HOST_EMU  // device only (tests/native/: the host emulation imports its lists from the oracle)
   if (!h || !flags) return 1;
   CUDA_TRY(cudaSetDevice(h->device));
   CUDA_TRY(cudaStreamSynchronize(h->stream));
@@ -2395,9 +2387,6 @@ int spsph_dist_flags(spsph_handle *h, int32_t *flags) {
   }
   CUDA_TRY(cudaMemcpy(flags, h->lflag, (size_t)h->hp.ntotal2 * sizeof(int), cudaMemcpyDeviceToHost));
   return 0;
-#else
-  return 1;
-#endif  // SPSPH_HOST_EMU
 }
 
 int spsph_destroy(spsph_handle *h) {

@@ -37,9 +37,11 @@ def _built(tmp_path_factory):
 def pytest_collection_modifyitems(config, items):
     if not os.environ.get("SPSPH_EMULATE"):
         return
-    skip = pytest.mark.skip(reason="not available on the host-emulated engine (multi-GPU, 4 M particles, driver binary)")
+    skip = pytest.mark.skip(reason="not available on the serial host-emulated engine (multi-GPU, 4 M particles, driver "
+                                   "binary; the tile kernels' warp collectives need the SIMT emulation: "
+                                   "tests/test_step_emulation_cpu.py::test_emulated_engine_simt_mode_tile_path)")
     for it in items:
-        if any(k in it.nodeid for k in ("test_multi_gpu", "4m_bitwise", "driver_frames", "bui_full")):
+        if any(k in it.nodeid for k in ("test_multi_gpu", "4m_bitwise", "driver_frames", "bui_full", "test_gpu_tile_path")):
             it.add_marker(skip)
 
 

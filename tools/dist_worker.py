@@ -29,7 +29,13 @@ def main():
     import torch.distributed as td
     rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
     local = int(os.environ.get("LOCAL_RANK", rank))
-    torch.cuda.set_device(local)
+    emu = os.environ.get("SPSPH_EMU_SO")
+    if emu:  # tests/test_dist_emulated_cpu.py: the host-emulated engine (no GPU), NCCL replaced through SPSPH_NCCL_SO
+        import spsph.engine as E
+        E._lib, E._CUDA_SO = None, emu
+        local = 0
+    else:
+        torch.cuda.set_device(local)
     td.init_process_group("gloo")
     d = tempfile.mkdtemp()
     if a.kind == "refined_bui":

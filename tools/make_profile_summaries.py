@@ -96,7 +96,12 @@ def kernel_summaries():
     b = [traffic[k] for k in ("k_sweep_b_sp", "k_sweep_b_node", "k_artvisc") if k in traffic]
     if len(b) == 3:
         per_launch = sum(t["dram_read"] + t["dram_write"] for t in b)  # one stage
+        import bench  # SASS hashes of the captured kernels in the library built from these sources (bench.py compares)
+        sass = {m: v for m, v in bench.kernel_sass_hashes().items() if any(f"{len(n)}{n}" in m for n in traffic)}
         json.dump({"dram_bytes_per_launch": per_launch, "csrc_sha256": csrc_hash(), "round": TAG,
+                   "kernel_sass_sha256": sass,
+                   "sass_tie": "SASS hashes of every instantiation of the captured kernels in the library built from "
+                               "csrc_sha256 (the build the capture ran)",
                    "note": "dram__bytes_read.sum + dram__bytes_write.sum of one k_sweep_b_sp + one k_sweep_b_node + one "
                            "k_artvisc launch (= one RK stage of sweep B, the unit bench.py times as 'k_sweep_b'), "
                            "ncu --set full, 4 002 483-particle refined Bui column",
