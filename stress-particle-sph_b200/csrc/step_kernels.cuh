@@ -21,6 +21,7 @@
 // kernel only gathers from the format it does not write, so there are no read/write races.
 // List rows are streamed through shared memory with cp.async (ell_stream), four entries in flight per thread.
 #pragma once
+#include "spsph.h"  // SPSPH_COL_* column codes of k_pack_frame
 #include "grid_kernels.cuh"
 
 namespace spsph {
