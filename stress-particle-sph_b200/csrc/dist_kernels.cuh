@@ -459,4 +459,40 @@ __global__ void k_gt_finish(const long long *__restrict__ out2, const GtSel *__r
   if (sel->err || out2[2] != 1) *err = 1;
 }
 
+// ------------------------------------------------------------------------------------------------------
+// Halo peeling. The ghost region is computed redundantly and loses one cut-off distance u of validity per dependent
+// sweep, so a ghost at depth floor(d / u) (d = distance from this rank's slab) stops mattering once more sweeps have
+// run than the halo is cells deep. The pair-sum kernels take the list lengths as an argument: handing them copies in
+// which the lengths of the ghosts that are too deep for a sweep are zero skips those ghosts' list walks without any
+// change to the kernels. Level l = 1 .. PEEL_LEVELS serves the sweeps 3 l + 1 .. 3 l + 3 of a step (1-based) and keeps
+// depth <= halo_cells - (3 l + 1); the sweeps 1 .. 3 use the original arrays.
+//   Bit-identical on every particle that is still computed, by induction over the sweeps: a particle computed in
+//   sweep j has d < (halo_cells - j + 1) u, its partners are at most u further out, i.e. inside what sweep j - 1 computed.
+// ------------------------------------------------------------------------------------------------------
+constexpr int PEEL_LEVELS = 3;
+__host__ __device__ inline int peel_max_depth(int halo_cells, int level) {
+  const int m = halo_cells - (3 * level + 1);
+  return m > 0 ? m : 0;  // owned particles (depth 0) are never peeled
+}
+__global__ void k_peel_counts(SlotMap M, SortArrays S, DistGeom D, int halo_cells, const int *__restrict__ n0,
+                              const int *__restrict__ n1, int *__restrict__ p0, int *__restrict__ p1, size_t stride) {
+  const double inv_u = (double)halo_cells / D.H;
+  const int T = M.nnp + M.nsp;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < T; t += gridDim.x * blockDim.x) {
+    int sp, k;
+    if (!slot_decode(M, t, sp, k)) continue;  // padding, or a slot past this rank's local particles: never read
+    const double x = S.pos[sp][k].x;
+    const double d = fmax(fmax(D.lo - x, x - D.hi), 0.0);
+    const double q = d * inv_u;
+    const int depth = q < 1.0e6 ? (int)q : 1000000;
+    const int a = n0[t], b = n1[t];
+#pragma unroll
+    for (int l = 1; l <= PEEL_LEVELS; ++l) {
+      const bool keep = depth <= peel_max_depth(halo_cells, l);
+      p0[(size_t)(l - 1) * stride + t] = keep ? a : 0;
+      p1[(size_t)(l - 1) * stride + t] = keep ? b : 0;
+    }
+  }
+}
+
 }  // namespace spsph

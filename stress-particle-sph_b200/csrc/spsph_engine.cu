@@ -172,6 +172,11 @@ struct spsph_handle {
   int *rows_ids = nullptr;
   char *rows_buf = nullptr;
   size_t rows_cap = 0;
+  // halo peeling (dist_kernels.cuh, k_peel_counts): per-level copies of the list-length arrays n0 / n1
+  int *peel0 = nullptr, *peel1 = nullptr;
+  size_t peel_stride = 0;
+  int halo_cells = 0;
+  bool peel = false;
   double *frame_buf = nullptr;  // spsph_download_frame: the packed (count, ncols) table
   size_t frame_cap = 0;
 
@@ -1231,16 +1236,16 @@ static int materialize_lists(spsph_handle *h) {
 #define SPSPH_LAUNCH_A_SP(FIRST, FROMB, GRID, STREAM, ST, DOBC)                                                       \
   do {                                                                                                               \
     if (h->umor)                                                                                                     \
-      k_sweep_a_sp<FIRST, FROMB, true><<<GRID, SWEEP_T, 0, STREAM>>>(P, M, ord_s, h->L, h->n0, ST, adapt, DOBC, h->pal_node); \
+      k_sweep_a_sp<FIRST, FROMB, true><<<GRID, SWEEP_T, 0, STREAM>>>(P, M, ord_s, h->L, cnt0, ST, adapt, DOBC, h->pal_node); \
     else                                                                                                             \
-      k_sweep_a_sp<FIRST, FROMB, false><<<GRID, SWEEP_T, 0, STREAM>>>(P, M, ord_s, h->L, h->n0, ST, adapt, DOBC, h->pal_node); \
+      k_sweep_a_sp<FIRST, FROMB, false><<<GRID, SWEEP_T, 0, STREAM>>>(P, M, ord_s, h->L, cnt0, ST, adapt, DOBC, h->pal_node); \
   } while (0)
 #define SPSPH_LAUNCH_A_NODE(FIRST, FROMB, EPSP, GRID, STREAM, ST, DOBC)                                                      \
   do {                                                                                                                      \
     if (h->umor)                                                                                                            \
-      k_sweep_a_node<FIRST, FROMB, EPSP, true><<<GRID, SWEEP_T, 0, STREAM>>>(P, M, ord_n, h->L, h->n0, ST, adapt, DOBC, h->pal_sp); \
+      k_sweep_a_node<FIRST, FROMB, EPSP, true><<<GRID, SWEEP_T, 0, STREAM>>>(P, M, ord_n, h->L, cnt0, ST, adapt, DOBC, h->pal_sp); \
     else                                                                                                                    \
-      k_sweep_a_node<FIRST, FROMB, EPSP, false><<<GRID, SWEEP_T, 0, STREAM>>>(P, M, ord_n, h->L, h->n0, ST, adapt, DOBC, h->pal_sp); \
+      k_sweep_a_node<FIRST, FROMB, EPSP, false><<<GRID, SWEEP_T, 0, STREAM>>>(P, M, ord_n, h->L, cnt0, ST, adapt, DOBC, h->pal_sp); \
   } while (0)
 
 int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
@@ -1278,8 +1283,23 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   const int adapt = P.adapt, bc = p.no_bcs > 0 ? 1 : 0;
   const int *ord_n = S.order[0], *ord_s = S.order[1];
   bool first_a = true;
+  // list lengths the pair-sum kernels walk: the arrays of the neighbour build, or (slab runs) the peeled copy that
+  // serves the current dependent sweep -- ghosts too deep to matter any more have length zero there (k_peel_counts)
+  const int *cnt0 = h->n0, *cnt1 = h->n1;
+  int sweep_no = 0;
+  auto next_sweep = [&]() {
+    ++sweep_no;
+    const int level = h->peel ? std::min(PEEL_LEVELS, (sweep_no - 1) / 3) : 0;
+    cnt0 = level ? h->peel0 + (size_t)(level - 1) * h->peel_stride : h->n0;
+    cnt1 = level ? h->peel1 + (size_t)(level - 1) * h->peel_stride : h->n1;
+  };
+  if (h->peel) {
+    k_peel_counts<<<148 * 4, 256, 0, s>>>(M, S, h->D, h->halo_cells, h->n0, h->n1, h->peel0, h->peel1, h->peel_stride);
+    mark(h, KID_HALO);
+  }
   // SPH_shift block, main:99-109: format B -> the other format-B buffer set
   if (p.sph_shift && itimestep > 1 && ((itimestep - 1) % p.shift_update == 0)) {
+    next_sweep();
     const StatePtrs sw = state_ptrs(h, 1 - h->cur);
     SPSPH_LAUNCH_A_SP(true, true, GSW, s, sw, 0);
     SPSPH_LAUNCH_A_NODE(true, true, true, GNW, s, sw, 0);
@@ -1318,6 +1338,7 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     }
   };
   for (int stg = 0; stg < 4; ++stg) {
+    next_sweep();
     if (std_sph) {
       k_sweep_a_std<<<list_grid(h, P.ntotal, 256), 256, 0, s>>>(P, st, local_list(h, P.ntotal));
     } else {
@@ -1338,32 +1359,34 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
     const int sflags = (last ? 1 : 0) | (stg == 0 ? 2 : 0);  // k_sweep_b_*: last stage / accumulators start from zero
     const double f1n = last ? 0.0 : f1rk[stg + 1];
     const bool artv = (P.alpha > 0 || P.beta > 0);
+    next_sweep();
     fork();
     if (artv) {
       if (h->uniform_h)
-        k_artvisc<true><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, h->n1, st, h->h_uniform);
+        k_artvisc<true><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, cnt1, st, h->h_uniform);
       else
-        k_artvisc<false><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, h->n1, st, 0.f);
+        k_artvisc<false><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, cnt1, st, 0.f);
     }
     if (p.art_stress) {  // main:746
       k_art_force_prep<<<GN, 128, 0, s2>>>(P, M, ord_n, st);
-      k_art_force<<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, h->n1, st, h->art_w2);
+      k_art_force<<<GN, 128, 0, s2>>>(P, M, ord_n, h->L, cnt1, st, h->art_w2);
     }
     const double f2n = last ? 0.0 : f2rk[stg + 1];
     if (cd) {  // the node side reads the stress particles' density before their side integrates it
-      k_sweep_b_node<true><<<GNW, SWEEP_T, 0, s>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], sflags);
-      k_sweep_b_sp<true><<<GSW, SWEEP_T, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], sflags, f2n);
+      k_sweep_b_node<true><<<GNW, SWEEP_T, 0, s>>>(P, M, ord_n, h->L, cnt0, st, f1n, f2rk[stg], sflags);
+      k_sweep_b_sp<true><<<GSW, SWEEP_T, 0, s>>>(P, M, ord_s, h->L, cnt0, st, f1n, f2rk[stg], sflags, f2n);
     } else if (stg == 0) {
-      k_sweep_b_sp<true><<<GSW, SWEEP_T, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], sflags, f2n);
-      k_sweep_b_node<true><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], sflags);
+      k_sweep_b_sp<true><<<GSW, SWEEP_T, 0, s>>>(P, M, ord_s, h->L, cnt0, st, f1n, f2rk[stg], sflags, f2n);
+      k_sweep_b_node<true><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, cnt0, st, f1n, f2rk[stg], sflags);
     } else {
-      k_sweep_b_sp<false><<<GSW, SWEEP_T, 0, s>>>(P, M, ord_s, h->L, h->n0, st, f1n, f2rk[stg], sflags, f2n);
-      k_sweep_b_node<false><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, h->n0, st, f1n, f2rk[stg], sflags);
+      k_sweep_b_sp<false><<<GSW, SWEEP_T, 0, s>>>(P, M, ord_s, h->L, cnt0, st, f1n, f2rk[stg], sflags, f2n);
+      k_sweep_b_node<false><<<GNW, SWEEP_T, 0, s2>>>(P, M, ord_n, h->L, cnt0, st, f1n, f2rk[stg], sflags);
     }
     join();
     mark(h, KID_SWEEPB, artv ? 3 : 2);
   }
   // final stress_point_update + adapt_stress2 + BCs, main:130-135
+  next_sweep();
   if (std_sph) {
     k_sweep_a_std<<<list_grid(h, P.ntotal, 256), 256, 0, s>>>(P, st, local_list(h, P.ntotal));
   } else {
@@ -1380,7 +1403,8 @@ int step_impl(spsph_handle *h, int itimestep, double time_sph, double dt) {
   }
   mark(h, KID_SWEEPA, 2);
   // positions, main:140-182
-  k_move<<<GB, 128, 0, s>>>(P, M, S, h->L, h->n1, st, h->x, h->x00, h->displ);
+  next_sweep();
+  k_move<<<GB, 128, 0, s>>>(P, M, S, h->L, cnt1, st, h->x, h->x00, h->displ);
   mark(h, KID_MOVE);
   if (h->fs_each_step) {
     // get_nodes_on_free_surface, main:152-154: after the position update, before the stress particles are re-seated;
@@ -2339,6 +2363,17 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
         dalloc(h, &h->halo_recv[side], msg))
       return 1;
   CUDA_TRY(cudaMemset(h->halo_cnt, 0, 4 * sizeof(int)));
+  h->halo_cells = halo_cells;
+  {  // halo peeling (k_peel_counts): opt-in with SPSPH_PEEL=1 -- bit-identical (tests/test_dist_emulated_cpu.py, and the
+     // parity check of bench.py --gpus 2 on hardware) but not faster where it could be measured: 1.79 against 1.76 ms per
+     // step on two slabs of a 1 M-particle column (170-cell slabs, 13-cell halos)
+    const char *e = std::getenv("SPSPH_PEEL");
+    h->peel = nranks > 1 && halo_cells > 4 && D.H > 0.0 && e && std::atoi(e) != 0;
+    if (h->peel) {
+      h->peel_stride = (size_t)h->M.nnp + h->M.nsp;
+      if (dalloc(h, &h->peel0, PEEL_LEVELS * h->peel_stride) || dalloc(h, &h->peel1, PEEL_LEVELS * h->peel_stride)) return 1;
+    }
+  }
   h->dist = true;
   k_dist_init_flags<<<((int)n2 + 255) / 256, 256, 0, h->stream>>>(h->P, h->D, h->x, h->lflag);
   if (rebuild_local_list(h)) return 1;

@@ -34,10 +34,11 @@ def emu_dist(tmp_path_factory):
     return so, nccl
 
 
-def _run_ranks(emu_dist, tmp_path, kind, steps, port, extra=(), world=2):
+def _run_ranks(emu_dist, tmp_path, kind, steps, port, extra=(), world=2, peel=False):
     so, nccl = emu_dist
     out = str(tmp_path / "dist")
-    env = dict(os.environ, SPSPH_EMU_SO=so, SPSPH_NCCL_SO=nccl, SPSPH_FAKE_NCCL_DIR=str(tmp_path), OMP_NUM_THREADS="1")
+    env = dict(os.environ, SPSPH_EMU_SO=so, SPSPH_NCCL_SO=nccl, SPSPH_FAKE_NCCL_DIR=str(tmp_path), OMP_NUM_THREADS="1",
+               SPSPH_PEEL="1" if peel else "0")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "dist_worker.py"), "--kind", kind,
            "--steps", str(steps), "--out", out] + list(extra)
@@ -69,7 +70,9 @@ def _assert_owned_equal_oracle(prob, ranks, steps, label, exact=True, min_share=
 @pytest.mark.parametrize("kind,steps,port", [("vs", 30, 29611), ("sl", 12, 29612), ("bui", 300, 29613)])
 def test_two_emulated_slabs_match_oracle(emu_dist, tmp_path, deck_dir, kind, steps, port):
     import spsph
-    ranks = _run_ranks(emu_dist, tmp_path, kind, steps, port)
+    # halo peeling (SPSPH_PEEL=1, k_peel_counts: per-sweep list lengths with the too-deep ghosts zeroed) rides along in
+    # the long Bui run: it must not change a bit of any owned particle
+    ranks = _run_ranks(emu_dist, tmp_path, kind, steps, port, peel=(kind == "bui"))
     _assert_owned_equal_oracle(spsph.load(deck_dir(kind), kind), ranks, steps, f"{kind}, 2 emulated slabs")
 
 
@@ -101,11 +104,12 @@ def test_two_emulated_slabs_replanned(emu_dist, tmp_path, deck_dir):
 
 def test_four_emulated_slabs_interior_ranks(emu_dist, tmp_path):
     """four slabs of a refined Bui column (the BASELINE configs[3] workload at 1/800 of its size): the two interior
-    ranks exchange halos with both neighbours; distributed pair count and owned particles equal the oracle's"""
+    ranks exchange halos with both neighbours, halo peeling on (a third of the ghost list entries skipped in the late
+    sweeps of this geometry); distributed pair count and owned particles equal the oracle's"""
     import spsph
     from spsph import decks
     steps, ncol = 12, 204
-    ranks = _run_ranks(emu_dist, tmp_path, "refined_bui", steps, 29641, extra=["--ncol", str(ncol)], world=4)
+    ranks = _run_ranks(emu_dist, tmp_path, "refined_bui", steps, 29641, extra=["--ncol", str(ncol)], world=4, peel=True)
     d = str(tmp_path / "deck")
     os.makedirs(d)
     decks.write_deck(d, decks.refined_bui_spec(ncol=ncol))
