@@ -42,3 +42,30 @@ def test_emulated_engine_reproduces_reference_binary(emu_engine, case, tmp_path)
         done = step
         compare_with_golden(case, g, step, eng.download(), prob.params, "emulated CUDA engine")
     eng.close()
+
+
+def test_emulated_engine_frame_packing(emu_engine, deck_dir):  # noqa: F811
+    """spsph_download_frame (k_pack_frame; the columns OutputRes prints, mat:2919-3060) on the emulated engine: every
+    packed column equals the array a complete spsph_download returns, and the ParaView rows of the reference
+    executable's own frame (golden `bui`, step 50) come out of it bit for bit. The hardware twin is
+    tests/test_zz_gpu_new_paths.py::test_download_frame_equals_download."""
+    import spsph
+    from spsph.engine import FRAME_COLS
+    g = np.load(golden_path("bui"))
+    prob = spsph.load(deck_dir("bui"), "bui")
+    p, dt = prob.params, prob.blocks[0]["dt"]
+    eng = emu_engine.Engine(prob)
+    eng.run(1, 0.0, dt, 50)
+    cols = ["x", "y", "vx", "vy", "sxx", "syy", "sxy", "szz", "epsp"]
+    nodes = eng.download_frame(cols, 0, p.nnode)
+    sps = eng.download_frame(cols, p.nnode, p.ntotal - p.nnode)
+    for tab, tag in ((nodes, "n50"), (sps, "s50")):
+        ref = np.column_stack([g[f"{tag}_x"], g[f"{tag}_vel"], g[f"{tag}_stress"], g[f"{tag}_strain"]])
+        assert np.array_equal(tab, ref), f"packed frame ({tag}) differs from the reference executable's frame"
+    full = eng.download()
+    everything = eng.download_frame(list(FRAME_COLS))
+    assert np.array_equal(everything[:, FRAME_COLS["rho"]], full["rho"])
+    assert np.array_equal(everything[:p.nnode, FRAME_COLS["disp_10"]], full["disp_10"])
+    assert np.array_equal(everything[:p.ntotal, FRAME_COLS["bc_or_not"]], full["bc_or_not"].astype(np.float64))
+    assert not everything[p.ntotal:, FRAME_COLS["vx"]].any()  # wall particles carry no velocity
+    eng.close()
