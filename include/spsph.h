@@ -127,6 +127,9 @@ int spsph_profile_get(spsph_handle *h, int kid, const char **name, double *total
  * and migrants with the neighbouring slabs over NCCL once per step; spsph_download returns this rank's local
  * view and spsph_dist_flags tells which entries are authoritative (1 owned, 2 ghost, 0 remote/stale).
  * id128: NCCL unique id from spsph_dist_unique_id on rank 0, distributed by the launcher (file, MPI, torch). */
+/* The NCCL library is libnccl.so.2 from the loader's search path unless the environment variable SPSPH_NCCL_SO names
+ * another file. SPSPH_PEEL=1 (read by spsph_dist_init) switches halo peeling on: the pair sums skip the ghost
+ * particles that are too deep in the halo to matter for the remaining sweeps of a step; same results. */
 int spsph_dist_unique_id(char *id128);
 int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *id128, const double *planes,
                     int32_t halo_cells, int32_t halo_capacity);
@@ -154,7 +157,8 @@ int spsph_download_rows(spsph_handle *h, const spsph_state *s, const int32_t *id
  * copied out in a single transfer, instead of a spsph_download of every array. cols: ncols <= SPSPH_FRAME_MAX_COLS
  * column codes in the order the writer prints them. Columns that exist only for velocity particles (DISP10, DISPLX/Y)
  * read 0 for the others; wall particles carry x, y, RHO, HSML only. BC_OR_NOT (2 = node on the free surface, as
- * written to surface_points.csv, mat:3061-3078) runs get_nodes_on_free_surface first, like spsph_download. */
+ * written to surface_points.csv, mat:3061-3078) runs get_nodes_on_free_surface first, like spsph_download. In a
+ * multi-GPU run the rows of particles this rank does not own are stale, as in spsph_download (spsph_dist_flags). */
 enum {
   SPSPH_COL_X = 0, SPSPH_COL_Y, SPSPH_COL_VX, SPSPH_COL_VY, SPSPH_COL_SXX, SPSPH_COL_SYY, SPSPH_COL_SXY,
   SPSPH_COL_SZZ, SPSPH_COL_EPSP, SPSPH_COL_DISP10, SPSPH_COL_RHO, SPSPH_COL_HSML, SPSPH_COL_DISPLX,
