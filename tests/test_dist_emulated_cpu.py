@@ -97,7 +97,7 @@ def test_two_emulated_slabs_replanned(emu_dist, tmp_path, deck_dir):
     """dynamic re-slabbing (spsph_dist_set_planes): the plane swings by 0.3 halo distances every 40 steps, the
     particles that change owner travel with the next halo exchange"""
     import spsph
-    steps = 200
+    steps = 130
     ranks = _run_ranks(emu_dist, tmp_path, "bui", steps, 29631, extra=["--replan", "40"])
     _assert_owned_equal_oracle(spsph.load(deck_dir("bui"), "bui"), ranks, steps, "bui, re-planned slabs", min_share=0.05)
 
