@@ -114,3 +114,18 @@ def test_four_emulated_slabs_interior_ranks(emu_dist, tmp_path):
     os.makedirs(d)
     decks.write_deck(d, decks.refined_bui_spec(ncol=ncol))
     _assert_owned_equal_oracle(spsph.load(d, "bui"), ranks, steps, "refined bui, 4 emulated slabs", min_share=0.1)
+
+
+def test_two_emulated_slabs_gauss_kernel_halo(emu_dist, tmp_path):
+    """Gauss kernel (cut-off 3 h on cells of 2 h): the halo distance follows the cut-off. On the
+    emulated ranks exp() is the oracle's libm, so the comparison is bitwise here (1e-9 on the GPU)"""
+    import spsph
+    from spsph import decks
+    steps = 20
+    ranks = _run_ranks(emu_dist, tmp_path, "vs_gauss", steps, 29651)
+    d = str(tmp_path / "deck")
+    os.makedirs(d)
+    spec = decks.vertical_slope_spec()
+    spec["skf"] = 2
+    decks.write_deck(d, spec)
+    _assert_owned_equal_oracle(spsph.load(d, "vs"), ranks, steps, "vs, Gauss kernel, 2 emulated slabs")
