@@ -129,3 +129,14 @@ def test_two_emulated_slabs_gauss_kernel_halo(emu_dist, tmp_path):
     spec["skf"] = 2
     decks.write_deck(d, spec)
     _assert_owned_equal_oracle(spsph.load(d, "vs"), ranks, steps, "vs, Gauss kernel, 2 emulated slabs")
+
+
+def test_two_emulated_slabs_row_transfers(emu_dist, tmp_path, deck_dir):
+    """rank-local transfers in a slab run (what bench.py's end-to-end leg does at N > 1): after spsph_dist_init every
+    rank uploads only its slab + halo rows (spsph_upload_rows) and fetches only the rows it owns at the end
+    (spsph_download_rows, ownership after migration from spsph_dist_flags); everything else is NaN in what this test
+    merges, so a row that was not transferred cannot pass"""
+    import spsph
+    steps = 60
+    ranks = _run_ranks(emu_dist, tmp_path, "bui", steps, 29661, extra=["--rows"])
+    _assert_owned_equal_oracle(spsph.load(deck_dir("bui"), "bui"), ranks, steps, "bui, row-wise transfers, 2 emulated slabs")

@@ -24,6 +24,9 @@ def main():
     ap.add_argument("--replan", type=int, default=0,
                     help="every N steps: re-slab (spsph_dist_set_planes); the interior planes are pushed back and forth by "
                          "0.3 halo distances and then rebalanced on the owned counts (spsph.dist.rebalance)")
+    ap.add_argument("--rows", action="store_true",
+                    help="rank-local transfers: after dist_init the rank uploads only its slab + halo rows again "
+                         "(spsph_upload_rows) and reads its results back with spsph_download_rows of the rows it owns")
     a = ap.parse_args()
     import torch
     import torch.distributed as td
@@ -59,6 +62,10 @@ def main():
     eng = spsph.Engine(prob, device=local)
     eng.dist_init(rank, world, uid[0], plan)
     dt = prob.blocks[0]["dt"]
+    if a.rows:
+        from spsph.engine import row_arrays
+        ids_local = dist.local_ids(prob, plan, rank)
+        eng.upload_rows(row_arrays(prob.params, prob.arrays, ids_local), ids_local)
     if a.replan > 0:
         planes, t, done, k = np.array(plan["planes"]), 0.0, 0, 0
         while done < a.steps:
@@ -78,6 +85,15 @@ def main():
     ms, launches = eng.last_run()
     arrs = eng.download()
     flags = eng.dist_flags()
+    if a.rows:  # the owned rows, fetched row-wise, replace the complete download in what the parity check reads
+        from spsph.engine import _row_selector
+        keys = ("x", "vel", "stress", "internal_vars", "f_drucker", "displ")
+        owned = np.flatnonzero(flags == 1).astype(np.int32)
+        rows = eng.download_rows(owned, keys=keys)
+        for k in keys:
+            full = np.full_like(arrs[k], np.nan)  # anything that is not an owned row must not be looked at
+            full[_row_selector(prob.params, owned, k)] = rows[k]
+            arrs[k] = full
     os.makedirs(a.out, exist_ok=True)
     np.savez(os.path.join(a.out, f"rank{rank}.npz"), flags=flags, ms=ms, npairs=eng.pair_stats()["npairs"],
              tile_steps=eng.path_counts()[0],
