@@ -201,6 +201,8 @@ struct spsph_handle {
   // NCCL transfers; both ends of a link derive the same size from the same number (the message header)
   int halo_prev_send[2] = {0, 0}, halo_prev_recv[2] = {0, 0};
   bool halo_prev_valid = false;
+  int halo_full_msgs = 0;  // exchanges still to run with full-capacity messages after a change of the slab planes
+  int halo_slack = 4096;   // records a halo message may grow by from one step to the next, on top of 12.5 % (SPSPH_HALO_SLACK)
   double *dist_h = nullptr;               // pinned: [0..1] received header counts, [2..3] halo_cnt + error flags (as int)
   int *halo_ids[2] = {nullptr, nullptr};
   double *halo_send[2] = {nullptr, nullptr}, *halo_recv[2] = {nullptr, nullptr};
@@ -594,7 +596,7 @@ static int rebuild_local_list(spsph_handle *h) {
 // 12.5 % + 4096 records (counts drift by a few particles per step; an overflow raises the error flag).
 static int halo_limit(const spsph_handle *h, int prev_count) {
   if (!h->halo_prev_valid) return h->D.cap;
-  const long long l = (long long)prev_count + prev_count / 8 + 4096;
+  const long long l = (long long)prev_count + prev_count / 8 + h->halo_slack;
   return l < h->D.cap ? (int)l : h->D.cap;
 }
 int halo_exchange(spsph_handle *h) {
@@ -835,7 +837,11 @@ static int dist_status_apply(spsph_handle *h) {
     h->halo_prev_send[side] = hc[side];
     h->halo_prev_recv[side] = (int)h->dist_h[side];
   }
-  h->halo_prev_valid = true;
+  // After spsph_dist_set_planes the counts of two exchanges are no guide for the next one: the first carries the
+  // particles that change slab on top of the halo band, and the rank that gains them sends a band that is short by
+  // the moved strip -- its band of the following step is larger by up to 50 %, beyond the 12.5 % the limit allows.
+  if (h->halo_full_msgs > 0) --h->halo_full_msgs;
+  h->halo_prev_valid = h->halo_full_msgs == 0;
   return 0;
 }
 
@@ -2364,6 +2370,7 @@ int spsph_dist_init(spsph_handle *h, int32_t rank, int32_t nranks, const char *i
       return 1;
   CUDA_TRY(cudaMemset(h->halo_cnt, 0, 4 * sizeof(int)));
   h->halo_cells = halo_cells;
+  if (const char *e = std::getenv("SPSPH_HALO_SLACK")) h->halo_slack = std::max(0, std::atoi(e));
   {  // halo peeling (k_peel_counts): opt-in with SPSPH_PEEL=1 -- bit-identical (tests/test_dist_emulated_cpu.py, and the
      // parity check of bench.py --gpus 2 on hardware) but not faster where it could be measured: 1.79 against 1.76 ms per
      // step on two slabs of a 1 M-particle column (170-cell slabs, 13-cell halos)
@@ -2403,6 +2410,7 @@ int spsph_dist_set_planes(spsph_handle *h, const double *planes) {
   D.lo = lo;
   D.hi = hi;
   h->halo_prev_valid = false;  // the next messages also carry the particles that change slab: full-capacity transfers
+  h->halo_full_msgs = 2;       // ... and the step after that too (see dist_status_apply)
   return 0;
 }
 
