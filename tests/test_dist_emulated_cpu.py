@@ -157,3 +157,16 @@ def test_replanned_slabs_message_limit_regression(emu_dist, tmp_path, monkeypatc
     os.makedirs(d)
     decks.write_deck(d, decks.refined_bui_spec(ncol=ncol))
     _assert_owned_equal_oracle(spsph.load(d, "bui"), ranks, steps, "refined bui, planes moved every 4 steps", min_share=0.1)
+
+
+def test_four_emulated_slabs_wide_slope(emu_dist, tmp_path):
+    """the weak-scaling workload (BASELINE configs[4]: wide vertical slope, one 10 m x 10 m block per rank, elastic, CSPM,
+    boundary conditions with a gravity ramp, inside approach) at 1/550 of its size on four slabs"""
+    import spsph
+    from spsph import decks
+    steps, ncol, world = 15, 60, 4
+    ranks = _run_ranks(emu_dist, tmp_path, "wide_slope", steps, 29681, extra=["--ncol", str(ncol)], world=world)
+    d = str(tmp_path / "deck")
+    os.makedirs(d)
+    decks.write_deck(d, decks.wide_slope_spec(ncol=ncol, nslab=world))
+    _assert_owned_equal_oracle(spsph.load(d, "vs"), ranks, steps, "wide slope, 4 emulated slabs", min_share=0.1)
