@@ -34,11 +34,27 @@ def emu_dist(tmp_path_factory):
     return so, nccl
 
 
-def _run_ranks(emu_dist, tmp_path, kind, steps, port, extra=(), world=2, peel=False):
+@pytest.fixture(scope="module")
+def emu_dist_simt(emu_dist, tmp_path_factory):
+    """the same with the lockstep (SIMT) emulation: warp collectives and block barriers have their real meaning, which
+    the cell-tile kernels need (tests/test_step_emulation_cpu.py)"""
+    d = tmp_path_factory.mktemp("emu_dist_simt")
+    cpp, so = str(d / "engine_host.cpp"), str(d / "libspsph_emu_simt.so")
+    subprocess.run([sys.executable, os.path.join(NATIVE, "make_engine_host.py"),
+                    os.path.join(ROOT, "stress-particle-sph_b200", "csrc", "spsph_engine.cu"), cpp], check=True,
+                   stdout=subprocess.DEVNULL)
+    subprocess.run(["g++", "-O1", "-ffp-contract=off", "-fno-fast-math", "-std=c++17", "-fPIC", "-shared", "-w",
+                    "-DSPSPH_EMU_SIMT", "-D__noinline__=", "-fno-gnu-unique", "-I/usr/local/cuda/include", "-I" + NATIVE,
+                    "-I" + os.path.join(ROOT, "stress-particle-sph_b200", "csrc"), "-I" + os.path.join(ROOT, "include"),
+                    "-o", so, cpp, "-ldl"], check=True)
+    return so, emu_dist[1]
+
+
+def _run_ranks(emu_dist, tmp_path, kind, steps, port, extra=(), world=2, peel=False, env_extra=None):
     so, nccl = emu_dist
     out = str(tmp_path / "dist")
     env = dict(os.environ, SPSPH_EMU_SO=so, SPSPH_NCCL_SO=nccl, SPSPH_FAKE_NCCL_DIR=str(tmp_path), OMP_NUM_THREADS="1",
-               SPSPH_PEEL="1" if peel else "0")
+               SPSPH_PEEL="1" if peel else "0", **(env_extra or {}))
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr",
            "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "tools", "dist_worker.py"), "--kind", kind,
            "--steps", str(steps), "--out", out] + list(extra)
@@ -170,3 +186,14 @@ def test_four_emulated_slabs_wide_slope(emu_dist, tmp_path):
     os.makedirs(d)
     decks.write_deck(d, decks.wide_slope_spec(ncol=ncol, nslab=world))
     _assert_owned_equal_oracle(spsph.load(d, "vs"), ranks, steps, "wide slope, 4 emulated slabs", min_share=0.1)
+
+
+def test_two_emulated_slabs_tile_path(emu_dist_simt, tmp_path, deck_dir):
+    """the cell-tile path (SPSPH_TILE=1: one-pass build with entry codes, shared-memory partner tiles) on two slabs of
+    the SIMT emulation: the ranks agree on the path through the all-reduced pair count and overflow flags, every step
+    runs on the tile kernels, owned particles equal the oracle bit for bit"""
+    import spsph
+    steps = 6
+    ranks = _run_ranks(emu_dist_simt, tmp_path, "bui", steps, 29691, env_extra={"SPSPH_TILE": "1"})
+    assert all(int(r["tile_steps"]) == steps for r in ranks), [int(r["tile_steps"]) for r in ranks]
+    _assert_owned_equal_oracle(spsph.load(deck_dir("bui"), "bui"), ranks, steps, "bui, tile path, 2 SIMT-emulated slabs")
