@@ -124,7 +124,7 @@ def test_four_emulated_slabs_interior_ranks(emu_dist, tmp_path):
     sweeps of this geometry); distributed pair count and owned particles equal the oracle's"""
     import spsph
     from spsph import decks
-    steps, ncol = 12, 204
+    steps, ncol = 8, 204
     ranks = _run_ranks(emu_dist, tmp_path, "refined_bui", steps, 29641, extra=["--ncol", str(ncol)], world=4, peel=True)
     d = str(tmp_path / "deck")
     os.makedirs(d)
@@ -167,7 +167,7 @@ def test_replanned_slabs_message_limit_regression(emu_dist, tmp_path, monkeypatc
     import spsph
     from spsph import decks
     monkeypatch.setenv("SPSPH_HALO_SLACK", "0")
-    steps, ncol = 14, 204
+    steps, ncol = 8, 204
     ranks = _run_ranks(emu_dist, tmp_path, "refined_bui", steps, 29671, extra=["--ncol", str(ncol), "--replan", "4"])
     d = str(tmp_path / "deck")
     os.makedirs(d)
