@@ -4,7 +4,7 @@ stand-in like tests/test_dist_emulated_cpu.py, runs tools/dist_worker.py under t
 merged owned particles and the all-reduced pair count with the single-domain oracle, bit for bit.
 
 usage: python tools/emulated_slab_cases.py case:steps:ranks [case:steps:ranks ...]
-  e.g. python tools/emulated_slab_cases.py bui_standard:30:2 bui_inside_sp1_long:1501:2 bui_out_domain:202:2
+  e.g. python tools/emulated_slab_cases.py bui_standard:30:2 bui_inside_sp1_long:1501:2 refined_bui@408:6:8
 (round 2: all of bui_standard, bui_inside_sp1/3, bui_shift5, bui_quintic, bui_art_stress, sl_tresca, vs_standard,
 bui_plane_stress, bui_sml15, bui_out_domain pass on two ranks)"""
 import os
@@ -47,15 +47,20 @@ def main(argv):
         case, steps, world = arg.split(":")
         steps, world, port = int(steps), int(world), port + 1
         out = tempfile.mkdtemp(dir=work)
+        if case.startswith("refined_bui@"):  # the bench workload at a reduced size: refined_bui@<columns>
+            ncol = int(case.split("@")[1])
+            kind_args = ["--kind", "refined_bui", "--ncol", str(ncol)]
+        else:
+            kind_args = ["--kind", "case:" + case]
         r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
                             "--master-addr", "127.0.0.1", "--master-port", str(port),
-                            os.path.join(ROOT, "tools", "dist_worker.py"), "--kind", "case:" + case, "--steps", str(steps),
+                            os.path.join(ROOT, "tools", "dist_worker.py")] + kind_args + ["--steps", str(steps),
                             "--out", out], capture_output=True, text=True, env=env)
         if r.returncode:
             print(case, "RUN FAILED:", [ln for ln in r.stderr.splitlines() if "Error" in ln][:3], flush=True)
             failed += 1
             continue
-        variant, spec = spec_of(case)
+        variant, spec = ("bui", decks.refined_bui_spec(ncol=ncol)) if case.startswith("refined_bui@") else spec_of(case)
         d = tempfile.mkdtemp(dir=work)
         decks.write_deck(d, spec)
         prob = spsph.load(d, variant)
