@@ -6,7 +6,8 @@ merged owned particles and the all-reduced pair count with the single-domain ora
 usage: python tools/emulated_slab_cases.py case:steps:ranks [case:steps:ranks ...]
   e.g. python tools/emulated_slab_cases.py bui_standard:30:2 bui_inside_sp1_long:1501:2 refined_bui@408:6:8
 (round 2: all of bui_standard, bui_inside_sp1/3, bui_shift5, bui_quintic, bui_art_stress, sl_tresca, vs_standard,
-bui_plane_stress, bui_sml15, bui_out_domain pass on two ranks)"""
+bui_plane_stress, bui_sml15, bui_out_domain pass on two ranks; refined_bui@204:1200:4 -- 21 list-growth steps on four
+ranks -- and refined_bui@408:6:8 pass as well)"""
 import os
 import subprocess
 import sys
